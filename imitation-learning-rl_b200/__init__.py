@@ -1,0 +1,9 @@
+"""imitation-learning-rl_b200 — B200-native batched humanoid imitation env (one hot path of
+AdityaPutraS/Imitation-Learning-RL): env step / reset + imitation reward + observation as sm_100a CUDA kernels behind
+the C ABI of include/ilrl.h.  Import name: `ilrl_b200` (see ilrl_b200.py at the repo root; the directory name has a
+hyphen).  The CUDA library is required; nothing here falls back to a CPU implementation."""
+from . import _build, _lib  # noqa: F401
+from .batched_env import BatchedHumanoidEnv  # noqa: F401
+from .clips import CLIP_NAMES, load_clip  # noqa: F401
+
+__all__ = ["BatchedHumanoidEnv", "CLIP_NAMES", "load_clip"]

@@ -1,0 +1,29 @@
+"""Builds libilrl_b200.so in-tree with nvcc for sm_100a (the only target; there is no CPU build of the product)."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libilrl_b200.so")
+SRC = os.path.join(HERE, "csrc", "ilrl_capi.cu")
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("ilrl_env.cuh", "ilrl_physics.cuh", "ilrl_constants.h",
+                                                        "ilrl_model_data.h")] + [
+    os.path.join(os.path.dirname(HERE), "include", "ilrl.h")]
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
+              "-shared"]
+
+
+def stale():
+    return (not os.path.exists(SO)) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS)
+
+
+def build(force=False, verbose=False):
+    if not force and not stale():
+        return SO
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
+    subprocess.check_call(cmd)
+    return SO
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

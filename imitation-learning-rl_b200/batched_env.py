@@ -1,0 +1,183 @@
+"""BatchedHumanoidEnv — N humanoid imitation envs on one B200 behind the C ABI (include/ilrl.h).
+
+Host-side plumbing only: torch owns the device buffers and the stream, every computation happens in
+libilrl_b200.so's CUDA kernels.  There is no CPU path: constructing this class without a CUDA device raises.
+The single-env, reference-shaped views (`LowLevelHumanoidEnv`, `HierarchicalHumanoidEnv`) and the RLlib-shaped
+adapters are thin wrappers around this class.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .clips import CLIP_NAMES, load_clip
+
+OBS_LOW, OBS_HIGH, ACT_LOW, ACT_HIGH = 70, 44, 17, 2
+PHYS_WORDS, ENV_WORDS, TERM_WORDS, STATS_WORDS = 47, 28, 12, 16
+INT32_MIN = -2 ** 31
+TERM_NAMES = ["deltaJoints", "deltaVelJoints", "delta_lowTargetScore", "electricityScore", "jointLimitScore",
+              "aliveReward", "bodyPostureScore", "lowTargetScore", "deltaEndPoints", "highTargetScore", "driftScore",
+              "delta_highTargetScore"]
+# envf word indices (csrc/ilrl_constants.h)
+(E_FRAME, E_CLIP, E_T, E_TARGET_X, E_TARGET_Y, E_START_X, E_START_Y, E_SEP_X, E_SEP_Y, E_SEP_Z, E_ROBOT_X, E_ROBOT_Y,
+ E_HLDEG, E_WALK_X, E_WALK_Y, E_LOW_TARGET_SCORE, E_JOINT_SCORE, E_JVEL_SCORE, E_POSTURE_SCORE, E_OBS_SIN, E_OBS_COS,
+ E_STEPS_REMAINING, E_CUM_DRIFT, E_HIGH_TARGET_SCORE, E_CUM_ALIVE, E_HIGH_PENDING, E_EP_RETURN,
+ E_EP_LEN) = range(28)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class BatchedHumanoidEnv:
+    """mode "low": LowLevelHumanoidEnv semantics (REF low_level_env.py); "hier": HierarchicalHumanoidEnv
+    (REF hier_env.py).  clips: list of clip names staged in HBM; clip_of_env: per-env index into that list."""
+
+    def __init__(self, num_envs, mode="low", clips=("motion09_03",), clip_of_env=None, device=0, seed=0,
+                 auto_reset=True, max_timestep=3000, step_per_level=5):
+        if not torch.cuda.is_available():
+            raise _lib.IlrlError("BatchedHumanoidEnv needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.L = _lib.lib()
+        self.num_envs = int(num_envs)
+        self.mode = {"low": 0, "hier": 1}[mode]
+        self.device = torch.device("cuda", device)
+        self.clip_names = list(clips)
+        cfg = _lib.Config(device=device, num_envs=self.num_envs, mode=self.mode, auto_reset=int(bool(auto_reset)),
+                          seed=seed, skip_frame=2, max_timestep=max_timestep, step_per_level=step_per_level, reserved=0)
+        h = C.c_void_p()
+        rc = self.L.ilrl_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise _lib.IlrlError("ilrl_create failed (%d): %s" % (rc, self.L.ilrl_last_error(None).decode()))
+        self.h = h
+        self.max_frame = []
+        for ci, name in enumerate(self.clip_names):
+            c = load_clip(name)
+            self._ck(self.L.ilrl_load_clip(self.h, ci, c["pos"].ctypes.data, len(c["pos"]), c["rel"].ctypes.data,
+                                           len(c["rel"]), c["vel"].ctypes.data, len(c["vel"]), c["ep"].ctypes.data,
+                                           len(c["ep"]), c["max_frame"]))
+            self.max_frame.append(c["max_frame"])
+        ids = None
+        if clip_of_env is not None:
+            ids = np.ascontiguousarray(clip_of_env, dtype=np.int32)
+            assert ids.shape == (self.num_envs,)
+        self._ck(self.L.ilrl_set_clip_ids(self.h, None if ids is None else ids.ctypes.data))
+        n, dev = self.num_envs, self.device
+        self.obs = torch.zeros(n, OBS_LOW, device=dev)
+        self.reward = torch.zeros(n, device=dev)
+        self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self.terms = torch.zeros(n, TERM_WORDS, device=dev)
+        if self.mode == 1:
+            self.high_obs = torch.zeros(n, OBS_HIGH, device=dev)
+            self.high_reward = torch.zeros(n, device=dev)
+            self.high_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+        self._forced = None
+
+    # ------------------------------------------------------------------ plumbing
+    def _ck(self, rc):
+        if rc != 0:
+            raise _lib.IlrlError("ilrl call failed (%d): %s" % (rc, self.L.ilrl_last_error(self.h).decode()))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def close(self):
+        if getattr(self, "h", None) is not None:
+            self.L.ilrl_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _f32(self, x, shape):
+        t = torch.as_tensor(x, dtype=torch.float32, device=self.device).contiguous()
+        assert tuple(t.shape) == tuple(shape), (tuple(t.shape), shape)
+        return t
+
+    # ------------------------------------------------------------------ env API (device tensors)
+    def reset(self, mask=None, start_frame=None, target_deg=None, reset_yaw_deg=None):
+        """reset() / resetFromFrame() of the masked envs (all if mask is None).  Returns the obs tensor
+        ([N,70] low-level obs in "low" mode, [N,44] high-level obs in "hier" mode); unmasked rows keep old values."""
+        n = self.num_envs
+        m = None if mask is None else torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        sf = None if start_frame is None else torch.as_tensor(start_frame, device=self.device).to(torch.int32).contiguous()
+        td = None if target_deg is None else torch.as_tensor(target_deg, device=self.device).to(torch.int32).contiguous()
+        yw = None if reset_yaw_deg is None else self._f32(reset_yaw_deg, (n,))
+        out = self.high_obs if self.mode == 1 else self.obs
+        self._ck(self.L.ilrl_reset(self.h, _ptr(m), _ptr(sf), _ptr(td), _ptr(yw), _ptr(out), self._stream()))
+        if self.mode == 1:
+            self._ck(self.L.ilrl_high_readout(self.h, None, None, _ptr(self.high_flags), self._stream()))
+        return out
+
+    def step(self, action, physics=True):
+        """One low-level step of every env.  action [N,17] (device tensor).  -> (obs [N,70], reward [N], done [N] u8,
+        terms [N,12]) — views of buffers owned by this object, overwritten by the next call."""
+        a = self._f32(action, (self.num_envs, ACT_LOW))
+        fn = self.L.ilrl_step if physics else self.L.ilrl_step_no_physics
+        self._ck(fn(self.h, _ptr(a), _ptr(self.obs), _ptr(self.reward), _ptr(self.done), _ptr(self.terms), self._stream()))
+        return self.obs, self.reward, self.done, self.terms
+
+    def step_host(self, action_np, obs_np, reward_np, done_np, terms_np=None):
+        """Same step through host (numpy) buffers: H2D of the actions, kernel, D2H of obs/reward/done, synchronous."""
+        assert action_np.dtype == np.float32 and action_np.flags.c_contiguous
+        self._ck(self.L.ilrl_step_host(self.h, action_np.ctypes.data, obs_np.ctypes.data, reward_np.ctypes.data,
+                                       done_np.ctypes.data, None if terms_np is None else terms_np.ctypes.data,
+                                       self._stream()))
+
+    def high_step(self, action2):
+        """hier mode: heading action [N,2] for the envs waiting for one; returns the low-level obs tensor [N,70]
+        (rows of envs that were not waiting are untouched)."""
+        a = self._f32(action2, (self.num_envs, ACT_HIGH))
+        self._ck(self.L.ilrl_high_step(self.h, _ptr(a), _ptr(self.obs), self._stream()))
+        return self.obs
+
+    def high_readout(self):
+        """hier mode: (high_obs [N,44], high_reward [N], flags [N] u8: bit0 episode ended, bit1 high agent present,
+        bit2 waiting for a high-level action)."""
+        self._ck(self.L.ilrl_high_readout(self.h, _ptr(self.high_obs), _ptr(self.high_reward), _ptr(self.high_flags),
+                                          self._stream()))
+        return self.high_obs, self.high_reward, self.high_flags
+
+    # ------------------------------------------------------------------ parity-harness / introspection entry points
+    def get_state(self):
+        phys = torch.empty(self.num_envs, PHYS_WORDS, device=self.device)
+        envf = torch.empty(self.num_envs, ENV_WORDS, device=self.device)
+        self._ck(self.L.ilrl_get_state(self.h, _ptr(phys), _ptr(envf), self._stream()))
+        return phys, envf
+
+    def set_state(self, phys=None, envf=None):
+        p = None if phys is None else self._f32(phys, (self.num_envs, PHYS_WORDS))
+        e = None if envf is None else self._f32(envf, (self.num_envs, ENV_WORDS))
+        self._ck(self.L.ilrl_set_state(self.h, _ptr(p), _ptr(e), self._stream()))
+
+    def set_forced_target_deg(self, deg):
+        """Per-env heading (int degrees) used by the next target re-sampling instead of the env's own draw;
+        INT32_MIN entries (or deg=None) = draw normally."""
+        if deg is None:
+            self._forced = None
+            self._ck(self.L.ilrl_set_forced_target_deg(self.h, None))
+        else:
+            self._forced = torch.as_tensor(deg, device=self.device).to(torch.int32).contiguous()
+            self._ck(self.L.ilrl_set_forced_target_deg(self.h, _ptr(self._forced)))
+
+    def physics_only(self, torque):
+        t = self._f32(torque, (self.num_envs, ACT_LOW))
+        self._ck(self.L.ilrl_physics_only(self.h, _ptr(t), self._stream()))
+
+    def endpoint_score(self):
+        out = torch.empty(self.num_envs, device=self.device)
+        self._ck(self.L.ilrl_endpoint_score(self.h, _ptr(out), self._stream()))
+        return out
+
+    def stats(self):
+        """Device tensor [16]: {episodes, sum return, sum length, steps, sum reward, sums of the first 11 terms}
+        accumulated since the previous call.  All-reduce it across ranks with torch.distributed (NCCL) if needed."""
+        out = torch.empty(STATS_WORDS, device=self.device)
+        self._ck(self.L.ilrl_stats(self.h, _ptr(out), self._stream()))
+        return out
+
+    def launch_count(self):
+        return int(self.L.ilrl_launch_count(self.h))

@@ -1,0 +1,744 @@
+// ilrl_capi.cu — kernels + the C ABI declared in include/ilrl.h (libilrl_b200.so, sm_100a only, no CPU path).
+//
+// Data layout in HBM (per handle, N envs):
+//   phys  [47][N] fp32  structure-of-arrays: word-major, env-minor -> every load/store of a warp is one coalesced
+//   envf  [28][N] fp32  128-byte line per word.  Persistent state = 75 words + 1 rng counter = 304 B / env.
+//   rng   [N]     u32   Philox draw counter
+//   clips: the 4 tables of every loaded motion clip, row-major fp32, read through the read-only path (L2-resident,
+//          ~200 KB for all four clips).
+// I/O with the caller (row-major [N,17] actions, [N,70] observations) is staged through shared memory so that global
+// accesses are coalesced although every thread produces/consumes a whole row.
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/ilrl.h"
+#include "ilrl_env.cuh"
+
+namespace ilrl {
+
+constexpr int BLOCK = 64;  // envs (= threads) per CTA
+
+struct StepArgs {
+  int n;
+  int skip_physics;
+  int auto_reset;
+  int max_timestep;
+  float step_per_level;
+  uint64_t seed;
+  float* phys;         // [47][n]
+  float* envf;         // [28][n]
+  uint32_t* rng;       // [n]
+  const float* action; // [n,17]
+  float* obs;          // [n,70]
+  float* reward;       // [n]
+  uint8_t* done;       // [n]
+  float* terms;        // [n,12] or null
+  float* high_obs;     // [n,44]   (hier)
+  float* high_reward;  // [n]
+  uint8_t* high_flags; // [n]
+  const int32_t* forced_deg;  // [n] or null
+  float* stats;        // [16] or null
+  Row* rows;           // [n][MAXROWS] scratch in global memory (per-thread constraint rows)
+  ClipDesc clips[MAX_CLIPS];
+};
+
+__device__ __forceinline__ void load_state(const StepArgs& a, int i, Phys& s, EnvW& w) {
+  const float* p = a.phys + i;
+  const int n = a.n;
+#pragma unroll
+  for (int k = 0; k < 3; k++) s.p[k] = p[(0 + k) * n];
+#pragma unroll
+  for (int k = 0; k < 4; k++) s.quat[k] = p[(3 + k) * n];
+#pragma unroll
+  for (int k = 0; k < 3; k++) s.v[k] = p[(7 + k) * n];
+#pragma unroll
+  for (int k = 0; k < 3; k++) s.w[k] = p[(10 + k) * n];
+#pragma unroll
+  for (int k = 0; k < NJ; k++) { s.q[k] = p[(13 + k) * n]; s.qd[k] = p[(30 + k) * n]; }
+  const float* e = a.envf + i;
+#pragma unroll
+  for (int k = 0; k < ILRL_ENV_WORDS; k++) w.e[k] = e[k * n];
+}
+__device__ __forceinline__ void store_state(const StepArgs& a, int i, const Phys& s, const EnvW& w) {
+  float* p = a.phys + i;
+  const int n = a.n;
+#pragma unroll
+  for (int k = 0; k < 3; k++) p[(0 + k) * n] = s.p[k];
+#pragma unroll
+  for (int k = 0; k < 4; k++) p[(3 + k) * n] = s.quat[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) p[(7 + k) * n] = s.v[k];
+#pragma unroll
+  for (int k = 0; k < 3; k++) p[(10 + k) * n] = s.w[k];
+#pragma unroll
+  for (int k = 0; k < NJ; k++) { p[(13 + k) * n] = s.q[k]; p[(30 + k) * n] = s.qd[k]; }
+  float* e = a.envf + i;
+#pragma unroll
+  for (int k = 0; k < ILRL_ENV_WORDS; k++) e[k * n] = w.e[k];
+}
+
+// stage a [rows_in_block, W] row-major tile between global memory and per-thread rows through shared memory
+template <int W>
+__device__ __forceinline__ void tile_load(const float* g, int base, int n, float* sm, float* mine) {
+  const int cnt = min(BLOCK, n - base) * W;
+  for (int t = threadIdx.x; t < cnt; t += BLOCK) sm[t] = g[(size_t)base * W + t];
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < W; k++) mine[k] = sm[threadIdx.x * W + k];  // W odd (17) -> conflict-free
+  __syncthreads();
+}
+template <int W>
+__device__ __forceinline__ void tile_store(float* g, int base, int n, float* sm, const float* mine, bool valid) {
+  __syncthreads();
+  if (valid) {
+#pragma unroll
+    for (int k = 0; k < W; k++) sm[threadIdx.x * (W + 1) + k] = mine[k];  // pad to an odd stride
+  }
+  __syncthreads();
+  const int cnt = min(BLOCK, n - base) * W;
+  for (int t = threadIdx.x; t < cnt; t += BLOCK) {
+    int r = t / W, c = t - r * W;
+    g[(size_t)base * W + t] = sm[r * (W + 1) + c];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K1: fused step
+// MODE 0 = LowLevelHumanoidEnv.step (REF low_level_env.py:475-526), MODE 1 = HierarchicalHumanoidEnv low_level_step
+// (REF hier_env.py:355-366, 583-642).  One thread = one env.
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs a) {
+  __shared__ float sm[BLOCK * 71];
+  const int base = blockIdx.x * BLOCK;
+  const int i = base + threadIdx.x;
+  const bool valid = i < a.n;
+  float act[NJ];
+  tile_load<NJ>(a.action, base, a.n, sm, act);
+  float obs[70];
+  bool write_obs = false;
+  float st_ep = 0.f, st_ret = 0.f, st_len = 0.f, st_steps = 0.f, st_rew = 0.f, st_terms[11];
+#pragma unroll
+  for (int t = 0; t < 11; t++) st_terms[t] = 0.f;
+
+  if (valid) {
+    Phys s;
+    EnvW w;
+    load_state(a, i, s, w);
+    const bool pending = MODE == 1 && w.e[ILRL_E_HIGH_PENDING] != 0.f;
+    if (pending) {
+      a.reward[i] = 0.f; a.done[i] = 0;
+      if (a.terms) for (int t = 0; t < ILRL_TERM_WORDS; t++) a.terms[(size_t)i * ILRL_TERM_WORDS + t] = 0.f;
+    } else {
+      const ClipDesc cl = a.clips[(int)w.e[ILRL_E_CLIP]];
+      Work k;
+      Calc c;
+      float terms[ILRL_TERM_WORDS];
+#pragma unroll
+      for (int t = 0; t < ILRL_TERM_WORDS; t++) terms[t] = 0.f;
+      // apply_action (REF humanoid.py:54-60): clip, gear x power, motor slot -> joint slot
+      float tau[NJ];
+#pragma unroll
+      for (int m = 0; m < NJ; m++) tau[kMotorJoint[m]] = kMotorGear[m] * fminf(fmaxf(act[m], -1.f), 1.f);
+      if (MODE == 1) {
+        // (Q13) robot_pos is refreshed from the PREVIOUS calc_state at the top of step()
+        fk(s, k);
+        w.e[ILRL_E_ROBOT_X] = (32.f * s.p[0] + k.sumx) * (1.f / 33.f);
+        w.e[ILRL_E_ROBOT_Y] = (32.f * s.p[1] + k.sumy) * (1.f / 33.f);
+        w.e[ILRL_E_STEPS_REMAINING] -= 1.f;
+      }
+      if (!a.skip_physics) {
+        Row* rows = a.rows + (size_t)i * MAXROWS;
+#pragma unroll 1
+        for (int sub = 0; sub < ILRL_SUBSTEPS; sub++) substep(s, tau, k, rows, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+      }
+      fk(s, k);
+      calc_state(s, k.sumx, k.sumy, w.e[ILRL_E_WALK_X], w.e[ILRL_E_WALK_Y], c);
+      w.e[ILRL_E_OBS_SIN] = c.obs[1]; w.e[ILRL_E_OBS_COS] = c.obs[2];
+      if (MODE == 0) { w.e[ILRL_E_ROBOT_X] = c.bx; w.e[ILRL_E_ROBOT_Y] = c.by; }
+      float reward = update_reward<MODE>(s, c, w, cl, act, terms);
+      inc_frame(w, cl, 2);
+      uint32_t ctr = a.rng[i];
+      int deg;
+      if (a.forced_deg && a.forced_deg[i] != INT_MIN) deg = a.forced_deg[i];
+      else {
+        // drawn unconditionally-looking but consumed only on a switch: peek without advancing unless used
+        uint32_t c2 = ctr;
+        deg = rand_int(a.seed, (uint32_t)i, c2, -180, 180);
+        float dist = hyp(w.e[ILRL_E_ROBOT_X] - w.e[ILRL_E_TARGET_X], w.e[ILRL_E_ROBOT_Y] - w.e[ILRL_E_TARGET_Y]);
+        if (dist <= (float)ILRL_TARGET_REACHED) ctr = c2;
+      }
+      check_target<MODE>(c, w, deg);
+      terms[ILRL_T_LOWTARGET] = w.e[ILRL_E_LOW_TARGET_SCORE];
+      bool done = check_done<MODE>(w, terms[ILRL_T_ALIVE]);
+      w.e[ILRL_E_T] += 1.f;
+      if (w.e[ILRL_E_T] >= (float)a.max_timestep) done = true;
+      w.e[ILRL_E_EP_RETURN] += reward;
+      w.e[ILRL_E_EP_LEN] += 1.f;
+      write_low_obs(c.obs, w, cl, obs);
+      write_obs = true;
+      uint8_t hflags = 0;
+      if (MODE == 1) {
+        if (done || w.e[ILRL_E_STEPS_REMAINING] <= 0.f) {
+          update_reward_high(w, terms, a.step_per_level);
+          a.high_reward[i] = terms[ILRL_T_DHIGHTARGET] * 0.3f + terms[ILRL_T_DRIFT] * 0.7f;
+          float ho[44];
+          write_high_obs(c, w, ho);
+          for (int t = 0; t < 44; t++) a.high_obs[(size_t)i * 44 + t] = ho[t];
+          w.e[ILRL_E_CUM_ALIVE] = 0.f;
+          hflags = done ? 3 : 2;
+          if (!done) { w.e[ILRL_E_HIGH_PENDING] = 1.f; hflags |= 4; }
+        }
+        terms[ILRL_T_HIGHTARGET] = w.e[ILRL_E_HIGH_TARGET_SCORE];
+      }
+      a.reward[i] = reward;
+      a.done[i] = done ? 1 : 0;
+      if (a.terms) for (int t = 0; t < ILRL_TERM_WORDS; t++) a.terms[(size_t)i * ILRL_TERM_WORDS + t] = terms[t];
+      st_steps = 1.f; st_rew = reward;
+#pragma unroll
+      for (int t = 0; t < 11; t++) st_terms[t] = terms[t];
+      if (done) {
+        st_ep = 1.f; st_ret = w.e[ILRL_E_EP_RETURN]; st_len = w.e[ILRL_E_EP_LEN];
+        if (a.auto_reset) {
+          int sf = rand_int(a.seed, (uint32_t)i, ctr, 0, cl.max_frame - 5);
+          float yaw = MODE == 1 ? (float)rand_int(a.seed, (uint32_t)i, ctr, -180, 180) : 0.f;
+          int tdeg = rand_int(a.seed, (uint32_t)i, ctr, -180, 180);
+          reset_env<MODE>(s, w, cl, sf, yaw, tdeg, a.step_per_level, k, c);
+          if (MODE == 0) write_low_obs(c.obs, w, cl, obs);
+          else {
+            float ho[44];
+            write_high_obs(c, w, ho);
+            for (int t = 0; t < 44; t++) a.high_obs[(size_t)i * 44 + t] = ho[t];
+            hflags |= 4;
+          }
+        }
+      }
+      if (MODE == 1) a.high_flags[i] = hflags;
+      a.rng[i] = ctr;
+      store_state(a, i, s, w);
+    }
+  }
+  // observations: only envs that stepped write their row (pending hier envs keep theirs)
+  {
+    __syncthreads();
+    if (write_obs) {
+#pragma unroll
+      for (int t = 0; t < 70; t++) sm[threadIdx.x * 71 + t] = obs[t];
+    }
+    unsigned long long okmask = __ballot_sync(0xffffffffu, write_obs);
+    __shared__ unsigned int wrote[BLOCK / 32];
+    if ((threadIdx.x & 31) == 0) wrote[threadIdx.x >> 5] = (unsigned int)okmask;
+    __syncthreads();
+    const int cnt = min(BLOCK, a.n - base) * 70;
+    for (int t = threadIdx.x; t < cnt; t += BLOCK) {
+      int r = t / 70, cc = t - r * 70;
+      if ((wrote[r >> 5] >> (r & 31)) & 1u) a.obs[(size_t)base * 70 + t] = sm[r * 71 + cc];
+    }
+  }
+  // K5: episode / reward statistics -> one atomicAdd per warp per slot
+  if (a.stats) {
+    float v[16] = {st_ep, st_ret, st_len, st_steps, st_rew};
+#pragma unroll
+    for (int t = 0; t < 11; t++) v[5 + t] = st_terms[t];
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+      float x = v[t];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) == 0 && x != 0.f) atomicAdd(a.stats + t, x);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K2: reset
+struct ResetArgs {
+  int n;
+  float step_per_level;
+  uint64_t seed;
+  float* phys; float* envf; uint32_t* rng;
+  const uint8_t* mask; const int32_t* start_frame; const int32_t* target_deg; const float* yaw_deg;
+  float* obs;
+  uint8_t* high_flags;
+  ClipDesc clips[MAX_CLIPS];
+};
+struct StateView { int n; float* phys; float* envf; uint32_t* rng; };
+
+template <int MODE>
+__global__ void __launch_bounds__(BLOCK) reset_kernel(const ResetArgs a) {
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= a.n) return;
+  if (a.mask && !a.mask[i]) return;
+  StepArgs v; v.n = a.n; v.phys = a.phys; v.envf = a.envf;
+  Phys s; EnvW w;
+  load_state(v, i, s, w);
+  const ClipDesc cl = a.clips[(int)w.e[ILRL_E_CLIP]];
+  uint32_t ctr = a.rng[i];
+  int sf = a.start_frame ? a.start_frame[i] : rand_int(a.seed, (uint32_t)i, ctr, 0, cl.max_frame - 5);
+  float yaw = a.yaw_deg ? a.yaw_deg[i] : (MODE == 1 ? (float)rand_int(a.seed, (uint32_t)i, ctr, -180, 180) : 0.f);
+  int tdeg = a.target_deg ? a.target_deg[i] : rand_int(a.seed, (uint32_t)i, ctr, -180, 180);
+  Work k; Calc c;
+  reset_env<MODE>(s, w, cl, sf, yaw, tdeg, a.step_per_level, k, c);
+  a.rng[i] = ctr;
+  store_state(v, i, s, w);
+  if (a.obs) {
+    if (MODE == 0) {
+      float o[70];
+      write_low_obs(c.obs, w, cl, o);
+      for (int t = 0; t < 70; t++) a.obs[(size_t)i * 70 + t] = o[t];
+    } else {
+      float o[44];
+      write_high_obs(c, w, o);
+      for (int t = 0; t < 44; t++) a.obs[(size_t)i * 44 + t] = o[t];
+    }
+  }
+  if (MODE == 1 && a.high_flags) a.high_flags[i] = 4;
+}
+
+// ------------------------------------------------------------------------------------------------ K4: high-level step
+struct HighArgs {
+  int n; float step_per_level;
+  float* phys; float* envf;
+  const float* action2; float* low_obs;
+  ClipDesc clips[MAX_CLIPS];
+};
+__global__ void __launch_bounds__(BLOCK) high_step_kernel(const HighArgs a) {
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= a.n) return;
+  StepArgs v; v.n = a.n; v.phys = a.phys; v.envf = a.envf;
+  Phys s; EnvW w;
+  load_state(v, i, s, w);
+  if (w.e[ILRL_E_HIGH_PENDING] == 0.f) return;
+  const ClipDesc cl = a.clips[(int)w.e[ILRL_E_CLIP]];
+  Work k; Calc c;
+  fk(s, k);
+  calc_state(s, k.sumx, k.sumy, w.e[ILRL_E_WALK_X], w.e[ILRL_E_WALK_Y], c);
+  c.obs[1] = w.e[ILRL_E_OBS_SIN]; c.obs[2] = w.e[ILRL_E_OBS_COS];  // cur_obs predates the walk-target change below
+  w.e[ILRL_E_ROBOT_X] = c.bx; w.e[ILRL_E_ROBOT_Y] = c.by;
+  const float R2D = 57.29577951308232f, D2R = 0.017453292519943295f;
+  float ndeg = atan2f(a.action2[2 * i + 1], a.action2[2 * i]) * R2D + c.yaw * R2D;
+  float h = ndeg * D2R, sh, ch;
+  w.e[ILRL_E_HLDEG] = h;
+  sincosf(h, &sh, &ch);
+  float wx = w.e[ILRL_E_ROBOT_X] + ch * 5.f, wy = w.e[ILRL_E_ROBOT_Y] + sh * 5.f;
+  w.e[ILRL_E_WALK_X] = wx; w.e[ILRL_E_WALK_Y] = wy;
+  float vx = wx - w.e[ILRL_E_ROBOT_X], vy = wy - w.e[ILRL_E_ROBOT_Y];
+  float dx = w.e[ILRL_E_SEP_X] - w.e[ILRL_E_ROBOT_X], dy = w.e[ILRL_E_SEP_Y] - w.e[ILRL_E_ROBOT_Y], dz = w.e[ILRL_E_SEP_Z];
+  float len = sqrtf(dx * dx + dy * dy + dz * dz), ivn = rsqrtf(vx * vx + vy * vy);
+  w.e[ILRL_E_SEP_X] = -vx * ivn * len + w.e[ILRL_E_ROBOT_X];
+  w.e[ILRL_E_SEP_Y] = -vy * ivn * len + w.e[ILRL_E_ROBOT_Y];
+  w.e[ILRL_E_SEP_Z] = 0.f;
+  w.e[ILRL_E_STEPS_REMAINING] = a.step_per_level;
+  w.e[ILRL_E_HIGH_PENDING] = 0.f;
+  float o[70];
+  write_low_obs(c.obs, w, cl, o);
+  for (int t = 0; t < 70; t++) a.low_obs[(size_t)i * 70 + t] = o[t];
+  float* e = a.envf + i;
+#pragma unroll
+  for (int kk = 0; kk < ILRL_ENV_WORDS; kk++) e[kk * a.n] = w.e[kk];
+}
+
+// ------------------------------------------------------------------------------------------------ harness kernels
+__global__ void state_get_kernel(StateView v, float* phys_aos, float* envf_aos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  if (phys_aos) for (int k = 0; k < ILRL_PHYS_WORDS; k++) phys_aos[(size_t)i * ILRL_PHYS_WORDS + k] = v.phys[(size_t)k * v.n + i];
+  if (envf_aos) for (int k = 0; k < ILRL_ENV_WORDS; k++) envf_aos[(size_t)i * ILRL_ENV_WORDS + k] = v.envf[(size_t)k * v.n + i];
+}
+__global__ void state_set_kernel(StateView v, const float* phys_aos, const float* envf_aos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  if (phys_aos) for (int k = 0; k < ILRL_PHYS_WORDS; k++) v.phys[(size_t)k * v.n + i] = phys_aos[(size_t)i * ILRL_PHYS_WORDS + k];
+  if (envf_aos) for (int k = 0; k < ILRL_ENV_WORDS; k++) v.envf[(size_t)k * v.n + i] = envf_aos[(size_t)i * ILRL_ENV_WORDS + k];
+}
+__global__ void clip_ids_kernel(StateView v, const int32_t* ids) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= v.n) return;
+  v.envf[(size_t)ILRL_E_CLIP * v.n + i] = ids ? (float)ids[i] : 0.f;
+}
+__global__ void __launch_bounds__(BLOCK) physics_only_kernel(StateView v, const float* torque, Row* rows, int nsub, float* dbg, int dbg_env) {
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= v.n) return;
+  StepArgs a; a.n = v.n; a.phys = v.phys; a.envf = v.envf;
+  Phys s; EnvW w;
+  load_state(a, i, s, w);
+  float tau[NJ];
+  for (int j = 0; j < NJ; j++) tau[j] = torque[(size_t)i * NJ + j];
+  Work k;
+  for (int sub = 0; sub < nsub; sub++)
+    substep(s, tau, k, rows + (size_t)i * MAXROWS, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), (dbg && i == dbg_env) ? dbg : nullptr);
+  store_state(a, i, s, w);
+}
+struct EpArgs { StateView v; float* score; ClipDesc clips[MAX_CLIPS]; };
+__global__ void __launch_bounds__(BLOCK) endpoint_kernel(const EpArgs a) {
+  const int i = blockIdx.x * BLOCK + threadIdx.x;
+  if (i >= a.v.n) return;
+  StepArgs sa; sa.n = a.v.n; sa.phys = a.v.phys; sa.envf = a.v.envf;
+  Phys s; EnvW w;
+  load_state(sa, i, s, w);
+  Work k;
+  fk(s, k);
+  a.score[i] = endpoint_score(s, k, w, a.clips[(int)w.e[ILRL_E_CLIP]]);
+}
+__global__ void stats_fetch_kernel(float* acc, float* out) {
+  int t = threadIdx.x;
+  if (t < ILRL_STATS_WORDS) { out[t] = acc[t]; acc[t] = 0.f; }
+}
+
+}  // namespace ilrl
+
+// ================================================================================================ host side (C ABI)
+using namespace ilrl;
+
+struct ilrl_env {
+  ilrl_config cfg;
+  int n;
+  float* phys = nullptr;
+  float* envf = nullptr;
+  uint32_t* rng = nullptr;
+  Row* rows = nullptr;
+  float* high_obs = nullptr;
+  float* high_reward = nullptr;
+  uint8_t* high_flags = nullptr;
+  float* stats = nullptr;
+  float* clip_mem[MAX_CLIPS] = {nullptr};
+  ClipDesc clips[MAX_CLIPS];
+  bool clip_loaded[MAX_CLIPS] = {false};
+  const int32_t* forced_deg = nullptr;
+  // host-buffer path
+  float *h_action = nullptr, *h_obs = nullptr, *h_reward = nullptr, *h_terms = nullptr;
+  uint8_t* h_done = nullptr;
+  float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_terms = nullptr;
+  uint8_t* d_done = nullptr;
+  int substeps = ILRL_SUBSTEPS;  // harness only (ilrl_debug_substeps)
+  float* dbg = nullptr;          // harness only (ilrl_debug_dump)
+  int dbg_env = 0;
+  int64_t launches = 0;
+  bool timing = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float timed_ms = 0.f;
+  int64_t timed_launches = 0;
+  std::string err;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(ilrl_env* e, int code, const std::string& msg) {
+  if (e) e->err = msg; else g_create_err = msg;
+  return code;
+}
+#define CK(call)                                                                                       \
+  do {                                                                                                 \
+    cudaError_t _r = (call);                                                                           \
+    if (_r != cudaSuccess) return fail(env, ILRL_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_r)); \
+  } while (0)
+
+static inline int nblk(int n) { return (n + BLOCK - 1) / BLOCK; }
+
+extern "C" {
+
+const char* ilrl_last_error(const ilrl_env* env) { return env ? env->err.c_str() : g_create_err.c_str(); }
+
+int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
+  ilrl_env* env = nullptr;
+  if (!cfg || !out) return fail(nullptr, ILRL_ERR_ARG, "ilrl_create: null argument");
+  if (cfg->num_envs <= 0 || (cfg->mode != 0 && cfg->mode != 1)) return fail(nullptr, ILRL_ERR_ARG, "ilrl_create: bad num_envs/mode");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
+    return fail(nullptr, ILRL_ERR_CUDA, "ilrl_create: no CUDA device (this library has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, ILRL_ERR_ARG, "ilrl_create: bad device ordinal");
+  CK(cudaSetDevice(cfg->device));
+  env = new (std::nothrow) ilrl_env();
+  if (!env) return fail(nullptr, ILRL_ERR_ARG, "ilrl_create: out of host memory");
+  env->cfg = *cfg;
+  if (env->cfg.skip_frame <= 0) env->cfg.skip_frame = 2;
+  if (env->cfg.max_timestep <= 0) env->cfg.max_timestep = 3000;
+  if (env->cfg.step_per_level <= 0) env->cfg.step_per_level = 5;
+  const int n = env->n = cfg->num_envs;
+  memset(env->clips, 0, sizeof env->clips);
+#define CKC(call)                                                                              \
+  do {                                                                                         \
+    cudaError_t _r = (call);                                                                   \
+    if (_r != cudaSuccess) {                                                                   \
+      g_create_err = std::string(#call) + ": " + cudaGetErrorString(_r);                       \
+      ilrl_destroy(env);                                                                       \
+      return ILRL_ERR_CUDA;                                                                    \
+    }                                                                                          \
+  } while (0)
+  CKC(cudaMalloc(&env->phys, sizeof(float) * ILRL_PHYS_WORDS * n));
+  CKC(cudaMalloc(&env->envf, sizeof(float) * ILRL_ENV_WORDS * n));
+  CKC(cudaMalloc(&env->rng, sizeof(uint32_t) * n));
+  CKC(cudaMalloc(&env->rows, sizeof(Row) * (size_t)MAXROWS * n));
+  CKC(cudaMalloc(&env->high_obs, sizeof(float) * 44 * n));
+  CKC(cudaMalloc(&env->high_reward, sizeof(float) * n));
+  CKC(cudaMalloc(&env->high_flags, n));
+  CKC(cudaMalloc(&env->stats, sizeof(float) * ILRL_STATS_WORDS));
+  CKC(cudaMemset(env->phys, 0, sizeof(float) * ILRL_PHYS_WORDS * n));
+  CKC(cudaMemset(env->envf, 0, sizeof(float) * ILRL_ENV_WORDS * n));
+  CKC(cudaMemset(env->rng, 0, sizeof(uint32_t) * n));
+  CKC(cudaMemset(env->high_obs, 0, sizeof(float) * 44 * n));
+  CKC(cudaMemset(env->high_reward, 0, sizeof(float) * n));
+  CKC(cudaMemset(env->high_flags, 0, n));
+  CKC(cudaMemset(env->stats, 0, sizeof(float) * ILRL_STATS_WORDS));
+  CKC(cudaEventCreate(&env->ev0));
+  CKC(cudaEventCreate(&env->ev1));
+  CKC(cudaDeviceSynchronize());
+  *out = env;
+  return ILRL_OK;
+}
+
+void ilrl_destroy(ilrl_env* env) {
+  if (!env) return;
+  cudaSetDevice(env->cfg.device);
+  cudaDeviceSynchronize();
+  cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->rows);
+  cudaFree(env->high_obs); cudaFree(env->high_reward); cudaFree(env->high_flags); cudaFree(env->stats);
+  for (int c = 0; c < MAX_CLIPS; c++) cudaFree(env->clip_mem[c]);
+  cudaFreeHost(env->h_action); cudaFreeHost(env->h_obs); cudaFreeHost(env->h_reward); cudaFreeHost(env->h_terms);
+  cudaFreeHost(env->h_done);
+  cudaFree(env->d_action); cudaFree(env->d_obs); cudaFree(env->d_reward); cudaFree(env->d_terms); cudaFree(env->d_done);
+  if (env->ev0) cudaEventDestroy(env->ev0);
+  if (env->ev1) cudaEventDestroy(env->ev1);
+  delete env;
+}
+
+int ilrl_load_clip(ilrl_env* env, int32_t clip, const float* pos, int32_t n_pos, const float* rel, int32_t n_rel,
+                   const float* vel, int32_t n_vel, const float* ep, int32_t n_ep, int32_t max_frame) {
+  if (!env) return ILRL_ERR_ARG;
+  if (clip < 0 || clip >= MAX_CLIPS || !pos || !rel || !vel || !ep) return fail(env, ILRL_ERR_ARG, "ilrl_load_clip: bad argument");
+  // every frame the step/reset path can index must exist in all four tables
+  if (max_frame < 7 || max_frame > n_pos - 1 || max_frame > n_rel - 1 || max_frame > n_vel || max_frame > n_ep - 1)
+    return fail(env, ILRL_ERR_ARG, "ilrl_load_clip: max_frame exceeds a table (clamp it; see DESIGN.md on motion13_13)");
+  CK(cudaSetDevice(env->cfg.device));
+  size_t words = (size_t)14 * (n_pos + n_rel + n_vel) + (size_t)27 * n_ep;
+  cudaFree(env->clip_mem[clip]);
+  env->clip_mem[clip] = nullptr;
+  CK(cudaMalloc(&env->clip_mem[clip], words * sizeof(float)));
+  float* d = env->clip_mem[clip];
+  ClipDesc& c = env->clips[clip];
+  c.pos = d; CK(cudaMemcpy(d, pos, sizeof(float) * 14 * n_pos, cudaMemcpyHostToDevice)); d += 14 * n_pos;
+  c.rel = d; CK(cudaMemcpy(d, rel, sizeof(float) * 14 * n_rel, cudaMemcpyHostToDevice)); d += 14 * n_rel;
+  c.vel = d; CK(cudaMemcpy(d, vel, sizeof(float) * 14 * n_vel, cudaMemcpyHostToDevice)); d += 14 * n_vel;
+  c.ep = d;  CK(cudaMemcpy(d, ep, sizeof(float) * 27 * n_ep, cudaMemcpyHostToDevice));
+  c.n_pos = n_pos; c.n_vel = n_vel; c.max_frame = max_frame; c.pad = 0;
+  env->clip_loaded[clip] = true;
+  return ILRL_OK;
+}
+
+static StateView view(ilrl_env* env) { StateView v; v.n = env->n; v.phys = env->phys; v.envf = env->envf; v.rng = env->rng; return v; }
+
+int ilrl_set_clip_ids(ilrl_env* env, const int32_t* ids_host) {
+  if (!env) return ILRL_ERR_ARG;
+  CK(cudaSetDevice(env->cfg.device));
+  int32_t* d = nullptr;
+  if (ids_host) {
+    for (int i = 0; i < env->n; i++)
+      if (ids_host[i] < 0 || ids_host[i] >= MAX_CLIPS || !env->clip_loaded[ids_host[i]])
+        return fail(env, ILRL_ERR_STATE, "ilrl_set_clip_ids: env refers to a clip that is not loaded");
+    CK(cudaMalloc(&d, sizeof(int32_t) * env->n));
+    CK(cudaMemcpy(d, ids_host, sizeof(int32_t) * env->n, cudaMemcpyHostToDevice));
+  } else if (!env->clip_loaded[0]) {
+    return fail(env, ILRL_ERR_STATE, "ilrl_set_clip_ids: clip 0 is not loaded");
+  }
+  clip_ids_kernel<<<(env->n + 255) / 256, 256>>>(view(env), d);
+  env->launches++;
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  cudaFree(d);
+  return ILRL_OK;
+}
+
+static int check_ready(ilrl_env* env) {
+  if (!env->clip_loaded[0]) return fail(env, ILRL_ERR_STATE, "no motion clip loaded (ilrl_load_clip / ilrl_set_clip_ids first)");
+  return ILRL_OK;
+}
+
+int ilrl_reset(ilrl_env* env, const uint8_t* mask, const int32_t* start_frame, const int32_t* target_deg,
+               const float* yaw_deg, float* obs, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (int r = check_ready(env)) return r;
+  CK(cudaSetDevice(env->cfg.device));
+  ResetArgs a;
+  a.n = env->n; a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
+  a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
+  a.mask = mask; a.start_frame = start_frame; a.target_deg = target_deg; a.yaw_deg = yaw_deg; a.obs = obs;
+  a.high_flags = env->high_flags;
+  memcpy(a.clips, env->clips, sizeof a.clips);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (env->cfg.mode == 0) reset_kernel<0><<<nblk(env->n), BLOCK, 0, st>>>(a);
+  else reset_kernel<1><<<nblk(env->n), BLOCK, 0, st>>>(a);
+  env->launches++;
+  CK(cudaGetLastError());
+  return ILRL_OK;
+}
+
+static int do_step(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms,
+                   void* stream, int skip_physics) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!action || !obs || !reward || !done) return fail(env, ILRL_ERR_ARG, "ilrl_step: null buffer");
+  if (int r = check_ready(env)) return r;
+  CK(cudaSetDevice(env->cfg.device));
+  StepArgs a;
+  a.n = env->n; a.skip_physics = skip_physics; a.auto_reset = env->cfg.auto_reset; a.max_timestep = env->cfg.max_timestep;
+  a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
+  a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
+  a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.terms = terms;
+  a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
+  a.forced_deg = env->forced_deg; a.stats = env->stats; a.rows = env->rows;
+  memcpy(a.clips, env->clips, sizeof a.clips);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (env->timing) CK(cudaEventRecord(env->ev0, st));
+  if (env->cfg.mode == 0) step_kernel<0><<<nblk(env->n), BLOCK, 0, st>>>(a);
+  else step_kernel<1><<<nblk(env->n), BLOCK, 0, st>>>(a);
+  env->launches++;
+  CK(cudaGetLastError());
+  if (env->timing) {
+    CK(cudaEventRecord(env->ev1, st));
+    CK(cudaEventSynchronize(env->ev1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, env->ev0, env->ev1));
+    env->timed_ms += ms;
+    env->timed_launches++;
+  }
+  return ILRL_OK;
+}
+
+int ilrl_step(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms, void* stream) {
+  return do_step(env, action, obs, reward, done, terms, stream, 0);
+}
+int ilrl_step_no_physics(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms,
+                         void* stream) {
+  return do_step(env, action, obs, reward, done, terms, stream, 1);
+}
+
+int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* reward_h, uint8_t* done_h, float* terms_h,
+                   void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!action_h || !obs_h || !reward_h || !done_h) return fail(env, ILRL_ERR_ARG, "ilrl_step_host: null buffer");
+  CK(cudaSetDevice(env->cfg.device));
+  const size_t n = env->n;
+  if (!env->d_action) {  // staging buffers: pinned host mirrors + device I/O, allocated on first use
+    CK(cudaMallocHost(&env->h_action, sizeof(float) * 17 * n));
+    CK(cudaMallocHost(&env->h_obs, sizeof(float) * 70 * n));
+    CK(cudaMallocHost(&env->h_reward, sizeof(float) * n));
+    CK(cudaMallocHost(&env->h_terms, sizeof(float) * ILRL_TERM_WORDS * n));
+    CK(cudaMallocHost(&env->h_done, n));
+    CK(cudaMalloc(&env->d_action, sizeof(float) * 17 * n));
+    CK(cudaMalloc(&env->d_obs, sizeof(float) * 70 * n));
+    CK(cudaMalloc(&env->d_reward, sizeof(float) * n));
+    CK(cudaMalloc(&env->d_terms, sizeof(float) * ILRL_TERM_WORDS * n));
+    CK(cudaMalloc(&env->d_done, n));
+    CK(cudaMemset(env->d_obs, 0, sizeof(float) * 70 * n));
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  memcpy(env->h_action, action_h, sizeof(float) * 17 * n);
+  CK(cudaMemcpyAsync(env->d_action, env->h_action, sizeof(float) * 17 * n, cudaMemcpyHostToDevice, st));
+  int r = do_step(env, env->d_action, env->d_obs, env->d_reward, env->d_done, terms_h ? env->d_terms : nullptr, stream, 0);
+  if (r) return r;
+  CK(cudaMemcpyAsync(env->h_obs, env->d_obs, sizeof(float) * 70 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(env->h_reward, env->d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(env->h_done, env->d_done, n, cudaMemcpyDeviceToHost, st));
+  if (terms_h) CK(cudaMemcpyAsync(env->h_terms, env->d_terms, sizeof(float) * ILRL_TERM_WORDS * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  memcpy(obs_h, env->h_obs, sizeof(float) * 70 * n);
+  memcpy(reward_h, env->h_reward, sizeof(float) * n);
+  memcpy(done_h, env->h_done, n);
+  if (terms_h) memcpy(terms_h, env->h_terms, sizeof(float) * ILRL_TERM_WORDS * n);
+  return ILRL_OK;
+}
+
+int ilrl_high_step(ilrl_env* env, const float* action2, float* low_obs, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (env->cfg.mode != 1) return fail(env, ILRL_ERR_ARG, "ilrl_high_step: handle is not in hier mode");
+  if (!action2 || !low_obs) return fail(env, ILRL_ERR_ARG, "ilrl_high_step: null buffer");
+  if (int r = check_ready(env)) return r;
+  CK(cudaSetDevice(env->cfg.device));
+  HighArgs a;
+  a.n = env->n; a.step_per_level = (float)env->cfg.step_per_level; a.phys = env->phys; a.envf = env->envf;
+  a.action2 = action2; a.low_obs = low_obs;
+  memcpy(a.clips, env->clips, sizeof a.clips);
+  high_step_kernel<<<nblk(env->n), BLOCK, 0, (cudaStream_t)stream>>>(a);
+  env->launches++;
+  CK(cudaGetLastError());
+  return ILRL_OK;
+}
+
+int ilrl_high_readout(ilrl_env* env, float* high_obs, float* high_reward, uint8_t* high_flags, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (env->cfg.mode != 1) return fail(env, ILRL_ERR_ARG, "ilrl_high_readout: handle is not in hier mode");
+  CK(cudaSetDevice(env->cfg.device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (high_obs) CK(cudaMemcpyAsync(high_obs, env->high_obs, sizeof(float) * 44 * env->n, cudaMemcpyDeviceToDevice, st));
+  if (high_reward) CK(cudaMemcpyAsync(high_reward, env->high_reward, sizeof(float) * env->n, cudaMemcpyDeviceToDevice, st));
+  if (high_flags) CK(cudaMemcpyAsync(high_flags, env->high_flags, env->n, cudaMemcpyDeviceToDevice, st));
+  return ILRL_OK;
+}
+
+int ilrl_get_state(ilrl_env* env, float* phys, float* envf, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  CK(cudaSetDevice(env->cfg.device));
+  state_get_kernel<<<(env->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(view(env), phys, envf);
+  env->launches++;
+  CK(cudaGetLastError());
+  return ILRL_OK;
+}
+int ilrl_set_state(ilrl_env* env, const float* phys, const float* envf, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  CK(cudaSetDevice(env->cfg.device));
+  state_set_kernel<<<(env->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(view(env), phys, envf);
+  env->launches++;
+  CK(cudaGetLastError());
+  return ILRL_OK;
+}
+int ilrl_set_forced_target_deg(ilrl_env* env, const int32_t* deg) {
+  if (!env) return ILRL_ERR_ARG;
+  env->forced_deg = deg;
+  return ILRL_OK;
+}
+int ilrl_physics_only(ilrl_env* env, const float* torque, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!torque) return fail(env, ILRL_ERR_ARG, "ilrl_physics_only: null buffer");
+  CK(cudaSetDevice(env->cfg.device));
+  physics_only_kernel<<<nblk(env->n), BLOCK, 0, (cudaStream_t)stream>>>(view(env), torque, env->rows, env->substeps, env->dbg, env->dbg_env);
+  env->launches++;
+  CK(cudaGetLastError());
+  return ILRL_OK;
+}
+int ilrl_endpoint_score(ilrl_env* env, float* score, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!score) return fail(env, ILRL_ERR_ARG, "ilrl_endpoint_score: null buffer");
+  if (int r = check_ready(env)) return r;
+  CK(cudaSetDevice(env->cfg.device));
+  EpArgs a; a.v = view(env); a.score = score;
+  memcpy(a.clips, env->clips, sizeof a.clips);
+  endpoint_kernel<<<nblk(env->n), BLOCK, 0, (cudaStream_t)stream>>>(a);
+  env->launches++;
+  CK(cudaGetLastError());
+  return ILRL_OK;
+}
+int ilrl_stats(ilrl_env* env, float* stats16, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!stats16) return fail(env, ILRL_ERR_ARG, "ilrl_stats: null buffer");
+  CK(cudaSetDevice(env->cfg.device));
+  stats_fetch_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(env->stats, stats16);
+  env->launches++;
+  CK(cudaGetLastError());
+  return ILRL_OK;
+}
+/* harness only, not in ilrl.h: number of substeps ilrl_physics_only runs */
+int ilrl_debug_substeps(ilrl_env* env, int32_t n) { if (!env || n < 1) return ILRL_ERR_ARG; env->substeps = n; return ILRL_OK; }
+/* harness only, not in ilrl.h: dump the constraint rows of env `i` of the next ilrl_physics_only into dbg_dev[400] */
+int ilrl_debug_dump(ilrl_env* env, float* dbg_dev, int32_t i) { if (!env) return ILRL_ERR_ARG; env->dbg = dbg_dev; env->dbg_env = i; return ILRL_OK; }
+int64_t ilrl_launch_count(const ilrl_env* env) { return env ? env->launches : 0; }
+int ilrl_kernel_timing(ilrl_env* env, int32_t on, float* ms_out, int64_t* launches_out) {
+  if (!env) return ILRL_ERR_ARG;
+  if (ms_out) *ms_out = env->timed_ms;
+  if (launches_out) *launches_out = env->timed_launches;
+  env->timed_ms = 0.f; env->timed_launches = 0;
+  env->timing = on != 0;
+  return ILRL_OK;
+}
+
+}  // extern "C"

@@ -58,7 +58,8 @@ enum {
   ILRL_E_WALK_Y, ILRL_E_LOW_TARGET_SCORE, ILRL_E_JOINT_SCORE, ILRL_E_JVEL_SCORE, ILRL_E_POSTURE_SCORE,
   ILRL_E_OBS_SIN, ILRL_E_OBS_COS,                       /* cur_obs[1:3] of the last calc_state (hier low obs reuse) */
   ILRL_E_STEPS_REMAINING, ILRL_E_CUM_DRIFT, ILRL_E_HIGH_TARGET_SCORE, ILRL_E_CUM_ALIVE, ILRL_E_HIGH_PENDING,
-  ILRL_ENV_WORDS /* = 26 */
+  ILRL_E_EP_RETURN, ILRL_E_EP_LEN,                      /* running episode return / length (statistics only) */
+  ILRL_ENV_WORDS /* = 28 */
 };
 /* per-step "terms" row (the attributes RewardLogCallback reads, REF custom_callback.py:43-80) */
 enum {

@@ -1,0 +1,555 @@
+// ilrl_physics.cuh — per-env rigid-body substep for the humanoid of REF humanoid_symmetric_2.xml, sm_100a, fp32.
+//
+// Replaces, per env, what the reference reaches through `flat_env.scene.global_step()`
+// (REF low_level_env.py:479, hier_env.py:589) -> pybullet stepSimulation -> Bullet btMultiBody:
+//   forward dynamics by Featherstone's articulated-body algorithm (floating torso + 17 hinges), torque actuation,
+//   Bullet's velocity damping, ground-plane contact with friction and violated-joint-limit rows solved by 5
+//   projected-Gauss-Seidel sweeps on the velocities, semi-implicit integration.  Constants: ilrl_constants.h.
+//
+// Formulation (chosen for the GPU, not Bullet's link-local one): every spatial vector of one env is expressed in
+// WORLD axes about ONE reference point, the torso origin at the start of the substep.  Parent->child spatial
+// transforms are then the identity: the inward pass is plain additions and rank-1 downdates of symmetric 6x6
+// matrices, the outward pass plain additions — no per-link 6x6 congruence transforms, and fp32 stays accurate
+// however far the robot has walked because only offsets from the torso enter.
+//
+// One thread owns one env (see DESIGN.md "Mapping" for why not a warp per env); all loops below run over
+// compile-time tables, so every thread of a warp executes the same link at the same time and table reads are
+// immediates after unrolling.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "ilrl_constants.h"
+#include "ilrl_model_data.h"
+
+namespace ilrl {
+
+constexpr int NB = ILRL_NB, NJ = ILRL_NJ, NS = ILRL_NS, NV = 6 + ILRL_NJ, NMAP = ILRL_NMAP;
+constexpr int MAXC = ILRL_MAX_CONTACTS, MAXROWS = ILRL_MAX_ROWS;
+
+// ---- model tables (generated from the reference MJCF by tools/gen_model.py)
+__device__ constexpr int kBodyParent[NB] = ILRL_BODY_PARENT;
+__device__ constexpr int kBodyLink[NB] = ILRL_BODY_LINK;
+__device__ constexpr float kBodyPos[NB * 3] = ILRL_BODY_POS;
+__device__ constexpr float kBodyQuat[NB * 4] = ILRL_BODY_QUAT;
+__device__ constexpr float kBodyMass[NB] = ILRL_BODY_MASS;
+__device__ constexpr float kBodyInertia[NB * 3] = ILRL_BODY_INERTIA;
+__device__ constexpr int kJointBody[NJ] = ILRL_JOINT_BODY;
+__device__ constexpr int kJointParent[NJ] = ILRL_JOINT_PARENT;
+__device__ constexpr float kJointAnchor[NJ * 3] = ILRL_JOINT_ANCHOR;
+__device__ constexpr float kJointAxis[NJ * 3] = ILRL_JOINT_AXIS;
+__device__ constexpr float kJointLo[NJ] = ILRL_JOINT_LO;
+__device__ constexpr float kJointHi[NJ] = ILRL_JOINT_HI;
+__device__ constexpr int kSphereBody[NS] = ILRL_SPHERE_BODY;
+__device__ constexpr int kSphereLink[NS] = ILRL_SPHERE_LINK;
+__device__ constexpr float kSphereC[NS * 3] = ILRL_SPHERE_C;
+__device__ constexpr float kSphereR[NS] = ILRL_SPHERE_R;
+
+// ---- small vector helpers
+struct V3 { float x, y, z; };
+__device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return mk(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return mk(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ V3 operator*(float s, V3 a) { return mk(s * a.x, s * a.y, s * a.z); }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) { return mk(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 ld3(const float* p) { return mk(p[0], p[1], p[2]); }
+__device__ __forceinline__ void st3(float* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
+// row-major 3x3
+__device__ __forceinline__ V3 mv(const float* R, V3 v) {
+  return mk(R[0] * v.x + R[1] * v.y + R[2] * v.z, R[3] * v.x + R[4] * v.y + R[5] * v.z, R[6] * v.x + R[7] * v.y + R[8] * v.z);
+}
+__device__ __forceinline__ V3 mtv(const float* R, V3 v) {
+  return mk(R[0] * v.x + R[3] * v.y + R[6] * v.z, R[1] * v.x + R[4] * v.y + R[7] * v.z, R[2] * v.x + R[5] * v.y + R[8] * v.z);
+}
+__device__ __forceinline__ void mm(const float* A, const float* B, float* O) {
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) O[i * 3 + j] = A[i * 3] * B[j] + A[i * 3 + 1] * B[3 + j] + A[i * 3 + 2] * B[6 + j];
+}
+__device__ __forceinline__ void quat2mat(float x, float y, float z, float w, float* R) {
+  float s = 2.0f / (x * x + y * y + z * z + w * w);
+  R[0] = 1 - s * (y * y + z * z); R[1] = s * (x * y - w * z);     R[2] = s * (x * z + w * y);
+  R[3] = s * (x * y + w * z);     R[4] = 1 - s * (x * x + z * z); R[5] = s * (y * z - w * x);
+  R[6] = s * (x * z - w * y);     R[7] = s * (y * z + w * x);     R[8] = 1 - s * (x * x + y * y);
+}
+
+// spatial vectors: motion (w, v) / force (n, f), world axes, about the reference point
+struct SV { V3 a, l; };  // angular part, linear part
+__device__ __forceinline__ SV operator+(SV p, SV q) { SV r; r.a = p.a + q.a; r.l = p.l + q.l; return r; }
+__device__ __forceinline__ SV operator*(float s, SV p) { SV r; r.a = s * p.a; r.l = s * p.l; return r; }
+__device__ __forceinline__ float sdot(SV m, SV f) { return dot(m.a, f.a) + dot(m.l, f.l); }
+__device__ __forceinline__ SV crm(SV v, SV x) { SV r; r.a = cross(v.a, x.a); r.l = cross(v.a, x.l) + cross(v.l, x.a); return r; }
+__device__ __forceinline__ SV crf(SV v, SV f) { SV r; r.a = cross(v.a, f.a) + cross(v.l, f.l); r.l = cross(v.a, f.l); return r; }
+__device__ __forceinline__ SV ldsv(const float* p) { SV r; r.a = ld3(p); r.l = ld3(p + 3); return r; }
+__device__ __forceinline__ void stsv(float* p, SV v) { st3(p, v.a); st3(p + 3, v.l); }
+
+// symmetric spatial inertia in 3x3 blocks: n = A w + B v, f = B^T w + C v.  A, C symmetric (xx,xy,xz,yy,yz,zz)
+struct Inertia {
+  float A[6], B[9], C[6];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < 6; i++) { A[i] = 0; C[i] = 0; }
+#pragma unroll
+    for (int i = 0; i < 9; i++) B[i] = 0;
+  }
+  __device__ __forceinline__ void add(const Inertia& o) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) { A[i] += o.A[i]; C[i] += o.C[i]; }
+#pragma unroll
+    for (int i = 0; i < 9; i++) B[i] += o.B[i];
+  }
+};
+__device__ __forceinline__ V3 symv(const float* S, V3 v) {
+  return mk(S[0] * v.x + S[1] * v.y + S[2] * v.z, S[1] * v.x + S[3] * v.y + S[4] * v.z, S[2] * v.x + S[4] * v.y + S[5] * v.z);
+}
+__device__ __forceinline__ SV imul(const Inertia& I, SV m) {
+  SV r;
+  r.a = symv(I.A, m.a) + mv(I.B, m.l);
+  r.l = mtv(I.B, m.a) + symv(I.C, m.l);
+  return r;
+}
+// I -= U U^T * dinv
+__device__ __forceinline__ void downdate(Inertia& I, SV U, float dinv) {
+  V3 ua = dinv * U.a, ul = dinv * U.l;
+  I.A[0] -= ua.x * U.a.x; I.A[1] -= ua.x * U.a.y; I.A[2] -= ua.x * U.a.z;
+  I.A[3] -= ua.y * U.a.y; I.A[4] -= ua.y * U.a.z; I.A[5] -= ua.z * U.a.z;
+  I.B[0] -= ua.x * U.l.x; I.B[1] -= ua.x * U.l.y; I.B[2] -= ua.x * U.l.z;
+  I.B[3] -= ua.y * U.l.x; I.B[4] -= ua.y * U.l.y; I.B[5] -= ua.y * U.l.z;
+  I.B[6] -= ua.z * U.l.x; I.B[7] -= ua.z * U.l.y; I.B[8] -= ua.z * U.l.z;
+  I.C[0] -= ul.x * U.l.x; I.C[1] -= ul.x * U.l.y; I.C[2] -= ul.x * U.l.z;
+  I.C[3] -= ul.y * U.l.y; I.C[4] -= ul.y * U.l.z; I.C[5] -= ul.z * U.l.z;
+}
+
+// per-env physics state held by the owning thread
+struct Phys {
+  float p[3], quat[4], v[3], w[3];  // torso position, orientation (x,y,z,w), linear / angular velocity (world)
+  float q[NJ], qd[NJ];
+};
+
+// per-thread scratch of one substep (local memory; every index below is warp-uniform)
+struct Work {
+  float R[NB][9];   // body rotations (world)
+  float o[NB][3];   // body origins relative to the torso origin (world axes)
+  float S[NJ][6];   // joint motion subspace (axis, anchor x axis)
+  float V[NJ][6];   // link spatial velocities
+  float cJ[NJ][6];  // velocity-product accelerations
+  float U[NJ][6];   // IA * S
+  float Dinv[NJ], u[NJ];
+  float L0[21];     // Cholesky factor of the base articulated inertia (packed lower, row-major)
+  float sumx, sumy; // sum of the 32 part origins (15 bodies + 17 joint anchors), relative to the torso
+};
+
+// ---- forward kinematics: body frames, joint subspaces, (optionally) link velocities and bias accelerations
+__device__ __forceinline__ void fk(const Phys& s, Work& k) {
+  quat2mat(s.quat[0], s.quat[1], s.quat[2], s.quat[3], k.R[0]);
+  k.o[0][0] = k.o[0][1] = k.o[0][2] = 0.f;
+  float sx = 0.f, sy = 0.f;
+#pragma unroll
+  for (int b = 1; b < NB; b++) {
+    const int p = kBodyParent[b];
+    float Rc[9];
+    const bool ident = kBodyQuat[4 * b] == 0.f && kBodyQuat[4 * b + 1] == 0.f && kBodyQuat[4 * b + 2] == 0.f;
+    if (ident) {
+#pragma unroll
+      for (int i = 0; i < 9; i++) Rc[i] = k.R[p][i];
+    } else {
+      float Q[9];
+      quat2mat(kBodyQuat[4 * b], kBodyQuat[4 * b + 1], kBodyQuat[4 * b + 2], kBodyQuat[4 * b + 3], Q);
+      mm(k.R[p], Q, Rc);
+    }
+    V3 oc = ld3(k.o[p]) + mv(k.R[p], mk(kBodyPos[3 * b], kBodyPos[3 * b + 1], kBodyPos[3 * b + 2]));
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      if (kJointBody[j] != b) continue;
+      const V3 an = mk(kJointAnchor[3 * j], kJointAnchor[3 * j + 1], kJointAnchor[3 * j + 2]);
+      const V3 ax = mk(kJointAxis[3 * j], kJointAxis[3 * j + 1], kJointAxis[3 * j + 2]);
+      V3 rw = oc + mv(Rc, an);
+      V3 aw = mv(Rc, ax);
+      st3(k.S[j], aw);
+      st3(k.S[j] + 3, cross(rw, aw));
+      sx += rw.x; sy += rw.y;
+      // Rn = Rc * Rot(ax, q)   (Rodrigues)
+      float sn, cs;
+      sincosf(s.q[j], &sn, &cs);
+      float t = 1.f - cs, Rj[9], Rn[9];
+      Rj[0] = t * ax.x * ax.x + cs;        Rj[1] = t * ax.x * ax.y - sn * ax.z; Rj[2] = t * ax.x * ax.z + sn * ax.y;
+      Rj[3] = t * ax.x * ax.y + sn * ax.z; Rj[4] = t * ax.y * ax.y + cs;        Rj[5] = t * ax.y * ax.z - sn * ax.x;
+      Rj[6] = t * ax.x * ax.z - sn * ax.y; Rj[7] = t * ax.y * ax.z + sn * ax.x; Rj[8] = t * ax.z * ax.z + cs;
+      mm(Rc, Rj, Rn);
+      oc = rw - mv(Rn, an);
+#pragma unroll
+      for (int i = 0; i < 9; i++) Rc[i] = Rn[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 9; i++) k.R[b][i] = Rc[i];
+    st3(k.o[b], oc);
+    sx += oc.x; sy += oc.y;
+  }
+  k.sumx = sx; k.sumy = sy;
+}
+
+// rigid-body spatial inertia (about the reference point, world axes) of body b and its bias force
+// p = V x* (I V) - f_ext  with gravity and Bullet's velocity damping as external forces.
+__device__ __forceinline__ void body_inertia_bias(const Work& k, int b, SV V, Inertia& I, SV& pb) {
+  const float m = kBodyMass[b];
+  const float* R = k.R[b];
+  V3 c = ld3(k.o[b]);
+  const float ix = kBodyInertia[3 * b], iy = kBodyInertia[3 * b + 1], iz = kBodyInertia[3 * b + 2];
+  // Ic = R diag(i) R^T
+  float Ic[6];
+  Ic[0] = ix * R[0] * R[0] + iy * R[1] * R[1] + iz * R[2] * R[2];
+  Ic[1] = ix * R[0] * R[3] + iy * R[1] * R[4] + iz * R[2] * R[5];
+  Ic[2] = ix * R[0] * R[6] + iy * R[1] * R[7] + iz * R[2] * R[8];
+  Ic[3] = ix * R[3] * R[3] + iy * R[4] * R[4] + iz * R[5] * R[5];
+  Ic[4] = ix * R[3] * R[6] + iy * R[4] * R[7] + iz * R[5] * R[8];
+  Ic[5] = ix * R[6] * R[6] + iy * R[7] * R[7] + iz * R[8] * R[8];
+  float cc = dot(c, c);
+  I.A[0] = Ic[0] + m * (cc - c.x * c.x); I.A[1] = Ic[1] - m * c.x * c.y; I.A[2] = Ic[2] - m * c.x * c.z;
+  I.A[3] = Ic[3] + m * (cc - c.y * c.y); I.A[4] = Ic[4] - m * c.y * c.z; I.A[5] = Ic[5] + m * (cc - c.z * c.z);
+  I.B[0] = 0;        I.B[1] = -m * c.z; I.B[2] = m * c.y;
+  I.B[3] = m * c.z;  I.B[4] = 0;        I.B[5] = -m * c.x;
+  I.B[6] = -m * c.y; I.B[7] = m * c.x;  I.B[8] = 0;
+  I.C[0] = m; I.C[1] = 0; I.C[2] = 0; I.C[3] = m; I.C[4] = 0; I.C[5] = m;
+  // momentum about the reference point and its velocity-product rate
+  V3 vc = V.l + cross(V.a, c);          // velocity of the body origin (= COM in Bullet's MJCF import)
+  V3 Iw = symv(Ic, V.a);
+  SV h; h.l = m * vc; h.a = Iw + cross(c, h.l);
+  pb = crf(V, h);
+  // external: gravity at the COM + Bullet's damping  -m v (K1 + K2|v|),  -Iw (K1 + K2|w|)
+  float vn = sqrtf(dot(vc, vc)), wn = sqrtf(dot(V.a, V.a));
+  float kl = m * ((float)ILRL_DAMP_K1_LIN + (float)ILRL_DAMP_K2_LIN * vn);
+  float ka = (float)ILRL_DAMP_K1_ANG + (float)ILRL_DAMP_K2_ANG * wn;
+  V3 F = mk(-kl * vc.x, -kl * vc.y, -kl * vc.z - m * (float)ILRL_GRAVITY);
+  V3 N = mk(-ka * Iw.x, -ka * Iw.y, -ka * Iw.z);
+  pb.a = pb.a - (N + cross(c, F));
+  pb.l = pb.l - F;
+}
+
+// Cholesky of the 6x6 SPD base inertia [[A,B],[B^T,C]] -> packed lower L (row-major: L[i*(i+1)/2 + j])
+__device__ __forceinline__ void chol6(const Inertia& I, float* L) {
+  float M[6][6];
+  M[0][0] = I.A[0]; M[0][1] = I.A[1]; M[0][2] = I.A[2]; M[1][1] = I.A[3]; M[1][2] = I.A[4]; M[2][2] = I.A[5];
+  M[3][3] = I.C[0]; M[3][4] = I.C[1]; M[3][5] = I.C[2]; M[4][4] = I.C[3]; M[4][5] = I.C[4]; M[5][5] = I.C[5];
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = 0; j < 3; j++) M[i][3 + j] = I.B[i * 3 + j];
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    float sdiag = M[j][j];
+#pragma unroll
+    for (int c = 0; c < j; c++) sdiag -= L[j * (j + 1) / 2 + c] * L[j * (j + 1) / 2 + c];
+    float inv = rsqrtf(fmaxf(sdiag, 1e-20f));
+    L[j * (j + 1) / 2 + j] = inv;  // store the INVERSE of the diagonal
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      float t = M[j][i];  // symmetric: M[i][j] == M[j][i]
+#pragma unroll
+      for (int c = 0; c < j; c++) t -= L[i * (i + 1) / 2 + c] * L[j * (j + 1) / 2 + c];
+      L[i * (i + 1) / 2 + j] = t * inv;
+    }
+  }
+}
+// x = M^-1 b with the factor above (diagonal entries hold 1/L_jj)
+__device__ __forceinline__ SV chol6_solve(const float* L, SV b) {
+  float y[6] = {b.a.x, b.a.y, b.a.z, b.l.x, b.l.y, b.l.z};
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float t = y[i];
+#pragma unroll
+    for (int c = 0; c < i; c++) t -= L[i * (i + 1) / 2 + c] * y[c];
+    y[i] = t * L[i * (i + 1) / 2 + i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    float t = y[i];
+#pragma unroll
+    for (int c = i + 1; c < 6; c++) t -= L[c * (c + 1) / 2 + i] * y[c];
+    y[i] = t * L[i * (i + 1) / 2 + i];
+  }
+  SV r; r.a = mk(y[0], y[1], y[2]); r.l = mk(y[3], y[4], y[5]);
+  return r;
+}
+
+// tree shape helpers (compile-time): link 2 (abdomen_x) carries both legs, the base carries spine + both arms
+__device__ constexpr bool is_leaf(int l) {
+  for (int j = 0; j < NJ; j++) if (kJointParent[j] == l) return false;
+  return true;
+}
+constexpr int kPelvisLink = 2;
+
+// ---- forward dynamics: returns base spatial acceleration a0 and qdd[NJ]; leaves S,U,Dinv,L0 in k for the rows
+__device__ __forceinline__ void aba(const Phys& s, const float* tau, Work& k, SV& a0, float* qdd) {
+  SV V0; V0.a = ld3(s.w); V0.l = ld3(s.v);
+  // outward: link velocities and velocity-product accelerations
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const int p = kJointParent[j];
+    SV Vp = p < 0 ? V0 : ldsv(k.V[p]);
+    SV X = s.qd[j] * ldsv(k.S[j]);
+    stsv(k.V[j], Vp + X);
+    stsv(k.cJ[j], crm(Vp, X));
+  }
+  // inward: articulated inertias; three running accumulators suffice for this tree
+  Inertia cur, pel, bas, Ib;
+  SV pcur, ppel, pbas, pb;
+  pel.zero(); ppel.a = ppel.l = mk(0, 0, 0);
+  body_inertia_bias(k, 0, V0, bas, pbas);
+#pragma unroll
+  for (int j = NJ - 1; j >= 0; j--) {
+    if (is_leaf(j)) { cur.zero(); pcur.a = pcur.l = mk(0, 0, 0); }
+    if (j == kPelvisLink) { cur = pel; pcur = ppel; }
+    SV Vj = ldsv(k.V[j]);
+#pragma unroll
+    for (int b = 1; b < NB; b++) {
+      if (kBodyLink[b] != j) continue;
+      body_inertia_bias(k, b, Vj, Ib, pb);
+      cur.add(Ib); pcur = pcur + pb;
+    }
+    SV S = ldsv(k.S[j]);
+    SV U = imul(cur, S);
+    float D = sdot(S, U);
+    float dinv = 1.0f / fmaxf(D, 1e-9f);
+    float u = tau[j] - sdot(S, pcur);
+    stsv(k.U[j], U); k.Dinv[j] = dinv; k.u[j] = u;
+    downdate(cur, U, dinv);
+    pcur = pcur + imul(cur, ldsv(k.cJ[j])) + (u * dinv) * U;
+    const int p = kJointParent[j];
+    if (p < 0) { bas.add(cur); pbas = pbas + pcur; }
+    else if (p == kPelvisLink) { pel.add(cur); ppel = ppel + pcur; }
+    // else: flows on to the next (parent) link through `cur`
+  }
+  chol6(bas, k.L0);
+  SV np0; np0.a = mk(-pbas.a.x, -pbas.a.y, -pbas.a.z); np0.l = mk(-pbas.l.x, -pbas.l.y, -pbas.l.z);
+  a0 = chol6_solve(k.L0, np0);
+  // outward: accelerations
+  SV acur = a0, apel = a0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const int p = kJointParent[j];
+    SV ap = p < 0 ? a0 : (p == kPelvisLink ? apel : acur);
+    SV ad = ap + ldsv(k.cJ[j]);
+    float qa = k.Dinv[j] * (k.u[j] - sdot(ad, ldsv(k.U[j])));
+    qdd[j] = qa;
+    acur = ad + qa * ldsv(k.S[j]);
+    if (j == kPelvisLink) apel = acur;
+  }
+}
+
+// ---- response of the generalized velocities to a unit impulse: spatial force F on link `link` (link = -1: base)
+//      or a unit generalized impulse on joint `jl` (F ignored).  Uses S,U,Dinv,L0 left by aba().  O(n).
+__device__ __forceinline__ void unit_response(const Work& k, int link, SV F, int jl, float* resp /*[NV]*/) {
+  float ul[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) ul[j] = 0.f;
+  SV pf;  // bias force flowing to the base (sign: p = -F)
+  int l;
+  if (jl >= 0) {
+    ul[jl] = 1.f;
+    pf = k.Dinv[jl] * ldsv(k.U[jl]);
+    l = kJointParent[jl];
+  } else {
+    pf.a = mk(-F.a.x, -F.a.y, -F.a.z); pf.l = mk(-F.l.x, -F.l.y, -F.l.z);
+    l = link;
+  }
+  for (; l >= 0; l = kJointParent[l]) {
+    float u = -sdot(ldsv(k.S[l]), pf);
+    ul[l] = u;
+    pf = pf + (u * k.Dinv[l]) * ldsv(k.U[l]);
+  }
+  SV npf; npf.a = mk(-pf.a.x, -pf.a.y, -pf.a.z); npf.l = mk(-pf.l.x, -pf.l.y, -pf.l.z);
+  SV a0 = chol6_solve(k.L0, npf);
+  resp[0] = a0.a.x; resp[1] = a0.a.y; resp[2] = a0.a.z; resp[3] = a0.l.x; resp[4] = a0.l.y; resp[5] = a0.l.z;
+  SV acur = a0, apel = a0;
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    const int p = kJointParent[j];
+    SV ap = p < 0 ? a0 : (p == kPelvisLink ? apel : acur);
+    float qa = k.Dinv[j] * (ul[j] - sdot(ap, ldsv(k.U[j])));
+    resp[6 + j] = qa;
+    acur = ap + qa * ldsv(k.S[j]);
+    if (j == kPelvisLink) apel = acur;
+  }
+}
+
+// one constraint row (contact rows keep their wrench F; limit rows their joint)
+struct Row {
+  float resp[NV];
+  float F[6];      // contact: unit wrench about the reference point; limit: unused
+  int link;        // contact: link index (-1 base); limit: joint index
+  float dir;       // limit: +1 (lower) / -1 (upper); contact rows: 0
+  float rhs, dinv, lam;
+};
+
+// J . x for a row, x = generalized velocity-like vector (base angular, base linear, joints)
+__device__ __forceinline__ float row_jdot(const Work& k, const Row& r, const float* x) {
+  if (r.dir != 0.f) return r.dir * x[6 + r.link];
+  SV F = ldsv(r.F);
+  float acc = F.a.x * x[0] + F.a.y * x[1] + F.a.z * x[2] + F.l.x * x[3] + F.l.y * x[4] + F.l.z * x[5];
+  for (int l = r.link; l >= 0; l = kJointParent[l]) acc += sdot(ldsv(k.S[l]), F) * x[6 + l];
+  return acc;
+}
+
+__device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+
+// ---- one substep of dt (REF: scene.global_step() runs 4 of these with the torques held)
+__device__ __forceinline__ void substep(Phys& s, const float* tau, Work& k, Row* rows, float dt, float* dbg = nullptr) {
+  fk(s, k);
+  SV a0;
+  float nu[NV];
+  {
+    float qdd[NJ];
+    aba(s, tau, k, a0, qdd);
+    // classical acceleration of the torso origin = spatial linear acceleration + w x v
+    V3 w = ld3(s.w), v = ld3(s.v);
+    V3 lin = a0.l + cross(w, v);
+    nu[0] = s.w[0] + dt * a0.a.x; nu[1] = s.w[1] + dt * a0.a.y; nu[2] = s.w[2] + dt * a0.a.z;
+    nu[3] = s.v[0] + dt * lin.x;  nu[4] = s.v[1] + dt * lin.y;  nu[5] = s.v[2] + dt * lin.z;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) nu[6 + j] = s.qd[j] + dt * qdd[j];
+#pragma unroll
+    for (int i = 0; i < NV; i++) nu[i] = clampf(nu[i], -(float)ILRL_MAX_COORD_VEL, (float)ILRL_MAX_COORD_VEL);
+  }
+  // ---- rows: violated joint limits ...
+  int nlim = 0, ncon = 0;
+  const float idt = 1.0f / dt;
+#pragma unroll 1
+  for (int j = 0; j < NJ; j++) {
+    float pen, dir;
+    if (s.q[j] - kJointLo[j] <= 0.f) { pen = s.q[j] - kJointLo[j]; dir = 1.f; }
+    else if (kJointHi[j] - s.q[j] <= 0.f) { pen = kJointHi[j] - s.q[j]; dir = -1.f; }
+    else continue;
+    Row& r = rows[nlim++];
+    r.link = j; r.dir = dir;
+    SV z; z.a = z.l = mk(0, 0, 0);
+    unit_response(k, -1, z, j, r.resp);
+    float d = r.resp[6 + j];
+    r.dinv = 1.0f / d;
+    r.rhs = (-pen * (float)ILRL_LIMIT_ERP * idt - dir * nu[6 + j]) * r.dinv;
+    r.lam = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; i++) r.resp[i] *= dir;
+  }
+  // ---- ... then ground contacts: the deepest ILRL_MAX_CONTACTS spheres below the breaking distance
+  {
+    float sd[NS];
+    uint32_t act = 0;
+    int nact = 0;
+#pragma unroll
+    for (int i = 0; i < NS; i++) {
+      const int b = kSphereBody[i];
+      float cz = k.o[b][2] + k.R[b][6] * kSphereC[3 * i] + k.R[b][7] * kSphereC[3 * i + 1] + k.R[b][8] * kSphereC[3 * i + 2];
+      sd[i] = s.p[2] + cz - kSphereR[i];
+      if (sd[i] < (float)ILRL_CONTACT_BREAK) { act |= 1u << i; nact++; }
+    }
+    while (nact > MAXC) {
+      int worst = -1;
+      float wd = -1e30f;
+      for (int i = 0; i < NS; i++)
+        if (((act >> i) & 1u) && sd[i] >= wd) { wd = sd[i]; worst = i; }
+      act &= ~(1u << worst);
+      nact--;
+    }
+#pragma unroll 1
+    for (int i = 0; i < NS; i++) {
+      if (!((act >> i) & 1u)) continue;
+      const int b = kSphereBody[i];
+      V3 c = ld3(k.o[b]) + mv(k.R[b], mk(kSphereC[3 * i], kSphereC[3 * i + 1], kSphereC[3 * i + 2]));
+      V3 x = mk(c.x, c.y, c.z - kSphereR[i]);  // contact point on the robot, relative to the reference point
+      float dist = sd[i];
+      const int link = kSphereLink[i];
+      if (dbg) { dbg[230 + ncon] = (float)i; dbg[240 + ncon] = dist; dbg[250 + ncon] = c.z + s.p[2] - kSphereR[i]; for (int q = 0; q < NS; q++) dbg[260 + q] = sd[q]; dbg[259] = (float)act; }
+      // normal (0,0,1), tangents btPlaneSpace1 -> (0,-1,0), (1,0,0)
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        V3 d = t == 0 ? mk(0, 0, 1) : (t == 1 ? mk(0, -1, 0) : mk(1, 0, 0));
+        Row& r = rows[nlim + 3 * ncon + t];
+        SV F; F.a = cross(x, d); F.l = d;
+        stsv(r.F, F); r.link = link; r.dir = 0.f; r.lam = 0.f;
+        unit_response(k, link, F, -1, r.resp);
+        float dd = row_jdot(k, r, r.resp), rv = row_jdot(k, r, nu);
+        r.dinv = 1.0f / dd;
+        float pos = t == 0 ? (dist > 0.f ? -dist * idt : -dist * (float)ILRL_CONTACT_ERP * idt) : 0.f;
+        r.rhs = (pos - rv) * r.dinv;
+      }
+      ncon++;
+    }
+  }
+  // ---- projected Gauss-Seidel on the velocity change dv (limits, normals, friction pairs with implicit cone)
+  if (nlim + ncon > 0) {
+    float dv[NV];
+#pragma unroll
+    for (int i = 0; i < NV; i++) dv[i] = 0.f;
+#pragma unroll 1
+    for (int it = 0; it < ILRL_SOLVER_ITERS; it++) {
+#pragma unroll 1
+      for (int ri = 0; ri < nlim; ri++) {
+        Row& r = rows[ri];
+        float nl = fmaxf(r.lam + r.rhs - (r.dir * dv[6 + r.link]) * r.dinv, 0.f);
+        float dl = nl - r.lam;
+        r.lam = nl;
+#pragma unroll
+        for (int i = 0; i < NV; i++) dv[i] += dl * r.resp[i];
+      }
+#pragma unroll 1
+      for (int ci = 0; ci < ncon; ci++) {
+        Row& r = rows[nlim + 3 * ci];
+        float nl = fmaxf(r.lam + r.rhs - row_jdot(k, r, dv) * r.dinv, 0.f);
+        float dl = nl - r.lam;
+        r.lam = nl;
+#pragma unroll
+        for (int i = 0; i < NV; i++) dv[i] += dl * r.resp[i];
+      }
+#pragma unroll 1
+      for (int ci = 0; ci < ncon; ci++) {
+        Row& rn = rows[nlim + 3 * ci];
+        if (!(rn.lam > 0.f)) continue;
+        Row& r1 = rows[nlim + 3 * ci + 1];
+        Row& r2 = rows[nlim + 3 * ci + 2];
+        float lim = (float)ILRL_FRICTION * rn.lam;
+        float s1 = r1.lam + r1.rhs - row_jdot(k, r1, dv) * r1.dinv;
+        float s2 = r2.lam + r2.rhs - row_jdot(k, r2, dv) * r2.dinv;
+        float n2 = s1 * s1 + s2 * s2;
+        if (n2 > lim * lim) { float sc = lim * rsqrtf(n2); s1 *= sc; s2 *= sc; }
+        float d1 = s1 - r1.lam, d2 = s2 - r2.lam;
+        r1.lam = s1; r2.lam = s2;
+#pragma unroll
+        for (int i = 0; i < NV; i++) dv[i] += d1 * r1.resp[i] + d2 * r2.resp[i];
+      }
+    }
+    if (dbg) {
+      dbg[0] = (float)nlim; dbg[1] = (float)ncon;
+      for (int r = 0; r < nlim + 3 * ncon; r++) {
+        dbg[2 + 5 * r] = (float)rows[r].link; dbg[3 + 5 * r] = rows[r].dir; dbg[4 + 5 * r] = rows[r].rhs;
+        dbg[5 + 5 * r] = rows[r].dinv; dbg[6 + 5 * r] = rows[r].lam;
+      }
+      for (int i = 0; i < NV; i++) { dbg[300 + i] = nu[i]; dbg[330 + i] = dv[i]; dbg[360 + i] = rows[0].resp[i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; i++) nu[i] = clampf(nu[i] + dv[i], -(float)ILRL_MAX_COORD_VEL, (float)ILRL_MAX_COORD_VEL);
+  }
+  // ---- integrate (exponential map on the torso quaternion, as btMultiBody::stepPositionsMultiDof)
+#pragma unroll
+  for (int i = 0; i < 3; i++) { s.w[i] = nu[i]; s.v[i] = nu[3 + i]; s.p[i] += dt * nu[3 + i]; }
+  {
+    float wn = sqrtf(nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]), sc, cw;
+    if (wn < 1e-3f) sc = 0.5f * dt - dt * dt * dt * 0.020833333333f * wn * wn;
+    else sc = sinf(0.5f * wn * dt) / wn;
+    cw = cosf(0.5f * wn * dt);
+    float dx = nu[0] * sc, dy = nu[1] * sc, dz = nu[2] * sc;
+    float x = s.quat[0], y = s.quat[1], z = s.quat[2], ww = s.quat[3];
+    float nx = cw * x + dx * ww + dy * z - dz * y;
+    float ny = cw * y - dx * z + dy * ww + dz * x;
+    float nz = cw * z + dx * y - dy * x + dz * ww;
+    float nw = cw * ww - dx * x - dy * y - dz * z;
+    float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+    s.quat[0] = nx * inv; s.quat[1] = ny * inv; s.quat[2] = nz * inv; s.quat[3] = nw * inv;
+  }
+#pragma unroll
+  for (int j = 0; j < NJ; j++) { s.qd[j] = nu[6 + j]; s.q[j] += dt * s.qd[j]; }
+}
+
+}  // namespace ilrl

@@ -1,0 +1,121 @@
+/* ilrl.h — C ABI of the B200-native batched humanoid-imitation env (libilrl_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of AdityaPutraS/Imitation-Learning-RL: the env step / reset + imitation reward +
+ * observation that the reference reaches through
+ *     LowLevelHumanoidEnv.{reset,resetFromFrame,step}          REF low_level_env.py:224-305, 322-323, 475-526
+ *     HierarchicalHumanoidEnv.{reset,resetFromFrame,step}      REF hier_env.py:235-319, 355-366, 538-642
+ *     CustomHumanoidRobot.apply_action / calc_state            REF humanoid.py:54-60 (+ pybullet_envs WalkerBase)
+ *     scene.global_step() -> pybullet.stepSimulation           REF low_level_env.py:479, hier_env.py:589
+ * The reference has no FFI of its own (it is pure Python over pybullet's C extension); the entry points below are
+ * what a ctypes binding inside those two env classes binds (shown in INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C types only; every array argument named *_dev is a DEVICE pointer to caller-owned contiguous memory,
+ *     every *_host argument a HOST pointer; `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ *   - calls taking device pointers are asynchronous on `stream`; calls taking host pointers return after the data
+ *     has arrived (they synchronise `stream`).
+ *   - return 0 on success, a negative ilrl_status otherwise; ilrl_last_error() gives the text.
+ *   - one handle = one GPU = N envs; a handle is not thread-safe.
+ *   - there is NO CPU fallback: if no CUDA device is usable ilrl_create fails with ILRL_ERR_CUDA.
+ * Layouts: observations [N,70] (low) / [N,44] (high) row-major fp32, actions [N,17] / [N,2] fp32, reward [N] fp32,
+ * done [N] uint8, terms [N,12] fp32 (ILRL_T_* order, ilrl_constants.h), phys [N,47] and envf [N,28] fp32
+ * (ILRL_PHYS_WORDS / ILRL_E_* order).
+ */
+#ifndef ILRL_H
+#define ILRL_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ilrl_env ilrl_env; /* opaque */
+
+typedef enum {
+  ILRL_OK = 0,
+  ILRL_ERR_ARG = -1,   /* bad argument (NULL, out of range, clip not loaded, wrong mode) */
+  ILRL_ERR_CUDA = -2,  /* CUDA runtime error or no device */
+  ILRL_ERR_STATE = -3  /* call order violated (e.g. step before every clip id has a loaded clip) */
+} ilrl_status;
+
+typedef struct {
+  int32_t device;         /* CUDA ordinal */
+  int32_t num_envs;       /* N */
+  int32_t mode;           /* 0 = LowLevelHumanoidEnv, 1 = HierarchicalHumanoidEnv */
+  int32_t auto_reset;     /* 1: an env that finishes is reset inside the same step kernel (obs = first obs of the
+                             new episode, done = 1); 0: the caller resets, as the reference env does (Q19) */
+  uint64_t seed;          /* Philox key for start frames, headings and re-sampled targets */
+  int32_t skip_frame;     /* 2  REF low_level_env.py:162 */
+  int32_t max_timestep;   /* 3000 REF low_level_env.py:73 */
+  int32_t step_per_level; /* 5  REF hier_env.py:58 */
+  int32_t reserved;
+} ilrl_config;
+
+int ilrl_create(const ilrl_config* cfg, ilrl_env** out);
+void ilrl_destroy(ilrl_env* env);
+const char* ilrl_last_error(const ilrl_env* env); /* env may be NULL: error of the last failed ilrl_create */
+
+/* Stage one motion clip (the four CSV tables the reference reads at REF low_level_env.py:58-71) once in HBM.
+ * Row-major host fp32; max_frame as the reference computes it (len(pos) - 1, REF low_level_env.py:80-82) — callers
+ * clamp it for motion13_13 whose velocity table is short (declared divergence). clip in [0, 8). */
+int ilrl_load_clip(ilrl_env* env, int32_t clip, const float* pos14_host, int32_t n_pos, const float* rel14_host,
+                   int32_t n_rel, const float* vel14_host, int32_t n_vel, const float* ep27_host, int32_t n_ep,
+                   int32_t max_frame);
+/* Which clip each env imitates (`reference_name` / `selected_motion`). clip_of_env_host[N]; NULL = all envs clip 0. */
+int ilrl_set_clip_ids(ilrl_env* env, const int32_t* clip_of_env_host);
+
+/* reset()/resetFromFrame() for the envs whose mask byte is non-zero (mask_dev NULL = all).
+ * start_frame_dev / target_deg_dev / reset_yaw_deg_dev: per-env overrides, NULL = drawn as the reference draws them
+ * (start frame U{0..max_frame-6}, heading U{-180..179} deg; reset_yaw 0 in low mode, U{-180..179} in hier mode).
+ * obs_dev: [N,70] in low mode, [N,44] (high-level obs) in hier mode; rows of unmasked envs are left untouched. */
+int ilrl_reset(ilrl_env* env, const uint8_t* mask_dev, const int32_t* start_frame_dev, const int32_t* target_deg_dev,
+               const float* reset_yaw_deg_dev, float* obs_dev, void* stream);
+
+/* One low-level env step for every env: apply_action -> 4 physics substeps -> calc_state -> reward -> frame advance
+ * -> target bookkeeping -> observation -> termination (-> reset if auto_reset).  terms_dev may be NULL.
+ * In hier mode envs that are waiting for a high-level action are skipped (done 0, reward 0, obs row untouched) and
+ * the high-level outputs are kept inside the handle until ilrl_high_readout. */
+int ilrl_step(ilrl_env* env, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+              float* terms_dev, void* stream);
+
+/* Same step through HOST buffers: copies the actions up, runs the step, copies obs/reward/done back and waits.
+ * This is the call the reference-facing Python env classes make (end-to-end path measured by bench.py "e2e"). */
+int ilrl_step_host(ilrl_env* env, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host,
+                   float* terms_host, void* stream);
+
+/* hier mode: high-level agent's action (cos, sin of the heading) for every env that is waiting for one; the others
+ * ignore their row.  low_obs_dev [N,70]: the low-level obs the reference returns from high_level_step. */
+int ilrl_high_step(ilrl_env* env, const float* action2_dev, float* low_obs_dev, void* stream);
+/* hier mode: high-level obs [N,44], reward [N] and flags [N] (bit0 = episode ended this step, bit1 = high-level
+ * agent present in the reference's returned dicts, bit2 = env is now waiting for a high-level action). */
+int ilrl_high_readout(ilrl_env* env, float* high_obs_dev, float* high_reward_dev, uint8_t* high_flags_dev,
+                      void* stream);
+
+/* Parity harness: read / overwrite the full per-env state (AoS fp32 as documented above). */
+int ilrl_get_state(ilrl_env* env, float* phys_dev, float* envf_dev, void* stream);
+int ilrl_set_state(ilrl_env* env, const float* phys_dev, const float* envf_dev, void* stream);
+/* Parity harness: the random heading the next target re-sampling uses, per env (INT32_MIN entry = draw normally);
+ * NULL clears the override.  The pointer must stay valid until cleared. */
+int ilrl_set_forced_target_deg(ilrl_env* env, const int32_t* deg_dev);
+/* Parity harness (K3): everything ilrl_step does EXCEPT the physics, on the state currently held. */
+int ilrl_step_no_physics(ilrl_env* env, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
+                         float* terms_dev, void* stream);
+/* Parity harness: physics only (one env step = 4 substeps) with joint-order torques [N,17]; no env bookkeeping. */
+int ilrl_physics_only(ilrl_env* env, const float* torque_dev, void* stream);
+/* calcEndPointScore (REF low_level_env.py:361-382; not on any step path, used by param_check.py): score [N]. */
+int ilrl_endpoint_score(ilrl_env* env, float* score_dev, void* stream);
+
+/* Episode statistics accumulated on the device since the last call (then zeroed): stats16_dev[16] =
+ * {episodes, sum return, sum length, steps, sum reward, sum of the 11 first terms}.  The caller all-reduces the 16
+ * floats across ranks (NCCL sum) — the only collective of the path. */
+int ilrl_stats(ilrl_env* env, float* stats16_dev, void* stream);
+
+/* How many kernels of this library have been launched through the handle (bench.py "gpu_launches"). */
+int64_t ilrl_launch_count(const ilrl_env* env);
+/* Time of the step kernels only, measured with CUDA events on `stream` around each ilrl_step since the last call:
+ * returns accumulated milliseconds and the number of timed launches, then clears both. Enable with on = 1. */
+int ilrl_kernel_timing(ilrl_env* env, int32_t on, float* ms_out, int64_t* launches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

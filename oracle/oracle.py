@@ -15,12 +15,13 @@ _ROOT = os.path.dirname(_HERE)
 _SO = os.path.join(_HERE, "_build", "libilrl_oracle.so")
 _DATA = os.path.join(_ROOT, "imitation-learning-rl_b200", "data")
 
-PHYS_WORDS, ENV_WORDS, TERM_WORDS = 47, 26, 12
+PHYS_WORDS, ENV_WORDS, TERM_WORDS = 47, 28, 12
 CLIPS = ["motion02_04", "motion08_03", "motion09_03", "motion13_13"]
 # envf word indices (ilrl_constants.h)
 (E_FRAME, E_CLIP, E_T, E_TARGET_X, E_TARGET_Y, E_START_X, E_START_Y, E_SEP_X, E_SEP_Y, E_SEP_Z, E_ROBOT_X, E_ROBOT_Y,
  E_HLDEG, E_WALK_X, E_WALK_Y, E_LOW_TARGET_SCORE, E_JOINT_SCORE, E_JVEL_SCORE, E_POSTURE_SCORE, E_OBS_SIN, E_OBS_COS,
- E_STEPS_REMAINING, E_CUM_DRIFT, E_HIGH_TARGET_SCORE, E_CUM_ALIVE, E_HIGH_PENDING) = range(26)
+ E_STEPS_REMAINING, E_CUM_DRIFT, E_HIGH_TARGET_SCORE, E_CUM_ALIVE, E_HIGH_PENDING, E_EP_RETURN,
+ E_EP_LEN) = range(28)
 
 
 def build(force=False):
@@ -172,7 +173,8 @@ class OracleEnv:
 
     def set(self, phys, envf):
         p = np.ascontiguousarray(phys, dtype=np.float64)
-        e = np.ascontiguousarray(envf, dtype=np.float64)
+        e = np.zeros(ENV_WORDS)
+        e[:len(envf)] = envf  # golden fixtures carry the first 26 words
         self.L.ilrl_oracle_env_set(self.h, _d(p), _d(e))
 
     def low_step(self, action, rand_deg=0, skip_physics=False):

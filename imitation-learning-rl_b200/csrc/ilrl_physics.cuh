@@ -46,6 +46,42 @@ __device__ constexpr int kSphereLink[NS] = ILRL_SPHERE_LINK;
 __device__ constexpr float kSphereC[NS * 3] = ILRL_SPHERE_C;
 __device__ constexpr float kSphereR[NS] = ILRL_SPHERE_R;
 
+// ---- derived tree tables (compile-time) and the loop policy for per-link loops
+// ILRL_UNROLL_LINKS = 1: loops over links/bodies are fully unrolled (tables fold into immediates, ~370 KB of SASS);
+//                     0: they stay rolled and index the tables at run time (compact code that fits the instruction
+//                        caches; the index is warp-uniform).  See DESIGN.md "Kernel generations".
+#ifndef ILRL_UNROLL_LINKS
+#define ILRL_UNROLL_LINKS 1
+#endif
+#if ILRL_UNROLL_LINKS
+#define ILRL_LINK_LOOP _Pragma("unroll")
+#else
+#define ILRL_LINK_LOOP _Pragma("unroll 1")
+#endif
+struct TreeTables {
+  int bodyJ0[NB], bodyNJ[NB];   // first joint / number of joints of a body
+  int linkB0[NJ], linkB1[NJ];   // bodies carried by a link (-1: none)
+  int leaf[NJ];                 // link has no child link
+  int bodyIdent[NB];            // body frame has no fixed rotation relative to its parent
+  constexpr TreeTables() : bodyJ0(), bodyNJ(), linkB0(), linkB1(), leaf(), bodyIdent() {
+    constexpr int jb[NJ] = ILRL_JOINT_BODY;
+    constexpr int jp[NJ] = ILRL_JOINT_PARENT;
+    constexpr int bl[NB] = ILRL_BODY_LINK;
+    constexpr double bq[NB * 4] = ILRL_BODY_QUAT;
+    for (int b = 0; b < NB; b++) {
+      bodyJ0[b] = 0; bodyNJ[b] = 0;
+      for (int j = NJ - 1; j >= 0; j--) if (jb[j] == b) { bodyJ0[b] = j; bodyNJ[b]++; }
+      bodyIdent[b] = (bq[4 * b] == 0.0 && bq[4 * b + 1] == 0.0 && bq[4 * b + 2] == 0.0) ? 1 : 0;
+    }
+    for (int j = 0; j < NJ; j++) {
+      linkB0[j] = -1; linkB1[j] = -1; leaf[j] = 1;
+      for (int b = 1; b < NB; b++) if (bl[b] == j) { if (linkB0[j] < 0) linkB0[j] = b; else linkB1[j] = b; }
+      for (int c = 0; c < NJ; c++) if (jp[c] == j) leaf[j] = 0;
+    }
+  }
+};
+__device__ constexpr TreeTables kTree{};
+
 // ---- small vector helpers
 struct V3 { float x, y, z; };
 __device__ __forceinline__ V3 mk(float x, float y, float z) { V3 r; r.x = x; r.y = y; r.z = z; return r; }
@@ -147,12 +183,11 @@ __device__ __forceinline__ void fk(const Phys& s, Work& k) {
   quat2mat(s.quat[0], s.quat[1], s.quat[2], s.quat[3], k.R[0]);
   k.o[0][0] = k.o[0][1] = k.o[0][2] = 0.f;
   float sx = 0.f, sy = 0.f;
-#pragma unroll
+  ILRL_LINK_LOOP
   for (int b = 1; b < NB; b++) {
     const int p = kBodyParent[b];
     float Rc[9];
-    const bool ident = kBodyQuat[4 * b] == 0.f && kBodyQuat[4 * b + 1] == 0.f && kBodyQuat[4 * b + 2] == 0.f;
-    if (ident) {
+    if (kTree.bodyIdent[b]) {
 #pragma unroll
       for (int i = 0; i < 9; i++) Rc[i] = k.R[p][i];
     } else {
@@ -161,9 +196,8 @@ __device__ __forceinline__ void fk(const Phys& s, Work& k) {
       mm(k.R[p], Q, Rc);
     }
     V3 oc = ld3(k.o[p]) + mv(k.R[p], mk(kBodyPos[3 * b], kBodyPos[3 * b + 1], kBodyPos[3 * b + 2]));
-#pragma unroll
-    for (int j = 0; j < NJ; j++) {
-      if (kJointBody[j] != b) continue;
+    ILRL_LINK_LOOP
+    for (int j = kTree.bodyJ0[b]; j < kTree.bodyJ0[b] + kTree.bodyNJ[b]; j++) {
       const V3 an = mk(kJointAnchor[3 * j], kJointAnchor[3 * j + 1], kJointAnchor[3 * j + 2]);
       const V3 ax = mk(kJointAxis[3 * j], kJointAxis[3 * j + 1], kJointAxis[3 * j + 2]);
       V3 rw = oc + mv(Rc, an);
@@ -285,7 +319,7 @@ constexpr int kPelvisLink = 2;
 __device__ __forceinline__ void aba(const Phys& s, const float* tau, Work& k, SV& a0, float* qdd) {
   SV V0; V0.a = ld3(s.w); V0.l = ld3(s.v);
   // outward: link velocities and velocity-product accelerations
-#pragma unroll
+  ILRL_LINK_LOOP
   for (int j = 0; j < NJ; j++) {
     const int p = kJointParent[j];
     SV Vp = p < 0 ? V0 : ldsv(k.V[p]);
@@ -298,17 +332,13 @@ __device__ __forceinline__ void aba(const Phys& s, const float* tau, Work& k, SV
   SV pcur, ppel, pbas, pb;
   pel.zero(); ppel.a = ppel.l = mk(0, 0, 0);
   body_inertia_bias(k, 0, V0, bas, pbas);
-#pragma unroll
+  ILRL_LINK_LOOP
   for (int j = NJ - 1; j >= 0; j--) {
-    if (is_leaf(j)) { cur.zero(); pcur.a = pcur.l = mk(0, 0, 0); }
+    if (kTree.leaf[j]) { cur.zero(); pcur.a = pcur.l = mk(0, 0, 0); }
     if (j == kPelvisLink) { cur = pel; pcur = ppel; }
     SV Vj = ldsv(k.V[j]);
-#pragma unroll
-    for (int b = 1; b < NB; b++) {
-      if (kBodyLink[b] != j) continue;
-      body_inertia_bias(k, b, Vj, Ib, pb);
-      cur.add(Ib); pcur = pcur + pb;
-    }
+    if (kTree.linkB0[j] >= 0) { body_inertia_bias(k, kTree.linkB0[j], Vj, Ib, pb); cur.add(Ib); pcur = pcur + pb; }
+    if (kTree.linkB1[j] >= 0) { body_inertia_bias(k, kTree.linkB1[j], Vj, Ib, pb); cur.add(Ib); pcur = pcur + pb; }
     SV S = ldsv(k.S[j]);
     SV U = imul(cur, S);
     float D = sdot(S, U);
@@ -327,7 +357,7 @@ __device__ __forceinline__ void aba(const Phys& s, const float* tau, Work& k, SV
   a0 = chol6_solve(k.L0, np0);
   // outward: accelerations
   SV acur = a0, apel = a0;
-#pragma unroll
+  ILRL_LINK_LOOP
   for (int j = 0; j < NJ; j++) {
     const int p = kJointParent[j];
     SV ap = p < 0 ? a0 : (p == kPelvisLink ? apel : acur);
@@ -364,7 +394,7 @@ __device__ __forceinline__ void unit_response(const Work& k, int link, SV F, int
   SV a0 = chol6_solve(k.L0, npf);
   resp[0] = a0.a.x; resp[1] = a0.a.y; resp[2] = a0.a.z; resp[3] = a0.l.x; resp[4] = a0.l.y; resp[5] = a0.l.z;
   SV acur = a0, apel = a0;
-#pragma unroll
+  ILRL_LINK_LOOP
   for (int j = 0; j < NJ; j++) {
     const int p = kJointParent[j];
     SV ap = p < 0 ? a0 : (p == kPelvisLink ? apel : acur);
@@ -438,7 +468,7 @@ __device__ __forceinline__ void substep(Phys& s, const float* tau, Work& k, Row*
     float sd[NS];
     uint32_t act = 0;
     int nact = 0;
-#pragma unroll
+    ILRL_LINK_LOOP
     for (int i = 0; i < NS; i++) {
       const int b = kSphereBody[i];
       float cz = k.o[b][2] + k.R[b][6] * kSphereC[3 * i] + k.R[b][7] * kSphereC[3 * i + 1] + k.R[b][8] * kSphereC[3 * i + 2];

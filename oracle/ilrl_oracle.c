@@ -7,7 +7,7 @@
  * What it restates, and how each part is pinned:
  *   (A) env logic — reset / step / reward terms / frame indexing / target bookkeeping / observation / termination /
  *       hierarchical protocol of REF low_level_env.py:174-526 and REF hier_env.py:174-642 (+ math_util.py:20-27).
- *       PINNED: tests/golden/*.npz hold traces of the UNMODIFIED reference Python (imported from /root/reference under
+ *       PINNED: the .npz files under tests/golden/ hold traces of the UNMODIFIED reference Python (imported from /root/reference under
  *       oracle/ref_shim.py) and tests/test_oracle_golden.py replays them through this file.
  *   (B) calc_state / apply_action of the un-vendored pybullet_envs WalkerBase + REF humanoid.py:12-60 — restated
  *       from memory of the upstream source; pinned only by the reference notebook outputs listed in SURVEY.md §4
@@ -850,3 +850,37 @@ const double* ilrl_oracle_env_phys(orc_env* v) { return v->phys; }
 double* ilrl_oracle_env_phys_mut(orc_env* v) { return v->phys; }
 void ilrl_oracle_env_refresh(orc_env* v) { do_calc_state(v); }
 void ilrl_oracle_env_terms(const orc_env* v, double* terms) { memcpy(terms, v->terms, sizeof v->terms); }
+
+/* ------------------------------------------------------------------ CPU baseline driver (bench.py only)
+ * Advance `n` low-level envs by `steps` env steps each with uniform random actions in [-1,1] and reset-on-done,
+ * entirely in C (no Python in the loop).  Returns the number of env steps executed; *episodes gets the resets. */
+static uint64_t sm64(uint64_t* s) {
+  uint64_t z = (*s += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+long ilrl_oracle_rollout(orc_env** envs, int n, int steps, uint64_t seed, long* episodes, double* reward_sum) {
+  uint64_t st = seed * 0x2545F4914F6CDD1Dull + 1;
+  long done_steps = 0, eps = 0;
+  double rs = 0;
+  for (int t = 0; t < steps; t++)
+    for (int i = 0; i < n; i++) {
+      orc_env* v = envs[i];
+      double a[NJ], obs[70], rew;
+      for (int k = 0; k < NJ; k++) a[k] = (double)(sm64(&st) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+      int deg = (int)(sm64(&st) % 360) - 180;
+      int done = ilrl_oracle_low_step(v, a, deg, 0, obs, &rew);
+      rs += rew;
+      done_steps++;
+      if (done) {
+        int sf = (int)(sm64(&st) % (uint64_t)(v->clip.max_frame - 5));
+        int td = (int)(sm64(&st) % 360) - 180;
+        ilrl_oracle_env_reset(v, sf, 0.0, td, obs);
+        eps++;
+      }
+    }
+  if (episodes) *episodes = eps;
+  if (reward_sum) *reward_sum = rs;
+  return done_steps;
+}

@@ -227,11 +227,8 @@ __device__ __forceinline__ void fk(const Phys& s, Work& k) {
 
 // rigid-body spatial inertia (about the reference point, world axes) of body b and its bias force
 // p = V x* (I V) - f_ext  with gravity and Bullet's velocity damping as external forces.
-__device__ __forceinline__ void body_inertia_bias(const Work& k, int b, SV V, Inertia& I, SV& pb) {
-  const float m = kBodyMass[b];
-  const float* R = k.R[b];
-  V3 c = ld3(k.o[b]);
-  const float ix = kBodyInertia[3 * b], iy = kBodyInertia[3 * b + 1], iz = kBodyInertia[3 * b + 2];
+__device__ __forceinline__ void rigid_inertia_bias(const float* R, V3 c, float m, float ix, float iy, float iz, SV V,
+                                                   Inertia& I, SV& pb) {
   // Ic = R diag(i) R^T
   float Ic[6];
   Ic[0] = ix * R[0] * R[0] + iy * R[1] * R[1] + iz * R[2] * R[2];
@@ -260,6 +257,10 @@ __device__ __forceinline__ void body_inertia_bias(const Work& k, int b, SV V, In
   V3 N = mk(-ka * Iw.x, -ka * Iw.y, -ka * Iw.z);
   pb.a = pb.a - (N + cross(c, F));
   pb.l = pb.l - F;
+}
+__device__ __forceinline__ void body_inertia_bias(const Work& k, int b, SV V, Inertia& I, SV& pb) {
+  rigid_inertia_bias(k.R[b], ld3(k.o[b]), kBodyMass[b], kBodyInertia[3 * b], kBodyInertia[3 * b + 1],
+                     kBodyInertia[3 * b + 2], V, I, pb);
 }
 
 // Cholesky of the 6x6 SPD base inertia [[A,B],[B^T,C]] -> packed lower L (row-major: L[i*(i+1)/2 + j])

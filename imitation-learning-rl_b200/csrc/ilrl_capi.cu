@@ -17,11 +17,13 @@
 #include <string>
 
 #include "../../include/ilrl.h"
-#include "ilrl_env.cuh"
+#include "ilrl_quad.cuh"
 
 namespace ilrl {
 
-constexpr int BLOCK = 64;  // envs (= threads) per CTA
+constexpr int BLOCK = 64;  // threads per CTA of the thread-per-env service kernels (reset, high step, harness)
+using quad::QE;
+using quad::QT;
 
 struct StepArgs {
   int n;
@@ -43,7 +45,7 @@ struct StepArgs {
   uint8_t* high_flags; // [n]
   const int32_t* forced_deg;  // [n] or null
   float* stats;        // [16] or null
-  Row* rows;           // [n][MAXROWS] scratch in global memory (per-thread constraint rows)
+  float* gscr;         // [n][GROWS][ROWW] overflow scratch for constraint rows beyond the shared-memory budget
   ClipDesc clips[MAX_CLIPS];
 };
 
@@ -82,160 +84,194 @@ __device__ __forceinline__ void store_state(const StepArgs& a, int i, const Phys
   for (int k = 0; k < ILRL_ENV_WORDS; k++) e[k * n] = w.e[k];
 }
 
-// stage a [rows_in_block, W] row-major tile between global memory and per-thread rows through shared memory
-template <int W>
-__device__ __forceinline__ void tile_load(const float* g, int base, int n, float* sm, float* mine) {
-  const int cnt = min(BLOCK, n - base) * W;
-  for (int t = threadIdx.x; t < cnt; t += BLOCK) sm[t] = g[(size_t)base * W + t];
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < W; k++) mine[k] = sm[threadIdx.x * W + k];  // W odd (17) -> conflict-free
-  __syncthreads();
-}
-template <int W>
-__device__ __forceinline__ void tile_store(float* g, int base, int n, float* sm, const float* mine, bool valid) {
-  __syncthreads();
-  if (valid) {
-#pragma unroll
-    for (int k = 0; k < W; k++) sm[threadIdx.x * (W + 1) + k] = mine[k];  // pad to an odd stride
-  }
-  __syncthreads();
-  const int cnt = min(BLOCK, n - base) * W;
-  for (int t = threadIdx.x; t < cnt; t += BLOCK) {
-    int r = t / W, c = t - r * W;
-    g[(size_t)base * W + t] = sm[r * (W + 1) + c];
-  }
+// shared-memory setup common to the quad kernels: role constants in, response scratch zeroed
+__device__ __forceinline__ void quad_smem_init(quad::Smem& sm) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&quad::kRoles);
+  uint32_t* dst = &sm.role[0][0];
+  for (int t = threadIdx.x; t < 4 * quad::ROLE_WORDS; t += QT) dst[t] = src[t];
+  float* z = &sm.scr[0][0][0];
+  for (int t = threadIdx.x; t < QT * 3 * NJ; t += QT) z[t] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------ K1: fused step
 // MODE 0 = LowLevelHumanoidEnv.step (REF low_level_env.py:475-526), MODE 1 = HierarchicalHumanoidEnv low_level_step
-// (REF hier_env.py:355-366, 583-642).  One thread = one env.
+// (REF hier_env.py:355-366, 583-642).  Four lanes = one env (ilrl_quad.cuh): the physics substeps run distributed
+// over the quad; the env bookkeeping after them is computed redundantly by the four lanes (identical instruction
+// stream, no divergence) and the outputs are dealt to the lanes for the stores.
 template <int MODE>
-__global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs a) {
-  __shared__ float sm[BLOCK * 71];
-  const int base = blockIdx.x * BLOCK;
-  const int i = base + threadIdx.x;
+__global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  quad::Smem& sm = *reinterpret_cast<quad::Smem*>(smraw);
+  const int tid = threadIdx.x, e = tid >> 2, role = tid & 3;
+  const unsigned qm = 0xFu << ((tid & 31) & ~3);
+  const int base = blockIdx.x * QE;
+  const int i = base + e;
   const bool valid = i < a.n;
-  float act[NJ];
-  tile_load<NJ>(a.action, base, a.n, sm, act);
-  float obs[70];
+  quad_smem_init(sm);
+  {
+    const int cnt = min(QE, a.n - base) * NJ;
+    float* dst = &sm.act[0][0];
+    for (int t = tid; t < cnt; t += QT) dst[t] = a.action[(size_t)base * NJ + t];
+  }
+  __syncthreads();
+  const quad::Role& rc = *reinterpret_cast<const quad::Role*>(sm.role[role]);
   bool write_obs = false;
   float st_ep = 0.f, st_ret = 0.f, st_len = 0.f, st_steps = 0.f, st_rew = 0.f, st_terms[11];
 #pragma unroll
   for (int t = 0; t < 11; t++) st_terms[t] = 0.f;
 
-  if (valid) {
-    Phys s;
-    EnvW w;
-    load_state(a, i, s, w);
-    const bool pending = MODE == 1 && w.e[ILRL_E_HIGH_PENDING] != 0.f;
-    if (pending) {
-      a.reward[i] = 0.f; a.done[i] = 0;
-      if (a.terms) for (int t = 0; t < ILRL_TERM_WORDS; t++) a.terms[(size_t)i * ILRL_TERM_WORDS + t] = 0.f;
-    } else {
-      const ClipDesc cl = a.clips[(int)w.e[ILRL_E_CLIP]];
-      Work k;
-      Calc c;
-      float terms[ILRL_TERM_WORDS];
+  const bool pending = valid && MODE == 1 && a.envf[(size_t)ILRL_E_HIGH_PENDING * a.n + i] != 0.f;
+  if (valid && pending) {
+    if (role == 0) { a.reward[i] = 0.f; a.done[i] = 0; }
+    if (a.terms)
+      for (int t = role; t < ILRL_TERM_WORDS; t += 4) a.terms[(size_t)i * ILRL_TERM_WORDS + t] = 0.f;
+  } else if (valid) {
+    quad::QState s;
+    quad::qload(a.phys, a.n, i, rc, s);
+    float act[NJ];
 #pragma unroll
-      for (int t = 0; t < ILRL_TERM_WORDS; t++) terms[t] = 0.f;
-      // apply_action (REF humanoid.py:54-60): clip, gear x power, motor slot -> joint slot
-      float tau[NJ];
+    for (int m = 0; m < NJ; m++) act[m] = sm.act[e][m];
+    // apply_action (REF humanoid.py:54-60): clip, gear x power, motor slot -> joint slot
+    float tau_s[3], tau_l[4];
 #pragma unroll
-      for (int m = 0; m < NJ; m++) tau[kMotorJoint[m]] = kMotorGear[m] * fminf(fmaxf(act[m], -1.f), 1.f);
-      if (MODE == 1) {
-        // (Q13) robot_pos is refreshed from the PREVIOUS calc_state at the top of step()
-        fk(s, k);
-        w.e[ILRL_E_ROBOT_X] = (32.f * s.p[0] + k.sumx) * (1.f / 33.f);
-        w.e[ILRL_E_ROBOT_Y] = (32.f * s.p[1] + k.sumy) * (1.f / 33.f);
-        w.e[ILRL_E_STEPS_REMAINING] -= 1.f;
-      }
-      if (!a.skip_physics) {
-        Row* rows = a.rows + (size_t)i * MAXROWS;
+    for (int m = 0; m < 3; m++) tau_s[m] = kMotorGear[m] * fminf(fmaxf(act[m], -1.f), 1.f);  // motors 0..2 = spine joints 0..2
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      tau_l[k] = rc.motor[k] >= 0 ? rc.gear[k] * fminf(fmaxf(sm.act[e][rc.motor[k]], -1.f), 1.f) : 0.f;
+    float stale_x = 0.f, stale_y = 0.f;
+    if (MODE == 1) {
+      // (Q13) robot_pos is refreshed from the PREVIOUS calc_state at the top of step()
+      float sx, sy, fx, fy;
+      quad::qpose_sums(s, rc, qm, sx, sy, fx, fy);
+      stale_x = (32.f * s.p[0] + sx) * (1.f / 33.f);
+      stale_y = (32.f * s.p[1] + sy) * (1.f / 33.f);
+    }
+    if (!a.skip_physics) {
+      float* gscr = a.gscr + (size_t)i * quad::GROWS * quad::ROWW;
 #pragma unroll 1
-        for (int sub = 0; sub < ILRL_SUBSTEPS; sub++) substep(s, tau, k, rows, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
-      }
-      fk(s, k);
-      calc_state(s, k.sumx, k.sumy, w.e[ILRL_E_WALK_X], w.e[ILRL_E_WALK_Y], c);
-      w.e[ILRL_E_OBS_SIN] = c.obs[1]; w.e[ILRL_E_OBS_COS] = c.obs[2];
-      if (MODE == 0) { w.e[ILRL_E_ROBOT_X] = c.bx; w.e[ILRL_E_ROBOT_Y] = c.by; }
-      float reward = update_reward<MODE>(s, c, w, cl, act, terms);
-      inc_frame(w, cl, 2);
-      uint32_t ctr = a.rng[i];
-      int deg;
-      if (a.forced_deg && a.forced_deg[i] != INT_MIN) deg = a.forced_deg[i];
-      else {
-        // drawn unconditionally-looking but consumed only on a switch: peek without advancing unless used
-        uint32_t c2 = ctr;
-        deg = rand_int(a.seed, (uint32_t)i, c2, -180, 180);
-        float dist = hyp(w.e[ILRL_E_ROBOT_X] - w.e[ILRL_E_TARGET_X], w.e[ILRL_E_ROBOT_Y] - w.e[ILRL_E_TARGET_Y]);
-        if (dist <= (float)ILRL_TARGET_REACHED) ctr = c2;
-      }
-      check_target<MODE>(c, w, deg);
-      terms[ILRL_T_LOWTARGET] = w.e[ILRL_E_LOW_TARGET_SCORE];
-      bool done = check_done<MODE>(w, terms[ILRL_T_ALIVE]);
-      w.e[ILRL_E_T] += 1.f;
-      if (w.e[ILRL_E_T] >= (float)a.max_timestep) done = true;
-      w.e[ILRL_E_EP_RETURN] += reward;
-      w.e[ILRL_E_EP_LEN] += 1.f;
+      for (int sub = 0; sub < ILRL_SUBSTEPS; sub++)
+        quad::qsubstep(s, tau_s, tau_l, rc, sm, gscr, e, tid, role, qm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+    }
+    float sumx, sumy, rfx, rfy;
+    quad::qpose_sums(s, rc, qm, sumx, sumy, rfx, rfy);
+    Phys ps;
+    quad::qgather(s, rc, sm, e, role, qm, ps);
+    EnvW w;
+    {
+      const float* ew = a.envf + i;
+#pragma unroll
+      for (int k = 0; k < ILRL_ENV_WORDS; k++) w.e[k] = ew[(size_t)k * a.n];
+    }
+    if (MODE == 1) {
+      w.e[ILRL_E_ROBOT_X] = stale_x; w.e[ILRL_E_ROBOT_Y] = stale_y;
+      w.e[ILRL_E_STEPS_REMAINING] -= 1.f;
+    }
+    const ClipDesc cl = a.clips[(int)w.e[ILRL_E_CLIP]];
+    Calc c;
+    float terms[ILRL_TERM_WORDS];
+#pragma unroll
+    for (int t = 0; t < ILRL_TERM_WORDS; t++) terms[t] = 0.f;
+    calc_state(ps, sumx, sumy, w.e[ILRL_E_WALK_X], w.e[ILRL_E_WALK_Y], c);
+    w.e[ILRL_E_OBS_SIN] = c.obs[1]; w.e[ILRL_E_OBS_COS] = c.obs[2];
+    if (MODE == 0) { w.e[ILRL_E_ROBOT_X] = c.bx; w.e[ILRL_E_ROBOT_Y] = c.by; }
+    float reward = update_reward<MODE>(ps, c, w, cl, act, terms);
+    inc_frame(w, cl, 2);
+    uint32_t ctr = a.rng[i];
+    int deg;
+    if (a.forced_deg && a.forced_deg[i] != INT_MIN) deg = a.forced_deg[i];
+    else {
+      // the draw is consumed (counter advanced) only when the target actually switches
+      uint32_t c2 = ctr;
+      deg = rand_int(a.seed, (uint32_t)i, c2, -180, 180);
+      float dist = hyp(w.e[ILRL_E_ROBOT_X] - w.e[ILRL_E_TARGET_X], w.e[ILRL_E_ROBOT_Y] - w.e[ILRL_E_TARGET_Y]);
+      if (dist <= (float)ILRL_TARGET_REACHED) ctr = c2;
+    }
+    check_target<MODE>(c, w, deg);
+    terms[ILRL_T_LOWTARGET] = w.e[ILRL_E_LOW_TARGET_SCORE];
+    bool done = check_done<MODE>(w, terms[ILRL_T_ALIVE]);
+    w.e[ILRL_E_T] += 1.f;
+    if (w.e[ILRL_E_T] >= (float)a.max_timestep) done = true;
+    w.e[ILRL_E_EP_RETURN] += reward;
+    w.e[ILRL_E_EP_LEN] += 1.f;
+    float* so = sm.obs[e];
+    {
+      float obs[70];
       write_low_obs(c.obs, w, cl, obs);
-      write_obs = true;
-      uint8_t hflags = 0;
-      if (MODE == 1) {
-        if (done || w.e[ILRL_E_STEPS_REMAINING] <= 0.f) {
-          update_reward_high(w, terms, a.step_per_level);
-          a.high_reward[i] = terms[ILRL_T_DHIGHTARGET] * 0.3f + terms[ILRL_T_DRIFT] * 0.7f;
-          float ho[44];
-          write_high_obs(c, w, ho);
-          for (int t = 0; t < 44; t++) a.high_obs[(size_t)i * 44 + t] = ho[t];
-          w.e[ILRL_E_CUM_ALIVE] = 0.f;
-          hflags = done ? 3 : 2;
-          if (!done) { w.e[ILRL_E_HIGH_PENDING] = 1.f; hflags |= 4; }
-        }
-        terms[ILRL_T_HIGHTARGET] = w.e[ILRL_E_HIGH_TARGET_SCORE];
+#pragma unroll
+      for (int t = 0; t < 70; t++) if ((t & 3) == role) so[t] = obs[t];
+    }
+    write_obs = true;
+    uint8_t hflags = 0;
+    if (MODE == 1) {
+      if (done || w.e[ILRL_E_STEPS_REMAINING] <= 0.f) {
+        update_reward_high(w, terms, a.step_per_level);
+        if (role == 0) a.high_reward[i] = terms[ILRL_T_DHIGHTARGET] * 0.3f + terms[ILRL_T_DRIFT] * 0.7f;
+        float ho[44];
+        write_high_obs(c, w, ho);
+#pragma unroll
+        for (int t = 0; t < 44; t++) if ((t & 3) == role) a.high_obs[(size_t)i * 44 + t] = ho[t];
+        w.e[ILRL_E_CUM_ALIVE] = 0.f;
+        hflags = done ? 3 : 2;
+        if (!done) { w.e[ILRL_E_HIGH_PENDING] = 1.f; hflags |= 4; }
       }
-      a.reward[i] = reward;
-      a.done[i] = done ? 1 : 0;
-      if (a.terms) for (int t = 0; t < ILRL_TERM_WORDS; t++) a.terms[(size_t)i * ILRL_TERM_WORDS + t] = terms[t];
+      terms[ILRL_T_HIGHTARGET] = w.e[ILRL_E_HIGH_TARGET_SCORE];
+    }
+    if (role == 0) { a.reward[i] = reward; a.done[i] = done ? 1 : 0; }
+    if (a.terms) {
+#pragma unroll
+      for (int t = 0; t < ILRL_TERM_WORDS; t++) if ((t & 3) == role) a.terms[(size_t)i * ILRL_TERM_WORDS + t] = terms[t];
+    }
+    if (role == 0) {
       st_steps = 1.f; st_rew = reward;
 #pragma unroll
       for (int t = 0; t < 11; t++) st_terms[t] = terms[t];
-      if (done) {
-        st_ep = 1.f; st_ret = w.e[ILRL_E_EP_RETURN]; st_len = w.e[ILRL_E_EP_LEN];
-        if (a.auto_reset) {
-          int sf = rand_int(a.seed, (uint32_t)i, ctr, 0, cl.max_frame - 5);
-          float yaw = MODE == 1 ? (float)rand_int(a.seed, (uint32_t)i, ctr, -180, 180) : 0.f;
-          int tdeg = rand_int(a.seed, (uint32_t)i, ctr, -180, 180);
-          reset_env<MODE>(s, w, cl, sf, yaw, tdeg, a.step_per_level, k, c);
-          if (MODE == 0) write_low_obs(c.obs, w, cl, obs);
-          else {
-            float ho[44];
-            write_high_obs(c, w, ho);
-            for (int t = 0; t < 44; t++) a.high_obs[(size_t)i * 44 + t] = ho[t];
-            hflags |= 4;
-          }
+    }
+    if (done) {
+      if (role == 0) { st_ep = 1.f; st_ret = w.e[ILRL_E_EP_RETURN]; st_len = w.e[ILRL_E_EP_LEN]; }
+      if (a.auto_reset) {
+        int sf = rand_int(a.seed, (uint32_t)i, ctr, 0, cl.max_frame - 5);
+        float yaw = MODE == 1 ? (float)rand_int(a.seed, (uint32_t)i, ctr, -180, 180) : 0.f;
+        int tdeg = rand_int(a.seed, (uint32_t)i, ctr, -180, 180);
+        ResetCtx rx;
+        reset_pose<MODE>(ps, w, cl, sf, yaw, tdeg, rx);
+        quad::qscatter(ps, rc, sm, e, role, qm, s);
+        quad::qpose_sums(s, rc, qm, sumx, sumy, rfx, rfy);
+        reset_finish<MODE>(ps, w, cl, rx, rfx, rfy, sumx, sumy, a.step_per_level, c);
+        if (MODE == 0) {
+          float obs[70];
+          write_low_obs(c.obs, w, cl, obs);
+#pragma unroll
+          for (int t = 0; t < 70; t++) if ((t & 3) == role) so[t] = obs[t];
+        } else {
+          float ho[44];
+          write_high_obs(c, w, ho);
+#pragma unroll
+          for (int t = 0; t < 44; t++) if ((t & 3) == role) a.high_obs[(size_t)i * 44 + t] = ho[t];
+          hflags |= 4;
         }
       }
+    }
+    if (role == 0) {
       if (MODE == 1) a.high_flags[i] = hflags;
       a.rng[i] = ctr;
-      store_state(a, i, s, w);
+    }
+    quad::qstore_phys(a.phys, a.n, i, role, ps);
+    {
+      float* ew = a.envf + i;
+#pragma unroll
+      for (int k = 0; k < ILRL_ENV_WORDS; k++) if ((k & 3) == role) ew[(size_t)k * a.n] = w.e[k];
     }
   }
-  // observations: only envs that stepped write their row (pending hier envs keep theirs)
+  // observations: only envs that stepped write their row (pending hier envs keep theirs); coalesced CTA store
   {
+    __shared__ unsigned int wrote[QT / 32];
+    unsigned int okmask = __ballot_sync(0xffffffffu, write_obs);
+    if ((tid & 31) == 0) wrote[tid >> 5] = okmask;
     __syncthreads();
-    if (write_obs) {
-#pragma unroll
-      for (int t = 0; t < 70; t++) sm[threadIdx.x * 71 + t] = obs[t];
-    }
-    unsigned long long okmask = __ballot_sync(0xffffffffu, write_obs);
-    __shared__ unsigned int wrote[BLOCK / 32];
-    if ((threadIdx.x & 31) == 0) wrote[threadIdx.x >> 5] = (unsigned int)okmask;
-    __syncthreads();
-    const int cnt = min(BLOCK, a.n - base) * 70;
-    for (int t = threadIdx.x; t < cnt; t += BLOCK) {
+    const int cnt = min(QE, a.n - base) * 70;
+    for (int t = tid; t < cnt; t += QT) {
       int r = t / 70, cc = t - r * 70;
-      if ((wrote[r >> 5] >> (r & 31)) & 1u) a.obs[(size_t)base * 70 + t] = sm[r * 71 + cc];
+      if ((wrote[r >> 3] >> ((r & 7) * 4)) & 1u) a.obs[(size_t)base * 70 + t] = sm.obs[r][cc];
     }
   }
   // K5: episode / reward statistics -> one atomicAdd per warp per slot
@@ -248,7 +284,7 @@ __global__ void __launch_bounds__(BLOCK) step_kernel(const StepArgs a) {
       float x = v[t];
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-      if ((threadIdx.x & 31) == 0 && x != 0.f) atomicAdd(a.stats + t, x);
+      if ((tid & 31) == 0 && x != 0.f) atomicAdd(a.stats + t, x);
     }
   }
 }
@@ -358,18 +394,29 @@ __global__ void clip_ids_kernel(StateView v, const int32_t* ids) {
   if (i >= v.n) return;
   v.envf[(size_t)ILRL_E_CLIP * v.n + i] = ids ? (float)ids[i] : 0.f;
 }
-__global__ void __launch_bounds__(BLOCK) physics_only_kernel(StateView v, const float* torque, Row* rows, int nsub, float* dbg, int dbg_env) {
-  const int i = blockIdx.x * BLOCK + threadIdx.x;
+__global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const float* torque, float* gscr_all, int nsub) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  quad::Smem& sm = *reinterpret_cast<quad::Smem*>(smraw);
+  const int tid = threadIdx.x, e = tid >> 2, role = tid & 3;
+  const unsigned qm = 0xFu << ((tid & 31) & ~3);
+  const int i = blockIdx.x * QE + e;
+  quad_smem_init(sm);
+  __syncthreads();
   if (i >= v.n) return;
-  StepArgs a; a.n = v.n; a.phys = v.phys; a.envf = v.envf;
-  Phys s; EnvW w;
-  load_state(a, i, s, w);
-  float tau[NJ];
-  for (int j = 0; j < NJ; j++) tau[j] = torque[(size_t)i * NJ + j];
-  Work k;
+  const quad::Role& rc = *reinterpret_cast<const quad::Role*>(sm.role[role]);
+  quad::QState s;
+  quad::qload(v.phys, v.n, i, rc, s);
+  float tau_s[3], tau_l[4];
+#pragma unroll
+  for (int k = 0; k < 3; k++) tau_s[k] = torque[(size_t)i * NJ + k];
+#pragma unroll
+  for (int k = 0; k < 4; k++) tau_l[k] = rc.j[k] >= 0 ? torque[(size_t)i * NJ + rc.j[k]] : 0.f;
+  float* gscr = gscr_all + (size_t)i * quad::GROWS * quad::ROWW;
   for (int sub = 0; sub < nsub; sub++)
-    substep(s, tau, k, rows + (size_t)i * MAXROWS, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), (dbg && i == dbg_env) ? dbg : nullptr);
-  store_state(a, i, s, w);
+    quad::qsubstep(s, tau_s, tau_l, rc, sm, gscr, e, tid, role, qm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+  Phys ps;
+  quad::qgather(s, rc, sm, e, role, qm, ps);
+  quad::qstore_phys(v.phys, v.n, i, role, ps);
 }
 struct EpArgs { StateView v; float* score; ClipDesc clips[MAX_CLIPS]; };
 __global__ void __launch_bounds__(BLOCK) endpoint_kernel(const EpArgs a) {
@@ -398,7 +445,7 @@ struct ilrl_env {
   float* phys = nullptr;
   float* envf = nullptr;
   uint32_t* rng = nullptr;
-  Row* rows = nullptr;
+  float* gscr = nullptr;
   float* high_obs = nullptr;
   float* high_reward = nullptr;
   uint8_t* high_flags = nullptr;
@@ -413,8 +460,6 @@ struct ilrl_env {
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_terms = nullptr;
   uint8_t* d_done = nullptr;
   int substeps = ILRL_SUBSTEPS;  // harness only (ilrl_debug_substeps)
-  float* dbg = nullptr;          // harness only (ilrl_debug_dump)
-  int dbg_env = 0;
   int64_t launches = 0;
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -470,7 +515,10 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMalloc(&env->phys, sizeof(float) * ILRL_PHYS_WORDS * n));
   CKC(cudaMalloc(&env->envf, sizeof(float) * ILRL_ENV_WORDS * n));
   CKC(cudaMalloc(&env->rng, sizeof(uint32_t) * n));
-  CKC(cudaMalloc(&env->rows, sizeof(Row) * (size_t)MAXROWS * n));
+  CKC(cudaMalloc(&env->gscr, sizeof(float) * (size_t)quad::GROWS * quad::ROWW * n));
+  CKC(cudaFuncSetAttribute(step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(quad::Smem)));
+  CKC(cudaFuncSetAttribute(step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(quad::Smem)));
+  CKC(cudaFuncSetAttribute(physics_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(quad::Smem)));
   CKC(cudaMalloc(&env->high_obs, sizeof(float) * 44 * n));
   CKC(cudaMalloc(&env->high_reward, sizeof(float) * n));
   CKC(cudaMalloc(&env->high_flags, n));
@@ -493,7 +541,7 @@ void ilrl_destroy(ilrl_env* env) {
   if (!env) return;
   cudaSetDevice(env->cfg.device);
   cudaDeviceSynchronize();
-  cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->rows);
+  cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr);
   cudaFree(env->high_obs); cudaFree(env->high_reward); cudaFree(env->high_flags); cudaFree(env->stats);
   for (int c = 0; c < MAX_CLIPS; c++) cudaFree(env->clip_mem[c]);
   cudaFreeHost(env->h_action); cudaFreeHost(env->h_obs); cudaFreeHost(env->h_reward); cudaFreeHost(env->h_terms);
@@ -586,12 +634,13 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
   a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.terms = terms;
   a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
-  a.forced_deg = env->forced_deg; a.stats = env->stats; a.rows = env->rows;
+  a.forced_deg = env->forced_deg; a.stats = env->stats; a.gscr = env->gscr;
   memcpy(a.clips, env->clips, sizeof a.clips);
   cudaStream_t st = (cudaStream_t)stream;
   if (env->timing) CK(cudaEventRecord(env->ev0, st));
-  if (env->cfg.mode == 0) step_kernel<0><<<nblk(env->n), BLOCK, 0, st>>>(a);
-  else step_kernel<1><<<nblk(env->n), BLOCK, 0, st>>>(a);
+  const int qblk = (env->n + QE - 1) / QE;
+  if (env->cfg.mode == 0) step_kernel<0><<<qblk, QT, sizeof(quad::Smem), st>>>(a);
+  else step_kernel<1><<<qblk, QT, sizeof(quad::Smem), st>>>(a);
   env->launches++;
   CK(cudaGetLastError());
   if (env->timing) {
@@ -701,7 +750,7 @@ int ilrl_physics_only(ilrl_env* env, const float* torque, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (!torque) return fail(env, ILRL_ERR_ARG, "ilrl_physics_only: null buffer");
   CK(cudaSetDevice(env->cfg.device));
-  physics_only_kernel<<<nblk(env->n), BLOCK, 0, (cudaStream_t)stream>>>(view(env), torque, env->rows, env->substeps, env->dbg, env->dbg_env);
+  physics_only_kernel<<<(env->n + QE - 1) / QE, QT, sizeof(quad::Smem), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);
   env->launches++;
   CK(cudaGetLastError());
   return ILRL_OK;
@@ -729,8 +778,6 @@ int ilrl_stats(ilrl_env* env, float* stats16, void* stream) {
 }
 /* harness only, not in ilrl.h: number of substeps ilrl_physics_only runs */
 int ilrl_debug_substeps(ilrl_env* env, int32_t n) { if (!env || n < 1) return ILRL_ERR_ARG; env->substeps = n; return ILRL_OK; }
-/* harness only, not in ilrl.h: dump the constraint rows of env `i` of the next ilrl_physics_only into dbg_dev[400] */
-int ilrl_debug_dump(ilrl_env* env, float* dbg_dev, int32_t i) { if (!env) return ILRL_ERR_ARG; env->dbg = dbg_dev; env->dbg_env = i; return ILRL_OK; }
 int64_t ilrl_launch_count(const ilrl_env* env) { return env ? env->launches : 0; }
 int ilrl_kernel_timing(ilrl_env* env, int32_t on, float* ms_out, int64_t* launches_out) {
   if (!env) return ILRL_ERR_ARG;

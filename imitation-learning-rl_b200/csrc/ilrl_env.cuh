@@ -228,13 +228,17 @@ __device__ __forceinline__ void rotz(float rad, const float* v, float* o) {
   o[0] = c * v[0] - s * v[1]; o[1] = s * v[0] + c * v[1]; o[2] = v[2];
 }
 
-// resetFromFrame.  yaw_deg: low = caller's resetYaw (rotates the body only), hier = reset()'s own draw, folded into
-// the heading (Q16).  Leaves FK of the reset pose in k and the calc_state result in c.
+// resetFromFrame, in two phases around the forward kinematics of the reset pose (the caller runs its own FK between
+// them: thread-per-env fk() in the reset kernel, the 4-lane qfk() in the fused step kernel).
+// yaw_deg: low = caller's resetYaw (rotates the body only), hier = reset()'s own draw, folded into the heading (Q16).
+struct ResetCtx { float sep[3]; float rot; int start_frame; };
+
 template <int MODE>
-__device__ __forceinline__ void reset_env(Phys& s, EnvW& w, const ClipDesc& cl, int start_frame, float yaw_deg,
-                                          int target_deg, float step_per_level, Work& k, Calc& c) {
+__device__ __forceinline__ void reset_pose(Phys& s, EnvW& w, const ClipDesc& cl, int start_frame, float yaw_deg,
+                                           int target_deg, ResetCtx& rx) {
   const float D2R = 0.017453292519943295f;
-  float sepx = w.e[ILRL_E_SEP_X], sepy = w.e[ILRL_E_SEP_Y], sepz = w.e[ILRL_E_SEP_Z];
+  rx.sep[0] = w.e[ILRL_E_SEP_X]; rx.sep[1] = w.e[ILRL_E_SEP_Y]; rx.sep[2] = w.e[ILRL_E_SEP_Z];
+  rx.start_frame = start_frame;
   float clip_id = w.e[ILRL_E_CLIP];
 #pragma unroll
   for (int i = 0; i < ILRL_ENV_WORDS; i++) w.e[i] = 0.f;
@@ -266,15 +270,22 @@ __device__ __forceinline__ void reset_env(Phys& s, EnvW& w, const ClipDesc& cl, 
   s.quat[0] = 0.f; s.quat[1] = 0.f; s.quat[2] = sh; s.quat[3] = ch;
   w.e[ILRL_E_HLDEG] = deg_to_target * D2R;
   s.w[0] = s.w[1] = s.w[2] = 0.f;
-  const float rot = deg_to_target * D2R;
+  rx.rot = deg_to_target * D2R;
+}
+
+// rfx, rfy: origin of the right_foot body relative to the torso origin; sumx, sumy: sums of the 31 part offsets.
+template <int MODE>
+__device__ __forceinline__ void reset_finish(Phys& s, EnvW& w, const ClipDesc& cl, const ResetCtx& rx, float rfx,
+                                             float rfy, float sumx, float sumy, float step_per_level, Calc& c) {
+  const int start_frame = rx.start_frame;
+  const float rot = rx.rot;
   const float* ep0 = cl.ep + start_frame * 27;
-  fk(s, k);
   if (MODE == 0) {
     const float* ep1 = cl.ep + ((start_frame + 2) % cl.max_frame) * 27;
     float rf[3] = {__ldg(ep0 + 9), __ldg(ep0 + 10), __ldg(ep0 + 11)}, rfr[3];  // RightFoot
     rotz(rot, rf, rfr);
-    w.e[ILRL_E_SEP_X] = s.p[0] + k.o[5][0] - rfr[0];  // body 5 = right_foot
-    w.e[ILRL_E_SEP_Y] = s.p[1] + k.o[5][1] - rfr[1];
+    w.e[ILRL_E_SEP_X] = s.p[0] + rfx - rfr[0];
+    w.e[ILRL_E_SEP_Y] = s.p[1] + rfy - rfr[1];
     w.e[ILRL_E_SEP_Z] = 0.f;
     float d[3] = {__ldg(ep1 + 6) - __ldg(ep0 + 6), __ldg(ep1 + 7) - __ldg(ep0 + 7), __ldg(ep1 + 8) - __ldg(ep0 + 8)}, dr[3];
     rotz(rot, d, dr);  // RightLeg displacement over skipFrame frames
@@ -282,7 +293,7 @@ __device__ __forceinline__ void reset_env(Phys& s, EnvW& w, const ClipDesc& cl, 
     for (int i = 0; i < 3; i++) s.v[i] = (dr[i] / 0.0165f) / 1.2f;
   } else {
     const float* ep1 = cl.ep + (start_frame + 1) * 27;
-    w.e[ILRL_E_SEP_X] = sepx; w.e[ILRL_E_SEP_Y] = sepy; w.e[ILRL_E_SEP_Z] = sepz;
+    w.e[ILRL_E_SEP_X] = rx.sep[0]; w.e[ILRL_E_SEP_Y] = rx.sep[1]; w.e[ILRL_E_SEP_Z] = rx.sep[2];
     float d[3] = {__ldg(ep1 + 6) - __ldg(ep0 + 6), __ldg(ep1 + 7) - __ldg(ep0 + 7), __ldg(ep1 + 8) - __ldg(ep0 + 8)}, dr[3];
     rotz(rot, d, dr);
 #pragma unroll
@@ -292,8 +303,18 @@ __device__ __forceinline__ void reset_env(Phys& s, EnvW& w, const ClipDesc& cl, 
     w.e[ILRL_E_HIGH_PENDING] = 1.f;
   }
   inc_frame(w, cl, 2);
-  calc_state(s, k.sumx, k.sumy, w.e[ILRL_E_WALK_X], w.e[ILRL_E_WALK_Y], c);
+  calc_state(s, sumx, sumy, w.e[ILRL_E_WALK_X], w.e[ILRL_E_WALK_Y], c);
   w.e[ILRL_E_OBS_SIN] = c.obs[1]; w.e[ILRL_E_OBS_COS] = c.obs[2];
+}
+
+// thread-per-env form (reset kernel).  Leaves FK of the reset pose in k and the calc_state result in c.
+template <int MODE>
+__device__ __forceinline__ void reset_env(Phys& s, EnvW& w, const ClipDesc& cl, int start_frame, float yaw_deg,
+                                          int target_deg, float step_per_level, Work& k, Calc& c) {
+  ResetCtx rx;
+  reset_pose<MODE>(s, w, cl, start_frame, yaw_deg, target_deg, rx);
+  fk(s, k);
+  reset_finish<MODE>(s, w, cl, rx, k.o[5][0], k.o[5][1], k.sumx, k.sumy, step_per_level, c);  // body 5 = right_foot
 }
 
 // calcEndPointScore(useExp=True)

@@ -19,9 +19,16 @@
 namespace ilrl {
 namespace quad {
 
-constexpr int QE = 16;        // envs per CTA
+#ifndef ILRL_QE
+#define ILRL_QE 16
+#endif
+#ifndef ILRL_RSM
+#define ILRL_RSM 16
+#endif
+constexpr int QE = ILRL_QE;   // envs per CTA
 constexpr int QT = 4 * QE;    // threads per CTA
-constexpr int RSM = 12;       // constraint rows per env kept in shared memory (the rest overflow to global scratch)
+constexpr int RSM = ILRL_RSM; // constraint rows per env kept in shared memory (the rest overflow to global scratch)
+constexpr int GROWS = MAXROWS - RSM;  // rows per env in the global overflow scratch
 constexpr int SL = 25;        // slice layout of a generalized vector: base 6 | spine 3 | 4 limbs x 4 slots
 constexpr int ROWW = 2 * SL;  // a stored row: response slices + Jacobian slices
 constexpr int LW = 13;        // per-link record: S(6) U(6) 1/D
@@ -121,6 +128,7 @@ struct Smem {
   float link[NJ][LW][QE];        // per-link S, U, 1/D of every env (env-minor: conflict-free across the 8 envs of a warp)
   float nu[QE][SL];              // unconstrained new velocities in slice layout
   float qj[QE][NJ];              // joint positions (limit rows may be built by any lane)
+  float qdj[QE][NJ];             // joint velocities (gather / scatter between the quad layout and a full Phys)
   float sph[QE][NS][4];          // contact point (relative to the torso origin) and distance of every sphere
   float lam[QE][MAXROWS];
   float rhs[QE][MAXROWS];
@@ -638,6 +646,88 @@ __device__ __forceinline__ void qsubstep(QState& s, const float* tau_s, const fl
   for (int i = 0; i < 3; i++) { s.qds[i] = nu.s[i]; s.qs[i] += dt * nu.s[i]; }
 #pragma unroll
   for (int i = 0; i < 4; i++) { s.qdl[i] = nu.l[i]; s.ql[i] += dt * nu.l[i]; }
+}
+
+// ---- state movement between HBM (SoA phys[47][n]), the quad layout and a replicated full Phys
+__device__ __forceinline__ void qload(const float* phys, int n, int i, const Role& rc, QState& s) {
+  const float* p = phys + i;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { s.p[k] = p[k * n]; s.v[k] = p[(7 + k) * n]; s.w[k] = p[(10 + k) * n]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) s.quat[k] = p[(3 + k) * n];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { s.qs[k] = p[(13 + k) * n]; s.qds[k] = p[(30 + k) * n]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int j = rc.j[k];
+    s.ql[k] = j >= 0 ? p[(13 + j) * n] : 0.f;
+    s.qdl[k] = j >= 0 ? p[(30 + j) * n] : 0.f;
+  }
+}
+// quad layout -> full Phys in every lane (through shared memory)
+__device__ __forceinline__ void qgather(const QState& s, const Role& rc, Smem& sm, int e, int role, unsigned qm, Phys& ps) {
+  __syncwarp(qm);
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (rc.j[k] >= 0) { sm.qj[e][rc.j[k]] = s.ql[k]; sm.qdj[e][rc.j[k]] = s.qdl[k]; }
+  if (role == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) { sm.qj[e][k] = s.qs[k]; sm.qdj[e][k] = s.qds[k]; }
+  }
+  __syncwarp(qm);
+#pragma unroll
+  for (int j = 0; j < NJ; j++) { ps.q[j] = sm.qj[e][j]; ps.qd[j] = sm.qdj[e][j]; }
+#pragma unroll
+  for (int k = 0; k < 3; k++) { ps.p[k] = s.p[k]; ps.v[k] = s.v[k]; ps.w[k] = s.w[k]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) ps.quat[k] = s.quat[k];
+}
+// full (replicated) Phys -> quad layout
+__device__ __forceinline__ void qscatter(const Phys& ps, const Role& rc, Smem& sm, int e, int role, unsigned qm, QState& s) {
+  __syncwarp(qm);
+  if (role == 0) {
+#pragma unroll
+    for (int j = 0; j < NJ; j++) { sm.qj[e][j] = ps.q[j]; sm.qdj[e][j] = ps.qd[j]; }
+  }
+  __syncwarp(qm);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { s.p[k] = ps.p[k]; s.v[k] = ps.v[k]; s.w[k] = ps.w[k]; s.qs[k] = ps.q[k]; s.qds[k] = ps.qd[k]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) s.quat[k] = ps.quat[k];
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const int j = rc.j[k];
+    s.ql[k] = j >= 0 ? sm.qj[e][j] : 0.f;
+    s.qdl[k] = j >= 0 ? sm.qdj[e][j] : 0.f;
+  }
+}
+// kinematics of the current pose: sums of the 31 part offsets and the right-foot origin (role 0's end body)
+__device__ __forceinline__ void qpose_sums(const QState& s, const Role& rc, unsigned qm, float& sumx, float& sumy,
+                                           float& rfx, float& rfy) {
+  QKin k;
+  qfk(s, rc, k);
+  sumx = k.ssx + qsum(k.sx, qm);
+  sumy = k.ssy + qsum(k.sy, qm);
+  const int l0 = (threadIdx.x & 31) & ~3;
+  rfx = __shfl_sync(qm, k.oE.x, l0);
+  rfy = __shfl_sync(qm, k.oE.y, l0);
+}
+// store a replicated Phys: the 47 words are dealt to the 4 lanes
+__device__ __forceinline__ void qstore_phys(float* phys, int n, int i, int role, const Phys& ps) {
+  float* p = phys + i;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (((0 + k) & 3) == role) p[(0 + k) * n] = ps.p[k];
+    if (((7 + k) & 3) == role) p[(7 + k) * n] = ps.v[k];
+    if (((10 + k) & 3) == role) p[(10 + k) * n] = ps.w[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) if (((3 + k) & 3) == role) p[(3 + k) * n] = ps.quat[k];
+#pragma unroll
+  for (int k = 0; k < NJ; k++) {
+    if (((13 + k) & 3) == role) p[(13 + k) * n] = ps.q[k];
+    if (((30 + k) & 3) == role) p[(30 + k) * n] = ps.qd[k];
+  }
 }
 
 }  // namespace quad

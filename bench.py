@@ -174,7 +174,7 @@ def run_ours(args):
     cpu_base = None
     if world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        steps = 150  # ~10-20 s: cores x 64 envs x 150 steps at ~6.4k env-steps/s/core
+        steps = 2400  # ~12 s of CPU work: cores x 64 envs x 2400 steps at ~13k env-steps/s/core
         total, dt = cpu_rollout(cores, 64, 10, steps)
         cpu_base = {"value": total / dt, "unit": UNIT, "cores": cores, "kind": "port",
                     "sample": "%d host threads x 64 oracle envs (oracle/ilrl_oracle.c, fp64) x %d env steps of the "
@@ -225,8 +225,8 @@ def run_ours(args):
     launches = env.launch_count() - l0
     st = env.stats()  # {episodes, sum return, sum length, steps, sum reward, ...}: the only cross-rank exchange
     t_ms = torch.tensor([ms], device=dev)
+    ilrl_b200.stats.allreduce_stats(st)  # NCCL sum of 16 floats over the ranks (no-op at N=1)
     if world > 1:
-        dist.all_reduce(st, op=dist.ReduceOp.SUM)
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
     clk = clocks.stop() if clocks else None

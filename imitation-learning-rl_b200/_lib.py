@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "libilrl_b200.so")
+SO = os.environ.get("ILRL_SO") or os.path.join(HERE, "libilrl_b200.so")  # ILRL_SO: development builds only
 
 SYMBOLS = ["ilrl_create", "ilrl_destroy", "ilrl_last_error", "ilrl_load_clip", "ilrl_set_clip_ids", "ilrl_reset",
            "ilrl_step", "ilrl_step_host", "ilrl_high_step", "ilrl_high_readout", "ilrl_get_state", "ilrl_set_state",
@@ -40,7 +40,7 @@ def lib():
     L.ilrl_last_error.restype = C.c_char_p
     L.ilrl_load_clip.argtypes = [_vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, _vp, C.c_int32, C.c_int32]
     L.ilrl_set_clip_ids.argtypes = [_vp, _vp]
-    L.ilrl_reset.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.ilrl_reset.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.ilrl_step.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.ilrl_step_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.ilrl_step_no_physics.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp]

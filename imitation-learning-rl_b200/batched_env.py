@@ -98,7 +98,7 @@ class BatchedHumanoidEnv:
         return t
 
     # ------------------------------------------------------------------ env API (device tensors)
-    def reset(self, mask=None, start_frame=None, target_deg=None, reset_yaw_deg=None):
+    def reset(self, mask=None, start_frame=None, target_deg=None, reset_yaw_deg=None, target_xy=None):
         """reset() / resetFromFrame() of the masked envs (all if mask is None).  Returns the obs tensor
         ([N,70] low-level obs in "low" mode, [N,44] high-level obs in "hier" mode); unmasked rows keep old values."""
         n = self.num_envs
@@ -106,8 +106,9 @@ class BatchedHumanoidEnv:
         sf = None if start_frame is None else torch.as_tensor(start_frame, device=self.device).to(torch.int32).contiguous()
         td = None if target_deg is None else torch.as_tensor(target_deg, device=self.device).to(torch.int32).contiguous()
         yw = None if reset_yaw_deg is None else self._f32(reset_yaw_deg, (n,))
+        xy = None if target_xy is None else self._f32(target_xy, (n, 2))
         out = self.high_obs if self.mode == 1 else self.obs
-        self._ck(self.L.ilrl_reset(self.h, _ptr(m), _ptr(sf), _ptr(td), _ptr(yw), _ptr(out), self._stream()))
+        self._ck(self.L.ilrl_reset(self.h, _ptr(m), _ptr(sf), _ptr(td), _ptr(yw), _ptr(xy), _ptr(out), self._stream()))
         if self.mode == 1:
             self._ck(self.L.ilrl_high_readout(self.h, None, None, _ptr(self.high_flags), self._stream()))
         return out
@@ -140,6 +141,13 @@ class BatchedHumanoidEnv:
         self._ck(self.L.ilrl_high_readout(self.h, _ptr(self.high_obs), _ptr(self.high_reward), _ptr(self.high_flags),
                                           self._stream()))
         return self.high_obs, self.high_reward, self.high_flags
+
+    def set_clip_of_env(self, clip_of_env):
+        """Re-assign which staged clip each env imitates (`selected_motion`).  Takes effect at once, as in the reference;
+        change it between episodes (a frame index valid in one clip may not exist in a shorter one)."""
+        ids = np.ascontiguousarray(clip_of_env, dtype=np.int32)
+        assert ids.shape == (self.num_envs,)
+        self._ck(self.L.ilrl_set_clip_ids(self.h, ids.ctypes.data))
 
     # ------------------------------------------------------------------ parity-harness / introspection entry points
     def get_state(self):

@@ -120,7 +120,10 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
 #pragma unroll
   for (int t = 0; t < 11; t++) st_terms[t] = 0.f;
 
-  const bool pending = valid && MODE == 1 && a.envf[(size_t)ILRL_E_HIGH_PENDING * a.n + i] != 0.f;
+  // skipped envs: hier envs waiting for a high-level action, and rows whose first action component is NaN (the
+  // batched adapters' "no action for this env in this call"; the reference asserts finite actions, REF humanoid.py:55)
+  const bool pending = valid && ((MODE == 1 && a.envf[(size_t)ILRL_E_HIGH_PENDING * a.n + i] != 0.f) ||
+                                 isnan(sm.act[e][0]));
   if (valid && pending) {
     if (role == 0) { a.reward[i] = 0.f; a.done[i] = 0; }
     if (a.terms)
@@ -295,7 +298,7 @@ struct ResetArgs {
   float step_per_level;
   uint64_t seed;
   float* phys; float* envf; uint32_t* rng;
-  const uint8_t* mask; const int32_t* start_frame; const int32_t* target_deg; const float* yaw_deg;
+  const uint8_t* mask; const int32_t* start_frame; const int32_t* target_deg; const float* yaw_deg; const float* target_xy;
   float* obs;
   uint8_t* high_flags;
   ClipDesc clips[MAX_CLIPS];
@@ -314,9 +317,11 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const ResetArgs a) {
   uint32_t ctr = a.rng[i];
   int sf = a.start_frame ? a.start_frame[i] : rand_int(a.seed, (uint32_t)i, ctr, 0, cl.max_frame - 5);
   float yaw = a.yaw_deg ? a.yaw_deg[i] : (MODE == 1 ? (float)rand_int(a.seed, (uint32_t)i, ctr, -180, 180) : 0.f);
-  int tdeg = a.target_deg ? a.target_deg[i] : rand_int(a.seed, (uint32_t)i, ctr, -180, 180);
+  int tdeg = (a.target_deg || a.target_xy) ? (a.target_deg ? a.target_deg[i] : 0) : rand_int(a.seed, (uint32_t)i, ctr, -180, 180);
+  float txy[2] = {0.f, 0.f};
+  if (a.target_xy) { txy[0] = a.target_xy[2 * i]; txy[1] = a.target_xy[2 * i + 1]; }
   Work k; Calc c;
-  reset_env<MODE>(s, w, cl, sf, yaw, tdeg, a.step_per_level, k, c);
+  reset_env<MODE>(s, w, cl, sf, yaw, tdeg, a.step_per_level, k, c, a.target_xy ? txy : nullptr);
   a.rng[i] = ctr;
   store_state(v, i, s, w);
   if (a.obs) {
@@ -346,7 +351,7 @@ __global__ void __launch_bounds__(BLOCK) high_step_kernel(const HighArgs a) {
   StepArgs v; v.n = a.n; v.phys = a.phys; v.envf = a.envf;
   Phys s; EnvW w;
   load_state(v, i, s, w);
-  if (w.e[ILRL_E_HIGH_PENDING] == 0.f) return;
+  if (w.e[ILRL_E_HIGH_PENDING] == 0.f || isnan(a.action2[2 * i])) return;  // not waiting / no action in this call
   const ClipDesc cl = a.clips[(int)w.e[ILRL_E_CLIP]];
   Work k; Calc c;
   fk(s, k);
@@ -604,14 +609,14 @@ static int check_ready(ilrl_env* env) {
 }
 
 int ilrl_reset(ilrl_env* env, const uint8_t* mask, const int32_t* start_frame, const int32_t* target_deg,
-               const float* yaw_deg, float* obs, void* stream) {
+               const float* yaw_deg, const float* target_xy, float* obs, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (int r = check_ready(env)) return r;
   CK(cudaSetDevice(env->cfg.device));
   ResetArgs a;
   a.n = env->n; a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
   a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
-  a.mask = mask; a.start_frame = start_frame; a.target_deg = target_deg; a.yaw_deg = yaw_deg; a.obs = obs;
+  a.mask = mask; a.start_frame = start_frame; a.target_deg = target_deg; a.yaw_deg = yaw_deg; a.target_xy = target_xy; a.obs = obs;
   a.high_flags = env->high_flags;
   memcpy(a.clips, env->clips, sizeof a.clips);
   cudaStream_t st = (cudaStream_t)stream;

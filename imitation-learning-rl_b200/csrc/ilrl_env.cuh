@@ -235,7 +235,7 @@ struct ResetCtx { float sep[3]; float rot; int start_frame; };
 
 template <int MODE>
 __device__ __forceinline__ void reset_pose(Phys& s, EnvW& w, const ClipDesc& cl, int start_frame, float yaw_deg,
-                                           int target_deg, ResetCtx& rx) {
+                                           int target_deg, ResetCtx& rx, const float* target_xy = nullptr) {
   const float D2R = 0.017453292519943295f;
   rx.sep[0] = w.e[ILRL_E_SEP_X]; rx.sep[1] = w.e[ILRL_E_SEP_Y]; rx.sep[2] = w.e[ILRL_E_SEP_Z];
   rx.start_frame = start_frame;
@@ -243,10 +243,19 @@ __device__ __forceinline__ void reset_pose(Phys& s, EnvW& w, const ClipDesc& cl,
 #pragma unroll
   for (int i = 0; i < ILRL_ENV_WORDS; i++) w.e[i] = 0.f;
   w.e[ILRL_E_CLIP] = clip_id;
-  float st, ct;
-  sincosf((float)target_deg * D2R, &st, &ct);
-  w.e[ILRL_E_TARGET_X] = ct * (float)ILRL_TARGET_LEN;
-  w.e[ILRL_E_TARGET_Y] = st * (float)ILRL_TARGET_LEN;
+  // degToTarget = rad2deg(atan2(target)): for a drawn target it is the integer draw itself (exact in fp32); an
+  // explicit target (usePredefinedTarget, REF low_level_env.py:253-255) gives whatever its direction is
+  float deg_to_target;
+  if (target_xy) {
+    w.e[ILRL_E_TARGET_X] = target_xy[0]; w.e[ILRL_E_TARGET_Y] = target_xy[1];
+    deg_to_target = atan2f(target_xy[1], target_xy[0]) * 57.29577951308232f;
+  } else {
+    float st, ct;
+    sincosf((float)target_deg * D2R, &st, &ct);
+    w.e[ILRL_E_TARGET_X] = ct * (float)ILRL_TARGET_LEN;
+    w.e[ILRL_E_TARGET_Y] = st * (float)ILRL_TARGET_LEN;
+    deg_to_target = (float)target_deg;
+  }
   w.e[ILRL_E_FRAME] = (float)start_frame;
 #pragma unroll
   for (int j = 0; j < NJ; j++) { s.q[j] = 0.f; s.qd[j] = 0.f; }
@@ -258,8 +267,7 @@ __device__ __forceinline__ void reset_pose(Phys& s, EnvW& w, const ClipDesc& cl,
     s.qd[kMapJoint[m]] = __ldg(vel + kMapCol[m]);
   }
   s.p[0] = 0.f; s.p[1] = 0.f; s.p[2] = (float)ILRL_RESET_Z;
-  // degToTarget = rad2deg(atan2(target)) is the integer draw itself (exact in fp32)
-  float deg_to_target = (float)target_deg, body_deg;
+  float body_deg;
   if (MODE == 1) { deg_to_target += yaw_deg; body_deg = deg_to_target; }
   else body_deg = deg_to_target + yaw_deg;
   float sd, cd;
@@ -310,9 +318,10 @@ __device__ __forceinline__ void reset_finish(Phys& s, EnvW& w, const ClipDesc& c
 // thread-per-env form (reset kernel).  Leaves FK of the reset pose in k and the calc_state result in c.
 template <int MODE>
 __device__ __forceinline__ void reset_env(Phys& s, EnvW& w, const ClipDesc& cl, int start_frame, float yaw_deg,
-                                          int target_deg, float step_per_level, Work& k, Calc& c) {
+                                          int target_deg, float step_per_level, Work& k, Calc& c,
+                                          const float* target_xy = nullptr) {
   ResetCtx rx;
-  reset_pose<MODE>(s, w, cl, start_frame, yaw_deg, target_deg, rx);
+  reset_pose<MODE>(s, w, cl, start_frame, yaw_deg, target_deg, rx, target_xy);
   fk(s, k);
   reset_finish<MODE>(s, w, cl, rx, k.o[5][0], k.o[5][1], k.sumx, k.sumy, step_per_level, c);  // body 5 = right_foot
 }

@@ -1,0 +1,382 @@
+"""Reference-shaped single-env classes: the drop-in faces of the hot path.
+
+`LowLevelHumanoidEnv` mirrors REF low_level_env.py:36-526 (a `gym.Env`), `HierarchicalHumanoidEnv` mirrors
+REF hier_env.py:39-642 (an RLlib `MultiAgentEnv`): same class names, constructor arguments, spaces, methods, return
+shapes/dtypes, agent ids, public attributes (the ones `custom_callback.py`, `env_check*.py` and `env_vis*.py` read or
+write) and error behaviour (`assert np.isfinite(action).all()` REF humanoid.py:55, `assert len(action_dict) == 1`
+REF hier_env.py:356).  Each instance is an N = 1 view of `BatchedHumanoidEnv`: every number it returns is computed by
+the CUDA kernels behind the C ABI (include/ilrl.h); the host only moves 1 action up and 1 obs row + the env words
+down per call and mirrors the reference's Python-side bookkeeping that is not per-step arithmetic (the
+`usePredefinedTarget` list, the `debug` done rule, the `rng` the reference draws its integers from).
+
+For throughput use `BatchedHumanoidEnv` or the adapters in rllib_adapters.py; these classes exist so the reference's
+drivers (`train_config.make_env_low/make_env_hier`, `env_check.py`, ...) run unchanged on top of the new path.
+"""
+import copy
+
+import numpy as np
+
+from . import batched_env as B
+from .batched_env import BatchedHumanoidEnv
+from .clips import load_clip
+
+try:  # gym is not part of this image; the reference needs it only for the Box spaces and the Env base class
+    from gym import Env as _GymEnv
+    from gym.spaces import Box
+except Exception:  # pragma: no cover - exercised in this image
+    class _GymEnv(object):
+        pass
+
+    class Box(object):
+        """Minimal stand-in for gym.spaces.Box (low/high/shape/dtype/sample/contains)."""
+
+        def __init__(self, low, high, shape=None, dtype=np.float32):
+            self.shape = tuple(shape) if shape is not None else np.shape(low)
+            self.dtype = np.dtype(dtype)
+            self.low = np.full(self.shape, low, dtype=self.dtype)
+            self.high = np.full(self.shape, high, dtype=self.dtype)
+            self._rng = np.random.default_rng()
+
+        def sample(self):
+            lo = np.where(np.isfinite(self.low), self.low, -1.0)
+            hi = np.where(np.isfinite(self.high), self.high, 1.0)
+            return self._rng.uniform(lo, hi).astype(self.dtype)
+
+        def contains(self, x):
+            x = np.asarray(x)
+            return x.shape == self.shape and bool(np.all(x >= self.low) and np.all(x <= self.high))
+
+        def __repr__(self):
+            return "Box(%s, %s, %s, %s)" % (self.low.min(), self.high.max(), self.shape, self.dtype)
+
+try:
+    from ray.rllib.env import MultiAgentEnv as _MultiAgentEnv
+except Exception:  # pragma: no cover - ray is not part of this image
+    class _MultiAgentEnv(object):
+        pass
+
+# the reference's dictionaries, kept as data because drivers read them (REF low_level_env.py:86-152)
+JOINT_MAP = {
+    "right_knee": "rightKnee", "right_hip_x": "rightHipX", "right_hip_y": "rightHipY", "right_hip_z": "rightHipZ",
+    "left_knee": "leftKnee", "left_hip_x": "leftHipX", "left_hip_y": "leftHipY", "left_hip_z": "leftHipZ",
+    "right_shoulder_x": "rightShoulderX", "right_shoulder_y": "rightShoulderY", "right_elbow": "rightElbow",
+    "left_shoulder_x": "leftShoulderX", "left_shoulder_y": "leftShoulderY", "left_elbow": "leftElbow",
+}
+_REWARD_ATTRS = dict(deltaJoints=0, deltaVelJoints=1, delta_lowTargetScore=2, electricityScore=3, jointLimitScore=4,
+                     aliveReward=5, bodyPostureScore=6, lowTargetScore=7, deltaEndPoints=8, highTargetScore=9,
+                     driftScore=10, delta_highTargetScore=11)
+
+
+class _SingleEnv(object):
+    """Shared plumbing of the two N = 1 views."""
+
+    metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 60}
+
+    def _make(self, mode, clips, selected, device, seed):
+        self._env = BatchedHumanoidEnv(1, mode, clips=clips, clip_of_env=np.array([selected], np.int32), device=device,
+                                       seed=0 if seed is None else int(seed), auto_reset=False)
+        self.rng = np.random.default_rng(seed)
+        self.cur_timestep = 0
+        self.max_timestep = 3000
+        self.frame = 0
+        self.joint_map = dict(JOINT_MAP)
+        self.target = np.array([1.0, 0.0, 0.0])
+        self.targetLen = 5
+        self.highLevelDegTarget = 0.0
+        self.predefinedTarget = np.array([[]])
+        self.predefinedTargetIndex = 0
+        self.usePredefinedTarget = False
+        self.skipFrame = 2
+        self.starting_ep_pos = np.zeros(3)
+        self.starting_robot_pos = np.zeros(3)
+        self.robot_pos = np.zeros(3)
+        self.last_robotPos = np.zeros(3)
+        self.frame_update_cnt = 0
+        self.cur_obs = np.zeros(42, np.float32)
+        self.initReward()
+
+    # REF low_level_env.py:174-197 / hier_env.py:174-199
+    def initReward(self):
+        for k in _REWARD_ATTRS:
+            setattr(self, k, 0)
+        self.baseReward = 0
+        self.last_lowTargetScore = 0
+        self.bodySpeedScore = 0
+        self.cumulative_driftScore = 0
+        self.cumulative_aliveReward = 0
+        self.delta_deltaJoints = self.delta_deltaVelJoints = self.delta_deltaEndPoints = 0
+        self.delta_bodyPostureScore = 0
+
+    def close(self):
+        self._env.close()
+
+    def render(self, mode="human"):
+        """The reference forwards to PyBullet's renderer (REF low_level_env.py:202-203); there is no renderer on
+        this path.  "rgb_array" returns a black frame of the reference's render size so gym's Monitor keeps working."""
+        if mode == "rgb_array":
+            return np.zeros((240, 320, 3), np.uint8)
+        return None
+
+    def seed(self, seed=None):
+        self.rng = np.random.default_rng(seed)
+        return [seed]
+
+    # ---- state mirror: pull the env words of the single env and expose them under the reference's names
+    def _pull(self, terms=None):
+        phys, envf = self._env.get_state()
+        e = envf[0].cpu().numpy().astype(np.float64)
+        self._phys = phys[0].cpu().numpy().astype(np.float64)
+        self._envf = e
+        self.frame = int(e[B.E_FRAME])
+        self.cur_timestep = int(e[B.E_T])
+        self.target = np.array([e[B.E_TARGET_X], e[B.E_TARGET_Y], 0.0])
+        self.starting_robot_pos = np.array([e[B.E_START_X], e[B.E_START_Y], 0.0])
+        self.starting_ep_pos = np.array([e[B.E_SEP_X], e[B.E_SEP_Y], e[B.E_SEP_Z]])
+        self.robot_pos = np.array([e[B.E_ROBOT_X], e[B.E_ROBOT_Y], 0.0])
+        self.highLevelDegTarget = float(e[B.E_HLDEG])
+        self.lowTargetScore = float(e[B.E_LOW_TARGET_SCORE])
+        self.highTargetScore = float(e[B.E_HIGH_TARGET_SCORE])
+        if terms is not None:
+            t = terms[0].cpu().numpy().astype(np.float64)
+            for k, i in _REWARD_ATTRS.items():
+                setattr(self, k, float(t[i]))
+        return e
+
+    def _push_env_words(self, **words):
+        e = self._envf.astype(np.float32).copy()
+        for k, v in words.items():
+            e[getattr(B, k)] = v
+        self._env.set_state(None, e[None, :])
+        self._envf = e.astype(np.float64)
+
+    def _peek_deg(self):
+        """The integer the reference would draw with `self.rng.integers(-180, 180)` IF the target is reached this
+        step (REF low_level_env.py:240-245, 416-417): drawn on a copy of the generator and committed afterwards only
+        when the kernel reports that the target switched, so `self.rng` stays in step with the reference's."""
+        saved = copy.deepcopy(self.rng.bit_generator.state)
+        deg = int(self.rng.integers(-180, 180))
+        after = copy.deepcopy(self.rng.bit_generator.state)
+        self.rng.bit_generator.state = saved
+        return deg, after
+
+    def _after_target_logic(self, old_target, after_state):
+        """Commit the peeked draw and apply the usePredefinedTarget list (REF low_level_env.py:419-429) when the
+        kernel switched the target this step."""
+        switched = not np.allclose(self.target[:2], old_target[:2], atol=0, rtol=0)
+        if not switched:
+            return
+        self.rng.bit_generator.state = after_state
+        if self.usePredefinedTarget:
+            self.predefinedTargetIndex = (self.predefinedTargetIndex + 1) % len(self.predefinedTarget)
+            new = np.asarray(self.predefinedTarget[self.predefinedTargetIndex], dtype=np.float64)
+            start = self.starting_robot_pos  # = the old target (Q8)
+            score = -float(np.linalg.norm(new[:2] - start[:2]))
+            words = dict(E_TARGET_X=new[0], E_TARGET_Y=new[1])
+            if self._env.mode == 0:
+                # lowTargetScore restart + the per-step heading / walk-target refresh on the new target
+                h = float(np.arctan2(new[1] - self.robot_pos[1], new[0] - self.robot_pos[0]))
+                words.update(E_LOW_TARGET_SCORE=score, E_HLDEG=h, E_WALK_X=self.robot_pos[0] + np.cos(h) * 10,
+                             E_WALK_Y=self.robot_pos[1] + np.sin(h) * 10)
+                self.lowTargetScore, self.highLevelDegTarget = score, h
+            else:
+                words.update(E_HIGH_TARGET_SCORE=score)
+                self.highTargetScore = score
+            self._push_env_words(**words)
+            self.target = np.array([new[0], new[1], 0.0])
+
+    def _first_target_xy(self):
+        if self.usePredefinedTarget:
+            self.predefinedTargetIndex = 0
+            t = np.asarray(self.predefinedTarget[0], dtype=np.float32)
+            return t[None, :2].copy()
+        return None
+
+
+class LowLevelHumanoidEnv(_SingleEnv, _GymEnv):
+    """REF low_level_env.py:36.  `useCustomEnv=True` (random heightfield terrain, REF humanoid.py:68-144) is outside
+    this path and raises; `customRobot` is accepted and ignored (the kernels model `CustomHumanoidRobot` on
+    `humanoid_symmetric_2.xml`, the robot every reference config passes)."""
+
+    def __init__(self, reference_name="motion08_03", useCustomEnv=False, customRobot=None, device=0, seed=None):
+        if useCustomEnv:
+            raise NotImplementedError("useCustomEnv=True (CustomScene heightfield terrain) is out of scope of the "
+                                      "B200 path (DESIGN.md section 7); the reference's training configs use False")
+        self.useCustomEnv = False
+        self.reference_name = reference_name
+        self.observation_space = Box(low=-np.inf, high=np.inf, shape=[8 + 17 * 2 + 14 * 2])
+        self.action_space = Box(low=-1, high=1, shape=[17])
+        self.max_frame = load_clip(reference_name)["max_frame"]
+        self._make("low", [reference_name], 0, device, seed)
+
+    def reset(self, resetYaw=0):
+        # REF low_level_env.py:224-232: the start frame comes from the env's own generator
+        return self.resetFromFrame(startFrame=int(self.rng.integers(0, self.max_frame - 5)), resetYaw=resetYaw,
+                                   startFromRef=True, initVel=True)
+
+    def resetFromFrame(self, startFrame=0, resetYaw=0, startFromRef=True, initVel=True):
+        if not startFromRef:
+            raise NotImplementedError("startFromRef=False (keep PyBullet's U(-0.1, 0.1) joint noise) is not part of "
+                                      "the B200 path; every reference caller passes True")
+        xy = self._first_target_xy()
+        deg = None if xy is not None else np.array([int(self.rng.integers(-180, 180))], np.int32)
+        obs = self._env.reset(start_frame=np.array([startFrame], np.int32), target_deg=deg,
+                              reset_yaw_deg=np.array([resetYaw], np.float32), target_xy=xy)
+        obs = obs[0].cpu().numpy().astype(np.float64)
+        self.initReward()
+        self._pull()
+        if not initVel:
+            p = self._phys.astype(np.float32)
+            p[7:10] = 0.0
+            self._env.set_state(p[None, :], None)
+        self.last_robotPos = self.robot_pos.copy()
+        self.cur_obs = obs[:42].astype(np.float32)
+        return obs
+
+    def step(self, action, debug=False):
+        return self.low_level_step(action, debug=debug)
+
+    def low_level_step(self, action, debug=False):
+        a = np.asarray(action, dtype=np.float32).reshape(17)
+        assert np.isfinite(a).all()
+        deg, after = self._peek_deg()
+        self._env.set_forced_target_deg(np.array([deg], np.int64))
+        old_target = self.target.copy()
+        obs, rew, done, terms = self._env.step(a[None, :])
+        obs = obs[0].cpu().numpy().astype(np.float64)
+        reward = float(rew[0].item())
+        done = bool(done[0].item())
+        self._pull(terms)
+        self._after_target_logic(old_target, after)
+        if debug:  # REF low_level_env.py:467-473: the debug rule ignores the distance test
+            done = not (self.aliveReward > 0) or self.cur_timestep >= self.max_timestep
+        self.cur_obs = obs[:42].astype(np.float32)
+        return obs, reward, done, {}
+
+    def getLowLevelObs(self):
+        return np.hstack((self.cur_obs.astype(np.float64), self._obs_tail(self.reference_name, self.frame)))
+
+    @staticmethod
+    def _obs_tail(name, frame):
+        c = load_clip(name)
+        cols = [3, 0, 1, 2, 7, 4, 5, 6, 8, 9, 10, 11, 12, 13]  # joint_map order -> CSV column
+        return np.stack([c["rel"][frame, cols], c["vel"][frame, cols]], 1).reshape(-1).astype(np.float64)
+
+    def calcEndPointScore(self, useExp=False):
+        s = float(self._env.endpoint_score()[0].item())
+        return s if useExp else float(np.log(s) / 3.0)
+
+
+class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
+    """REF hier_env.py:39.  `selected_motion` indexes `motion_list` and may be reassigned between episodes, as the
+    reference's evaluation scripts do (REF env_check_hier.py:93)."""
+
+    def __init__(self, customRobot=None, device=0, seed=None):
+        self.motion_list = ["motion08_03", "motion09_03"]
+        self.high_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[8 + 17 * 2 + 2])
+        self.high_level_act_space = Box(low=-1, high=1, shape=[2])
+        self.low_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[8 + 17 * 2 + 14 * 2])
+        self.low_level_act_space = Box(low=-1, high=1, shape=[17])
+        self.step_per_level = 5
+        self.steps_remaining_at_level = self.step_per_level
+        self.num_high_level_steps = 0
+        self.max_frame = [load_clip(m)["max_frame"] for m in self.motion_list]
+        self._selected_motion = 1
+        self.selected_motion_frame = 0
+        self.low_level_agent_id = "low_level_agent"
+        self._make("hier", self.motion_list, self._selected_motion, device, seed)
+
+    @property
+    def selected_motion(self):
+        return self._selected_motion
+
+    @selected_motion.setter
+    def selected_motion(self, v):
+        v = int(v)
+        if not 0 <= v < len(self.motion_list):
+            raise IndexError("selected_motion %d outside motion_list" % v)
+        self._selected_motion = v
+        self._env.set_clip_of_env(np.array([v], np.int32))
+
+    def _pull(self, terms=None):
+        e = _SingleEnv._pull(self, terms)
+        self.selected_motion_frame = self.frame
+        self.steps_remaining_at_level = int(e[B.E_STEPS_REMAINING])
+        self.cumulative_driftScore = float(e[B.E_CUM_DRIFT])
+        self.cumulative_aliveReward = float(e[B.E_CUM_ALIVE])
+        return e
+
+    def reset(self):
+        # REF hier_env.py:235-243: both integers come from the env's own generator, start frame first
+        sf = int(self.rng.integers(0, self.max_frame[self._selected_motion] - 5))
+        yaw = int(self.rng.integers(-180, 180))
+        return self.resetFromFrame(startFrame=sf, resetYaw=yaw, startFromRef=True, initVel=True)
+
+    def resetFromFrame(self, startFrame=0, resetYaw=0, startFromRef=True, initVel=True):
+        if not startFromRef:
+            raise NotImplementedError("startFromRef=False is not part of the B200 path; every reference caller "
+                                      "passes True")
+        xy = self._first_target_xy()
+        deg = None if xy is not None else np.array([int(self.rng.integers(-180, 180))], np.int32)
+        hobs = self._env.reset(start_frame=np.array([startFrame], np.int32), target_deg=deg,
+                               reset_yaw_deg=np.array([resetYaw], np.float32), target_xy=xy)
+        hobs = hobs[0].cpu().numpy().astype(np.float64)
+        self.initReward()
+        self._pull()
+        if not initVel:
+            p = self._phys.astype(np.float32)
+            p[7:10] = 0.0
+            self._env.set_state(p[None, :], None)
+        self.num_high_level_steps = 0
+        self.low_level_agent_id = "low_level_agent"
+        return {"high_level_agent": hobs}
+
+    def step(self, action_dict, debug=False):
+        assert len(action_dict) == 1, action_dict
+        if "high_level_agent" in action_dict:
+            return self.high_level_step(action_dict["high_level_agent"], debug=debug)
+        return self.low_level_step(list(action_dict.values())[0], debug=debug)
+
+    def _set_pending(self, flag):
+        if bool(self._envf[B.E_HIGH_PENDING]) != bool(flag):
+            self._push_env_words(E_HIGH_PENDING=1.0 if flag else 0.0)
+
+    def high_level_step(self, action, debug=False):
+        a = np.asarray(action, dtype=np.float32).reshape(2)
+        self._set_pending(True)   # the reference applies a high-level action whenever one arrives
+        obs = self._env.high_step(a[None, :])
+        obs = obs[0].cpu().numpy().astype(np.float64)
+        self._pull()
+        self.num_high_level_steps += 1
+        return {self.low_level_agent_id: obs}, {self.low_level_agent_id: 0}, {"__all__": False}, {}
+
+    def low_level_step(self, action, debug=False):
+        a = np.asarray(action, dtype=np.float32).reshape(17)
+        assert np.isfinite(a).all()
+        self._set_pending(False)  # ... and a low-level action whenever one arrives
+        deg, after = self._peek_deg()
+        self._env.set_forced_target_deg(np.array([deg], np.int64))
+        old_target = self.target.copy()
+        obs, rew, done, terms = self._env.step(a[None, :])
+        hobs, hrew, hflags = self._env.high_readout()
+        low_obs = obs[0].cpu().numpy().astype(np.float64)
+        flags = int(hflags[0].item())
+        self._pull(terms)
+        self._after_target_logic(old_target, after)
+        ended, high_present = bool(flags & 1), bool(flags & 2)
+        o, r, d = {}, {}, {"__all__": False}
+        if ended:
+            d["__all__"] = True
+            r["high_level_agent"] = float(hrew[0].item())
+            o["high_level_agent"] = hobs[0].cpu().numpy().astype(np.float64)
+            o[self.low_level_agent_id] = low_obs
+            r[self.low_level_agent_id] = float(rew[0].item())
+        elif high_present:
+            r["high_level_agent"] = float(hrew[0].item())
+            o["high_level_agent"] = hobs[0].cpu().numpy().astype(np.float64)
+        else:
+            o = {self.low_level_agent_id: low_obs}
+            r = {self.low_level_agent_id: float(rew[0].item())}
+        if debug and ended and self.aliveReward > 0 and self.cur_timestep < self.max_timestep:
+            # REF hier_env.py:573-581: the debug rule ignores the distance test
+            d["__all__"] = False
+        return o, r, d, {}

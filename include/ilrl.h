@@ -66,14 +66,17 @@ int ilrl_set_clip_ids(ilrl_env* env, const int32_t* clip_of_env_host);
 /* reset()/resetFromFrame() for the envs whose mask byte is non-zero (mask_dev NULL = all).
  * start_frame_dev / target_deg_dev / reset_yaw_deg_dev: per-env overrides, NULL = drawn as the reference draws them
  * (start frame U{0..max_frame-6}, heading U{-180..179} deg; reset_yaw 0 in low mode, U{-180..179} in hier mode).
+ * target_xy_dev [N,2]: explicit first target instead of 5 m along the drawn heading (the reference's
+ * usePredefinedTarget path, REF low_level_env.py:253-255, hier_env.py:261-265); NULL = none.
  * obs_dev: [N,70] in low mode, [N,44] (high-level obs) in hier mode; rows of unmasked envs are left untouched. */
 int ilrl_reset(ilrl_env* env, const uint8_t* mask_dev, const int32_t* start_frame_dev, const int32_t* target_deg_dev,
-               const float* reset_yaw_deg_dev, float* obs_dev, void* stream);
+               const float* reset_yaw_deg_dev, const float* target_xy_dev, float* obs_dev, void* stream);
 
 /* One low-level env step for every env: apply_action -> 4 physics substeps -> calc_state -> reward -> frame advance
  * -> target bookkeeping -> observation -> termination (-> reset if auto_reset).  terms_dev may be NULL.
  * In hier mode envs that are waiting for a high-level action are skipped (done 0, reward 0, obs row untouched) and
- * the high-level outputs are kept inside the handle until ilrl_high_readout. */
+ * the high-level outputs are kept inside the handle until ilrl_high_readout.  In both modes an env whose action row
+ * starts with NaN is skipped the same way ("no action for this env in this call"). */
 int ilrl_step(ilrl_env* env, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
               float* terms_dev, void* stream);
 
@@ -83,7 +86,8 @@ int ilrl_step_host(ilrl_env* env, const float* action_host, float* obs_host, flo
                    float* terms_host, void* stream);
 
 /* hier mode: high-level agent's action (cos, sin of the heading) for every env that is waiting for one; the others
- * ignore their row.  low_obs_dev [N,70]: the low-level obs the reference returns from high_level_step. */
+ * ignore their row, and so does a waiting env whose row starts with NaN.  low_obs_dev [N,70]: the low-level obs
+ * the reference returns from high_level_step. */
 int ilrl_high_step(ilrl_env* env, const float* action2_dev, float* low_obs_dev, void* stream);
 /* hier mode: high-level obs [N,44], reward [N] and flags [N] (bit0 = episode ended this step, bit1 = high-level
  * agent present in the reference's returned dicts, bit2 = env is now waiting for a high-level action). */

@@ -1,0 +1,275 @@
+"""GPU tests of the reference-shaped faces of the path (run on the B200 box: pytest -m gpu): the N = 1 classes that
+mirror REF low_level_env.py / hier_env.py, the RLlib-shaped batched adapters, and size-independent properties of the
+fused step kernel at BASELINE.json's full batch sizes.  The checker is the CPU oracle (oracle/), itself pinned
+against the unmodified reference Python by tests/test_oracle_golden.py."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("no CUDA device", allow_module_level=True)
+
+import ilrl_b200  # noqa: E402
+from ilrl_b200 import (BatchedHumanoidEnv, HierBaseEnv, HierarchicalHumanoidEnv, LowLevelHumanoidEnv,  # noqa: E402
+                       LowLevelVectorEnv, policy_mapping_fn, stats)
+from ilrl_b200 import batched_env as B  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+
+
+def _oracle_from(env, clip, mode):
+    """An oracle env holding exactly the state of the N = 1 view `env`."""
+    v = O.OracleEnv(clip, mode)
+    phys, envf = env._env.get_state()
+    v.set(phys[0].cpu().numpy().astype(np.float64), envf[0].cpu().numpy().astype(np.float64))
+    return v
+
+
+def test_low_level_env_matches_oracle_over_an_episode():
+    """LowLevelHumanoidEnv (REF low_level_env.py:36) driven exactly like the reference's eval loop
+    (REF env_check.py:130-144); every step is checked against the oracle restarted from the env's pre-step state."""
+    env = LowLevelHumanoidEnv(reference_name="motion09_03", seed=3)
+    assert tuple(env.observation_space.shape) == (70,) and tuple(env.action_space.shape) == (17,)
+    rng = np.random.default_rng(11)
+    obs = env.resetFromFrame(startFrame=0, resetYaw=0, startFromRef=True, initVel=True)
+    assert obs.shape == (70,) and obs.dtype == np.float64
+    assert env.frame == 2 and env.cur_timestep == 0                       # reset advances by skipFrame (golden §4.1)
+    steps = 0
+    for t in range(60):
+        v = _oracle_from(env, "motion09_03", 0)
+        a = rng.uniform(-1, 1, 17)
+        frame_before = env.frame
+        obs, rew, done, info = env.step(a)
+        o1, r1, d1 = v.low_step(a.astype(np.float32).astype(np.float64))
+        assert isinstance(rew, float) and isinstance(done, bool) and info == {}
+        assert env.frame == (frame_before + 2) % (env.max_frame - 1)      # REF low_level_env.py:218-222, bit-exact
+        assert abs(rew - r1) <= 5e-3, (t, rew, r1)
+        np.testing.assert_allclose(obs[42:], o1[42:], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(obs[:42], o1[:42], rtol=0, atol=2e-2)  # through 4 physics substeps
+        assert env.deltaJoints > 0 and env.aliveReward in (2.0, -1.0)
+        steps += 1
+        if done:
+            break
+    assert steps >= 5
+    with pytest.raises(AssertionError):
+        env.step(np.full(17, np.nan))
+    with pytest.raises(NotImplementedError):
+        LowLevelHumanoidEnv(useCustomEnv=True)
+    env.close()
+
+
+def test_low_level_env_rng_and_predefined_targets():
+    """`reset()` consumes the env's generator exactly as REF low_level_env.py:224-257 (start frame, then heading);
+    `usePredefinedTarget` walks the target list as REF low_level_env.py:253-255, 419-421 (REF env_check.py:68-134)."""
+    env = LowLevelHumanoidEnv(reference_name="motion09_03", seed=5)
+    ref = np.random.default_rng(5)
+    env.reset()
+    sf, deg = int(ref.integers(0, env.max_frame - 5)), int(ref.integers(-180, 180))
+    assert env.frame == (sf + 2) % (env.max_frame - 1)
+    np.testing.assert_allclose(env.target[:2], 5 * np.array([np.cos(np.deg2rad(deg)), np.sin(np.deg2rad(deg))]), atol=1e-5)
+    assert env.rng.bit_generator.state == ref.bit_generator.state
+    env.step(np.zeros(17))                                              # no target switch -> no draw consumed
+    assert env.rng.bit_generator.state == ref.bit_generator.state
+    # predefined targets: first target at reset, next one when the robot is within 0.5 m
+    env.usePredefinedTarget = True
+    env.predefinedTarget = np.array([[0.3, 0.1, 0.0], [4.0, 3.0, 0.0], [-2.0, 5.0, 0.0]])
+    env.resetFromFrame(startFrame=0, resetYaw=0, startFromRef=True, initVel=True)
+    np.testing.assert_allclose(env.target, [0.3, 0.1, 0.0], atol=1e-6)
+    np.testing.assert_allclose(env.highLevelDegTarget, np.arctan2(0.1, 0.3), atol=1e-5)
+    env.step(np.zeros(17))                                              # robot starts 0.32 m from the target
+    assert env.predefinedTargetIndex == 1
+    np.testing.assert_allclose(env.target, [4.0, 3.0, 0.0], atol=1e-6)
+    np.testing.assert_allclose(env.starting_robot_pos, [0.3, 0.1, 0.0], atol=1e-6)     # (Q8) the OLD target
+    np.testing.assert_allclose(env.lowTargetScore, -np.hypot(3.7, 2.9), rtol=1e-5)
+    env.close()
+
+
+def test_hierarchical_env_protocol_and_values():
+    """HierarchicalHumanoidEnv (REF hier_env.py:39): reset -> {high}; high step -> {low} reward 0; 4 low steps ->
+    {low}; 5th low step -> {high} only, values against the oracle."""
+    env = HierarchicalHumanoidEnv(seed=2)
+    assert tuple(env.high_level_obs_space.shape) == (44,) and tuple(env.low_level_act_space.shape) == (17,)
+    assert env.selected_motion == 1 and env.motion_list == ["motion08_03", "motion09_03"]
+    rng = np.random.default_rng(4)
+    o = env.reset()
+    assert list(o) == ["high_level_agent"] and o["high_level_agent"].shape == (44,)
+    with pytest.raises(AssertionError):
+        env.step({"high_level_agent": [1, 0], "low_level_agent": np.zeros(17)})
+    for cycle in range(3):
+        v = _oracle_from(env, "motion09_03", 1)
+        ha = rng.uniform(-1, 1, 2)
+        o, r, d, _ = env.step({"high_level_agent": ha})
+        assert list(o) == ["low_level_agent"] and r == {"low_level_agent": 0} and d == {"__all__": False}
+        lo = v.high_step(ha.astype(np.float32).astype(np.float64))
+        np.testing.assert_allclose(o["low_level_agent"], lo, rtol=1e-5, atol=1e-5)
+        assert env.steps_remaining_at_level == 5 and policy_mapping_fn(env.low_level_agent_id) == "low_level_policy"
+        for k in range(5):
+            a = rng.uniform(-0.3, 0.3, 17)
+            o, r, d, _ = env.step({env.low_level_agent_id: a})
+            if d["__all__"]:
+                assert sorted(o) == ["high_level_agent", "low_level_agent"] and sorted(r) == sorted(o)
+                break
+            if k < 4:
+                assert list(o) == ["low_level_agent"] and list(r) == ["low_level_agent"]
+            else:
+                assert list(o) == ["high_level_agent"] and list(r) == ["high_level_agent"]
+                assert o["high_level_agent"].shape == (44,)
+                # (Q14) driftScore = cumulative / 6 <= 5/6
+                assert 0.0 <= env.driftScore <= 5.0 / 6.0 + 1e-6
+        if d["__all__"]:
+            break
+    env.selected_motion = 0
+    o = env.reset()
+    assert env.frame <= env.max_frame[0]
+    env.close()
+
+
+def test_vector_env_adapter():
+    """RLlib VectorEnv shape (ray 1.2.0): vector_reset / vector_step / reset_at / get_unwrapped."""
+    n = 96
+    ve = LowLevelVectorEnv(n, reference_name="motion09_03", seed=9)
+    obs = ve.vector_reset()
+    assert len(obs) == n and obs[0].shape == (70,)
+    rng = np.random.default_rng(0)
+    seen_done = 0
+    for t in range(40):
+        obs, rew, done, info = ve.vector_step([rng.uniform(-1, 1, 17) for _ in range(n)])
+        assert len(obs) == len(rew) == len(done) == len(info) == n and isinstance(done[0], bool)
+        for i in np.nonzero(done)[0]:
+            o = ve.reset_at(int(i))
+            assert o.shape == (70,) and np.isfinite(o).all()
+            seen_done += 1
+        u = ve.get_unwrapped()[0]
+        assert np.isfinite([u.deltaJoints, u.deltaEndPoints, u.lowTargetScore, u.deltaVelJoints, u.bodyPostureScore,
+                            u.highTargetScore, u.driftScore, u.baseReward, u.aliveReward, u.electricityScore,
+                            u.jointLimitScore]).all()
+        assert u.robot_pos.shape == (3,)
+    assert seen_done > 0
+    _, envf = ve.env.get_state()
+    assert (envf[:, B.E_T].cpu().numpy() < 41).all()                      # every done env was re-initialised
+    ve.close()
+
+
+def test_hier_base_env_adapter():
+    """RLlib BaseEnv shape: poll / send_actions / try_reset with the two agent ids; envs at different levels advance
+    in the same call."""
+    n = 24
+    be = HierBaseEnv(n, seed=1)
+    rng = np.random.default_rng(2)
+    obs, rew, done, info, off = be.poll()
+    assert sorted(obs) == list(range(n)) and all(list(o) == ["high_level_agent"] for o in obs.values())
+    low_steps = 0
+    for it in range(30):
+        acts = {}
+        for i, o in obs.items():
+            if done.get(i, {}).get("__all__"):
+                continue
+            if "high_level_agent" in o and "low_level_agent" not in o:
+                acts[i] = {"high_level_agent": rng.uniform(-1, 1, 2)}
+            else:
+                acts[i] = {"low_level_agent": rng.uniform(-1, 1, 17)}
+                low_steps += 1
+        # env 0 deliberately lags one call behind: it must simply not move
+        be.send_actions(acts)
+        new_obs, rew, done, info, off = be.poll()
+        assert sorted(new_obs) == sorted(acts)
+        for i, d in done.items():
+            if d["__all__"]:
+                assert sorted(new_obs[i]) == ["high_level_agent", "low_level_agent"]
+                new_obs[i] = be.try_reset(i)
+                done[i] = {"__all__": False}
+                assert list(new_obs[i]) == ["high_level_agent"]
+        obs = new_obs
+    assert low_steps > n * 10
+    be.stop()
+
+
+@pytest.mark.parametrize("n,mode", [(4096, "low"), (16384, "hier"), (65536, "low"), (37, "low"), (1, "low")])
+def test_full_size_properties(n, mode):
+    """BASELINE.json's batch sizes (and ragged / single-env edge cases): properties that need no oracle.
+    Determinism across handles, batch-invariance (an env's trajectory does not depend on its neighbours), frame
+    advance rule bit-exact, finite outputs, statistics = sums of the per-step outputs."""
+    clips = ilrl_b200.CLIP_NAMES if mode == "low" else ["motion08_03", "motion09_03"]
+    first, count = stats.shard_envs(n, 1, 0)
+    cid = stats.clip_of_env(first, count, len(clips))
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    acts = [torch.rand(n, 17, device="cuda", generator=g) * 2 - 1 for _ in range(6)]
+    hact = torch.rand(n, 2, device="cuda", generator=g) * 2 - 1
+
+    def run(seed):
+        env = BatchedHumanoidEnv(n, mode, clips=clips, clip_of_env=cid, seed=seed, auto_reset=True)
+        env.reset()
+        if mode == "hier":
+            env.high_step(hact)
+        out, rsum, dsum = [], 0.0, 0
+        f0 = env.get_state()[1][:, B.E_FRAME].clone()
+        for a in acts[:5]:
+            obs, rew, done, terms = env.step(a)
+            out.append((obs.clone(), rew.clone(), done.clone()))
+            rsum += float(rew.double().sum())
+            dsum += int(done.sum())
+        st = env.stats().cpu().numpy()
+        phys, envf = env.get_state()
+        env.close()
+        return out, phys, envf, st, rsum, dsum, f0
+
+    a_out, a_phys, a_envf, st, rsum, dsum, f0 = run(21)
+    b_out, b_phys, b_envf, _, _, _, _ = run(21)
+    for (o1, r1, d1), (o2, r2, d2) in zip(a_out, b_out):
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2)   # bitwise deterministic
+        assert bool(torch.isfinite(o1).all()) and bool(torch.isfinite(r1).all())
+    assert torch.equal(a_phys, b_phys) and torch.equal(a_envf, b_envf)
+    assert st[0] == dsum and st[3] == n * 5
+    assert abs(st[4] - rsum) <= 1e-3 * max(1.0, abs(rsum))
+    # frame rule on the envs that never finished: 5 advances of 2 modulo (max_frame - 1)
+    never = torch.stack([d for _, _, d in a_out]).sum(0) == 0
+    mf = torch.tensor([ilrl_b200.load_clip(c)["max_frame"] for c in clips], device="cuda")[torch.as_tensor(cid, device="cuda").long()]
+    want = (f0.long() + 10) % (mf - 1)
+    assert torch.equal(a_envf[:, B.E_FRAME].long()[never], want[never])
+    # batch-invariance: replay a few envs alone from their recorded start state
+    if n >= 37:
+        pick = [0, 5, n // 2, n - 1]
+        env = BatchedHumanoidEnv(n, mode, clips=clips, clip_of_env=cid, seed=21, auto_reset=True)
+        env.reset()
+        if mode == "hier":
+            env.high_step(hact)
+        p0, e0 = env.get_state()
+        env.close()
+        small = BatchedHumanoidEnv(len(pick), mode, clips=clips, clip_of_env=cid[pick], seed=99, auto_reset=False)
+        small.set_state(p0[pick], e0[pick])
+        obs, rew, done, _ = small.step(acts[0][pick])
+        assert torch.equal(obs, a_out[0][0][pick]) or bool((done != 0).any())
+        nd = done == 0
+        assert torch.equal(obs[nd], a_out[0][0][pick][nd]) and torch.equal(rew[nd], a_out[0][1][pick][nd])
+        small.close()
+
+
+def test_nan_action_rows_are_skipped():
+    n = 64
+    env = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], seed=4, auto_reset=False)
+    env.reset()
+    p0, e0 = [t.clone() for t in env.get_state()]
+    a = torch.rand(n, 17, device="cuda") * 2 - 1
+    a[::2, 0] = float("nan")
+    obs0 = env.obs.clone()
+    obs, rew, done, _ = env.step(a)
+    p1, e1 = env.get_state()
+    skipped = torch.arange(n, device="cuda") % 2 == 0
+    assert torch.equal(p1[skipped], p0[skipped]) and torch.equal(e1[skipped], e0[skipped])
+    assert torch.equal(obs[skipped], obs0[skipped]) and bool((rew[skipped] == 0).all()) and bool((done[skipped] == 0).all())
+    assert bool((e1[~skipped, B.E_T] == 1).all())
+    env.close()
+
+
+def test_motion13_13_never_reads_past_its_velocity_table():
+    """Declared divergence: max_frame of motion13_13 is clamped to its 120 velocity rows; a long rollout must stay
+    finite and inside the table (the reference would raise IndexError at frame >= 120)."""
+    n = 256
+    env = BatchedHumanoidEnv(n, "low", clips=["motion13_13"], seed=8, auto_reset=True)
+    env.reset()
+    for t in range(80):
+        obs, rew, done, _ = env.step(torch.zeros(n, 17, device="cuda"))
+        assert bool(torch.isfinite(obs).all())
+        assert int(env.get_state()[1][:, B.E_FRAME].max()) < 119
+    env.close()

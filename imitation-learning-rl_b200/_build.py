@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libilrl_b200.so")
 SRC = os.path.join(HERE, "csrc", "ilrl_capi.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("ilrl_env.cuh", "ilrl_quad.cuh", "ilrl_physics.cuh", "ilrl_constants.h",
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("ilrl_env.cuh", "ilrl_chain.cuh", "ilrl_physics.cuh", "ilrl_constants.h",
                                                         "ilrl_model_data.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "ilrl.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",

@@ -17,13 +17,13 @@
 #include <string>
 
 #include "../../include/ilrl.h"
-#include "ilrl_quad.cuh"
+#include "ilrl_chain.cuh"
 
 namespace ilrl {
 
 constexpr int BLOCK = 64;  // threads per CTA of the thread-per-env service kernels (reset, high step, harness)
-using quad::QE;
-using quad::QT;
+using chain::QE;
+using chain::QT;
 
 struct StepArgs {
   int n;
@@ -45,7 +45,7 @@ struct StepArgs {
   uint8_t* high_flags; // [n]
   const int32_t* forced_deg;  // [n] or null
   float* stats;        // [16] or null
-  float* gscr;         // [n][GROWS][ROWW] overflow scratch for constraint rows beyond the shared-memory budget
+  float* gscr;         // [n][GROWS][RW] overflow scratch for constraint rows beyond the shared-memory budget
   ClipDesc clips[MAX_CLIPS];
 };
 
@@ -84,13 +84,26 @@ __device__ __forceinline__ void store_state(const StepArgs& a, int i, const Phys
   for (int k = 0; k < ILRL_ENV_WORDS; k++) e[k * n] = w.e[k];
 }
 
-// shared-memory setup common to the quad kernels: role constants in, response scratch zeroed
-__device__ __forceinline__ void quad_smem_init(quad::Smem& sm) {
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(&quad::kRoles);
-  uint32_t* dst = &sm.role[0][0];
-  for (int t = threadIdx.x; t < 4 * quad::ROLE_WORDS; t += QT) dst[t] = src[t];
-  float* z = &sm.scr[0][0][0];
-  for (int t = threadIdx.x; t < QT * 3 * NJ; t += QT) z[t] = 0.f;
+// shared-memory setup common to the quad kernels: model tables in, response scratch zeroed
+__device__ __forceinline__ void quad_smem_init(chain::Smem& sm) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&chain::kTables);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.T);
+  for (int t = threadIdx.x; t < chain::TABLE_WORDS; t += QT) dst[t] = src[t];
+  float* z = &sm.su[0][0][0];
+  for (int t = threadIdx.x; t < 3 * chain::NL * QT; t += QT) z[t] = 0.f;
+}
+// torques of this lane's chain into the link records: apply_action (REF humanoid.py:54-60): clip, gear x power,
+// motor slot -> joint.  act: the env's action row in shared memory (null: joint-order torques in `torque`)
+__device__ __forceinline__ void set_torques(chain::Smem& sm, int e, int tid, int role, const float* act, const float* torque) {
+#pragma unroll
+  for (int c = 0; c < chain::NL; c++) {
+    int st;
+    float* rec = chain::link_rec(sm, c, e, tid, st);
+    const chain::LinkC& L = c < 3 ? sm.T.lc[4][c] : sm.T.lc[role][c - 3];
+    float t = 0.f;
+    if (L.j >= 0) t = act ? L.gear * fminf(fmaxf(act[L.motor], -1.f), 1.f) : torque[L.j];
+    rec[chain::W_TAU * st] = t;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K1: fused step
@@ -101,8 +114,8 @@ __device__ __forceinline__ void quad_smem_init(quad::Smem& sm) {
 template <int MODE>
 __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  quad::Smem& sm = *reinterpret_cast<quad::Smem*>(smraw);
-  const int tid = threadIdx.x, e = tid >> 2, role = tid & 3;
+  chain::Smem& sm = *reinterpret_cast<chain::Smem*>(smraw);
+  const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
   const int base = blockIdx.x * QE;
   const int i = base + e;
@@ -114,7 +127,6 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     for (int t = tid; t < cnt; t += QT) dst[t] = a.action[(size_t)base * NJ + t];
   }
   __syncthreads();
-  const quad::Role& rc = *reinterpret_cast<const quad::Role*>(sm.role[role]);
   bool write_obs = false;
   float st_ep = 0.f, st_ret = 0.f, st_len = 0.f, st_steps = 0.f, st_rew = 0.f, st_terms[11];
 #pragma unroll
@@ -129,36 +141,31 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     if (a.terms)
       for (int t = role; t < ILRL_TERM_WORDS; t += 4) a.terms[(size_t)i * ILRL_TERM_WORDS + t] = 0.f;
   } else if (valid) {
-    quad::QState s;
-    quad::qload(a.phys, a.n, i, rc, s);
+    chain::Base b;
+    chain::load_base(a.phys, a.n, i, b);
+    chain::load_links(a.phys, a.n, i, sm, e, tid, role);
     float act[NJ];
 #pragma unroll
     for (int m = 0; m < NJ; m++) act[m] = sm.act[e][m];
-    // apply_action (REF humanoid.py:54-60): clip, gear x power, motor slot -> joint slot
-    float tau_s[3], tau_l[4];
-#pragma unroll
-    for (int m = 0; m < 3; m++) tau_s[m] = kMotorGear[m] * fminf(fmaxf(act[m], -1.f), 1.f);  // motors 0..2 = spine joints 0..2
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      tau_l[k] = rc.motor[k] >= 0 ? rc.gear[k] * fminf(fmaxf(sm.act[e][rc.motor[k]], -1.f), 1.f) : 0.f;
+    set_torques(sm, e, tid, role, sm.act[e], nullptr);
+    __syncwarp(qm);
     float stale_x = 0.f, stale_y = 0.f;
+    float sumx, sumy, rfx, rfy;
     if (MODE == 1) {
       // (Q13) robot_pos is refreshed from the PREVIOUS calc_state at the top of step()
-      float sx, sy, fx, fy;
-      quad::qpose_sums(s, rc, qm, sx, sy, fx, fy);
-      stale_x = (32.f * s.p[0] + sx) * (1.f / 33.f);
-      stale_y = (32.f * s.p[1] + sy) * (1.f / 33.f);
+      chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);
+      stale_x = (32.f * b.p[0] + sumx) * (1.f / 33.f);
+      stale_y = (32.f * b.p[1] + sumy) * (1.f / 33.f);
     }
     if (!a.skip_physics) {
-      float* gscr = a.gscr + (size_t)i * quad::GROWS * quad::ROWW;
+      float* gscr = a.gscr + (size_t)i * chain::GROWS * chain::RW;
 #pragma unroll 1
       for (int sub = 0; sub < ILRL_SUBSTEPS; sub++)
-        quad::qsubstep(s, tau_s, tau_l, rc, sm, gscr, e, tid, role, qm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+        chain::substep(b, sm, gscr, e, tid, role, qm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
     }
-    float sumx, sumy, rfx, rfy;
-    quad::qpose_sums(s, rc, qm, sumx, sumy, rfx, rfy);
+    chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);
     Phys ps;
-    quad::qgather(s, rc, sm, e, role, qm, ps);
+    chain::gather(b, sm, e, qb, qm, ps);
     EnvW w;
     {
       const float* ew = a.envf + i;
@@ -237,8 +244,8 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
         int tdeg = rand_int(a.seed, (uint32_t)i, ctr, -180, 180);
         ResetCtx rx;
         reset_pose<MODE>(ps, w, cl, sf, yaw, tdeg, rx);
-        quad::qscatter(ps, rc, sm, e, role, qm, s);
-        quad::qpose_sums(s, rc, qm, sumx, sumy, rfx, rfy);
+        chain::scatter(ps, sm, e, qb, role, qm, b);
+        chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);
         reset_finish<MODE>(ps, w, cl, rx, rfx, rfy, sumx, sumy, a.step_per_level, c);
         if (MODE == 0) {
           float obs[70];
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
       if (MODE == 1) a.high_flags[i] = hflags;
       a.rng[i] = ctr;
     }
-    quad::qstore_phys(a.phys, a.n, i, role, ps);
+    chain::store_phys(a.phys, a.n, i, role, ps);
     {
       float* ew = a.envf + i;
 #pragma unroll
@@ -401,27 +408,24 @@ __global__ void clip_ids_kernel(StateView v, const int32_t* ids) {
 }
 __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const float* torque, float* gscr_all, int nsub) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  quad::Smem& sm = *reinterpret_cast<quad::Smem*>(smraw);
-  const int tid = threadIdx.x, e = tid >> 2, role = tid & 3;
+  chain::Smem& sm = *reinterpret_cast<chain::Smem*>(smraw);
+  const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
   const int i = blockIdx.x * QE + e;
   quad_smem_init(sm);
   __syncthreads();
   if (i >= v.n) return;
-  const quad::Role& rc = *reinterpret_cast<const quad::Role*>(sm.role[role]);
-  quad::QState s;
-  quad::qload(v.phys, v.n, i, rc, s);
-  float tau_s[3], tau_l[4];
-#pragma unroll
-  for (int k = 0; k < 3; k++) tau_s[k] = torque[(size_t)i * NJ + k];
-#pragma unroll
-  for (int k = 0; k < 4; k++) tau_l[k] = rc.j[k] >= 0 ? torque[(size_t)i * NJ + rc.j[k]] : 0.f;
-  float* gscr = gscr_all + (size_t)i * quad::GROWS * quad::ROWW;
+  chain::Base b;
+  chain::load_base(v.phys, v.n, i, b);
+  chain::load_links(v.phys, v.n, i, sm, e, tid, role);
+  set_torques(sm, e, tid, role, nullptr, torque + (size_t)i * NJ);
+  __syncwarp(qm);
+  float* gscr = gscr_all + (size_t)i * chain::GROWS * chain::RW;
   for (int sub = 0; sub < nsub; sub++)
-    quad::qsubstep(s, tau_s, tau_l, rc, sm, gscr, e, tid, role, qm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+    chain::substep(b, sm, gscr, e, tid, role, qm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
   Phys ps;
-  quad::qgather(s, rc, sm, e, role, qm, ps);
-  quad::qstore_phys(v.phys, v.n, i, role, ps);
+  chain::gather(b, sm, e, qb, qm, ps);
+  chain::store_phys(v.phys, v.n, i, role, ps);
 }
 struct EpArgs { StateView v; float* score; ClipDesc clips[MAX_CLIPS]; };
 __global__ void __launch_bounds__(BLOCK) endpoint_kernel(const EpArgs a) {
@@ -520,10 +524,10 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMalloc(&env->phys, sizeof(float) * ILRL_PHYS_WORDS * n));
   CKC(cudaMalloc(&env->envf, sizeof(float) * ILRL_ENV_WORDS * n));
   CKC(cudaMalloc(&env->rng, sizeof(uint32_t) * n));
-  CKC(cudaMalloc(&env->gscr, sizeof(float) * (size_t)quad::GROWS * quad::ROWW * n));
-  CKC(cudaFuncSetAttribute(step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(quad::Smem)));
-  CKC(cudaFuncSetAttribute(step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(quad::Smem)));
-  CKC(cudaFuncSetAttribute(physics_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(quad::Smem)));
+  CKC(cudaMalloc(&env->gscr, sizeof(float) * (size_t)chain::GROWS * chain::RW * n));
+  CKC(cudaFuncSetAttribute(step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(chain::Smem)));
+  CKC(cudaFuncSetAttribute(step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(chain::Smem)));
+  CKC(cudaFuncSetAttribute(physics_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(chain::Smem)));
   CKC(cudaMalloc(&env->high_obs, sizeof(float) * 44 * n));
   CKC(cudaMalloc(&env->high_reward, sizeof(float) * n));
   CKC(cudaMalloc(&env->high_flags, n));
@@ -644,8 +648,8 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   cudaStream_t st = (cudaStream_t)stream;
   if (env->timing) CK(cudaEventRecord(env->ev0, st));
   const int qblk = (env->n + QE - 1) / QE;
-  if (env->cfg.mode == 0) step_kernel<0><<<qblk, QT, sizeof(quad::Smem), st>>>(a);
-  else step_kernel<1><<<qblk, QT, sizeof(quad::Smem), st>>>(a);
+  if (env->cfg.mode == 0) step_kernel<0><<<qblk, QT, sizeof(chain::Smem), st>>>(a);
+  else step_kernel<1><<<qblk, QT, sizeof(chain::Smem), st>>>(a);
   env->launches++;
   CK(cudaGetLastError());
   if (env->timing) {
@@ -755,7 +759,7 @@ int ilrl_physics_only(ilrl_env* env, const float* torque, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (!torque) return fail(env, ILRL_ERR_ARG, "ilrl_physics_only: null buffer");
   CK(cudaSetDevice(env->cfg.device));
-  physics_only_kernel<<<(env->n + QE - 1) / QE, QT, sizeof(quad::Smem), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);
+  physics_only_kernel<<<(env->n + QE - 1) / QE, QT, sizeof(chain::Smem), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);
   env->launches++;
   CK(cudaGetLastError());
   return ILRL_OK;

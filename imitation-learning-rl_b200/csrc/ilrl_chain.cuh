@@ -1,0 +1,907 @@
+// ilrl_chain.cuh — third kernel generation of the physics substep: FOUR LANES PER ENV, every per-link computation a
+// ROLLED loop over a 7-link chain, all per-link data in shared memory.
+//
+// Why (profiles/r1_v2_step_kernel_ncu.md): the second generation kept each limb in registers and therefore had to be
+// fully unrolled: 12 k SASS instructions (190 KB) per substep, re-fetched from L2 four times per env step; 36 % of the
+// stall samples were `no_instruction`.  Here
+//   * lane r of a quad walks the chain  spine(3 links, identical in all four lanes) + limb r (4 slots; the arms have a
+//     leading dummy slot with a zero axis).  For the legs that chain IS the path torso -> foot; the arms restart from
+//     the torso at chain index 3.  Forward kinematics / velocities / body inertias, the inward articulated-inertia
+//     pass and the outward acceleration pass are three `#pragma unroll 1` loops over the chain index whose bodies are
+//     a few hundred instructions each: one substep is ~4 k instructions and its loops run out of the instruction caches;
+//   * per-link records (S, cJ, U, 1/D, u, q, qd, tau, nu) live in shared memory, thread-minor (conflict-free); the
+//     spine's are stored once per env.  They double as the publication that lets ANY lane build constraint rows;
+//   * the limbs' articulated inertias meet at the pelvis / torso through two rounds of __shfl_xor over 27 words;
+//   * constraint rows are built three at a time (one contact = normal + 2 friction directions, or up to three joint
+//     limits) by ONE routine with 3-way instruction-level parallelism, dealt round-robin to the lanes, and stored as
+//     40-word records (128-bit loads, env stride = 4 mod 32 words: the 8 envs of a warp hit 8 different bank groups);
+//   * projected Gauss-Seidel keeps the velocity change distributed like the state (base + spine replicated, limb
+//     private); a row's limb part belongs to one lane, so the 4-lane reduction is a single broadcast shuffle.
+// Row order, row formulas and constants are exactly those of the oracle (oracle/ilrl_oracle.c) and of the earlier
+// generations (git history): limits in joint order, then contacts in sphere-table order, 5 sweeps.
+#pragma once
+#include "ilrl_env.cuh"
+
+namespace ilrl {
+namespace chain {
+
+#ifndef ILRL_QE
+#define ILRL_QE 16
+#endif
+#ifndef ILRL_RSM
+#define ILRL_RSM 16
+#endif
+constexpr int QE = ILRL_QE;            // envs per CTA
+constexpr int QT = 4 * QE;             // threads per CTA
+constexpr int NL = 7;                  // chain links per lane: 3 spine + 4 limb slots
+constexpr int RSM = ILRL_RSM;          // constraint rows per env kept in shared memory (the rest: global scratch)
+constexpr int RW = 40;                 // words per stored row
+constexpr int ROWSTRIDE = RSM * RW + 4;  // env stride in words: = 4 (mod 32)
+constexpr int GROWS = MAXROWS - RSM;   // rows per env in the global overflow scratch
+// link record words
+enum { W_S = 0, W_CJ = 6, W_U = 12, W_DINV = 18, W_UU = 19, W_Q = 20, W_QD = 21, W_TAU = 22, W_NU = 23, LKW = 24 };
+// body record words: rigid inertia about the reference point (A 6, m*c 3, m 1) + bias force 6
+constexpr int RECW = 16;
+// stored row words
+enum { R_RB = 0 /*resp base 6*/, R_RS = 6 /*resp spine 3*/, R_JS = 9 /*J spine 3*/, R_JB = 12 /*J base 6*/, R_RHS = 18,
+       R_DINV = 19, R_RL = 20 /*resp limbs 4x4*/, R_JL = 36 /*J of the row's limb 4*/ };
+
+// ---- compile-time model tables in chain form
+struct LinkC {
+  float pre[3];   // translation (parent body frame) applied before the joint: the body position when the link starts a body
+  float an[3];    // joint anchor (body frame)
+  float ax[3];    // joint axis (body frame); zero for a dummy slot
+  float lo, hi;   // limits (dummy: never violated)
+  float gear;     // torque per unit of clipped action
+  int j;          // global joint index, -1 = dummy slot
+  int motor;      // action slot that drives the joint (humanoid.py:28-37), -1 = none
+  int rot;        // 1: the body that starts here carries the fixed rotation kQ
+  int nbody;      // rigid bodies completed by this link
+};
+struct BodyC {
+  float off[3];      // body origin relative to the link's body origin (0, or the fixed child's position)
+  float m, ix, iy, iz;
+  int nsph;
+  float sph[2][4];   // centre (body frame), radius
+  int sidx[2];       // global sphere index
+  int pad[2];
+};
+struct Tables {
+  LinkC lc[5][4];        // chains 0..3 = limbs (right leg, left leg, right arm, left arm), 4 = spine (3 links)
+  BodyC bc[5][2][2];     // [chain][slot][k]: limb slot 0 = link 2 (body A), slot 1 = link 3 (bodies B, E);
+                         //                    spine slot 0 = link 1 (lwaist), slot 1 = link 2 (pelvis)
+  int sphL[NS], sphC[NS];  // chain (limb 0..3, -1 = spine/torso) and chain index (-1 = torso) carrying sphere g
+  int jL[NJ], jC[NJ];      // the same for joint j
+  float Q[9];              // fixed rotation of lwaist / pelvis in their parent frame
+  constexpr Tables() : lc(), bc(), sphL(), sphC(), jL(), jC(), Q() {
+    constexpr int jb[NJ] = ILRL_JOINT_BODY;
+    constexpr double bp[NB * 3] = ILRL_BODY_POS;
+    constexpr double bq[NB * 4] = ILRL_BODY_QUAT;
+    constexpr double bm[NB] = ILRL_BODY_MASS;
+    constexpr double bi[NB * 3] = ILRL_BODY_INERTIA;
+    constexpr double ja[NJ * 3] = ILRL_JOINT_ANCHOR;
+    constexpr double jx[NJ * 3] = ILRL_JOINT_AXIS;
+    constexpr double jlo[NJ] = ILRL_JOINT_LO;
+    constexpr double jhi[NJ] = ILRL_JOINT_HI;
+    constexpr int sb[NS] = ILRL_SPHERE_BODY;
+    constexpr int sl[NS] = ILRL_SPHERE_LINK;
+    constexpr double sc[NS * 3] = ILRL_SPHERE_C;
+    constexpr double sr[NS] = ILRL_SPHERE_R;
+    constexpr int mj[NJ] = ILRL_MOTOR_JOINT;
+    constexpr double mg[NJ] = ILRL_MOTOR_GEAR;
+    constexpr int first[4] = {3, 7, 11, 14};
+    constexpr int count[4] = {4, 4, 3, 3};
+    int body_of[5][2][2] = {};
+    for (int q = 0; q < 5; q++) {
+      for (int k = 0; k < 4; k++) {
+        LinkC& o = lc[q][k];
+        int j = -1;
+        if (q < 4) { const int lead = 4 - count[q]; j = k < lead ? -1 : first[q] + (k - lead); }
+        else if (k < 3) j = k;
+        o.j = j; o.motor = -1; o.gear = 0.f; o.rot = 0; o.nbody = 0;
+        o.lo = -1e30f; o.hi = 1e30f;
+        for (int i = 0; i < 3; i++) { o.pre[i] = 0.f; o.an[i] = 0.f; o.ax[i] = 0.f; }
+        if (q == 4 && k == 3) continue;
+        const int jr = j >= 0 ? j : first[q];          // a dummy slot borrows the anchor of the body's first joint
+        for (int i = 0; i < 3; i++) { o.an[i] = (float)ja[3 * jr + i]; if (j >= 0) o.ax[i] = (float)jx[3 * j + i]; }
+        if (j >= 0) {
+          o.lo = (float)jlo[j]; o.hi = (float)jhi[j];
+          for (int m = 0; m < NJ; m++) if (mj[m] == j) { o.motor = m; o.gear = (float)mg[m]; }
+        }
+        // does this link start a new body?  (first link of the chain, or the body of its joint differs from the previous link's)
+        const int b = jb[jr];
+        bool starts = k == 0;
+        if (k > 0) { const int jp = lc[q][k - 1].j >= 0 ? lc[q][k - 1].j : first[q]; starts = jb[jp] != b; }
+        if (starts) {
+          for (int i = 0; i < 3; i++) o.pre[i] = (float)bp[3 * b + i];
+          o.rot = (bq[4 * b] != 0.0 || bq[4 * b + 1] != 0.0 || bq[4 * b + 2] != 0.0) ? 1 : 0;
+        }
+      }
+      // bodies completed by links
+      if (q < 4) {
+        const int bA = jb[first[q]], bB = jb[first[q] + count[q] - 1], bE = bB + 1;
+        lc[q][2].nbody = 1; lc[q][3].nbody = 2;
+        body_of[q][0][0] = bA; body_of[q][0][1] = -1; body_of[q][1][0] = bB; body_of[q][1][1] = bE;
+      } else {
+        lc[q][1].nbody = 1; lc[q][2].nbody = 1;
+        body_of[q][0][0] = 1; body_of[q][0][1] = -1; body_of[q][1][0] = 2; body_of[q][1][1] = -1;
+      }
+      for (int s = 0; s < 2; s++)
+        for (int k = 0; k < 2; k++) {
+          BodyC& o = bc[q][s][k];
+          const int b = body_of[q][s][k];
+          o.nsph = 0; o.m = 0.f; o.ix = o.iy = o.iz = 0.f; o.pad[0] = o.pad[1] = 0;
+          for (int i = 0; i < 3; i++) o.off[i] = 0.f;
+          for (int t = 0; t < 2; t++) { o.sidx[t] = 0; for (int i = 0; i < 4; i++) o.sph[t][i] = 0.f; }
+          if (b < 0) continue;
+          if (k == 1) for (int i = 0; i < 3; i++) o.off[i] = (float)bp[3 * b + i];   // fixed child of the slot's first body
+          o.m = (float)bm[b]; o.ix = (float)bi[3 * b]; o.iy = (float)bi[3 * b + 1]; o.iz = (float)bi[3 * b + 2];
+          for (int g = 0; g < NS; g++)
+            if (sb[g] == b) {
+              const int t = o.nsph++;
+              o.sidx[t] = g;
+              for (int i = 0; i < 3; i++) o.sph[t][i] = (float)sc[3 * g + i];
+              o.sph[t][3] = (float)sr[g];
+            }
+        }
+    }
+    for (int j = 0; j < NJ; j++) {
+      if (j < 3) { jL[j] = -1; jC[j] = j; }
+      else
+        for (int q = 0; q < 4; q++)
+          for (int k = 0; k < 4; k++) if (lc[q][k].j == j) { jL[j] = q; jC[j] = 3 + k; }
+    }
+    for (int g = 0; g < NS; g++) {
+      if (sl[g] < 0) { sphL[g] = -1; sphC[g] = -1; } else { sphL[g] = jL[sl[g]]; sphC[g] = jC[sl[g]]; }
+    }
+    // kQ from the quaternion of body 1 (bodies 1 and 2 carry the same one)
+    const double x = bq[4], y = bq[5], z = bq[6], w = bq[7];
+    const double s = 2.0 / (x * x + y * y + z * z + w * w);
+    Q[0] = (float)(1 - s * (y * y + z * z)); Q[1] = (float)(s * (x * y - w * z)); Q[2] = (float)(s * (x * z + w * y));
+    Q[3] = (float)(s * (x * y + w * z)); Q[4] = (float)(1 - s * (x * x + z * z)); Q[5] = (float)(s * (y * z - w * x));
+    Q[6] = (float)(s * (x * z - w * y)); Q[7] = (float)(s * (y * z + w * x)); Q[8] = (float)(1 - s * (x * x + y * y));
+  }
+};
+__device__ constexpr Tables kTables{};
+constexpr int TABLE_WORDS = sizeof(Tables) / 4;
+static_assert(sizeof(Tables) % 4 == 0, "table copy is word-wise");
+
+// ---- shared memory of one CTA
+struct __align__(16) Smem {
+  float rows[QE][ROWSTRIDE];   // stored rows (first: 16-byte aligned)
+  Tables T;
+  float lk[4][LKW][QT];        // limb link records, per thread
+  float sp[3][LKW][QE];        // spine link records, per env
+  float rl[2][RECW][QT];       // limb body records (slot 0 = A, 1 = B + E)
+  float rs[2][RECW][QE];       // spine body records (slot 0 = lwaist, 1 = pelvis)
+  float L0[21][QE];            // Cholesky factor of the base articulated inertia
+  float sph[NS][4][QE];        // contact candidates: x, y, z - r (relative to the torso origin), distance
+  float lam[MAXROWS][QE];
+  float su[3][NL][QT];         // response scratch: u of the chain links of up to 3 impulses (kept zero between uses)
+  float act[QE][NJ];           // actions (motor order)
+  float obs[QE][71];
+  signed char rowL[MAXROWS][QE];  // limb that owns the row's limb block (-1: none)
+};
+
+// replicated floating-base state of one env
+struct Base { float p[3], quat[4], v[3], w[3]; };
+
+__device__ __forceinline__ float qsum(float v, unsigned qm) {
+  v += __shfl_xor_sync(qm, v, 1);
+  v += __shfl_xor_sync(qm, v, 2);
+  return v;
+}
+__device__ __forceinline__ SV neg(SV a) { SV r; r.a = mk(-a.a.x, -a.a.y, -a.a.z); r.l = mk(-a.l.x, -a.l.y, -a.l.z); return r; }
+__device__ __forceinline__ SV svzero() { SV r; r.a = r.l = mk(0, 0, 0); return r; }
+__device__ __forceinline__ V3 rd3(const float* p) { return mk(p[0], p[1], p[2]); }
+__device__ __forceinline__ float rcp_or_zero(float d) { return d > 1e-9f ? __frcp_rn(d) : 0.f; }
+
+// sin/cos of a joint angle.  Joint angles stay within a few radians of their limits (|q| << 100), so the Payne-Hanek
+// large-argument path of sincosf() would be dead weight in the instruction stream: two-constant Cody-Waite reduction
+// by pi/2 + the minimax polynomials of the usual fast path, max error 7e-8 for |q| < 100 (checked on the host).
+__device__ __forceinline__ void sincos_joint(float x, float& s, float& c) {
+  const float k = rintf(x * 0.636619772f);
+  float r = fmaf(k, -1.57079601e+00f, x);
+  r = fmaf(k, -3.13916473e-07f, r);
+  r = fmaf(k, -5.39030253e-15f, r);
+  const int q = (int)k;
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.95152959e-4f, 8.33216087e-3f);
+  sp = fmaf(sp, r2, -1.66666546e-1f);
+  sp = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.44331571e-5f, -1.38873163e-3f);
+  cp = fmaf(cp, r2, 4.16666457e-2f);
+  cp = fmaf(cp, r2, -0.5f);
+  cp = fmaf(cp, r2, 1.0f);
+  const float a = (q & 1) ? cp : sp, b = (q & 1) ? sp : cp;
+  s = (q & 2) ? -a : a;
+  c = ((q + 1) & 2) ? -b : b;
+}
+
+// position of the n-th (0-based) set bit of m (m has more than n bits set)
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+#pragma unroll 1
+  for (int i = 0; i < n; i++) m &= m - 1;
+  return __ffs(m) - 1;
+}
+
+// link record of chain index c of THIS lane (spine: the env's shared record), and its word stride
+__device__ __forceinline__ float* link_rec(Smem& sm, int c, int e, int tid, int& st) {
+  st = c < 3 ? QE : QT;
+  return c < 3 ? &sm.sp[c][0][e] : &sm.lk[c - 3][0][tid];
+}
+// link record of chain index c of limb L of this env (L < 0 or c < 3: spine)
+__device__ __forceinline__ const float* link_rec_of(const Smem& sm, int L, int c, int e, int qb, int& st) {
+  st = c < 3 ? QE : QT;
+  return c < 3 ? &sm.sp[c][0][e] : &sm.lk[c - 3][0][qb + L];
+}
+__device__ __forceinline__ SV ld6(const float* p, int st) {
+  SV r; r.a = mk(p[0], p[st], p[2 * st]); r.l = mk(p[3 * st], p[4 * st], p[5 * st]);
+  return r;
+}
+__device__ __forceinline__ void st6(float* p, int st, SV v) {
+  p[0] = v.a.x; p[st] = v.a.y; p[2 * st] = v.a.z; p[3 * st] = v.l.x; p[4 * st] = v.l.y; p[5 * st] = v.l.z;
+}
+
+// rigid inertia (about the reference point, world axes) and bias force of one body, ACCUMULATED into rec[16]
+__device__ __forceinline__ void rigid_rec(const float* R, V3 c, float m, float ix, float iy, float iz, SV V, float* rec) {
+  float Ic[6];
+  Ic[0] = ix * R[0] * R[0] + iy * R[1] * R[1] + iz * R[2] * R[2];
+  Ic[1] = ix * R[0] * R[3] + iy * R[1] * R[4] + iz * R[2] * R[5];
+  Ic[2] = ix * R[0] * R[6] + iy * R[1] * R[7] + iz * R[2] * R[8];
+  Ic[3] = ix * R[3] * R[3] + iy * R[4] * R[4] + iz * R[5] * R[5];
+  Ic[4] = ix * R[3] * R[6] + iy * R[4] * R[7] + iz * R[5] * R[8];
+  Ic[5] = ix * R[6] * R[6] + iy * R[7] * R[7] + iz * R[8] * R[8];
+  const float cc = dot(c, c);
+  rec[0] += Ic[0] + m * (cc - c.x * c.x); rec[1] += Ic[1] - m * c.x * c.y; rec[2] += Ic[2] - m * c.x * c.z;
+  rec[3] += Ic[3] + m * (cc - c.y * c.y); rec[4] += Ic[4] - m * c.y * c.z; rec[5] += Ic[5] + m * (cc - c.z * c.z);
+  rec[6] += m * c.x; rec[7] += m * c.y; rec[8] += m * c.z; rec[9] += m;
+  // momentum about the reference point and its velocity-product rate; gravity + Bullet's damping as external forces
+  V3 vc = V.l + cross(V.a, c);
+  V3 Iw = symv(Ic, V.a);
+  SV h; h.l = m * vc; h.a = Iw + cross(c, h.l);
+  SV pb = crf(V, h);
+  const float vn = sqrtf(dot(vc, vc)), wn = sqrtf(dot(V.a, V.a));
+  const float kl = m * ((float)ILRL_DAMP_K1_LIN + (float)ILRL_DAMP_K2_LIN * vn);
+  const float ka = (float)ILRL_DAMP_K1_ANG + (float)ILRL_DAMP_K2_ANG * wn;
+  V3 F = mk(-kl * vc.x, -kl * vc.y, -kl * vc.z - m * (float)ILRL_GRAVITY);
+  V3 N = mk(-ka * Iw.x, -ka * Iw.y, -ka * Iw.z);
+  pb.a = pb.a - (N + cross(c, F));
+  pb.l = pb.l - F;
+  rec[10] += pb.a.x; rec[11] += pb.a.y; rec[12] += pb.a.z; rec[13] += pb.l.x; rec[14] += pb.l.y; rec[15] += pb.l.z;
+}
+
+struct IP { Inertia I; SV p; };  // articulated inertia + bias force (27 words)
+
+__device__ __forceinline__ void ip_add_rec(IP& x, const float* r, int st) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) x.I.A[i] += r[i * st];
+  const float mx = r[6 * st], my = r[7 * st], mz = r[8 * st], m = r[9 * st];
+  x.I.B[1] -= mz; x.I.B[2] += my; x.I.B[3] += mz; x.I.B[5] -= mx; x.I.B[6] -= my; x.I.B[7] += mx;
+  x.I.C[0] += m; x.I.C[3] += m; x.I.C[5] += m;
+  x.p.a.x += r[10 * st]; x.p.a.y += r[11 * st]; x.p.a.z += r[12 * st];
+  x.p.l.x += r[13 * st]; x.p.l.y += r[14 * st]; x.p.l.z += r[15 * st];
+}
+__device__ __forceinline__ void ip_shfl_add(IP& x, unsigned qm, int lane_mask) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) { x.I.A[i] += __shfl_xor_sync(qm, x.I.A[i], lane_mask); x.I.C[i] += __shfl_xor_sync(qm, x.I.C[i], lane_mask); }
+#pragma unroll
+  for (int i = 0; i < 9; i++) x.I.B[i] += __shfl_xor_sync(qm, x.I.B[i], lane_mask);
+  x.p.a.x += __shfl_xor_sync(qm, x.p.a.x, lane_mask); x.p.a.y += __shfl_xor_sync(qm, x.p.a.y, lane_mask);
+  x.p.a.z += __shfl_xor_sync(qm, x.p.a.z, lane_mask); x.p.l.x += __shfl_xor_sync(qm, x.p.l.x, lane_mask);
+  x.p.l.y += __shfl_xor_sync(qm, x.p.l.y, lane_mask); x.p.l.z += __shfl_xor_sync(qm, x.p.l.z, lane_mask);
+}
+__device__ __forceinline__ IP ip_shfl_get(const IP& x, unsigned qm, int lane_mask) {
+  IP y;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { y.I.A[i] = __shfl_xor_sync(qm, x.I.A[i], lane_mask); y.I.C[i] = __shfl_xor_sync(qm, x.I.C[i], lane_mask); }
+#pragma unroll
+  for (int i = 0; i < 9; i++) y.I.B[i] = __shfl_xor_sync(qm, x.I.B[i], lane_mask);
+  y.p.a.x = __shfl_xor_sync(qm, x.p.a.x, lane_mask); y.p.a.y = __shfl_xor_sync(qm, x.p.a.y, lane_mask);
+  y.p.a.z = __shfl_xor_sync(qm, x.p.a.z, lane_mask); y.p.l.x = __shfl_xor_sync(qm, x.p.l.x, lane_mask);
+  y.p.l.y = __shfl_xor_sync(qm, x.p.l.y, lane_mask); y.p.l.z = __shfl_xor_sync(qm, x.p.l.z, lane_mask);
+  return y;
+}
+
+// Cholesky factor of the base inertia, stored per env in shared memory (diagonal entries hold 1 / L_jj)
+__device__ __forceinline__ void chol6_to_smem(const Inertia& I, float* L /* [21][QE], this env's column */) {
+  float Lr[21];
+  chol6(I, Lr);
+#pragma unroll
+  for (int i = 0; i < 21; i++) L[i * QE] = Lr[i];
+}
+__device__ __forceinline__ SV chol6_solve_smem(const float* L, SV b) {
+  float y[6] = {b.a.x, b.a.y, b.a.z, b.l.x, b.l.y, b.l.z};
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float t = y[i];
+#pragma unroll
+    for (int c = 0; c < i; c++) t -= L[(i * (i + 1) / 2 + c) * QE] * y[c];
+    y[i] = t * L[(i * (i + 1) / 2 + i) * QE];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    float t = y[i];
+#pragma unroll
+    for (int c = i + 1; c < 6; c++) t -= L[(c * (c + 1) / 2 + i) * QE] * y[c];
+    y[i] = t * L[(i * (i + 1) / 2 + i) * QE];
+  }
+  SV r; r.a = mk(y[0], y[1], y[2]); r.l = mk(y[3], y[4], y[5]);
+  return r;
+}
+
+// ---- phase A: forward kinematics, link velocities, velocity-product accelerations, body records, contact candidates.
+// Returns the candidate mask of the spheres this lane saw, the sums of part origins (spine part replicated in ssx/ssy,
+// limb part in sx/sy) and the origin of the lane's end body.
+struct FkOut { uint32_t act; float sx, sy, ssx, ssy, ex, ey; };
+
+__device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid, int role, FkOut& o) {
+  const Tables& T = sm.T;
+  float R0[9];
+  quat2mat(b.quat[0], b.quat[1], b.quat[2], b.quat[3], R0);
+  SV V0; V0.a = rd3(b.w); V0.l = rd3(b.v);
+  uint32_t act = 0;
+  // torso spheres
+#pragma unroll 1
+  for (int g = NS - 5; g < NS; g++) {
+    V3 c = mv(R0, mk(kSphereC[3 * g], kSphereC[3 * g + 1], kSphereC[3 * g + 2]));
+    const float rad = kSphereR[g], d = b.p[2] + c.z - rad;
+    if (d < (float)ILRL_CONTACT_BREAK) act |= 1u << g;
+    float* sp = &sm.sph[g][0][e];
+    sp[0] = c.x; sp[QE] = c.y; sp[2 * QE] = c.z - rad; sp[3 * QE] = d;
+  }
+  float Rc[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) Rc[i] = R0[i];
+  V3 oc = mk(0.f, 0.f, 0.f);
+  SV Vp = V0;
+  float sx = 0.f, sy = 0.f, ssx = 0.f, ssy = 0.f, ex = 0.f, ey = 0.f;
+#pragma unroll 1
+  for (int c = 0; c < NL; c++) {
+    if (c == 3 && role >= 2) {  // the arms hang off the torso
+#pragma unroll
+      for (int i = 0; i < 9; i++) Rc[i] = R0[i];
+      oc = mk(0.f, 0.f, 0.f);
+      Vp = V0;
+    }
+    const LinkC& L = c < 3 ? T.lc[4][c] : T.lc[role][c - 3];
+    int st;
+    float* rec = link_rec(sm, c, e, tid, st);
+    oc = oc + mv(Rc, rd3(L.pre));
+    if (L.rot) {
+      float Rn[9];
+      mm(Rc, T.Q, Rn);
+#pragma unroll
+      for (int i = 0; i < 9; i++) Rc[i] = Rn[i];
+    }
+    const V3 an = rd3(L.an), ax = rd3(L.ax);
+    const V3 rw = oc + mv(Rc, an);
+    SV S;
+    S.a = mv(Rc, ax);
+    S.l = cross(rw, S.a);
+    {
+      float sn, cs;
+      sincos_joint(rec[W_Q * st], sn, cs);
+      const float t = 1.f - cs;
+      float Rj[9], Rn[9];
+      Rj[0] = t * ax.x * ax.x + cs;        Rj[1] = t * ax.x * ax.y - sn * ax.z; Rj[2] = t * ax.x * ax.z + sn * ax.y;
+      Rj[3] = t * ax.x * ax.y + sn * ax.z; Rj[4] = t * ax.y * ax.y + cs;        Rj[5] = t * ax.y * ax.z - sn * ax.x;
+      Rj[6] = t * ax.x * ax.z - sn * ax.y; Rj[7] = t * ax.y * ax.z + sn * ax.x; Rj[8] = t * ax.z * ax.z + cs;
+      mm(Rc, Rj, Rn);
+      oc = rw - mv(Rn, an);
+#pragma unroll
+      for (int i = 0; i < 9; i++) Rc[i] = Rn[i];
+    }
+    {
+      SV X = rec[W_QD * st] * S;
+      st6(rec + W_S * st, st, S);
+      st6(rec + W_CJ * st, st, crm(Vp, X));
+      Vp = Vp + X;
+    }
+    if (c < 3) { ssx += rw.x; ssy += rw.y; }
+    else if (L.j >= 0) { sx += rw.x; sy += rw.y; }
+    const int nb = L.nbody;
+    if (nb > 0) {
+      float rcd[RECW];
+#pragma unroll
+      for (int i = 0; i < RECW; i++) rcd[i] = 0.f;
+      const int slot = (c == 2 || c == 6) ? 1 : 0;
+#pragma unroll 1
+      for (int k = 0; k < nb; k++) {
+        const BodyC& B = T.bc[c < 3 ? 4 : role][slot][k];
+        const V3 ob = oc + mv(Rc, rd3(B.off));
+        rigid_rec(Rc, ob, B.m, B.ix, B.iy, B.iz, Vp, rcd);
+        if (c < 3) { ssx += ob.x; ssy += ob.y; } else { sx += ob.x; sy += ob.y; }
+        ex = ob.x; ey = ob.y;
+#pragma unroll 1
+        for (int t = 0; t < B.nsph; t++) {
+          const int g = B.sidx[t];
+          V3 cs_ = ob + mv(Rc, rd3(B.sph[t]));
+          const float rad = B.sph[t][3], d = b.p[2] + cs_.z - rad;
+          if (d < (float)ILRL_CONTACT_BREAK) act |= 1u << g;
+          float* sp = &sm.sph[g][0][e];
+          sp[0] = cs_.x; sp[QE] = cs_.y; sp[2 * QE] = cs_.z - rad; sp[3 * QE] = d;
+        }
+      }
+      float* br = c < 3 ? &sm.rs[slot][0][e] : &sm.rl[slot][0][tid];
+#pragma unroll
+      for (int i = 0; i < RECW; i++) br[i * st] = rcd[i];
+    }
+  }
+  o.act = act; o.sx = sx; o.sy = sy; o.ssx = ssx; o.ssy = ssy; o.ex = ex; o.ey = ey;
+}
+
+// sums of the 31 part offsets (relative to the torso) and the right-foot origin, for calc_state / resetFromFrame
+__device__ __forceinline__ void pose_sums(const Base& b, Smem& sm, int e, int tid, int role, unsigned qm, float& sumx,
+                                          float& sumy, float& rfx, float& rfy) {
+  FkOut o;
+  __syncwarp(qm);
+  fk_phase(b, sm, e, tid, role, o);
+  sumx = o.ssx + qsum(o.sx, qm);
+  sumy = o.ssy + qsum(o.sy, qm);
+  const int l0 = (tid & 31) & ~3;
+  rfx = __shfl_sync(qm, o.ex, l0);
+  rfy = __shfl_sync(qm, o.ey, l0);
+  __syncwarp(qm);
+}
+
+// ---- constraint-row construction: responses of the generalized velocities to up to three unit impulses
+struct Imp {
+  int L, c;      // chain that carries the impulse: limb (-1 = spine / torso) and chain index (-1 = torso)
+  int jl;        // 1: generalized impulse `dir` on the joint of (L, c); 0: spatial force F on the body after (L, c)
+  float dir;
+  SV F;
+  float* row;    // where the row is stored (null: slot unused)
+};
+
+// inward walk of one impulse from its link to the base.  Leaves u of the visited links in su (chain-local), writes the
+// row's Jacobian chain entries, returns the force arriving at the base and rv = J . nu (chain part).
+__device__ __forceinline__ SV walk_in(const Smem& sm, const Imp& im, float* su /* stride QT */, int e, int qb, float& rv) {
+  SV pf = svzero();
+  rv = 0.f;
+  if (!im.row) return pf;
+  int c = im.c;
+  if (im.jl) {
+    int st;
+    const float* rec = link_rec_of(sm, im.L, c, e, qb, st);
+    su[c * QT] = im.dir;
+    pf = (im.dir * rec[W_DINV * st]) * ld6(rec + W_U * st, st);
+    rv = im.dir * rec[W_NU * st];
+    im.row[c < 3 ? R_JS + c : R_JL + c - 3] = im.dir;
+    c--;
+  } else {
+    pf = neg(im.F);
+  }
+#pragma unroll 1
+  for (; c >= 0; c--) {
+    if (c == 2 && im.L >= 2) break;  // arms attach to the torso
+    int st;
+    const float* rec = link_rec_of(sm, im.L, c, e, qb, st);
+    const SV S = ld6(rec + W_S * st, st), U = ld6(rec + W_U * st, st);
+    const float u = -sdot(S, pf);
+    su[c * QT] = u;
+    pf = pf + (u * rec[W_DINV * st]) * U;
+    if (!im.jl) {
+      const float Jl = sdot(S, im.F);
+      rv += Jl * rec[W_NU * st];
+      im.row[c < 3 ? R_JS + c : R_JL + c - 3] = Jl;
+    }
+  }
+  return pf;
+}
+// J . resp over the chain entries of a finished row, and restore the scratch to zero
+__device__ __forceinline__ float walk_dd(const Imp& im, float* su) {
+  float dd = 0.f;
+  if (!im.row) return dd;
+#pragma unroll 1
+  for (int c = im.c; c >= 0; c--) {
+    if (c == 2 && im.L >= 2) break;
+    su[c * QT] = 0.f;
+    dd += c < 3 ? im.row[R_JS + c] * im.row[R_RS + c] : im.row[R_JL + c - 3] * im.row[R_RL + 4 * im.L + c - 3];
+  }
+  return dd;
+}
+
+__device__ __forceinline__ void responses3(Smem& sm, Imp* im, const float* nub, int e, int tid, int qb, float idt,
+                                           const float* pos /* [3] position term of each row */) {
+  float* su0 = &sm.su[0][0][tid];
+  float* su1 = &sm.su[1][0][tid];
+  float* su2 = &sm.su[2][0][tid];
+  // clear the rows
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    if (im[i].row) {
+      float4* r4 = reinterpret_cast<float4*>(im[i].row);
+#pragma unroll 1
+      for (int t = 0; t < RW / 4; t++) r4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  float rv[3];
+  SV pf[3];
+  pf[0] = walk_in(sm, im[0], su0, e, qb, rv[0]);
+  pf[1] = walk_in(sm, im[1], su1, e, qb, rv[1]);
+  pf[2] = walk_in(sm, im[2], su2, e, qb, rv[2]);
+  // base part: J_base = F (contact rows), response of the base
+  SV ap[3], a0[3], apel[3];
+  float dd[3];
+  const float* L0 = &sm.L0[0][e];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    a0[i] = chol6_solve_smem(L0, neg(pf[i]));
+    ap[i] = a0[i];
+    dd[i] = 0.f;
+    if (im[i].row) {
+      float* r = im[i].row;
+      r[R_RB + 0] = a0[i].a.x; r[R_RB + 1] = a0[i].a.y; r[R_RB + 2] = a0[i].a.z;
+      r[R_RB + 3] = a0[i].l.x; r[R_RB + 4] = a0[i].l.y; r[R_RB + 5] = a0[i].l.z;
+      if (!im[i].jl) {
+        const SV F = im[i].F;
+        r[R_JB + 0] = F.a.x; r[R_JB + 1] = F.a.y; r[R_JB + 2] = F.a.z; r[R_JB + 3] = F.l.x; r[R_JB + 4] = F.l.y; r[R_JB + 5] = F.l.z;
+        rv[i] += F.a.x * nub[0] + F.a.y * nub[1] + F.a.z * nub[2] + F.l.x * nub[3] + F.l.y * nub[4] + F.l.z * nub[5];
+        dd[i] = sdot(a0[i], F);
+      }
+    }
+  }
+  // outward sweep: spine, then the four limbs
+#pragma unroll 1
+  for (int c = 0; c < 3; c++) {
+    const float* rec = &sm.sp[c][0][e];
+    const SV S = ld6(rec + W_S * QE, QE), U = ld6(rec + W_U * QE, QE);
+    const float di = rec[W_DINV * QE];
+    const float u0 = su0[c * QT], u1 = su1[c * QT], u2 = su2[c * QT];
+    const float q0 = di * (u0 - sdot(ap[0], U)), q1 = di * (u1 - sdot(ap[1], U)), q2 = di * (u2 - sdot(ap[2], U));
+    ap[0] = ap[0] + q0 * S; ap[1] = ap[1] + q1 * S; ap[2] = ap[2] + q2 * S;
+    if (im[0].row) im[0].row[R_RS + c] = q0;
+    if (im[1].row) im[1].row[R_RS + c] = q1;
+    if (im[2].row) im[2].row[R_RS + c] = q2;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) apel[i] = ap[i];
+#pragma unroll 1
+  for (int r = 0; r < 4; r++) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) ap[i] = r < 2 ? apel[i] : a0[i];
+    const bool m0 = im[0].L == r, m1 = im[1].L == r, m2 = im[2].L == r;
+#pragma unroll 1
+    for (int k = 0; k < 4; k++) {
+      const float* rec = &sm.lk[k][0][qb + r];
+      const SV S = ld6(rec + W_S * QT, QT), U = ld6(rec + W_U * QT, QT);
+      const float di = rec[W_DINV * QT];
+      const float u0 = m0 ? su0[(3 + k) * QT] : 0.f, u1 = m1 ? su1[(3 + k) * QT] : 0.f, u2 = m2 ? su2[(3 + k) * QT] : 0.f;
+      const float q0 = di * (u0 - sdot(ap[0], U)), q1 = di * (u1 - sdot(ap[1], U)), q2 = di * (u2 - sdot(ap[2], U));
+      ap[0] = ap[0] + q0 * S; ap[1] = ap[1] + q1 * S; ap[2] = ap[2] + q2 * S;
+      if (im[0].row) im[0].row[R_RL + 4 * r + k] = q0;
+      if (im[1].row) im[1].row[R_RL + 4 * r + k] = q1;
+      if (im[2].row) im[2].row[R_RL + 4 * r + k] = q2;
+    }
+  }
+  dd[0] += walk_dd(im[0], su0);
+  dd[1] += walk_dd(im[1], su1);
+  dd[2] += walk_dd(im[2], su2);
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+    if (im[i].row) {
+      const float di = __frcp_rn(dd[i]);
+      im[i].row[R_DINV] = di;
+      im[i].row[R_RHS] = (pos[i] - rv[i]) * di;
+    }
+}
+
+// ---- projected Gauss-Seidel pieces.  dvb: base (replicated), dvc: chain (spine replicated, limb private)
+struct RowRegs { float4 a, b, c, d, e, rl, jl; };  // 20 shared words, own limb response, the row's limb Jacobian
+template <class P4>
+__device__ __forceinline__ void row_load(P4 rp, int role, RowRegs& r) {
+  r.a = rp[0]; r.b = rp[1]; r.c = rp[2]; r.d = rp[3]; r.e = rp[4];
+  r.rl = rp[5 + role];
+  r.jl = rp[9];
+}
+__device__ __forceinline__ float row_jdot(const RowRegs& r, const float* dvb, const float* dvc, bool mine, int src, unsigned qm) {
+  // words: a = RB0..3, b = RB4,5 RS0,1, c = RS2 JS0..2, d = JB0..3, e = JB4,5 rhs dinv
+  float rep = r.d.x * dvb[0] + r.d.y * dvb[1] + r.d.z * dvb[2] + r.d.w * dvb[3] + r.e.x * dvb[4] + r.e.y * dvb[5] +
+              r.c.y * dvc[0] + r.c.z * dvc[1] + r.c.w * dvc[2];
+  float own = mine ? r.jl.x * dvc[3] + r.jl.y * dvc[4] + r.jl.z * dvc[5] + r.jl.w * dvc[6] : 0.f;
+  return rep + __shfl_sync(qm, own, src);
+}
+__device__ __forceinline__ void row_axpy(const RowRegs& r, float a, float* dvb, float* dvc) {
+  dvb[0] += a * r.a.x; dvb[1] += a * r.a.y; dvb[2] += a * r.a.z; dvb[3] += a * r.a.w; dvb[4] += a * r.b.x; dvb[5] += a * r.b.y;
+  dvc[0] += a * r.b.z; dvc[1] += a * r.b.w; dvc[2] += a * r.c.x;
+  dvc[3] += a * r.rl.x; dvc[4] += a * r.rl.y; dvc[5] += a * r.rl.z; dvc[6] += a * r.rl.w;
+}
+__device__ __forceinline__ void row_fetch(const Smem& sm, const float* gscr, int e, int r, int role, RowRegs& rr) {
+  if (r < RSM) row_load(reinterpret_cast<const float4*>(&sm.rows[e][r * RW]), role, rr);
+  else row_load(reinterpret_cast<const float4*>(gscr + (size_t)(r - RSM) * RW), role, rr);
+}
+
+// ---- one substep of dt for the env of this quad.  Joint state / torques live in the link records.
+__device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, int tid, int role, unsigned qm, float dt) {
+  const int qb = tid & ~3;
+  const Tables& T = sm.T;
+  // ---- phase A
+  FkOut fo;
+  fk_phase(b, sm, e, tid, role, fo);
+  uint32_t act = fo.act, lim = 0;
+  // ---- phase B: inward pass
+  SV a0;
+  {
+    IP x, arms;
+    x.I.zero(); x.p = svzero();
+    arms.I.zero(); arms.p = svzero();
+#pragma unroll 1
+    for (int c = NL - 1; c >= 0; c--) {
+      if (c == 2) {
+        // the limbs are done: legs (lanes 0,1) meet at the pelvis, arms (lanes 2,3) at the torso
+        ip_shfl_add(x, qm, 1);
+        IP y = ip_shfl_get(x, qm, 2);
+        if (role < 2) arms = y; else { arms = x; x = y; }
+      }
+      int st;
+      float* rec = link_rec(sm, c, e, tid, st);
+      if (c == 1 || c == 2 || c == 5 || c == 6) {
+        const int slot = (c == 2 || c == 6) ? 1 : 0;
+        ip_add_rec(x, c < 3 ? &sm.rs[slot][0][e] : &sm.rl[slot][0][tid], st);
+      }
+      const SV S = ld6(rec + W_S * st, st), cJ = ld6(rec + W_CJ * st, st);
+      const SV U = imul(x.I, S);
+      const float dinv = rcp_or_zero(sdot(S, U));  // a dummy slot has S = 0
+      const float u = rec[W_TAU * st] - sdot(S, x.p);
+      st6(rec + W_U * st, st, U);
+      rec[W_DINV * st] = dinv; rec[W_UU * st] = u;
+      downdate(x.I, U, dinv);
+      x.p = x.p + imul(x.I, cJ) + (u * dinv) * U;
+    }
+    // floating base: torso + spine/legs + arms
+    float rcd[RECW];
+#pragma unroll
+    for (int i = 0; i < RECW; i++) rcd[i] = 0.f;
+    float R0[9];
+    quat2mat(b.quat[0], b.quat[1], b.quat[2], b.quat[3], R0);
+    SV V0; V0.a = rd3(b.w); V0.l = rd3(b.v);
+    rigid_rec(R0, mk(0.f, 0.f, 0.f), kBodyMass[0], kBodyInertia[0], kBodyInertia[1], kBodyInertia[2], V0, rcd);
+    ip_add_rec(x, rcd, 1);
+    x.I.add(arms.I); x.p = x.p + arms.p;
+    chol6_to_smem(x.I, &sm.L0[0][e]);
+    __syncwarp(qm);
+    a0 = chol6_solve_smem(&sm.L0[0][e], neg(x.p));
+  }
+  // ---- phase C: outward pass -> unconstrained new velocities; violated limits
+  float nub[6];
+  {
+    const float M = (float)ILRL_MAX_COORD_VEL;
+    V3 w = rd3(b.w), v = rd3(b.v);
+    V3 lin = a0.l + cross(w, v);  // classical acceleration of the torso origin
+    nub[0] = clampf(b.w[0] + dt * a0.a.x, -M, M); nub[1] = clampf(b.w[1] + dt * a0.a.y, -M, M);
+    nub[2] = clampf(b.w[2] + dt * a0.a.z, -M, M); nub[3] = clampf(b.v[0] + dt * lin.x, -M, M);
+    nub[4] = clampf(b.v[1] + dt * lin.y, -M, M);  nub[5] = clampf(b.v[2] + dt * lin.z, -M, M);
+    SV ap = a0;
+#pragma unroll 1
+    for (int c = 0; c < NL; c++) {
+      if (c == 3 && role >= 2) ap = a0;
+      int st;
+      float* rec = link_rec(sm, c, e, tid, st);
+      const LinkC& L = c < 3 ? T.lc[4][c] : T.lc[role][c - 3];
+      const SV ad = ap + ld6(rec + W_CJ * st, st);
+      const float qa = rec[W_DINV * st] * (rec[W_UU * st] - sdot(ad, ld6(rec + W_U * st, st)));
+      rec[W_NU * st] = clampf(rec[W_QD * st] + dt * qa, -M, M);
+      ap = ad + qa * ld6(rec + W_S * st, st);
+      const float q = rec[W_Q * st];
+      if (L.j >= 0 && (q - L.lo <= 0.f || L.hi - q <= 0.f)) lim |= 1u << L.j;
+    }
+  }
+  lim |= __shfl_xor_sync(qm, lim, 1); lim |= __shfl_xor_sync(qm, lim, 2);
+  act |= __shfl_xor_sync(qm, act, 1); act |= __shfl_xor_sync(qm, act, 2);
+  __syncwarp(qm);
+  int nact = __popc(act);
+  while (nact > MAXC) {  // keep the deepest MAXC (ties: drop the highest index); replicated in the quad
+    int worst = -1;
+    float wd = -1e30f;
+#pragma unroll 1
+    for (int g = 0; g < NS; g++)
+      if (((act >> g) & 1u) && sm.sph[g][3][e] >= wd) { wd = sm.sph[g][3][e]; worst = g; }
+    act &= ~(1u << worst);
+    nact--;
+  }
+  const int nlim = __popc(lim), ncon = nact, nrows = nlim + 3 * ncon;
+  float dvb[6], dvc[NL];
+#pragma unroll
+  for (int i = 0; i < 6; i++) dvb[i] = 0.f;
+#pragma unroll
+  for (int i = 0; i < NL; i++) dvc[i] = 0.f;
+  if (nrows > 0) {
+    const float idt = 1.0f / dt;
+    // ---- build the rows three at a time; items are dealt round-robin to the 4 lanes
+    const int nlg = (nlim + 2) / 3;
+#pragma unroll 1
+    for (int it = role; it < nlg + ncon; it += 4) {
+      Imp im[3];
+      float pos[3] = {0.f, 0.f, 0.f};
+      int r0;
+      if (it < nlg) {
+        r0 = 3 * it;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          im[i].row = nullptr; im[i].L = -1; im[i].c = -1; im[i].jl = 1; im[i].dir = 0.f; im[i].F = svzero();
+          if (r0 + i < nlim) {
+            const int j = nth_set_bit(lim, r0 + i);
+            im[i].L = T.jL[j]; im[i].c = T.jC[j];
+            int st;
+            const float* qrec = link_rec_of(sm, im[i].L, im[i].c, e, qb, st);
+            const float q = qrec[W_Q * st];
+            float pen;
+            if (q - kJointLo[j] <= 0.f) { pen = q - kJointLo[j]; im[i].dir = 1.f; } else { pen = kJointHi[j] - q; im[i].dir = -1.f; }
+            pos[i] = -pen * (float)ILRL_LIMIT_ERP * idt;
+          }
+        }
+      } else {
+        const int ci = it - nlg;
+        r0 = nlim + 3 * ci;
+        const int g = nth_set_bit(act, ci);
+        const float* sp = &sm.sph[g][0][e];
+        const V3 xx = mk(sp[0], sp[QE], sp[2 * QE]);
+        const float dist = sp[3 * QE];
+        pos[0] = dist > 0.f ? -dist * idt : -dist * (float)ILRL_CONTACT_ERP * idt;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          im[i].L = T.sphL[g]; im[i].c = T.sphC[g]; im[i].jl = 0; im[i].dir = 0.f;
+          // normal (0,0,1), tangents btPlaneSpace1 -> (0,-1,0), (1,0,0)
+          im[i].F.l = i == 0 ? mk(0.f, 0.f, 1.f) : (i == 1 ? mk(0.f, -1.f, 0.f) : mk(1.f, 0.f, 0.f));
+          im[i].F.a = cross(xx, im[i].F.l);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const int r = r0 + i;
+        const bool used = it >= nlg || r < nlim;
+        im[i].row = !used ? nullptr : (r < RSM ? &sm.rows[e][r * RW] : gscr + (size_t)(r - RSM) * RW);
+        if (used) { sm.lam[r][e] = 0.f; sm.rowL[r][e] = (signed char)(im[i].c >= 3 ? im[i].L : -1); }
+      }
+      responses3(sm, im, nub, e, tid, qb, idt, pos);
+    }
+    __syncwarp(qm);
+    // ---- projected Gauss-Seidel on the velocity change
+#pragma unroll 1
+    for (int itn = 0; itn < ILRL_SOLVER_ITERS; itn++) {
+#pragma unroll 1
+      for (int k = 0; k < nlim + ncon; k++) {  // limits, then contact normals
+        const int r = k < nlim ? k : nlim + 3 * (k - nlim);
+        RowRegs rr;
+        row_fetch(sm, gscr, e, r, role, rr);
+        const int L = sm.rowL[r][e];
+        const float lam = sm.lam[r][e];
+        const float nl = fmaxf(lam + rr.e.z - row_jdot(rr, dvb, dvc, role == L, qb + (L & 3), qm) * rr.e.w, 0.f);
+        sm.lam[r][e] = nl;
+        row_axpy(rr, nl - lam, dvb, dvc);
+      }
+#pragma unroll 1
+      for (int c = 0; c < ncon; c++) {  // friction pairs, cone re-projected on the current normal impulse
+        const int rn = nlim + 3 * c;
+        const float ln = sm.lam[rn][e];
+        if (!(ln > 0.f)) continue;
+        RowRegs r1, r2;
+        row_fetch(sm, gscr, e, rn + 1, role, r1);
+        row_fetch(sm, gscr, e, rn + 2, role, r2);
+        const int L = sm.rowL[rn][e];
+        const float lim_f = (float)ILRL_FRICTION * ln;
+        const float l1 = sm.lam[rn + 1][e], l2 = sm.lam[rn + 2][e];
+        float s1 = l1 + r1.e.z - row_jdot(r1, dvb, dvc, role == L, qb + (L & 3), qm) * r1.e.w;
+        float s2 = l2 + r2.e.z - row_jdot(r2, dvb, dvc, role == L, qb + (L & 3), qm) * r2.e.w;
+        const float n2 = s1 * s1 + s2 * s2;
+        if (n2 > lim_f * lim_f) { const float sc = lim_f * rsqrtf(n2); s1 *= sc; s2 *= sc; }
+        sm.lam[rn + 1][e] = s1; sm.lam[rn + 2][e] = s2;
+        row_axpy(r1, s1 - l1, dvb, dvc);
+        row_axpy(r2, s2 - l2, dvb, dvc);
+      }
+    }
+    __syncwarp(qm);
+  }
+  // ---- integrate (exponential map on the torso quaternion, as btMultiBody::stepPositionsMultiDof)
+  {
+    const float M = (float)ILRL_MAX_COORD_VEL;
+    float nu[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) nu[i] = nrows > 0 ? clampf(nub[i] + dvb[i], -M, M) : nub[i];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { b.w[i] = nu[i]; b.v[i] = nu[3 + i]; b.p[i] += dt * nu[3 + i]; }
+    const float wn = sqrtf(nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]);
+    float sc, cw, sh;
+    sincos_joint(0.5f * wn * dt, sh, cw);
+    if (wn < 1e-3f) sc = 0.5f * dt - dt * dt * dt * 0.020833333333f * wn * wn;
+    else sc = sh / wn;
+    const float dx = nu[0] * sc, dy = nu[1] * sc, dz = nu[2] * sc;
+    const float x_ = b.quat[0], y_ = b.quat[1], z_ = b.quat[2], w_ = b.quat[3];
+    const float nx = cw * x_ + dx * w_ + dy * z_ - dz * y_;
+    const float ny = cw * y_ - dx * z_ + dy * w_ + dz * x_;
+    const float nz = cw * z_ + dx * y_ - dy * x_ + dz * w_;
+    const float nw = cw * w_ - dx * x_ - dy * y_ - dz * z_;
+    const float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
+    b.quat[0] = nx * inv; b.quat[1] = ny * inv; b.quat[2] = nz * inv; b.quat[3] = nw * inv;
+#pragma unroll
+    for (int c = 0; c < NL; c++) {
+      int st;
+      float* rec = link_rec(sm, c, e, tid, st);
+      const float nuc = rec[W_NU * st];
+      const float qd = nrows > 0 ? clampf(nuc + dvc[c], -M, M) : nuc;
+      if (c >= 3 || role == 0) {  // the spine records are shared by the quad: one writer for the read-modify-write
+        rec[W_QD * st] = qd;
+        rec[W_Q * st] += dt * qd;
+      }
+    }
+  }
+  __syncwarp(qm);
+}
+
+// ---- state movement between HBM (SoA phys[47][n]), the link records and a replicated full Phys
+__device__ __forceinline__ void load_base(const float* phys, int n, int i, Base& b) {
+  const float* p = phys + i;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { b.p[k] = p[k * n]; b.v[k] = p[(7 + k) * n]; b.w[k] = p[(10 + k) * n]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) b.quat[k] = p[(3 + k) * n];
+}
+// joint state of this lane's chain from HBM into the link records (spine: every lane writes the same values)
+__device__ __forceinline__ void load_links(const float* phys, int n, int i, Smem& sm, int e, int tid, int role) {
+  const float* p = phys + i;
+#pragma unroll
+  for (int c = 0; c < NL; c++) {
+    int st;
+    float* rec = link_rec(sm, c, e, tid, st);
+    const int j = c < 3 ? c : sm.T.lc[role][c - 3].j;
+    rec[W_Q * st] = j >= 0 ? p[(13 + j) * n] : 0.f;
+    rec[W_QD * st] = j >= 0 ? p[(30 + j) * n] : 0.f;
+  }
+}
+// link records -> full Phys in every lane
+__device__ __forceinline__ void gather(const Base& b, const Smem& sm, int e, int qb, unsigned qm, Phys& ps) {
+  __syncwarp(qm);
+#pragma unroll
+  for (int j = 0; j < NJ; j++) {
+    constexpr Tables T{};
+    const int L = T.jL[j], c = T.jC[j];
+    const float* rec = c < 3 ? &sm.sp[c][0][e] : &sm.lk[c - 3][0][qb + L];
+    const int st = c < 3 ? QE : QT;
+    ps.q[j] = rec[W_Q * st];
+    ps.qd[j] = rec[W_QD * st];
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) { ps.p[k] = b.p[k]; ps.v[k] = b.v[k]; ps.w[k] = b.w[k]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) ps.quat[k] = b.quat[k];
+}
+// full (replicated) Phys -> base registers + link records
+__device__ __forceinline__ void scatter(const Phys& ps, Smem& sm, int e, int qb, int role, unsigned qm, Base& b) {
+  __syncwarp(qm);
+  if (role == 0) {
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      constexpr Tables T{};
+      const int L = T.jL[j], c = T.jC[j];
+      float* rec = c < 3 ? &sm.sp[c][0][e] : &sm.lk[c - 3][0][qb + L];
+      const int st = c < 3 ? QE : QT;
+      rec[W_Q * st] = ps.q[j];
+      rec[W_QD * st] = ps.qd[j];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 3; k++) { b.p[k] = ps.p[k]; b.v[k] = ps.v[k]; b.w[k] = ps.w[k]; }
+#pragma unroll
+  for (int k = 0; k < 4; k++) b.quat[k] = ps.quat[k];
+  __syncwarp(qm);
+}
+// store a replicated Phys: the 47 words are dealt to the 4 lanes
+__device__ __forceinline__ void store_phys(float* phys, int n, int i, int role, const Phys& ps) {
+  float* p = phys + i;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (((0 + k) & 3) == role) p[(0 + k) * n] = ps.p[k];
+    if (((7 + k) & 3) == role) p[(7 + k) * n] = ps.v[k];
+    if (((10 + k) & 3) == role) p[(10 + k) * n] = ps.w[k];
+  }
+#pragma unroll
+  for (int k = 0; k < 4; k++) if (((3 + k) & 3) == role) p[(3 + k) * n] = ps.quat[k];
+#pragma unroll
+  for (int k = 0; k < NJ; k++) {
+    if (((13 + k) & 3) == role) p[(13 + k) * n] = ps.q[k];
+    if (((30 + k) & 3) == role) p[(30 + k) * n] = ps.qd[k];
+  }
+}
+
+}  // namespace chain
+}  // namespace ilrl

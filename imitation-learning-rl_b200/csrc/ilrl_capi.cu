@@ -88,7 +88,14 @@ __device__ __forceinline__ void store_state(const StepArgs& a, int i, const Phys
 __device__ __forceinline__ void quad_smem_init(chain::Smem& sm) {
   const uint32_t* src = reinterpret_cast<const uint32_t*>(&chain::kTables);
   uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.T);
-  for (int t = threadIdx.x; t < chain::TABLE_WORDS; t += QT) dst[t] = src[t];
+  {  // all loads of a thread in flight together (the copy is on every CTA's critical path)
+    constexpr int PER = (chain::TABLE_WORDS + QT - 1) / QT;
+    uint32_t v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) { const int t = threadIdx.x + k * QT; v[k] = t < chain::TABLE_WORDS ? __ldg(src + t) : 0u; }
+#pragma unroll
+    for (int k = 0; k < PER; k++) { const int t = threadIdx.x + k * QT; if (t < chain::TABLE_WORDS) dst[t] = v[k]; }
+  }
   float* z = &sm.su[0][0][0];
   for (int t = threadIdx.x; t < 3 * chain::NL * QT; t += QT) z[t] = 0.f;
 }
@@ -97,12 +104,11 @@ __device__ __forceinline__ void quad_smem_init(chain::Smem& sm) {
 __device__ __forceinline__ void set_torques(chain::Smem& sm, int e, int tid, int role, const float* act, const float* torque) {
 #pragma unroll
   for (int c = 0; c < chain::NL; c++) {
-    int st;
-    float* rec = chain::link_rec(sm, c, e, tid, st);
+    float* rec = chain::link_rec(sm, c, e, tid);
     const chain::LinkC& L = c < 3 ? sm.T.lc[4][c] : sm.T.lc[role][c - 3];
     float t = 0.f;
     if (L.j >= 0) t = act ? L.gear * fminf(fmaxf(act[L.motor], -1.f), 1.f) : torque[L.j];
-    rec[chain::W_TAU * st] = t;
+    rec[chain::W_TAU] = t;
   }
 }
 
@@ -203,7 +209,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     if (w.e[ILRL_E_T] >= (float)a.max_timestep) done = true;
     w.e[ILRL_E_EP_RETURN] += reward;
     w.e[ILRL_E_EP_LEN] += 1.f;
-    float* so = sm.obs[e];
+    float* so = &sm.rows[e][0];  // the env's row block is free after the substeps: stage the obs row there
     {
       float obs[70];
       write_low_obs(c.obs, w, cl, obs);
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     const int cnt = min(QE, a.n - base) * 70;
     for (int t = tid; t < cnt; t += QT) {
       int r = t / 70, cc = t - r * 70;
-      if ((wrote[r >> 3] >> ((r & 7) * 4)) & 1u) a.obs[(size_t)base * 70 + t] = sm.obs[r][cc];
+      if ((wrote[r >> 3] >> ((r & 7) * 4)) & 1u) a.obs[(size_t)base * 70 + t] = sm.rows[r][cc];
     }
   }
   // K5: episode / reward statistics -> one atomicAdd per warp per slot

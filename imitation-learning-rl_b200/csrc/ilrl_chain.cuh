@@ -38,10 +38,11 @@ constexpr int RSM = ILRL_RSM;          // constraint rows per env kept in shared
 constexpr int RW = 40;                 // words per stored row
 constexpr int ROWSTRIDE = RSM * RW + 4;  // env stride in words: = 4 (mod 32)
 constexpr int GROWS = MAXROWS - RSM;   // rows per env in the global overflow scratch
-// link record words
-enum { W_S = 0, W_CJ = 6, W_U = 12, W_DINV = 18, W_UU = 19, W_Q = 20, W_QD = 21, W_TAU = 22, W_NU = 23, LKW = 24 };
-// body record words: rigid inertia about the reference point (A 6, m*c 3, m 1) + bias force 6
-constexpr int RECW = 16;
+// link record: 24 words in 6 float4 (S | cJ | U dinv u | q qd tau nu), one contiguous 28-word slot per thread: a
+// 28-word stride puts the float4 of 8 consecutive threads in 8 different bank groups (conflict-free LDS.128 / STS.128)
+enum { W_S = 0, W_CJ = 6, W_U = 12, W_DINV = 18, W_UU = 19, W_Q = 20, W_QD = 21, W_TAU = 22, W_NU = 23, LKW = 28 };
+// body record words: rigid inertia about the reference point (A 6, m*c 3, m 1) + bias force 6; 20-word slots (same reason)
+constexpr int RECW = 16, BRW = 20;
 // stored row words
 enum { R_RB = 0 /*resp base 6*/, R_RS = 6 /*resp spine 3*/, R_JS = 9 /*J spine 3*/, R_JB = 12 /*J base 6*/, R_RHS = 18,
        R_DINV = 19, R_RL = 20 /*resp limbs 4x4*/, R_JL = 36 /*J of the row's limb 4*/ };
@@ -168,20 +169,24 @@ static_assert(sizeof(Tables) % 4 == 0, "table copy is word-wise");
 
 // ---- shared memory of one CTA
 struct __align__(16) Smem {
-  float rows[QE][ROWSTRIDE];   // stored rows (first: 16-byte aligned)
-  Tables T;
-  float lk[4][LKW][QT];        // limb link records, per thread
-  float sp[3][LKW][QE];        // spine link records, per env
-  float rl[2][RECW][QT];       // limb body records (slot 0 = A, 1 = B + E)
-  float rs[2][RECW][QE];       // spine body records (slot 0 = lwaist, 1 = pelvis)
+  // --- float4-accessed arrays first (every size below is a multiple of 16 bytes)
+  float rows[QE][ROWSTRIDE];   // stored rows; after the substeps the first 71 words of an env's block stage its obs row
+  float lk[4][QT][LKW];        // limb link records, per thread
+  float sp[3][QE][LKW];        // spine link records, per env
+  float rl[2][QT][BRW];        // limb body records (slot 0 = A, 1 = B + E)
+  float rs[2][QE][BRW];        // spine body records (slot 0 = lwaist, 1 = pelvis)
+  // --- scalar-accessed
   float L0[21][QE];            // Cholesky factor of the base articulated inertia
   float sph[NS][4][QE];        // contact candidates: x, y, z - r (relative to the torso origin), distance
   float lam[MAXROWS][QE];
   float su[3][NL][QT];         // response scratch: u of the chain links of up to 3 impulses (kept zero between uses)
   float act[QE][NJ];           // actions (motor order)
-  float obs[QE][71];
+  Tables T;
   signed char rowL[MAXROWS][QE];  // limb that owns the row's limb block (-1: none)
 };
+static_assert((sizeof(float) * QE * ROWSTRIDE) % 16 == 0 && (sizeof(float) * LKW) % 16 == 0 && (sizeof(float) * BRW) % 16 == 0,
+              "float4 alignment of the shared-memory records");
+static_assert(ROWSTRIDE >= 71, "the obs row is staged in the env's row block");
 
 // replicated floating-base state of one env
 struct Base { float p[3], quat[4], v[3], w[3]; };
@@ -225,22 +230,46 @@ __device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
   return __ffs(m) - 1;
 }
 
-// link record of chain index c of THIS lane (spine: the env's shared record), and its word stride
-__device__ __forceinline__ float* link_rec(Smem& sm, int c, int e, int tid, int& st) {
-  st = c < 3 ? QE : QT;
-  return c < 3 ? &sm.sp[c][0][e] : &sm.lk[c - 3][0][tid];
+// link record of chain index c of THIS lane (spine: the env's shared record)
+__device__ __forceinline__ float* link_rec(Smem& sm, int c, int e, int tid) {
+  return c < 3 ? &sm.sp[c][e][0] : &sm.lk[c - 3][tid][0];
 }
 // link record of chain index c of limb L of this env (L < 0 or c < 3: spine)
-__device__ __forceinline__ const float* link_rec_of(const Smem& sm, int L, int c, int e, int qb, int& st) {
-  st = c < 3 ? QE : QT;
-  return c < 3 ? &sm.sp[c][0][e] : &sm.lk[c - 3][0][qb + L];
+__device__ __forceinline__ const float* link_rec_of(const Smem& sm, int L, int c, int e, int qb) {
+  return c < 3 ? &sm.sp[c][e][0] : &sm.lk[c - 3][qb + L][0];
 }
-__device__ __forceinline__ SV ld6(const float* p, int st) {
-  SV r; r.a = mk(p[0], p[st], p[2 * st]); r.l = mk(p[3 * st], p[4 * st], p[5 * st]);
-  return r;
+// record field access in whole float4 (word layout: S 0..5 | cJ 6..11 | U 12..17, dinv 18, u 19 | q qd tau nu 20..23)
+__device__ __forceinline__ void ld_SU(const float* rec, SV& S, SV& U, float& dinv) {
+  const float4* r = reinterpret_cast<const float4*>(rec);
+  const float4 a = r[0], b = r[1], c = r[3], d = r[4];
+  S.a = mk(a.x, a.y, a.z); S.l = mk(a.w, b.x, b.y);
+  U.a = mk(c.x, c.y, c.z); U.l = mk(c.w, d.x, d.y);
+  dinv = d.z;
 }
-__device__ __forceinline__ void st6(float* p, int st, SV v) {
-  p[0] = v.a.x; p[st] = v.a.y; p[2 * st] = v.a.z; p[3 * st] = v.l.x; p[4 * st] = v.l.y; p[5 * st] = v.l.z;
+__device__ __forceinline__ void ld_ScJ(const float* rec, SV& S, SV& cJ) {
+  const float4* r = reinterpret_cast<const float4*>(rec);
+  const float4 a = r[0], b = r[1], c = r[2];
+  S.a = mk(a.x, a.y, a.z); S.l = mk(a.w, b.x, b.y);
+  cJ.a = mk(b.z, b.w, c.x); cJ.l = mk(c.y, c.z, c.w);
+}
+__device__ __forceinline__ void ld_all(const float* rec, SV& S, SV& cJ, SV& U, float& dinv, float& u) {
+  const float4* r = reinterpret_cast<const float4*>(rec);
+  const float4 a = r[0], b = r[1], c = r[2], d = r[3], f = r[4];
+  S.a = mk(a.x, a.y, a.z); S.l = mk(a.w, b.x, b.y);
+  cJ.a = mk(b.z, b.w, c.x); cJ.l = mk(c.y, c.z, c.w);
+  U.a = mk(d.x, d.y, d.z); U.l = mk(d.w, f.x, f.y);
+  dinv = f.z; u = f.w;
+}
+__device__ __forceinline__ void st_ScJ(float* rec, SV S, SV cJ) {
+  float4* r = reinterpret_cast<float4*>(rec);
+  r[0] = make_float4(S.a.x, S.a.y, S.a.z, S.l.x);
+  r[1] = make_float4(S.l.y, S.l.z, cJ.a.x, cJ.a.y);
+  r[2] = make_float4(cJ.a.z, cJ.l.x, cJ.l.y, cJ.l.z);
+}
+__device__ __forceinline__ void st_Udu(float* rec, SV U, float dinv, float u) {
+  float4* r = reinterpret_cast<float4*>(rec);
+  r[3] = make_float4(U.a.x, U.a.y, U.a.z, U.l.x);
+  r[4] = make_float4(U.l.y, U.l.z, dinv, u);
 }
 
 // rigid inertia (about the reference point, world axes) and bias force of one body, ACCUMULATED into rec[16]
@@ -273,14 +302,20 @@ __device__ __forceinline__ void rigid_rec(const float* R, V3 c, float m, float i
 
 struct IP { Inertia I; SV p; };  // articulated inertia + bias force (27 words)
 
-__device__ __forceinline__ void ip_add_rec(IP& x, const float* r, int st) {
+__device__ __forceinline__ void ip_add_rec(IP& x, const float* r) {
 #pragma unroll
-  for (int i = 0; i < 6; i++) x.I.A[i] += r[i * st];
-  const float mx = r[6 * st], my = r[7 * st], mz = r[8 * st], m = r[9 * st];
+  for (int i = 0; i < 6; i++) x.I.A[i] += r[i];
+  const float mx = r[6], my = r[7], mz = r[8], m = r[9];
   x.I.B[1] -= mz; x.I.B[2] += my; x.I.B[3] += mz; x.I.B[5] -= mx; x.I.B[6] -= my; x.I.B[7] += mx;
   x.I.C[0] += m; x.I.C[3] += m; x.I.C[5] += m;
-  x.p.a.x += r[10 * st]; x.p.a.y += r[11 * st]; x.p.a.z += r[12 * st];
-  x.p.l.x += r[13 * st]; x.p.l.y += r[14 * st]; x.p.l.z += r[15 * st];
+  x.p.a.x += r[10]; x.p.a.y += r[11]; x.p.a.z += r[12];
+  x.p.l.x += r[13]; x.p.l.y += r[14]; x.p.l.z += r[15];
+}
+__device__ __forceinline__ void ip_add_rec4(IP& x, const float* rec) {  // 16-byte aligned record in shared memory
+  const float4* r4 = reinterpret_cast<const float4*>(rec);
+  const float4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
+  const float r[16] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w, d.x, d.y, d.z, d.w};
+  ip_add_rec(x, r);
 }
 __device__ __forceinline__ void ip_shfl_add(IP& x, unsigned qm, int lane_mask) {
 #pragma unroll
@@ -365,8 +400,7 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
       Vp = V0;
     }
     const LinkC& L = c < 3 ? T.lc[4][c] : T.lc[role][c - 3];
-    int st;
-    float* rec = link_rec(sm, c, e, tid, st);
+    float* rec = link_rec(sm, c, e, tid);
     oc = oc + mv(Rc, rd3(L.pre));
     if (L.rot) {
       float Rn[9];
@@ -381,7 +415,7 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
     S.l = cross(rw, S.a);
     {
       float sn, cs;
-      sincos_joint(rec[W_Q * st], sn, cs);
+      sincos_joint(rec[W_Q], sn, cs);
       const float t = 1.f - cs;
       float Rj[9], Rn[9];
       Rj[0] = t * ax.x * ax.x + cs;        Rj[1] = t * ax.x * ax.y - sn * ax.z; Rj[2] = t * ax.x * ax.z + sn * ax.y;
@@ -393,9 +427,8 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
       for (int i = 0; i < 9; i++) Rc[i] = Rn[i];
     }
     {
-      SV X = rec[W_QD * st] * S;
-      st6(rec + W_S * st, st, S);
-      st6(rec + W_CJ * st, st, crm(Vp, X));
+      SV X = rec[W_QD] * S;
+      st_ScJ(rec, S, crm(Vp, X));
       Vp = Vp + X;
     }
     if (c < 3) { ssx += rw.x; ssy += rw.y; }
@@ -423,9 +456,9 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
           sp[0] = cs_.x; sp[QE] = cs_.y; sp[2 * QE] = cs_.z - rad; sp[3 * QE] = d;
         }
       }
-      float* br = c < 3 ? &sm.rs[slot][0][e] : &sm.rl[slot][0][tid];
+      float4* br = reinterpret_cast<float4*>(c < 3 ? &sm.rs[slot][e][0] : &sm.rl[slot][tid][0]);
 #pragma unroll
-      for (int i = 0; i < RECW; i++) br[i * st] = rcd[i];
+      for (int i = 0; i < RECW / 4; i++) br[i] = make_float4(rcd[4 * i], rcd[4 * i + 1], rcd[4 * i + 2], rcd[4 * i + 3]);
     }
   }
   o.act = act; o.sx = sx; o.sy = sy; o.ssx = ssx; o.ssy = ssy; o.ex = ex; o.ey = ey;
@@ -462,11 +495,13 @@ __device__ __forceinline__ SV walk_in(const Smem& sm, const Imp& im, float* su /
   if (!im.row) return pf;
   int c = im.c;
   if (im.jl) {
-    int st;
-    const float* rec = link_rec_of(sm, im.L, c, e, qb, st);
+    const float* rec = link_rec_of(sm, im.L, c, e, qb);
+    SV S, U;
+    float di;
+    ld_SU(rec, S, U, di);
     su[c * QT] = im.dir;
-    pf = (im.dir * rec[W_DINV * st]) * ld6(rec + W_U * st, st);
-    rv = im.dir * rec[W_NU * st];
+    pf = (im.dir * di) * U;
+    rv = im.dir * rec[W_NU];
     im.row[c < 3 ? R_JS + c : R_JL + c - 3] = im.dir;
     c--;
   } else {
@@ -475,15 +510,16 @@ __device__ __forceinline__ SV walk_in(const Smem& sm, const Imp& im, float* su /
 #pragma unroll 1
   for (; c >= 0; c--) {
     if (c == 2 && im.L >= 2) break;  // arms attach to the torso
-    int st;
-    const float* rec = link_rec_of(sm, im.L, c, e, qb, st);
-    const SV S = ld6(rec + W_S * st, st), U = ld6(rec + W_U * st, st);
+    const float* rec = link_rec_of(sm, im.L, c, e, qb);
+    SV S, U;
+    float di;
+    ld_SU(rec, S, U, di);
     const float u = -sdot(S, pf);
     su[c * QT] = u;
-    pf = pf + (u * rec[W_DINV * st]) * U;
+    pf = pf + (u * di) * U;
     if (!im.jl) {
       const float Jl = sdot(S, im.F);
-      rv += Jl * rec[W_NU * st];
+      rv += Jl * rec[W_NU];
       im.row[c < 3 ? R_JS + c : R_JL + c - 3] = Jl;
     }
   }
@@ -544,9 +580,9 @@ __device__ __forceinline__ void responses3(Smem& sm, Imp* im, const float* nub, 
   // outward sweep: spine, then the four limbs
 #pragma unroll 1
   for (int c = 0; c < 3; c++) {
-    const float* rec = &sm.sp[c][0][e];
-    const SV S = ld6(rec + W_S * QE, QE), U = ld6(rec + W_U * QE, QE);
-    const float di = rec[W_DINV * QE];
+    SV S, U;
+    float di;
+    ld_SU(&sm.sp[c][e][0], S, U, di);
     const float u0 = su0[c * QT], u1 = su1[c * QT], u2 = su2[c * QT];
     const float q0 = di * (u0 - sdot(ap[0], U)), q1 = di * (u1 - sdot(ap[1], U)), q2 = di * (u2 - sdot(ap[2], U));
     ap[0] = ap[0] + q0 * S; ap[1] = ap[1] + q1 * S; ap[2] = ap[2] + q2 * S;
@@ -563,9 +599,9 @@ __device__ __forceinline__ void responses3(Smem& sm, Imp* im, const float* nub, 
     const bool m0 = im[0].L == r, m1 = im[1].L == r, m2 = im[2].L == r;
 #pragma unroll 1
     for (int k = 0; k < 4; k++) {
-      const float* rec = &sm.lk[k][0][qb + r];
-      const SV S = ld6(rec + W_S * QT, QT), U = ld6(rec + W_U * QT, QT);
-      const float di = rec[W_DINV * QT];
+      SV S, U;
+      float di;
+      ld_SU(&sm.lk[k][qb + r][0], S, U, di);
       const float u0 = m0 ? su0[(3 + k) * QT] : 0.f, u1 = m1 ? su1[(3 + k) * QT] : 0.f, u2 = m2 ? su2[(3 + k) * QT] : 0.f;
       const float q0 = di * (u0 - sdot(ap[0], U)), q1 = di * (u1 - sdot(ap[1], U)), q2 = di * (u2 - sdot(ap[2], U));
       ap[0] = ap[0] + q0 * S; ap[1] = ap[1] + q1 * S; ap[2] = ap[2] + q2 * S;
@@ -633,18 +669,17 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
         IP y = ip_shfl_get(x, qm, 2);
         if (role < 2) arms = y; else { arms = x; x = y; }
       }
-      int st;
-      float* rec = link_rec(sm, c, e, tid, st);
+      float* rec = link_rec(sm, c, e, tid);
       if (c == 1 || c == 2 || c == 5 || c == 6) {
         const int slot = (c == 2 || c == 6) ? 1 : 0;
-        ip_add_rec(x, c < 3 ? &sm.rs[slot][0][e] : &sm.rl[slot][0][tid], st);
+        ip_add_rec4(x, c < 3 ? &sm.rs[slot][e][0] : &sm.rl[slot][tid][0]);
       }
-      const SV S = ld6(rec + W_S * st, st), cJ = ld6(rec + W_CJ * st, st);
+      SV S, cJ;
+      ld_ScJ(rec, S, cJ);
       const SV U = imul(x.I, S);
       const float dinv = rcp_or_zero(sdot(S, U));  // a dummy slot has S = 0
-      const float u = rec[W_TAU * st] - sdot(S, x.p);
-      st6(rec + W_U * st, st, U);
-      rec[W_DINV * st] = dinv; rec[W_UU * st] = u;
+      const float u = rec[W_TAU] - sdot(S, x.p);
+      st_Udu(rec, U, dinv, u);
       downdate(x.I, U, dinv);
       x.p = x.p + imul(x.I, cJ) + (u * dinv) * U;
     }
@@ -656,7 +691,7 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
     quat2mat(b.quat[0], b.quat[1], b.quat[2], b.quat[3], R0);
     SV V0; V0.a = rd3(b.w); V0.l = rd3(b.v);
     rigid_rec(R0, mk(0.f, 0.f, 0.f), kBodyMass[0], kBodyInertia[0], kBodyInertia[1], kBodyInertia[2], V0, rcd);
-    ip_add_rec(x, rcd, 1);
+    ip_add_rec(x, rcd);
     x.I.add(arms.I); x.p = x.p + arms.p;
     chol6_to_smem(x.I, &sm.L0[0][e]);
     __syncwarp(qm);
@@ -675,14 +710,17 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
 #pragma unroll 1
     for (int c = 0; c < NL; c++) {
       if (c == 3 && role >= 2) ap = a0;
-      int st;
-      float* rec = link_rec(sm, c, e, tid, st);
+      float* rec = link_rec(sm, c, e, tid);
       const LinkC& L = c < 3 ? T.lc[4][c] : T.lc[role][c - 3];
-      const SV ad = ap + ld6(rec + W_CJ * st, st);
-      const float qa = rec[W_DINV * st] * (rec[W_UU * st] - sdot(ad, ld6(rec + W_U * st, st)));
-      rec[W_NU * st] = clampf(rec[W_QD * st] + dt * qa, -M, M);
-      ap = ad + qa * ld6(rec + W_S * st, st);
-      const float q = rec[W_Q * st];
+      SV S, cJ, U;
+      float di, uu;
+      ld_all(rec, S, cJ, U, di, uu);
+      const float4 st4 = reinterpret_cast<const float4*>(rec)[5];  // q, qd, tau, nu
+      const SV ad = ap + cJ;
+      const float qa = di * (uu - sdot(ad, U));
+      rec[W_NU] = clampf(st4.y + dt * qa, -M, M);
+      ap = ad + qa * S;
+      const float q = st4.x;
       if (L.j >= 0 && (q - L.lo <= 0.f || L.hi - q <= 0.f)) lim |= 1u << L.j;
     }
   }
@@ -722,9 +760,7 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
           if (r0 + i < nlim) {
             const int j = nth_set_bit(lim, r0 + i);
             im[i].L = T.jL[j]; im[i].c = T.jC[j];
-            int st;
-            const float* qrec = link_rec_of(sm, im[i].L, im[i].c, e, qb, st);
-            const float q = qrec[W_Q * st];
+            const float q = link_rec_of(sm, im[i].L, im[i].c, e, qb)[W_Q];
             float pen;
             if (q - kJointLo[j] <= 0.f) { pen = q - kJointLo[j]; im[i].dir = 1.f; } else { pen = kJointHi[j] - q; im[i].dir = -1.f; }
             pos[i] = -pen * (float)ILRL_LIMIT_ERP * idt;
@@ -759,13 +795,27 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
     // ---- projected Gauss-Seidel on the velocity change
 #pragma unroll 1
     for (int itn = 0; itn < ILRL_SOLVER_ITERS; itn++) {
+      // limits, then contact normals.  The next row (independent of dv) is fetched while this one is applied.
+      const int nfirst = nlim + ncon;
+      RowRegs rn_;
+      int Ln = 0;
+      float lamn = 0.f;
+      {
+        const int r = nlim > 0 ? 0 : nlim;
+        row_fetch(sm, gscr, e, r, role, rn_);
+        Ln = sm.rowL[r][e]; lamn = sm.lam[r][e];
+      }
 #pragma unroll 1
-      for (int k = 0; k < nlim + ncon; k++) {  // limits, then contact normals
+      for (int k = 0; k < nfirst; k++) {
         const int r = k < nlim ? k : nlim + 3 * (k - nlim);
-        RowRegs rr;
-        row_fetch(sm, gscr, e, r, role, rr);
-        const int L = sm.rowL[r][e];
-        const float lam = sm.lam[r][e];
+        const RowRegs rr = rn_;
+        const int L = Ln;
+        const float lam = lamn;
+        if (k + 1 < nfirst) {
+          const int r2 = k + 1 < nlim ? k + 1 : nlim + 3 * (k + 1 - nlim);
+          row_fetch(sm, gscr, e, r2, role, rn_);
+          Ln = sm.rowL[r2][e]; lamn = sm.lam[r2][e];
+        }
         const float nl = fmaxf(lam + rr.e.z - row_jdot(rr, dvb, dvc, role == L, qb + (L & 3), qm) * rr.e.w, 0.f);
         sm.lam[r][e] = nl;
         row_axpy(rr, nl - lam, dvb, dvc);
@@ -815,13 +865,12 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
     b.quat[0] = nx * inv; b.quat[1] = ny * inv; b.quat[2] = nz * inv; b.quat[3] = nw * inv;
 #pragma unroll
     for (int c = 0; c < NL; c++) {
-      int st;
-      float* rec = link_rec(sm, c, e, tid, st);
-      const float nuc = rec[W_NU * st];
+      float* rec = link_rec(sm, c, e, tid);
+      const float nuc = rec[W_NU];
       const float qd = nrows > 0 ? clampf(nuc + dvc[c], -M, M) : nuc;
       if (c >= 3 || role == 0) {  // the spine records are shared by the quad: one writer for the read-modify-write
-        rec[W_QD * st] = qd;
-        rec[W_Q * st] += dt * qd;
+        rec[W_QD] = qd;
+        rec[W_Q] += dt * qd;
       }
     }
   }
@@ -841,11 +890,10 @@ __device__ __forceinline__ void load_links(const float* phys, int n, int i, Smem
   const float* p = phys + i;
 #pragma unroll
   for (int c = 0; c < NL; c++) {
-    int st;
-    float* rec = link_rec(sm, c, e, tid, st);
+    float* rec = link_rec(sm, c, e, tid);
     const int j = c < 3 ? c : sm.T.lc[role][c - 3].j;
-    rec[W_Q * st] = j >= 0 ? p[(13 + j) * n] : 0.f;
-    rec[W_QD * st] = j >= 0 ? p[(30 + j) * n] : 0.f;
+    rec[W_Q] = j >= 0 ? p[(13 + j) * n] : 0.f;
+    rec[W_QD] = j >= 0 ? p[(30 + j) * n] : 0.f;
   }
 }
 // link records -> full Phys in every lane
@@ -855,10 +903,9 @@ __device__ __forceinline__ void gather(const Base& b, const Smem& sm, int e, int
   for (int j = 0; j < NJ; j++) {
     constexpr Tables T{};
     const int L = T.jL[j], c = T.jC[j];
-    const float* rec = c < 3 ? &sm.sp[c][0][e] : &sm.lk[c - 3][0][qb + L];
-    const int st = c < 3 ? QE : QT;
-    ps.q[j] = rec[W_Q * st];
-    ps.qd[j] = rec[W_QD * st];
+    const float* rec = c < 3 ? &sm.sp[c][e][0] : &sm.lk[c - 3][qb + L][0];
+    ps.q[j] = rec[W_Q];
+    ps.qd[j] = rec[W_QD];
   }
 #pragma unroll
   for (int k = 0; k < 3; k++) { ps.p[k] = b.p[k]; ps.v[k] = b.v[k]; ps.w[k] = b.w[k]; }
@@ -873,10 +920,9 @@ __device__ __forceinline__ void scatter(const Phys& ps, Smem& sm, int e, int qb,
     for (int j = 0; j < NJ; j++) {
       constexpr Tables T{};
       const int L = T.jL[j], c = T.jC[j];
-      float* rec = c < 3 ? &sm.sp[c][0][e] : &sm.lk[c - 3][0][qb + L];
-      const int st = c < 3 ? QE : QT;
-      rec[W_Q * st] = ps.q[j];
-      rec[W_QD * st] = ps.qd[j];
+      float* rec = c < 3 ? &sm.sp[c][e][0] : &sm.lk[c - 3][qb + L][0];
+      rec[W_Q] = ps.q[j];
+      rec[W_QD] = ps.qd[j];
     }
   }
 #pragma unroll

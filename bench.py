@@ -244,8 +244,10 @@ def run_ours(args):
     kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
 
     # end-to-end through the C ABI with HOST buffers (H2D actions, kernel, D2H obs/reward/done inside the timing)
-    host_act = pool[:64].cpu().numpy().astype(np.float32)
-    obs_h = np.zeros((n, 70), np.float32); rew_h = np.zeros(n, np.float32); done_h = np.zeros(n, np.uint8)
+    # pinned host memory on both sides (the contract's e2e definition): DMA endpoints, no staging copies
+    host_act = pool[:64].cpu().pin_memory().numpy()
+    obs_h = torch.zeros(n, 70).pin_memory().numpy(); rew_h = torch.zeros(n).pin_memory().numpy()
+    done_h = torch.zeros(n, dtype=torch.uint8).pin_memory().numpy()
     KE = min(K, 300)
     for i in range(5):
         env.step_host(host_act[i % 64], obs_h, rew_h, done_h)
@@ -288,7 +290,7 @@ def run_ours(args):
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 17 * 4,
                     "d2h_bytes_per_step": n * (70 * 4 + 4 + 1), "steps": KE,
-                    "api": "ilrl_step_host (C ABI, host buffers)"},
+                    "api": "ilrl_step_host (C ABI, pinned host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

@@ -697,19 +697,28 @@ int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* re
     CK(cudaMemset(env->d_obs, 0, sizeof(float) * 70 * n));
   }
   cudaStream_t st = (cudaStream_t)stream;
-  memcpy(env->h_action, action_h, sizeof(float) * 17 * n);
-  CK(cudaMemcpyAsync(env->d_action, env->h_action, sizeof(float) * 17 * n, cudaMemcpyHostToDevice, st));
+  // Page-locked caller buffers are DMA targets as they are; pageable ones go through the handle's pinned mirrors.
+  auto pinned = [](const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  const bool pa = pinned(action_h), po = pinned(obs_h), pr = pinned(reward_h), pd = pinned(done_h),
+             pt = terms_h && pinned(terms_h);
+  if (!pa) memcpy(env->h_action, action_h, sizeof(float) * 17 * n);
+  CK(cudaMemcpyAsync(env->d_action, pa ? action_h : env->h_action, sizeof(float) * 17 * n, cudaMemcpyHostToDevice, st));
   int r = do_step(env, env->d_action, env->d_obs, env->d_reward, env->d_done, terms_h ? env->d_terms : nullptr, stream, 0);
   if (r) return r;
-  CK(cudaMemcpyAsync(env->h_obs, env->d_obs, sizeof(float) * 70 * n, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(env->h_reward, env->d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(env->h_done, env->d_done, n, cudaMemcpyDeviceToHost, st));
-  if (terms_h) CK(cudaMemcpyAsync(env->h_terms, env->d_terms, sizeof(float) * ILRL_TERM_WORDS * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(po ? obs_h : env->h_obs, env->d_obs, sizeof(float) * 70 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(pr ? reward_h : env->h_reward, env->d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(pd ? done_h : env->h_done, env->d_done, n, cudaMemcpyDeviceToHost, st));
+  if (terms_h)
+    CK(cudaMemcpyAsync(pt ? terms_h : env->h_terms, env->d_terms, sizeof(float) * ILRL_TERM_WORDS * n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  memcpy(obs_h, env->h_obs, sizeof(float) * 70 * n);
-  memcpy(reward_h, env->h_reward, sizeof(float) * n);
-  memcpy(done_h, env->h_done, n);
-  if (terms_h) memcpy(terms_h, env->h_terms, sizeof(float) * ILRL_TERM_WORDS * n);
+  if (!po) memcpy(obs_h, env->h_obs, sizeof(float) * 70 * n);
+  if (!pr) memcpy(reward_h, env->h_reward, sizeof(float) * n);
+  if (!pd) memcpy(done_h, env->h_done, n);
+  if (terms_h && !pt) memcpy(terms_h, env->h_terms, sizeof(float) * ILRL_TERM_WORDS * n);
   return ILRL_OK;
 }
 

@@ -370,6 +370,8 @@ __device__ __forceinline__ SV chol6_solve_smem(const float* L, SV b) {
 // limb part in sx/sy) and the origin of the lane's end body.
 struct FkOut { uint32_t act; float sx, sy, ssx, ssy, ex, ey; };
 
+// FULL = false: pose only (part-origin sums and the end-body origin), nothing is written to shared memory.
+template <bool FULL>
 __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid, int role, FkOut& o) {
   const Tables& T = sm.T;
   float R0[9];
@@ -378,7 +380,7 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
   uint32_t act = 0;
   // torso spheres
 #pragma unroll 1
-  for (int g = NS - 5; g < NS; g++) {
+  for (int g = NS - 5; FULL && g < NS; g++) {
     V3 c = mv(R0, mk(kSphereC[3 * g], kSphereC[3 * g + 1], kSphereC[3 * g + 2]));
     const float rad = kSphereR[g], d = b.p[2] + c.z - rad;
     if (d < (float)ILRL_CONTACT_BREAK) act |= 1u << g;
@@ -426,7 +428,7 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
 #pragma unroll
       for (int i = 0; i < 9; i++) Rc[i] = Rn[i];
     }
-    {
+    if (FULL) {
       SV X = rec[W_QD] * S;
       st_ScJ(rec, S, crm(Vp, X));
       Vp = Vp + X;
@@ -443,11 +445,11 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
       for (int k = 0; k < nb; k++) {
         const BodyC& B = T.bc[c < 3 ? 4 : role][slot][k];
         const V3 ob = oc + mv(Rc, rd3(B.off));
-        rigid_rec(Rc, ob, B.m, B.ix, B.iy, B.iz, Vp, rcd);
+        if (FULL) rigid_rec(Rc, ob, B.m, B.ix, B.iy, B.iz, Vp, rcd);
         if (c < 3) { ssx += ob.x; ssy += ob.y; } else { sx += ob.x; sy += ob.y; }
         ex = ob.x; ey = ob.y;
 #pragma unroll 1
-        for (int t = 0; t < B.nsph; t++) {
+        for (int t = 0; FULL && t < B.nsph; t++) {
           const int g = B.sidx[t];
           V3 cs_ = ob + mv(Rc, rd3(B.sph[t]));
           const float rad = B.sph[t][3], d = b.p[2] + cs_.z - rad;
@@ -456,9 +458,11 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
           sp[0] = cs_.x; sp[QE] = cs_.y; sp[2 * QE] = cs_.z - rad; sp[3 * QE] = d;
         }
       }
-      float4* br = reinterpret_cast<float4*>(c < 3 ? &sm.rs[slot][e][0] : &sm.rl[slot][tid][0]);
+      if (FULL) {
+        float4* br = reinterpret_cast<float4*>(c < 3 ? &sm.rs[slot][e][0] : &sm.rl[slot][tid][0]);
 #pragma unroll
-      for (int i = 0; i < RECW / 4; i++) br[i] = make_float4(rcd[4 * i], rcd[4 * i + 1], rcd[4 * i + 2], rcd[4 * i + 3]);
+        for (int i = 0; i < RECW / 4; i++) br[i] = make_float4(rcd[4 * i], rcd[4 * i + 1], rcd[4 * i + 2], rcd[4 * i + 3]);
+      }
     }
   }
   o.act = act; o.sx = sx; o.sy = sy; o.ssx = ssx; o.ssy = ssy; o.ex = ex; o.ey = ey;
@@ -469,7 +473,7 @@ __device__ __forceinline__ void pose_sums(const Base& b, Smem& sm, int e, int ti
                                           float& sumy, float& rfx, float& rfy) {
   FkOut o;
   __syncwarp(qm);
-  fk_phase(b, sm, e, tid, role, o);
+  fk_phase<false>(b, sm, e, tid, role, o);
   sumx = o.ssx + qsum(o.sx, qm);
   sumy = o.ssy + qsum(o.sy, qm);
   const int l0 = (tid & 31) & ~3;
@@ -538,8 +542,33 @@ __device__ __forceinline__ float walk_dd(const Imp& im, float* su) {
   return dd;
 }
 
+// the three impulses of ONE contact share their chain: one walk, link records loaded once, 3-way ILP
+__device__ __forceinline__ void walk_in3(const Smem& sm, const Imp* im, float* su0, float* su1, float* su2, int e, int qb,
+                                         SV* pf, float* rv) {
+#pragma unroll
+  for (int i = 0; i < 3; i++) { pf[i] = neg(im[i].F); rv[i] = 0.f; }
+  const int L = im[0].L;
+#pragma unroll 1
+  for (int c = im[0].c; c >= 0; c--) {
+    if (c == 2 && L >= 2) break;  // arms attach to the torso
+    const float* rec = link_rec_of(sm, L, c, e, qb);
+    SV S, U;
+    float di;
+    ld_SU(rec, S, U, di);
+    const float nu = rec[W_NU];
+    const int jw = c < 3 ? R_JS + c : R_JL + c - 3;
+    const float u0 = -sdot(S, pf[0]), u1 = -sdot(S, pf[1]), u2 = -sdot(S, pf[2]);
+    const float J0 = sdot(S, im[0].F), J1 = sdot(S, im[1].F), J2 = sdot(S, im[2].F);
+    su0[c * QT] = u0; su1[c * QT] = u1; su2[c * QT] = u2;
+    pf[0] = pf[0] + (u0 * di) * U; pf[1] = pf[1] + (u1 * di) * U; pf[2] = pf[2] + (u2 * di) * U;
+    rv[0] += J0 * nu; rv[1] += J1 * nu; rv[2] += J2 * nu;
+    im[0].row[jw] = J0; im[1].row[jw] = J1; im[2].row[jw] = J2;
+  }
+}
+
+// contact = true: im[0..2] are the normal and the two friction directions of one contact (all rows used, same chain)
 __device__ __forceinline__ void responses3(Smem& sm, Imp* im, const float* nub, int e, int tid, int qb, float idt,
-                                           const float* pos /* [3] position term of each row */) {
+                                           const float* pos /* [3] position term of each row */, bool contact) {
   float* su0 = &sm.su[0][0][tid];
   float* su1 = &sm.su[1][0][tid];
   float* su2 = &sm.su[2][0][tid];
@@ -553,9 +582,12 @@ __device__ __forceinline__ void responses3(Smem& sm, Imp* im, const float* nub, 
     }
   float rv[3];
   SV pf[3];
-  pf[0] = walk_in(sm, im[0], su0, e, qb, rv[0]);
-  pf[1] = walk_in(sm, im[1], su1, e, qb, rv[1]);
-  pf[2] = walk_in(sm, im[2], su2, e, qb, rv[2]);
+  if (contact) walk_in3(sm, im, su0, su1, su2, e, qb, pf, rv);
+  else {
+    pf[0] = walk_in(sm, im[0], su0, e, qb, rv[0]);
+    pf[1] = walk_in(sm, im[1], su1, e, qb, rv[1]);
+    pf[2] = walk_in(sm, im[2], su2, e, qb, rv[2]);
+  }
   // base part: J_base = F (contact rows), response of the base
   SV ap[3], a0[3], apel[3];
   float dd[3];
@@ -598,7 +630,7 @@ __device__ __forceinline__ void responses3(Smem& sm, Imp* im, const float* nub, 
     for (int i = 0; i < 3; i++) ap[i] = r < 2 ? apel[i] : a0[i];
     const bool m0 = im[0].L == r, m1 = im[1].L == r, m2 = im[2].L == r;
 #pragma unroll 1
-    for (int k = 0; k < 4; k++) {
+    for (int k = r < 2 ? 0 : 1; k < 4; k++) {  // the arms' leading slot is a dummy: its response stays 0
       SV S, U;
       float di;
       ld_SU(&sm.lk[k][qb + r][0], S, U, di);
@@ -653,7 +685,7 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
   const Tables& T = sm.T;
   // ---- phase A
   FkOut fo;
-  fk_phase(b, sm, e, tid, role, fo);
+  fk_phase<true>(b, sm, e, tid, role, fo);
   uint32_t act = fo.act, lim = 0;
   // ---- phase B: inward pass
   SV a0;
@@ -789,7 +821,7 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
         im[i].row = !used ? nullptr : (r < RSM ? &sm.rows[e][r * RW] : gscr + (size_t)(r - RSM) * RW);
         if (used) { sm.lam[r][e] = 0.f; sm.rowL[r][e] = (signed char)(im[i].c >= 3 ? im[i].L : -1); }
       }
-      responses3(sm, im, nub, e, tid, qb, idt, pos);
+      responses3(sm, im, nub, e, tid, qb, idt, pos, it >= nlg);
     }
     __syncwarp(qm);
     // ---- projected Gauss-Seidel on the velocity change

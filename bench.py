@@ -111,7 +111,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    EMIT(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -294,13 +294,32 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clk,
         }
-        print(json.dumps(line), flush=True)
+        EMIT(json.dumps(line))
     env.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, torchrun notices) may write to fd 1; the contract is ONE JSON line on
+    stdout.  Point fd 1 at stderr for the whole run and return a writer bound to the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    out = os.fdopen(real, "w")
+
+    def emit(line):
+        out.write(line + "\n")
+        out.flush()
+    return emit
+
+
+EMIT = print
+
+
 def main():
+    global EMIT
+    EMIT = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=1000)

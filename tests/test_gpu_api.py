@@ -273,3 +273,58 @@ def test_motion13_13_never_reads_past_its_velocity_table():
         assert bool(torch.isfinite(obs).all())
         assert int(env.get_state()[1][:, B.E_FRAME].max()) < 119
     env.close()
+
+
+def _ks(a, b):
+    """two-sample Kolmogorov-Smirnov statistic"""
+    a, b = np.sort(np.asarray(a, dtype=np.float64)), np.sort(np.asarray(b, dtype=np.float64))
+    allv = np.concatenate([a, b])
+    return float(np.abs(np.searchsorted(a, allv, side="right") / len(a) - np.searchsorted(b, allv, side="right") / len(b)).max())
+
+
+def test_episode_distributions_agree_with_oracle_on_random_rollouts():
+    """north_star: episode-return distributions must agree on random-action rollouts.  First episode of every env
+    (uniform start frame / heading, uniform actions in [-1, 1]) on the CUDA path vs the fp64 oracle: two-sample KS on
+    episode length and episode return, threshold = the alpha = 0.001 critical value for these sample sizes."""
+    n_gpu, n_cpu, cap = 4096, 1500, 600
+    env = BatchedHumanoidEnv(n_gpu, "low", clips=["motion09_03"], seed=77, auto_reset=True)
+    env.reset()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    ret = torch.zeros(n_gpu, device="cuda", dtype=torch.float64)
+    length = torch.zeros(n_gpu, device="cuda")
+    alive = torch.ones(n_gpu, device="cuda", dtype=torch.bool)
+    for t in range(cap):
+        a = torch.rand(n_gpu, 17, device="cuda", generator=g) * 2 - 1
+        obs, rew, done, _ = env.step(a)
+        ret += torch.where(alive, rew.double(), torch.zeros_like(ret))
+        length += alive.float()
+        alive &= done == 0
+        if not bool(alive.any()):
+            break
+    assert not bool(alive.any()), "some first episodes did not end within %d steps" % cap
+    env.close()
+    g_len, g_ret = length.cpu().numpy(), ret.cpu().numpy()
+
+    rng = np.random.default_rng(123)
+    c_len, c_ret = [], []
+    v = O.OracleEnv("motion09_03", 0)
+    mf = O.load_clip("motion09_03")["max_frame"]
+    for ep in range(n_cpu):
+        v.reset(int(rng.integers(0, mf - 5)), 0.0, int(rng.integers(-180, 180)))
+        r_sum, steps = 0.0, 0
+        while True:
+            o, r, d = v.low_step(rng.uniform(-1, 1, 17), rand_deg=int(rng.integers(-180, 180)))
+            r_sum += r
+            steps += 1
+            if d or steps >= cap:
+                break
+        c_len.append(steps)
+        c_ret.append(r_sum)
+    crit = 1.95 * np.sqrt((n_gpu + n_cpu) / (n_gpu * n_cpu))
+    ks_len, ks_ret = _ks(g_len, c_len), _ks(g_ret, c_ret)
+    print("episodes: gpu mean len %.2f ret %.3f | oracle mean len %.2f ret %.3f | KS len %.4f ret %.4f (crit %.4f)" % (
+        g_len.mean(), g_ret.mean(), np.mean(c_len), np.mean(c_ret), ks_len, ks_ret, crit))
+    assert ks_len <= crit, (ks_len, crit)
+    assert ks_ret <= crit, (ks_ret, crit)
+    assert abs(g_len.mean() - np.mean(c_len)) <= 0.05 * np.mean(c_len)

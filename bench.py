@@ -30,6 +30,17 @@ METRIC = "imitation env-steps/sec (physics+reward)"
 UNIT = "env-steps/s"
 ENVS_PER_GPU = 4096
 CLIP = "motion09_03"
+# BASELINE.json configs: the contract line is cfg 2 ("low4096"); the others are extra measurement modes
+WORKLOADS = {
+    "low4096": dict(mode="low", envs=4096, total=None, clips=[CLIP],
+                    name="low-level imitation env, 4096 batched envs per GPU, motion09_03, random start frames, random actions, auto-reset"),
+    "hier16384": dict(mode="hier", envs=16384, total=None, clips=["motion08_03", "motion09_03"],
+                      name="hierarchical env (HumanoidBulletEnvHier-v0), 16384 envs per GPU, selected_motion=1, step_per_level=5, "
+                           "random high (heading) and low (torque) actions, auto-reset; low-level steps counted"),
+    "multiclip65536": dict(mode="low", envs=None, total=65536, clips=["motion02_04", "motion08_03", "motion09_03", "motion13_13"],
+                           name="multi-clip imitation (02_04, 08_03, 09_03, 13_13; clip = env id mod 4), 65536 envs sharded "
+                                "over the GPUs, random actions, auto-reset"),
+}
 BYTES_PER_ENV_STEP = 929  # 2 x 288 B state + 68 B action + 280 B obs + 4 B reward + 1 B done
 WORKLOAD = "low-level imitation env, %d batched envs per GPU, %s, random start frames, random actions, auto-reset" % (
     ENVS_PER_GPU, CLIP)
@@ -192,16 +203,34 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    n = ENVS_PER_GPU
-    env = BatchedHumanoidEnv(n, "low", clips=[CLIP], device=local_rank, seed=1234 + rank, auto_reset=True)
+    wl = WORKLOADS[args.workload]
+    hier = wl["mode"] == "hier"
+    if wl["total"]:  # strong scaling over a fixed total (cfg 4): contiguous env-id blocks, clip = global id mod 4
+        first, n = ilrl_b200.stats.shard_envs(wl["total"], world, rank)
+    else:
+        first, n = rank * wl["envs"], wl["envs"]
+    cid = ilrl_b200.stats.clip_of_env(first, n, len(wl["clips"])) if len(wl["clips"]) > 2 else (
+        np.ones(n, np.int32) if hier else None)
+    env = BatchedHumanoidEnv(n, wl["mode"], clips=wl["clips"], clip_of_env=cid, device=local_rank, seed=1234 + rank,
+                             auto_reset=True)
     env.reset()
-    # action pool larger than L2 (126 MB): 512 batches x 4096 x 17 x 4 B = 142 MB, rotated through -> inputs are
-    # never L2-resident from the previous use.  (The 1.2 MB of persistent env state IS on-chip between steps: that is
-    # the workload — state never leaves the GPU.)
-    POOL = 512
+    # action pool larger than L2 (126 MB), e.g. 512 batches x 4096 x 17 x 4 B = 142 MB, rotated through -> inputs are
+    # never L2-resident from the previous use.  (The persistent env state IS on-chip between steps: that is the
+    # workload — state never leaves the GPU.)
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + rank)
+    POOL = max(8, min(512, (160 << 20) // (n * 17 * 4)))  # keep the pool just above L2 size at every N
     pool = torch.rand(POOL, n, 17, device=dev, generator=g) * 2 - 1
+    hpool = torch.rand(64, n, 2, device=dev, generator=g) * 2 - 1 if hier else None
+    calls = [0]
+
+    def one_step(i):
+        """one low-level env step of every env; in hier mode the waiting envs first get their heading action
+        (the kernel ignores the others), so that every call advances every env by one low-level step"""
+        if hier:
+            env.high_step(hpool[calls[0] % 64])
+        calls[0] += 1
+        env.step(pool[i % POOL])
 
     def barrier():
         if world > 1:
@@ -209,7 +238,7 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     for i in range(W):
-        env.step(pool[i % POOL])
+        one_step(i)
     env.stats()
     barrier()
     clocks = ClockSampler(local_rank) if rank == 0 else None
@@ -218,7 +247,7 @@ def run_ours(args):
     barrier()
     e0.record()
     for i in range(K):
-        env.step(pool[(W + i) % POOL])
+        one_step(W + i)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -230,13 +259,18 @@ def run_ours(args):
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
     clk = clocks.stop() if clocks else None
-    value = world * n * K / (ms * 1e-3)
+    n_all = torch.tensor([float(n)], device=dev)
+    if world > 1:
+        dist.all_reduce(n_all, op=dist.ReduceOp.SUM)
+    value = float(n_all.item()) * K / (ms * 1e-3)
 
     # per-launch kernel time: events around every launch, on the launching stream, in a separate pass
     KT = min(K, 200)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KT)]
     torch.cuda.synchronize()
     for i, (a, b) in enumerate(evs):
+        if hier:
+            env.high_step(hpool[i % 64])
         a.record()
         env.step(pool[(W + K + i) % POOL])
         b.record()
@@ -245,22 +279,28 @@ def run_ours(args):
 
     # end-to-end through the C ABI with HOST buffers (H2D actions, kernel, D2H obs/reward/done inside the timing)
     # pinned host memory on both sides (the contract's e2e definition): DMA endpoints, no staging copies
-    host_act = pool[:64].cpu().pin_memory().numpy()
+    NH = min(64, POOL)
+    host_act = pool[:NH].cpu().pin_memory().numpy()
     obs_h = torch.zeros(n, 70).pin_memory().numpy(); rew_h = torch.zeros(n).pin_memory().numpy()
     done_h = torch.zeros(n, dtype=torch.uint8).pin_memory().numpy()
     KE = min(K, 300)
+    def host_step(i):
+        if hier:
+            env.high_step(hpool[i % 64])
+        env.step_host(host_act[i % NH], obs_h, rew_h, done_h)
+
     for i in range(5):
-        env.step_host(host_act[i % 64], obs_h, rew_h, done_h)
+        host_step(i)
     barrier()
     t0 = time.perf_counter()
     for i in range(KE):
-        env.step_host(host_act[i % 64], obs_h, rew_h, done_h)
+        host_step(i)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t_e = torch.tensor([e2e_s], device=dev)
     if world > 1:
         dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_val = world * n * KE / float(t_e.item())
+    e2e_val = float(n_all.item()) * KE / float(t_e.item())
 
     if rank == 0:
         peak, which = measured_peak()
@@ -275,11 +315,11 @@ def run_ours(args):
         stn = st.cpu().numpy()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "envs_per_gpu": n, "clip": CLIP, "auto_reset": True,
-                       "l2": "action batches rotate through a 142 MB pool (> 126 MB L2); the 1.2 MB env state is "
-                             "persistent on-device state by design",
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if wl["total"] else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["name"], "envs_per_gpu": n, "clips": wl["clips"], "auto_reset": True,
+                       "l2": "action batches rotate through a %d MB pool (> 126 MB L2); the env state is "
+                             "persistent on-device state by design" % (POOL * n * 17 * 4 >> 20),
                        "episodes": float(stn[0]), "mean_episode_len": float(stn[2] / max(stn[0], 1)),
                        "mean_step_reward": float(stn[4] / max(stn[3], 1))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -326,6 +366,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="low4096", choices=sorted(WORKLOADS),
+                    help="low4096 = the contract line (BASELINE cfg 2); the others are extra measurement modes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

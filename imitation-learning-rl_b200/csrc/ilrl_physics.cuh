@@ -12,9 +12,9 @@
 // matrices, the outward pass plain additions — no per-link 6x6 congruence transforms, and fp32 stays accurate
 // however far the robot has walked because only offsets from the torso enter.
 //
-// One thread owns one env (see DESIGN.md "Mapping" for why not a warp per env); all loops below run over
-// compile-time tables, so every thread of a warp executes the same link at the same time and table reads are
-// immediates after unrolling.
+// This header holds the shared vocabulary: model tables, small vector / spatial-inertia helpers, the thread-per-env
+// forward kinematics used by the service kernels (reset, high-level step, end-point score) and the base Cholesky.
+// The substep itself (four lanes per env, rolled chain loops) lives in ilrl_chain.cuh.
 #pragma once
 #include <cuda_runtime.h>
 #include <math.h>
@@ -309,278 +309,8 @@ __device__ __forceinline__ SV chol6_solve(const float* L, SV b) {
   return r;
 }
 
-// tree shape helpers (compile-time): link 2 (abdomen_x) carries both legs, the base carries spine + both arms
-__device__ constexpr bool is_leaf(int l) {
-  for (int j = 0; j < NJ; j++) if (kJointParent[j] == l) return false;
-  return true;
-}
 constexpr int kPelvisLink = 2;
 
-// ---- forward dynamics: returns base spatial acceleration a0 and qdd[NJ]; leaves S,U,Dinv,L0 in k for the rows
-__device__ __forceinline__ void aba(const Phys& s, const float* tau, Work& k, SV& a0, float* qdd) {
-  SV V0; V0.a = ld3(s.w); V0.l = ld3(s.v);
-  // outward: link velocities and velocity-product accelerations
-  ILRL_LINK_LOOP
-  for (int j = 0; j < NJ; j++) {
-    const int p = kJointParent[j];
-    SV Vp = p < 0 ? V0 : ldsv(k.V[p]);
-    SV X = s.qd[j] * ldsv(k.S[j]);
-    stsv(k.V[j], Vp + X);
-    stsv(k.cJ[j], crm(Vp, X));
-  }
-  // inward: articulated inertias; three running accumulators suffice for this tree
-  Inertia cur, pel, bas, Ib;
-  SV pcur, ppel, pbas, pb;
-  pel.zero(); ppel.a = ppel.l = mk(0, 0, 0);
-  body_inertia_bias(k, 0, V0, bas, pbas);
-  ILRL_LINK_LOOP
-  for (int j = NJ - 1; j >= 0; j--) {
-    if (kTree.leaf[j]) { cur.zero(); pcur.a = pcur.l = mk(0, 0, 0); }
-    if (j == kPelvisLink) { cur = pel; pcur = ppel; }
-    SV Vj = ldsv(k.V[j]);
-    if (kTree.linkB0[j] >= 0) { body_inertia_bias(k, kTree.linkB0[j], Vj, Ib, pb); cur.add(Ib); pcur = pcur + pb; }
-    if (kTree.linkB1[j] >= 0) { body_inertia_bias(k, kTree.linkB1[j], Vj, Ib, pb); cur.add(Ib); pcur = pcur + pb; }
-    SV S = ldsv(k.S[j]);
-    SV U = imul(cur, S);
-    float D = sdot(S, U);
-    float dinv = 1.0f / fmaxf(D, 1e-9f);
-    float u = tau[j] - sdot(S, pcur);
-    stsv(k.U[j], U); k.Dinv[j] = dinv; k.u[j] = u;
-    downdate(cur, U, dinv);
-    pcur = pcur + imul(cur, ldsv(k.cJ[j])) + (u * dinv) * U;
-    const int p = kJointParent[j];
-    if (p < 0) { bas.add(cur); pbas = pbas + pcur; }
-    else if (p == kPelvisLink) { pel.add(cur); ppel = ppel + pcur; }
-    // else: flows on to the next (parent) link through `cur`
-  }
-  chol6(bas, k.L0);
-  SV np0; np0.a = mk(-pbas.a.x, -pbas.a.y, -pbas.a.z); np0.l = mk(-pbas.l.x, -pbas.l.y, -pbas.l.z);
-  a0 = chol6_solve(k.L0, np0);
-  // outward: accelerations
-  SV acur = a0, apel = a0;
-  ILRL_LINK_LOOP
-  for (int j = 0; j < NJ; j++) {
-    const int p = kJointParent[j];
-    SV ap = p < 0 ? a0 : (p == kPelvisLink ? apel : acur);
-    SV ad = ap + ldsv(k.cJ[j]);
-    float qa = k.Dinv[j] * (k.u[j] - sdot(ad, ldsv(k.U[j])));
-    qdd[j] = qa;
-    acur = ad + qa * ldsv(k.S[j]);
-    if (j == kPelvisLink) apel = acur;
-  }
-}
-
-// ---- response of the generalized velocities to a unit impulse: spatial force F on link `link` (link = -1: base)
-//      or a unit generalized impulse on joint `jl` (F ignored).  Uses S,U,Dinv,L0 left by aba().  O(n).
-__device__ __forceinline__ void unit_response(const Work& k, int link, SV F, int jl, float* resp /*[NV]*/) {
-  float ul[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; j++) ul[j] = 0.f;
-  SV pf;  // bias force flowing to the base (sign: p = -F)
-  int l;
-  if (jl >= 0) {
-    ul[jl] = 1.f;
-    pf = k.Dinv[jl] * ldsv(k.U[jl]);
-    l = kJointParent[jl];
-  } else {
-    pf.a = mk(-F.a.x, -F.a.y, -F.a.z); pf.l = mk(-F.l.x, -F.l.y, -F.l.z);
-    l = link;
-  }
-  for (; l >= 0; l = kJointParent[l]) {
-    float u = -sdot(ldsv(k.S[l]), pf);
-    ul[l] = u;
-    pf = pf + (u * k.Dinv[l]) * ldsv(k.U[l]);
-  }
-  SV npf; npf.a = mk(-pf.a.x, -pf.a.y, -pf.a.z); npf.l = mk(-pf.l.x, -pf.l.y, -pf.l.z);
-  SV a0 = chol6_solve(k.L0, npf);
-  resp[0] = a0.a.x; resp[1] = a0.a.y; resp[2] = a0.a.z; resp[3] = a0.l.x; resp[4] = a0.l.y; resp[5] = a0.l.z;
-  SV acur = a0, apel = a0;
-  ILRL_LINK_LOOP
-  for (int j = 0; j < NJ; j++) {
-    const int p = kJointParent[j];
-    SV ap = p < 0 ? a0 : (p == kPelvisLink ? apel : acur);
-    float qa = k.Dinv[j] * (ul[j] - sdot(ap, ldsv(k.U[j])));
-    resp[6 + j] = qa;
-    acur = ap + qa * ldsv(k.S[j]);
-    if (j == kPelvisLink) apel = acur;
-  }
-}
-
-// one constraint row (contact rows keep their wrench F; limit rows their joint)
-struct Row {
-  float resp[NV];
-  float F[6];      // contact: unit wrench about the reference point; limit: unused
-  int link;        // contact: link index (-1 base); limit: joint index
-  float dir;       // limit: +1 (lower) / -1 (upper); contact rows: 0
-  float rhs, dinv, lam;
-};
-
-// J . x for a row, x = generalized velocity-like vector (base angular, base linear, joints)
-__device__ __forceinline__ float row_jdot(const Work& k, const Row& r, const float* x) {
-  if (r.dir != 0.f) return r.dir * x[6 + r.link];
-  SV F = ldsv(r.F);
-  float acc = F.a.x * x[0] + F.a.y * x[1] + F.a.z * x[2] + F.l.x * x[3] + F.l.y * x[4] + F.l.z * x[5];
-  for (int l = r.link; l >= 0; l = kJointParent[l]) acc += sdot(ldsv(k.S[l]), F) * x[6 + l];
-  return acc;
-}
-
 __device__ __forceinline__ float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
-
-// ---- one substep of dt (REF: scene.global_step() runs 4 of these with the torques held)
-__device__ __forceinline__ void substep(Phys& s, const float* tau, Work& k, Row* rows, float dt, float* dbg = nullptr) {
-  fk(s, k);
-  SV a0;
-  float nu[NV];
-  {
-    float qdd[NJ];
-    aba(s, tau, k, a0, qdd);
-    // classical acceleration of the torso origin = spatial linear acceleration + w x v
-    V3 w = ld3(s.w), v = ld3(s.v);
-    V3 lin = a0.l + cross(w, v);
-    nu[0] = s.w[0] + dt * a0.a.x; nu[1] = s.w[1] + dt * a0.a.y; nu[2] = s.w[2] + dt * a0.a.z;
-    nu[3] = s.v[0] + dt * lin.x;  nu[4] = s.v[1] + dt * lin.y;  nu[5] = s.v[2] + dt * lin.z;
-#pragma unroll
-    for (int j = 0; j < NJ; j++) nu[6 + j] = s.qd[j] + dt * qdd[j];
-#pragma unroll
-    for (int i = 0; i < NV; i++) nu[i] = clampf(nu[i], -(float)ILRL_MAX_COORD_VEL, (float)ILRL_MAX_COORD_VEL);
-  }
-  // ---- rows: violated joint limits ...
-  int nlim = 0, ncon = 0;
-  const float idt = 1.0f / dt;
-#pragma unroll 1
-  for (int j = 0; j < NJ; j++) {
-    float pen, dir;
-    if (s.q[j] - kJointLo[j] <= 0.f) { pen = s.q[j] - kJointLo[j]; dir = 1.f; }
-    else if (kJointHi[j] - s.q[j] <= 0.f) { pen = kJointHi[j] - s.q[j]; dir = -1.f; }
-    else continue;
-    Row& r = rows[nlim++];
-    r.link = j; r.dir = dir;
-    SV z; z.a = z.l = mk(0, 0, 0);
-    unit_response(k, -1, z, j, r.resp);
-    float d = r.resp[6 + j];
-    r.dinv = 1.0f / d;
-    r.rhs = (-pen * (float)ILRL_LIMIT_ERP * idt - dir * nu[6 + j]) * r.dinv;
-    r.lam = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; i++) r.resp[i] *= dir;
-  }
-  // ---- ... then ground contacts: the deepest ILRL_MAX_CONTACTS spheres below the breaking distance
-  {
-    float sd[NS];
-    uint32_t act = 0;
-    int nact = 0;
-    ILRL_LINK_LOOP
-    for (int i = 0; i < NS; i++) {
-      const int b = kSphereBody[i];
-      float cz = k.o[b][2] + k.R[b][6] * kSphereC[3 * i] + k.R[b][7] * kSphereC[3 * i + 1] + k.R[b][8] * kSphereC[3 * i + 2];
-      sd[i] = s.p[2] + cz - kSphereR[i];
-      if (sd[i] < (float)ILRL_CONTACT_BREAK) { act |= 1u << i; nact++; }
-    }
-    while (nact > MAXC) {
-      int worst = -1;
-      float wd = -1e30f;
-      for (int i = 0; i < NS; i++)
-        if (((act >> i) & 1u) && sd[i] >= wd) { wd = sd[i]; worst = i; }
-      act &= ~(1u << worst);
-      nact--;
-    }
-#pragma unroll 1
-    for (int i = 0; i < NS; i++) {
-      if (!((act >> i) & 1u)) continue;
-      const int b = kSphereBody[i];
-      V3 c = ld3(k.o[b]) + mv(k.R[b], mk(kSphereC[3 * i], kSphereC[3 * i + 1], kSphereC[3 * i + 2]));
-      V3 x = mk(c.x, c.y, c.z - kSphereR[i]);  // contact point on the robot, relative to the reference point
-      float dist = sd[i];
-      const int link = kSphereLink[i];
-      if (dbg) { dbg[230 + ncon] = (float)i; dbg[240 + ncon] = dist; dbg[250 + ncon] = c.z + s.p[2] - kSphereR[i]; for (int q = 0; q < NS; q++) dbg[260 + q] = sd[q]; dbg[259] = (float)act; }
-      // normal (0,0,1), tangents btPlaneSpace1 -> (0,-1,0), (1,0,0)
-#pragma unroll
-      for (int t = 0; t < 3; t++) {
-        V3 d = t == 0 ? mk(0, 0, 1) : (t == 1 ? mk(0, -1, 0) : mk(1, 0, 0));
-        Row& r = rows[nlim + 3 * ncon + t];
-        SV F; F.a = cross(x, d); F.l = d;
-        stsv(r.F, F); r.link = link; r.dir = 0.f; r.lam = 0.f;
-        unit_response(k, link, F, -1, r.resp);
-        float dd = row_jdot(k, r, r.resp), rv = row_jdot(k, r, nu);
-        r.dinv = 1.0f / dd;
-        float pos = t == 0 ? (dist > 0.f ? -dist * idt : -dist * (float)ILRL_CONTACT_ERP * idt) : 0.f;
-        r.rhs = (pos - rv) * r.dinv;
-      }
-      ncon++;
-    }
-  }
-  // ---- projected Gauss-Seidel on the velocity change dv (limits, normals, friction pairs with implicit cone)
-  if (nlim + ncon > 0) {
-    float dv[NV];
-#pragma unroll
-    for (int i = 0; i < NV; i++) dv[i] = 0.f;
-#pragma unroll 1
-    for (int it = 0; it < ILRL_SOLVER_ITERS; it++) {
-#pragma unroll 1
-      for (int ri = 0; ri < nlim; ri++) {
-        Row& r = rows[ri];
-        float nl = fmaxf(r.lam + r.rhs - (r.dir * dv[6 + r.link]) * r.dinv, 0.f);
-        float dl = nl - r.lam;
-        r.lam = nl;
-#pragma unroll
-        for (int i = 0; i < NV; i++) dv[i] += dl * r.resp[i];
-      }
-#pragma unroll 1
-      for (int ci = 0; ci < ncon; ci++) {
-        Row& r = rows[nlim + 3 * ci];
-        float nl = fmaxf(r.lam + r.rhs - row_jdot(k, r, dv) * r.dinv, 0.f);
-        float dl = nl - r.lam;
-        r.lam = nl;
-#pragma unroll
-        for (int i = 0; i < NV; i++) dv[i] += dl * r.resp[i];
-      }
-#pragma unroll 1
-      for (int ci = 0; ci < ncon; ci++) {
-        Row& rn = rows[nlim + 3 * ci];
-        if (!(rn.lam > 0.f)) continue;
-        Row& r1 = rows[nlim + 3 * ci + 1];
-        Row& r2 = rows[nlim + 3 * ci + 2];
-        float lim = (float)ILRL_FRICTION * rn.lam;
-        float s1 = r1.lam + r1.rhs - row_jdot(k, r1, dv) * r1.dinv;
-        float s2 = r2.lam + r2.rhs - row_jdot(k, r2, dv) * r2.dinv;
-        float n2 = s1 * s1 + s2 * s2;
-        if (n2 > lim * lim) { float sc = lim * rsqrtf(n2); s1 *= sc; s2 *= sc; }
-        float d1 = s1 - r1.lam, d2 = s2 - r2.lam;
-        r1.lam = s1; r2.lam = s2;
-#pragma unroll
-        for (int i = 0; i < NV; i++) dv[i] += d1 * r1.resp[i] + d2 * r2.resp[i];
-      }
-    }
-    if (dbg) {
-      dbg[0] = (float)nlim; dbg[1] = (float)ncon;
-      for (int r = 0; r < nlim + 3 * ncon; r++) {
-        dbg[2 + 5 * r] = (float)rows[r].link; dbg[3 + 5 * r] = rows[r].dir; dbg[4 + 5 * r] = rows[r].rhs;
-        dbg[5 + 5 * r] = rows[r].dinv; dbg[6 + 5 * r] = rows[r].lam;
-      }
-      for (int i = 0; i < NV; i++) { dbg[300 + i] = nu[i]; dbg[330 + i] = dv[i]; dbg[360 + i] = rows[0].resp[i]; }
-    }
-#pragma unroll
-    for (int i = 0; i < NV; i++) nu[i] = clampf(nu[i] + dv[i], -(float)ILRL_MAX_COORD_VEL, (float)ILRL_MAX_COORD_VEL);
-  }
-  // ---- integrate (exponential map on the torso quaternion, as btMultiBody::stepPositionsMultiDof)
-#pragma unroll
-  for (int i = 0; i < 3; i++) { s.w[i] = nu[i]; s.v[i] = nu[3 + i]; s.p[i] += dt * nu[3 + i]; }
-  {
-    float wn = sqrtf(nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]), sc, cw;
-    if (wn < 1e-3f) sc = 0.5f * dt - dt * dt * dt * 0.020833333333f * wn * wn;
-    else sc = sinf(0.5f * wn * dt) / wn;
-    cw = cosf(0.5f * wn * dt);
-    float dx = nu[0] * sc, dy = nu[1] * sc, dz = nu[2] * sc;
-    float x = s.quat[0], y = s.quat[1], z = s.quat[2], ww = s.quat[3];
-    float nx = cw * x + dx * ww + dy * z - dz * y;
-    float ny = cw * y - dx * z + dy * ww + dz * x;
-    float nz = cw * z + dx * y - dy * x + dz * ww;
-    float nw = cw * ww - dx * x - dy * y - dz * z;
-    float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
-    s.quat[0] = nx * inv; s.quat[1] = ny * inv; s.quat[2] = nz * inv; s.quat[3] = nw * inv;
-  }
-#pragma unroll
-  for (int j = 0; j < NJ; j++) { s.qd[j] = nu[6 + j]; s.q[j] += dt * s.qd[j]; }
-}
 
 }  // namespace ilrl

@@ -444,6 +444,25 @@ __global__ void __launch_bounds__(BLOCK) endpoint_kernel(const EpArgs a) {
   fk(s, k);
   a.score[i] = endpoint_score(s, k, w, a.clips[(int)w.e[ILRL_E_CLIP]]);
 }
+// Generalised advantage estimation over a [T, N] rollout: one thread per env walks its column backwards
+// (adjacent threads = adjacent envs: every access of a warp is one coalesced line).
+__global__ void gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const uint8_t* __restrict__ done,
+                           float gamma, float lam, float* __restrict__ adv, float* __restrict__ ret, int T, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  float vnext = val[(size_t)T * n + i];
+  for (int t = T - 1; t >= 0; t--) {
+    const size_t k = (size_t)t * n + i;
+    const float nd = done[k] ? 0.f : 1.f;
+    const float v = val[k];
+    const float delta = rew[k] + gamma * vnext * nd - v;
+    a = delta + gamma * lam * nd * a;
+    adv[k] = a;
+    ret[k] = a + v;
+    vnext = v;
+  }
+}
 __global__ void stats_fetch_kernel(float* acc, float* out) {
   int t = threadIdx.x;
   if (t < ILRL_STATS_WORDS) { out[t] = acc[t]; acc[t] = 0.f; }
@@ -799,6 +818,12 @@ int ilrl_stats(ilrl_env* env, float* stats16, void* stream) {
   env->launches++;
   CK(cudaGetLastError());
   return ILRL_OK;
+}
+int ilrl_gae(const float* reward, const float* value, const uint8_t* done, float gamma, float lam, float* advantage,
+             float* value_target, int32_t T, int32_t n, void* stream) {
+  if (!reward || !value || !done || !advantage || !value_target || T <= 0 || n <= 0) return ILRL_ERR_ARG;
+  gae_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reward, value, done, gamma, lam, advantage, value_target, T, n);
+  return cudaGetLastError() == cudaSuccess ? ILRL_OK : ILRL_ERR_CUDA;
 }
 /* harness only, not in ilrl.h: number of substeps ilrl_physics_only runs */
 int ilrl_debug_substeps(ilrl_env* env, int32_t n) { if (!env || n < 1) return ILRL_ERR_ARG; env->substeps = n; return ILRL_OK; }

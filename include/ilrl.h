@@ -115,6 +115,14 @@ int ilrl_endpoint_score(ilrl_env* env, float* score_dev, void* stream);
  * floats across ranks (NCCL sum) — the only collective of the path. */
 int ilrl_stats(ilrl_env* env, float* stats16_dev, void* stream);
 
+/* Rollout post-processing on the device (what RLlib's `compute_advantages` does on the host
+ * for the reference's PPO configs, gamma / lambda of REF train_config.py:97-98): generalised advantage estimation
+ * over a [T, N] rollout laid out step-major.  reward_dev [T,N], value_dev [T+1,N] (row T = value of the state after
+ * the last step), done_dev [T,N] uint8 (a done step does not bootstrap), outputs advantage_dev / value_target_dev
+ * [T,N].  No handle: pure function of its arguments, asynchronous on `stream`. */
+int ilrl_gae(const float* reward_dev, const float* value_dev, const uint8_t* done_dev, float gamma, float lambda_,
+             float* advantage_dev, float* value_target_dev, int32_t T, int32_t n, void* stream);
+
 /* How many kernels of this library have been launched through the handle (bench.py "gpu_launches"). */
 int64_t ilrl_launch_count(const ilrl_env* env);
 /* Time of the step kernels only, measured with CUDA events on `stream` around each ilrl_step since the last call:

@@ -330,7 +330,7 @@ def run_ours(args):
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 17 * 4,
                     "d2h_bytes_per_step": n * (70 * 4 + 4 + 1), "steps": KE,
-                    "api": "ilrl_step_host (C ABI, pinned host buffers)"},
+                    "api": "ilrl_step_host (C ABI, pinned + mapped host buffers: actions read and obs/reward/done written in place by the step kernel)"},
             "gpu_launches": int(launches),
             "clocks": clk,
         }

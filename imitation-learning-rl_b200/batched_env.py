@@ -124,9 +124,10 @@ class BatchedHumanoidEnv:
     def step_host(self, action_np, obs_np, reward_np, done_np, terms_np=None):
         """Same step through host (numpy) buffers: H2D of the actions, kernel, D2H of obs/reward/done, synchronous."""
         assert action_np.dtype == np.float32 and action_np.flags.c_contiguous
-        self._ck(self.L.ilrl_step_host(self.h, action_np.ctypes.data, obs_np.ctypes.data, reward_np.ctypes.data,
-                                       done_np.ctypes.data, None if terms_np is None else terms_np.ctypes.data,
-                                       self._stream()))
+        assert obs_np.dtype == np.float32 and reward_np.dtype == np.float32 and done_np.dtype == np.uint8
+        ptr = lambda a: a.__array_interface__["data"][0]  # noqa: E731  (cheaper than ndarray.ctypes)
+        self._ck(self.L.ilrl_step_host(self.h, ptr(action_np), ptr(obs_np), ptr(reward_np), ptr(done_np),
+                                       None if terms_np is None else ptr(terms_np), self._stream()))
 
     def high_step(self, action2):
         """hier mode: heading action [N,2] for the envs waiting for one; returns the low-level obs tensor [N,70]

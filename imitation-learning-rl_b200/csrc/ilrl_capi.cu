@@ -494,6 +494,7 @@ struct ilrl_env {
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_terms = nullptr;
   uint8_t* d_done = nullptr;
   int substeps = ILRL_SUBSTEPS;  // harness only (ilrl_debug_substeps)
+  bool no_zero_copy = false;     // harness only (ilrl_debug_zero_copy): force the explicit-copy host path
   int64_t launches = 0;
   bool timing = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -724,6 +725,22 @@ int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* re
   };
   const bool pa = pinned(action_h), po = pinned(obs_h), pr = pinned(reward_h), pd = pinned(done_h),
              pt = terms_h && pinned(terms_h);
+  if (pa && po && pr && pd && (!terms_h || pt) && !env->no_zero_copy) {
+    // Zero-copy: the step kernel reads the action tiles from, and writes obs / reward / done to, the caller's
+    // page-locked buffers through their device mappings.  One launch + one synchronise; the output writes of CTAs
+    // that finish early overlap the tail of the kernel instead of waiting for a separate D2H copy.
+    void *da = nullptr, *dobs = nullptr, *dr = nullptr, *dd = nullptr, *dt = nullptr;
+    if (cudaHostGetDevicePointer(&da, const_cast<float*>(action_h), 0) == cudaSuccess &&
+        cudaHostGetDevicePointer(&dobs, obs_h, 0) == cudaSuccess && cudaHostGetDevicePointer(&dr, reward_h, 0) == cudaSuccess &&
+        cudaHostGetDevicePointer(&dd, done_h, 0) == cudaSuccess &&
+        (!terms_h || cudaHostGetDevicePointer(&dt, terms_h, 0) == cudaSuccess)) {
+      int r = do_step(env, (const float*)da, (float*)dobs, (float*)dr, (uint8_t*)dd, (float*)dt, stream, 0);
+      if (r) return r;
+      CK(cudaStreamSynchronize(st));
+      return ILRL_OK;
+    }
+    cudaGetLastError();  // not mappable after all: fall through to explicit copies
+  }
   if (!pa) memcpy(env->h_action, action_h, sizeof(float) * 17 * n);
   CK(cudaMemcpyAsync(env->d_action, pa ? action_h : env->h_action, sizeof(float) * 17 * n, cudaMemcpyHostToDevice, st));
   int r = do_step(env, env->d_action, env->d_obs, env->d_reward, env->d_done, terms_h ? env->d_terms : nullptr, stream, 0);
@@ -825,6 +842,8 @@ int ilrl_gae(const float* reward, const float* value, const uint8_t* done, float
   gae_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reward, value, done, gamma, lam, advantage, value_target, T, n);
   return cudaGetLastError() == cudaSuccess ? ILRL_OK : ILRL_ERR_CUDA;
 }
+/* harness only, not in ilrl.h: on = 0 forces ilrl_step_host onto explicit copies even for page-locked buffers */
+int ilrl_debug_zero_copy(ilrl_env* env, int32_t on) { if (!env) return ILRL_ERR_ARG; env->no_zero_copy = on == 0; return ILRL_OK; }
 /* harness only, not in ilrl.h: number of substeps ilrl_physics_only runs */
 int ilrl_debug_substeps(ilrl_env* env, int32_t n) { if (!env || n < 1) return ILRL_ERR_ARG; env->substeps = n; return ILRL_OK; }
 int64_t ilrl_launch_count(const ilrl_env* env) { return env ? env->launches : 0; }

@@ -81,8 +81,9 @@ int ilrl_step(ilrl_env* env, const float* action_dev, float* obs_dev, float* rew
               float* terms_dev, void* stream);
 
 /* Same step through HOST buffers: copies the actions up, runs the step, copies obs/reward/done back and waits.
- * Page-locked buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory) are used as DMA endpoints directly;
- * pageable ones are staged through pinned mirrors owned by the handle.
+ * When every buffer is page-locked and mapped (cudaHostAlloc / cudaHostRegister / torch pin_memory) the kernel reads
+ * and writes them in place (zero-copy: one launch, one synchronise); otherwise page-locked buffers are DMA endpoints
+ * and pageable ones are staged through pinned mirrors owned by the handle.
  * This is the call the reference-facing Python env classes make (end-to-end path measured by bench.py "e2e"). */
 int ilrl_step_host(ilrl_env* env, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host,
                    float* terms_host, void* stream);

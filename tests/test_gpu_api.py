@@ -328,3 +328,38 @@ def test_episode_distributions_agree_with_oracle_on_random_rollouts():
     assert ks_len <= crit, (ks_len, crit)
     assert ks_ret <= crit, (ks_ret, crit)
     assert abs(g_len.mean() - np.mean(c_len)) <= 0.05 * np.mean(c_len)
+
+
+def test_step_host_paths_agree():
+    """ilrl_step_host: pageable buffers (staged), page-locked buffers with explicit copies, and page-locked buffers
+    read / written in place by the kernel must give bit-identical results to the device-pointer call."""
+    import ctypes as C
+    n = 300
+    rng = np.random.default_rng(3)
+    acts = rng.uniform(-1.2, 1.2, (4, n, 17)).astype(np.float32)
+    ref = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], seed=11, auto_reset=True)
+    ref.reset()
+    want = []
+    for a in acts:
+        o, r, d, t = ref.step(torch.from_numpy(a).cuda())
+        want.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy(), t.cpu().numpy().copy()))
+    ref.close()
+    for kind in ("pageable", "pinned_copy", "zero_copy"):
+        env = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], seed=11, auto_reset=True)
+        env.reset()
+        env.L.ilrl_debug_zero_copy.argtypes = [C.c_void_p, C.c_int32]
+        env.L.ilrl_debug_zero_copy(env.h, 1 if kind == "zero_copy" else 0)
+
+        def buf(shape, dtype):
+            t = torch.zeros(*shape, dtype=dtype)
+            return (t if kind == "pageable" else t.pin_memory()).numpy()
+        a_h, o_h, r_h, d_h, t_h = buf((n, 17), torch.float32), buf((n, 70), torch.float32), buf((n,), torch.float32), \
+            buf((n,), torch.uint8), buf((n, 12), torch.float32)
+        for k, a in enumerate(acts):
+            a_h[:] = a
+            env.step_host(a_h, o_h, r_h, d_h, t_h)
+            np.testing.assert_array_equal(o_h, want[k][0], err_msg=kind)
+            np.testing.assert_array_equal(r_h, want[k][1], err_msg=kind)
+            np.testing.assert_array_equal(d_h, want[k][2], err_msg=kind)
+            np.testing.assert_array_equal(t_h, want[k][3], err_msg=kind)
+        env.close()

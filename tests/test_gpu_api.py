@@ -363,3 +363,81 @@ def test_step_host_paths_agree():
             np.testing.assert_array_equal(d_h, want[k][2], err_msg=kind)
             np.testing.assert_array_equal(t_h, want[k][3], err_msg=kind)
         env.close()
+
+
+def test_c_abi_error_behaviour_on_device():
+    """Call-order and argument errors come back as negative ilrl_status codes with a message, never as a crash."""
+    import ctypes as C
+    from ilrl_b200 import _lib
+    L = _lib.lib()
+    cfg = _lib.Config(device=0, num_envs=32, mode=0, auto_reset=0, seed=1, skip_frame=2, max_timestep=3000,
+                      step_per_level=5, reserved=0)
+    h = C.c_void_p()
+    assert L.ilrl_create(C.byref(cfg), C.byref(h)) == 0
+    buf = torch.zeros(32, 70, device="cuda")
+    act = torch.zeros(32, 17, device="cuda")
+    rew = torch.zeros(32, device="cuda")
+    done = torch.zeros(32, dtype=torch.uint8, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    # no clip loaded yet
+    assert L.ilrl_reset(h, None, None, None, None, None, p(buf), None) == -3
+    assert L.ilrl_step(h, p(act), p(buf), p(rew), p(done), None, None) == -3
+    assert b"clip" in L.ilrl_last_error(h)
+    assert L.ilrl_set_clip_ids(h, None) == -3
+    # a clip whose max_frame runs past a table is refused (motion13_13 unclamped: 219 > 120 velocity rows)
+    c = ilrl_b200.load_clip("motion13_13")
+    args = (c["pos"].ctypes.data, len(c["pos"]), c["rel"].ctypes.data, len(c["rel"]), c["vel"].ctypes.data,
+            len(c["vel"]), c["ep"].ctypes.data, len(c["ep"]))
+    assert L.ilrl_load_clip(h, 0, *args, len(c["pos"]) - 1) == -1
+    assert L.ilrl_load_clip(h, 9, *args, c["max_frame"]) == -1           # clip slot out of range
+    assert L.ilrl_load_clip(h, 0, *args, c["max_frame"]) == 0
+    ids = np.full(32, 3, np.int32)
+    assert L.ilrl_set_clip_ids(h, ids.ctypes.data) == -3                  # clip 3 is not loaded
+    assert L.ilrl_set_clip_ids(h, None) == 0
+    # hier-only entry points on a low-level handle, null buffers
+    assert L.ilrl_high_step(h, p(act), p(buf), None) == -1
+    assert L.ilrl_high_readout(h, None, None, None, None) == -1
+    assert L.ilrl_step(h, None, p(buf), p(rew), p(done), None, None) == -1
+    assert L.ilrl_reset(h, None, None, None, None, None, p(buf), None) == 0
+    assert L.ilrl_step(h, p(act), p(buf), p(rew), p(done), None, None) == 0
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(buf).all()) and L.ilrl_launch_count(h) >= 3
+    L.ilrl_destroy(h)
+    L.ilrl_destroy(None)                                                  # no-op
+
+
+def test_hier_multi_step_rollout_tracks_oracle():
+    """16 hierarchical envs driven through the batched protocol for 3 high-level periods; every low-level step is
+    checked against the oracle restarted from the pre-step state (rewards, flags, high-level reward at boundaries)."""
+    n = 16
+    rng = np.random.default_rng(9)
+    env = BatchedHumanoidEnv(n, "hier", clips=["motion08_03", "motion09_03"], clip_of_env=np.ones(n, np.int32), seed=5,
+                             auto_reset=False)
+    env.reset()
+    checked = 0
+    for period in range(3):
+        ha = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        env.high_step(ha)
+        for k in range(5):
+            phys, envf = [t.cpu().numpy().astype(np.float64) for t in env.get_state()]
+            a = rng.uniform(-0.5, 0.5, (n, 17)).astype(np.float32)
+            deg = rng.integers(-180, 180, n)
+            env.set_forced_target_deg(deg)
+            obs, rew, done, _ = env.step(a)
+            ho, hr, hf = env.high_readout()
+            obs, rew, done, ho, hr, hf = [t.cpu().numpy() for t in (obs, rew, done, ho, hr, hf)]
+            for i in range(n):
+                if envf[i, B.E_HIGH_PENDING] != 0:      # finished earlier and is waiting for a reset / high action
+                    continue
+                v = O.OracleEnv("motion09_03", 1)
+                v.set(phys[i], envf[i])
+                lo, lr, hi_o, hi_r, ended, high_present = v.hier_low_step(a[i].astype(np.float64), rand_deg=int(deg[i]))
+                assert abs(rew[i] - lr) <= 5e-3
+                if bool(done[i]) == ended:              # the alive threshold can flip on fp32 z
+                    assert bool(hf[i] & 2) == high_present
+                    if high_present:
+                        assert abs(hr[i] - hi_r) <= 2e-2 * max(1.0, abs(hi_r))
+                        np.testing.assert_allclose(ho[i][:5], hi_o[:5], atol=2e-3)
+                checked += 1
+    assert checked >= n * 10
+    env.close()

@@ -827,30 +827,32 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
     // ---- projected Gauss-Seidel on the velocity change
 #pragma unroll 1
     for (int itn = 0; itn < ILRL_SOLVER_ITERS; itn++) {
-      // limits, then contact normals.  The next row (independent of dv) is fetched while this one is applied.
+      // limits, then contact normals.  The next row (independent of dv) is fetched while this one is applied:
+      // two register buffers used alternately (the loop is unrolled by two so that no copies are needed).
       const int nfirst = nlim + ncon;
-      RowRegs rn_;
-      int Ln = 0;
-      float lamn = 0.f;
-      {
-        const int r = nlim > 0 ? 0 : nlim;
-        row_fetch(sm, gscr, e, r, role, rn_);
-        Ln = sm.rowL[r][e]; lamn = sm.lam[r][e];
-      }
-#pragma unroll 1
-      for (int k = 0; k < nfirst; k++) {
-        const int r = k < nlim ? k : nlim + 3 * (k - nlim);
-        const RowRegs rr = rn_;
-        const int L = Ln;
-        const float lam = lamn;
-        if (k + 1 < nfirst) {
-          const int r2 = k + 1 < nlim ? k + 1 : nlim + 3 * (k + 1 - nlim);
-          row_fetch(sm, gscr, e, r2, role, rn_);
-          Ln = sm.rowL[r2][e]; lamn = sm.lam[r2][e];
-        }
+      auto row_of = [&](int k) { return k < nlim ? k : nlim + 3 * (k - nlim); };
+      auto fetch = [&](int k, RowRegs& rr, int& L, float& lam) {
+        const int r = row_of(k);
+        row_fetch(sm, gscr, e, r, role, rr);
+        L = sm.rowL[r][e]; lam = sm.lam[r][e];
+      };
+      auto apply = [&](int k, const RowRegs& rr, int L, float lam) {
         const float nl = fmaxf(lam + rr.e.z - row_jdot(rr, dvb, dvc, role == L, qb + (L & 3), qm) * rr.e.w, 0.f);
-        sm.lam[r][e] = nl;
+        sm.lam[row_of(k)][e] = nl;
         row_axpy(rr, nl - lam, dvb, dvc);
+      };
+      RowRegs ra, rb;
+      int La = 0, Lb = 0;
+      float lama = 0.f, lamb = 0.f;
+      fetch(0, ra, La, lama);  // nrows > 0 implies nfirst > 0
+#pragma unroll 1
+      for (int k = 0; k < nfirst; k += 2) {
+        if (k + 1 < nfirst) fetch(k + 1, rb, Lb, lamb);
+        apply(k, ra, La, lama);
+        if (k + 1 < nfirst) {
+          if (k + 2 < nfirst) fetch(k + 2, ra, La, lama);
+          apply(k + 1, rb, Lb, lamb);
+        }
       }
 #pragma unroll 1
       for (int c = 0; c < ncon; c++) {  // friction pairs, cone re-projected on the current normal impulse

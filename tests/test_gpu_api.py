@@ -441,3 +441,31 @@ def test_hier_multi_step_rollout_tracks_oracle():
                 checked += 1
     assert checked >= n * 10
     env.close()
+
+
+def test_long_bang_bang_stress_stays_finite():
+    """8192 envs x 1500 steps of saturating +-1 actions (the hardest case for the limit / contact rows): every
+    observation, reward and state word stays finite, episodes keep ending and restarting, frames stay in range."""
+    n = 8192
+    env = BatchedHumanoidEnv(n, "low", clips=ilrl_b200.CLIP_NAMES, clip_of_env=np.arange(n, dtype=np.int32) % 4, seed=31,
+                             auto_reset=True)
+    env.reset()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    bad = torch.zeros((), device="cuda", dtype=torch.int64)
+    for t in range(1500):
+        a = (torch.rand(n, 17, device="cuda", generator=g) < 0.5).float() * 2 - 1
+        if t % 7 == 0:
+            a = a * 50.0                      # far outside the Box: torque is clipped, the electricity cost is not (Q4)
+        obs, rew, done, _ = env.step(a)
+        bad += (~torch.isfinite(obs)).sum() + (~torch.isfinite(rew)).sum()
+    phys, envf = env.get_state()
+    st = env.stats().cpu().numpy()
+    assert int(bad) == 0
+    assert bool(torch.isfinite(phys).all()) and bool(torch.isfinite(envf).all())
+    assert st[0] > n and st[3] == n * 1500
+    mf = torch.tensor([ilrl_b200.load_clip(c)["max_frame"] for c in ilrl_b200.CLIP_NAMES], device="cuda")[
+        torch.arange(n, device="cuda") % 4]
+    assert bool((envf[:, B.E_FRAME] < (mf - 1).float()).all()) and bool((envf[:, B.E_FRAME] >= 0).all())
+    assert bool((phys[:, 13:30].abs() < 10).all())      # joint angles stay near their limits
+    env.close()

@@ -674,9 +674,67 @@ __device__ __forceinline__ void row_axpy(const RowRegs& r, float a, float* dvb, 
   dvc[0] += a * r.b.z; dvc[1] += a * r.b.w; dvc[2] += a * r.c.x;
   dvc[3] += a * r.rl.x; dvc[4] += a * r.rl.y; dvc[5] += a * r.rl.z; dvc[6] += a * r.rl.w;
 }
+// OVER = false: the env has no row beyond the shared-memory budget (the common case): plain shared-memory loads, no
+// predicated-off global loads in the instruction stream (those would take issue slots in every row evaluation).
+template <bool OVER>
 __device__ __forceinline__ void row_fetch(const Smem& sm, const float* gscr, int e, int r, int role, RowRegs& rr) {
-  if (r < RSM) row_load(reinterpret_cast<const float4*>(&sm.rows[e][r * RW]), role, rr);
+  if (!OVER || r < RSM) row_load(reinterpret_cast<const float4*>(&sm.rows[e][r * RW]), role, rr);
   else row_load(reinterpret_cast<const float4*>(gscr + (size_t)(r - RSM) * RW), role, rr);
+}
+
+// 5 projected-Gauss-Seidel sweeps on the velocity change (dvb: base, dvc: chain) of the env of this quad
+template <bool OVER>
+__device__ __forceinline__ void pgs_sweeps(Smem& sm, const float* gscr, int e, int role, int qb, unsigned qm, int nlim,
+                                           int ncon, float* dvb, float* dvc) {
+#pragma unroll 1
+  for (int itn = 0; itn < ILRL_SOLVER_ITERS; itn++) {
+    // limits, then contact normals.  The next row (independent of dv) is fetched while this one is applied:
+    // two register buffers used alternately (the loop is unrolled by two so that no copies are needed).
+    const int nfirst = nlim + ncon;
+    auto row_of = [&](int k) { return k < nlim ? k : nlim + 3 * (k - nlim); };
+    auto fetch = [&](int k, RowRegs& rr, int& L, float& lam) {
+      const int r = row_of(k);
+      row_fetch<OVER>(sm, gscr, e, r, role, rr);
+      L = sm.rowL[r][e]; lam = sm.lam[r][e];
+    };
+    auto apply = [&](int k, const RowRegs& rr, int L, float lam) {
+      const float nl = fmaxf(lam + rr.e.z - row_jdot(rr, dvb, dvc, role == L, qb + (L & 3), qm) * rr.e.w, 0.f);
+      sm.lam[row_of(k)][e] = nl;
+      row_axpy(rr, nl - lam, dvb, dvc);
+    };
+    RowRegs ra, rb;
+    int La = 0, Lb = 0;
+    float lama = 0.f, lamb = 0.f;
+    fetch(0, ra, La, lama);  // nrows > 0 implies nfirst > 0
+#pragma unroll 1
+    for (int k = 0; k < nfirst; k += 2) {
+      if (k + 1 < nfirst) fetch(k + 1, rb, Lb, lamb);
+      apply(k, ra, La, lama);
+      if (k + 1 < nfirst) {
+        if (k + 2 < nfirst) fetch(k + 2, ra, La, lama);
+        apply(k + 1, rb, Lb, lamb);
+      }
+    }
+#pragma unroll 1
+    for (int c = 0; c < ncon; c++) {  // friction pairs, cone re-projected on the current normal impulse
+      const int rn = nlim + 3 * c;
+      const float ln = sm.lam[rn][e];
+      if (!(ln > 0.f)) continue;
+      RowRegs r1, r2;
+      row_fetch<OVER>(sm, gscr, e, rn + 1, role, r1);
+      row_fetch<OVER>(sm, gscr, e, rn + 2, role, r2);
+      const int L = sm.rowL[rn][e];
+      const float lim_f = (float)ILRL_FRICTION * ln;
+      const float l1 = sm.lam[rn + 1][e], l2 = sm.lam[rn + 2][e];
+      float s1 = l1 + r1.e.z - row_jdot(r1, dvb, dvc, role == L, qb + (L & 3), qm) * r1.e.w;
+      float s2 = l2 + r2.e.z - row_jdot(r2, dvb, dvc, role == L, qb + (L & 3), qm) * r2.e.w;
+      const float n2 = s1 * s1 + s2 * s2;
+      if (n2 > lim_f * lim_f) { const float sc = lim_f * rsqrtf(n2); s1 *= sc; s2 *= sc; }
+      sm.lam[rn + 1][e] = s1; sm.lam[rn + 2][e] = s2;
+      row_axpy(r1, s1 - l1, dvb, dvc);
+      row_axpy(r2, s2 - l2, dvb, dvc);
+    }
+  }
 }
 
 // ---- one substep of dt for the env of this quad.  Joint state / torques live in the link records.
@@ -825,55 +883,8 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
     }
     __syncwarp(qm);
     // ---- projected Gauss-Seidel on the velocity change
-#pragma unroll 1
-    for (int itn = 0; itn < ILRL_SOLVER_ITERS; itn++) {
-      // limits, then contact normals.  The next row (independent of dv) is fetched while this one is applied:
-      // two register buffers used alternately (the loop is unrolled by two so that no copies are needed).
-      const int nfirst = nlim + ncon;
-      auto row_of = [&](int k) { return k < nlim ? k : nlim + 3 * (k - nlim); };
-      auto fetch = [&](int k, RowRegs& rr, int& L, float& lam) {
-        const int r = row_of(k);
-        row_fetch(sm, gscr, e, r, role, rr);
-        L = sm.rowL[r][e]; lam = sm.lam[r][e];
-      };
-      auto apply = [&](int k, const RowRegs& rr, int L, float lam) {
-        const float nl = fmaxf(lam + rr.e.z - row_jdot(rr, dvb, dvc, role == L, qb + (L & 3), qm) * rr.e.w, 0.f);
-        sm.lam[row_of(k)][e] = nl;
-        row_axpy(rr, nl - lam, dvb, dvc);
-      };
-      RowRegs ra, rb;
-      int La = 0, Lb = 0;
-      float lama = 0.f, lamb = 0.f;
-      fetch(0, ra, La, lama);  // nrows > 0 implies nfirst > 0
-#pragma unroll 1
-      for (int k = 0; k < nfirst; k += 2) {
-        if (k + 1 < nfirst) fetch(k + 1, rb, Lb, lamb);
-        apply(k, ra, La, lama);
-        if (k + 1 < nfirst) {
-          if (k + 2 < nfirst) fetch(k + 2, ra, La, lama);
-          apply(k + 1, rb, Lb, lamb);
-        }
-      }
-#pragma unroll 1
-      for (int c = 0; c < ncon; c++) {  // friction pairs, cone re-projected on the current normal impulse
-        const int rn = nlim + 3 * c;
-        const float ln = sm.lam[rn][e];
-        if (!(ln > 0.f)) continue;
-        RowRegs r1, r2;
-        row_fetch(sm, gscr, e, rn + 1, role, r1);
-        row_fetch(sm, gscr, e, rn + 2, role, r2);
-        const int L = sm.rowL[rn][e];
-        const float lim_f = (float)ILRL_FRICTION * ln;
-        const float l1 = sm.lam[rn + 1][e], l2 = sm.lam[rn + 2][e];
-        float s1 = l1 + r1.e.z - row_jdot(r1, dvb, dvc, role == L, qb + (L & 3), qm) * r1.e.w;
-        float s2 = l2 + r2.e.z - row_jdot(r2, dvb, dvc, role == L, qb + (L & 3), qm) * r2.e.w;
-        const float n2 = s1 * s1 + s2 * s2;
-        if (n2 > lim_f * lim_f) { const float sc = lim_f * rsqrtf(n2); s1 *= sc; s2 *= sc; }
-        sm.lam[rn + 1][e] = s1; sm.lam[rn + 2][e] = s2;
-        row_axpy(r1, s1 - l1, dvb, dvc);
-        row_axpy(r2, s2 - l2, dvb, dvc);
-      }
-    }
+    if (nrows <= RSM) pgs_sweeps<false>(sm, gscr, e, role, qb, qm, nlim, ncon, dvb, dvc);
+    else pgs_sweeps<true>(sm, gscr, e, role, qb, qm, nlim, ncon, dvb, dvc);
     __syncwarp(qm);
   }
   // ---- integrate (exponential map on the torso quaternion, as btMultiBody::stepPositionsMultiDof)

@@ -65,7 +65,9 @@ struct BodyC {
   int nsph;
   float sph[2][4];   // centre (body frame), radius
   int sidx[2];       // global sphere index
-  int pad[2];
+  float reach;       // max over the body's spheres of |centre| + radius: no sphere can touch the ground while
+                     // origin_z - reach >= the breaking distance
+  int pad;
 };
 struct Tables {
   LinkC lc[5][4];        // chains 0..3 = limbs (right leg, left leg, right arm, left arm), 4 = spine (3 links)
@@ -74,7 +76,8 @@ struct Tables {
   int sphL[NS], sphC[NS];  // chain (limb 0..3, -1 = spine/torso) and chain index (-1 = torso) carrying sphere g
   int jL[NJ], jC[NJ];      // the same for joint j
   float Q[9];              // fixed rotation of lwaist / pelvis in their parent frame
-  constexpr Tables() : lc(), bc(), sphL(), sphC(), jL(), jC(), Q() {
+  float torso_reach;       // as BodyC::reach, for the 5 torso spheres
+  constexpr Tables() : lc(), bc(), sphL(), sphC(), jL(), jC(), Q(), torso_reach(0.f) {
     constexpr int jb[NJ] = ILRL_JOINT_BODY;
     constexpr double bp[NB * 3] = ILRL_BODY_POS;
     constexpr double bq[NB * 4] = ILRL_BODY_QUAT;
@@ -131,7 +134,7 @@ struct Tables {
         for (int k = 0; k < 2; k++) {
           BodyC& o = bc[q][s][k];
           const int b = body_of[q][s][k];
-          o.nsph = 0; o.m = 0.f; o.ix = o.iy = o.iz = 0.f; o.pad[0] = o.pad[1] = 0;
+          o.nsph = 0; o.m = 0.f; o.ix = o.iy = o.iz = 0.f; o.pad = 0; o.reach = 0.f;
           for (int i = 0; i < 3; i++) o.off[i] = 0.f;
           for (int t = 0; t < 2; t++) { o.sidx[t] = 0; for (int i = 0; i < 4; i++) o.sph[t][i] = 0.f; }
           if (b < 0) continue;
@@ -143,6 +146,11 @@ struct Tables {
               o.sidx[t] = g;
               for (int i = 0; i < 3; i++) o.sph[t][i] = (float)sc[3 * g + i];
               o.sph[t][3] = (float)sr[g];
+              // |c| + r, rounded up (1-norm bound on the centre: no sqrt in a constexpr constructor, and it is safe)
+              double n1 = 0.0;
+              for (int i = 0; i < 3; i++) n1 += sc[3 * g + i] < 0 ? -sc[3 * g + i] : sc[3 * g + i];
+              const float rch = (float)(n1 + sr[g]) * 1.0001f;
+              if (rch > o.reach) o.reach = rch;
             }
         }
     }
@@ -154,6 +162,12 @@ struct Tables {
     }
     for (int g = 0; g < NS; g++) {
       if (sl[g] < 0) { sphL[g] = -1; sphC[g] = -1; } else { sphL[g] = jL[sl[g]]; sphC[g] = jC[sl[g]]; }
+    }
+    for (int g = NS - 5; g < NS; g++) {
+      double n1 = 0.0;
+      for (int i = 0; i < 3; i++) n1 += sc[3 * g + i] < 0 ? -sc[3 * g + i] : sc[3 * g + i];
+      const float rch = (float)(n1 + sr[g]) * 1.0001f;
+      if (rch > torso_reach) torso_reach = rch;
     }
     // kQ from the quaternion of body 1 (bodies 1 and 2 carry the same one)
     const double x = bq[4], y = bq[5], z = bq[6], w = bq[7];
@@ -379,13 +393,18 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
   SV V0; V0.a = rd3(b.w); V0.l = rd3(b.v);
   uint32_t act = 0;
   // torso spheres
+  // (a body whose origin is higher than its reach + the breaking distance cannot have a candidate: skip its spheres)
+  if (FULL && b.p[2] - T.torso_reach < (float)ILRL_CONTACT_BREAK) {
 #pragma unroll 1
-  for (int g = NS - 5; FULL && g < NS; g++) {
-    V3 c = mv(R0, mk(kSphereC[3 * g], kSphereC[3 * g + 1], kSphereC[3 * g + 2]));
-    const float rad = kSphereR[g], d = b.p[2] + c.z - rad;
-    if (d < (float)ILRL_CONTACT_BREAK) act |= 1u << g;
-    float* sp = &sm.sph[g][0][e];
-    sp[0] = c.x; sp[QE] = c.y; sp[2 * QE] = c.z - rad; sp[3 * QE] = d;
+    for (int g = NS - 5; g < NS; g++) {
+      V3 c = mv(R0, mk(kSphereC[3 * g], kSphereC[3 * g + 1], kSphereC[3 * g + 2]));
+      const float rad = kSphereR[g], d = b.p[2] + c.z - rad;
+      if (d < (float)ILRL_CONTACT_BREAK) {
+        act |= 1u << g;
+        float* sp = &sm.sph[g][0][e];
+        sp[0] = c.x; sp[QE] = c.y; sp[2 * QE] = c.z - rad; sp[3 * QE] = d;
+      }
+    }
   }
   float Rc[9];
 #pragma unroll
@@ -448,14 +467,18 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
         if (FULL) rigid_rec(Rc, ob, B.m, B.ix, B.iy, B.iz, Vp, rcd);
         if (c < 3) { ssx += ob.x; ssy += ob.y; } else { sx += ob.x; sy += ob.y; }
         ex = ob.x; ey = ob.y;
+        if (FULL && b.p[2] + ob.z - B.reach < (float)ILRL_CONTACT_BREAK) {
 #pragma unroll 1
-        for (int t = 0; FULL && t < B.nsph; t++) {
-          const int g = B.sidx[t];
-          V3 cs_ = ob + mv(Rc, rd3(B.sph[t]));
-          const float rad = B.sph[t][3], d = b.p[2] + cs_.z - rad;
-          if (d < (float)ILRL_CONTACT_BREAK) act |= 1u << g;
-          float* sp = &sm.sph[g][0][e];
-          sp[0] = cs_.x; sp[QE] = cs_.y; sp[2 * QE] = cs_.z - rad; sp[3 * QE] = d;
+          for (int t = 0; t < B.nsph; t++) {
+            const int g = B.sidx[t];
+            V3 cs_ = ob + mv(Rc, rd3(B.sph[t]));
+            const float rad = B.sph[t][3], d = b.p[2] + cs_.z - rad;
+            if (d < (float)ILRL_CONTACT_BREAK) {
+              act |= 1u << g;
+              float* sp = &sm.sph[g][0][e];
+              sp[0] = cs_.x; sp[QE] = cs_.y; sp[2 * QE] = cs_.z - rad; sp[3 * QE] = d;
+            }
+          }
         }
       }
       if (FULL) {

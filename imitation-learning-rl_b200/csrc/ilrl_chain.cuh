@@ -687,10 +687,12 @@ __device__ __forceinline__ void row_load(P4 rp, int role, RowRegs& r) {
 }
 __device__ __forceinline__ float row_jdot(const RowRegs& r, const float* dvb, const float* dvc, bool mine, int src, unsigned qm) {
   // words: a = RB0..3, b = RB4,5 RS0,1, c = RS2 JS0..2, d = JB0..3, e = JB4,5 rhs dinv
-  float rep = r.d.x * dvb[0] + r.d.y * dvb[1] + r.d.z * dvb[2] + r.d.w * dvb[3] + r.e.x * dvb[4] + r.e.y * dvb[5] +
-              r.c.y * dvc[0] + r.c.z * dvc[1] + r.c.w * dvc[2];
-  float own = mine ? r.jl.x * dvc[3] + r.jl.y * dvc[4] + r.jl.z * dvc[5] + r.jl.w * dvc[6] : 0.f;
-  return rep + __shfl_sync(qm, own, src);
+  // three short chains instead of one 9-deep one: this dot product sits on the Gauss-Seidel critical path
+  const float r0 = fmaf(r.d.z, dvb[2], fmaf(r.d.y, dvb[1], r.d.x * dvb[0]));
+  const float r1 = fmaf(r.e.y, dvb[5], fmaf(r.e.x, dvb[4], r.d.w * dvb[3]));
+  const float r2 = fmaf(r.c.w, dvc[2], fmaf(r.c.z, dvc[1], r.c.y * dvc[0]));
+  const float own = mine ? fmaf(r.jl.y, dvc[4], r.jl.x * dvc[3]) + fmaf(r.jl.w, dvc[6], r.jl.z * dvc[5]) : 0.f;
+  return (r0 + r1) + (r2 + __shfl_sync(qm, own, src));
 }
 __device__ __forceinline__ void row_axpy(const RowRegs& r, float a, float* dvb, float* dvc) {
   dvb[0] += a * r.a.x; dvb[1] += a * r.a.y; dvb[2] += a * r.a.z; dvb[3] += a * r.a.w; dvb[4] += a * r.b.x; dvb[5] += a * r.b.y;

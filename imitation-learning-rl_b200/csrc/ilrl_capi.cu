@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -24,6 +25,8 @@ namespace ilrl {
 constexpr int BLOCK = 64;  // threads per CTA of the thread-per-env service kernels (reset, high step, harness)
 using chain::QE;
 using chain::QT;
+using SmemSmall = chain::SmemT<chain::LayoutSmall>;
+using SmemLarge = chain::SmemT<chain::LayoutLarge>;
 
 struct StepArgs {
   int n;
@@ -84,11 +87,13 @@ __device__ __forceinline__ void store_state(const StepArgs& a, int i, const Phys
   for (int k = 0; k < ILRL_ENV_WORDS; k++) e[k * n] = w.e[k];
 }
 
-// shared-memory setup common to the quad kernels: model tables in, response scratch zeroed
-__device__ __forceinline__ void quad_smem_init(chain::Smem& sm) {
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(&chain::kTables);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.T);
-  {  // all loads of a thread in flight together (the copy is on every CTA's critical path)
+// shared-memory setup common to the quad kernels: model tables in (layouts that stage them)
+template <class SM>
+__device__ __forceinline__ void quad_smem_init(SM& sm) {
+  if constexpr (SM::TSM) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&chain::kTables);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.T);
+    // all loads of a thread in flight together (the copy is on every CTA's critical path)
     constexpr int PER = (chain::TABLE_WORDS + QT - 1) / QT;
     uint32_t v[PER];
 #pragma unroll
@@ -96,16 +101,15 @@ __device__ __forceinline__ void quad_smem_init(chain::Smem& sm) {
 #pragma unroll
     for (int k = 0; k < PER; k++) { const int t = threadIdx.x + k * QT; if (t < chain::TABLE_WORDS) dst[t] = v[k]; }
   }
-  float* z = &sm.su[0][0][0];
-  for (int t = threadIdx.x; t < 3 * chain::NL * QT; t += QT) z[t] = 0.f;
 }
 // torques of this lane's chain into the link records: apply_action (REF humanoid.py:54-60): clip, gear x power,
 // motor slot -> joint.  act: the env's action row in shared memory (null: joint-order torques in `torque`)
-__device__ __forceinline__ void set_torques(chain::Smem& sm, int e, int tid, int role, const float* act, const float* torque) {
+template <class SM>
+__device__ __forceinline__ void set_torques(SM& sm, int e, int tid, int role, const float* act, const float* torque) {
 #pragma unroll
   for (int c = 0; c < chain::NL; c++) {
     float* rec = chain::link_rec(sm, c, e, tid);
-    const chain::LinkC& L = c < 3 ? sm.T.lc[4][c] : sm.T.lc[role][c - 3];
+    const chain::LinkC& L = c < 3 ? chain::tables(sm).lc[4][c] : chain::tables(sm).lc[role][c - 3];
     float t = 0.f;
     if (L.j >= 0) t = act ? L.gear * fminf(fmaxf(act[L.motor], -1.f), 1.f) : torque[L.j];
     rec[chain::W_TAU] = t;
@@ -117,10 +121,10 @@ __device__ __forceinline__ void set_torques(chain::Smem& sm, int e, int tid, int
 // (REF hier_env.py:355-366, 583-642).  Four lanes = one env (ilrl_quad.cuh): the physics substeps run distributed
 // over the quad; the env bookkeeping after them is computed redundantly by the four lanes (identical instruction
 // stream, no divergence) and the outputs are dealt to the lanes for the stores.
-template <int MODE>
+template <int MODE, class SM>
 __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  chain::Smem& sm = *reinterpret_cast<chain::Smem*>(smraw);
+  SM& sm = *reinterpret_cast<SM*>(smraw);
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
   const int base = blockIdx.x * QE;
@@ -129,8 +133,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   quad_smem_init(sm);
   {
     const int cnt = min(QE, a.n - base) * NJ;
-    float* dst = &sm.act[0][0];
-    for (int t = tid; t < cnt; t += QT) dst[t] = a.action[(size_t)base * NJ + t];
+    for (int t = tid; t < cnt; t += QT) sm.act(t / NJ)[t % NJ] = a.action[(size_t)base * NJ + t];
   }
   __syncthreads();
   bool write_obs = false;
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   // skipped envs: hier envs waiting for a high-level action, and rows whose first action component is NaN (the
   // batched adapters' "no action for this env in this call"; the reference asserts finite actions, REF humanoid.py:55)
   const bool pending = valid && ((MODE == 1 && a.envf[(size_t)ILRL_E_HIGH_PENDING * a.n + i] != 0.f) ||
-                                 isnan(sm.act[e][0]));
+                                 isnan(sm.act(e)[0]));
   if (valid && pending) {
     if (role == 0) { a.reward[i] = 0.f; a.done[i] = 0; }
     if (a.terms)
@@ -152,8 +155,8 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     chain::load_links(a.phys, a.n, i, sm, e, tid, role);
     float act[NJ];
 #pragma unroll
-    for (int m = 0; m < NJ; m++) act[m] = sm.act[e][m];
-    set_torques(sm, e, tid, role, sm.act[e], nullptr);
+    for (int m = 0; m < NJ; m++) act[m] = sm.act(e)[m];
+    set_torques(sm, e, tid, role, sm.act(e), nullptr);
     __syncwarp(qm);
     float stale_x = 0.f, stale_y = 0.f;
     float sumx, sumy, rfx, rfy;
@@ -412,9 +415,10 @@ __global__ void clip_ids_kernel(StateView v, const int32_t* ids) {
   if (i >= v.n) return;
   v.envf[(size_t)ILRL_E_CLIP * v.n + i] = ids ? (float)ids[i] : 0.f;
 }
+template <class SM>
 __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const float* torque, float* gscr_all, int nsub) {
   extern __shared__ __align__(16) unsigned char smraw[];
-  chain::Smem& sm = *reinterpret_cast<chain::Smem*>(smraw);
+  SM& sm = *reinterpret_cast<SM*>(smraw);
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
   const int i = blockIdx.x * QE + e;
@@ -494,6 +498,7 @@ struct ilrl_env {
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_terms = nullptr;
   uint8_t* d_done = nullptr;
   int substeps = ILRL_SUBSTEPS;  // harness only (ilrl_debug_substeps)
+  bool large_layout = false;     // shared-memory layout of the step kernel (chosen at create time from N)
   bool no_zero_copy = false;     // harness only (ilrl_debug_zero_copy): force the explicit-copy host path
   int64_t launches = 0;
   bool timing = false;
@@ -551,9 +556,22 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMalloc(&env->envf, sizeof(float) * ILRL_ENV_WORDS * n));
   CKC(cudaMalloc(&env->rng, sizeof(uint32_t) * n));
   CKC(cudaMalloc(&env->gscr, sizeof(float) * (size_t)chain::GROWS * chain::RW * n));
-  CKC(cudaFuncSetAttribute(step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(chain::Smem)));
-  CKC(cudaFuncSetAttribute(step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(chain::Smem)));
-  CKC(cudaFuncSetAttribute(physics_only_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(chain::Smem)));
+  CKC(cudaFuncSetAttribute(step_kernel<0, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
+  CKC(cudaFuncSetAttribute(step_kernel<1, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
+  CKC(cudaFuncSetAttribute(physics_only_kernel<SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
+  CKC(cudaFuncSetAttribute(step_kernel<0, SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
+  CKC(cudaFuncSetAttribute(step_kernel<1, SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
+  CKC(cudaFuncSetAttribute(physics_only_kernel<SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
+  {
+    // Layout: everything on chip for small batches, where the step time is one warp's latency; from about three
+    // waves of CTAs on (measured on B200: 8192 envs 35.3 M/s small vs 32.3 M/s large; 16384: 40.2 vs 42.3; 65536: 44.8
+    // vs 50.8) resident warps per SM limit throughput and the 3-CTAs-per-SM layout wins.
+    // ILRL_LAYOUT=small|large overrides (measurement aid).
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, cfg->device));
+    env->large_layout = (n + QE - 1) / QE >= 6 * prop.multiProcessorCount;
+    if (const char* o = getenv("ILRL_LAYOUT")) env->large_layout = o[0] == 'l' || o[0] == 'L';
+  }
   CKC(cudaMalloc(&env->high_obs, sizeof(float) * 44 * n));
   CKC(cudaMalloc(&env->high_reward, sizeof(float) * n));
   CKC(cudaMalloc(&env->high_flags, n));
@@ -674,8 +692,13 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   cudaStream_t st = (cudaStream_t)stream;
   if (env->timing) CK(cudaEventRecord(env->ev0, st));
   const int qblk = (env->n + QE - 1) / QE;
-  if (env->cfg.mode == 0) step_kernel<0><<<qblk, QT, sizeof(chain::Smem), st>>>(a);
-  else step_kernel<1><<<qblk, QT, sizeof(chain::Smem), st>>>(a);
+  if (env->large_layout) {
+    if (env->cfg.mode == 0) step_kernel<0, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
+    else step_kernel<1, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
+  } else {
+    if (env->cfg.mode == 0) step_kernel<0, SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a);
+    else step_kernel<1, SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a);
+  }
   env->launches++;
   CK(cudaGetLastError());
   if (env->timing) {
@@ -810,7 +833,10 @@ int ilrl_physics_only(ilrl_env* env, const float* torque, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (!torque) return fail(env, ILRL_ERR_ARG, "ilrl_physics_only: null buffer");
   CK(cudaSetDevice(env->cfg.device));
-  physics_only_kernel<<<(env->n + QE - 1) / QE, QT, sizeof(chain::Smem), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);
+  if (env->large_layout)
+    physics_only_kernel<SmemLarge><<<(env->n + QE - 1) / QE, QT, sizeof(SmemLarge), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);
+  else
+    physics_only_kernel<SmemSmall><<<(env->n + QE - 1) / QE, QT, sizeof(SmemSmall), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);
   env->launches++;
   CK(cudaGetLastError());
   return ILRL_OK;

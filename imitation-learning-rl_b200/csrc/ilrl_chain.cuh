@@ -20,6 +20,8 @@
 // Row order, row formulas and constants are exactly those of the oracle (oracle/ilrl_oracle.c) and of the earlier
 // generations (git history): limits in joint order, then contacts in sphere-table order, 5 sweeps.
 #pragma once
+#include <type_traits>
+
 #include "ilrl_env.cuh"
 
 namespace ilrl {
@@ -28,21 +30,16 @@ namespace chain {
 #ifndef ILRL_QE
 #define ILRL_QE 16
 #endif
-#ifndef ILRL_RSM
-#define ILRL_RSM 16
-#endif
 constexpr int QE = ILRL_QE;            // envs per CTA
 constexpr int QT = 4 * QE;             // threads per CTA
 constexpr int NL = 7;                  // chain links per lane: 3 spine + 4 limb slots
-constexpr int RSM = ILRL_RSM;          // constraint rows per env kept in shared memory (the rest: global scratch)
 constexpr int RW = 40;                 // words per stored row
-constexpr int ROWSTRIDE = RSM * RW + 4;  // env stride in words: = 4 (mod 32)
-constexpr int GROWS = MAXROWS - RSM;   // rows per env in the global overflow scratch
+constexpr int GROWS = MAXROWS;         // rows per env in the global overflow scratch (sized for the smallest on-chip budget)
 // link record: 24 words in 6 float4 (S | cJ | U dinv u | q qd tau nu), one contiguous 28-word slot per thread: a
 // 28-word stride puts the float4 of 8 consecutive threads in 8 different bank groups (conflict-free LDS.128 / STS.128)
 enum { W_S = 0, W_CJ = 6, W_U = 12, W_DINV = 18, W_UU = 19, W_Q = 20, W_QD = 21, W_TAU = 22, W_NU = 23, LKW = 28 };
-// body record words: rigid inertia about the reference point (A 6, m*c 3, m 1) + bias force 6; 20-word slots (same reason)
-constexpr int RECW = 16, BRW = 20;
+// body record words: rigid inertia about the reference point (A 6, m*c 3, m 1) + bias force 6
+constexpr int RECW = 16;
 // stored row words
 enum { R_RB = 0 /*resp base 6*/, R_RS = 6 /*resp spine 3*/, R_JS = 9 /*J spine 3*/, R_JB = 12 /*J base 6*/, R_RHS = 18,
        R_DINV = 19, R_RL = 20 /*resp limbs 4x4*/, R_JL = 36 /*J of the row's limb 4*/ };
@@ -181,26 +178,74 @@ __device__ constexpr Tables kTables{};
 constexpr int TABLE_WORDS = sizeof(Tables) / 4;
 static_assert(sizeof(Tables) % 4 == 0, "table copy is word-wise");
 
-// ---- shared memory of one CTA
-struct __align__(16) Smem {
+// ---- shared memory of one CTA, in two layouts chosen by the host from the batch size
+//   LayoutSmall: up to one wave of CTAs at 2 per SM (<= 4736 envs on 148 SMs): everything on chip - 16 rows per env,
+//                padded (conflict-free) body records, model tables in shared memory.  107 KB.
+//   LayoutLarge: larger batches, where resident warps per SM are what limits throughput: 8 rows per env on chip (the
+//                rest in the L2-resident global scratch), unpadded body records, model tables read through L1.
+//                73 KB -> 3 CTAs per SM.
+// In both, the body records (written by the FK phase, consumed by the inward pass) share their storage with what
+// only the row phase uses (response scratch, multipliers, row owners) and with the action tile (consumed before the
+// first substep).
+template <int RSM_, int BRW_, bool TSM_>
+struct Layout {
+  static constexpr int RSM = RSM_;               // constraint rows per env kept in shared memory
+  static constexpr int ROWSTRIDE = RSM_ * RW + 4;  // env stride in words: = 4 (mod 32)
+  static constexpr int BRW = BRW_;               // words per body record (20: room for padding; 16: dense)
+  static constexpr bool TSM = TSM_;              // model tables staged in shared memory
+};
+using LayoutSmall = Layout<16, 20, true>;
+using LayoutLarge = Layout<8, 16, false>;
+
+// Per-env scratch block, seen in two ways that are never live at the same time within an env:
+//   body view (FK phase -> inward pass): body records of the four lanes (2 each, lane stride 40 words) + the spine's 2
+//   row view  (row phase)              : response scratch u[lane][3 impulses][7 links], multipliers, action tile
+//                                        (consumed before the first substep), row owners (bytes)
+// The block is PER ENV because warps of a CTA run unsynchronised: one env's row phase must never touch another env's
+// body records.  Env stride = 4 (mod 32) words and lane stride 40: the float4 accesses of the 2 envs x 4 lanes of a
+// quarter-warp fall in 8 different bank groups, and scalar accesses of the 8 envs of a warp in 8 different banks.
+constexpr int SCR_LANE = 40;                       // lane stride of the body view
+constexpr int SCR_SU = 0, SCR_LAM = 4 * 3 * NL, SCR_ACT = SCR_LAM + MAXROWS, SCR_ROWL = SCR_ACT + NJ;  // row view (words)
+constexpr int SCR_ROWVIEW = SCR_ROWL + (MAXROWS + 3) / 4;
+template <int BRW> constexpr int scr_words() {
+  int w = 4 * SCR_LANE + 2 * BRW;                  // body view
+  if (w < SCR_ROWVIEW) w = SCR_ROWVIEW;
+  while (w % 32 != 4) w++;
+  return w;
+}
+
+struct NoTables {};
+template <class LY>
+struct __align__(16) SmemT {
+  static constexpr int RSM = LY::RSM, ROWSTRIDE = LY::ROWSTRIDE, BRW = LY::BRW, ES = scr_words<LY::BRW>();
+  static constexpr bool TSM = LY::TSM;
+  static_assert(2 * BRW <= SCR_LANE, "two body records per lane");
   // --- float4-accessed arrays first (every size below is a multiple of 16 bytes)
   float rows[QE][ROWSTRIDE];   // stored rows; after the substeps the first 71 words of an env's block stage its obs row
   float lk[4][QT][LKW];        // limb link records, per thread
   float sp[3][QE][LKW];        // spine link records, per env
-  float rl[2][QT][BRW];        // limb body records (slot 0 = A, 1 = B + E)
-  float rs[2][QE][BRW];        // spine body records (slot 0 = lwaist, 1 = pelvis)
+  float scr[QE][ES];           // per-env scratch block (see above)
   // --- scalar-accessed
   float L0[21][QE];            // Cholesky factor of the base articulated inertia
   float sph[NS][4][QE];        // contact candidates: x, y, z - r (relative to the torso origin), distance
-  float lam[MAXROWS][QE];
-  float su[3][NL][QT];         // response scratch: u of the chain links of up to 3 impulses (kept zero between uses)
-  float act[QE][NJ];           // actions (motor order)
-  Tables T;
-  signed char rowL[MAXROWS][QE];  // limb that owns the row's limb block (-1: none)
+  typename std::conditional<TSM, Tables, NoTables>::type T;
+  static_assert((sizeof(float) * QE * ROWSTRIDE) % 16 == 0 && (sizeof(float) * LKW) % 16 == 0 && BRW % 4 == 0 && ES % 4 == 0,
+                "float4 alignment of the shared-memory records");
+  static_assert(ROWSTRIDE >= 71, "the obs row is staged in the env's row block");
+  // body view
+  __device__ __forceinline__ float* rl(int e, int lane, int slot) { return &scr[e][lane * SCR_LANE + slot * BRW]; }
+  __device__ __forceinline__ float* rs(int e, int slot) { return &scr[e][4 * SCR_LANE + slot * BRW]; }
+  // row view
+  __device__ __forceinline__ float* su(int e, int lane, int i) { return &scr[e][SCR_SU + (lane * 3 + i) * NL]; }
+  __device__ __forceinline__ float* lam(int e) { return &scr[e][SCR_LAM]; }
+  __device__ __forceinline__ float* act(int e) { return &scr[e][SCR_ACT]; }
+  __device__ __forceinline__ signed char* rowL(int e) { return reinterpret_cast<signed char*>(&scr[e][SCR_ROWL]); }
 };
-static_assert((sizeof(float) * QE * ROWSTRIDE) % 16 == 0 && (sizeof(float) * LKW) % 16 == 0 && (sizeof(float) * BRW) % 16 == 0,
-              "float4 alignment of the shared-memory records");
-static_assert(ROWSTRIDE >= 71, "the obs row is staged in the env's row block");
+// the model tables as the kernel sees them: the CTA's shared-memory copy, or the global object through L1
+template <class SM>
+__device__ __forceinline__ const Tables& tables(const SM& sm) {
+  if constexpr (SM::TSM) return sm.T; else return kTables;
+}
 
 // replicated floating-base state of one env
 struct Base { float p[3], quat[4], v[3], w[3]; };
@@ -245,11 +290,13 @@ __device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
 }
 
 // link record of chain index c of THIS lane (spine: the env's shared record)
-__device__ __forceinline__ float* link_rec(Smem& sm, int c, int e, int tid) {
+template <class SM>
+__device__ __forceinline__ float* link_rec(SM& sm, int c, int e, int tid) {
   return c < 3 ? &sm.sp[c][e][0] : &sm.lk[c - 3][tid][0];
 }
 // link record of chain index c of limb L of this env (L < 0 or c < 3: spine)
-__device__ __forceinline__ const float* link_rec_of(const Smem& sm, int L, int c, int e, int qb) {
+template <class SM>
+__device__ __forceinline__ const float* link_rec_of(const SM& sm, int L, int c, int e, int qb) {
   return c < 3 ? &sm.sp[c][e][0] : &sm.lk[c - 3][qb + L][0];
 }
 // record field access in whole float4 (word layout: S 0..5 | cJ 6..11 | U 12..17, dinv 18, u 19 | q qd tau nu 20..23)
@@ -385,9 +432,9 @@ __device__ __forceinline__ SV chol6_solve_smem(const float* L, SV b) {
 struct FkOut { uint32_t act; float sx, sy, ssx, ssy, ex, ey; };
 
 // FULL = false: pose only (part-origin sums and the end-body origin), nothing is written to shared memory.
-template <bool FULL>
-__device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid, int role, FkOut& o) {
-  const Tables& T = sm.T;
+template <bool FULL, class SM>
+__device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, int role, FkOut& o) {
+  const Tables& T = tables(sm);
   float R0[9];
   quat2mat(b.quat[0], b.quat[1], b.quat[2], b.quat[3], R0);
   SV V0; V0.a = rd3(b.w); V0.l = rd3(b.v);
@@ -482,7 +529,7 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
         }
       }
       if (FULL) {
-        float4* br = reinterpret_cast<float4*>(c < 3 ? &sm.rs[slot][e][0] : &sm.rl[slot][tid][0]);
+        float4* br = reinterpret_cast<float4*>(c < 3 ? sm.rs(e, slot) : sm.rl(e, role, slot));
 #pragma unroll
         for (int i = 0; i < RECW / 4; i++) br[i] = make_float4(rcd[4 * i], rcd[4 * i + 1], rcd[4 * i + 2], rcd[4 * i + 3]);
       }
@@ -492,7 +539,8 @@ __device__ __forceinline__ void fk_phase(const Base& b, Smem& sm, int e, int tid
 }
 
 // sums of the 31 part offsets (relative to the torso) and the right-foot origin, for calc_state / resetFromFrame
-__device__ __forceinline__ void pose_sums(const Base& b, Smem& sm, int e, int tid, int role, unsigned qm, float& sumx,
+template <class SM>
+__device__ __forceinline__ void pose_sums(const Base& b, SM& sm, int e, int tid, int role, unsigned qm, float& sumx,
                                           float& sumy, float& rfx, float& rfy) {
   FkOut o;
   __syncwarp(qm);
@@ -516,7 +564,8 @@ struct Imp {
 
 // inward walk of one impulse from its link to the base.  Leaves u of the visited links in su (chain-local), writes the
 // row's Jacobian chain entries, returns the force arriving at the base and rv = J . nu (chain part).
-__device__ __forceinline__ SV walk_in(const Smem& sm, const Imp& im, float* su /* stride QT */, int e, int qb, float& rv) {
+template <class SM>
+__device__ __forceinline__ SV walk_in(const SM& sm, const Imp& im, float* su, int e, int qb, float& rv) {
   SV pf = svzero();
   rv = 0.f;
   if (!im.row) return pf;
@@ -526,7 +575,7 @@ __device__ __forceinline__ SV walk_in(const Smem& sm, const Imp& im, float* su /
     SV S, U;
     float di;
     ld_SU(rec, S, U, di);
-    su[c * QT] = im.dir;
+    su[c] = im.dir;
     pf = (im.dir * di) * U;
     rv = im.dir * rec[W_NU];
     im.row[c < 3 ? R_JS + c : R_JL + c - 3] = im.dir;
@@ -542,7 +591,7 @@ __device__ __forceinline__ SV walk_in(const Smem& sm, const Imp& im, float* su /
     float di;
     ld_SU(rec, S, U, di);
     const float u = -sdot(S, pf);
-    su[c * QT] = u;
+    su[c] = u;
     pf = pf + (u * di) * U;
     if (!im.jl) {
       const float Jl = sdot(S, im.F);
@@ -559,14 +608,15 @@ __device__ __forceinline__ float walk_dd(const Imp& im, float* su) {
 #pragma unroll 1
   for (int c = im.c; c >= 0; c--) {
     if (c == 2 && im.L >= 2) break;
-    su[c * QT] = 0.f;
+    su[c] = 0.f;
     dd += c < 3 ? im.row[R_JS + c] * im.row[R_RS + c] : im.row[R_JL + c - 3] * im.row[R_RL + 4 * im.L + c - 3];
   }
   return dd;
 }
 
 // the three impulses of ONE contact share their chain: one walk, link records loaded once, 3-way ILP
-__device__ __forceinline__ void walk_in3(const Smem& sm, const Imp* im, float* su0, float* su1, float* su2, int e, int qb,
+template <class SM>
+__device__ __forceinline__ void walk_in3(const SM& sm, const Imp* im, float* su0, float* su1, float* su2, int e, int qb,
                                          SV* pf, float* rv) {
 #pragma unroll
   for (int i = 0; i < 3; i++) { pf[i] = neg(im[i].F); rv[i] = 0.f; }
@@ -582,7 +632,7 @@ __device__ __forceinline__ void walk_in3(const Smem& sm, const Imp* im, float* s
     const int jw = c < 3 ? R_JS + c : R_JL + c - 3;
     const float u0 = -sdot(S, pf[0]), u1 = -sdot(S, pf[1]), u2 = -sdot(S, pf[2]);
     const float J0 = sdot(S, im[0].F), J1 = sdot(S, im[1].F), J2 = sdot(S, im[2].F);
-    su0[c * QT] = u0; su1[c * QT] = u1; su2[c * QT] = u2;
+    su0[c] = u0; su1[c] = u1; su2[c] = u2;
     pf[0] = pf[0] + (u0 * di) * U; pf[1] = pf[1] + (u1 * di) * U; pf[2] = pf[2] + (u2 * di) * U;
     rv[0] += J0 * nu; rv[1] += J1 * nu; rv[2] += J2 * nu;
     im[0].row[jw] = J0; im[1].row[jw] = J1; im[2].row[jw] = J2;
@@ -590,11 +640,12 @@ __device__ __forceinline__ void walk_in3(const Smem& sm, const Imp* im, float* s
 }
 
 // contact = true: im[0..2] are the normal and the two friction directions of one contact (all rows used, same chain)
-__device__ __forceinline__ void responses3(Smem& sm, Imp* im, const float* nub, int e, int tid, int qb, float idt,
+template <class SM>
+__device__ __forceinline__ void responses3(SM& sm, Imp* im, const float* nub, int e, int tid, int qb, float idt,
                                            const float* pos /* [3] position term of each row */, bool contact) {
-  float* su0 = &sm.su[0][0][tid];
-  float* su1 = &sm.su[1][0][tid];
-  float* su2 = &sm.su[2][0][tid];
+  float* su0 = sm.su(e, tid & 3, 0);
+  float* su1 = sm.su(e, tid & 3, 1);
+  float* su2 = sm.su(e, tid & 3, 2);
   // clear the rows
 #pragma unroll
   for (int i = 0; i < 3; i++)
@@ -638,7 +689,7 @@ __device__ __forceinline__ void responses3(Smem& sm, Imp* im, const float* nub, 
     SV S, U;
     float di;
     ld_SU(&sm.sp[c][e][0], S, U, di);
-    const float u0 = su0[c * QT], u1 = su1[c * QT], u2 = su2[c * QT];
+    const float u0 = su0[c], u1 = su1[c], u2 = su2[c];
     const float q0 = di * (u0 - sdot(ap[0], U)), q1 = di * (u1 - sdot(ap[1], U)), q2 = di * (u2 - sdot(ap[2], U));
     ap[0] = ap[0] + q0 * S; ap[1] = ap[1] + q1 * S; ap[2] = ap[2] + q2 * S;
     if (im[0].row) im[0].row[R_RS + c] = q0;
@@ -657,7 +708,7 @@ __device__ __forceinline__ void responses3(Smem& sm, Imp* im, const float* nub, 
       SV S, U;
       float di;
       ld_SU(&sm.lk[k][qb + r][0], S, U, di);
-      const float u0 = m0 ? su0[(3 + k) * QT] : 0.f, u1 = m1 ? su1[(3 + k) * QT] : 0.f, u2 = m2 ? su2[(3 + k) * QT] : 0.f;
+      const float u0 = m0 ? su0[3 + k] : 0.f, u1 = m1 ? su1[3 + k] : 0.f, u2 = m2 ? su2[3 + k] : 0.f;
       const float q0 = di * (u0 - sdot(ap[0], U)), q1 = di * (u1 - sdot(ap[1], U)), q2 = di * (u2 - sdot(ap[2], U));
       ap[0] = ap[0] + q0 * S; ap[1] = ap[1] + q1 * S; ap[2] = ap[2] + q2 * S;
       if (im[0].row) im[0].row[R_RL + 4 * r + k] = q0;
@@ -701,15 +752,15 @@ __device__ __forceinline__ void row_axpy(const RowRegs& r, float a, float* dvb, 
 }
 // OVER = false: the env has no row beyond the shared-memory budget (the common case): plain shared-memory loads, no
 // predicated-off global loads in the instruction stream (those would take issue slots in every row evaluation).
-template <bool OVER>
-__device__ __forceinline__ void row_fetch(const Smem& sm, const float* gscr, int e, int r, int role, RowRegs& rr) {
-  if (!OVER || r < RSM) row_load(reinterpret_cast<const float4*>(&sm.rows[e][r * RW]), role, rr);
-  else row_load(reinterpret_cast<const float4*>(gscr + (size_t)(r - RSM) * RW), role, rr);
+template <bool OVER, class SM>
+__device__ __forceinline__ void row_fetch(const SM& sm, const float* gscr, int e, int r, int role, RowRegs& rr) {
+  if (!OVER || r < SM::RSM) row_load(reinterpret_cast<const float4*>(&sm.rows[e][r * RW]), role, rr);
+  else row_load(reinterpret_cast<const float4*>(gscr + (size_t)(r - SM::RSM) * RW), role, rr);
 }
 
 // 5 projected-Gauss-Seidel sweeps on the velocity change (dvb: base, dvc: chain) of the env of this quad
-template <bool OVER>
-__device__ __forceinline__ void pgs_sweeps(Smem& sm, const float* gscr, int e, int role, int qb, unsigned qm, int nlim,
+template <bool OVER, class SM>
+__device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int role, int qb, unsigned qm, int nlim,
                                            int ncon, float* dvb, float* dvc) {
 #pragma unroll 1
   for (int itn = 0; itn < ILRL_SOLVER_ITERS; itn++) {
@@ -720,11 +771,11 @@ __device__ __forceinline__ void pgs_sweeps(Smem& sm, const float* gscr, int e, i
     auto fetch = [&](int k, RowRegs& rr, int& L, float& lam) {
       const int r = row_of(k);
       row_fetch<OVER>(sm, gscr, e, r, role, rr);
-      L = sm.rowL[r][e]; lam = sm.lam[r][e];
+      L = sm.rowL(e)[r]; lam = sm.lam(e)[r];
     };
     auto apply = [&](int k, const RowRegs& rr, int L, float lam) {
       const float nl = fmaxf(lam + rr.e.z - row_jdot(rr, dvb, dvc, role == L, qb + (L & 3), qm) * rr.e.w, 0.f);
-      sm.lam[row_of(k)][e] = nl;
+      sm.lam(e)[row_of(k)] = nl;
       row_axpy(rr, nl - lam, dvb, dvc);
     };
     RowRegs ra, rb;
@@ -743,19 +794,19 @@ __device__ __forceinline__ void pgs_sweeps(Smem& sm, const float* gscr, int e, i
 #pragma unroll 1
     for (int c = 0; c < ncon; c++) {  // friction pairs, cone re-projected on the current normal impulse
       const int rn = nlim + 3 * c;
-      const float ln = sm.lam[rn][e];
+      const float ln = sm.lam(e)[rn];
       if (!(ln > 0.f)) continue;
       RowRegs r1, r2;
       row_fetch<OVER>(sm, gscr, e, rn + 1, role, r1);
       row_fetch<OVER>(sm, gscr, e, rn + 2, role, r2);
-      const int L = sm.rowL[rn][e];
+      const int L = sm.rowL(e)[rn];
       const float lim_f = (float)ILRL_FRICTION * ln;
-      const float l1 = sm.lam[rn + 1][e], l2 = sm.lam[rn + 2][e];
+      const float l1 = sm.lam(e)[rn + 1], l2 = sm.lam(e)[rn + 2];
       float s1 = l1 + r1.e.z - row_jdot(r1, dvb, dvc, role == L, qb + (L & 3), qm) * r1.e.w;
       float s2 = l2 + r2.e.z - row_jdot(r2, dvb, dvc, role == L, qb + (L & 3), qm) * r2.e.w;
       const float n2 = s1 * s1 + s2 * s2;
       if (n2 > lim_f * lim_f) { const float sc = lim_f * rsqrtf(n2); s1 *= sc; s2 *= sc; }
-      sm.lam[rn + 1][e] = s1; sm.lam[rn + 2][e] = s2;
+      sm.lam(e)[rn + 1] = s1; sm.lam(e)[rn + 2] = s2;
       row_axpy(r1, s1 - l1, dvb, dvc);
       row_axpy(r2, s2 - l2, dvb, dvc);
     }
@@ -763,9 +814,11 @@ __device__ __forceinline__ void pgs_sweeps(Smem& sm, const float* gscr, int e, i
 }
 
 // ---- one substep of dt for the env of this quad.  Joint state / torques live in the link records.
-__device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, int tid, int role, unsigned qm, float dt) {
+template <class SM>
+__device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int tid, int role, unsigned qm, float dt) {
+  constexpr int RSM = SM::RSM;
   const int qb = tid & ~3;
-  const Tables& T = sm.T;
+  const Tables& T = tables(sm);
   // ---- phase A
   FkOut fo;
   fk_phase<true>(b, sm, e, tid, role, fo);
@@ -787,7 +840,7 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
       float* rec = link_rec(sm, c, e, tid);
       if (c == 1 || c == 2 || c == 5 || c == 6) {
         const int slot = (c == 2 || c == 6) ? 1 : 0;
-        ip_add_rec4(x, c < 3 ? &sm.rs[slot][e][0] : &sm.rl[slot][tid][0]);
+        ip_add_rec4(x, c < 3 ? sm.rs(e, slot) : sm.rl(e, role, slot));
       }
       SV S, cJ;
       ld_ScJ(rec, S, cJ);
@@ -860,6 +913,13 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
   for (int i = 0; i < NL; i++) dvc[i] = 0.f;
   if (nrows > 0) {
     const float idt = 1.0f / dt;
+    // the response scratch shares its storage with the body records of the FK phase: clear this lane's part
+    {
+      float* z = sm.su(e, role, 0);
+#pragma unroll
+      for (int i = 0; i < 3 * NL; i++) z[i] = 0.f;
+    }
+    __syncwarp(qm);
     // ---- build the rows three at a time; items are dealt round-robin to the 4 lanes
     const int nlg = (nlim + 2) / 3;
 #pragma unroll 1
@@ -902,7 +962,7 @@ __device__ __forceinline__ void substep(Base& b, Smem& sm, float* gscr, int e, i
         const int r = r0 + i;
         const bool used = it >= nlg || r < nlim;
         im[i].row = !used ? nullptr : (r < RSM ? &sm.rows[e][r * RW] : gscr + (size_t)(r - RSM) * RW);
-        if (used) { sm.lam[r][e] = 0.f; sm.rowL[r][e] = (signed char)(im[i].c >= 3 ? im[i].L : -1); }
+        if (used) { sm.lam(e)[r] = 0.f; sm.rowL(e)[r] = (signed char)(im[i].c >= 3 ? im[i].L : -1); }
       }
       responses3(sm, im, nub, e, tid, qb, idt, pos, it >= nlg);
     }
@@ -956,18 +1016,20 @@ __device__ __forceinline__ void load_base(const float* phys, int n, int i, Base&
   for (int k = 0; k < 4; k++) b.quat[k] = p[(3 + k) * n];
 }
 // joint state of this lane's chain from HBM into the link records (spine: every lane writes the same values)
-__device__ __forceinline__ void load_links(const float* phys, int n, int i, Smem& sm, int e, int tid, int role) {
+template <class SM>
+__device__ __forceinline__ void load_links(const float* phys, int n, int i, SM& sm, int e, int tid, int role) {
   const float* p = phys + i;
 #pragma unroll
   for (int c = 0; c < NL; c++) {
     float* rec = link_rec(sm, c, e, tid);
-    const int j = c < 3 ? c : sm.T.lc[role][c - 3].j;
+    const int j = c < 3 ? c : tables(sm).lc[role][c - 3].j;
     rec[W_Q] = j >= 0 ? p[(13 + j) * n] : 0.f;
     rec[W_QD] = j >= 0 ? p[(30 + j) * n] : 0.f;
   }
 }
 // link records -> full Phys in every lane
-__device__ __forceinline__ void gather(const Base& b, const Smem& sm, int e, int qb, unsigned qm, Phys& ps) {
+template <class SM>
+__device__ __forceinline__ void gather(const Base& b, const SM& sm, int e, int qb, unsigned qm, Phys& ps) {
   __syncwarp(qm);
 #pragma unroll
   for (int j = 0; j < NJ; j++) {
@@ -983,7 +1045,8 @@ __device__ __forceinline__ void gather(const Base& b, const Smem& sm, int e, int
   for (int k = 0; k < 4; k++) ps.quat[k] = b.quat[k];
 }
 // full (replicated) Phys -> base registers + link records
-__device__ __forceinline__ void scatter(const Phys& ps, Smem& sm, int e, int qb, int role, unsigned qm, Base& b) {
+template <class SM>
+__device__ __forceinline__ void scatter(const Phys& ps, SM& sm, int e, int qb, int role, unsigned qm, Base& b) {
   __syncwarp(qm);
   if (role == 0) {
 #pragma unroll

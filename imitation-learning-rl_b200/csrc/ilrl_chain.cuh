@@ -194,8 +194,13 @@ struct Layout {
   static constexpr int BRW = BRW_;               // words per body record (20: room for padding; 16: dense)
   static constexpr bool TSM = TSM_;              // model tables staged in shared memory
 };
+#ifndef ILRL_LARGE_RSM  // (overridable for layout experiments)
+#define ILRL_LARGE_RSM 8
+#define ILRL_LARGE_BRW 16
+#define ILRL_LARGE_TSM false
+#endif
 using LayoutSmall = Layout<16, 20, true>;
-using LayoutLarge = Layout<8, 16, false>;
+using LayoutLarge = Layout<ILRL_LARGE_RSM, ILRL_LARGE_BRW, ILRL_LARGE_TSM>;
 
 // Per-env scratch block, seen in two ways that are never live at the same time within an env:
 //   body view (FK phase -> inward pass): body records of the four lanes (2 each, lane stride 40 words) + the spine's 2

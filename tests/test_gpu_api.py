@@ -504,3 +504,32 @@ def test_physical_invariants_after_long_rollout():
     # in BOTH this path and the fp64 oracle (tools/diag_limits.py replays the worst cases on the oracle: identical).
     assert worst_viol <= 3.2, worst_viol
     env.close()
+
+
+def test_both_shared_memory_layouts_are_bit_identical(monkeypatch):
+    """The step kernel has two shared-memory layouts picked from the batch size (all on chip / 3 CTAs per SM with rows
+    spilling to the global scratch beyond 8).  They must agree bit for bit, including envs with many rows."""
+    n = 777
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    acts = [(torch.rand(n, 17, device="cuda", generator=g) * 2 - 1) * (3.0 if t % 3 == 0 else 1.0) for t in range(12)]
+    outs = {}
+    for layout in ("small", "large"):
+        monkeypatch.setenv("ILRL_LAYOUT", layout)
+        for mode in ("low", "hier"):
+            clips = ["motion08_03", "motion09_03"]
+            env = BatchedHumanoidEnv(n, mode, clips=clips, clip_of_env=np.arange(n, dtype=np.int32) % 2, seed=5, auto_reset=True)
+            env.reset()
+            rec = []
+            for t, a in enumerate(acts):
+                if mode == "hier":
+                    env.high_step(a[:, :2].contiguous())
+                o, r, d, tm = env.step(a)
+                rec.append((o.clone(), r.clone(), d.clone(), tm.clone()))
+            rec.append(tuple(x.clone() for x in env.get_state()))
+            outs[(layout, mode)] = rec
+            env.close()
+    for mode in ("low", "hier"):
+        for x, y in zip(outs[("small", mode)], outs[("large", mode)]):
+            for u, v in zip(x, y):
+                assert torch.equal(u, v), mode

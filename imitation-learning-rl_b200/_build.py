@@ -8,8 +8,11 @@ SRC = os.path.join(HERE, "csrc", "ilrl_capi.cu")
 DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("ilrl_env.cuh", "ilrl_chain.cuh", "ilrl_physics.cuh", "ilrl_constants.h",
                                                         "ilrl_model_data.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "ilrl.h")]
-NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-              "-shared"]
+# -ftz / -prec-div=false / -prec-sqrt=false: flush denormals, 2-ulp division and square root without their slow-path
+# subroutines (+4..5 % throughput).  NOT --use_fast_math: sincosf / expf / atan2f keep full accuracy (the reward and
+# observation parity bar is 1e-5 relative; the whole GPU suite passes with these flags).
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-ftz=true",
+              "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-shared"]
 
 
 def stale():

@@ -55,6 +55,8 @@ struct LinkC {
   int motor;      // action slot that drives the joint (humanoid.py:28-37), -1 = none
   int rot;        // 1: the body that starts here carries the fixed rotation kQ
   int nbody;      // rigid bodies completed by this link
+  int pad[2];     // 18 words: a chain of 4 is 72 words = 8 (mod 32), so the four roles of a quad - which read the same
+                  // field of four different chains in one instruction - hit four different banks
 };
 struct BodyC {
   float off[3];      // body origin relative to the link's body origin (0, or the fixed child's position)
@@ -64,7 +66,7 @@ struct BodyC {
   int sidx[2];       // global sphere index
   float reach;       // max over the body's spheres of |centre| + radius: no sphere can touch the ground while
                      // origin_z - reach >= the breaking distance
-  int pad;
+  int pad[3];        // 22 words: a chain's 4 records are 88 words = 24 (mod 32) (bank spread over the roles, as LinkC)
 };
 struct Tables {
   LinkC lc[5][4];        // chains 0..3 = limbs (right leg, left leg, right arm, left arm), 4 = spine (3 links)
@@ -99,7 +101,7 @@ struct Tables {
         int j = -1;
         if (q < 4) { const int lead = 4 - count[q]; j = k < lead ? -1 : first[q] + (k - lead); }
         else if (k < 3) j = k;
-        o.j = j; o.motor = -1; o.gear = 0.f; o.rot = 0; o.nbody = 0;
+        o.j = j; o.motor = -1; o.gear = 0.f; o.rot = 0; o.nbody = 0; o.pad[0] = o.pad[1] = 0;
         o.lo = -1e30f; o.hi = 1e30f;
         for (int i = 0; i < 3; i++) { o.pre[i] = 0.f; o.an[i] = 0.f; o.ax[i] = 0.f; }
         if (q == 4 && k == 3) continue;
@@ -131,7 +133,7 @@ struct Tables {
         for (int k = 0; k < 2; k++) {
           BodyC& o = bc[q][s][k];
           const int b = body_of[q][s][k];
-          o.nsph = 0; o.m = 0.f; o.ix = o.iy = o.iz = 0.f; o.pad = 0; o.reach = 0.f;
+          o.nsph = 0; o.m = 0.f; o.ix = o.iy = o.iz = 0.f; o.pad[0] = o.pad[1] = o.pad[2] = 0; o.reach = 0.f;
           for (int i = 0; i < 3; i++) o.off[i] = 0.f;
           for (int t = 0; t < 2; t++) { o.sidx[t] = 0; for (int i = 0; i < 4; i++) o.sph[t][i] = 0.f; }
           if (b < 0) continue;

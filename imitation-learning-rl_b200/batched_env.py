@@ -72,6 +72,7 @@ class BatchedHumanoidEnv:
             self.high_reward = torch.zeros(n, device=dev)
             self.high_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._forced = None
+        self._host_key = None
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):
@@ -123,11 +124,23 @@ class BatchedHumanoidEnv:
 
     def step_host(self, action_np, obs_np, reward_np, done_np, terms_np=None):
         """Same step through host (numpy) buffers: H2D of the actions, kernel, D2H of obs/reward/done, synchronous."""
-        assert action_np.dtype == np.float32 and action_np.flags.c_contiguous
-        assert obs_np.dtype == np.float32 and reward_np.dtype == np.float32 and done_np.dtype == np.uint8
-        ptr = lambda a: a.__array_interface__["data"][0]  # noqa: E731  (cheaper than ndarray.ctypes)
-        self._ck(self.L.ilrl_step_host(self.h, ptr(action_np), ptr(obs_np), ptr(reward_np), ptr(done_np),
-                                       None if terms_np is None else ptr(terms_np), self._stream()))
+        # the argument tuple of the previous call is reused while the same buffers come back (the usual loop): dtype /
+        # layout checks and pointer extraction cost more Python time than the ctypes call itself
+        key = (id(action_np), id(obs_np), id(reward_np), id(done_np), id(terms_np))
+        if self._host_key != key:
+            assert action_np.dtype == np.float32 and action_np.flags.c_contiguous and action_np.shape == (self.num_envs, ACT_LOW)
+            assert obs_np.dtype == np.float32 and obs_np.flags.c_contiguous and obs_np.shape == (self.num_envs, OBS_LOW)
+            assert reward_np.dtype == np.float32 and done_np.dtype == np.uint8
+            assert reward_np.shape == (self.num_envs,) and done_np.shape == (self.num_envs,)
+            assert terms_np is None or (terms_np.dtype == np.float32 and terms_np.shape == (self.num_envs, TERM_WORDS))
+            ptr = lambda a: a.__array_interface__["data"][0]  # noqa: E731  (cheaper than ndarray.ctypes)
+            self._host_args = (ptr(action_np), ptr(obs_np), ptr(reward_np), ptr(done_np),
+                               None if terms_np is None else ptr(terms_np))
+            self._host_refs = (action_np, obs_np, reward_np, done_np, terms_np)  # keep the ids valid
+            self._host_key = key
+        rc = self.L.ilrl_step_host(self.h, *self._host_args, self._stream())
+        if rc != 0:
+            self._ck(rc)
 
     def high_step(self, action2):
         """hier mode: heading action [N,2] for the envs waiting for one; returns the low-level obs tensor [N,70]

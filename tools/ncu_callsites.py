@@ -16,7 +16,7 @@ inside, chain, fresh = False, [], True
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0])
 for ln in open(dis):
     if ln.startswith("//---") and ".text." in ln:
-        inside = kern in ln
+        inside = all(k in ln for k in kern.split(","))
         continue
     if not inside:
         continue

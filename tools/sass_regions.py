@@ -8,7 +8,7 @@ cnt = collections.Counter()
 total = 0
 for ln in open(path):
     if ln.startswith("//---") and ".text." in ln:
-        inside = kern in ln
+        inside = all(k in ln for k in kern.split(","))
         continue
     if not inside:
         continue

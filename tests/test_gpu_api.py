@@ -533,3 +533,34 @@ def test_both_shared_memory_layouts_are_bit_identical(monkeypatch):
         for x, y in zip(outs[("small", mode)], outs[("large", mode)]):
             for u, v in zip(x, y):
                 assert torch.equal(u, v), mode
+
+
+def test_reference_evaluation_loop_runs_unchanged():
+    """The loop of REF env_check.py:104-166 (predefined target chain, resetFromFrame(0, 0, True, True),
+    step(action, debug=True), drift from robot_pos / starting_robot_pos / target, cur_timestep) on the N = 1 class."""
+    from scipy.spatial.transform import Rotation as R
+
+    def calc_drift(p, a, b):          # distance of p to the segment a-b (REF math_util.py:20-31)
+        ab, ap = b - a, p - a
+        t = np.clip(np.dot(ap, ab) / np.dot(ab, ab), 0.0, 1.0)
+        return float(np.linalg.norm(a + t * ab - p))
+
+    env = LowLevelHumanoidEnv(reference_name="motion09_03", useCustomEnv=False, customRobot=None, seed=1)
+    env.usePredefinedTarget = True
+    temp, target = np.array([0.0, 0.0, 0.0]), []
+    for i in range(100):
+        temp = temp + R.from_euler("z", 30 * i, degrees=True).apply(np.array([0.0, 1.0, 0.0]) * 5)
+        target.append(temp)
+    env.predefinedTarget = np.array(target).copy()
+    rng = np.random.default_rng(0)
+    for episode in range(2):
+        obs = env.resetFromFrame(startFrame=0, resetYaw=0, startFromRef=True, initVel=True)
+        np.testing.assert_allclose(env.target, target[0], atol=1e-5)
+        done, drift = False, []
+        while not done:
+            obs, reward, done, info = env.step(rng.uniform(-0.2, 0.2, 17), debug=True)
+            drift.append(calc_drift(env.robot_pos, env.starting_robot_pos, env.target))
+            # debug=True: the episode ends only when the robot is down (or at max_timestep), REF low_level_env.py:467-473
+            assert done == (env.aliveReward <= 0 or env.cur_timestep >= env.max_timestep)
+        assert 1 <= env.cur_timestep <= env.max_timestep and np.isfinite(drift).all()
+    env.close()

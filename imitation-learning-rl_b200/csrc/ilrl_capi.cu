@@ -131,9 +131,11 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   const int i = base + e;
   const bool valid = i < a.n;
   quad_smem_init(sm);
-  {
-    const int cnt = min(QE, a.n - base) * NJ;
-    for (int t = tid; t < cnt; t += QT) sm.act(t / NJ)[t % NJ] = a.action[(size_t)base * NJ + t];
+  if (valid) {  // the quad stages its env's action row (the 8 rows of a warp are one contiguous 544-byte block)
+    const float* arow = a.action + (size_t)i * NJ;
+    float* dst = sm.act(e);
+#pragma unroll
+    for (int m = role; m < NJ; m += 4) dst[m] = arow[m];
   }
   __syncthreads();
   bool write_obs = false;

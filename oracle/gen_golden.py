@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 from oracle import oracle as O  # noqa: E402
 from oracle import ref_shim as S  # noqa: E402
 
-OUT = os.path.join(ROOT, "tests", "golden")
+OUT = os.environ.get("ILRL_GOLDEN_OUT") or os.path.join(ROOT, "tests", "golden")  # (the reproducibility test writes elsewhere)
 os.makedirs(OUT, exist_ok=True)
 CLIPS = O.CLIPS
 LO, HI = np.array(S.MODEL["joint_lo"]), np.array(S.MODEL["joint_hi"])

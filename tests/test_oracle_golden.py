@@ -182,3 +182,27 @@ def test_notebook_vectors():
     _, xyz, _, _, _ = O.calc_state(p, 0.0, 0.0)
     bo, ao, _ = O.fk(p)
     np.testing.assert_allclose(xyz[:2], (bo[:, :2].sum(0) + ao[:, :2].sum(0)) / 33.0, atol=1e-12)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference checkout exists only in the build container")
+def test_golden_fixtures_regenerate_bit_identically_from_the_reference(tmp_path):
+    """The committed fixtures ARE what the unmodified reference Python produces: oracle/gen_golden.py (which imports
+    /root/reference through oracle/ref_shim.py) is re-run into a scratch directory and every array compared bit for bit.
+    Runs only where the reference is mounted (never on the GPU box)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ILRL_GOLDEN_OUT=str(tmp_path))
+    subprocess.check_call([sys.executable, os.path.join(root, "oracle", "gen_golden.py")], env=env,
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    gold = os.path.join(root, "tests", "golden")
+    names = sorted(f for f in os.listdir(gold))
+    assert sorted(os.listdir(str(tmp_path))) == names
+    for f in names:
+        if f.endswith(".npz"):
+            with np.load(os.path.join(gold, f)) as a, np.load(os.path.join(str(tmp_path), f)) as b:
+                assert sorted(a.files) == sorted(b.files), f
+                for k in a.files:
+                    assert np.array_equal(a[k], b[k]), (f, k)
+        else:
+            assert open(os.path.join(gold, f)).read() == open(os.path.join(str(tmp_path), f)).read(), f

@@ -49,6 +49,8 @@ struct StepArgs {
   const int32_t* forced_deg;  // [n] or null
   float* stats;        // [16] or null
   float* gscr;         // [n][GROWS][RW] overflow scratch for constraint rows beyond the shared-memory budget
+  unsigned int* tile_counter;  // [2]: next tile to hand out, CTAs that have left (both zero between launches)
+  int ntiles;
   ClipDesc clips[MAX_CLIPS];
 };
 
@@ -127,10 +129,19 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   SM& sm = *reinterpret_cast<SM*>(smraw);
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
-  const int base = blockIdx.x * QE;
+  quad_smem_init(sm);
+  // Persistent CTAs: the grid is at most what is resident at once (SMs x CTAs per SM) and tiles of QE envs are handed
+  // out through an atomic counter, so a large batch has no partially filled last wave and no per-tile table copy, and
+  // CTAs that drew cheap tiles simply take more of them.  The last CTA to leave resets the counters (graph-safe).
+  __shared__ int s_tile;
+  for (;;) {
+  if (tid == 0) s_tile = (int)atomicAdd(a.tile_counter, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile >= a.ntiles) break;
+  const int base = tile * QE;
   const int i = base + e;
   const bool valid = i < a.n;
-  quad_smem_init(sm);
   if (valid) {  // the quad stages its env's action row (the 8 rows of a warp are one contiguous 544-byte block)
     const float* arow = a.action + (size_t)i * NJ;
     float* dst = sm.act(e);
@@ -307,6 +318,12 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
       for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
       if ((tid & 31) == 0 && x != 0.f) atomicAdd(a.stats + t, x);
     }
+  }
+  __syncthreads();  // every warp is done with this tile's shared memory (and with s_tile) before the next one
+  }  // tile loop
+  if (tid == 0 && atomicAdd(a.tile_counter + 1, 1u) == gridDim.x - 1) {  // last CTA out: ready for the next launch
+    a.tile_counter[0] = 0u;
+    a.tile_counter[1] = 0u;
   }
 }
 
@@ -490,6 +507,8 @@ struct ilrl_env {
   float* high_reward = nullptr;
   uint8_t* high_flags = nullptr;
   float* stats = nullptr;
+  unsigned int* tile_counter = nullptr;
+  int grid_small = 0, grid_large = 0;  // resident CTAs of the step kernel in each layout
   float* clip_mem[MAX_CLIPS] = {nullptr};
   ClipDesc clips[MAX_CLIPS];
   bool clip_loaded[MAX_CLIPS] = {false};
@@ -573,11 +592,24 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
     env->large_layout = (n + QE - 1) / QE >= 6 * prop.multiProcessorCount;
     if (const char* o = getenv("ILRL_LAYOUT")) env->large_layout = o[0] == 'l' || o[0] == 'L';
+    int occ_s = 0, occ_l = 0;
+    if (cfg->mode == 0) {
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, step_kernel<0, SmemSmall>, QT, sizeof(SmemSmall)));
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, step_kernel<0, SmemLarge>, QT, sizeof(SmemLarge)));
+    } else {
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, step_kernel<1, SmemSmall>, QT, sizeof(SmemSmall)));
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, step_kernel<1, SmemLarge>, QT, sizeof(SmemLarge)));
+    }
+    if (occ_s < 1 || occ_l < 1) { g_create_err = "step kernel does not fit on this device"; ilrl_destroy(env); return ILRL_ERR_CUDA; }
+    env->grid_small = occ_s * prop.multiProcessorCount;
+    env->grid_large = occ_l * prop.multiProcessorCount;
   }
   CKC(cudaMalloc(&env->high_obs, sizeof(float) * 44 * n));
   CKC(cudaMalloc(&env->high_reward, sizeof(float) * n));
   CKC(cudaMalloc(&env->high_flags, n));
   CKC(cudaMalloc(&env->stats, sizeof(float) * ILRL_STATS_WORDS));
+  CKC(cudaMalloc(&env->tile_counter, 2 * sizeof(unsigned int)));
+  CKC(cudaMemset(env->tile_counter, 0, 2 * sizeof(unsigned int)));
   CKC(cudaMemset(env->phys, 0, sizeof(float) * ILRL_PHYS_WORDS * n));
   CKC(cudaMemset(env->envf, 0, sizeof(float) * ILRL_ENV_WORDS * n));
   CKC(cudaMemset(env->rng, 0, sizeof(uint32_t) * n));
@@ -597,7 +629,7 @@ void ilrl_destroy(ilrl_env* env) {
   cudaSetDevice(env->cfg.device);
   cudaDeviceSynchronize();
   cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr);
-  cudaFree(env->high_obs); cudaFree(env->high_reward); cudaFree(env->high_flags); cudaFree(env->stats);
+  cudaFree(env->high_obs); cudaFree(env->high_reward); cudaFree(env->high_flags); cudaFree(env->stats); cudaFree(env->tile_counter);
   for (int c = 0; c < MAX_CLIPS; c++) cudaFree(env->clip_mem[c]);
   cudaFreeHost(env->h_action); cudaFreeHost(env->h_obs); cudaFreeHost(env->h_reward); cudaFreeHost(env->h_terms);
   cudaFreeHost(env->h_done);
@@ -689,11 +721,12 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
   a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.terms = terms;
   a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
-  a.forced_deg = env->forced_deg; a.stats = env->stats; a.gscr = env->gscr;
+  a.forced_deg = env->forced_deg; a.stats = env->stats; a.gscr = env->gscr; a.tile_counter = env->tile_counter;
   memcpy(a.clips, env->clips, sizeof a.clips);
   cudaStream_t st = (cudaStream_t)stream;
   if (env->timing) CK(cudaEventRecord(env->ev0, st));
-  const int qblk = (env->n + QE - 1) / QE;
+  a.ntiles = (env->n + QE - 1) / QE;
+  const int qblk = min(a.ntiles, env->large_layout ? env->grid_large : env->grid_small);
   if (env->large_layout) {
     if (env->cfg.mode == 0) step_kernel<0, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
     else step_kernel<1, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);

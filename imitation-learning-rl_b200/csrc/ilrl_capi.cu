@@ -584,13 +584,14 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaFuncSetAttribute(step_kernel<1, SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(physics_only_kernel<SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   {
-    // Layout: everything on chip for small batches, where the step time is one warp's latency; from about three
-    // waves of CTAs on (measured on B200: 8192 envs 35.3 M/s small vs 32.3 M/s large; 16384: 40.2 vs 42.3; 65536: 44.8
-    // vs 50.8) resident warps per SM limit throughput and the 3-CTAs-per-SM layout wins.
+    // Layout.  With persistent CTAs a step takes about ceil(tiles / resident CTAs) tile times,
+    // and a tile of the dense layout takes ~1.19x a tile of the all-on-chip one (measured on B200 at one wave: 25.8 vs
+    // 30.6 M env-steps/s): pick whichever estimate is smaller.  E.g. 4096 envs (256 tiles) -> on chip; 6144 (384) ->
+    // dense, one wave instead of two; 8192 (512) -> on chip; from 9488 envs on -> dense.  Measured pairs (M env-steps/s,
+    // on-chip vs dense): 6144: 30.7 / 35.8; 8192: 38.7 / 34.3; 12288: 41.1 / 43.9; 16384: 43.0 / 45.2; 32768: 48.7 / 52.0.
     // ILRL_LAYOUT=small|large overrides (measurement aid).
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
-    env->large_layout = (n + QE - 1) / QE >= 6 * prop.multiProcessorCount;
     if (const char* o = getenv("ILRL_LAYOUT")) env->large_layout = o[0] == 'l' || o[0] == 'L';
     int occ_s = 0, occ_l = 0;
     if (cfg->mode == 0) {
@@ -603,6 +604,11 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
     if (occ_s < 1 || occ_l < 1) { g_create_err = "step kernel does not fit on this device"; ilrl_destroy(env); return ILRL_ERR_CUDA; }
     env->grid_small = occ_s * prop.multiProcessorCount;
     env->grid_large = occ_l * prop.multiProcessorCount;
+    if (!getenv("ILRL_LAYOUT")) {
+      const int tiles = (n + QE - 1) / QE;
+      const int rounds_s = (tiles + env->grid_small - 1) / env->grid_small, rounds_l = (tiles + env->grid_large - 1) / env->grid_large;
+      env->large_layout = 1.19f * (float)rounds_l < (float)rounds_s;
+    }
   }
   CKC(cudaMalloc(&env->high_obs, sizeof(float) * 44 * n));
   CKC(cudaMalloc(&env->high_reward, sizeof(float) * n));

@@ -184,6 +184,62 @@ class _SingleEnv(object):
             self._push_env_words(**words)
             self.target = np.array([new[0], new[1], 0.0])
 
+    # ---- the reference's individual score methods, callable at any time on the current state (param_check.py calls
+    # calcEndPointScore / calcJointScore between steps, REF param_check.py:43-60).  They are evaluated by the same
+    # kernel as a step: the env state is saved, one step with the physics skipped runs, the terms are read, and the
+    # state is put back.
+    def _peek_terms(self, action=None):
+        phys, envf = self._env.get_state()
+        tmp = envf.clone()
+        tmp[:, B.E_HIGH_PENDING] = 0.0
+        self._env.set_state(None, tmp)
+        self._env.set_forced_target_deg(np.array([0], np.int64))     # no draw is consumed by the peek
+        a = np.zeros((1, 17), np.float32) if action is None else np.asarray(action, np.float32).reshape(1, 17)
+        _, _, _, terms = self._env.step(a, physics=False)
+        t = terms[0].cpu().numpy().astype(np.float64)
+        self._env.set_state(phys, envf)
+        return t
+
+    def calcJointScore(self, useExp=False):          # REF low_level_env.py:325-341
+        v = self._peek_terms()[0]
+        return float(v) if useExp else float(np.log(max(v, 1e-300)) / 4.0)
+
+    def calcJointVelScore(self, useExp=False):       # REF low_level_env.py:343-359
+        v = self._peek_terms()[1]
+        return float(v) if useExp else float(2.0 * np.log(max(v, 1e-300)))
+
+    def calcBodyPostureScore(self, useExp=False):    # REF low_level_env.py:405-410
+        v = self._peek_terms()[6]
+        return float(v) if useExp else float(np.log(max(v, 1e-300)))
+
+    def calcAliveReward(self):                       # REF low_level_env.py:384-387
+        return float(self._peek_terms()[5])
+
+    def calcJointLimitCost(self):                    # REF low_level_env.py:396-397
+        return float(self._peek_terms()[4])
+
+    def calcElectricityCost(self, action):           # REF low_level_env.py:389-394
+        return float(self._peek_terms(action)[3])
+
+    def calcEndPointScore(self, useExp=False):       # REF low_level_env.py:361-382
+        s = float(self._env.endpoint_score()[0].item())
+        return s if useExp else float(np.log(max(s, 1e-300)) / 3.0)
+
+    def setJointsOrientation(self, idx):             # REF low_level_env.py:205-216
+        """Joint positions / velocities of reference frame `idx` (the three abdomen joints zero), base untouched."""
+        name = self.reference_name if hasattr(self, "reference_name") else self.motion_list[self.selected_motion]
+        c = load_clip(name)
+        phys, _ = self._env.get_state()
+        p = phys[0].cpu().numpy()
+        p[13:30] = 0.0
+        p[30:47] = 0.0
+        joints = [6, 3, 5, 4, 10, 7, 9, 8, 12, 11, 13, 15, 14, 16]      # joint_map order -> joint slot
+        cols = [3, 0, 1, 2, 7, 4, 5, 6, 8, 9, 10, 11, 12, 13]           # joint_map order -> CSV column
+        for j, col in zip(joints, cols):
+            p[13 + j] = c["pos"][idx, col]
+            p[30 + j] = c["vel"][idx, col]
+        self._env.set_state(p[None, :], None)
+
     def _first_target_xy(self):
         if self.usePredefinedTarget:
             self.predefinedTargetIndex = 0
@@ -261,9 +317,6 @@ class LowLevelHumanoidEnv(_SingleEnv, _GymEnv):
         cols = [3, 0, 1, 2, 7, 4, 5, 6, 8, 9, 10, 11, 12, 13]  # joint_map order -> CSV column
         return np.stack([c["rel"][frame, cols], c["vel"][frame, cols]], 1).reshape(-1).astype(np.float64)
 
-    def calcEndPointScore(self, useExp=False):
-        s = float(self._env.endpoint_score()[0].item())
-        return s if useExp else float(np.log(s) / 3.0)
 
 
 class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):

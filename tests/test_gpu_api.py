@@ -564,3 +564,36 @@ def test_reference_evaluation_loop_runs_unchanged():
             assert done == (env.aliveReward <= 0 or env.cur_timestep >= env.max_timestep)
         assert 1 <= env.cur_timestep <= env.max_timestep and np.isfinite(drift).all()
     env.close()
+
+
+def test_individual_score_methods_match_oracle_and_leave_the_state_alone():
+    """calcJointScore / calcJointVelScore / calcEndPointScore / ... as param_check.py uses them (REF param_check.py:43-60):
+    values against the oracle's terms on the same state; the env state is unchanged by the calls."""
+    env = LowLevelHumanoidEnv(reference_name="motion09_03", seed=2)
+    env.resetFromFrame(10)
+    for t in range(3):
+        env.step(np.random.default_rng(t).uniform(-1, 1, 17))
+    for f in (4, 33, 60):
+        env.setJointsOrientation(f)
+        before = [x.clone() for x in env._env.get_state()]
+        v = _oracle_from(env, "motion09_03", 0)
+        a = np.linspace(-1.5, 1.5, 17)
+        js, jv, ep = env.calcJointScore(useExp=True), env.calcJointVelScore(useExp=True), env.calcEndPointScore(useExp=True)
+        post, alive, lim, el = env.calcBodyPostureScore(useExp=True), env.calcAliveReward(), env.calcJointLimitCost(), \
+            env.calcElectricityCost(a)
+        after = env._env.get_state()
+        assert torch.equal(before[0], after[0]) and torch.equal(before[1], after[1])
+        want_ep = v.endpoint_score()
+        v.low_step(a.astype(np.float32).astype(np.float64), skip_physics=True)
+        terms = v.get()[2]
+        np.testing.assert_allclose([js, jv, el, lim, alive, post], [terms[0], terms[1], terms[3], terms[4], terms[5], terms[6]],
+                                   rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(ep, want_ep, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(env.calcJointScore(), np.log(js) / 4, rtol=1e-6)
+        np.testing.assert_allclose(env.calcEndPointScore(), np.log(ep) / 3, rtol=1e-6)
+        # joint pose is the clip's frame f (joint_map order), abdomen zero
+        p = after[0][0].cpu().numpy()
+        c = ilrl_b200.load_clip("motion09_03")
+        np.testing.assert_allclose(p[13 + 6], c["pos"][f, 3], atol=1e-7)      # right_knee <- rightKnee column
+        assert (p[13:16] == 0).all()
+    env.close()

@@ -62,6 +62,16 @@ JOINT_MAP = {
     "right_shoulder_x": "rightShoulderX", "right_shoulder_y": "rightShoulderY", "right_elbow": "rightElbow",
     "left_shoulder_x": "leftShoulderX", "left_shoulder_y": "leftShoulderY", "left_elbow": "leftElbow",
 }
+JOINT_COLS = ["rightHipX", "rightHipY", "rightHipZ", "rightKnee", "leftHipX", "leftHipY", "leftHipZ", "leftKnee",
+              "rightShoulderX", "rightShoulderY", "rightElbow", "leftShoulderX", "leftShoulderY", "leftElbow"]
+EP_COLS = ["%s_%sposition" % (b, a) for b in ("LeftLeg", "LeftFoot", "RightLeg", "RightFoot", "Head", "LeftForeArm",
+                                                "LeftHand", "RightForeArm", "RightHand") for a in "XYZ"]
+JOINT_WEIGHT = {"right_knee": 3, "right_hip_x": 1, "right_hip_y": 3, "right_hip_z": 1, "left_knee": 3, "left_hip_x": 1,
+                "left_hip_y": 3, "left_hip_z": 1, "right_shoulder_x": 0.1, "right_shoulder_y": 0.3, "right_elbow": 0.3,
+                "left_shoulder_x": 0.1, "left_shoulder_y": 0.3, "left_elbow": 0.3}        # REF low_level_env.py:103-119
+JOINT_VEL_WEIGHT = {k: (1 if ("knee" in k or "hip" in k) else 0.1) for k in JOINT_WEIGHT}  # REF low_level_env.py:121-137
+END_POINT_MAP = {"link0_11": "RightLeg", "right_foot": "RightFoot", "link0_18": "LeftLeg", "left_foot": "LeftFoot"}
+END_POINT_WEIGHT = {"link0_11": 1, "right_foot": 3, "link0_18": 1, "left_foot": 3}         # REF low_level_env.py:139-152
 _REWARD_ATTRS = dict(deltaJoints=0, deltaVelJoints=1, delta_lowTargetScore=2, electricityScore=3, jointLimitScore=4,
                      aliveReward=5, bodyPostureScore=6, lowTargetScore=7, deltaEndPoints=8, highTargetScore=9,
                      driftScore=10, delta_highTargetScore=11)
@@ -80,6 +90,11 @@ class _SingleEnv(object):
         self.max_timestep = 3000
         self.frame = 0
         self.joint_map = dict(JOINT_MAP)
+        self.joint_weight, self.joint_vel_weight = dict(JOINT_WEIGHT), dict(JOINT_VEL_WEIGHT)
+        self.joint_weight_sum = sum(self.joint_weight.values())
+        self.joint_vel_weight_sum = sum(self.joint_vel_weight.values())
+        self.end_point_map, self.end_point_weight = dict(END_POINT_MAP), dict(END_POINT_WEIGHT)
+        self.end_point_weight_sum = sum(self.end_point_weight.values())
         self.target = np.array([1.0, 0.0, 0.0])
         self.targetLen = 5
         self.highLevelDegTarget = 0.0
@@ -109,6 +124,28 @@ class _SingleEnv(object):
 
     def close(self):
         self._env.close()
+
+    # the four reference tables as pandas DataFrames with the CSV's own column names (REF low_level_env.py:58-71 reads
+    # them with pd.read_csv; drivers index them with .iloc[frame][column]).  Built on first use.
+    def _frames(self, name):
+        import pandas as pd
+        c = load_clip(name)
+        return (pd.DataFrame(c["pos"].astype(np.float64), columns=JOINT_COLS),
+                pd.DataFrame(c["vel"].astype(np.float64), columns=JOINT_COLS),
+                pd.DataFrame(c["rel"].astype(np.float64), columns=JOINT_COLS),
+                pd.DataFrame(c["ep"].astype(np.float64), columns=EP_COLS))
+
+    def _table(self, k):
+        if getattr(self, "_df", None) is None:
+            names = [self.reference_name] if hasattr(self, "reference_name") else self.motion_list
+            self._df = [self._frames(n) for n in names]
+        t = [d[k] for d in self._df]
+        return t[0] if hasattr(self, "reference_name") else t   # a list per motion in the hierarchical env
+
+    joints_df = property(lambda self: self._table(0))
+    joints_vel_df = property(lambda self: self._table(1))
+    joints_rel_df = property(lambda self: self._table(2))
+    end_point_df = property(lambda self: self._table(3))
 
     def render(self, mode="human"):
         """The reference forwards to PyBullet's renderer (REF low_level_env.py:202-203); there is no renderer on

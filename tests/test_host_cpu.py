@@ -190,3 +190,27 @@ def test_allreduce_is_a_noop_without_a_group():
     assert torch.equal(stats.allreduce_stats(v.clone()), v)
     with pytest.raises(ValueError):
         stats.allreduce_stats(torch.zeros(3))
+
+
+def test_reference_named_tables_and_weights():
+    """The DataFrames / dictionaries the reference env exposes as attributes (REF low_level_env.py:58-152): same
+    column names as the CSV headers, same weights (python float sums 17.400000000000002 and 8.6)."""
+    from ilrl_b200 import ref_api
+
+    class View(ref_api._SingleEnv):
+        reference_name = "motion09_03"
+    v = View.__new__(View)
+    v._df = None
+    assert list(v.joints_df.columns) == ref_api.JOINT_COLS and v.joints_df.shape == (90, 14)
+    assert v.joints_vel_df.shape == (89, 14) and v.joints_rel_df.shape == (90, 14)
+    assert list(v.end_point_df.columns)[:3] == ["LeftLeg_Xposition", "LeftLeg_Yposition", "LeftLeg_Zposition"]
+    assert v.end_point_df.shape == (90, 27)
+    assert sum(ref_api.JOINT_WEIGHT.values()) == 17.400000000000002 and abs(sum(ref_api.JOINT_VEL_WEIGHT.values()) - 8.6) < 1e-12
+    assert list(ref_api.JOINT_MAP) == list(ref_api.JOINT_WEIGHT) == list(ref_api.JOINT_VEL_WEIGHT)
+    if os.path.isdir("/root/reference"):
+        import pandas as pd
+        ref = pd.read_csv("/root/reference/Joints CSV With Hand/motion09_03JointPosRad.csv")
+        assert list(ref.columns) == ref_api.JOINT_COLS
+        np.testing.assert_allclose(v.joints_df.values, ref.values, atol=2e-7)
+        ep = pd.read_csv("/root/reference/Joints CSV With Hand/motion09_03JointVecFromHip.csv")
+        assert list(ep.columns) == ref_api.EP_COLS

@@ -58,9 +58,10 @@ class RolloutCollector:
     """Collects [T, N] fragments from a BatchedHumanoidEnv (mode "low", auto_reset=True) with a policy living on the
     same GPU.  `collect()` returns a dict of step-major device tensors named like RLlib's SampleBatch columns."""
 
-    def __init__(self, env, policy=None, horizon=8, gamma=0.99, lam=0.9, seed=0, use_graph=True):
+    def __init__(self, env, policy=None, horizon=8, gamma=0.99, lam=0.9, seed=0, use_graph=True, autocast_dtype=None):
         assert isinstance(env, BatchedHumanoidEnv) and env.mode == 0
         self.env, self.T, self.gamma, self.lam = env, int(horizon), float(gamma), float(lam)
+        self.autocast_dtype = autocast_dtype  # e.g. torch.bfloat16: policy GEMMs on the tensor cores (inference only)
         dev, n, T = env.device, env.num_envs, self.T
         self.policy = (policy if policy is not None else GaussianMLPPolicy()).to(dev).eval()
         self.gen = torch.Generator(device=dev)
@@ -82,8 +83,14 @@ class RolloutCollector:
     def _loop(self):
         b, env = self.buf, self.env
         std = self.policy.log_std.exp()
+        def forward(obs):
+            if self.autocast_dtype is None:
+                return self.policy(obs)
+            with torch.autocast("cuda", dtype=self.autocast_dtype):
+                m, v = self.policy(obs)
+            return m.float(), v.float()
         for t in range(self.T):
-            mean, v = self.policy(self.cur_obs)
+            mean, v = forward(self.cur_obs)
             a = mean + std * self._noise[t]
             b["obs"][t].copy_(self.cur_obs)
             b["actions"][t].copy_(a)
@@ -95,7 +102,7 @@ class RolloutCollector:
             b["rewards"][t].copy_(rew)
             b["dones"][t].copy_(done)
             self.cur_obs.copy_(obs)
-        b["vf_preds"][self.T].copy_(self.policy(self.cur_obs)[1])
+        b["vf_preds"][self.T].copy_(forward(self.cur_obs)[1])
 
     @torch.no_grad()
     def collect(self):

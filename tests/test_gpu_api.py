@@ -597,3 +597,38 @@ def test_individual_score_methods_match_oracle_and_leave_the_state_alone():
         np.testing.assert_allclose(p[13 + 6], c["pos"][f, 3], atol=1e-7)      # right_knee <- rightKnee column
         assert (p[13:16] == 0).all()
     env.close()
+
+
+def test_max_timestep_and_step_per_level_are_honoured():
+    """`max_timestep` (REF low_level_env.py:73, 522-524) ends an episode whatever the robot does; `step_per_level`
+    (REF hier_env.py:58) sets the high-level period and the divisor of the high-level reward (Q14)."""
+    n = 64
+    env = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], seed=2, auto_reset=True, max_timestep=4)
+    env.reset()
+    zero = torch.zeros(n, 17, device="cuda")
+    for t in range(1, 9):
+        _, _, done, _ = env.step(zero)
+        tt = env.get_state()[1][:, B.E_T]
+        if t % 4 == 0:
+            assert bool((done == 1).all()) and bool((tt == 0).all())          # horizon reached -> reset in the kernel
+        else:
+            assert bool((tt[done == 0] == t % 4).all())
+    env.close()
+    env = BatchedHumanoidEnv(n, "hier", clips=["motion08_03", "motion09_03"], clip_of_env=np.ones(n, np.int32), seed=2,
+                             auto_reset=False, step_per_level=3)
+    env.reset()
+    env.high_step(torch.ones(n, 2, device="cuda"))
+    for k in range(3):
+        _, _, done, terms = env.step(zero)
+        ho, hr, hf = env.high_readout()
+        alive = done == 0
+        if k < 2:
+            assert bool(((hf[alive] & 2) == 0).all())                              # high-level agent not yet due
+        else:
+            assert bool(((hf[alive] & 6) == 6).all())                              # due, and the env now waits for it
+            # driftScore = cumulative / (step_per_level + 1) <= 3/4
+            assert bool((terms[alive, 10] <= 0.75 + 1e-6).all()) and bool((terms[alive, 10] >= 0).all())
+    before = env.get_state()[1][:, B.E_T].clone()
+    env.step(zero)                                                                 # everyone waits: nothing moves
+    assert torch.equal(env.get_state()[1][:, B.E_T], before)
+    env.close()

@@ -133,9 +133,14 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   // Persistent CTAs: the grid is at most what is resident at once (SMs x CTAs per SM) and tiles of QE envs are handed
   // out through an atomic counter, so a large batch has no partially filled last wave and no per-tile table copy, and
   // CTAs that drew cheap tiles simply take more of them.  The last CTA to leave resets the counters (graph-safe).
+  // (The first tile of a CTA is its own index: a batch that fits one wave never touches the counter.)
   __shared__ int s_tile;
-  for (;;) {
-  if (tid == 0) s_tile = (int)atomicAdd(a.tile_counter, 1u);
+  const bool one_wave = a.ntiles <= (int)gridDim.x;
+  for (int it = 0;; it++) {
+  if (it > 0) {
+    if (one_wave) break;
+    if (tid == 0) s_tile = (int)gridDim.x + (int)atomicAdd(a.tile_counter, 1u);
+  } else if (tid == 0) s_tile = (int)blockIdx.x;
   __syncthreads();
   const int tile = s_tile;
   if (tile >= a.ntiles) break;
@@ -315,13 +320,13 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     for (int t = 0; t < 16; t++) {
       float x = v[t];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      for (int o = 16; o >= 4; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);  // (lanes 1..3 of a quad hold 0)
       if ((tid & 31) == 0 && x != 0.f) atomicAdd(a.stats + t, x);
     }
   }
   __syncthreads();  // every warp is done with this tile's shared memory (and with s_tile) before the next one
   }  // tile loop
-  if (tid == 0 && atomicAdd(a.tile_counter + 1, 1u) == gridDim.x - 1) {  // last CTA out: ready for the next launch
+  if (!one_wave && tid == 0 && atomicAdd(a.tile_counter + 1, 1u) == gridDim.x - 1) {  // last CTA out: ready for the next launch
     a.tile_counter[0] = 0u;
     a.tile_counter[1] = 0u;
   }

@@ -211,8 +211,8 @@ def run_ours(args):
         first, n = rank * wl["envs"], wl["envs"]
     cid = ilrl_b200.stats.clip_of_env(first, n, len(wl["clips"])) if len(wl["clips"]) > 2 else (
         np.ones(n, np.int32) if hier else None)
-    env = BatchedHumanoidEnv(n, wl["mode"], clips=wl["clips"], clip_of_env=cid, device=local_rank, seed=1234 + rank,
-                             auto_reset=True)
+    env = BatchedHumanoidEnv(n, wl["mode"], clips=wl["clips"], clip_of_env=cid, device=local_rank, seed=1234,
+                             auto_reset=True, env_id_base=first)  # same seed, global env ids: sharding-invariant
     env.reset()
     # action pool larger than L2 (126 MB), e.g. 512 batches x 4096 x 17 x 4 B = 142 MB, rotated through -> inputs are
     # never L2-resident from the previous use.  (The persistent env state IS on-chip between steps: that is the

@@ -14,7 +14,7 @@ SYMBOLS = ["ilrl_create", "ilrl_destroy", "ilrl_last_error", "ilrl_load_clip", "
 class Config(C.Structure):
     _fields_ = [("device", C.c_int32), ("num_envs", C.c_int32), ("mode", C.c_int32), ("auto_reset", C.c_int32),
                 ("seed", C.c_uint64), ("skip_frame", C.c_int32), ("max_timestep", C.c_int32),
-                ("step_per_level", C.c_int32), ("reserved", C.c_int32)]
+                ("step_per_level", C.c_int32), ("env_id_base", C.c_int32)]
 
 
 class IlrlError(RuntimeError):

@@ -32,10 +32,12 @@ def _ptr(t):
 
 class BatchedHumanoidEnv:
     """mode "low": LowLevelHumanoidEnv semantics (REF low_level_env.py); "hier": HierarchicalHumanoidEnv
-    (REF hier_env.py).  clips: list of clip names staged in HBM; clip_of_env: per-env index into that list."""
+    (REF hier_env.py).  clips: list of clip names staged in HBM; clip_of_env: per-env index into that list.
+    env_id_base: global id of env 0 when a batch is sharded over several handles / GPUs (with the same seed the
+    shards then reproduce exactly what one handle holding the whole batch would do)."""
 
     def __init__(self, num_envs, mode="low", clips=("motion09_03",), clip_of_env=None, device=0, seed=0,
-                 auto_reset=True, max_timestep=3000, step_per_level=5):
+                 auto_reset=True, max_timestep=3000, step_per_level=5, env_id_base=0):
         if not torch.cuda.is_available():
             raise _lib.IlrlError("BatchedHumanoidEnv needs a CUDA device (sm_100a); there is no CPU fallback")
         self.L = _lib.lib()
@@ -44,7 +46,8 @@ class BatchedHumanoidEnv:
         self.device = torch.device("cuda", device)
         self.clip_names = list(clips)
         cfg = _lib.Config(device=device, num_envs=self.num_envs, mode=self.mode, auto_reset=int(bool(auto_reset)),
-                          seed=seed, skip_frame=2, max_timestep=max_timestep, step_per_level=step_per_level, reserved=0)
+                          seed=seed, skip_frame=2, max_timestep=max_timestep, step_per_level=step_per_level,
+                          env_id_base=int(env_id_base))
         h = C.c_void_p()
         rc = self.L.ilrl_create(C.byref(cfg), C.byref(h))
         if rc != 0:

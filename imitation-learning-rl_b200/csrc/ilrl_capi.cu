@@ -30,6 +30,7 @@ using SmemLarge = chain::SmemT<chain::LayoutLarge>;
 
 struct StepArgs {
   int n;
+  int id_base;         // global id of env 0 of this handle: the Philox counter of env i is id_base + i
   int skip_physics;
   int auto_reset;
   int max_timestep;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     else {
       // the draw is consumed (counter advanced) only when the target actually switches
       uint32_t c2 = ctr;
-      deg = rand_int(a.seed, (uint32_t)i, c2, -180, 180);
+      deg = rand_int(a.seed, (uint32_t)(i + a.id_base), c2, -180, 180);
       float dist = hyp(w.e[ILRL_E_ROBOT_X] - w.e[ILRL_E_TARGET_X], w.e[ILRL_E_ROBOT_Y] - w.e[ILRL_E_TARGET_Y]);
       if (dist <= (float)ILRL_TARGET_REACHED) ctr = c2;
     }
@@ -266,9 +267,9 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     if (done) {
       if (role == 0) { st_ep = 1.f; st_ret = w.e[ILRL_E_EP_RETURN]; st_len = w.e[ILRL_E_EP_LEN]; }
       if (a.auto_reset) {
-        int sf = rand_int(a.seed, (uint32_t)i, ctr, 0, cl.max_frame - 5);
-        float yaw = MODE == 1 ? (float)rand_int(a.seed, (uint32_t)i, ctr, -180, 180) : 0.f;
-        int tdeg = rand_int(a.seed, (uint32_t)i, ctr, -180, 180);
+        int sf = rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, 0, cl.max_frame - 5);
+        float yaw = MODE == 1 ? (float)rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180) : 0.f;
+        int tdeg = rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180);
         ResetCtx rx;
         reset_pose<MODE>(ps, w, cl, sf, yaw, tdeg, rx);
         chain::scatter(ps, sm, e, qb, role, qm, b);
@@ -335,6 +336,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
 // ------------------------------------------------------------------------------------------------ K2: reset
 struct ResetArgs {
   int n;
+  int id_base;
   float step_per_level;
   uint64_t seed;
   float* phys; float* envf; uint32_t* rng;
@@ -355,9 +357,9 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const ResetArgs a) {
   load_state(v, i, s, w);
   const ClipDesc cl = a.clips[(int)w.e[ILRL_E_CLIP]];
   uint32_t ctr = a.rng[i];
-  int sf = a.start_frame ? a.start_frame[i] : rand_int(a.seed, (uint32_t)i, ctr, 0, cl.max_frame - 5);
-  float yaw = a.yaw_deg ? a.yaw_deg[i] : (MODE == 1 ? (float)rand_int(a.seed, (uint32_t)i, ctr, -180, 180) : 0.f);
-  int tdeg = (a.target_deg || a.target_xy) ? (a.target_deg ? a.target_deg[i] : 0) : rand_int(a.seed, (uint32_t)i, ctr, -180, 180);
+  int sf = a.start_frame ? a.start_frame[i] : rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, 0, cl.max_frame - 5);
+  float yaw = a.yaw_deg ? a.yaw_deg[i] : (MODE == 1 ? (float)rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180) : 0.f);
+  int tdeg = (a.target_deg || a.target_xy) ? (a.target_deg ? a.target_deg[i] : 0) : rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180);
   float txy[2] = {0.f, 0.f};
   if (a.target_xy) { txy[0] = a.target_xy[2 * i]; txy[1] = a.target_xy[2 * i + 1]; }
   Work k; Calc c;
@@ -707,7 +709,7 @@ int ilrl_reset(ilrl_env* env, const uint8_t* mask, const int32_t* start_frame, c
   if (int r = check_ready(env)) return r;
   CK(cudaSetDevice(env->cfg.device));
   ResetArgs a;
-  a.n = env->n; a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
+  a.n = env->n; a.id_base = env->cfg.env_id_base; a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
   a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
   a.mask = mask; a.start_frame = start_frame; a.target_deg = target_deg; a.yaw_deg = yaw_deg; a.target_xy = target_xy; a.obs = obs;
   a.high_flags = env->high_flags;
@@ -727,7 +729,7 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   if (int r = check_ready(env)) return r;
   CK(cudaSetDevice(env->cfg.device));
   StepArgs a;
-  a.n = env->n; a.skip_physics = skip_physics; a.auto_reset = env->cfg.auto_reset; a.max_timestep = env->cfg.max_timestep;
+  a.n = env->n; a.id_base = env->cfg.env_id_base; a.skip_physics = skip_physics; a.auto_reset = env->cfg.auto_reset; a.max_timestep = env->cfg.max_timestep;
   a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
   a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
   a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.terms = terms;

@@ -47,7 +47,9 @@ typedef struct {
   int32_t skip_frame;     /* 2  REF low_level_env.py:162 */
   int32_t max_timestep;   /* 3000 REF low_level_env.py:73 */
   int32_t step_per_level; /* 5  REF hier_env.py:58 */
-  int32_t reserved;
+  int32_t env_id_base;    /* global id of env 0 of this handle (0 on a single GPU).  The random draws of env i are a
+                             function of (seed, env_id_base + i, draw index) only, so sharding a batch over GPUs with
+                             the same seed does not change any env's trajectory */
 } ilrl_config;
 
 int ilrl_create(const ilrl_config* cfg, ilrl_env** out);

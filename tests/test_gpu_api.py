@@ -371,7 +371,7 @@ def test_c_abi_error_behaviour_on_device():
     from ilrl_b200 import _lib
     L = _lib.lib()
     cfg = _lib.Config(device=0, num_envs=32, mode=0, auto_reset=0, seed=1, skip_frame=2, max_timestep=3000,
-                      step_per_level=5, reserved=0)
+                      step_per_level=5, env_id_base=0)
     h = C.c_void_p()
     assert L.ilrl_create(C.byref(cfg), C.byref(h)) == 0
     buf = torch.zeros(32, 70, device="cuda")

@@ -41,7 +41,7 @@ def test_create_fails_loudly_without_a_device():
     from ilrl_b200.batched_env import BatchedHumanoidEnv
     L = _lib.lib()
     cfg = _lib.Config(device=0, num_envs=8, mode=0, auto_reset=1, seed=1, skip_frame=2, max_timestep=3000,
-                      step_per_level=5, reserved=0)
+                      step_per_level=5, env_id_base=0)
     h = C.c_void_p()
     rc = L.ilrl_create(C.byref(cfg), C.byref(h))
     assert rc == -2 and not h.value                     # ILRL_ERR_CUDA, no handle

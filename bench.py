@@ -9,6 +9,7 @@ only collective is the NCCL all-reduce of the 16-float statistics vector at the 
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            -> this framework
   python bench.py --impl reference [--steps K] [--warmup W]      -> CPU arm: the oracle port of the reference path
+  python bench.py --workload hier16384|multiclip65536|rollout16384x8   -> extra measurement modes (BASELINE cfg 3/4/5)
                                                                     (PyBullet is not installable in this image)
 Prints ONE JSON line on rank 0.
 """
@@ -357,6 +358,62 @@ def _quiet_stdout():
 EMIT = print
 
 
+def run_rollout(args):
+    """Extra measurement mode (BASELINE cfg 5): on-device rollout collection, 16384 envs x 8 steps per GPU per
+    iteration (= 1 M env-steps per iteration on 8 GPUs): policy MLP (torch, bf16 autocast) -> sample -> fused env step,
+    captured in one CUDA graph, + GAE (ilrl_gae).  A "step" is one iteration; value = env-steps/s of the whole job."""
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+    import torch.distributed as dist
+    import ilrl_b200
+    from ilrl_b200 import BatchedHumanoidEnv, GaussianMLPPolicy, RolloutCollector
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, T = 16384, 8
+    K, W = min(args.steps, 200), max(3, min(args.warmup, 20))
+    torch.manual_seed(0)
+    env = BatchedHumanoidEnv(n, "low", clips=[CLIP], device=local_rank, seed=1234, auto_reset=True, env_id_base=rank * n)
+    col = RolloutCollector(env, GaussianMLPPolicy(), horizon=T, gamma=0.99, lam=0.9, seed=rank, autocast_dtype=torch.bfloat16)
+    for _ in range(W):
+        col.collect()
+    env.stats()
+    l0 = env.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(K):
+        batch = col.collect()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    st = ilrl_b200.stats.allreduce_stats(env.stats())
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms = float(t_ms.item())
+    if rank == 0:
+        summ = ilrl_b200.stats.summarize(st)
+        EMIT(json.dumps({
+            "metric": "rollout env-steps/sec (policy + physics + reward + GAE on device)", "value": world * n * T * K / (ms * 1e-3),
+            "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "on-device PPO rollout collection: %d envs x %d steps per GPU per iteration, %s, "
+                                   "70-256-256-17 tanh Gaussian policy + value net (bf16 autocast), gamma 0.99 lambda 0.9"
+                                   % (n, T, CLIP), "envs_per_gpu": n, "horizon": T,
+                       "episode_len_mean": summ["episode_len_mean"], "sample_batch_columns": sorted(batch.keys())},
+            "gpu_launches": int(env.launch_count() - l0)}))
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     global EMIT
     EMIT = _quiet_stdout()
@@ -366,11 +423,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="low4096", choices=sorted(WORKLOADS),
+    ap.add_argument("--workload", default="low4096", choices=sorted(WORKLOADS) + ["rollout16384x8"],
                     help="low4096 = the contract line (BASELINE cfg 2); the others are extra measurement modes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "rollout16384x8":
+        run_rollout(args)
     else:
         run_ours(args)
 

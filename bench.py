@@ -9,8 +9,8 @@ only collective is the NCCL all-reduce of the 16-float statistics vector at the 
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            -> this framework
   python bench.py --impl reference [--steps K] [--warmup W]      -> CPU arm: the oracle port of the reference path
-  python bench.py --workload hier16384|multiclip65536|rollout16384x8   -> extra measurement modes (BASELINE cfg 3/4/5)
                                                                     (PyBullet is not installable in this image)
+  python bench.py --workload hier16384|multiclip65536|rollout16384x8   -> extra measurement modes (BASELINE cfg 3/4/5)
 Prints ONE JSON line on rank 0.
 """
 import argparse

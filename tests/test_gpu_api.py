@@ -632,3 +632,45 @@ def test_max_timestep_and_step_per_level_are_honoured():
     env.step(zero)                                                                 # everyone waits: nothing moves
     assert torch.equal(env.get_state()[1][:, B.E_T], before)
     env.close()
+
+
+def test_concurrent_handles_and_streams():
+    """Several handles alive at once, stepped on different CUDA streams in interleaved order (what several RLlib
+    workers sharing one GPU do): each must reproduce what it computes alone."""
+    n = 512
+    g = torch.Generator(device="cuda")
+    g.manual_seed(1)
+    acts = [torch.rand(n, 17, device="cuda", generator=g) * 2 - 1 for _ in range(10)]
+
+    def alone(seed, mode):
+        env = BatchedHumanoidEnv(n, mode, clips=["motion08_03", "motion09_03"], clip_of_env=np.ones(n, np.int32), seed=seed, auto_reset=True)
+        env.reset()
+        for a in acts:
+            if mode == "hier":
+                env.high_step(a[:, :2].contiguous())
+            env.step(a)
+        out = [t.clone() for t in env.get_state()]
+        env.close()
+        return out
+
+    want = [alone(1, "low"), alone(2, "low"), alone(3, "hier")]
+    envs = [BatchedHumanoidEnv(n, m, clips=["motion08_03", "motion09_03"], clip_of_env=np.ones(n, np.int32), seed=s, auto_reset=True)
+            for s, m in ((1, "low"), (2, "low"), (3, "hier"))]
+    streams = [torch.cuda.Stream() for _ in envs]
+    torch.cuda.synchronize()
+    for env, st in zip(envs, streams):
+        with torch.cuda.stream(st):
+            env.reset()
+    for a in acts:
+        for k in (2, 0, 1):
+            with torch.cuda.stream(streams[k]):
+                if envs[k].mode == 1:
+                    envs[k].high_step(a[:, :2].contiguous())
+                envs[k].step(a)
+    torch.cuda.synchronize()
+    for env, st, w in zip(envs, streams, want):
+        with torch.cuda.stream(st):
+            got = env.get_state()
+        torch.cuda.synchronize()
+        assert torch.equal(got[0], w[0]) and torch.equal(got[1], w[1])
+        env.close()

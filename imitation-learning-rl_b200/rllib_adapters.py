@@ -60,7 +60,11 @@ class LowLevelVectorEnv(_VectorEnv):
         self.num_envs = int(num_envs)
         self.observation_space = Box(low=-np.inf, high=np.inf, shape=[70])
         self.action_space = Box(low=-1, high=1, shape=[17])
-        self._terms_host = np.zeros((self.num_envs, B.TERM_WORDS), np.float32)
+        # pinned host buffers: ilrl_step_host reads the actions from / writes the results to them in place (zero-copy)
+        pin = lambda *shape, dtype=torch.float32: torch.zeros(*shape, dtype=dtype).pin_memory().numpy()  # noqa: E731
+        self._act_host, self._obs_host = pin(self.num_envs, 17), pin(self.num_envs, 70)
+        self._rew_host, self._done_host = pin(self.num_envs), pin(self.num_envs, dtype=torch.uint8)
+        self._terms_host = pin(self.num_envs, B.TERM_WORDS)
         self._next_obs = np.zeros((self.num_envs, 70), np.float32)
         self._views = [_EnvAttrView(self, i) for i in range(self.num_envs)]
 
@@ -73,14 +77,15 @@ class LowLevelVectorEnv(_VectorEnv):
         return self._next_obs[index].astype(np.float64)
 
     def vector_step(self, actions):
-        a = torch.as_tensor(np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 17))
-        assert bool(torch.isfinite(a).all())
-        obs, rew, done, terms = self.env.step(a.to(self.env.device))
-        obs_h, rew_h, done_h = obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy().astype(bool)
-        self._terms_host[:] = terms.cpu().numpy()
+        self._act_host[:] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 17)
+        assert np.isfinite(self._act_host).all()
+        self.env.step_host(self._act_host, self._obs_host, self._rew_host, self._done_host, self._terms_host)
+        done_h = self._done_host.astype(bool)
+        obs64 = self._obs_host.astype(np.float64)
         if done_h.any():  # one masked reset for every env that finished; their first obs waits for reset_at()
-            self._next_obs[done_h] = self.env.reset(mask=done).cpu().numpy()[done_h]
-        return ([o for o in obs_h.astype(np.float64)], [float(r) for r in rew_h], [bool(d) for d in done_h],
+            mask = torch.from_numpy(self._done_host).to(self.env.device)
+            self._next_obs[done_h] = self.env.reset(mask=mask).cpu().numpy()[done_h]
+        return ([o for o in obs64], [float(r) for r in self._rew_host], [bool(d) for d in done_h],
                 [{} for _ in range(self.num_envs)])
 
     def get_unwrapped(self):

@@ -7,7 +7,10 @@
 //   clips: the 4 tables of every loaded motion clip, row-major fp32, read through the read-only path (L2-resident,
 //          ~200 KB for all four clips).
 // I/O with the caller (row-major [N,17] actions, [N,70] observations) is staged through shared memory so that global
-// accesses are coalesced although every thread produces/consumes a whole row.
+// accesses are coalesced although every quad produces/consumes a whole row.
+// The fused step kernel (K1) maps FOUR LANES to one env and is persistent (tiles of 16 envs handed out through an
+// atomic counter); its physics lives in ilrl_chain.cuh, the env logic in ilrl_env.cuh.  The service kernels (reset,
+// high-level step, harness) map one thread to one env.
 #include <cuda_runtime.h>
 #include <limits.h>
 #include <stdio.h>
@@ -121,7 +124,7 @@ __device__ __forceinline__ void set_torques(SM& sm, int e, int tid, int role, co
 
 // ------------------------------------------------------------------------------------------------ K1: fused step
 // MODE 0 = LowLevelHumanoidEnv.step (REF low_level_env.py:475-526), MODE 1 = HierarchicalHumanoidEnv low_level_step
-// (REF hier_env.py:355-366, 583-642).  Four lanes = one env (ilrl_quad.cuh): the physics substeps run distributed
+// (REF hier_env.py:355-366, 583-642).  Four lanes = one env (ilrl_chain.cuh): the physics substeps run distributed
 // over the quad; the env bookkeeping after them is computed redundantly by the four lanes (identical instruction
 // stream, no divergence) and the outputs are dealt to the lanes for the stores.
 template <int MODE, class SM>

@@ -5,7 +5,7 @@
  *             btMultiBody*, pybullet_envs): NOT pinned by any reference test or fixture ("parity unpinned",
  *             DESIGN.md section 3).  Every such value lives here so that it can be re-validated in one place the
  *             first time a real PyBullet is importable.
- * Included by oracle/ilrl_oracle.c (double) and csrc/ilrl_kernels.cu (float); values only, no code. */
+ * Included by oracle/ilrl_oracle.c (double) and the CUDA sources under csrc/ (float); values only, no code. */
 #ifndef ILRL_CONSTANTS_H
 #define ILRL_CONSTANTS_H
 

@@ -34,7 +34,8 @@ constexpr int QE = ILRL_QE;            // envs per CTA
 constexpr int QT = 4 * QE;             // threads per CTA
 constexpr int NL = 7;                  // chain links per lane: 3 spine + 4 limb slots
 constexpr int RW = 40;                 // words per stored row
-constexpr int GROWS = MAXROWS;         // rows per env in the global overflow scratch (sized for the smallest on-chip budget)
+constexpr int MIN_RSM = 8;             // smallest on-chip row budget of any layout
+constexpr int GROWS = MAXROWS - MIN_RSM;  // rows per env in the global overflow scratch
 // link record: 24 words in 6 float4 (S | cJ | U dinv u | q qd tau nu), one contiguous 28-word slot per thread: a
 // 28-word stride puts the float4 of 8 consecutive threads in 8 different bank groups (conflict-free LDS.128 / STS.128)
 enum { W_S = 0, W_CJ = 6, W_U = 12, W_DINV = 18, W_UU = 19, W_Q = 20, W_QD = 21, W_TAU = 22, W_NU = 23, LKW = 28 };
@@ -201,6 +202,7 @@ struct Layout {
 #define ILRL_LARGE_BRW 16
 #define ILRL_LARGE_TSM false
 #endif
+static_assert(ILRL_LARGE_RSM >= MIN_RSM, "the overflow scratch holds MAXROWS - MIN_RSM rows per env");
 using LayoutSmall = Layout<16, 20, true>;
 using LayoutLarge = Layout<ILRL_LARGE_RSM, ILRL_LARGE_BRW, ILRL_LARGE_TSM>;
 

@@ -360,8 +360,8 @@ EMIT = print
 
 def run_rollout(args):
     """Extra measurement mode (BASELINE cfg 5): on-device rollout collection, 16384 envs x 8 steps per GPU per
-    iteration (= 1 M env-steps per iteration on 8 GPUs): policy MLP (torch, bf16 autocast) -> sample -> fused env step,
-    captured in one CUDA graph, + GAE (ilrl_gae).  A "step" is one iteration; value = env-steps/s of the whole job."""
+    iteration (= 1 M env-steps per iteration on 8 GPUs): fused tcgen05 policy / value / sampling kernel -> fused env step,
+    2 launches per step captured in one CUDA graph, + GAE (ilrl_gae).  A "step" is one iteration; value = env-steps/s of the whole job."""
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -377,7 +377,7 @@ def run_rollout(args):
     K, W = min(args.steps, 200), max(3, min(args.warmup, 20))
     torch.manual_seed(0)
     env = BatchedHumanoidEnv(n, "low", clips=[CLIP], device=local_rank, seed=1234, auto_reset=True, env_id_base=rank * n)
-    col = RolloutCollector(env, GaussianMLPPolicy(), horizon=T, gamma=0.99, lam=0.9, seed=rank, autocast_dtype=torch.bfloat16)
+    col = RolloutCollector(env, GaussianMLPPolicy(), horizon=T, gamma=0.99, lam=0.9, seed=rank)
     for _ in range(W):
         col.collect()
     env.stats()
@@ -405,10 +405,12 @@ def run_rollout(args):
             "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "on-device PPO rollout collection: %d envs x %d steps per GPU per iteration, %s, "
-                                   "70-256-256-17 tanh Gaussian policy + value net (bf16 autocast), gamma 0.99 lambda 0.9"
+                                   "70-256-256-17 tanh Gaussian policy + value net (fused tcgen05 kernel, bf16 operands / fp32 accumulation), "
+                                   "gamma 0.99 lambda 0.9"
                                    % (n, T, CLIP), "envs_per_gpu": n, "horizon": T,
                        "episode_len_mean": summ["episode_len_mean"], "sample_batch_columns": sorted(batch.keys())},
-            "gpu_launches": int(env.launch_count() - l0)}))
+            # per iteration, replayed from the graph: T env steps + (T + 1) policy steps; + 1 GAE launch
+            "gpu_launches": K * (2 * T + 2)}))
     env.close()
     if world > 1:
         dist.destroy_process_group()

@@ -5,7 +5,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "libilrl_b200.so")
 SRC = os.path.join(HERE, "csrc", "ilrl_capi.cu")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("ilrl_env.cuh", "ilrl_chain.cuh", "ilrl_physics.cuh", "ilrl_constants.h",
+SRC_POLICY = os.path.join(HERE, "csrc", "ilrl_policy.cu")   # tcgen05 fused policy / value forward (rollout collection)
+DEPS = [SRC, SRC_POLICY] + [os.path.join(HERE, "csrc", f) for f in ("ilrl_env.cuh", "ilrl_chain.cuh", "ilrl_physics.cuh", "ilrl_constants.h",
                                                         "ilrl_model_data.h")] + [
     os.path.join(os.path.dirname(HERE), "include", "ilrl.h")]
 # -ftz / -prec-div=false / -prec-sqrt=false: flush denormals, 2-ulp division and square root without their slow-path
@@ -23,7 +24,7 @@ def build(force=False, verbose=False):
     if not force and not stale():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC]
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", SO, SRC, SRC_POLICY]
     subprocess.check_call(cmd)
     return SO
 

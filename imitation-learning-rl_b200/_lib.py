@@ -8,7 +8,8 @@ SO = os.environ.get("ILRL_SO") or os.path.join(HERE, "libilrl_b200.so")  # ILRL_
 SYMBOLS = ["ilrl_create", "ilrl_destroy", "ilrl_last_error", "ilrl_load_clip", "ilrl_set_clip_ids", "ilrl_reset",
            "ilrl_step", "ilrl_step_host", "ilrl_high_step", "ilrl_high_readout", "ilrl_get_state", "ilrl_set_state",
            "ilrl_set_forced_target_deg", "ilrl_step_no_physics", "ilrl_physics_only", "ilrl_endpoint_score",
-           "ilrl_stats", "ilrl_gae", "ilrl_launch_count", "ilrl_kernel_timing"]
+           "ilrl_stats", "ilrl_gae", "ilrl_policy_blob_bytes", "ilrl_policy_pack", "ilrl_policy_step",
+           "ilrl_launch_count", "ilrl_kernel_timing"]
 
 
 class Config(C.Structure):
@@ -53,6 +54,10 @@ def lib():
     L.ilrl_endpoint_score.argtypes = [_vp, _vp, _vp]
     L.ilrl_stats.argtypes = [_vp, _vp, _vp]
     L.ilrl_gae.argtypes = [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, C.c_int32, C.c_int32, _vp]
+    L.ilrl_policy_blob_bytes.restype = C.c_int64
+    L.ilrl_policy_blob_bytes.argtypes = []
+    L.ilrl_policy_pack.argtypes = [_vp] * 13 + [C.c_int32, C.c_int32, _vp, _vp]
+    L.ilrl_policy_step.argtypes = [_vp] * 7 + [C.c_int32, C.c_int32, C.c_int32, _vp]
     L.ilrl_launch_count.argtypes = [_vp]
     L.ilrl_launch_count.restype = C.c_int64
     L.ilrl_kernel_timing.argtypes = [_vp, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64)]

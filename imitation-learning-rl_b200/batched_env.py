@@ -125,6 +125,16 @@ class BatchedHumanoidEnv:
         self._ck(fn(self.h, _ptr(a), _ptr(self.obs), _ptr(self.reward), _ptr(self.done), _ptr(self.terms), self._stream()))
         return self.obs, self.reward, self.done, self.terms
 
+    def step_into(self, action, obs, reward, done, terms=None):
+        """`step` writing straight into caller-owned device tensors (rollout buffers): obs [N,70] f32, reward [N] f32,
+        done [N] u8, optional terms [N,12]; all contiguous, on this env's device."""
+        n = self.num_envs
+        for t, shape, dt in ((action, (n, ACT_LOW), torch.float32), (obs, (n, OBS_LOW), torch.float32),
+                             (reward, (n,), torch.float32), (done, (n,), torch.uint8)) + (
+                                 () if terms is None else ((terms, (n, TERM_WORDS), torch.float32),)):
+            assert t.is_cuda and t.device == self.device and t.dtype == dt and t.is_contiguous() and tuple(t.shape) == shape
+        self._ck(self.L.ilrl_step(self.h, _ptr(action), _ptr(obs), _ptr(reward), _ptr(done), _ptr(terms), self._stream()))
+
     def step_host(self, action_np, obs_np, reward_np, done_np, terms_np=None):
         """Same step through host (numpy) buffers: H2D of the actions, kernel, D2H of obs/reward/done, synchronous."""
         # the argument tuple of the previous call is reused while the same buffers come back (the usual loop): dtype /

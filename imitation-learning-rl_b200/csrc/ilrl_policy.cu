@@ -1,0 +1,357 @@
+// Fused Gaussian-MLP policy + value forward for on-device rollout collection.
+//
+// Replaces, per env step of a rollout, RLlib's default fully connected model of the reference's low-level policy
+// (REF train_config.py:91-113: fcnet_hiddens [256, 256], tanh, free log-std, vf_share_layers False) and the
+// action sampling / log-probability code around it:
+//
+//     mean  = W3p tanh(W2p tanh(W1p obs + b1p) + b2p) + b3p          value = w3v . tanh(W2v tanh(W1v obs + b1v) + b2v) + b3v
+//     a     = mean + exp(log_std) * noise          a_clipped = clip(a, -1, 1)          logp = sum_j N(a_j; mean_j, std_j)
+//
+// One CTA owns 128 envs (= the UMMA M dimension).  The six GEMMs run on the 5th-generation tensor cores: one thread
+// issues tcgen05.mma (kind::f16, bf16 operands, fp32 accumulation) with both operands in shared memory and the
+// accumulators in tensor memory (layer 1 -> columns 0..255, layer 2 -> 256..511, layer 3 -> 0..31); the four warps
+// read the accumulators back with tcgen05.ld, apply bias + tanh and write the next layer's A operand straight into
+// shared memory in the canonical K-major core-matrix layout, so hidden activations never touch HBM.  Weights are
+// pre-packed once (ilrl_policy_pack) into exactly that shared-memory image and streamed by cp.async.bulk through two
+// 64 KB buffers, the next chunk in flight while the current layer's epilogue runs.
+//
+// Shared-memory operand layout (no swizzle, K-major): an R x K bf16 matrix is stored as [K/8][R][8] — 16-byte rows of
+// 8 consecutive k, the R rows of one k-group contiguous.  In UMMA descriptor terms (cute/atom/mma_traits_sm100.hpp,
+// "((8,n),2):((1,SBO),LBO)" in 16-byte units): SBO = 128 B between 8-row groups, LBO = 16 R bytes between the two
+// k-halves of one K = 16 instruction; the next K step starts 32 R bytes further.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/ilrl.h"
+
+namespace {
+
+constexpr int TM = 128;    // envs per CTA
+constexpr int HID = 256;   // hidden width
+constexpr int K1 = 80;     // observation width padded to a multiple of 16 (70 low level, 44 high level)
+constexpr int N3 = 32;     // output width padded (17 / 2 action means, 1 value)
+constexpr uint32_t W1_BYTES = HID * K1 * 2, W2H_BYTES = 128 * HID * 2, W3_BYTES = N3 * HID * 2;
+constexpr uint32_t NET_BYTES = W1_BYTES + 2 * W2H_BYTES + W3_BYTES;
+constexpr uint32_t BIAS_WORDS = HID + HID + N3;
+constexpr uint32_t BLOB_BIAS = 2 * NET_BYTES, BLOB_LOGSTD = BLOB_BIAS + 2 * BIAS_WORDS * 4, BLOB_BYTES = BLOB_LOGSTD + N3 * 4;
+
+// shared memory map
+constexpr uint32_t S_H = 0, S_A0 = S_H + TM * HID * 2, S_B0 = S_A0 + TM * K1 * 2, S_B1 = S_B0 + W2H_BYTES,
+                   S_BIAS = S_B1 + W2H_BYTES, S_LOGSTD = S_BIAS + 2 * BIAS_WORDS * 4, S_BAR = S_LOGSTD + N3 * 4,
+                   S_TMEM = S_BAR + 32, SMEM_BYTES = S_TMEM + 16;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(W1_BYTES <= W2H_BYTES && W3_BYTES <= W2H_BYTES, "weight chunks must fit a buffer");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded: a protocol error must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+    if (spins > (1u << 20)) {
+      printf("ilrl_policy: mbarrier %u timed out (block %d thread %d)\n", bar, blockIdx.x, threadIdx.x);
+      __trap();
+    }
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  mbar_expect_tx(bar, bytes);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, no swizzle; rows = R of the operand image.  version 1 (Blackwell) in bits [46,48).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t rows) {
+  const uint32_t lbo = rows * 16, sbo = 128;
+  const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16);
+  const uint32_t hi = (sbo >> 4) | (1u << 14);
+  return ((uint64_t)hi << 32) | lo;
+}
+// D fp32, A/B bf16, both K-major, M = 128.
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((TM >> 4) << 24);
+}
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[128 x n] (+)= A[128 x 16 ksteps] * B[n x 16 ksteps]^T; A image has 128 rows, B image has n rows.
+__device__ __forceinline__ void gemm(uint32_t tmem_d, uint32_t a_s, uint32_t b_s, uint32_t n, int ksteps) {
+  const uint32_t idesc = umma_idesc(n);
+  const uint64_t ad = umma_desc(a_s, TM), bd = umma_desc(b_s, n);
+  for (int k = 0; k < ksteps; ++k)   // descriptor address field is in 16-byte units: one K step = 32 * rows bytes
+    umma(tmem_d, ad + (uint64_t)(k * 2 * TM), bd + (uint64_t)(k * 2 * n), idesc, k > 0);
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));   // 2^-11 relative: below the bf16 rounding of the result
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 p = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&p);
+}
+
+// accumulators [128 x 256] at `taddr` -> tanh(x + bias) -> bf16 A operand image H (this thread's row).
+__device__ __forceinline__ void epilogue_hidden(uint32_t taddr, const float* bias, uint8_t* H, int row) {
+#pragma unroll 1
+  for (int c = 0; c < HID / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(taddr + 32 * c, v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint32_t p[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int col = 32 * c + 8 * q + 2 * j;
+        p[j] = pack_bf16(tanh_fast(__uint_as_float(v[8 * q + 2 * j]) + bias[col]),
+                         tanh_fast(__uint_as_float(v[8 * q + 2 * j + 1]) + bias[col + 1]));
+      }
+      *reinterpret_cast<uint4*>(H + ((4 * c + q) * TM + row) * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+    }
+  }
+}
+
+struct PolicyArgs {
+  const uint8_t* blob;
+  const float* obs;      // [n, obs_dim]
+  const float* noise;    // [n, act_dim] or null (deterministic: a = mean)
+  float* action;         // [n, act_dim] raw sample, or null
+  float* action_clipped; // [n, act_dim] clip(a, -1, 1), or null
+  float* logp;           // [n] or null
+  float* value;          // [n] or null (skips the value net)
+  int obs_dim, act_dim, n, nets;
+};
+
+__global__ void __launch_bounds__(TM, 1) policy_kernel(const PolicyArgs A) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid, env = blockIdx.x * TM + row;
+  float* bias_s = reinterpret_cast<float*>(smem + S_BIAS);
+  float* logstd_s = reinterpret_cast<float*>(smem + S_LOGSTD);
+  const uint32_t bar_full0 = smem_u32(smem + S_BAR), bar_full1 = bar_full0 + 8, bar_mma = bar_full0 + 16;
+  const uint32_t sH = smem_u32(smem + S_H), sA0 = smem_u32(smem + S_A0), sB0 = smem_u32(smem + S_B0), sB1 = smem_u32(smem + S_B1);
+  const int first = (A.nets & 1) ? 0 : 1, last = (A.nets & 2) ? 1 : 0;
+
+  if (tid == 0) {
+    mbar_init(bar_full0, 1); mbar_init(bar_full1, 1); mbar_init(bar_mma, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + S_TMEM)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // observation tile -> bf16 A operand image (zero padded in k and for rows past n); biases and log-std
+  for (int i = tid; i < TM * K1 / 8; i += TM) *reinterpret_cast<uint4*>(smem + S_A0 + i * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 2 * (int)BIAS_WORDS + N3; i += TM)
+    bias_s[i] = reinterpret_cast<const float*>(A.blob + BLOB_BIAS)[i];   // log-std follows the biases in both
+  __syncthreads();
+  {
+    const int rows = min(TM, A.n - blockIdx.x * TM);
+    const float* src = A.obs + (size_t)blockIdx.x * TM * A.obs_dim;
+    for (int i = tid; i < rows * A.obs_dim; i += TM) {   // coalesced read of the contiguous tile
+      const int r = i / A.obs_dim, k = i - r * A.obs_dim;
+      *reinterpret_cast<__nv_bfloat16*>(smem + S_A0 + ((k >> 3) * TM + r) * 16 + (k & 7) * 2) = __float2bfloat16_rn(src[i]);
+    }
+  }
+  fence_proxy_async();
+  tc_before();
+  __syncthreads();
+  tc_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
+  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes = its 32 rows
+
+  uint32_t ph0 = 0, ph1 = 0, phm = 0;   // ph0 / ph1 are used by thread 0 only
+  if (tid == 0) {
+    bulk_load(sB0, A.blob + first * NET_BYTES, W1_BYTES, bar_full0);
+    bulk_load(sB1, A.blob + first * NET_BYTES + W1_BYTES, W2H_BYTES, bar_full1);
+  }
+  __syncwarp();
+
+  for (int net = first; net <= last; ++net) {
+    const uint8_t* wb = A.blob + net * NET_BYTES;
+    const float* bs = bias_s + net * BIAS_WORDS;
+    const bool has_next = net < last;
+    // layer 1: D[0..255] = obs * W1^T   (W1 in buffer 0)
+    if (tid == 0) {
+      mbar_wait(bar_full0, ph0); ph0 ^= 1;
+      tc_after();
+      gemm(tmem, sA0, sB0, HID, K1 / 16);
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, phm); phm ^= 1;
+    tc_after();
+    if (tid == 0) bulk_load(sB0, wb + W1_BYTES + W2H_BYTES, W2H_BYTES, bar_full0);   // second half of W2
+    __syncwarp();
+    epilogue_hidden(tlane, bs, smem + S_H, row);
+    fence_proxy_async();
+    tc_before();
+    __syncthreads();
+    // layer 2: D[256..383] = H * W2[0..127]^T (buffer 1), D[384..511] = H * W2[128..255]^T (buffer 0)
+    if (tid == 0) {
+      tc_after();
+      mbar_wait(bar_full1, ph1); ph1 ^= 1;
+      gemm(tmem + 256, sH, sB1, 128, HID / 16);
+      mbar_wait(bar_full0, ph0); ph0 ^= 1;
+      gemm(tmem + 384, sH, sB0, 128, HID / 16);
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, phm); phm ^= 1;
+    tc_after();
+    if (tid == 0) {
+      bulk_load(sB1, wb + W1_BYTES + 2 * W2H_BYTES, W3_BYTES, bar_full1);
+      if (has_next) bulk_load(sB0, wb + NET_BYTES, W1_BYTES, bar_full0);
+    }
+    __syncwarp();
+    epilogue_hidden(tlane + 256, bs + HID, smem + S_H, row);
+    fence_proxy_async();
+    tc_before();
+    __syncthreads();
+    // layer 3: D[0..31] = H * W3^T (buffer 1)
+    if (tid == 0) {
+      tc_after();
+      mbar_wait(bar_full1, ph1); ph1 ^= 1;
+      gemm(tmem, sH, sB1, N3, HID / 16);
+      umma_commit(bar_mma);
+    }
+    __syncwarp();
+    mbar_wait(bar_mma, phm); phm ^= 1;
+    tc_after();
+    if (tid == 0 && has_next) bulk_load(sB1, wb + NET_BYTES + W1_BYTES, W2H_BYTES, bar_full1);
+    __syncwarp();
+    {
+      uint32_t v[32];
+      tmem_ld32(tlane, v);
+      if (env < A.n) {
+        if (net == 0) {
+          float lp = 0.f;
+#pragma unroll
+          for (int j = 0; j < N3; ++j)
+            if (j < A.act_dim) {
+              const float mean = __uint_as_float(v[j]) + bs[2 * HID + j];
+              const float z = A.noise ? A.noise[(size_t)env * A.act_dim + j] : 0.f;
+              const float a = fmaf(__expf(logstd_s[j]), z, mean);
+              if (A.action) A.action[(size_t)env * A.act_dim + j] = a;
+              if (A.action_clipped) A.action_clipped[(size_t)env * A.act_dim + j] = fminf(fmaxf(a, -1.f), 1.f);
+              lp += -0.5f * z * z - logstd_s[j] - 0.9189385332046727f;
+            }
+          if (A.logp) A.logp[env] = lp;
+        } else {
+          A.value[env] = __uint_as_float(v[0]) + bs[2 * HID];
+        }
+      }
+    }
+    tc_before();
+    __syncthreads();   // every warp has read D[0..31] before the next net's layer 1 overwrites it
+  }
+  if (warp == 0) {
+    tc_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+  }
+}
+
+// fp32 torch-layout parameters ([out, in] row major) -> the blob of operand images, biases and log-std
+__global__ void pack_kernel(const float* w1p, const float* b1p, const float* w2p, const float* b2p, const float* w3p,
+                            const float* b3p, const float* w1v, const float* b1v, const float* w2v, const float* b2v,
+                            const float* w3v, const float* b3v, const float* log_std, int obs_dim, int act_dim, uint8_t* blob) {
+  const int net = blockIdx.y;
+  const float* w1 = net ? w1v : w1p; const float* w2 = net ? w2v : w2p; const float* w3 = net ? w3v : w3p;
+  const float* b1 = net ? b1v : b1p; const float* b2 = net ? b2v : b2p; const float* b3 = net ? b3v : b3p;
+  const int out_dim = net ? 1 : act_dim;
+  __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(blob + net * NET_BYTES);
+  const int total = (int)(NET_BYTES / 2);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    // invert the image addressing: i -> (chunk, k-group, row, k within group)
+    int e = i, rows, base_row = 0, which;
+    if (e < (int)(W1_BYTES / 2)) { which = 0; rows = HID; }
+    else if ((e -= W1_BYTES / 2) < (int)(W2H_BYTES / 2)) { which = 1; rows = 128; }
+    else if ((e -= W2H_BYTES / 2) < (int)(W2H_BYTES / 2)) { which = 1; rows = 128; base_row = 128; }
+    else { e -= W2H_BYTES / 2; which = 2; rows = N3; }
+    const int kg = e / (rows * 8), r = (e / 8) % rows, k = kg * 8 + (e & 7);
+    float x;
+    if (which == 0) x = k < obs_dim ? w1[r * obs_dim + k] : 0.f;
+    else if (which == 1) x = w2[(base_row + r) * HID + k];
+    else x = r < out_dim ? w3[r * HID + k] : 0.f;
+    img[i] = __float2bfloat16_rn(x);
+  }
+  float* bias = reinterpret_cast<float*>(blob + BLOB_BIAS) + net * BIAS_WORDS;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < (int)BIAS_WORDS; i += gridDim.x * blockDim.x)
+    bias[i] = i < HID ? b1[i] : i < 2 * HID ? b2[i - HID] : (i - 2 * HID < out_dim ? b3[i - 2 * HID] : 0.f);
+  if (net == 0 && blockIdx.x == 0 && threadIdx.x < N3)
+    reinterpret_cast<float*>(blob + BLOB_LOGSTD)[threadIdx.x] = threadIdx.x < act_dim ? log_std[threadIdx.x] : 0.f;
+}
+
+}  // namespace
+
+extern "C" {
+
+int64_t ilrl_policy_blob_bytes(void) { return BLOB_BYTES; }
+
+int ilrl_policy_pack(const float* w1_pi, const float* b1_pi, const float* w2_pi, const float* b2_pi, const float* w3_pi,
+                     const float* b3_pi, const float* w1_vf, const float* b1_vf, const float* w2_vf, const float* b2_vf,
+                     const float* w3_vf, const float* b3_vf, const float* log_std, int32_t obs_dim, int32_t act_dim,
+                     void* blob_dev, void* stream) {
+  if (!w1_pi || !b1_pi || !w2_pi || !b2_pi || !w3_pi || !b3_pi || !w1_vf || !b1_vf || !w2_vf || !b2_vf || !w3_vf ||
+      !b3_vf || !log_std || !blob_dev || obs_dim < 1 || obs_dim > K1 || act_dim < 1 || act_dim > N3)
+    return ILRL_ERR_ARG;
+  pack_kernel<<<dim3(128, 2), 256, 0, (cudaStream_t)stream>>>(w1_pi, b1_pi, w2_pi, b2_pi, w3_pi, b3_pi, w1_vf, b1_vf, w2_vf,
+                                                              b2_vf, w3_vf, b3_vf, log_std, obs_dim, act_dim, (uint8_t*)blob_dev);
+  return cudaGetLastError() == cudaSuccess ? ILRL_OK : ILRL_ERR_CUDA;
+}
+
+int ilrl_policy_step(const void* blob_dev, const float* obs_dev, const float* noise_dev, float* action_dev,
+                     float* action_clipped_dev, float* logp_dev, float* value_dev, int32_t obs_dim, int32_t act_dim,
+                     int32_t n, void* stream) {
+  const bool want_pi = action_dev || action_clipped_dev || logp_dev;
+  if (!blob_dev || !obs_dev || n <= 0 || obs_dim < 1 || obs_dim > K1 || act_dim < 1 || act_dim > N3 ||
+      (!want_pi && !value_dev) || ((uintptr_t)blob_dev & 15))
+    return ILRL_ERR_ARG;
+  static bool configured[64] = {};   // the opt-in to > 48 KB of dynamic shared memory is per device
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return ILRL_ERR_CUDA;
+  if (!configured[dev]) {
+    if (cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
+      return ILRL_ERR_CUDA;
+    configured[dev] = true;
+  }
+  PolicyArgs a;
+  a.blob = (const uint8_t*)blob_dev; a.obs = obs_dev; a.noise = noise_dev; a.action = action_dev;
+  a.action_clipped = action_clipped_dev; a.logp = logp_dev; a.value = value_dev;
+  a.obs_dim = obs_dim; a.act_dim = act_dim; a.n = n; a.nets = (want_pi ? 1 : 0) | (value_dev ? 2 : 0);
+  policy_kernel<<<(n + TM - 1) / TM, TM, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? ILRL_OK : ILRL_ERR_CUDA;
+}
+
+}  // extern "C"

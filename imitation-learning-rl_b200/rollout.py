@@ -4,13 +4,17 @@ The reference collects PPO sample batches with RLlib rollout workers: per env st
 worker, `env.step`, and at the end of the fragment `compute_advantages` on the host (REF train_config.py:91-113:
 2 x 256 tanh MLP, free log-std, gamma 0.99, lambda 0.9).  Here the whole fragment stays on the GPU:
 
-    for t in 0..T-1:   mean, value = policy(obs)              torch (cuBLAS GEMMs: plain library GEMMs, plumbing)
-                       action = mean + exp(log_std) * eps      torch Philox
-                       obs, reward, done = env.step(clip(a))   ONE fused CUDA kernel (csrc/)
+    for t in 0..T-1:   mean, value = policy(obs)               }  ONE tcgen05 kernel (csrc/ilrl_policy.cu): six GEMMs on
+                       action = mean + exp(log_std) * eps       }  the tensor cores, tanh / sampling / log-prob in the
+                       logp, clip(action)                       }  epilogues, hidden activations never leave the SM
+                       obs, reward, done = env.step(clip(a))   ONE fused CUDA kernel (csrc/ilrl_capi.cu), writing
+                                                               into the [T, N] rollout buffers in place
     advantages, value_targets = GAE(rewards, values, dones)    CUDA kernel (ilrl_gae)
 
-and the T-step loop is captured once into a CUDA graph, so an iteration is one graph launch: no Python, no launch
-gaps, observations and actions never leave HBM.  Output columns follow RLlib's SampleBatch names.
+and the T-step loop (2 launches per step) is captured once into a CUDA graph, so an iteration is one graph launch: no
+Python, no launch gaps, observations and actions never leave HBM.  The noise eps is drawn by torch's Philox, one
+launch per iteration.  `fused=False` keeps the torch module (cuBLAS) as the model.  Output columns follow RLlib's
+SampleBatch names.
 """
 import ctypes as C
 
@@ -40,6 +44,52 @@ class GaussianMLPPolicy(torch.nn.Module):
         return self.pi(obs), self.vf(obs).squeeze(-1)
 
 
+class FusedPolicy:
+    """The GaussianMLPPolicy forward + action sampling as ONE tcgen05 kernel (csrc/ilrl_policy.cu): bf16 operands, fp32
+    accumulation, hidden activations kept on chip.  `repack()` after the parameters change (optimizer step)."""
+
+    def __init__(self, policy):
+        lin = lambda seq: [m for m in seq if isinstance(m, torch.nn.Linear)]  # noqa: E731
+        self.policy, self._pi, self._vf = policy, lin(policy.pi), lin(policy.vf)
+        assert len(self._pi) == 3 and len(self._vf) == 3, "two hidden layers"
+        self.obs_dim, self.act_dim = self._pi[0].in_features, self._pi[2].out_features
+        assert self._pi[0].out_features == 256 and self._pi[1].out_features == 256 and self._vf[2].out_features == 1
+        assert self._vf[0].out_features == 256 and self._vf[1].out_features == 256 and self._vf[0].in_features == self.obs_dim
+        assert self.obs_dim <= 80 and self.act_dim <= 32
+        self.L = _lib.lib()
+        self.device = self._pi[0].weight.device
+        assert self.device.type == "cuda", "the fused policy is a CUDA kernel: move the policy to the GPU first"
+        self.blob = torch.empty(int(self.L.ilrl_policy_blob_bytes()), dtype=torch.uint8, device=self.device)
+        self.repack()
+
+    def _st(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def repack(self):
+        ps = []
+        for net in (self._pi, self._vf):
+            for m in net:
+                ps += [m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous()]
+        ps.append(self.policy.log_std.detach().float().contiguous())
+        rc = self.L.ilrl_policy_pack(*[_ptr(p) for p in ps], self.obs_dim, self.act_dim, _ptr(self.blob), self._st())
+        if rc != 0:
+            raise _lib.IlrlError("ilrl_policy_pack failed (%d)" % rc)
+        self._keep = ps   # alive until the pack kernel has certainly run
+
+    def step(self, obs, noise=None, action=None, action_clipped=None, logp=None, value=None):
+        """Outputs are written into the given contiguous fp32 CUDA tensors (None: not produced)."""
+        n = obs.shape[0]
+        assert obs.is_cuda and obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape == (n, self.obs_dim)
+        for t, shape in ((noise, (n, self.act_dim)), (action, (n, self.act_dim)), (action_clipped, (n, self.act_dim)),
+                         (logp, (n,)), (value, (n,))):
+            assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape)
+        p = lambda t: None if t is None else _ptr(t)  # noqa: E731
+        rc = self.L.ilrl_policy_step(_ptr(self.blob), _ptr(obs), p(noise), p(action), p(action_clipped), p(logp), p(value),
+                                     self.obs_dim, self.act_dim, n, self._st())
+        if rc != 0:
+            raise _lib.IlrlError("ilrl_policy_step failed (%d)" % rc)
+
+
 def gae(rewards, values, dones, gamma, lam, stream=None):
     """advantages, value_targets = GAE over a step-major rollout.  rewards [T,N] f32, values [T+1,N] f32,
     dones [T,N] uint8; all contiguous CUDA tensors."""
@@ -58,30 +108,50 @@ class RolloutCollector:
     """Collects [T, N] fragments from a BatchedHumanoidEnv (mode "low", auto_reset=True) with a policy living on the
     same GPU.  `collect()` returns a dict of step-major device tensors named like RLlib's SampleBatch columns."""
 
-    def __init__(self, env, policy=None, horizon=8, gamma=0.99, lam=0.9, seed=0, use_graph=True, autocast_dtype=None):
+    def __init__(self, env, policy=None, horizon=8, gamma=0.99, lam=0.9, seed=0, use_graph=True, autocast_dtype=None,
+                 fused=True):
         assert isinstance(env, BatchedHumanoidEnv) and env.mode == 0
         self.env, self.T, self.gamma, self.lam = env, int(horizon), float(gamma), float(lam)
-        self.autocast_dtype = autocast_dtype  # e.g. torch.bfloat16: policy GEMMs on the tensor cores (inference only)
+        self.autocast_dtype = autocast_dtype  # torch path only, e.g. torch.bfloat16
         dev, n, T = env.device, env.num_envs, self.T
         self.policy = (policy if policy is not None else GaussianMLPPolicy()).to(dev).eval()
+        # fused=True: model forward + sampling + log-prob are ONE tcgen05 kernel per step (FusedPolicy) and the env
+        # kernel writes into the rollout buffers directly: 2 launches per step.  fused=False: the torch module.
+        self.fused = FusedPolicy(self.policy) if fused else None
         self.gen = torch.Generator(device=dev)
         self.gen.manual_seed(seed)
         f = dict(device=dev, dtype=torch.float32)
-        self.cur_obs = torch.zeros(n, OBS_LOW, **f)
+        self._obs_all = torch.zeros(T + 1, n, OBS_LOW, **f)   # obs = rows 0..T-1, new_obs = rows 1..T
+        self.cur_obs = self._obs_all[T]                       # the observation the next fragment starts from
         self.buf = {
-            "obs": torch.zeros(T, n, OBS_LOW, **f), "new_obs": torch.zeros(T, n, OBS_LOW, **f),
+            "obs": self._obs_all[:T], "new_obs": self._obs_all[1:],
             "actions": torch.zeros(T, n, ACT_LOW, **f), "rewards": torch.zeros(T, n, **f),
             "dones": torch.zeros(T, n, device=dev, dtype=torch.uint8), "action_logp": torch.zeros(T, n, **f),
             "vf_preds": torch.zeros(T + 1, n, **f),
         }
         self._noise = torch.zeros(T, n, ACT_LOW, **f)
+        self._clipped = torch.zeros(n, ACT_LOW, **f)
         self._graph = None
         self._use_graph = use_graph
         self.cur_obs.copy_(env.reset())
 
+    def policy_updated(self):
+        """Call after the policy's parameters changed (optimizer step): re-packs the fused kernel's weights."""
+        if self.fused is not None:
+            self.fused.repack()
+
     @torch.no_grad()
     def _loop(self):
-        b, env = self.buf, self.env
+        b, env, T = self.buf, self.env, self.T
+        self._obs_all[0].copy_(self._obs_all[T])
+        if self.fused is not None:
+            for t in range(T):
+                self.fused.step(self._obs_all[t], self._noise[t], b["actions"][t], self._clipped, b["action_logp"][t],
+                                b["vf_preds"][t])
+                # RLlib clips actions to the Box before env.step (clip_actions=True); the batch keeps the raw sample
+                env.step_into(self._clipped, self._obs_all[t + 1], b["rewards"][t], b["dones"][t])
+            self.fused.step(self._obs_all[T], value=b["vf_preds"][T])
+            return
         std = self.policy.log_std.exp()
         def forward(obs):
             if self.autocast_dtype is None:
@@ -89,20 +159,15 @@ class RolloutCollector:
             with torch.autocast("cuda", dtype=self.autocast_dtype):
                 m, v = self.policy(obs)
             return m.float(), v.float()
-        for t in range(self.T):
-            mean, v = forward(self.cur_obs)
+        for t in range(T):
+            mean, v = forward(self._obs_all[t])
             a = mean + std * self._noise[t]
-            b["obs"][t].copy_(self.cur_obs)
             b["actions"][t].copy_(a)
             b["vf_preds"][t].copy_(v)
             b["action_logp"][t].copy_((-0.5 * self._noise[t] ** 2 - self.policy.log_std - 0.9189385332046727).sum(-1))
-            # RLlib clips actions to the Box before env.step (clip_actions=True); the batch keeps the raw sample
-            obs, rew, done, _ = env.step(a.clamp(-1.0, 1.0))
-            b["new_obs"][t].copy_(obs)
-            b["rewards"][t].copy_(rew)
-            b["dones"][t].copy_(done)
-            self.cur_obs.copy_(obs)
-        b["vf_preds"][self.T].copy_(forward(self.cur_obs)[1])
+            self._clipped.copy_(a.clamp(-1.0, 1.0))
+            env.step_into(self._clipped, self._obs_all[t + 1], b["rewards"][t], b["dones"][t])
+        b["vf_preds"][T].copy_(forward(self._obs_all[T])[1])
 
     @torch.no_grad()
     def collect(self):
@@ -118,7 +183,7 @@ class RolloutCollector:
                 saved = [t.clone() for t in self.env.get_state()] + [self.cur_obs.clone()]
                 self._loop()
                 self.env.set_state(saved[0], saved[1])
-                self.cur_obs.copy_(saved[2])
+                self.cur_obs.copy_(saved[2])   # = row T of the observation buffer, which the captured loop reads first
             torch.cuda.current_stream(self.env.device).wait_stream(s)
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):

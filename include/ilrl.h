@@ -126,6 +126,28 @@ int ilrl_stats(ilrl_env* env, float* stats16_dev, void* stream);
 int ilrl_gae(const float* reward_dev, const float* value_dev, const uint8_t* done_dev, float gamma, float lambda_,
              float* advantage_dev, float* value_target_dev, int32_t T, int32_t n, void* stream);
 
+/* ---- fused policy / value forward for on-device rollout collection -------------------
+ * Replaces the per-step model forward + action sampling RLlib does around env.step for the reference's policies
+ * (REF train_config.py:91-113 low level 70-256-256-17, :262-286 high level 44-256-256-2: fcnet_hiddens [256, 256],
+ * tanh, free log-std, separate value branch).  tcgen05 tensor-core kernel, bf16 operands, fp32 accumulation.
+ * No handle: pure functions of their arguments, asynchronous on `stream`; every pointer is a device pointer.
+ *
+ * ilrl_policy_pack: fp32 parameters in torch.nn.Linear layout ([out, in] row major; w1 [256, obs_dim], w2 [256, 256],
+ * w3_pi [act_dim, 256], w3_vf [1, 256], log_std [act_dim]) -> the packed blob (ilrl_policy_blob_bytes() bytes, 16-byte
+ * aligned) the step reads.  obs_dim <= 80, act_dim <= 32.  Repack after every optimizer update.
+ * ilrl_policy_step, for n envs: mean, value = model(obs); a = mean + exp(log_std) * noise (noise NULL: a = mean);
+ * writes action [n, act_dim] (raw sample), action_clipped = clip(a, -1, 1) (what env.step consumes, RLlib
+ * clip_actions=True), logp [n] (diagonal Gaussian log-density of a) and value [n].  Any output may be NULL; with all
+ * three policy outputs NULL only the value net runs (bootstrap value of the last observation). */
+int64_t ilrl_policy_blob_bytes(void);
+int ilrl_policy_pack(const float* w1_pi, const float* b1_pi, const float* w2_pi, const float* b2_pi, const float* w3_pi,
+                     const float* b3_pi, const float* w1_vf, const float* b1_vf, const float* w2_vf, const float* b2_vf,
+                     const float* w3_vf, const float* b3_vf, const float* log_std, int32_t obs_dim, int32_t act_dim,
+                     void* blob_dev, void* stream);
+int ilrl_policy_step(const void* blob_dev, const float* obs_dev, const float* noise_dev, float* action_dev,
+                     float* action_clipped_dev, float* logp_dev, float* value_dev, int32_t obs_dim, int32_t act_dim,
+                     int32_t n, void* stream);
+
 /* How many kernels of this library have been launched through the handle (bench.py "gpu_launches"). */
 int64_t ilrl_launch_count(const ilrl_env* env);
 /* Time of the step kernels only, measured with CUDA events on `stream` around each ilrl_step since the last call:

@@ -29,6 +29,7 @@
 namespace {
 
 constexpr int TM = 128;    // envs per CTA
+constexpr int NT = 256;    // threads per CTA: two per env row, each owning half of the 256 hidden columns
 constexpr int HID = 256;   // hidden width
 constexpr int K1 = 80;     // observation width padded to a multiple of 16 (70 low level, 44 high level)
 constexpr int N3 = 32;     // output width padded (17 / 2 action means, 1 value)
@@ -66,10 +67,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       __trap();
     }
 }
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  mbar_expect_tx(bar, bytes);
+__device__ __forceinline__ void bulk_copy(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(__cvta_generic_to_global(src)), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  mbar_expect_tx(bar, bytes);
+  bulk_copy(dst, src, bytes, bar);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -101,7 +105,8 @@ __device__ __forceinline__ void gemm(uint32_t tmem_d, uint32_t a_s, uint32_t b_s
   for (int k = 0; k < ksteps; ++k)   // descriptor address field is in 16-byte units: one K step = 32 * rows bytes
     umma(tmem_d, ad + (uint64_t)(k * 2 * TM), bd + (uint64_t)(k * 2 * n), idesc, k > 0);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+// Issue only: the registers are valid after tmem_wait(v), which also ties them to the wait for the compiler.
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
       "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
@@ -110,7 +115,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_wait(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :: "memory");
 }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
@@ -122,23 +134,34 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-// accumulators [128 x 256] at `taddr` -> tanh(x + bias) -> bf16 A operand image H (this thread's row).
-__device__ __forceinline__ void epilogue_hidden(uint32_t taddr, const float* bias, uint8_t* H, int row) {
-#pragma unroll 1
-  for (int c = 0; c < HID / 32; ++c) {
-    uint32_t v[32];
-    tmem_ld32(taddr + 32 * c, v);
+// 32 accumulator columns of this thread's row -> tanh(x + bias) -> four 16-byte k-groups of the bf16 A operand image
+__device__ __forceinline__ void hidden_chunk(const uint32_t (&v)[32], int c, const float* bias, uint8_t* H, int row) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      uint32_t p[4];
+  for (int q = 0; q < 4; ++q) {
+    uint32_t p[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int col = 32 * c + 8 * q + 2 * j;
-        p[j] = pack_bf16(tanh_fast(__uint_as_float(v[8 * q + 2 * j]) + bias[col]),
-                         tanh_fast(__uint_as_float(v[8 * q + 2 * j + 1]) + bias[col + 1]));
-      }
-      *reinterpret_cast<uint4*>(H + ((4 * c + q) * TM + row) * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+    for (int j = 0; j < 4; ++j) {
+      const int col = 32 * c + 8 * q + 2 * j;
+      p[j] = pack_bf16(tanh_fast(__uint_as_float(v[8 * q + 2 * j]) + bias[col]),
+                       tanh_fast(__uint_as_float(v[8 * q + 2 * j + 1]) + bias[col + 1]));
     }
+    *reinterpret_cast<uint4*>(H + ((4 * c + q) * TM + row) * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+  }
+}
+// accumulators [128 x 256] at `taddr` -> next layer's A operand H (this thread's row); the TMEM load of the next 32
+// columns is in flight while the current 32 are processed.
+__device__ __forceinline__ void epilogue_hidden(uint32_t taddr, const float* bias, uint8_t* H, int row, int half) {
+  uint32_t va[32], vb[32];
+  const int c0 = half * (HID / 64), c1 = c0 + HID / 64;   // this thread's 128 columns = 4 chunks of 32
+  tmem_ld32_issue(taddr + 32 * c0, va);
+#pragma unroll 1
+  for (int c = c0; c < c1; c += 2) {
+    tmem_wait(va);
+    tmem_ld32_issue(taddr + 32 * (c + 1), vb);
+    hidden_chunk(va, c, bias, H, row);
+    tmem_wait(vb);
+    if (c + 2 < c1) tmem_ld32_issue(taddr + 32 * (c + 2), va);
+    hidden_chunk(vb, c + 1, bias, H, row);
   }
 }
 
@@ -153,33 +176,55 @@ struct PolicyArgs {
   int obs_dim, act_dim, n, nets;
 };
 
-__global__ void __launch_bounds__(TM, 1) policy_kernel(const PolicyArgs A) {
+__global__ void __launch_bounds__(NT, 1) policy_kernel(const PolicyArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int row = tid, env = blockIdx.x * TM + row;
+  const int row = tid & (TM - 1), half = tid >> 7, env = blockIdx.x * TM + row;
   float* bias_s = reinterpret_cast<float*>(smem + S_BIAS);
   float* logstd_s = reinterpret_cast<float*>(smem + S_LOGSTD);
-  const uint32_t bar_full0 = smem_u32(smem + S_BAR), bar_full1 = bar_full0 + 8, bar_mma = bar_full0 + 16;
+  const uint32_t bar_full0 = smem_u32(smem + S_BAR), bar_full1 = bar_full0 + 8, bar_mma = bar_full0 + 16, bar_in = bar_full0 + 24;
   const uint32_t sH = smem_u32(smem + S_H), sA0 = smem_u32(smem + S_A0), sB0 = smem_u32(smem + S_B0), sB1 = smem_u32(smem + S_B1);
   const int first = (A.nets & 1) ? 0 : 1, last = (A.nets & 2) ? 1 : 0;
 
+  // A full, 16-byte aligned tile of observations is bulk-copied as raw fp32 into the (still unused) H region and
+  // converted from there; a ragged last tile or an unaligned tensor is read with plain loads.
+  const int rows = min(TM, A.n - blockIdx.x * TM);
+  const float* src = A.obs + (size_t)blockIdx.x * TM * A.obs_dim;
+  const bool fast = rows == TM && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+  constexpr uint32_t CONST_BYTES = (2 * BIAS_WORDS + N3) * 4;   // biases of both nets, then log-std: contiguous in both
   if (tid == 0) {
-    mbar_init(bar_full0, 1); mbar_init(bar_full1, 1); mbar_init(bar_mma, 1);
+    mbar_init(bar_full0, 1); mbar_init(bar_full1, 1); mbar_init(bar_mma, 1); mbar_init(bar_in, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    const uint32_t tile_bytes = (uint32_t)(TM * A.obs_dim * 4);
+    mbar_expect_tx(bar_in, CONST_BYTES + (fast ? tile_bytes : 0u));
+    bulk_copy(smem_u32(smem + S_BIAS), A.blob + BLOB_BIAS, CONST_BYTES, bar_in);
+    if (fast) bulk_copy(sH, src, tile_bytes, bar_in);
+    bulk_load(sB0, A.blob + first * NET_BYTES, W1_BYTES, bar_full0);
+    bulk_load(sB1, A.blob + first * NET_BYTES + W1_BYTES, W2H_BYTES, bar_full1);
   }
+  __syncwarp();
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem + S_TMEM)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  // observation tile -> bf16 A operand image (zero padded in k and for rows past n); biases and log-std
-  for (int i = tid; i < TM * K1 / 8; i += TM) *reinterpret_cast<uint4*>(smem + S_A0 + i * 16) = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 2 * (int)BIAS_WORDS + N3; i += TM)
-    bias_s[i] = reinterpret_cast<const float*>(A.blob + BLOB_BIAS)[i];   // log-std follows the biases in both
-  __syncthreads();
-  {
-    const int rows = min(TM, A.n - blockIdx.x * TM);
-    const float* src = A.obs + (size_t)blockIdx.x * TM * A.obs_dim;
-    for (int i = tid; i < rows * A.obs_dim; i += TM) {   // coalesced read of the contiguous tile
+  if (!fast)
+    for (int i = tid; i < TM * K1 / 8; i += NT) *reinterpret_cast<uint4*>(smem + S_A0 + i * 16) = make_uint4(0, 0, 0, 0);
+  __syncthreads();   // barrier inits visible to every thread; zero fill complete
+  mbar_wait(bar_in, 0);
+  // observation tile -> bf16 A operand image, zero padded in k (and for the rows past n)
+  if (fast) {
+    const float* rp = reinterpret_cast<const float*>(smem + S_H) + row * A.obs_dim;
+#pragma unroll
+    for (int kk = 0; kk < K1 / 16; ++kk) {
+      const int kg = half * (K1 / 16) + kk;
+      float x[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) x[e] = kg * 8 + e < A.obs_dim ? rp[kg * 8 + e] : 0.f;
+      *reinterpret_cast<uint4*>(smem + S_A0 + (kg * TM + row) * 16) =
+          make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+    }
+  } else {
+    for (int i = tid; i < rows * A.obs_dim; i += NT) {   // coalesced read of the contiguous tile
       const int r = i / A.obs_dim, k = i - r * A.obs_dim;
       *reinterpret_cast<__nv_bfloat16*>(smem + S_A0 + ((k >> 3) * TM + r) * 16 + (k & 7) * 2) = __float2bfloat16_rn(src[i]);
     }
@@ -189,14 +234,12 @@ __global__ void __launch_bounds__(TM, 1) policy_kernel(const PolicyArgs A) {
   __syncthreads();
   tc_after();
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
-  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);   // this warp's 32 TMEM lanes = its 32 rows
+  const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp reaches TMEM lanes 32 (warp % 4) ..: its rows
 
   uint32_t ph0 = 0, ph1 = 0, phm = 0;   // ph0 / ph1 are used by thread 0 only
-  if (tid == 0) {
-    bulk_load(sB0, A.blob + first * NET_BYTES, W1_BYTES, bar_full0);
-    bulk_load(sB1, A.blob + first * NET_BYTES + W1_BYTES, W2H_BYTES, bar_full1);
-  }
-  __syncwarp();
+  float z[N3];                          // this env's noise row, fetched while layer 3 of the policy net runs
+#pragma unroll
+  for (int j = 0; j < N3; ++j) z[j] = 0.f;
 
   for (int net = first; net <= last; ++net) {
     const uint8_t* wb = A.blob + net * NET_BYTES;
@@ -214,7 +257,7 @@ __global__ void __launch_bounds__(TM, 1) policy_kernel(const PolicyArgs A) {
     tc_after();
     if (tid == 0) bulk_load(sB0, wb + W1_BYTES + W2H_BYTES, W2H_BYTES, bar_full0);   // second half of W2
     __syncwarp();
-    epilogue_hidden(tlane, bs, smem + S_H, row);
+    epilogue_hidden(tlane, bs, smem + S_H, row, half);
     fence_proxy_async();
     tc_before();
     __syncthreads();
@@ -235,7 +278,7 @@ __global__ void __launch_bounds__(TM, 1) policy_kernel(const PolicyArgs A) {
       if (has_next) bulk_load(sB0, wb + NET_BYTES, W1_BYTES, bar_full0);
     }
     __syncwarp();
-    epilogue_hidden(tlane + 256, bs + HID, smem + S_H, row);
+    epilogue_hidden(tlane + 256, bs + HID, smem + S_H, row, half);
     fence_proxy_async();
     tc_before();
     __syncthreads();
@@ -247,13 +290,19 @@ __global__ void __launch_bounds__(TM, 1) policy_kernel(const PolicyArgs A) {
       umma_commit(bar_mma);
     }
     __syncwarp();
+    if (net == 0 && half == 0 && A.noise && env < A.n) {
+#pragma unroll
+      for (int j = 0; j < N3; ++j)
+        if (j < A.act_dim) z[j] = A.noise[(size_t)env * A.act_dim + j];
+    }
     mbar_wait(bar_mma, phm); phm ^= 1;
     tc_after();
     if (tid == 0 && has_next) bulk_load(sB1, wb + NET_BYTES + W1_BYTES, W2H_BYTES, bar_full1);
     __syncwarp();
-    {
+    if (half == 0) {   // warp-uniform: warps 0..3 own the 128 rows of the narrow output layer
       uint32_t v[32];
-      tmem_ld32(tlane, v);
+      tmem_ld32_issue(tlane, v);
+      tmem_wait(v);
       if (env < A.n) {
         if (net == 0) {
           float lp = 0.f;
@@ -261,11 +310,10 @@ __global__ void __launch_bounds__(TM, 1) policy_kernel(const PolicyArgs A) {
           for (int j = 0; j < N3; ++j)
             if (j < A.act_dim) {
               const float mean = __uint_as_float(v[j]) + bs[2 * HID + j];
-              const float z = A.noise ? A.noise[(size_t)env * A.act_dim + j] : 0.f;
-              const float a = fmaf(__expf(logstd_s[j]), z, mean);
+              const float a = fmaf(__expf(logstd_s[j]), z[j], mean);
               if (A.action) A.action[(size_t)env * A.act_dim + j] = a;
               if (A.action_clipped) A.action_clipped[(size_t)env * A.act_dim + j] = fminf(fmaxf(a, -1.f), 1.f);
-              lp += -0.5f * z * z - logstd_s[j] - 0.9189385332046727f;
+              lp += -0.5f * z[j] * z[j] - logstd_s[j] - 0.9189385332046727f;
             }
           if (A.logp) A.logp[env] = lp;
         } else {
@@ -350,7 +398,7 @@ int ilrl_policy_step(const void* blob_dev, const float* obs_dev, const float* no
   a.blob = (const uint8_t*)blob_dev; a.obs = obs_dev; a.noise = noise_dev; a.action = action_dev;
   a.action_clipped = action_clipped_dev; a.logp = logp_dev; a.value = value_dev;
   a.obs_dim = obs_dim; a.act_dim = act_dim; a.n = n; a.nets = (want_pi ? 1 : 0) | (value_dev ? 2 : 0);
-  policy_kernel<<<(n + TM - 1) / TM, TM, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  policy_kernel<<<(n + TM - 1) / TM, NT, SMEM_BYTES, (cudaStream_t)stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? ILRL_OK : ILRL_ERR_CUDA;
 }
 

@@ -41,7 +41,7 @@ constexpr uint32_t BLOB_BIAS = 2 * NET_BYTES, BLOB_LOGSTD = BLOB_BIAS + 2 * BIAS
 // shared memory map
 constexpr uint32_t S_H = 0, S_A0 = S_H + TM * HID * 2, S_B0 = S_A0 + TM * K1 * 2, S_B1 = S_B0 + W2H_BYTES,
                    S_BIAS = S_B1 + W2H_BYTES, S_LOGSTD = S_BIAS + 2 * BIAS_WORDS * 4, S_BAR = S_LOGSTD + N3 * 4,
-                   S_TMEM = S_BAR + 32, SMEM_BYTES = S_TMEM + 16;
+                   S_TMEM = S_BAR + 64, SMEM_BYTES = S_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(W1_BYTES <= W2H_BYTES && W3_BYTES <= W2H_BYTES, "weight chunks must fit a buffer");
 
@@ -51,6 +51,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -98,12 +101,13 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t b
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-// D[128 x n] (+)= A[128 x 16 ksteps] * B[n x 16 ksteps]^T; A image has 128 rows, B image has n rows.
-__device__ __forceinline__ void gemm(uint32_t tmem_d, uint32_t a_s, uint32_t b_s, uint32_t n, int ksteps) {
+// D[128 x n] (+)= A[:, 16 k0 .. 16 k1) * B[:, 16 k0 .. 16 k1)^T; A image has 128 rows, B image has n rows.  `fresh`: the
+// first of these K steps overwrites D instead of accumulating.
+__device__ __forceinline__ void gemm(uint32_t tmem_d, uint32_t a_s, uint32_t b_s, uint32_t n, int k0, int k1, bool fresh) {
   const uint32_t idesc = umma_idesc(n);
   const uint64_t ad = umma_desc(a_s, TM), bd = umma_desc(b_s, n);
-  for (int k = 0; k < ksteps; ++k)   // descriptor address field is in 16-byte units: one K step = 32 * rows bytes
-    umma(tmem_d, ad + (uint64_t)(k * 2 * TM), bd + (uint64_t)(k * 2 * n), idesc, k > 0);
+  for (int k = k0; k < k1; ++k)   // descriptor address field is in 16-byte units: one K step = 32 * rows bytes
+    umma(tmem_d, ad + (uint64_t)(k * 2 * TM), bd + (uint64_t)(k * 2 * n), idesc, !(fresh && k == k0));
 }
 // Issue only: the registers are valid after tmem_wait(v), which also ties them to the wait for the compiler.
 __device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&v)[32]) {
@@ -134,34 +138,48 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&p);
 }
 
-// 32 accumulator columns of this thread's row -> tanh(x + bias) -> four 16-byte k-groups of the bf16 A operand image
+// 32 accumulator columns of this thread's row -> tanh(x + bias) -> four 16-byte k-groups of the bf16 A operand image.
+// The biases are read (8 x LDS.128, same address in every lane) BEFORE any store: a shared-memory load cannot be moved
+// above a shared-memory store by the compiler, and interleaving them serialises load -> tanh -> store latencies.
 __device__ __forceinline__ void hidden_chunk(const uint32_t (&v)[32], int c, const float* bias, uint8_t* H, int row) {
+  float4 b[8];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    uint32_t p[4];
+  for (int q = 0; q < 8; ++q) b[q] = *reinterpret_cast<const float4*>(bias + 32 * c + 4 * q);
+  uint32_t p[16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int col = 32 * c + 8 * q + 2 * j;
-      p[j] = pack_bf16(tanh_fast(__uint_as_float(v[8 * q + 2 * j]) + bias[col]),
-                       tanh_fast(__uint_as_float(v[8 * q + 2 * j + 1]) + bias[col + 1]));
-    }
-    *reinterpret_cast<uint4*>(H + ((4 * c + q) * TM + row) * 16) = make_uint4(p[0], p[1], p[2], p[3]);
+  for (int q = 0; q < 8; ++q) {
+    p[2 * q] = pack_bf16(tanh_fast(__uint_as_float(v[4 * q]) + b[q].x), tanh_fast(__uint_as_float(v[4 * q + 1]) + b[q].y));
+    p[2 * q + 1] = pack_bf16(tanh_fast(__uint_as_float(v[4 * q + 2]) + b[q].z), tanh_fast(__uint_as_float(v[4 * q + 3]) + b[q].w));
   }
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(H + ((4 * c + q) * TM + row) * 16) = make_uint4(p[4 * q], p[4 * q + 1], p[4 * q + 2], p[4 * q + 3]);
 }
-// accumulators [128 x 256] at `taddr` -> next layer's A operand H (this thread's row); the TMEM load of the next 32
-// columns is in flight while the current 32 are processed.
-__device__ __forceinline__ void epilogue_hidden(uint32_t taddr, const float* bias, uint8_t* H, int row, int half) {
+// accumulators [128 x 256] at `taddr` -> next layer's A operand H.  A thread owns one row and 128 columns = 4 chunks of
+// 32; the TMEM load of the next chunk is in flight while the current one is processed.  After writing chunk i every
+// thread arrives on mbarrier `bar_chunk + 8 i` and carries on; `consume(i)` (thread 0 waits for all 256 arrivals there)
+// issues the next layer's K steps over exactly those columns — {2i, 2i+1} and {8+2i, 8+2i+1} — so that layer's
+// tensor-core time hides under this epilogue and no warp but the issuing one ever waits for a slower warp.
+template <class F>
+__device__ __forceinline__ void epilogue_hidden(uint32_t taddr, const float* bias, uint8_t* H, int row, int half,
+                                                uint32_t bar_chunk, F&& consume) {
   uint32_t va[32], vb[32];
-  const int c0 = half * (HID / 64), c1 = c0 + HID / 64;   // this thread's 128 columns = 4 chunks of 32
+  const int c0 = half * (HID / 64);
   tmem_ld32_issue(taddr + 32 * c0, va);
-#pragma unroll 1
-  for (int c = c0; c < c1; c += 2) {
+#pragma unroll
+  for (int i = 0; i < HID / 64; i += 2) {
     tmem_wait(va);
-    tmem_ld32_issue(taddr + 32 * (c + 1), vb);
-    hidden_chunk(va, c, bias, H, row);
+    tmem_ld32_issue(taddr + 32 * (c0 + i + 1), vb);
+    hidden_chunk(va, c0 + i, bias, H, row);
+    fence_proxy_async();   // generic-proxy stores of this thread -> visible to the tensor core's async-proxy reads
+    mbar_arrive(bar_chunk + 8 * i);
+    consume(i);
     tmem_wait(vb);
-    if (c + 2 < c1) tmem_ld32_issue(taddr + 32 * (c + 2), va);
-    hidden_chunk(vb, c + 1, bias, H, row);
+    if (i + 2 < HID / 64) tmem_ld32_issue(taddr + 32 * (c0 + i + 2), va);
+    hidden_chunk(vb, c0 + i + 1, bias, H, row);
+    fence_proxy_async();
+    mbar_arrive(bar_chunk + 8 * (i + 1));
+    consume(i + 1);
   }
 }
 
@@ -174,7 +192,10 @@ struct PolicyArgs {
   float* logp;           // [n] or null
   float* value;          // [n] or null (skips the value net)
   int obs_dim, act_dim, n, nets;
+  long long* timeline;   // harness: block 0 / thread 0 stamps clock64() at phase boundaries (null in normal use)
 };
+
+#define STAMP(i) do { if (A.timeline && blockIdx.x == 0 && tid == 0) A.timeline[i] = clock64(); } while (0)
 
 __global__ void __launch_bounds__(NT, 1) policy_kernel(const PolicyArgs A) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -182,25 +203,27 @@ __global__ void __launch_bounds__(NT, 1) policy_kernel(const PolicyArgs A) {
   const int row = tid & (TM - 1), half = tid >> 7, env = blockIdx.x * TM + row;
   float* bias_s = reinterpret_cast<float*>(smem + S_BIAS);
   float* logstd_s = reinterpret_cast<float*>(smem + S_LOGSTD);
-  const uint32_t bar_full0 = smem_u32(smem + S_BAR), bar_full1 = bar_full0 + 8, bar_mma = bar_full0 + 16, bar_in = bar_full0 + 24;
+  const uint32_t bar_full0 = smem_u32(smem + S_BAR), bar_full1 = bar_full0 + 8, bar_mma = bar_full0 + 16, bar_in = bar_full0 + 24,
+                 bar_chunk = bar_full0 + 32;   // four of them, one per 32-column chunk of a hidden epilogue
   const uint32_t sH = smem_u32(smem + S_H), sA0 = smem_u32(smem + S_A0), sB0 = smem_u32(smem + S_B0), sB1 = smem_u32(smem + S_B1);
   const int first = (A.nets & 1) ? 0 : 1, last = (A.nets & 2) ? 1 : 0;
 
   // A full, 16-byte aligned tile of observations is bulk-copied as raw fp32 into the (still unused) H region and
   // converted from there; a ragged last tile or an unaligned tensor is read with plain loads.
+  STAMP(0);
   const int rows = min(TM, A.n - blockIdx.x * TM);
   const float* src = A.obs + (size_t)blockIdx.x * TM * A.obs_dim;
   const bool fast = rows == TM && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
   constexpr uint32_t CONST_BYTES = (2 * BIAS_WORDS + N3) * 4;   // biases of both nets, then log-std: contiguous in both
   if (tid == 0) {
     mbar_init(bar_full0, 1); mbar_init(bar_full1, 1); mbar_init(bar_mma, 1); mbar_init(bar_in, 1);
+    for (int i = 0; i < HID / 64; ++i) mbar_init(bar_chunk + 8 * i, NT);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     const uint32_t tile_bytes = (uint32_t)(TM * A.obs_dim * 4);
     mbar_expect_tx(bar_in, CONST_BYTES + (fast ? tile_bytes : 0u));
-    bulk_copy(smem_u32(smem + S_BIAS), A.blob + BLOB_BIAS, CONST_BYTES, bar_in);
     if (fast) bulk_copy(sH, src, tile_bytes, bar_in);
+    bulk_copy(smem_u32(smem + S_BIAS), A.blob + BLOB_BIAS, CONST_BYTES, bar_in);
     bulk_load(sB0, A.blob + first * NET_BYTES, W1_BYTES, bar_full0);
-    bulk_load(sB1, A.blob + first * NET_BYTES + W1_BYTES, W2H_BYTES, bar_full1);
   }
   __syncwarp();
   if (warp == 0) {
@@ -210,7 +233,9 @@ __global__ void __launch_bounds__(NT, 1) policy_kernel(const PolicyArgs A) {
   if (!fast)
     for (int i = tid; i < TM * K1 / 8; i += NT) *reinterpret_cast<uint4*>(smem + S_A0 + i * 16) = make_uint4(0, 0, 0, 0);
   __syncthreads();   // barrier inits visible to every thread; zero fill complete
+  STAMP(1);
   mbar_wait(bar_in, 0);
+  STAMP(2);
   // observation tile -> bf16 A operand image, zero padded in k (and for the rows past n)
   if (fast) {
     const float* rp = reinterpret_cast<const float*>(smem + S_H) + row * A.obs_dim;
@@ -236,11 +261,19 @@ __global__ void __launch_bounds__(NT, 1) policy_kernel(const PolicyArgs A) {
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + S_TMEM);
   const uint32_t tlane = tmem + ((uint32_t)((warp & 3) * 32) << 16);   // a warp reaches TMEM lanes 32 (warp % 4) ..: its rows
 
-  uint32_t ph0 = 0, ph1 = 0, phm = 0;   // ph0 / ph1 are used by thread 0 only
-  float z[N3];                          // this env's noise row, fetched while layer 3 of the policy net runs
-#pragma unroll
-  for (int j = 0; j < N3; ++j) z[j] = 0.f;
+  uint32_t ph0 = 0, ph1 = 0, phm = 0, phc = 0;   // ph0 / ph1 / phc are used by thread 0 only
+  // (all CTAs start together: the 64 KB second-layer chunk is requested only now, behind the inputs of layer 1)
+  if (tid == 0) bulk_load(sB1, A.blob + first * NET_BYTES + W1_BYTES, W2H_BYTES, bar_full1);
+  __syncwarp();
+  // noise tile: bulk-copied (full, aligned tiles) into the upper part of buffer 0, which is free whenever a W1 chunk
+  // (40 KB of the 64) or nothing lives there; otherwise read with plain loads in the output epilogue
+  const float* noise_src = A.noise ? A.noise + (size_t)blockIdx.x * TM * A.act_dim : nullptr;
+  const bool noise_bulk = noise_src && rows == TM && (reinterpret_cast<uintptr_t>(noise_src) & 15) == 0;
+  const float* noise_s = reinterpret_cast<const float*>(smem + S_B0 + W1_BYTES);
+  float* stage_a = reinterpret_cast<float*>(smem + S_H);                 // output staging (H is free after layer 3)
+  float* stage_c = reinterpret_cast<float*>(smem + S_H + TM * N3 * 4);
 
+  STAMP(3);
   for (int net = first; net <= last; ++net) {
     const uint8_t* wb = A.blob + net * NET_BYTES;
     const float* bs = bias_s + net * BIAS_WORDS;
@@ -249,80 +282,122 @@ __global__ void __launch_bounds__(NT, 1) policy_kernel(const PolicyArgs A) {
     if (tid == 0) {
       mbar_wait(bar_full0, ph0); ph0 ^= 1;
       tc_after();
-      gemm(tmem, sA0, sB0, HID, K1 / 16);
+      STAMP(4 + 8 * net);
+      gemm(tmem, sA0, sB0, HID, 0, K1 / 16, true);
       umma_commit(bar_mma);
     }
     __syncwarp();
     mbar_wait(bar_mma, phm); phm ^= 1;
     tc_after();
+    STAMP(5 + 8 * net);
     if (tid == 0) bulk_load(sB0, wb + W1_BYTES + W2H_BYTES, W2H_BYTES, bar_full0);   // second half of W2
     __syncwarp();
-    epilogue_hidden(tlane, bs, smem + S_H, row, half);
-    fence_proxy_async();
-    tc_before();
-    __syncthreads();
-    // layer 2: D[256..383] = H * W2[0..127]^T (buffer 1), D[384..511] = H * W2[128..255]^T (buffer 0)
-    if (tid == 0) {
-      tc_after();
-      mbar_wait(bar_full1, ph1); ph1 ^= 1;
-      gemm(tmem + 256, sH, sB1, 128, HID / 16);
-      mbar_wait(bar_full0, ph0); ph0 ^= 1;
-      gemm(tmem + 384, sH, sB0, 128, HID / 16);
-      umma_commit(bar_mma);
-    }
-    __syncwarp();
+    // layer 1 epilogue, with layer 2 issued slice by slice underneath it:
+    // D[256..383] = H * W2[0..127]^T (buffer 1), D[384..511] = H * W2[128..255]^T (buffer 0)
+    epilogue_hidden(tlane, bs, smem + S_H, row, half, bar_chunk, [&](int i) {
+      if (tid == 0) {
+        mbar_wait(bar_chunk + 8 * i, phc);
+        tc_after();
+        if (i == 0) { mbar_wait(bar_full1, ph1); ph1 ^= 1; mbar_wait(bar_full0, ph0); ph0 ^= 1; }
+        gemm(tmem + 256, sH, sB1, 128, 2 * i, 2 * i + 2, i == 0);
+        gemm(tmem + 256, sH, sB1, 128, 8 + 2 * i, 8 + 2 * i + 2, false);
+        gemm(tmem + 384, sH, sB0, 128, 2 * i, 2 * i + 2, i == 0);
+        gemm(tmem + 384, sH, sB0, 128, 8 + 2 * i, 8 + 2 * i + 2, false);
+        if (i == HID / 64 - 1) umma_commit(bar_mma);
+      }
+      __syncwarp();
+    });
+    phc ^= 1;
+    STAMP(6 + 8 * net);
     mbar_wait(bar_mma, phm); phm ^= 1;
     tc_after();
+    STAMP(7 + 8 * net);
     if (tid == 0) {
       bulk_load(sB1, wb + W1_BYTES + 2 * W2H_BYTES, W3_BYTES, bar_full1);
       if (has_next) bulk_load(sB0, wb + NET_BYTES, W1_BYTES, bar_full0);
+      if (net == 0 && noise_bulk) bulk_load(sB0 + W1_BYTES, noise_src, (uint32_t)(TM * A.act_dim * 4), bar_in);
     }
     __syncwarp();
-    epilogue_hidden(tlane + 256, bs + HID, smem + S_H, row, half);
-    fence_proxy_async();
-    tc_before();
-    __syncthreads();
-    // layer 3: D[0..31] = H * W3^T (buffer 1)
-    if (tid == 0) {
-      tc_after();
-      mbar_wait(bar_full1, ph1); ph1 ^= 1;
-      gemm(tmem, sH, sB1, N3, HID / 16);
-      umma_commit(bar_mma);
-    }
-    __syncwarp();
-    if (net == 0 && half == 0 && A.noise && env < A.n) {
-#pragma unroll
-      for (int j = 0; j < N3; ++j)
-        if (j < A.act_dim) z[j] = A.noise[(size_t)env * A.act_dim + j];
-    }
+    // layer 2 epilogue, with layer 3 underneath: D[0..31] = H * W3^T (buffer 1)
+    epilogue_hidden(tlane + 256, bs + HID, smem + S_H, row, half, bar_chunk, [&](int i) {
+      if (tid == 0) {
+        mbar_wait(bar_chunk + 8 * i, phc);
+        tc_after();
+        if (i == 0) { mbar_wait(bar_full1, ph1); ph1 ^= 1; }
+        gemm(tmem, sH, sB1, N3, 2 * i, 2 * i + 2, i == 0);
+        gemm(tmem, sH, sB1, N3, 8 + 2 * i, 8 + 2 * i + 2, false);
+        if (i == HID / 64 - 1) umma_commit(bar_mma);
+      }
+      __syncwarp();
+    });
+    phc ^= 1;
+    STAMP(8 + 8 * net);
     mbar_wait(bar_mma, phm); phm ^= 1;
     tc_after();
+    STAMP(9 + 8 * net);
     if (tid == 0 && has_next) bulk_load(sB1, wb + NET_BYTES + W1_BYTES, W2H_BYTES, bar_full1);
     __syncwarp();
+    if (net == 0) STAMP(20);
     if (half == 0) {   // warp-uniform: warps 0..3 own the 128 rows of the narrow output layer
       uint32_t v[32];
       tmem_ld32_issue(tlane, v);
+      if (net == 0 && noise_bulk) mbar_wait(bar_in, 1);
+      if (net == 0) STAMP(21);
       tmem_wait(v);
-      if (env < A.n) {
-        if (net == 0) {
-          float lp = 0.f;
+      if (net == 0) STAMP(22);
+      if (net == 0) {   // sample, clip, log-density; the action tiles are staged in shared memory (row stride act_dim)
+        // branch-free over the padded width so that every load is issued before the first dependent use
+        float mean[N3], z[N3], ls[N3];
+#pragma unroll
+        for (int j = 0; j < N3; ++j) {
+          mean[j] = __uint_as_float(v[j]) + bs[2 * HID + j];
+          ls[j] = logstd_s[j];
+          z[j] = noise_bulk ? noise_s[row * A.act_dim + min(j, A.act_dim - 1)] : 0.f;
+        }
+        if (!noise_bulk && noise_src && env < A.n) {
 #pragma unroll
           for (int j = 0; j < N3; ++j)
-            if (j < A.act_dim) {
-              const float mean = __uint_as_float(v[j]) + bs[2 * HID + j];
-              const float a = fmaf(__expf(logstd_s[j]), z[j], mean);
-              if (A.action) A.action[(size_t)env * A.act_dim + j] = a;
-              if (A.action_clipped) A.action_clipped[(size_t)env * A.act_dim + j] = fminf(fmaxf(a, -1.f), 1.f);
-              lp += -0.5f * z[j] * z[j] - logstd_s[j] - 0.9189385332046727f;
-            }
-          if (A.logp) A.logp[env] = lp;
-        } else {
-          A.value[env] = __uint_as_float(v[0]) + bs[2 * HID];
+            if (j < A.act_dim) z[j] = noise_src[row * A.act_dim + j];
         }
+        float lp = 0.f;
+#pragma unroll
+        for (int j = 0; j < N3; ++j) {
+          const float a = fmaf(__expf(ls[j]), z[j], mean[j]);
+          if (j < A.act_dim) {
+            stage_a[row * A.act_dim + j] = a;
+            stage_c[row * A.act_dim + j] = fminf(fmaxf(a, -1.f), 1.f);
+            lp += -0.5f * z[j] * z[j] - ls[j] - 0.9189385332046727f;
+          }
+        }
+        if (A.logp && env < A.n) A.logp[env] = lp;
+      } else if (env < A.n) {
+        A.value[env] = __uint_as_float(v[0]) + bs[2 * HID];
       }
     }
+    if (net == 0) STAMP(23);
     tc_before();
-    __syncthreads();   // every warp has read D[0..31] before the next net's layer 1 overwrites it
+    __syncthreads();   // D[0..31] is consumed (the next net's layer 1 overwrites it); the staged tiles are complete
+    if (net == 0) STAMP(24);
+    if (net == 0) {    // coalesced stores of the contiguous [rows, act_dim] tiles, loads batched ahead of the stores
+      const int total = rows * A.act_dim;
+      const size_t base = (size_t)blockIdx.x * TM * A.act_dim;
+      constexpr int PER = TM * N3 / NT;
+      float ta[PER], tc[PER];
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int i = min(tid + u * NT, TM * N3 - 1);
+        ta[u] = stage_a[i];
+        tc[u] = stage_c[i];
+      }
+#pragma unroll
+      for (int u = 0; u < PER; ++u) {
+        const int i = tid + u * NT;
+        if (A.action && i < total) A.action[base + i] = ta[u];
+        if (A.action_clipped && i < total) A.action_clipped[base + i] = tc[u];
+      }
+      __syncthreads();   // before the next net's first epilogue writes H again
+    }
+    STAMP(10 + 8 * net);
   }
   if (warp == 0) {
     tc_after();
@@ -361,9 +436,14 @@ __global__ void pack_kernel(const float* w1p, const float* b1p, const float* w2p
     reinterpret_cast<float*>(blob + BLOB_LOGSTD)[threadIdx.x] = threadIdx.x < act_dim ? log_std[threadIdx.x] : 0.f;
 }
 
+long long* g_timeline = nullptr;
+
 }  // namespace
 
 extern "C" {
+
+/* harness only, not in ilrl.h: device buffer of 32 int64 that block 0 of the next policy steps stamps with clock64() */
+int ilrl_debug_policy_timeline(long long* dev32) { g_timeline = dev32; return ILRL_OK; }
 
 int64_t ilrl_policy_blob_bytes(void) { return BLOB_BYTES; }
 
@@ -397,7 +477,7 @@ int ilrl_policy_step(const void* blob_dev, const float* obs_dev, const float* no
   PolicyArgs a;
   a.blob = (const uint8_t*)blob_dev; a.obs = obs_dev; a.noise = noise_dev; a.action = action_dev;
   a.action_clipped = action_clipped_dev; a.logp = logp_dev; a.value = value_dev;
-  a.obs_dim = obs_dim; a.act_dim = act_dim; a.n = n; a.nets = (want_pi ? 1 : 0) | (value_dev ? 2 : 0);
+  a.obs_dim = obs_dim; a.act_dim = act_dim; a.n = n; a.nets = (want_pi ? 1 : 0) | (value_dev ? 2 : 0); a.timeline = g_timeline;
   policy_kernel<<<(n + TM - 1) / TM, NT, SMEM_BYTES, (cudaStream_t)stream>>>(a);
   return cudaGetLastError() == cudaSuccess ? ILRL_OK : ILRL_ERR_CUDA;
 }

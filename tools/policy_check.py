@@ -77,6 +77,27 @@ def main():
     us = e0.elapsed_time(e1) * 1e3 / 200
     flop = 2 * n * ((70 * 256 + 256 * 256) * 2 + 256 * 18)
     print("fused policy step N=%d: %.1f us (%.1f TFLOP/s useful)" % (n, us, flop / us * 1e-6))
+    import ctypes as C
+    from ilrl_b200 import _lib
+    tl = torch.zeros(32, dtype=torch.int64, device=dev)
+    _lib.lib().ilrl_debug_policy_timeline(C.c_void_p(tl.data_ptr()))
+    fp.step(obs, noise, a, ac, lp, v)
+    torch.cuda.synchronize()
+    _lib.lib().ilrl_debug_policy_timeline(None)
+    t = tl.cpu().numpy()
+    names = {0: "start", 1: "issued loads, alloc", 2: "inputs landed", 3: "A0 built", 4: "pi: W1 landed", 5: "pi: L1 mma done",
+             6: "pi: L1 epilogue (+L2 issue)", 7: "pi: L2 mma done", 8: "pi: L2 epilogue (+L3 issue)", 9: "pi: L3 mma done",
+             10: "pi: outputs", 12: "vf: W1 landed", 13: "vf: L1 mma done", 14: "vf: L1 epilogue", 15: "vf: L2 mma done",
+             16: "vf: L2 epilogue", 17: "vf: L3 mma done", 18: "vf: outputs"}
+    sub = {20: "next W2a requested", 21: "noise landed", 22: "D3 loaded", 23: "sampled + staged", 24: "cta barrier", 10: "tiles stored"}
+    prev = t[9]
+    for i in (20, 21, 22, 23, 24, 10):
+        print("    pi outputs: %-24s +%6d clk" % (sub[i], t[i] - prev))
+        prev = t[i]
+    prev = t[0]
+    for i in sorted(names):
+        print("  %-32s +%6d clk  (t = %6d)" % (names[i], t[i] - prev, t[i] - t[0]))
+        prev = t[i]
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
         for _ in range(10):
             pol(obs)

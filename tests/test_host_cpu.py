@@ -67,6 +67,28 @@ def test_bad_arguments_are_rejected_before_any_device_work():
     assert L.ilrl_launch_count(None) == 0
 
 
+def test_policy_entry_points_without_a_device():
+    """The fused policy kernel's C ABI: blob size is a pure function; argument errors come back before any CUDA call;
+    the host wrapper refuses a CPU-resident policy instead of falling back to torch."""
+    import ctypes as C
+    from ilrl_b200 import GaussianMLPPolicy, _lib
+    from ilrl_b200.rollout import FusedPolicy
+    L = _lib.lib()
+    per_net = (256 * 80 + 2 * 128 * 256 + 32 * 256) * 2       # bf16 operand images: W1 | W2 halves | W3
+    assert L.ilrl_policy_blob_bytes() == 2 * per_net + 2 * (256 + 256 + 32) * 4 + 32 * 4
+    x = C.c_void_p(16)   # never dereferenced: every call below fails validation first
+    assert L.ilrl_policy_step(None, x, None, None, None, None, x, 70, 17, 8, None) == -1
+    assert L.ilrl_policy_step(x, None, None, None, None, None, x, 70, 17, 8, None) == -1
+    assert L.ilrl_policy_step(x, x, None, None, None, None, None, 70, 17, 8, None) == -1   # no output requested
+    assert L.ilrl_policy_step(x, x, None, None, None, None, x, 81, 17, 8, None) == -1
+    assert L.ilrl_policy_step(x, x, None, None, None, None, x, 70, 33, 8, None) == -1
+    assert L.ilrl_policy_step(x, x, None, None, None, None, x, 70, 17, 0, None) == -1
+    assert L.ilrl_policy_step(C.c_void_p(8), x, None, None, None, None, x, 70, 17, 8, None) == -1   # blob not 16-byte aligned
+    assert L.ilrl_policy_pack(*([None] * 13), 70, 17, x, None) == -1
+    with pytest.raises(AssertionError, match="GPU"):
+        FusedPolicy(GaussianMLPPolicy())   # parameters on the CPU
+
+
 def test_product_never_touches_the_oracle():
     """The oracle is test infrastructure: nothing under the package may import, load or mention it."""
     for dirpath, _, files in os.walk(PKG):

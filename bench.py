@@ -10,7 +10,7 @@ only collective is the NCCL all-reduce of the 16-float statistics vector at the 
   python bench.py [--gpus N] [--steps K] [--warmup W]            -> this framework
   python bench.py --impl reference [--steps K] [--warmup W]      -> CPU arm: the oracle port of the reference path
                                                                     (PyBullet is not installable in this image)
-  python bench.py --workload hier16384|multiclip65536|rollout16384x8   -> extra measurement modes (BASELINE cfg 3/4/5)
+  python bench.py --workload hier16384|multiclip65536|rollout16384x8|hier_rollout16384x10   -> extra measurement modes (BASELINE cfg 3/4/5)
 Prints ONE JSON line on rank 0.
 """
 import argparse
@@ -358,8 +358,10 @@ def _quiet_stdout():
 EMIT = print
 
 
-def run_rollout(args):
-    """Extra measurement mode (BASELINE cfg 5): on-device rollout collection, 16384 envs x 8 steps per GPU per
+def run_rollout(args, hier=False):
+    """hier=True: the same for the hierarchical env (both policies on device, 5 launches per tick, horizon 10 =
+    rollout_fragment_length of REF train_config.py:257; counts low-level env steps).
+    Extra measurement mode (BASELINE cfg 5): on-device rollout collection, 16384 envs x 8 steps per GPU per
     iteration (= 1 M env-steps per iteration on 8 GPUs): fused tcgen05 policy / value / sampling kernel -> fused env step,
     2 launches per step captured in one CUDA graph, + GAE (ilrl_gae).  A "step" is one iteration; value = env-steps/s of the whole job."""
     rank = int(os.environ.get("RANK", "0"))
@@ -368,16 +370,21 @@ def run_rollout(args):
     import torch
     import torch.distributed as dist
     import ilrl_b200
-    from ilrl_b200 import BatchedHumanoidEnv, GaussianMLPPolicy, RolloutCollector
+    from ilrl_b200 import BatchedHumanoidEnv, GaussianMLPPolicy, HierRolloutCollector, RolloutCollector
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n, T = 16384, 8
+    n, T = 16384, (10 if hier else 8)
     K, W = min(args.steps, 200), max(3, min(args.warmup, 20))
     torch.manual_seed(0)
-    env = BatchedHumanoidEnv(n, "low", clips=[CLIP], device=local_rank, seed=1234, auto_reset=True, env_id_base=rank * n)
-    col = RolloutCollector(env, GaussianMLPPolicy(), horizon=T, gamma=0.99, lam=0.9, seed=rank)
+    if hier:
+        env = BatchedHumanoidEnv(n, "hier", clips=["motion08_03", "motion09_03"], clip_of_env=np.ones(n, np.int32),
+                                 device=local_rank, seed=1234, auto_reset=True, env_id_base=rank * n)
+        col = HierRolloutCollector(env, horizon=T, gamma=0.99, lam=0.9, seed=rank)
+    else:
+        env = BatchedHumanoidEnv(n, "low", clips=[CLIP], device=local_rank, seed=1234, auto_reset=True, env_id_base=rank * n)
+        col = RolloutCollector(env, GaussianMLPPolicy(), horizon=T, gamma=0.99, lam=0.9, seed=rank)
     for _ in range(W):
         col.collect()
     env.stats()
@@ -401,16 +408,20 @@ def run_rollout(args):
     if rank == 0:
         summ = ilrl_b200.stats.summarize(st)
         EMIT(json.dumps({
-            "metric": "rollout env-steps/sec (policy + physics + reward + GAE on device)", "value": world * n * T * K / (ms * 1e-3),
+            "metric": "rollout env-steps/sec (%spolicy + physics + reward + GAE on device)" % ("both policies: " if hier else ""), "value": world * n * T * K / (ms * 1e-3),
             "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "on-device PPO rollout collection: %d envs x %d steps per GPU per iteration, %s, "
-                                   "70-256-256-17 tanh Gaussian policy + value net (fused tcgen05 kernel, bf16 operands / fp32 accumulation), "
-                                   "gamma 0.99 lambda 0.9"
-                                   % (n, T, CLIP), "envs_per_gpu": n, "horizon": T,
-                       "episode_len_mean": summ["episode_len_mean"], "sample_batch_columns": sorted(batch.keys())},
-            # per iteration, replayed from the graph: T env steps + (T + 1) policy steps; + 1 GAE launch
-            "gpu_launches": K * (2 * T + 2)}))
+            "config": {"workload": ("on-device PPO rollout collection, hierarchical env: %d envs x %d low-level steps per GPU per "
+                                    "iteration, selected_motion=1, step_per_level=5, 44-256-256-2 and 70-256-256-17 tanh Gaussian "
+                                    "policies + value nets (fused tcgen05 kernel), gamma 0.99 lambda 0.9" % (n, T)) if hier else
+                                   ("on-device PPO rollout collection: %d envs x %d steps per GPU per iteration, %s, "
+                                    "70-256-256-17 tanh Gaussian policy + value net (fused tcgen05 kernel, bf16 operands / fp32 accumulation), "
+                                    "gamma 0.99 lambda 0.9" % (n, T, CLIP)), "envs_per_gpu": n, "horizon": T,
+                       "episode_len_mean": summ["episode_len_mean"],
+                       "sample_batch_columns": sorted(batch["low"].keys()) if hier else sorted(batch.keys())},
+            # per iteration, replayed from the graph: low: T env steps + (T + 1) policy steps, + 1 GAE launch;
+            # hier: 5 launches per tick + readout and two value calls after the last + 2 GAE launches
+            "gpu_launches": K * ((5 * T + 5) if hier else (2 * T + 2))}))
     env.close()
     if world > 1:
         dist.destroy_process_group()
@@ -425,13 +436,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="low4096", choices=sorted(WORKLOADS) + ["rollout16384x8"],
+    ap.add_argument("--workload", default="low4096", choices=sorted(WORKLOADS) + ["rollout16384x8", "hier_rollout16384x10"],
                     help="low4096 = the contract line (BASELINE cfg 2); the others are extra measurement modes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "rollout16384x8":
-        run_rollout(args)
+    elif args.workload in ("rollout16384x8", "hier_rollout16384x10"):
+        run_rollout(args, hier=args.workload.startswith("hier"))
     else:
         run_ours(args)
 

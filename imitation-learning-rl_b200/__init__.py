@@ -8,7 +8,8 @@ from .clips import CLIP_NAMES, load_clip  # noqa: F401
 from .ref_api import HierarchicalHumanoidEnv, LowLevelHumanoidEnv  # noqa: F401
 from .rllib_adapters import HierBaseEnv, LowLevelVectorEnv, policy_mapping_fn  # noqa: F401
 from . import stats  # noqa: F401
-from .rollout import GaussianMLPPolicy, RolloutCollector, gae  # noqa: F401
+from .rollout import FusedPolicy, GaussianMLPPolicy, HierRolloutCollector, RolloutCollector, gae, gae_decisions  # noqa: F401
 
 __all__ = ["BatchedHumanoidEnv", "CLIP_NAMES", "load_clip", "LowLevelHumanoidEnv", "HierarchicalHumanoidEnv",
-           "LowLevelVectorEnv", "HierBaseEnv", "policy_mapping_fn", "stats", "RolloutCollector", "GaussianMLPPolicy", "gae"]
+           "LowLevelVectorEnv", "HierBaseEnv", "policy_mapping_fn", "stats", "RolloutCollector", "HierRolloutCollector",
+           "GaussianMLPPolicy", "FusedPolicy", "gae", "gae_decisions"]

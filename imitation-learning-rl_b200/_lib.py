@@ -8,7 +8,7 @@ SO = os.environ.get("ILRL_SO") or os.path.join(HERE, "libilrl_b200.so")  # ILRL_
 SYMBOLS = ["ilrl_create", "ilrl_destroy", "ilrl_last_error", "ilrl_load_clip", "ilrl_set_clip_ids", "ilrl_reset",
            "ilrl_step", "ilrl_step_host", "ilrl_high_step", "ilrl_high_readout", "ilrl_get_state", "ilrl_set_state",
            "ilrl_set_forced_target_deg", "ilrl_step_no_physics", "ilrl_physics_only", "ilrl_endpoint_score",
-           "ilrl_stats", "ilrl_gae", "ilrl_policy_blob_bytes", "ilrl_policy_pack", "ilrl_policy_step",
+           "ilrl_stats", "ilrl_gae", "ilrl_gae_decisions", "ilrl_policy_blob_bytes", "ilrl_policy_pack", "ilrl_policy_step",
            "ilrl_launch_count", "ilrl_kernel_timing"]
 
 
@@ -54,6 +54,7 @@ def lib():
     L.ilrl_endpoint_score.argtypes = [_vp, _vp, _vp]
     L.ilrl_stats.argtypes = [_vp, _vp, _vp]
     L.ilrl_gae.argtypes = [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, C.c_int32, C.c_int32, _vp]
+    L.ilrl_gae_decisions.argtypes = [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]
     L.ilrl_policy_blob_bytes.restype = C.c_int64
     L.ilrl_policy_blob_bytes.argtypes = []
     L.ilrl_policy_pack.argtypes = [_vp] * 13 + [C.c_int32, C.c_int32, _vp, _vp]

@@ -169,6 +169,21 @@ class BatchedHumanoidEnv:
                                           self._stream()))
         return self.high_obs, self.high_reward, self.high_flags
 
+    def high_step_into(self, action2, low_obs):
+        """`high_step` writing the low-level obs rows of the envs that were waiting into a caller-owned [N,70] tensor."""
+        n = self.num_envs
+        for t, shape in ((action2, (n, ACT_HIGH)), (low_obs, (n, OBS_LOW))):
+            assert t.is_cuda and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape
+        self._ck(self.L.ilrl_high_step(self.h, _ptr(action2), _ptr(low_obs), self._stream()))
+
+    def high_readout_into(self, high_obs, high_reward, high_flags):
+        """`high_readout` into caller-owned tensors: [N,44] f32, [N] f32, [N] u8."""
+        n = self.num_envs
+        for t, shape, dt in ((high_obs, (n, OBS_HIGH), torch.float32), (high_reward, (n,), torch.float32),
+                             (high_flags, (n,), torch.uint8)):
+            assert t.is_cuda and t.device == self.device and t.dtype == dt and t.is_contiguous() and tuple(t.shape) == shape
+        self._ck(self.L.ilrl_high_readout(self.h, _ptr(high_obs), _ptr(high_reward), _ptr(high_flags), self._stream()))
+
     def set_clip_of_env(self, clip_of_env):
         """Re-assign which staged clip each env imitates (`selected_motion`).  Takes effect at once, as in the reference;
         change it between episodes (a frame index valid in one clip may not exist in a shorter one)."""

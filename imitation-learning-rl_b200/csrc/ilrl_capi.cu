@@ -496,6 +496,49 @@ __global__ void gae_kernel(const float* __restrict__ rew, const float* __restric
     vnext = v;
   }
 }
+// GAE for the HIGH-level agent of the hierarchical env, whose decisions are irregular in time: per env, a decision is
+// taken at every tick whose flag has bit2 (waiting) and its outcome — reward, end of episode, the next decision's value
+// — is what ilrl_high_readout reports at the next tick with bit1 (REF hier_env.py:524-536, 613-631).  Rows 0..T of
+// reward / flags / value are the readouts before tick t (row T: after the last step).  A decision whose outcome lies
+// beyond the fragment is marked invalid (valid = 0) and contributes only its value as the bootstrap of the one before.
+__global__ void gae_decisions_kernel(const float* __restrict__ rew, const uint8_t* __restrict__ flags,
+                                     const float* __restrict__ val, float gamma, float lam, float* __restrict__ adv,
+                                     float* __restrict__ ret, uint8_t* __restrict__ valid, int T, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int tau = -1;          // nearest later tick that reports an outcome
+  float a_tau = 0.f;     // advantage of the decision taken at tau (0 if none / invalid / episode ended there)
+  {
+    const uint8_t f = flags[(size_t)T * n + i];
+    if (f & 2) tau = T;
+  }
+  for (int t = T - 1; t >= 0; t--) {
+    const size_t k = (size_t)t * n + i;
+    const uint8_t f = flags[k];
+    float a = 0.f;
+    bool ok = false;
+    if (f & 4) {
+      if (tau >= 0) {
+        const size_t kt = (size_t)tau * n + i;
+        const bool ended = flags[kt] & 1;
+        const float v = val[k];
+        const float delta = rew[kt] + (ended ? 0.f : gamma * val[kt]) - v;
+        a = delta + (ended ? 0.f : gamma * lam * a_tau);
+        adv[k] = a;
+        ret[k] = a + v;
+        ok = true;
+      } else {
+        adv[k] = 0.f;
+        ret[k] = val[k];
+      }
+    } else {
+      adv[k] = 0.f;
+      ret[k] = 0.f;
+    }
+    valid[k] = ok ? 1 : 0;
+    if (f & 2) { tau = t; a_tau = ok ? a : 0.f; }
+  }
+}
 __global__ void stats_fetch_kernel(float* acc, float* out) {
   int t = threadIdx.x;
   if (t < ILRL_STATS_WORDS) { out[t] = acc[t]; acc[t] = 0.f; }
@@ -917,6 +960,13 @@ int ilrl_gae(const float* reward, const float* value, const uint8_t* done, float
              float* value_target, int32_t T, int32_t n, void* stream) {
   if (!reward || !value || !done || !advantage || !value_target || T <= 0 || n <= 0) return ILRL_ERR_ARG;
   gae_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reward, value, done, gamma, lam, advantage, value_target, T, n);
+  return cudaGetLastError() == cudaSuccess ? ILRL_OK : ILRL_ERR_CUDA;
+}
+int ilrl_gae_decisions(const float* reward, const uint8_t* flags, const float* value, float gamma, float lam,
+                       float* advantage, float* value_target, uint8_t* valid, int32_t T, int32_t n, void* stream) {
+  if (!reward || !flags || !value || !advantage || !value_target || !valid || T <= 0 || n <= 0) return ILRL_ERR_ARG;
+  gae_decisions_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reward, flags, value, gamma, lam, advantage,
+                                                                         value_target, valid, T, n);
   return cudaGetLastError() == cudaSuccess ? ILRL_OK : ILRL_ERR_CUDA;
 }
 /* harness only, not in ilrl.h: on = 0 forces ilrl_step_host onto explicit copies even for page-locked buffers */

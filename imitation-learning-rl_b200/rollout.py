@@ -197,3 +197,109 @@ class RolloutCollector:
         out["vf_preds"] = b["vf_preds"][:self.T]
         out["advantages"], out["value_targets"] = adv, vt
         return out
+
+
+def gae_decisions(rewards, flags, values, gamma, lam):
+    """GAE of the high-level agent (irregular decision times).  rewards / flags / values [T+1, N]: the
+    `high_readout` rows taken before every tick and once after the last, and the value estimates of those
+    observations.  -> advantages, value_targets [T, N] f32 and valid [T, N] uint8 (see include/ilrl.h)."""
+    T, n = rewards.shape[0] - 1, rewards.shape[1]
+    assert flags.shape == (T + 1, n) and values.shape == (T + 1, n) and flags.dtype == torch.uint8
+    assert rewards.is_cuda and rewards.is_contiguous() and flags.is_contiguous() and values.is_contiguous()
+    adv, ret = torch.empty(T, n, device=rewards.device), torch.empty(T, n, device=rewards.device)
+    valid = torch.empty(T, n, device=rewards.device, dtype=torch.uint8)
+    st = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)
+    rc = _lib.lib().ilrl_gae_decisions(_ptr(rewards), _ptr(flags), _ptr(values), gamma, lam, _ptr(adv), _ptr(ret),
+                                       _ptr(valid), T, n, st)
+    if rc != 0:
+        raise _lib.IlrlError("ilrl_gae_decisions failed (%d)" % rc)
+    return adv, ret, valid
+
+
+class HierRolloutCollector:
+    """On-device fragments of the hierarchical env (REF hier_env.py; train_config.py:260-321: two policies,
+    "high_level_policy" 44-256-256-2 and "low_level_policy" 70-256-256-17, both trained by PPO).
+
+    Every tick (5 launches, all T ticks replayed as one CUDA graph):
+        high_readout   -> high obs / reward / flags of every env        (K4 readout)
+        high policy    -> heading action for every env                  (tcgen05 policy kernel; used where an env waits)
+        high_step      -> envs waiting for a heading take it, their low-level obs row is refreshed
+        low policy     -> torques                                       (tcgen05 policy kernel)
+        step           -> one low-level env step of every env, into the buffers in place
+    The env is created with auto_reset=True: an env whose episode ends is reset inside the step and waits for a
+    heading at the next tick.  `collect()` returns {"low": {...}, "high": {...}} of step-major device tensors with
+    RLlib's SampleBatch column names; the high-level columns are dense [T, N] with `valid` marking the ticks at which
+    an env actually took a high-level decision whose outcome lies inside the fragment (the high-level agent acts once
+    per `step_per_level` low-level steps, at times that differ per env)."""
+
+    def __init__(self, env, high_policy=None, low_policy=None, horizon=10, gamma=0.99, lam=0.9, seed=0, use_graph=True):
+        assert isinstance(env, BatchedHumanoidEnv) and env.mode == 1, "needs a hier-mode env"
+        from .batched_env import ACT_HIGH, OBS_HIGH
+        self.env, self.T, self.gamma, self.lam = env, int(horizon), float(gamma), float(lam)
+        dev, n, T = env.device, env.num_envs, self.T
+        self.high_policy = (high_policy if high_policy is not None else GaussianMLPPolicy(OBS_HIGH, ACT_HIGH)).to(dev).eval()
+        self.low_policy = (low_policy if low_policy is not None else GaussianMLPPolicy(OBS_LOW, ACT_LOW)).to(dev).eval()
+        self.fused_high, self.fused_low = FusedPolicy(self.high_policy), FusedPolicy(self.low_policy)
+        self.gen = torch.Generator(device=dev)
+        self.gen.manual_seed(seed)
+        f = dict(device=dev, dtype=torch.float32)
+        u8 = dict(device=dev, dtype=torch.uint8)
+        self._lobs = torch.zeros(T + 1, n, OBS_LOW, **f)
+        self._hobs = torch.zeros(T + 1, n, OBS_HIGH, **f)
+        self.low = {"obs": self._lobs[:T], "new_obs": self._lobs[1:], "actions": torch.zeros(T, n, ACT_LOW, **f),
+                    "rewards": torch.zeros(T, n, **f), "dones": torch.zeros(T, n, **u8),
+                    "action_logp": torch.zeros(T, n, **f), "vf_preds": torch.zeros(T + 1, n, **f)}
+        self.high = {"obs": self._hobs[:T], "actions": torch.zeros(T, n, ACT_HIGH, **f),
+                     "action_logp": torch.zeros(T, n, **f), "vf_preds": torch.zeros(T + 1, n, **f),
+                     "readout_rewards": torch.zeros(T + 1, n, **f), "flags": torch.zeros(T + 1, n, **u8)}
+        self._noise_l, self._noise_h = torch.zeros(T, n, ACT_LOW, **f), torch.zeros(T, n, ACT_HIGH, **f)
+        self._clip_l, self._clip_h = torch.zeros(n, ACT_LOW, **f), torch.zeros(n, ACT_HIGH, **f)
+        self._graph, self._use_graph = None, use_graph
+        env.reset()   # every env now waits for its first heading; its low-level obs row is written by high_step
+
+    def policies_updated(self):
+        self.fused_high.repack()
+        self.fused_low.repack()
+
+    @torch.no_grad()
+    def _loop(self):
+        env, T, lo, hi = self.env, self.T, self.low, self.high
+        self._lobs[0].copy_(self._lobs[T])
+        for t in range(T):
+            env.high_readout_into(self._hobs[t], hi["readout_rewards"][t], hi["flags"][t])
+            self.fused_high.step(self._hobs[t], self._noise_h[t], hi["actions"][t], self._clip_h, hi["action_logp"][t],
+                                 hi["vf_preds"][t])
+            env.high_step_into(self._clip_h, self._lobs[t])
+            self.fused_low.step(self._lobs[t], self._noise_l[t], lo["actions"][t], self._clip_l, lo["action_logp"][t],
+                                lo["vf_preds"][t])
+            env.step_into(self._clip_l, self._lobs[t + 1], lo["rewards"][t], lo["dones"][t])
+        env.high_readout_into(self._hobs[T], hi["readout_rewards"][T], hi["flags"][T])
+        self.fused_high.step(self._hobs[T], value=hi["vf_preds"][T])
+        self.fused_low.step(self._lobs[T], value=lo["vf_preds"][T])
+
+    @torch.no_grad()
+    def collect(self):
+        self._noise_l.normal_(generator=self.gen)
+        self._noise_h.normal_(generator=self.gen)
+        if not self._use_graph:
+            self._loop()
+        elif self._graph is None:
+            # the first fragment runs eagerly (it is also the warm-up); capturing afterwards executes nothing, so the
+            # env advances by exactly one fragment per collect() with or without the graph
+            self._loop()
+            torch.cuda.synchronize(self.env.device)
+            self._graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph):
+                self._loop()
+        else:
+            self._graph.replay()
+        lo, hi, T = self.low, self.high, self.T
+        adv, vt = gae(lo["rewards"], lo["vf_preds"], lo["dones"], self.gamma, self.lam)
+        low = {k: lo[k] for k in ("obs", "new_obs", "actions", "rewards", "dones", "action_logp")}
+        low["vf_preds"], low["advantages"], low["value_targets"] = lo["vf_preds"][:T], adv, vt
+        hadv, hvt, valid = gae_decisions(hi["readout_rewards"], hi["flags"], hi["vf_preds"], self.gamma, self.lam)
+        high = {k: hi[k] for k in ("obs", "actions", "action_logp")}
+        high["vf_preds"], high["advantages"], high["value_targets"], high["valid"] = hi["vf_preds"][:T], hadv, hvt, valid
+        high["decided"] = (hi["flags"][:T] & 4) != 0     # every decision, with or without its outcome in the fragment
+        high["readout_rewards"], high["flags"] = hi["readout_rewards"], hi["flags"]
+        return {"low": low, "high": high}

@@ -126,6 +126,15 @@ int ilrl_stats(ilrl_env* env, float* stats16_dev, void* stream);
 int ilrl_gae(const float* reward_dev, const float* value_dev, const uint8_t* done_dev, float gamma, float lambda_,
              float* advantage_dev, float* value_target_dev, int32_t T, int32_t n, void* stream);
 
+/* GAE for the high-level agent of the hierarchical env over a fragment of T ticks (rows 0..T of the ilrl_high_readout
+ * outputs, taken before every tick and once after the last; value_dev [T+1,N] = value estimates of those high-level
+ * observations).  A decision is taken where flags has bit2; its reward / termination / successor value are the ones
+ * reported at the next row with bit1 (REF hier_env.py:524-536, 613-631).  Outputs [T,N]: advantage, value target and
+ * valid (1 = a decision with its outcome inside the fragment; everything else is 0 / masked out). */
+int ilrl_gae_decisions(const float* reward_dev, const uint8_t* flags_dev, const float* value_dev, float gamma,
+                       float lambda_, float* advantage_dev, float* value_target_dev, uint8_t* valid_dev, int32_t T,
+                       int32_t n, void* stream);
+
 /* ---- fused policy / value forward for on-device rollout collection -------------------
  * Replaces the per-step model forward + action sampling RLlib does around env.step for the reference's policies
  * (REF train_config.py:91-113 low level 70-256-256-17, :262-286 high level 44-256-256-2: fcnet_hiddens [256, 256],

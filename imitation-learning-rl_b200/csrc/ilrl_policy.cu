@@ -24,6 +24,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/ilrl.h"
 
 namespace {
@@ -466,13 +468,13 @@ int ilrl_policy_step(const void* blob_dev, const float* obs_dev, const float* no
   if (!blob_dev || !obs_dev || n <= 0 || obs_dim < 1 || obs_dim > K1 || act_dim < 1 || act_dim > N3 ||
       (!want_pi && !value_dev) || ((uintptr_t)blob_dev & 15))
     return ILRL_ERR_ARG;
-  static bool configured[64] = {};   // the opt-in to > 48 KB of dynamic shared memory is per device
+  static std::atomic<bool> configured[64];   // the opt-in to > 48 KB of dynamic shared memory is per device
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return ILRL_ERR_CUDA;
-  if (!configured[dev]) {
+  if (!configured[dev].load(std::memory_order_acquire)) {   // idempotent: a concurrent first call just repeats it
     if (cudaFuncSetAttribute(policy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess)
       return ILRL_ERR_CUDA;
-    configured[dev] = true;
+    configured[dev].store(true, std::memory_order_release);
   }
   PolicyArgs a;
   a.blob = (const uint8_t*)blob_dev; a.obs = obs_dev; a.noise = noise_dev; a.action = action_dev;

@@ -30,6 +30,7 @@ using chain::QE;
 using chain::QT;
 using SmemSmall = chain::SmemT<chain::LayoutSmall>;
 using SmemLarge = chain::SmemT<chain::LayoutLarge>;
+using SmemDense4 = chain::SmemT<chain::LayoutDense4>;
 
 struct StepArgs {
   int n;
@@ -561,7 +562,7 @@ struct ilrl_env {
   uint8_t* high_flags = nullptr;
   float* stats = nullptr;
   unsigned int* tile_counter = nullptr;
-  int grid_small = 0, grid_large = 0;  // resident CTAs of the step kernel in each layout
+  int grid_small = 0, grid_large = 0, grid_dense4 = 0;  // resident CTAs of the step kernel in each layout
   float* clip_mem[MAX_CLIPS] = {nullptr};
   ClipDesc clips[MAX_CLIPS];
   bool clip_loaded[MAX_CLIPS] = {false};
@@ -572,7 +573,8 @@ struct ilrl_env {
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_terms = nullptr;
   uint8_t* d_done = nullptr;
   int substeps = ILRL_SUBSTEPS;  // harness only (ilrl_debug_substeps)
-  bool large_layout = false;     // shared-memory layout of the step kernel (chosen at create time from N)
+  int layout = 0;                // shared-memory layout of the step kernel: 0 LayoutSmall, 1 LayoutLarge, 2 LayoutDense4
+                                 // (chosen at create time from N)
   bool no_zero_copy = false;     // harness only (ilrl_debug_zero_copy): force the explicit-copy host path
   int64_t launches = 0;
   bool timing = false;
@@ -636,31 +638,47 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(step_kernel<1, SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(physics_only_kernel<SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
+  CKC(cudaFuncSetAttribute(step_kernel<0, SmemDense4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDense4)));
+  CKC(cudaFuncSetAttribute(step_kernel<1, SmemDense4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDense4)));
+  CKC(cudaFuncSetAttribute(physics_only_kernel<SmemDense4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDense4)));
   {
-    // Layout.  With persistent CTAs a step takes about ceil(tiles / resident CTAs) tile times,
-    // and a tile of the dense layout takes ~1.19x a tile of the all-on-chip one (measured on B200 at one wave: 25.8 vs
-    // 30.6 M env-steps/s): pick whichever estimate is smaller.  E.g. 4096 envs (256 tiles) -> on chip; 6144 (384) ->
-    // dense, one wave instead of two; 8192 (512) -> on chip; from 9488 envs on -> dense.  Measured pairs (M env-steps/s,
-    // on-chip vs dense): 6144: 30.7 / 35.8; 8192: 38.7 / 34.3; 12288: 41.1 / 43.9; 16384: 43.0 / 45.2; 32768: 48.7 / 52.0.
-    // ILRL_LAYOUT=small|large overrides (measurement aid).
+    // Layout.  The step kernel is persistent: resident CTAs (SMs x CTAs per SM) pull 16-env tiles,
+    // so a step takes x = tiles / resident CTAs "rounds", the last one partly filled.  Measured on B200 (us per full
+    // round): on-chip 97 (2 CTAs per SM), dense 127 (3 per SM), dense4 171 (4 per SM); a partly filled round costs
+    // between the single-wave latency (~90) and the full-round time.  Estimate all three, take the smallest:
+    //   4096 envs -> on chip; 6144 -> dense (1 round instead of 2); 8192 -> dense4 (1 round: 43.7 M env-steps/s against
+    //   38.6 on chip / 34.3 dense); 12288 -> dense (43.8 against 41.3 / 41.2); 16384 -> dense4 (2 rounds instead of 3:
+    //   50.2 against 45.9 dense / 43.0 on chip); 32768, 65536 -> dense and dense4 within 2 % (52.0 / 52.9, 56.1 / 55.4).
+    // ILRL_LAYOUT=small|large|dense4 overrides (measurement aid).
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
-    if (const char* o = getenv("ILRL_LAYOUT")) env->large_layout = o[0] == 'l' || o[0] == 'L';
-    int occ_s = 0, occ_l = 0;
+    int occ[3] = {0, 0, 0};
     if (cfg->mode == 0) {
-      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, step_kernel<0, SmemSmall>, QT, sizeof(SmemSmall)));
-      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, step_kernel<0, SmemLarge>, QT, sizeof(SmemLarge)));
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], step_kernel<0, SmemSmall>, QT, sizeof(SmemSmall)));
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], step_kernel<0, SmemLarge>, QT, sizeof(SmemLarge)));
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], step_kernel<0, SmemDense4>, QT, sizeof(SmemDense4)));
     } else {
-      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, step_kernel<1, SmemSmall>, QT, sizeof(SmemSmall)));
-      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_l, step_kernel<1, SmemLarge>, QT, sizeof(SmemLarge)));
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], step_kernel<1, SmemSmall>, QT, sizeof(SmemSmall)));
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], step_kernel<1, SmemLarge>, QT, sizeof(SmemLarge)));
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], step_kernel<1, SmemDense4>, QT, sizeof(SmemDense4)));
     }
-    if (occ_s < 1 || occ_l < 1) { g_create_err = "step kernel does not fit on this device"; ilrl_destroy(env); return ILRL_ERR_CUDA; }
-    env->grid_small = occ_s * prop.multiProcessorCount;
-    env->grid_large = occ_l * prop.multiProcessorCount;
-    if (!getenv("ILRL_LAYOUT")) {
-      const int tiles = (n + QE - 1) / QE;
-      const int rounds_s = (tiles + env->grid_small - 1) / env->grid_small, rounds_l = (tiles + env->grid_large - 1) / env->grid_large;
-      env->large_layout = 1.19f * (float)rounds_l < (float)rounds_s;
+    if (occ[0] < 1 || occ[1] < 1 || occ[2] < 1) { g_create_err = "step kernel does not fit on this device"; ilrl_destroy(env); return ILRL_ERR_CUDA; }
+    env->grid_small = occ[0] * prop.multiProcessorCount;
+    env->grid_large = occ[1] * prop.multiProcessorCount;
+    env->grid_dense4 = occ[2] * prop.multiProcessorCount;
+    if (const char* o = getenv("ILRL_LAYOUT")) {
+      env->layout = (o[0] == 'l' || o[0] == 'L') ? 1 : (o[0] == 'd' || o[0] == 'D') ? 2 : 0;
+    } else {
+      const float tiles = (float)((n + QE - 1) / QE);
+      const float t_round[3] = {97.f, 127.f, 171.f}, t_wave = 90.f;
+      const int grid[3] = {env->grid_small, env->grid_large, env->grid_dense4};
+      float best = 0.f;
+      for (int l = 0; l < 3; l++) {
+        const float x = tiles / (float)grid[l], full = floorf(x), frac = x - full;
+        // (from 4 rounds on the CTAs have drifted apart and the tile queue keeps every SM busy: time ~ x)
+        const float est = x >= 4.f ? x * t_round[l] : full * t_round[l] + (frac > 0.f ? t_wave + (t_round[l] - t_wave) * frac : 0.f);
+        if (l == 0 || est < best) { best = est; env->layout = l; }
+      }
     }
   }
   CKC(cudaMalloc(&env->high_obs, sizeof(float) * 44 * n));
@@ -785,8 +803,11 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   cudaStream_t st = (cudaStream_t)stream;
   if (env->timing) CK(cudaEventRecord(env->ev0, st));
   a.ntiles = (env->n + QE - 1) / QE;
-  const int qblk = min(a.ntiles, env->large_layout ? env->grid_large : env->grid_small);
-  if (env->large_layout) {
+  const int qblk = min(a.ntiles, env->layout == 2 ? env->grid_dense4 : env->layout == 1 ? env->grid_large : env->grid_small);
+  if (env->layout == 2) {
+    if (env->cfg.mode == 0) step_kernel<0, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
+    else step_kernel<1, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
+  } else if (env->layout == 1) {
     if (env->cfg.mode == 0) step_kernel<0, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
     else step_kernel<1, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
   } else {
@@ -927,7 +948,9 @@ int ilrl_physics_only(ilrl_env* env, const float* torque, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (!torque) return fail(env, ILRL_ERR_ARG, "ilrl_physics_only: null buffer");
   CK(cudaSetDevice(env->cfg.device));
-  if (env->large_layout)
+  if (env->layout == 2)
+    physics_only_kernel<SmemDense4><<<(env->n + QE - 1) / QE, QT, sizeof(SmemDense4), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);
+  else if (env->layout == 1)
     physics_only_kernel<SmemLarge><<<(env->n + QE - 1) / QE, QT, sizeof(SmemLarge), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);
   else
     physics_only_kernel<SmemSmall><<<(env->n + QE - 1) / QE, QT, sizeof(SmemSmall), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);

@@ -34,7 +34,10 @@ constexpr int QE = ILRL_QE;            // envs per CTA
 constexpr int QT = 4 * QE;             // threads per CTA
 constexpr int NL = 7;                  // chain links per lane: 3 spine + 4 limb slots
 constexpr int RW = 40;                 // words per stored row
-constexpr int MIN_RSM = 8;             // smallest on-chip row budget of any layout
+#ifndef ILRL_MIN_RSM
+#define ILRL_MIN_RSM 2   // = the row budget of LayoutDense4
+#endif
+constexpr int MIN_RSM = ILRL_MIN_RSM;  // smallest on-chip row budget of any layout
 constexpr int GROWS = MAXROWS - MIN_RSM;  // rows per env in the global overflow scratch
 // link record: 24 words in 6 float4 (S | cJ | U dinv u | q qd tau nu), one contiguous 28-word slot per thread: a
 // 28-word stride puts the float4 of 8 consecutive threads in 8 different bank groups (conflict-free LDS.128 / STS.128)
@@ -181,21 +184,25 @@ __device__ constexpr Tables kTables{};
 constexpr int TABLE_WORDS = sizeof(Tables) / 4;
 static_assert(sizeof(Tables) % 4 == 0, "table copy is word-wise");
 
-// ---- shared memory of one CTA, in two layouts chosen by the host from the batch size
-//   LayoutSmall: up to one wave of CTAs at 2 per SM (<= 4736 envs on 148 SMs): everything on chip - 16 rows per env,
-//                padded (conflict-free) body records, model tables in shared memory.  107 KB.
-//   LayoutLarge: larger batches, where resident warps per SM are what limits throughput: 8 rows per env on chip (the
-//                rest in the L2-resident global scratch), unpadded body records, model tables read through L1.
-//                73 KB -> 3 CTAs per SM.
-// In both, the body records (written by the FK phase, consumed by the inward pass) share their storage with what
+// ---- shared memory of one CTA, in three layouts chosen by the host from the batch size (ilrl_create)
+//   LayoutSmall : up to one wave of CTAs at 2 per SM (<= 4736 envs on 148 SMs): everything on chip - 16 rows per env,
+//                 padded (conflict-free) body records, model tables in shared memory.  98 KB.
+//   LayoutLarge : larger batches, where resident warps per SM are what limits throughput: 8 rows per env on chip (the
+//                 rest in the L2-resident global scratch), unpadded body records, model tables read through L1.
+//                 73 KB -> 3 CTAs per SM (7104 envs per wave).
+//   LayoutDense4: 2 rows per env on chip, body-view lane stride 32 (4-way bank conflicts on its 4 float4 accesses per
+//                 substep).  55.5 KB -> 4 CTAs per SM (9472 envs per wave): a tile is ~1.35x slower than LayoutLarge's,
+//                 so it wins exactly where it saves a round of tiles (8192 envs: 1 instead of 2; 16384: 2 instead of 3).
+// In all, the body records (written by the FK phase, consumed by the inward pass) share their storage with what
 // only the row phase uses (response scratch, multipliers, row owners) and with the action tile (consumed before the
 // first substep).
-template <int RSM_, int BRW_, bool TSM_>
+template <int RSM_, int BRW_, bool TSM_, int LANE_>
 struct Layout {
   static constexpr int RSM = RSM_;               // constraint rows per env kept in shared memory
   static constexpr int ROWSTRIDE = RSM_ * RW + 4;  // env stride in words: = 4 (mod 32)
   static constexpr int BRW = BRW_;               // words per body record (20: room for padding; 16: dense)
   static constexpr bool TSM = TSM_;              // model tables staged in shared memory
+  static constexpr int LANE = LANE_;             // lane stride of the body view in the per-env scratch block (words)
 };
 #ifndef ILRL_LARGE_RSM  // (overridable for layout experiments)
 #define ILRL_LARGE_RSM 8
@@ -203,21 +210,21 @@ struct Layout {
 #define ILRL_LARGE_TSM false
 #endif
 static_assert(ILRL_LARGE_RSM >= MIN_RSM, "the overflow scratch holds MAXROWS - MIN_RSM rows per env");
-using LayoutSmall = Layout<16, 20, true>;
-using LayoutLarge = Layout<ILRL_LARGE_RSM, ILRL_LARGE_BRW, ILRL_LARGE_TSM>;
+using LayoutSmall = Layout<16, 20, true, 40>;
+using LayoutLarge = Layout<ILRL_LARGE_RSM, ILRL_LARGE_BRW, ILRL_LARGE_TSM, 40>;
+using LayoutDense4 = Layout<2, 16, false, 32>;
 
 // Per-env scratch block, seen in two ways that are never live at the same time within an env:
-//   body view (FK phase -> inward pass): body records of the four lanes (2 each, lane stride 40 words) + the spine's 2
+//   body view (FK phase -> inward pass): body records of the four lanes (2 each, lane stride LANE words) + the spine's 2
 //   row view  (row phase)              : response scratch u[lane][3 impulses][7 links], multipliers, action tile
 //                                        (consumed before the first substep), row owners (bytes)
 // The block is PER ENV because warps of a CTA run unsynchronised: one env's row phase must never touch another env's
-// body records.  Env stride = 4 (mod 32) words and lane stride 40: the float4 accesses of the 2 envs x 4 lanes of a
+// body records.  Env stride = 4 (mod 32) words and lane stride 40 (LayoutSmall / LayoutLarge): the float4 accesses of the 2 envs x 4 lanes of a
 // quarter-warp fall in 8 different bank groups, and scalar accesses of the 8 envs of a warp in 8 different banks.
-constexpr int SCR_LANE = 40;                       // lane stride of the body view
 constexpr int SCR_SU = 0, SCR_LAM = 4 * 3 * NL, SCR_ACT = SCR_LAM + MAXROWS, SCR_ROWL = SCR_ACT + NJ;  // row view (words)
 constexpr int SCR_ROWVIEW = SCR_ROWL + (MAXROWS + 3) / 4;
-template <int BRW> constexpr int scr_words() {
-  int w = 4 * SCR_LANE + 2 * BRW;                  // body view
+template <int BRW, int LANE> constexpr int scr_words() {
+  int w = 4 * LANE + 2 * BRW;                      // body view
   if (w < SCR_ROWVIEW) w = SCR_ROWVIEW;
   while (w % 32 != 4) w++;
   return w;
@@ -226,8 +233,9 @@ template <int BRW> constexpr int scr_words() {
 struct NoTables {};
 template <class LY>
 struct __align__(16) SmemT {
-  static constexpr int RSM = LY::RSM, ROWSTRIDE = LY::ROWSTRIDE, BRW = LY::BRW, ES = scr_words<LY::BRW>();
+  static constexpr int RSM = LY::RSM, ROWSTRIDE = LY::ROWSTRIDE, BRW = LY::BRW, ES = scr_words<LY::BRW, LY::LANE>();
   static constexpr bool TSM = LY::TSM;
+  static constexpr int SCR_LANE = LY::LANE;
   static_assert(2 * BRW <= SCR_LANE, "two body records per lane");
   // --- float4-accessed arrays first (every size below is a multiple of 16 bytes)
   float rows[QE][ROWSTRIDE];   // stored rows; after the substeps the first 71 words of an env's block stage its obs row
@@ -236,7 +244,7 @@ struct __align__(16) SmemT {
   float scr[QE][ES];           // per-env scratch block (see above)
   // --- scalar-accessed
   float L0[21][QE];            // Cholesky factor of the base articulated inertia
-  float sph[NS][4][QE];        // contact candidates: x, y, z - r (relative to the torso origin), distance
+  float sph[NS][3][QE];        // contact candidates: x, y, z - r relative to the torso origin (distance = base z + that)
   typename std::conditional<TSM, Tables, NoTables>::type T;
   static_assert((sizeof(float) * QE * ROWSTRIDE) % 16 == 0 && (sizeof(float) * LKW) % 16 == 0 && BRW % 4 == 0 && ES % 4 == 0,
                 "float4 alignment of the shared-memory records");
@@ -454,11 +462,11 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
 #pragma unroll 1
     for (int g = NS - 5; g < NS; g++) {
       V3 c = mv(R0, mk(kSphereC[3 * g], kSphereC[3 * g + 1], kSphereC[3 * g + 2]));
-      const float rad = kSphereR[g], d = b.p[2] + c.z - rad;
+      const float rad = kSphereR[g], d = b.p[2] + (c.z - rad);   // same association as where it is recomputed
       if (d < (float)ILRL_CONTACT_BREAK) {
         act |= 1u << g;
         float* sp = &sm.sph[g][0][e];
-        sp[0] = c.x; sp[QE] = c.y; sp[2 * QE] = c.z - rad; sp[3 * QE] = d;
+        sp[0] = c.x; sp[QE] = c.y; sp[2 * QE] = c.z - rad;
       }
     }
   }
@@ -528,11 +536,11 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
           for (int t = 0; t < B.nsph; t++) {
             const int g = B.sidx[t];
             V3 cs_ = ob + mv(Rc, rd3(B.sph[t]));
-            const float rad = B.sph[t][3], d = b.p[2] + cs_.z - rad;
+            const float rad = B.sph[t][3], d = b.p[2] + (cs_.z - rad);
             if (d < (float)ILRL_CONTACT_BREAK) {
               act |= 1u << g;
               float* sp = &sm.sph[g][0][e];
-              sp[0] = cs_.x; sp[QE] = cs_.y; sp[2 * QE] = cs_.z - rad; sp[3 * QE] = d;
+              sp[0] = cs_.x; sp[QE] = cs_.y; sp[2 * QE] = cs_.z - rad;
             }
           }
         }
@@ -910,7 +918,10 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
     float wd = -1e30f;
 #pragma unroll 1
     for (int g = 0; g < NS; g++)
-      if (((act >> g) & 1u) && sm.sph[g][3][e] >= wd) { wd = sm.sph[g][3][e]; worst = g; }
+      if ((act >> g) & 1u) {
+        const float d = b.p[2] + sm.sph[g][2][e];
+        if (d >= wd) { wd = d; worst = g; }
+      }
     act &= ~(1u << worst);
     nact--;
   }
@@ -956,7 +967,7 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
         const int g = nth_set_bit(act, ci);
         const float* sp = &sm.sph[g][0][e];
         const V3 xx = mk(sp[0], sp[QE], sp[2 * QE]);
-        const float dist = sp[3 * QE];
+        const float dist = b.p[2] + sp[2 * QE];
         pos[0] = dist > 0.f ? -dist * idt : -dist * (float)ILRL_CONTACT_ERP * idt;
 #pragma unroll
         for (int i = 0; i < 3; i++) {

@@ -514,7 +514,7 @@ def test_both_shared_memory_layouts_are_bit_identical(monkeypatch):
     g.manual_seed(3)
     acts = [(torch.rand(n, 17, device="cuda", generator=g) * 2 - 1) * (3.0 if t % 3 == 0 else 1.0) for t in range(12)]
     outs = {}
-    for layout in ("small", "large"):
+    for layout in ("small", "large", "dense4"):
         monkeypatch.setenv("ILRL_LAYOUT", layout)
         for mode in ("low", "hier"):
             clips = ["motion08_03", "motion09_03"]
@@ -530,9 +530,10 @@ def test_both_shared_memory_layouts_are_bit_identical(monkeypatch):
             outs[(layout, mode)] = rec
             env.close()
     for mode in ("low", "hier"):
-        for x, y in zip(outs[("small", mode)], outs[("large", mode)]):
-            for u, v in zip(x, y):
-                assert torch.equal(u, v), mode
+        for other in ("large", "dense4"):
+            for x, y in zip(outs[("small", mode)], outs[(other, mode)]):
+                for u, v in zip(x, y):
+                    assert torch.equal(u, v), (mode, other)
 
 
 def test_reference_evaluation_loop_runs_unchanged():

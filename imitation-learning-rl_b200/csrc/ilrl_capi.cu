@@ -172,29 +172,38 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     if (role == 0) { a.reward[i] = 0.f; a.done[i] = 0; }
     if (a.terms)
       for (int t = role; t < ILRL_TERM_WORDS; t += 4) a.terms[(size_t)i * ILRL_TERM_WORDS + t] = 0.f;
-  } else if (valid) {
-    chain::Base b;
+  }
+  // envs that step.  The physics substeps run between CTA barriers: the warps of a CTA (and, because tiles start
+  // together, mostly the CTAs of an SM) then execute the same 70 KB of substep code at about the same time and share
+  // the instruction cache — +4 % at 16384 envs, +5 % at 65536 (6 to 8 unsynchronised warps per SM otherwise thrash it).
+  const bool active = valid && !pending;
+  chain::Base b;
+  float act[NJ];
+  float stale_x = 0.f, stale_y = 0.f;
+  float sumx = 0.f, sumy = 0.f, rfx = 0.f, rfy = 0.f;
+  if (active) {
     chain::load_base(a.phys, a.n, i, b);
     chain::load_links(a.phys, a.n, i, sm, e, tid, role);
-    float act[NJ];
 #pragma unroll
     for (int m = 0; m < NJ; m++) act[m] = sm.act(e)[m];
     set_torques(sm, e, tid, role, sm.act(e), nullptr);
     __syncwarp(qm);
-    float stale_x = 0.f, stale_y = 0.f;
-    float sumx, sumy, rfx, rfy;
     if (MODE == 1) {
       // (Q13) robot_pos is refreshed from the PREVIOUS calc_state at the top of step()
       chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);
       stale_x = (32.f * b.p[0] + sumx) * (1.f / 33.f);
       stale_y = (32.f * b.p[1] + sumy) * (1.f / 33.f);
     }
-    if (!a.skip_physics) {
-      float* gscr = a.gscr + (size_t)i * chain::GROWS * chain::RW;
+  }
+  if (!a.skip_physics) {
+    float* gscr = a.gscr + (size_t)(valid ? i : 0) * chain::GROWS * chain::RW;
 #pragma unroll 1
-      for (int sub = 0; sub < ILRL_SUBSTEPS; sub++)
-        chain::substep(b, sm, gscr, e, tid, role, qm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+    for (int sub = 0; sub < ILRL_SUBSTEPS; sub++) {
+      __syncthreads();
+      if (active) chain::substep(b, sm, gscr, e, tid, role, qm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
     }
+  }
+  if (active) {
     chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);
     Phys ps;
     chain::gather(b, sm, e, qb, qm, ps);
@@ -644,7 +653,7 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   {
     // Layout.  The step kernel is persistent: resident CTAs (SMs x CTAs per SM) pull 16-env tiles,
     // so a step takes x = tiles / resident CTAs "rounds", the last one partly filled.  Measured on B200 (us per full
-    // round): on-chip 97 (2 CTAs per SM), dense 127 (3 per SM), dense4 171 (4 per SM); a partly filled round costs
+    // round): on-chip 95 (2 CTAs per SM), dense 121 (3 per SM), dense4 157 (4 per SM); a partly filled round costs
     // between the single-wave latency (~90) and the full-round time.  Estimate all three, take the smallest:
     //   4096 envs -> on chip; 6144 -> dense (1 round instead of 2); 8192 -> dense4 (1 round: 43.7 M env-steps/s against
     //   38.6 on chip / 34.3 dense); 12288 -> dense (43.8 against 41.3 / 41.2); 16384 -> dense4 (2 rounds instead of 3:
@@ -670,7 +679,7 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
       env->layout = (o[0] == 'l' || o[0] == 'L') ? 1 : (o[0] == 'd' || o[0] == 'D') ? 2 : 0;
     } else {
       const float tiles = (float)((n + QE - 1) / QE);
-      const float t_round[3] = {97.f, 127.f, 171.f}, t_wave = 90.f;
+      const float t_round[3] = {95.f, 121.f, 157.f}, t_wave = 90.f;
       const int grid[3] = {env->grid_small, env->grid_large, env->grid_dense4};
       float best = 0.f;
       for (int l = 0; l < 3; l++) {

@@ -652,12 +652,13 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaFuncSetAttribute(physics_only_kernel<SmemDense4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDense4)));
   {
     // Layout.  The step kernel is persistent: resident CTAs (SMs x CTAs per SM) pull 16-env tiles,
-    // so a step takes x = tiles / resident CTAs "rounds", the last one partly filled.  Measured on B200 (us per full
-    // round): on-chip 95 (2 CTAs per SM), dense 121 (3 per SM), dense4 157 (4 per SM); a partly filled round costs
-    // between the single-wave latency (~90) and the full-round time.  Estimate all three, take the smallest:
-    //   4096 envs -> on chip; 6144 -> dense (1 round instead of 2); 8192 -> dense4 (1 round: 43.7 M env-steps/s against
-    //   38.6 on chip / 34.3 dense); 12288 -> dense (43.8 against 41.3 / 41.2); 16384 -> dense4 (2 rounds instead of 3:
-    //   50.2 against 45.9 dense / 43.0 on chip); 32768, 65536 -> dense and dense4 within 2 % (52.0 / 52.9, 56.1 / 55.4).
+    // so a step takes x = tiles / resident CTAs "rounds", the last one partly filled.  Measured on B200 (us per round
+    // in steady state): on-chip 93 (2 CTAs per SM), dense 121 (3 per SM), dense4 155 (4 per SM); a partly filled round
+    // costs between the single-wave latency (~90) and the full-round time.  Estimate all three, take the smallest.
+    // Measured (M env-steps/s: on chip / dense / dense4; * = chosen):
+    //    4096: 33.0* /  -   /  -        6144: 30.8 / 36.6* / 35.9     8192: 38.8 / 34.6 / 45.2*   12288: 41.4 / 45.1* / 41.8
+    //   16384: 43.3 / 46.4 / 52.1*     24576: 45.2 / 51.4 / 54.4*    32768: 49.4 / 54.4 / 55.7*   65536: 50.7 / 58.7 / 60.2*
+    //  131072: 50.9 / 60.6 / 61.1*
     // ILRL_LAYOUT=small|large|dense4 overrides (measurement aid).
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
@@ -679,13 +680,13 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
       env->layout = (o[0] == 'l' || o[0] == 'L') ? 1 : (o[0] == 'd' || o[0] == 'D') ? 2 : 0;
     } else {
       const float tiles = (float)((n + QE - 1) / QE);
-      const float t_round[3] = {95.f, 121.f, 157.f}, t_wave = 90.f;
+      const float t_round[3] = {93.f, 121.f, 155.f}, t_wave = 90.f;
       const int grid[3] = {env->grid_small, env->grid_large, env->grid_dense4};
       float best = 0.f;
       for (int l = 0; l < 3; l++) {
         const float x = tiles / (float)grid[l], full = floorf(x), frac = x - full;
-        // (from 4 rounds on the CTAs have drifted apart and the tile queue keeps every SM busy: time ~ x)
-        const float est = x >= 4.f ? x * t_round[l] : full * t_round[l] + (frac > 0.f ? t_wave + (t_round[l] - t_wave) * frac : 0.f);
+        // (from 8 rounds on the CTAs have drifted apart and the tile queue keeps every SM busy: time ~ x)
+        const float est = x >= 8.f ? x * t_round[l] : full * t_round[l] + (frac > 0.f ? t_wave + (t_round[l] - t_wave) * frac : 0.f);
         if (l == 0 || est < best) { best = est; env->layout = l; }
       }
     }

@@ -185,8 +185,8 @@ constexpr int TABLE_WORDS = sizeof(Tables) / 4;
 static_assert(sizeof(Tables) % 4 == 0, "table copy is word-wise");
 
 // ---- shared memory of one CTA, in three layouts chosen by the host from the batch size (ilrl_create)
-//   LayoutSmall : up to one wave of CTAs at 2 per SM (<= 4736 envs on 148 SMs): everything on chip - 16 rows per env,
-//                 padded (conflict-free) body records, model tables in shared memory.  98 KB.
+//   LayoutSmall : up to one wave of CTAs at 2 per SM (<= 4736 envs on 148 SMs): everything on chip - 20 rows per env,
+//                 padded (conflict-free) body records, model tables in shared memory.  108 KB.
 //   LayoutLarge : larger batches, where resident warps per SM are what limits throughput: 8 rows per env on chip (the
 //                 rest in the L2-resident global scratch), unpadded body records, model tables read through L1.
 //                 73 KB -> 3 CTAs per SM (7104 envs per wave).
@@ -210,7 +210,10 @@ struct Layout {
 #define ILRL_LARGE_TSM false
 #endif
 static_assert(ILRL_LARGE_RSM >= MIN_RSM, "the overflow scratch holds MAXROWS - MIN_RSM rows per env");
-using LayoutSmall = Layout<16, 20, true, 40>;
+#ifndef ILRL_SMALL_RSM
+#define ILRL_SMALL_RSM 20   // 16 -> 20: +3 % at 4096 envs (fewer envs overflow, and a warp with both kinds runs two loop variants)
+#endif
+using LayoutSmall = Layout<ILRL_SMALL_RSM, 20, true, 40>;
 using LayoutLarge = Layout<ILRL_LARGE_RSM, ILRL_LARGE_BRW, ILRL_LARGE_TSM, 40>;
 using LayoutDense4 = Layout<2, 16, false, 32>;
 

@@ -327,7 +327,13 @@ def run_ours(args):
                          "traffic": traffic, "peak_source": which, "kernel_ms": kern_ms,
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n,
                          "note": "latency/issue-bound path (SURVEY 8d): HBM fraction is reported as the tier asks; "
-                                 "see profiles/ for SM issue utilisation"},
+                                 "see profiles/ for SM issue utilisation",
+                         # informative second view: what actually bounds the kernel.  6018 warp-instructions per
+                         # env-step (smsp__inst_executed.sum / 4096, profiles/r1_v7_step_kernel_ncu.md) against
+                         # 4 issue slots per SM per cycle at the sampled SM clock
+                         "issue": {"achieved_gwarp_inst_s": 6018.0 * n / (kern_ms * 1e-3) * 1e-9,
+                                   "peak_gwarp_inst_s": 148 * 4 * float((clk or {}).get("sm_mhz") or 1965.0) * 1e-3,
+                                   "warp_inst_per_env_step": 6018}},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 17 * 4,
                     "d2h_bytes_per_step": n * (70 * 4 + 4 + 1), "steps": KE,

@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   // together, mostly the CTAs of an SM) then execute the same 70 KB of substep code at about the same time and share
   // the instruction cache — +4 % at 16384 envs, +5 % at 65536 (6 to 8 unsynchronised warps per SM otherwise thrash it).
   const bool active = valid && !pending;
+  const unsigned wm = __ballot_sync(0xffffffffu, active);   // lanes of this warp that run the substeps
   chain::Base b;
   float act[NJ];
   float stale_x = 0.f, stale_y = 0.f;
@@ -200,7 +201,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
 #pragma unroll 1
     for (int sub = 0; sub < ILRL_SUBSTEPS; sub++) {
       __syncthreads();
-      if (active) chain::substep(b, sm, gscr, e, tid, role, qm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+      if (active) chain::substep(b, sm, gscr, e, tid, role, qm, wm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
     }
   }
   __syncthreads();   // the once-per-step tail (4 k instructions) is entered together as well: +3 % at 65536 envs
@@ -464,6 +465,7 @@ __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const flo
   const int i = blockIdx.x * QE + e;
   quad_smem_init(sm);
   __syncthreads();
+  const unsigned wm = __ballot_sync(0xffffffffu, i < v.n);
   if (i >= v.n) return;
   chain::Base b;
   chain::load_base(v.phys, v.n, i, b);
@@ -472,7 +474,7 @@ __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const flo
   __syncwarp(qm);
   float* gscr = gscr_all + (size_t)i * chain::GROWS * chain::RW;
   for (int sub = 0; sub < nsub; sub++)
-    chain::substep(b, sm, gscr, e, tid, role, qm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+    chain::substep(b, sm, gscr, e, tid, role, qm, wm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
   Phys ps;
   chain::gather(b, sm, e, qb, qm, ps);
   chain::store_phys(v.phys, v.n, i, role, ps);

@@ -660,12 +660,13 @@ __device__ __forceinline__ void walk_in3(const SM& sm, const Imp* im, float* su0
 }
 
 // contact = true: im[0..2] are the normal and the two friction directions of one contact (all rows used, same chain)
+// e, qb: the env whose rows are built (any env of this warp); su_e, su_lane: the scratch slot of the EXECUTING lane
 template <class SM>
-__device__ __forceinline__ void responses3(SM& sm, Imp* im, const float* nub, int e, int tid, int qb, float idt,
+__device__ __forceinline__ void responses3(SM& sm, Imp* im, const float* nub, int e, int su_e, int su_lane, int qb, float idt,
                                            const float* pos /* [3] position term of each row */, bool contact) {
-  float* su0 = sm.su(e, tid & 3, 0);
-  float* su1 = sm.su(e, tid & 3, 1);
-  float* su2 = sm.su(e, tid & 3, 2);
+  float* su0 = sm.su(su_e, su_lane, 0);
+  float* su1 = sm.su(su_e, su_lane, 1);
+  float* su2 = sm.su(su_e, su_lane, 2);
   // clear the rows
 #pragma unroll
   for (int i = 0; i < 3; i++)
@@ -835,7 +836,8 @@ __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int
 
 // ---- one substep of dt for the env of this quad.  Joint state / torques live in the link records.
 template <class SM>
-__device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int tid, int role, unsigned qm, float dt) {
+__device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int tid, int role, unsigned qm, unsigned wm,
+                                        float dt) {
   constexpr int RSM = SM::RSM;
   const int qb = tid & ~3;
   const Tables& T = tables(sm);
@@ -934,62 +936,95 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
   for (int i = 0; i < 6; i++) dvb[i] = 0.f;
 #pragma unroll
   for (int i = 0; i < NL; i++) dvc[i] = 0.f;
-  if (nrows > 0) {
+  // ---- build the rows three at a time (one contact, or up to three limits, per item).  The items of the warp's 8 envs
+  // form ONE pool that is dealt to all its lanes: an env with many rows is helped by the lanes of envs with few (every
+  // input of an item is in shared memory or one shuffle away), so a warp needs ceil(items / lanes) rounds of the
+  // builder instead of max over its envs of ceil(items / 4).  wm = lanes of this warp that execute the substep.
+  {
     const float idt = 1.0f / dt;
-    // the response scratch shares its storage with the body records of the FK phase: clear this lane's part
-    {
-      float* z = sm.su(e, role, 0);
+    const int lane = tid & 31, q_own = lane >> 2;
+    const int nlg_own = (nlim + 2) / 3, nit_own = nlg_own + ncon;
+    int cnt[8], total = 0;
 #pragma unroll
-      for (int i = 0; i < 3 * NL; i++) z[i] = 0.f;
+    for (int q = 0; q < 8; q++) {
+      const int c = __shfl_sync(wm, nit_own, 4 * q);
+      cnt[q] = ((wm >> (4 * q)) & 1u) ? c : 0;   // a quad that does not step has no items (its lanes are not here)
+      total += cnt[q];
     }
-    __syncwarp(qm);
-    // ---- build the rows three at a time; items are dealt round-robin to the 4 lanes
-    const int nlg = (nlim + 2) / 3;
+    if (total > 0) {
+      {  // the response scratch shares its storage with the body records of the FK phase: clear this lane's part
+        float* z = sm.su(e, role, 0);
+#pragma unroll
+        for (int i = 0; i < 3 * NL; i++) z[i] = 0.f;
+      }
+      const int nlanes = __popc(wm), rank = __popc(wm & ((1u << lane) - 1u));
 #pragma unroll 1
-    for (int it = role; it < nlg + ncon; it += 4) {
-      Imp im[3];
-      float pos[3] = {0.f, 0.f, 0.f};
-      int r0;
-      if (it < nlg) {
-        r0 = 3 * it;
+      for (int g0 = 0; g0 < total; g0 += nlanes) {
+        // item g -> (quad q, item k of that quad's env)
+        int k = g0 + rank, q = 0;
+        const bool has = k < total;
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-          im[i].row = nullptr; im[i].L = -1; im[i].c = -1; im[i].jl = 1; im[i].dir = 0.f; im[i].F = svzero();
-          if (r0 + i < nlim) {
-            const int j = nth_set_bit(lim, r0 + i);
-            im[i].L = T.jL[j]; im[i].c = T.jC[j];
-            const float q = link_rec_of(sm, im[i].L, im[i].c, e, qb)[W_Q];
-            float pen;
-            if (q - kJointLo[j] <= 0.f) { pen = q - kJointLo[j]; im[i].dir = 1.f; } else { pen = kJointHi[j] - q; im[i].dir = -1.f; }
-            pos[i] = -pen * (float)ILRL_LIMIT_ERP * idt;
+        for (int t = 0; t < 7; t++)
+          if (q == t && k >= cnt[t]) { k -= cnt[t]; q = t + 1; }
+        if (!has) { q = q_own; k = 0; }
+        const int src = 4 * q;
+        const uint32_t lim_q = __shfl_sync(wm, lim, src), act_q = __shfl_sync(wm, act, src);
+        const int nlim_q = __shfl_sync(wm, nlim, src);
+        const float bz_q = __shfl_sync(wm, b.p[2], src);
+        float nub_q[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) nub_q[i] = __shfl_sync(wm, nub[i], src);
+        if (has) {
+          const int e_q = (e & ~7) + q, qb_q = (tid & ~31) + 4 * q, nlg_q = (nlim_q + 2) / 3;
+          float* gscr_q = gscr + (ptrdiff_t)(q - q_own) * (GROWS * RW);
+          const int it = k;
+          Imp im[3];
+          float pos[3] = {0.f, 0.f, 0.f};
+          int r0;
+          if (it < nlg_q) {
+            r0 = 3 * it;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              im[i].row = nullptr; im[i].L = -1; im[i].c = -1; im[i].jl = 1; im[i].dir = 0.f; im[i].F = svzero();
+              if (r0 + i < nlim_q) {
+                const int j = nth_set_bit(lim_q, r0 + i);
+                im[i].L = T.jL[j]; im[i].c = T.jC[j];
+                const float q_ = link_rec_of(sm, im[i].L, im[i].c, e_q, qb_q)[W_Q];
+                float pen;
+                if (q_ - kJointLo[j] <= 0.f) { pen = q_ - kJointLo[j]; im[i].dir = 1.f; } else { pen = kJointHi[j] - q_; im[i].dir = -1.f; }
+                pos[i] = -pen * (float)ILRL_LIMIT_ERP * idt;
+              }
+            }
+          } else {
+            const int ci = it - nlg_q;
+            r0 = nlim_q + 3 * ci;
+            const int g = nth_set_bit(act_q, ci);
+            const float* sp = &sm.sph[g][0][e_q];
+            const V3 xx = mk(sp[0], sp[QE], sp[2 * QE]);
+            const float dist = bz_q + sp[2 * QE];
+            pos[0] = dist > 0.f ? -dist * idt : -dist * (float)ILRL_CONTACT_ERP * idt;
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              im[i].L = T.sphL[g]; im[i].c = T.sphC[g]; im[i].jl = 0; im[i].dir = 0.f;
+              // normal (0,0,1), tangents btPlaneSpace1 -> (0,-1,0), (1,0,0)
+              im[i].F.l = i == 0 ? mk(0.f, 0.f, 1.f) : (i == 1 ? mk(0.f, -1.f, 0.f) : mk(1.f, 0.f, 0.f));
+              im[i].F.a = cross(xx, im[i].F.l);
+            }
           }
-        }
-      } else {
-        const int ci = it - nlg;
-        r0 = nlim + 3 * ci;
-        const int g = nth_set_bit(act, ci);
-        const float* sp = &sm.sph[g][0][e];
-        const V3 xx = mk(sp[0], sp[QE], sp[2 * QE]);
-        const float dist = b.p[2] + sp[2 * QE];
-        pos[0] = dist > 0.f ? -dist * idt : -dist * (float)ILRL_CONTACT_ERP * idt;
 #pragma unroll
-        for (int i = 0; i < 3; i++) {
-          im[i].L = T.sphL[g]; im[i].c = T.sphC[g]; im[i].jl = 0; im[i].dir = 0.f;
-          // normal (0,0,1), tangents btPlaneSpace1 -> (0,-1,0), (1,0,0)
-          im[i].F.l = i == 0 ? mk(0.f, 0.f, 1.f) : (i == 1 ? mk(0.f, -1.f, 0.f) : mk(1.f, 0.f, 0.f));
-          im[i].F.a = cross(xx, im[i].F.l);
+          for (int i = 0; i < 3; i++) {
+            const int r = r0 + i;
+            const bool used = it >= nlg_q || r < nlim_q;
+            im[i].row = !used ? nullptr : (r < RSM ? &sm.rows[e_q][r * RW] : gscr_q + (size_t)(r - RSM) * RW);
+            if (used) { sm.lam(e_q)[r] = 0.f; sm.rowL(e_q)[r] = (signed char)(im[i].c >= 3 ? im[i].L : -1); }
+          }
+          responses3(sm, im, nub_q, e_q, e, role, qb_q, idt, pos, it >= nlg_q);
         }
       }
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const int r = r0 + i;
-        const bool used = it >= nlg || r < nlim;
-        im[i].row = !used ? nullptr : (r < RSM ? &sm.rows[e][r * RW] : gscr + (size_t)(r - RSM) * RW);
-        if (used) { sm.lam(e)[r] = 0.f; sm.rowL(e)[r] = (signed char)(im[i].c >= 3 ? im[i].L : -1); }
-      }
-      responses3(sm, im, nub, e, tid, qb, idt, pos, it >= nlg);
+      __syncwarp(wm);   // rows of an env may have been written by lanes of another quad
     }
-    __syncwarp(qm);
+  }
+  if (nrows > 0) {
     // ---- projected Gauss-Seidel on the velocity change
     // One loop variant per layout wherever both would be common: the quads of a warp that took different variants
     // run them one after the other (+4..9 % in the dense layouts from dropping the split).  Only the on-chip layout,

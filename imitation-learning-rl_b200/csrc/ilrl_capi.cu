@@ -657,11 +657,11 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
     // Layout.  The step kernel is persistent: resident CTAs (SMs x CTAs per SM) pull 16-env tiles,
     // so a step takes x = tiles / resident CTAs "rounds", the last one partly filled.  Measured on B200 (us per round
     // in steady state): on-chip 94 (2 CTAs per SM), dense 115 (3 per SM), dense4 141 (4 per SM); a partly filled round
-    // costs between the single-wave latency (~90) and the full-round time.  Estimate all three, take the smallest.
+    // costs between the single-wave latency (~80) and the full-round time.  Estimate all three, take the smallest.
     // Measured (M env-steps/s: on chip / dense / dense4; * = chosen):
-    //    4096: 32.8* / 29.8 / 27.6      6144: 30.6 / 40.2* / 37.3     8192: 38.6 / 36.5 / 47.0*   12288: 41.2 / 47.4* / 44.0
-    //   16384: 43.1 / 48.6 / 54.8*     24576: 45.1 / 53.3 / 57.7*    32768: 49.2 / 55.8 / 59.8*   65536: 50.5 / 60.5 / 65.8*
-    //  131072: 50.6 / 61.8 / 67.3*
+    //    4096: 37.9* / 32.7 / 29.5      6144: 32.1 / 43.5* / 39.6     8192: 41.5 / 37.4 / 50.0*   12288: 43.1 / 49.2* / 45.0
+    //   16384: 44.2 / 49.2 / 56.3*     24576: 45.5 / 53.7 / 58.7*    32768: 49.8 / 56.1 / 60.1*   65536: 50.7 / 60.6 / 65.7*
+    //  131072: 50.6 / 61.7 / 67.0*
     // ILRL_LAYOUT=small|large|dense4 overrides (measurement aid).
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
@@ -683,7 +683,7 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
       env->layout = (o[0] == 'l' || o[0] == 'L') ? 1 : (o[0] == 'd' || o[0] == 'D') ? 2 : 0;
     } else {
       const float tiles = (float)((n + QE - 1) / QE);
-      const float t_round[3] = {94.f, 115.f, 141.f}, t_wave = 90.f;
+      const float t_round[3] = {94.f, 115.f, 141.f}, t_wave = 80.f;
       const int grid[3] = {env->grid_small, env->grid_large, env->grid_dense4};
       float best = 0.f;
       for (int l = 0; l < 3; l++) {

@@ -107,16 +107,20 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    envs_per_core = 64  # bounded sample of the 4096-env workload: `cores` x 64 envs advance one env step per "step"
-    total, dt = cpu_rollout(cores, envs_per_core, args.warmup, args.steps)
+    envs_per_core = 64  # bounded sample of the 4096-env workload: `cores` x 64 envs
+    # one "step" of this arm advances every sampled env by `inner` env steps, sized so that the timed part lasts about
+    # 12 s whatever K is (a 20-step run of single env steps would time 20 ms of cold threads: measured 0.12 M env-steps/s
+    # against 0.21 M in steady state)
+    inner = max(1, min(200, int(12.0 * 2.0e5 / (cores * envs_per_core * max(args.steps, 1)))))
+    total, dt = cpu_rollout(cores, envs_per_core, min(args.warmup * inner, 200), args.steps * inner)
     value = total / dt
-    sample = "%d host threads x %d oracle envs (C, fp64, dense 23x23 dynamics) x %d steps of the same workload" % (
-        cores, envs_per_core, args.steps)
+    sample = "%d host threads x %d oracle envs (C, fp64, dense 23x23 dynamics) x %d steps of %d env steps of the same workload" % (
+        cores, envs_per_core, args.steps, inner)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_step": cores * envs_per_core,
+        "config": {"workload": WORKLOAD, "envs_per_step": cores * envs_per_core, "env_steps_per_env_per_step": inner,
                    "note": "reference arm = oracle/ilrl_oracle.c (port of the reference path; the reference's own "
                            "implementation needs PyBullet, which is not installable here)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},

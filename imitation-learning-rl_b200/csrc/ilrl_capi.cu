@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     if (w.e[ILRL_E_T] >= (float)a.max_timestep) done = true;
     w.e[ILRL_E_EP_RETURN] += reward;
     w.e[ILRL_E_EP_LEN] += 1.f;
-    float* so = &sm.rows[e][0];  // the env's row block is free after the substeps: stage the obs row there
+    float* so = &sm.scr[e][0];  // the env's scratch block is free after the substeps: stage the obs row there
     {
       float obs[70];
       write_low_obs(c.obs, w, cl, obs);
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     const int cnt = min(QE, a.n - base) * 70;
     for (int t = tid; t < cnt; t += QT) {
       int r = t / 70, cc = t - r * 70;
-      if ((wrote[r >> 3] >> ((r & 7) * 4)) & 1u) a.obs[(size_t)base * 70 + t] = sm.rows[r][cc];
+      if ((wrote[r >> 3] >> ((r & 7) * 4)) & 1u) a.obs[(size_t)base * 70 + t] = sm.scr[r][cc];
     }
   }
   // K5: episode / reward statistics -> one atomicAdd per warp per slot

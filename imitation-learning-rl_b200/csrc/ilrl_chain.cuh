@@ -33,20 +33,19 @@ namespace chain {
 constexpr int QE = ILRL_QE;            // envs per CTA
 constexpr int QT = 4 * QE;             // threads per CTA
 constexpr int NL = 7;                  // chain links per lane: 3 spine + 4 limb slots
-constexpr int RW = 40;                 // words per stored row
+constexpr int RW = 16;                 // words per stored row
 #ifndef ILRL_MIN_RSM
-#define ILRL_MIN_RSM 2   // = the row budget of LayoutDense4
+#define ILRL_MIN_RSM 4   // = the row budget of LayoutDense4
 #endif
 constexpr int MIN_RSM = ILRL_MIN_RSM;  // smallest on-chip row budget of any layout
 constexpr int GROWS = MAXROWS - MIN_RSM;  // rows per env in the global overflow scratch
-// link record: 24 words in 6 float4 (S | cJ | U dinv u | q qd tau nu), one contiguous 28-word slot per thread: a
+// link record: 25 words (S | cJ | U dinv u | q qd tau nu | sqrt(dinv)), one contiguous 28-word slot per thread: a
 // 28-word stride puts the float4 of 8 consecutive threads in 8 different bank groups (conflict-free LDS.128 / STS.128)
-enum { W_S = 0, W_CJ = 6, W_U = 12, W_DINV = 18, W_UU = 19, W_Q = 20, W_QD = 21, W_TAU = 22, W_NU = 23, LKW = 28 };
+enum { W_S = 0, W_CJ = 6, W_U = 12, W_DINV = 18, W_UU = 19, W_Q = 20, W_QD = 21, W_TAU = 22, W_NU = 23, W_SQD = 24, LKW = 28 };
 // body record words: rigid inertia about the reference point (A 6, m*c 3, m 1) + bias force 6
 constexpr int RECW = 16;
-// stored row words
-enum { R_RB = 0 /*resp base 6*/, R_RS = 6 /*resp spine 3*/, R_JS = 9 /*J spine 3*/, R_JB = 12 /*J base 6*/, R_RHS = 18,
-       R_DINV = 19, R_RL = 20 /*resp limbs 4x4*/, R_JL = 36 /*J of the row's limb 4*/ };
+// stored row words (whitened rows, see "constraint rows" below)
+enum { R_ZB = 0 /*base 6*/, R_RHS = 6, R_DINV = 7, R_ZS = 8 /*spine 3*/, R_LIMB = 11, R_ZL = 12 /*the row's limb 4*/ };
 
 // ---- compile-time model tables in chain form
 struct LinkC {
@@ -185,17 +184,15 @@ constexpr int TABLE_WORDS = sizeof(Tables) / 4;
 static_assert(sizeof(Tables) % 4 == 0, "table copy is word-wise");
 
 // ---- shared memory of one CTA, in three layouts chosen by the host from the batch size (ilrl_create)
-//   LayoutSmall : up to one wave of CTAs at 2 per SM (<= 4736 envs on 148 SMs): everything on chip - 20 rows per env,
-//                 padded (conflict-free) body records, model tables in shared memory.  108 KB.
-//   LayoutLarge : larger batches, where resident warps per SM are what limits throughput: 8 rows per env on chip (the
+//   LayoutSmall : up to one wave of CTAs at 2 per SM (<= 4736 envs on 148 SMs): everything on chip - every possible
+//                 row of an env (41, no overflow path at all), padded (conflict-free) body records, model tables in
+//                 shared memory.
+//   LayoutLarge : larger batches, where resident warps per SM are what limits throughput: 16 rows per env on chip (the
 //                 rest in the L2-resident global scratch), unpadded body records, model tables read through L1.
-//                 73 KB -> 3 CTAs per SM (7104 envs per wave).
-//   LayoutDense4: 2 rows per env on chip, body-view lane stride 32 (4-way bank conflicts on its 4 float4 accesses per
-//                 substep).  55.5 KB -> 4 CTAs per SM (9472 envs per wave): a tile is ~1.35x slower than LayoutLarge's,
-//                 so it wins exactly where it saves a round of tiles (8192 envs: 1 instead of 2; 16384: 2 instead of 3).
+//   LayoutDense4: 4 rows per env on chip, body-view lane stride 32 (4-way bank conflicts on its 4 float4 accesses per
+//                 substep): 4 CTAs per SM.
 // In all, the body records (written by the FK phase, consumed by the inward pass) share their storage with what
-// only the row phase uses (response scratch, multipliers, row owners) and with the action tile (consumed before the
-// first substep).
+// only the row phase uses (multipliers) and with the action tile (consumed before the first substep).
 template <int RSM_, int BRW_, bool TSM_, int LANE_>
 struct Layout {
   static constexpr int RSM = RSM_;               // constraint rows per env kept in shared memory
@@ -205,27 +202,26 @@ struct Layout {
   static constexpr int LANE = LANE_;             // lane stride of the body view in the per-env scratch block (words)
 };
 #ifndef ILRL_LARGE_RSM  // (overridable for layout experiments)
-#define ILRL_LARGE_RSM 8
+#define ILRL_LARGE_RSM 16
 #define ILRL_LARGE_BRW 16
 #define ILRL_LARGE_TSM false
 #endif
 static_assert(ILRL_LARGE_RSM >= MIN_RSM, "the overflow scratch holds MAXROWS - MIN_RSM rows per env");
 #ifndef ILRL_SMALL_RSM
-#define ILRL_SMALL_RSM 20   // 16 -> 20: +3 % at 4096 envs (fewer envs overflow, and a warp with both kinds runs two loop variants)
+#define ILRL_SMALL_RSM 42   // >= MAXROWS: no env of this layout ever has an overflow row
 #endif
 using LayoutSmall = Layout<ILRL_SMALL_RSM, 20, true, 40>;
 using LayoutLarge = Layout<ILRL_LARGE_RSM, ILRL_LARGE_BRW, ILRL_LARGE_TSM, 40>;
-using LayoutDense4 = Layout<2, 16, false, 32>;
+using LayoutDense4 = Layout<ILRL_MIN_RSM, 16, false, 32>;
 
 // Per-env scratch block, seen in two ways that are never live at the same time within an env:
 //   body view (FK phase -> inward pass): body records of the four lanes (2 each, lane stride LANE words) + the spine's 2
-//   row view  (row phase)              : response scratch u[lane][3 impulses][7 links], multipliers, action tile
-//                                        (consumed before the first substep), row owners (bytes)
+//   row view  (row phase)              : multipliers, action tile (consumed before the first substep)
 // The block is PER ENV because warps of a CTA run unsynchronised: one env's row phase must never touch another env's
 // body records.  Env stride = 4 (mod 32) words and lane stride 40 (LayoutSmall / LayoutLarge): the float4 accesses of the 2 envs x 4 lanes of a
 // quarter-warp fall in 8 different bank groups, and scalar accesses of the 8 envs of a warp in 8 different banks.
-constexpr int SCR_SU = 0, SCR_LAM = 4 * 3 * NL, SCR_ACT = SCR_LAM + MAXROWS, SCR_ROWL = SCR_ACT + NJ;  // row view (words)
-constexpr int SCR_ROWVIEW = SCR_ROWL + (MAXROWS + 3) / 4;
+constexpr int SCR_LAM = 0, SCR_ACT = SCR_LAM + MAXROWS;  // row view (words)
+constexpr int SCR_ROWVIEW = SCR_ACT + NJ;
 template <int BRW, int LANE> constexpr int scr_words() {
   int w = 4 * LANE + 2 * BRW;                      // body view
   if (w < SCR_ROWVIEW) w = SCR_ROWVIEW;
@@ -241,25 +237,24 @@ struct __align__(16) SmemT {
   static constexpr int SCR_LANE = LY::LANE;
   static_assert(2 * BRW <= SCR_LANE, "two body records per lane");
   // --- float4-accessed arrays first (every size below is a multiple of 16 bytes)
-  float rows[QE][ROWSTRIDE];   // stored rows; after the substeps the first 71 words of an env's block stage its obs row
+  float rows[QE][ROWSTRIDE];   // stored rows
   float lk[4][QT][LKW];        // limb link records, per thread
   float sp[3][QE][LKW];        // spine link records, per env
-  float scr[QE][ES];           // per-env scratch block (see above)
+  float scr[QE][ES];           // per-env scratch block (see above); after the substeps its first 70 words stage the obs row
   // --- scalar-accessed
   float L0[21][QE];            // Cholesky factor of the base articulated inertia
   float sph[NS][3][QE];        // contact candidates: x, y, z - r relative to the torso origin (distance = base z + that)
   typename std::conditional<TSM, Tables, NoTables>::type T;
   static_assert((sizeof(float) * QE * ROWSTRIDE) % 16 == 0 && (sizeof(float) * LKW) % 16 == 0 && BRW % 4 == 0 && ES % 4 == 0,
                 "float4 alignment of the shared-memory records");
-  static_assert(ROWSTRIDE >= 71, "the obs row is staged in the env's row block");
+  static_assert(ES >= 71, "the obs row is staged in the env's scratch block");
+  static_assert(RSM % 2 == 0, "env stride of the rows = 4 (mod 32) words");
   // body view
   __device__ __forceinline__ float* rl(int e, int lane, int slot) { return &scr[e][lane * SCR_LANE + slot * BRW]; }
   __device__ __forceinline__ float* rs(int e, int slot) { return &scr[e][4 * SCR_LANE + slot * BRW]; }
   // row view
-  __device__ __forceinline__ float* su(int e, int lane, int i) { return &scr[e][SCR_SU + (lane * 3 + i) * NL]; }
   __device__ __forceinline__ float* lam(int e) { return &scr[e][SCR_LAM]; }
   __device__ __forceinline__ float* act(int e) { return &scr[e][SCR_ACT]; }
-  __device__ __forceinline__ signed char* rowL(int e) { return reinterpret_cast<signed char*>(&scr[e][SCR_ROWL]); }
 };
 // the model tables as the kernel sees them: the CTA's shared-memory copy, or the global object through L1
 template <class SM>
@@ -573,263 +568,217 @@ __device__ __forceinline__ void pose_sums(const Base& b, SM& sm, int e, int tid,
   __syncwarp(qm);
 }
 
-// ---- constraint-row construction: responses of the generalized velocities to up to three unit impulses
-struct Imp {
-  int L, c;      // chain that carries the impulse: limb (-1 = spine / torso) and chain index (-1 = torso)
-  int jl;        // 1: generalized impulse `dir` on the joint of (L, c); 0: spatial force F on the body after (L, c)
-  float dir;
-  SV F;
-  float* row;    // where the row is stored (null: slot unused)
-};
+// ---- constraint rows in WHITENED form.
+// With the articulated-body quantities of the inward pass (U_c = IA_c S_c, d_c = S_c . U_c, base factor IA_0 = L0 L0^T)
+// the inverse joint-space inertia factorises as  M^-1 = W^T W,  W = D^-1/2 (inward sweep)  (innovations factorisation;
+// checked numerically against a composite-Jacobian M by tools/check_innovations_identity.py).  A constraint row J_i
+// therefore only needs its own inward sweep  z_i = W J_i^T : the innovations u_c of the links between the row's link
+// and the base, scaled by sqrt(1/d_c), and  L0^-1 (force arriving at the base)  - 13 numbers with the sparsity of J_i
+// itself (base 6, spine 3, the row's limb 4).  J_i M^-1 J_k^T = z_i . z_k, so projected Gauss-Seidel runs on
+// z = sum_k z_k lambda_k  (J_i . dv = z_i . z) and the velocity change  dv = W^T z  is recovered by ONE outward sweep
+// per substep, distributed over the quad like the forward dynamics.  Compared with storing M^-1 J^T per row (the
+// previous generation: an outward sweep over all 19 links per row, 40-word rows) a row costs a walk of <= 7 links,
+// is 16 words, and a Gauss-Seidel evaluation is 13 + 13 multiply-adds.  Same row order, formulas and constants as the
+// oracle (limits in joint order, contact normals, friction pairs; 5 sweeps).
+//
+// stored row (4 float4): zb[0..3] | zb[4] zb[5] rhs dinv | zs[0..2] limb | zl[0..3]      (limb: -1 = spine / torso)
 
-// inward walk of one impulse from its link to the base.  Leaves u of the visited links in su (chain-local), writes the
-// row's Jacobian chain entries, returns the force arriving at the base and rv = J . nu (chain part).
-template <class SM>
-__device__ __forceinline__ SV walk_in(const SM& sm, const Imp& im, float* su, int e, int qb, float& rv) {
-  SV pf = svzero();
-  rv = 0.f;
-  if (!im.row) return pf;
-  int c = im.c;
-  if (im.jl) {
-    const float* rec = link_rec_of(sm, im.L, c, e, qb);
-    SV S, U;
-    float di;
-    ld_SU(rec, S, U, di);
-    su[c] = im.dir;
-    pf = (im.dir * di) * U;
-    rv = im.dir * rec[W_NU];
-    im.row[c < 3 ? R_JS + c : R_JL + c - 3] = im.dir;
-    c--;
-  } else {
-    pf = neg(im.F);
+// y = L^-1 b  /  x = L^-T y  with the packed factor of this env in shared memory (diagonal entries hold 1 / L_jj)
+__device__ __forceinline__ void fwd_subst(const float* L, SV b, float* y) {
+  y[0] = b.a.x; y[1] = b.a.y; y[2] = b.a.z; y[3] = b.l.x; y[4] = b.l.y; y[5] = b.l.z;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float t = y[i];
+#pragma unroll
+    for (int c = 0; c < i; c++) t -= L[(i * (i + 1) / 2 + c) * QE] * y[c];
+    y[i] = t * L[(i * (i + 1) / 2 + i) * QE];
   }
+}
+__device__ __forceinline__ void bwd_subst(const float* L, float* y) {
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    float t = y[i];
+#pragma unroll
+    for (int c = i + 1; c < 6; c++) t -= L[(c * (c + 1) / 2 + i) * QE] * y[c];
+    y[i] = t * L[(i * (i + 1) / 2 + i) * QE];
+  }
+}
+__device__ __forceinline__ void ld_SUq(const float* rec, SV& S, SV& U, float& dinv, float& sqd) {
+  ld_SU(rec, S, U, dinv);
+  sqd = rec[W_SQD];
+}
+
+// row of a violated joint limit on joint j of env e (any env of this warp): generalized impulse `dir` on the joint
+template <class SM>
+__device__ __forceinline__ void build_limit_row(const SM& sm, const Tables& T, int j, int e, int qb, float idt, float* row) {
+  const int L = T.jL[j];
+  int c = T.jC[j];
+  const float* rec0 = link_rec_of(sm, L, c, e, qb);
+  const float q_ = rec0[W_Q], nu = rec0[W_NU];
+  float pen, dir;
+  if (q_ - kJointLo[j] <= 0.f) { pen = q_ - kJointLo[j]; dir = 1.f; } else { pen = kJointHi[j] - q_; dir = -1.f; }
+  float4* r4 = reinterpret_cast<float4*>(row);
+  r4[2] = make_float4(0.f, 0.f, 0.f, __int_as_float(c >= 3 ? L : -1));
+  r4[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  SV pf = svzero();
+  float dd = 0.f, f = dir;
 #pragma unroll 1
   for (; c >= 0; c--) {
-    if (c == 2 && im.L >= 2) break;  // arms attach to the torso
-    const float* rec = link_rec_of(sm, im.L, c, e, qb);
+    if (c == 2 && L >= 2) break;  // arms attach to the torso
     SV S, U;
-    float di;
-    ld_SU(rec, S, U, di);
-    const float u = -sdot(S, pf);
-    su[c] = u;
+    float di, sq;
+    ld_SUq(link_rec_of(sm, L, c, e, qb), S, U, di, sq);
+    const float u = f - sdot(S, pf);
+    f = 0.f;
+    const float z = u * sq;
+    row[c < 3 ? R_ZS + c : R_ZL + c - 3] = z;
+    dd = fmaf(z, z, dd);
     pf = pf + (u * di) * U;
-    if (!im.jl) {
-      const float Jl = sdot(S, im.F);
-      rv += Jl * rec[W_NU];
-      im.row[c < 3 ? R_JS + c : R_JL + c - 3] = Jl;
-    }
   }
-  return pf;
-}
-// J . resp over the chain entries of a finished row, and restore the scratch to zero
-__device__ __forceinline__ float walk_dd(const Imp& im, float* su) {
-  float dd = 0.f;
-  if (!im.row) return dd;
-#pragma unroll 1
-  for (int c = im.c; c >= 0; c--) {
-    if (c == 2 && im.L >= 2) break;
-    su[c] = 0.f;
-    dd += c < 3 ? im.row[R_JS + c] * im.row[R_RS + c] : im.row[R_JL + c - 3] * im.row[R_RL + 4 * im.L + c - 3];
-  }
-  return dd;
+  float y[6];
+  fwd_subst(&sm.L0[0][e], neg(pf), y);
+#pragma unroll
+  for (int i = 0; i < 6; i++) dd = fmaf(y[i], y[i], dd);
+  const float dinv = __frcp_rn(dd);
+  const float pos = -pen * (float)ILRL_LIMIT_ERP * idt;
+  r4[0] = make_float4(y[0], y[1], y[2], y[3]);
+  r4[1] = make_float4(y[4], y[5], (pos - dir * nu) * dinv, dinv);
 }
 
-// the three impulses of ONE contact share their chain: one walk, link records loaded once, 3-way ILP
+// the three rows (normal, two friction directions) of the ground contact of sphere g of env e: one walk, link records
+// loaded once, 3-way instruction-level parallelism.  xx: contact point relative to the torso origin, dist: its height.
 template <class SM>
-__device__ __forceinline__ void walk_in3(const SM& sm, const Imp* im, float* su0, float* su1, float* su2, int e, int qb,
-                                         SV* pf, float* rv) {
+__device__ __forceinline__ void build_contact_rows(const SM& sm, const Tables& T, int g, int e, int qb, float idt, V3 xx,
+                                                   float dist, const float* nub, float* row0, float* row1, float* row2) {
+  const int L = T.sphL[g];
+  int c = T.sphC[g];
+  float* rows[3] = {row0, row1, row2};
+  // normal (0,0,1), tangents btPlaneSpace1 -> (0,-1,0), (1,0,0); spatial force of a unit impulse at the contact point
+  SV F[3], pf[3];
+  F[0].l = mk(0.f, 0.f, 1.f); F[1].l = mk(0.f, -1.f, 0.f); F[2].l = mk(1.f, 0.f, 0.f);
+  float dd[3];
 #pragma unroll
-  for (int i = 0; i < 3; i++) { pf[i] = neg(im[i].F); rv[i] = 0.f; }
-  const int L = im[0].L;
+  for (int i = 0; i < 3; i++) {
+    F[i].a = cross(xx, F[i].l);
+    pf[i] = neg(F[i]);
+    dd[i] = 0.f;
+    float4* r4 = reinterpret_cast<float4*>(rows[i]);
+    r4[2] = make_float4(0.f, 0.f, 0.f, __int_as_float(c >= 3 ? L : -1));
+    r4[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  SV Vb;  // unconstrained new velocity of the contact body: J . nu = F . Vb
+  Vb.a = mk(nub[0], nub[1], nub[2]); Vb.l = mk(nub[3], nub[4], nub[5]);
 #pragma unroll 1
-  for (int c = im[0].c; c >= 0; c--) {
-    if (c == 2 && L >= 2) break;  // arms attach to the torso
+  for (; c >= 0; c--) {
+    if (c == 2 && L >= 2) break;
     const float* rec = link_rec_of(sm, L, c, e, qb);
     SV S, U;
-    float di;
-    ld_SU(rec, S, U, di);
-    const float nu = rec[W_NU];
-    const int jw = c < 3 ? R_JS + c : R_JL + c - 3;
+    float di, sq;
+    ld_SUq(rec, S, U, di, sq);
+    Vb = Vb + rec[W_NU] * S;
+    const int zw = c < 3 ? R_ZS + c : R_ZL + c - 3;
     const float u0 = -sdot(S, pf[0]), u1 = -sdot(S, pf[1]), u2 = -sdot(S, pf[2]);
-    const float J0 = sdot(S, im[0].F), J1 = sdot(S, im[1].F), J2 = sdot(S, im[2].F);
-    su0[c] = u0; su1[c] = u1; su2[c] = u2;
+    const float z0 = u0 * sq, z1 = u1 * sq, z2 = u2 * sq;
+    row0[zw] = z0; row1[zw] = z1; row2[zw] = z2;
+    dd[0] = fmaf(z0, z0, dd[0]); dd[1] = fmaf(z1, z1, dd[1]); dd[2] = fmaf(z2, z2, dd[2]);
     pf[0] = pf[0] + (u0 * di) * U; pf[1] = pf[1] + (u1 * di) * U; pf[2] = pf[2] + (u2 * di) * U;
-    rv[0] += J0 * nu; rv[1] += J1 * nu; rv[2] += J2 * nu;
-    im[0].row[jw] = J0; im[1].row[jw] = J1; im[2].row[jw] = J2;
   }
-}
-
-// contact = true: im[0..2] are the normal and the two friction directions of one contact (all rows used, same chain)
-// e, qb: the env whose rows are built (any env of this warp); su_e, su_lane: the scratch slot of the EXECUTING lane
-template <class SM>
-__device__ __forceinline__ void responses3(SM& sm, Imp* im, const float* nub, int e, int su_e, int su_lane, int qb, float idt,
-                                           const float* pos /* [3] position term of each row */, bool contact) {
-  float* su0 = sm.su(su_e, su_lane, 0);
-  float* su1 = sm.su(su_e, su_lane, 1);
-  float* su2 = sm.su(su_e, su_lane, 2);
-  // clear the rows
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-    if (im[i].row) {
-      float4* r4 = reinterpret_cast<float4*>(im[i].row);
-#pragma unroll 1
-      for (int t = 0; t < RW / 4; t++) r4[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  float rv[3];
-  SV pf[3];
-  if (contact) walk_in3(sm, im, su0, su1, su2, e, qb, pf, rv);
-  else {
-    pf[0] = walk_in(sm, im[0], su0, e, qb, rv[0]);
-    pf[1] = walk_in(sm, im[1], su1, e, qb, rv[1]);
-    pf[2] = walk_in(sm, im[2], su2, e, qb, rv[2]);
-  }
-  // base part: J_base = F (contact rows), response of the base
-  SV ap[3], a0[3], apel[3];
-  float dd[3];
   const float* L0 = &sm.L0[0][e];
 #pragma unroll
   for (int i = 0; i < 3; i++) {
-    a0[i] = chol6_solve_smem(L0, neg(pf[i]));
-    ap[i] = a0[i];
-    dd[i] = 0.f;
-    if (im[i].row) {
-      float* r = im[i].row;
-      r[R_RB + 0] = a0[i].a.x; r[R_RB + 1] = a0[i].a.y; r[R_RB + 2] = a0[i].a.z;
-      r[R_RB + 3] = a0[i].l.x; r[R_RB + 4] = a0[i].l.y; r[R_RB + 5] = a0[i].l.z;
-      if (!im[i].jl) {
-        const SV F = im[i].F;
-        r[R_JB + 0] = F.a.x; r[R_JB + 1] = F.a.y; r[R_JB + 2] = F.a.z; r[R_JB + 3] = F.l.x; r[R_JB + 4] = F.l.y; r[R_JB + 5] = F.l.z;
-        rv[i] += F.a.x * nub[0] + F.a.y * nub[1] + F.a.z * nub[2] + F.l.x * nub[3] + F.l.y * nub[4] + F.l.z * nub[5];
-        dd[i] = sdot(a0[i], F);
-      }
-    }
-  }
-  // outward sweep: spine, then the four limbs
-#pragma unroll 1
-  for (int c = 0; c < 3; c++) {
-    SV S, U;
-    float di;
-    ld_SU(&sm.sp[c][e][0], S, U, di);
-    const float u0 = su0[c], u1 = su1[c], u2 = su2[c];
-    const float q0 = di * (u0 - sdot(ap[0], U)), q1 = di * (u1 - sdot(ap[1], U)), q2 = di * (u2 - sdot(ap[2], U));
-    ap[0] = ap[0] + q0 * S; ap[1] = ap[1] + q1 * S; ap[2] = ap[2] + q2 * S;
-    if (im[0].row) im[0].row[R_RS + c] = q0;
-    if (im[1].row) im[1].row[R_RS + c] = q1;
-    if (im[2].row) im[2].row[R_RS + c] = q2;
-  }
+    float y[6];
+    fwd_subst(L0, neg(pf[i]), y);
+    float d = dd[i];
 #pragma unroll
-  for (int i = 0; i < 3; i++) apel[i] = ap[i];
-#pragma unroll 1
-  for (int r = 0; r < 4; r++) {
-#pragma unroll
-    for (int i = 0; i < 3; i++) ap[i] = r < 2 ? apel[i] : a0[i];
-    const bool m0 = im[0].L == r, m1 = im[1].L == r, m2 = im[2].L == r;
-#pragma unroll 1
-    for (int k = r < 2 ? 0 : 1; k < 4; k++) {  // the arms' leading slot is a dummy: its response stays 0
-      SV S, U;
-      float di;
-      ld_SU(&sm.lk[k][qb + r][0], S, U, di);
-      const float u0 = m0 ? su0[3 + k] : 0.f, u1 = m1 ? su1[3 + k] : 0.f, u2 = m2 ? su2[3 + k] : 0.f;
-      const float q0 = di * (u0 - sdot(ap[0], U)), q1 = di * (u1 - sdot(ap[1], U)), q2 = di * (u2 - sdot(ap[2], U));
-      ap[0] = ap[0] + q0 * S; ap[1] = ap[1] + q1 * S; ap[2] = ap[2] + q2 * S;
-      if (im[0].row) im[0].row[R_RL + 4 * r + k] = q0;
-      if (im[1].row) im[1].row[R_RL + 4 * r + k] = q1;
-      if (im[2].row) im[2].row[R_RL + 4 * r + k] = q2;
-    }
+    for (int k = 0; k < 6; k++) d = fmaf(y[k], y[k], d);
+    const float dinv = __frcp_rn(d);
+    const float pos = i == 0 ? (dist > 0.f ? -dist * idt : -dist * (float)ILRL_CONTACT_ERP * idt) : 0.f;
+    float4* r4 = reinterpret_cast<float4*>(rows[i]);
+    r4[0] = make_float4(y[0], y[1], y[2], y[3]);
+    r4[1] = make_float4(y[4], y[5], (pos - sdot(Vb, F[i])) * dinv, dinv);
   }
-  dd[0] += walk_dd(im[0], su0);
-  dd[1] += walk_dd(im[1], su1);
-  dd[2] += walk_dd(im[2], su2);
-#pragma unroll
-  for (int i = 0; i < 3; i++)
-    if (im[i].row) {
-      const float di = __frcp_rn(dd[i]);
-      im[i].row[R_DINV] = di;
-      im[i].row[R_RHS] = (pos[i] - rv[i]) * di;
-    }
 }
 
-// ---- projected Gauss-Seidel pieces.  dvb: base (replicated), dvc: chain (spine replicated, limb private)
-struct RowRegs { float4 a, b, c, d, e, rl, jl; };  // 20 shared words, own limb response, the row's limb Jacobian
+// ---- projected Gauss-Seidel on the whitened impulse sum z.  zb: base, zc: chain (spine replicated, limb private)
+struct RowRegs { float4 a, b, c, d; };
 template <class P4>
-__device__ __forceinline__ void row_load(P4 rp, int role, RowRegs& r) {
-  r.a = rp[0]; r.b = rp[1]; r.c = rp[2]; r.d = rp[3]; r.e = rp[4];
-  r.rl = rp[5 + role];
-  r.jl = rp[9];
-}
-__device__ __forceinline__ float row_jdot(const RowRegs& r, const float* dvb, const float* dvc, bool mine, int src, unsigned qm) {
-  // words: a = RB0..3, b = RB4,5 RS0,1, c = RS2 JS0..2, d = JB0..3, e = JB4,5 rhs dinv
+__device__ __forceinline__ void row_load(P4 rp, RowRegs& r) { r.a = rp[0]; r.b = rp[1]; r.c = rp[2]; r.d = rp[3]; }
+__device__ __forceinline__ float row_jdot(const RowRegs& r, const float* zb, const float* zc, bool mine, int src, unsigned qm) {
   // three short chains instead of one 9-deep one: this dot product sits on the Gauss-Seidel critical path
-  const float r0 = fmaf(r.d.z, dvb[2], fmaf(r.d.y, dvb[1], r.d.x * dvb[0]));
-  const float r1 = fmaf(r.e.y, dvb[5], fmaf(r.e.x, dvb[4], r.d.w * dvb[3]));
-  const float r2 = fmaf(r.c.w, dvc[2], fmaf(r.c.z, dvc[1], r.c.y * dvc[0]));
-  const float own = mine ? fmaf(r.jl.y, dvc[4], r.jl.x * dvc[3]) + fmaf(r.jl.w, dvc[6], r.jl.z * dvc[5]) : 0.f;
+  const float r0 = fmaf(r.a.z, zb[2], fmaf(r.a.y, zb[1], r.a.x * zb[0]));
+  const float r1 = fmaf(r.b.y, zb[5], fmaf(r.b.x, zb[4], r.a.w * zb[3]));
+  const float r2 = fmaf(r.c.z, zc[2], fmaf(r.c.y, zc[1], r.c.x * zc[0]));
+  const float own = mine ? fmaf(r.d.y, zc[4], r.d.x * zc[3]) + fmaf(r.d.w, zc[6], r.d.z * zc[5]) : 0.f;
   return (r0 + r1) + (r2 + __shfl_sync(qm, own, src));
 }
-__device__ __forceinline__ void row_axpy(const RowRegs& r, float a, float* dvb, float* dvc) {
-  dvb[0] += a * r.a.x; dvb[1] += a * r.a.y; dvb[2] += a * r.a.z; dvb[3] += a * r.a.w; dvb[4] += a * r.b.x; dvb[5] += a * r.b.y;
-  dvc[0] += a * r.b.z; dvc[1] += a * r.b.w; dvc[2] += a * r.c.x;
-  dvc[3] += a * r.rl.x; dvc[4] += a * r.rl.y; dvc[5] += a * r.rl.z; dvc[6] += a * r.rl.w;
+__device__ __forceinline__ void row_axpy(const RowRegs& r, float a, bool mine, float* zb, float* zc) {
+  zb[0] += a * r.a.x; zb[1] += a * r.a.y; zb[2] += a * r.a.z; zb[3] += a * r.a.w; zb[4] += a * r.b.x; zb[5] += a * r.b.y;
+  zc[0] += a * r.c.x; zc[1] += a * r.c.y; zc[2] += a * r.c.z;
+  const float al = mine ? a : 0.f;
+  zc[3] += al * r.d.x; zc[4] += al * r.d.y; zc[5] += al * r.d.z; zc[6] += al * r.d.w;
 }
 // OVER = false: the env has no row beyond the shared-memory budget (the common case): plain shared-memory loads, no
 // predicated-off global loads in the instruction stream (those would take issue slots in every row evaluation).
 template <bool OVER, class SM>
-__device__ __forceinline__ void row_fetch(const SM& sm, const float* gscr, int e, int r, int role, RowRegs& rr) {
-  if (!OVER || r < SM::RSM) row_load(reinterpret_cast<const float4*>(&sm.rows[e][r * RW]), role, rr);
-  else row_load(reinterpret_cast<const float4*>(gscr + (size_t)(r - SM::RSM) * RW), role, rr);
+__device__ __forceinline__ void row_fetch(const SM& sm, const float* gscr, int e, int r, RowRegs& rr) {
+  if (!OVER || r < SM::RSM) row_load(reinterpret_cast<const float4*>(&sm.rows[e][r * RW]), rr);
+  else row_load(reinterpret_cast<const float4*>(gscr + (size_t)(r - SM::RSM) * RW), rr);
 }
 
-// 5 projected-Gauss-Seidel sweeps on the velocity change (dvb: base, dvc: chain) of the env of this quad
+// 5 projected-Gauss-Seidel sweeps for the env of this quad
 template <bool OVER, class SM>
 __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int role, int qb, unsigned qm, int nlim,
-                                           int ncon, float* dvb, float* dvc) {
+                                           int ncon, float* zb, float* zc) {
+  float* lamv = sm.lam(e);
 #pragma unroll 1
   for (int itn = 0; itn < ILRL_SOLVER_ITERS; itn++) {
-    // limits, then contact normals.  The next row (independent of dv) is fetched while this one is applied:
+    // limits, then contact normals.  The next row (independent of z) is fetched while this one is applied:
     // two register buffers used alternately (the loop is unrolled by two so that no copies are needed).
     const int nfirst = nlim + ncon;
     auto row_of = [&](int k) { return k < nlim ? k : nlim + 3 * (k - nlim); };
-    auto fetch = [&](int k, RowRegs& rr, int& L, float& lam) {
+    auto fetch = [&](int k, RowRegs& rr, float& lam) {
       const int r = row_of(k);
-      row_fetch<OVER>(sm, gscr, e, r, role, rr);
-      L = sm.rowL(e)[r]; lam = sm.lam(e)[r];
+      row_fetch<OVER>(sm, gscr, e, r, rr);
+      lam = lamv[r];
     };
-    auto apply = [&](int k, const RowRegs& rr, int L, float lam) {
-      const float nl = fmaxf(lam + rr.e.z - row_jdot(rr, dvb, dvc, role == L, qb + (L & 3), qm) * rr.e.w, 0.f);
-      sm.lam(e)[row_of(k)] = nl;
-      row_axpy(rr, nl - lam, dvb, dvc);
+    auto apply = [&](int k, const RowRegs& rr, float lam) {
+      const int L = __float_as_int(rr.c.w);
+      const bool mine = role == L;
+      const float nl = fmaxf(lam + rr.b.z - row_jdot(rr, zb, zc, mine, qb + (L & 3), qm) * rr.b.w, 0.f);
+      lamv[row_of(k)] = nl;
+      row_axpy(rr, nl - lam, mine, zb, zc);
     };
     RowRegs ra, rb;
-    int La = 0, Lb = 0;
     float lama = 0.f, lamb = 0.f;
-    fetch(0, ra, La, lama);  // nrows > 0 implies nfirst > 0
+    fetch(0, ra, lama);  // nrows > 0 implies nfirst > 0
 #pragma unroll 1
     for (int k = 0; k < nfirst; k += 2) {
-      if (k + 1 < nfirst) fetch(k + 1, rb, Lb, lamb);
-      apply(k, ra, La, lama);
+      if (k + 1 < nfirst) fetch(k + 1, rb, lamb);
+      apply(k, ra, lama);
       if (k + 1 < nfirst) {
-        if (k + 2 < nfirst) fetch(k + 2, ra, La, lama);
-        apply(k + 1, rb, Lb, lamb);
+        if (k + 2 < nfirst) fetch(k + 2, ra, lama);
+        apply(k + 1, rb, lamb);
       }
     }
 #pragma unroll 1
     for (int c = 0; c < ncon; c++) {  // friction pairs, cone re-projected on the current normal impulse
       const int rn = nlim + 3 * c;
-      const float ln = sm.lam(e)[rn];
+      const float ln = lamv[rn];
       if (!(ln > 0.f)) continue;
       RowRegs r1, r2;
-      row_fetch<OVER>(sm, gscr, e, rn + 1, role, r1);
-      row_fetch<OVER>(sm, gscr, e, rn + 2, role, r2);
-      const int L = sm.rowL(e)[rn];
+      row_fetch<OVER>(sm, gscr, e, rn + 1, r1);
+      row_fetch<OVER>(sm, gscr, e, rn + 2, r2);
+      const int L = __float_as_int(r1.c.w);
+      const bool mine = role == L;
       const float lim_f = (float)ILRL_FRICTION * ln;
-      const float l1 = sm.lam(e)[rn + 1], l2 = sm.lam(e)[rn + 2];
-      float s1 = l1 + r1.e.z - row_jdot(r1, dvb, dvc, role == L, qb + (L & 3), qm) * r1.e.w;
-      float s2 = l2 + r2.e.z - row_jdot(r2, dvb, dvc, role == L, qb + (L & 3), qm) * r2.e.w;
+      const float l1 = lamv[rn + 1], l2 = lamv[rn + 2];
+      float s1 = l1 + r1.b.z - row_jdot(r1, zb, zc, mine, qb + (L & 3), qm) * r1.b.w;
+      float s2 = l2 + r2.b.z - row_jdot(r2, zb, zc, mine, qb + (L & 3), qm) * r2.b.w;
       const float n2 = s1 * s1 + s2 * s2;
       if (n2 > lim_f * lim_f) { const float sc = lim_f * rsqrtf(n2); s1 *= sc; s2 *= sc; }
-      sm.lam(e)[rn + 1] = s1; sm.lam(e)[rn + 2] = s2;
-      row_axpy(r1, s1 - l1, dvb, dvc);
-      row_axpy(r2, s2 - l2, dvb, dvc);
+      lamv[rn + 1] = s1; lamv[rn + 2] = s2;
+      row_axpy(r1, s1 - l1, mine, zb, zc);
+      row_axpy(r2, s2 - l2, mine, zb, zc);
     }
   }
 }
@@ -870,6 +819,7 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
       const float dinv = rcp_or_zero(sdot(S, U));  // a dummy slot has S = 0
       const float u = rec[W_TAU] - sdot(S, x.p);
       st_Udu(rec, U, dinv, u);
+      rec[W_SQD] = sqrtf(dinv);
       downdate(x.I, U, dinv);
       x.p = x.p + imul(x.I, cJ) + (u * dinv) * U;
     }
@@ -931,33 +881,30 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
     nact--;
   }
   const int nlim = __popc(lim), ncon = nact, nrows = nlim + 3 * ncon;
-  float dvb[6], dvc[NL];
+  float zb[6], zc[NL];   // whitened impulse sum: base (replicated), chain (spine replicated, limb private)
 #pragma unroll
-  for (int i = 0; i < 6; i++) dvb[i] = 0.f;
+  for (int i = 0; i < 6; i++) zb[i] = 0.f;
 #pragma unroll
-  for (int i = 0; i < NL; i++) dvc[i] = 0.f;
-  // ---- build the rows three at a time (one contact, or up to three limits, per item).  The items of the warp's 8 envs
-  // form ONE pool that is dealt to all its lanes: an env with many rows is helped by the lanes of envs with few (every
-  // input of an item is in shared memory or one shuffle away), so a warp needs ceil(items / lanes) rounds of the
+  for (int i = 0; i < NL; i++) zc[i] = 0.f;
+  // ---- build the rows.  The items (one violated limit = one row, one contact = three rows) of the warp's 8 envs form
+  // ONE pool per kind that is dealt to all its lanes: an env with many rows is helped by the lanes of envs with few
+  // (every input of an item is in shared memory or one shuffle away), so a warp needs ceil(items / lanes) rounds of a
   // builder instead of max over its envs of ceil(items / 4).  wm = lanes of this warp that execute the substep.
   {
     const float idt = 1.0f / dt;
     const int lane = tid & 31, q_own = lane >> 2;
-    const int nlg_own = (nlim + 2) / 3, nit_own = nlg_own + ncon;
-    int cnt[8], total = 0;
+    const int nlanes = __popc(wm), rank = __popc(wm & ((1u << lane) - 1u));
+    __syncwarp(wm);   // the link records and base factors of every env of the warp are complete
+#pragma unroll 1
+    for (int kind = 0; kind < 2; kind++) {
+      const int n_own = kind == 0 ? nlim : ncon;
+      int cnt[8], total = 0;
 #pragma unroll
-    for (int q = 0; q < 8; q++) {
-      const int c = __shfl_sync(wm, nit_own, 4 * q);
-      cnt[q] = ((wm >> (4 * q)) & 1u) ? c : 0;   // a quad that does not step has no items (its lanes are not here)
-      total += cnt[q];
-    }
-    if (total > 0) {
-      {  // the response scratch shares its storage with the body records of the FK phase: clear this lane's part
-        float* z = sm.su(e, role, 0);
-#pragma unroll
-        for (int i = 0; i < 3 * NL; i++) z[i] = 0.f;
+      for (int q = 0; q < 8; q++) {
+        const int c = __shfl_sync(wm, n_own, 4 * q);
+        cnt[q] = ((wm >> (4 * q)) & 1u) ? c : 0;   // a quad that does not step has no items (its lanes are not here)
+        total += cnt[q];
       }
-      const int nlanes = __popc(wm), rank = __popc(wm & ((1u << lane) - 1u));
 #pragma unroll 1
       for (int g0 = 0; g0 < total; g0 += nlanes) {
         // item g -> (quad q, item k of that quad's env)
@@ -968,77 +915,49 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
           if (q == t && k >= cnt[t]) { k -= cnt[t]; q = t + 1; }
         if (!has) { q = q_own; k = 0; }
         const int src = 4 * q;
-        const uint32_t lim_q = __shfl_sync(wm, lim, src), act_q = __shfl_sync(wm, act, src);
+        const uint32_t mask_q = __shfl_sync(wm, kind == 0 ? lim : act, src);
         const int nlim_q = __shfl_sync(wm, nlim, src);
-        const float bz_q = __shfl_sync(wm, b.p[2], src);
-        float nub_q[6];
+        float bz_q = 0.f, nub_q[6];
+        if (kind == 1) {
+          bz_q = __shfl_sync(wm, b.p[2], src);
 #pragma unroll
-        for (int i = 0; i < 6; i++) nub_q[i] = __shfl_sync(wm, nub[i], src);
+          for (int i = 0; i < 6; i++) nub_q[i] = __shfl_sync(wm, nub[i], src);
+        }
         if (has) {
-          const int e_q = (e & ~7) + q, qb_q = (tid & ~31) + 4 * q, nlg_q = (nlim_q + 2) / 3;
+          const int e_q = (e & ~7) + q, qb_q = (tid & ~31) + 4 * q;
           float* gscr_q = gscr + (ptrdiff_t)(q - q_own) * (GROWS * RW);
-          const int it = k;
-          Imp im[3];
-          float pos[3] = {0.f, 0.f, 0.f};
-          int r0;
-          if (it < nlg_q) {
-            r0 = 3 * it;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-              im[i].row = nullptr; im[i].L = -1; im[i].c = -1; im[i].jl = 1; im[i].dir = 0.f; im[i].F = svzero();
-              if (r0 + i < nlim_q) {
-                const int j = nth_set_bit(lim_q, r0 + i);
-                im[i].L = T.jL[j]; im[i].c = T.jC[j];
-                const float q_ = link_rec_of(sm, im[i].L, im[i].c, e_q, qb_q)[W_Q];
-                float pen;
-                if (q_ - kJointLo[j] <= 0.f) { pen = q_ - kJointLo[j]; im[i].dir = 1.f; } else { pen = kJointHi[j] - q_; im[i].dir = -1.f; }
-                pos[i] = -pen * (float)ILRL_LIMIT_ERP * idt;
-              }
-            }
+          auto row_ptr = [&](int r) { return r < RSM ? &sm.rows[e_q][r * RW] : gscr_q + (size_t)(r - RSM) * RW; };
+          const int g = nth_set_bit(mask_q, k);
+          if (kind == 0) {
+            sm.lam(e_q)[k] = 0.f;
+            build_limit_row(sm, T, g, e_q, qb_q, idt, row_ptr(k));
           } else {
-            const int ci = it - nlg_q;
-            r0 = nlim_q + 3 * ci;
-            const int g = nth_set_bit(act_q, ci);
+            const int r0 = nlim_q + 3 * k;
+            sm.lam(e_q)[r0] = 0.f; sm.lam(e_q)[r0 + 1] = 0.f; sm.lam(e_q)[r0 + 2] = 0.f;
             const float* sp = &sm.sph[g][0][e_q];
-            const V3 xx = mk(sp[0], sp[QE], sp[2 * QE]);
-            const float dist = bz_q + sp[2 * QE];
-            pos[0] = dist > 0.f ? -dist * idt : -dist * (float)ILRL_CONTACT_ERP * idt;
-#pragma unroll
-            for (int i = 0; i < 3; i++) {
-              im[i].L = T.sphL[g]; im[i].c = T.sphC[g]; im[i].jl = 0; im[i].dir = 0.f;
-              // normal (0,0,1), tangents btPlaneSpace1 -> (0,-1,0), (1,0,0)
-              im[i].F.l = i == 0 ? mk(0.f, 0.f, 1.f) : (i == 1 ? mk(0.f, -1.f, 0.f) : mk(1.f, 0.f, 0.f));
-              im[i].F.a = cross(xx, im[i].F.l);
-            }
+            build_contact_rows(sm, T, g, e_q, qb_q, idt, mk(sp[0], sp[QE], sp[2 * QE]), bz_q + sp[2 * QE], nub_q,
+                               row_ptr(r0), row_ptr(r0 + 1), row_ptr(r0 + 2));
           }
-#pragma unroll
-          for (int i = 0; i < 3; i++) {
-            const int r = r0 + i;
-            const bool used = it >= nlg_q || r < nlim_q;
-            im[i].row = !used ? nullptr : (r < RSM ? &sm.rows[e_q][r * RW] : gscr_q + (size_t)(r - RSM) * RW);
-            if (used) { sm.lam(e_q)[r] = 0.f; sm.rowL(e_q)[r] = (signed char)(im[i].c >= 3 ? im[i].L : -1); }
-          }
-          responses3(sm, im, nub_q, e_q, e, role, qb_q, idt, pos, it >= nlg_q);
         }
       }
-      __syncwarp(wm);   // rows of an env may have been written by lanes of another quad
     }
+    __syncwarp(wm);   // rows of an env may have been written by lanes of another quad
   }
   if (nrows > 0) {
-    // ---- projected Gauss-Seidel on the velocity change
+    // ---- projected Gauss-Seidel on the whitened impulse sum
     // One loop variant per layout wherever both would be common: the quads of a warp that took different variants
-    // run them one after the other (+4..9 % in the dense layouts from dropping the split).  Only the on-chip layout,
-    // where overflow rows are rare, keeps the loop without the overflow test for the envs that fit (+1.5 % there).
-    if (RSM >= 16 && nrows <= RSM) pgs_sweeps<false>(sm, gscr, e, role, qb, qm, nlim, ncon, dvb, dvc);
-    else pgs_sweeps<true>(sm, gscr, e, role, qb, qm, nlim, ncon, dvb, dvc);
-    __syncwarp(qm);
+    // run them one after the other.  The on-chip layout holds every row in shared memory: no overflow variant at all.
+    if (RSM >= MAXROWS) pgs_sweeps<false>(sm, gscr, e, role, qb, qm, nlim, ncon, zb, zc);
+    else pgs_sweeps<true>(sm, gscr, e, role, qb, qm, nlim, ncon, zb, zc);
+    bwd_subst(&sm.L0[0][e], zb);   // velocity change of the base: dv_base = L0^-T z_base
   }
-  // ---- integrate (exponential map on the torso quaternion, as btMultiBody::stepPositionsMultiDof)
+  // ---- velocity change of the chain (outward sweep of dv = W^T z) and integration (exponential map on the torso
+  // quaternion, as btMultiBody::stepPositionsMultiDof)
   {
     const float M = (float)ILRL_MAX_COORD_VEL;
     float nu[6];
 #pragma unroll
-    for (int i = 0; i < 6; i++) nu[i] = nrows > 0 ? clampf(nub[i] + dvb[i], -M, M) : nub[i];
+    for (int i = 0; i < 6; i++) nu[i] = nrows > 0 ? clampf(nub[i] + zb[i], -M, M) : nub[i];
 #pragma unroll
     for (int i = 0; i < 3; i++) { b.w[i] = nu[i]; b.v[i] = nu[3 + i]; b.p[i] += dt * nu[3 + i]; }
     const float wn = sqrtf(nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]);
@@ -1054,11 +973,23 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
     const float nw = cw * w_ - dx * x_ - dy * y_ - dz * z_;
     const float inv = rsqrtf(nx * nx + ny * ny + nz * nz + nw * nw);
     b.quat[0] = nx * inv; b.quat[1] = ny * inv; b.quat[2] = nz * inv; b.quat[3] = nw * inv;
+    SV a0v, ap;
+    a0v.a = mk(zb[0], zb[1], zb[2]); a0v.l = mk(zb[3], zb[4], zb[5]);
+    ap = a0v;
 #pragma unroll
     for (int c = 0; c < NL; c++) {
       float* rec = link_rec(sm, c, e, tid);
       const float nuc = rec[W_NU];
-      const float qd = nrows > 0 ? clampf(nuc + dvc[c], -M, M) : nuc;
+      float qd = nuc;
+      if (nrows > 0) {
+        if (c == 3 && role >= 2) ap = a0v;   // the arms hang off the torso
+        SV S, U;
+        float di, sq;
+        ld_SUq(rec, S, U, di, sq);
+        const float dq = sq * zc[c] - di * sdot(ap, U);
+        ap = ap + dq * S;
+        qd = clampf(nuc + dq, -M, M);
+      }
       if (c >= 3 || role == 0) {  // the spine records are shared by the quad: one writer for the read-modify-write
         rec[W_QD] = qd;
         rec[W_Q] += dt * qd;

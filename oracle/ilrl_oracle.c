@@ -228,6 +228,11 @@ double ilrl_oracle_energy(const double* phys) {
   return e;
 }
 
+/* Diagnostics (tools/rowstats.py): when set, every substep counts its (violated limits, kept contacts) pair in a
+ * [18][9] histogram.  Not thread-safe; single-threaded tools only. */
+static long* g_rowstats = 0;
+void ilrl_oracle_set_rowstats(long* hist /* [18*9] or NULL */) { g_rowstats = hist; }
+
 /* One Bullet substep.  flags: bit0 = no gravity, bit1 = no velocity damping, bit2 = no contacts, bit3 = no limits
  * (the flags exist only for the conservation / free-flight tests). */
 static void orc_substep(double* phys, const double* tau, double dt, int flags) {
@@ -372,6 +377,7 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
     }
   }
   int nrows = nlim + 3 * ncon;
+  if (g_rowstats) { g_rowstats[(nlim > 17 ? 17 : nlim) * 9 + (ncon > 8 ? 8 : ncon)]++; }
   for (int r = 0; r < nrows; r++) {
     chol_solve(L, NV, J[r], Rsp[r]);
     double d = 0, rv = 0;

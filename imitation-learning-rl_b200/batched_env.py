@@ -155,6 +155,33 @@ class BatchedHumanoidEnv:
         if rc != 0:
             self._ck(rc)
 
+    def step_host_async(self, part, nparts, action_np, obs_np, reward_np, done_np, terms_np=None):
+        """Enqueue one step of part `part` of `nparts` (contiguous blocks of envs, see `part_slice`) on the part's own
+        stream and return at once.  The arrays are the FULL [N, ...] pinned buffers (torch `pin_memory()`); the part's
+        rows of obs / reward / done are valid after `wait(part)`.  Lets a worker prepare the actions of one part while
+        the other steps (double-buffered rollout)."""
+        ptr = lambda a: None if a is None else a.__array_interface__["data"][0]  # noqa: E731
+        rc = self.L.ilrl_step_host_async(self.h, int(part), int(nparts), ptr(action_np), ptr(obs_np), ptr(reward_np),
+                                         ptr(done_np), ptr(terms_np))
+        if rc != 0:
+            self._ck(rc)
+
+    def wait(self, part):
+        rc = self.L.ilrl_wait(self.h, int(part))
+        if rc != 0:
+            self._ck(rc)
+
+    def part_slice(self, part, nparts):
+        """env index range of a part: ceil(N / nparts) rounded up to whole 16-env tiles"""
+        per = -(-self.num_envs // nparts)
+        per = -(-per // 16) * 16
+        first = min(part * per, self.num_envs)
+        return slice(first, min(first + per, self.num_envs))
+
+    def set_config(self, max_timestep=0, step_per_level=0, skip_frame=0):
+        """Change `max_timestep` / `step_per_level` / `skipFrame` of the live handle (0 = keep)."""
+        self._ck(self.L.ilrl_set_config(self.h, int(max_timestep), int(step_per_level), int(skip_frame)))
+
     def high_step(self, action2):
         """hier mode: heading action [N,2] for the envs waiting for one; returns the low-level obs tensor [N,70]
         (rows of envs that were not waiting are untouched)."""

@@ -33,7 +33,9 @@ using SmemLarge = chain::SmemT<chain::LayoutLarge>;
 using SmemDense4 = chain::SmemT<chain::LayoutDense4>;
 
 struct StepArgs {
-  int n;
+  int n;               // envs of the handle (stride of the structure-of-arrays state)
+  int first, end;      // this launch steps envs [first, end)  (the whole batch, or one part of it: ilrl_step_host_async)
+  int skip_frame;      // reference frames per env step (REF low_level_env.py:162)
   int id_base;         // global id of env 0 of this handle: the Philox counter of env i is id_base + i
   int skip_physics;
   int auto_reset;
@@ -149,15 +151,17 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   __syncthreads();
   const int tile = s_tile;
   if (tile >= a.ntiles) break;
-  const int base = tile * QE;
+  const int base = a.first + tile * QE;
   const int i = base + e;
-  const bool valid = i < a.n;
+  const bool valid = i < a.end;
   if (valid) {  // the quad stages its env's action row (the 8 rows of a warp are one contiguous 544-byte block)
     const float* arow = a.action + (size_t)i * NJ;
     float* dst = sm.act(e);
 #pragma unroll
     for (int m = role; m < NJ; m += 4) dst[m] = arow[m];
   }
+  // row 0 of every env must hold finite numbers: lanes past their own row count evaluate it with a zero step
+  reinterpret_cast<float4*>(&sm.rows[e][0])[role] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncthreads();
   bool write_obs = false;
   float st_ep = 0.f, st_ret = 0.f, st_len = 0.f, st_steps = 0.f, st_rew = 0.f, st_terms[11];
@@ -176,8 +180,9 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   // envs that step.  The physics substeps run between CTA barriers: the warps of a CTA (and, because tiles start
   // together, mostly the CTAs of an SM) then execute the same 70 KB of substep code at about the same time and share
   // the instruction cache — +4 % at 16384 envs, +5 % at 65536 (6 to 8 unsynchronised warps per SM otherwise thrash it).
+  // Every lane runs the substeps (compile-time full shuffle masks, chain::substep): the lanes of an env that does
+  // not step carry a benign dummy state that is never stored.
   const bool active = valid && !pending;
-  const unsigned wm = __ballot_sync(0xffffffffu, active);   // lanes of this warp that run the substeps
   chain::Base b;
   float act[NJ];
   float stale_x = 0.f, stale_y = 0.f;
@@ -195,13 +200,15 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
       stale_x = (32.f * b.p[0] + sumx) * (1.f / 33.f);
       stale_y = (32.f * b.p[1] + sumy) * (1.f / 33.f);
     }
+  } else {
+    chain::dummy_state(sm, e, tid, b);
   }
   if (!a.skip_physics) {
-    float* gscr = a.gscr + (size_t)(valid ? i : 0) * chain::GROWS * chain::RW;
+    float* gscr_tile = a.gscr + (size_t)min(base, a.n - 1) * chain::GROWS * chain::RW;
 #pragma unroll 1
     for (int sub = 0; sub < ILRL_SUBSTEPS; sub++) {
       __syncthreads();
-      if (active) chain::substep(b, sm, gscr, e, tid, role, qm, wm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+      chain::substep(b, sm, gscr_tile, e, tid, role, active, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
     }
   }
   __syncthreads();   // the once-per-step tail (4 k instructions) is entered together as well: +3 % at 65536 envs
@@ -228,7 +235,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     w.e[ILRL_E_OBS_SIN] = c.obs[1]; w.e[ILRL_E_OBS_COS] = c.obs[2];
     if (MODE == 0) { w.e[ILRL_E_ROBOT_X] = c.bx; w.e[ILRL_E_ROBOT_Y] = c.by; }
     float reward = update_reward<MODE>(ps, c, w, cl, act, terms);
-    inc_frame(w, cl, 2);
+    inc_frame(w, cl, a.skip_frame);
     uint32_t ctr = a.rng[i];
     int deg;
     if (a.forced_deg && a.forced_deg[i] != INT_MIN) deg = a.forced_deg[i];
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
         reset_pose<MODE>(ps, w, cl, sf, yaw, tdeg, rx);
         chain::scatter(ps, sm, e, qb, role, qm, b);
         chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);
-        reset_finish<MODE>(ps, w, cl, rx, rfx, rfy, sumx, sumy, a.step_per_level, c);
+        reset_finish<MODE>(ps, w, cl, rx, rfx, rfy, sumx, sumy, a.step_per_level, a.skip_frame, c);
         if (MODE == 0) {
           float obs[70];
           write_low_obs(c.obs, w, cl, obs);
@@ -321,7 +328,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     unsigned int okmask = __ballot_sync(0xffffffffu, write_obs);
     if ((tid & 31) == 0) wrote[tid >> 5] = okmask;
     __syncthreads();
-    const int cnt = min(QE, a.n - base) * 70;
+    const int cnt = min(QE, a.end - base) * 70;
     for (int t = tid; t < cnt; t += QT) {
       int r = t / 70, cc = t - r * 70;
       if ((wrote[r >> 3] >> ((r & 7) * 4)) & 1u) a.obs[(size_t)base * 70 + t] = sm.scr[r][cc];
@@ -351,6 +358,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
 // ------------------------------------------------------------------------------------------------ K2: reset
 struct ResetArgs {
   int n;
+  int skip_frame;
   int id_base;
   float step_per_level;
   uint64_t seed;
@@ -378,7 +386,7 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const ResetArgs a) {
   float txy[2] = {0.f, 0.f};
   if (a.target_xy) { txy[0] = a.target_xy[2 * i]; txy[1] = a.target_xy[2 * i + 1]; }
   Work k; Calc c;
-  reset_env<MODE>(s, w, cl, sf, yaw, tdeg, a.step_per_level, k, c, a.target_xy ? txy : nullptr);
+  reset_env<MODE>(s, w, cl, sf, yaw, tdeg, a.step_per_level, a.skip_frame, k, c, a.target_xy ? txy : nullptr);
   a.rng[i] = ctr;
   store_state(v, i, s, w);
   if (a.obs) {
@@ -465,16 +473,20 @@ __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const flo
   const int i = blockIdx.x * QE + e;
   quad_smem_init(sm);
   __syncthreads();
-  const unsigned wm = __ballot_sync(0xffffffffu, i < v.n);
-  if (i >= v.n) return;
+  const bool valid = i < v.n;
   chain::Base b;
-  chain::load_base(v.phys, v.n, i, b);
-  chain::load_links(v.phys, v.n, i, sm, e, tid, role);
-  set_torques(sm, e, tid, role, nullptr, torque + (size_t)i * NJ);
-  __syncwarp(qm);
-  float* gscr = gscr_all + (size_t)i * chain::GROWS * chain::RW;
+  if (valid) {
+    chain::load_base(v.phys, v.n, i, b);
+    chain::load_links(v.phys, v.n, i, sm, e, tid, role);
+    set_torques(sm, e, tid, role, nullptr, torque + (size_t)i * NJ);
+  } else {
+    chain::dummy_state(sm, e, tid, b);
+  }
+  __syncwarp();
+  float* gscr_tile = gscr_all + (size_t)blockIdx.x * QE * chain::GROWS * chain::RW;
   for (int sub = 0; sub < nsub; sub++)
-    chain::substep(b, sm, gscr, e, tid, role, qm, wm, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+    chain::substep(b, sm, gscr_tile, e, tid, role, valid, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+  if (!valid) return;
   Phys ps;
   chain::gather(b, sm, e, qb, qm, ps);
   chain::store_phys(v.phys, v.n, i, role, ps);
@@ -552,6 +564,16 @@ __global__ void gae_decisions_kernel(const float* __restrict__ rew, const uint8_
     if (f & 2) { tau = t; a_tau = ok ? a : 0.f; }
   }
 }
+// the high-level agent's outputs kept in the handle -> caller buffers (any of them may be null): one launch
+__global__ void high_readout_kernel(int n, const float* __restrict__ obs, const float* __restrict__ rew,
+                                    const uint8_t* __restrict__ flags, float* obs_out, float* rew_out, uint8_t* flags_out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (obs_out && t < 44 * n) obs_out[t] = obs[t];
+  if (t < n) {
+    if (rew_out) rew_out[t] = rew[t];
+    if (flags_out) flags_out[t] = flags[t];
+  }
+}
 __global__ void stats_fetch_kernel(float* acc, float* out) {
   int t = threadIdx.x;
   if (t < ILRL_STATS_WORDS) { out[t] = acc[t]; acc[t] = 0.f; }
@@ -562,6 +584,7 @@ __global__ void stats_fetch_kernel(float* acc, float* out) {
 // ================================================================================================ host side (C ABI)
 using namespace ilrl;
 
+constexpr int ILRL_MAX_PARTS = 8;
 struct ilrl_env {
   ilrl_config cfg;
   int n;
@@ -573,7 +596,11 @@ struct ilrl_env {
   float* high_reward = nullptr;
   uint8_t* high_flags = nullptr;
   float* stats = nullptr;
-  unsigned int* tile_counter = nullptr;
+  unsigned int* tile_counter = nullptr;   // [1 + ILRL_MAX_PARTS][2]: the whole batch, then one pair per part
+  cudaStream_t part_stream[ILRL_MAX_PARTS] = {nullptr};   // ilrl_step_host_async: one stream + completion event per part
+  cudaEvent_t part_event[ILRL_MAX_PARTS] = {nullptr};
+  bool part_busy[ILRL_MAX_PARTS] = {false};
+  int32_t* clip_ids_dev = nullptr;        // staging for ilrl_set_clip_ids
   int grid_small = 0, grid_large = 0, grid_dense4 = 0;  // resident CTAs of the step kernel in each layout
   float* clip_mem[MAX_CLIPS] = {nullptr};
   ClipDesc clips[MAX_CLIPS];
@@ -610,6 +637,19 @@ static int fail(ilrl_env* e, int code, const std::string& msg) {
 
 static inline int nblk(int n) { return (n + BLOCK - 1) / BLOCK; }
 
+// Every entry point runs on the handle's device and leaves the caller's current device as it found it (a process
+// that drives several GPUs, or torch with another current device, is not disturbed).
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t status;
+  explicit DeviceGuard(int dev) {
+    status = cudaGetDevice(&prev);
+    if (status == cudaSuccess && prev != dev) status = cudaSetDevice(dev); else if (status == cudaSuccess) prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(env) DeviceGuard _dg((env)->cfg.device); CK(_dg.status)
+
 extern "C" {
 
 const char* ilrl_last_error(const ilrl_env* env) { return env ? env->err.c_str() : g_create_err.c_str(); }
@@ -622,7 +662,8 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail(nullptr, ILRL_ERR_CUDA, "ilrl_create: no CUDA device (this library has no CPU path)");
   if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, ILRL_ERR_ARG, "ilrl_create: bad device ordinal");
-  CK(cudaSetDevice(cfg->device));
+  DeviceGuard dg(cfg->device);
+  CK(dg.status);
   env = new (std::nothrow) ilrl_env();
   if (!env) return fail(nullptr, ILRL_ERR_ARG, "ilrl_create: out of host memory");
   env->cfg = *cfg;
@@ -698,8 +739,8 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMalloc(&env->high_reward, sizeof(float) * n));
   CKC(cudaMalloc(&env->high_flags, n));
   CKC(cudaMalloc(&env->stats, sizeof(float) * ILRL_STATS_WORDS));
-  CKC(cudaMalloc(&env->tile_counter, 2 * sizeof(unsigned int)));
-  CKC(cudaMemset(env->tile_counter, 0, 2 * sizeof(unsigned int)));
+  CKC(cudaMalloc(&env->tile_counter, 2 * (1 + ILRL_MAX_PARTS) * sizeof(unsigned int)));
+  CKC(cudaMemset(env->tile_counter, 0, 2 * (1 + ILRL_MAX_PARTS) * sizeof(unsigned int)));
   CKC(cudaMemset(env->phys, 0, sizeof(float) * ILRL_PHYS_WORDS * n));
   CKC(cudaMemset(env->envf, 0, sizeof(float) * ILRL_ENV_WORDS * n));
   CKC(cudaMemset(env->rng, 0, sizeof(uint32_t) * n));
@@ -716,8 +757,13 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
 
 void ilrl_destroy(ilrl_env* env) {
   if (!env) return;
-  cudaSetDevice(env->cfg.device);
+  DeviceGuard dg(env->cfg.device);
   cudaDeviceSynchronize();
+  for (int p = 0; p < ILRL_MAX_PARTS; p++) {
+    if (env->part_stream[p]) cudaStreamDestroy(env->part_stream[p]);
+    if (env->part_event[p]) cudaEventDestroy(env->part_event[p]);
+  }
+  cudaFree(env->clip_ids_dev);
   cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr);
   cudaFree(env->high_obs); cudaFree(env->high_reward); cudaFree(env->high_flags); cudaFree(env->stats); cudaFree(env->tile_counter);
   for (int c = 0; c < MAX_CLIPS; c++) cudaFree(env->clip_mem[c]);
@@ -736,7 +782,7 @@ int ilrl_load_clip(ilrl_env* env, int32_t clip, const float* pos, int32_t n_pos,
   // every frame the step/reset path can index must exist in all four tables
   if (max_frame < 7 || max_frame > n_pos - 1 || max_frame > n_rel - 1 || max_frame > n_vel || max_frame > n_ep - 1)
     return fail(env, ILRL_ERR_ARG, "ilrl_load_clip: max_frame exceeds a table (clamp it; see DESIGN.md on motion13_13)");
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
   size_t words = (size_t)14 * (n_pos + n_rel + n_vel) + (size_t)27 * n_ep;
   cudaFree(env->clip_mem[clip]);
   env->clip_mem[clip] = nullptr;
@@ -756,13 +802,14 @@ static StateView view(ilrl_env* env) { StateView v; v.n = env->n; v.phys = env->
 
 int ilrl_set_clip_ids(ilrl_env* env, const int32_t* ids_host) {
   if (!env) return ILRL_ERR_ARG;
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
   int32_t* d = nullptr;
   if (ids_host) {
     for (int i = 0; i < env->n; i++)
       if (ids_host[i] < 0 || ids_host[i] >= MAX_CLIPS || !env->clip_loaded[ids_host[i]])
         return fail(env, ILRL_ERR_STATE, "ilrl_set_clip_ids: env refers to a clip that is not loaded");
-    CK(cudaMalloc(&d, sizeof(int32_t) * env->n));
+    if (!env->clip_ids_dev) CK(cudaMalloc(&env->clip_ids_dev, sizeof(int32_t) * env->n));
+    d = env->clip_ids_dev;
     CK(cudaMemcpy(d, ids_host, sizeof(int32_t) * env->n, cudaMemcpyHostToDevice));
   } else if (!env->clip_loaded[0]) {
     return fail(env, ILRL_ERR_STATE, "ilrl_set_clip_ids: clip 0 is not loaded");
@@ -771,7 +818,6 @@ int ilrl_set_clip_ids(ilrl_env* env, const int32_t* ids_host) {
   env->launches++;
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
-  cudaFree(d);
   return ILRL_OK;
 }
 
@@ -784,9 +830,9 @@ int ilrl_reset(ilrl_env* env, const uint8_t* mask, const int32_t* start_frame, c
                const float* yaw_deg, const float* target_xy, float* obs, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (int r = check_ready(env)) return r;
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
   ResetArgs a;
-  a.n = env->n; a.id_base = env->cfg.env_id_base; a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
+  a.n = env->n; a.skip_frame = env->cfg.skip_frame; a.id_base = env->cfg.env_id_base; a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
   a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
   a.mask = mask; a.start_frame = start_frame; a.target_deg = target_deg; a.yaw_deg = yaw_deg; a.target_xy = target_xy; a.obs = obs;
   a.high_flags = env->high_flags;
@@ -799,23 +845,26 @@ int ilrl_reset(ilrl_env* env, const uint8_t* mask, const int32_t* start_frame, c
   return ILRL_OK;
 }
 
+// part < 0: the whole batch; otherwise envs [first, first + count) on the part's own tile counters
 static int do_step(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms,
-                   void* stream, int skip_physics) {
+                   cudaStream_t st, int skip_physics, int first = 0, int count = -1, int part = -1) {
   if (!env) return ILRL_ERR_ARG;
   if (!action || !obs || !reward || !done) return fail(env, ILRL_ERR_ARG, "ilrl_step: null buffer");
   if (int r = check_ready(env)) return r;
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
+  if (count < 0) count = env->n;
   StepArgs a;
-  a.n = env->n; a.id_base = env->cfg.env_id_base; a.skip_physics = skip_physics; a.auto_reset = env->cfg.auto_reset; a.max_timestep = env->cfg.max_timestep;
+  a.n = env->n; a.first = first; a.end = first + count; a.skip_frame = env->cfg.skip_frame;
+  a.id_base = env->cfg.env_id_base; a.skip_physics = skip_physics; a.auto_reset = env->cfg.auto_reset; a.max_timestep = env->cfg.max_timestep;
   a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
   a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
   a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.terms = terms;
   a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
-  a.forced_deg = env->forced_deg; a.stats = env->stats; a.gscr = env->gscr; a.tile_counter = env->tile_counter;
+  a.forced_deg = env->forced_deg; a.stats = env->stats; a.gscr = env->gscr;
+  a.tile_counter = env->tile_counter + 2 * (part + 1);
   memcpy(a.clips, env->clips, sizeof a.clips);
-  cudaStream_t st = (cudaStream_t)stream;
   if (env->timing) CK(cudaEventRecord(env->ev0, st));
-  a.ntiles = (env->n + QE - 1) / QE;
+  a.ntiles = (count + QE - 1) / QE;
   const int qblk = min(a.ntiles, env->layout == 2 ? env->grid_dense4 : env->layout == 1 ? env->grid_large : env->grid_small);
   if (env->layout == 2) {
     if (env->cfg.mode == 0) step_kernel<0, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
@@ -841,19 +890,50 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
 }
 
 int ilrl_step(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms, void* stream) {
-  return do_step(env, action, obs, reward, done, terms, stream, 0);
+  return do_step(env, action, obs, reward, done, terms, (cudaStream_t)stream, 0);
 }
 int ilrl_step_no_physics(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms,
                          void* stream) {
-  return do_step(env, action, obs, reward, done, terms, stream, 1);
+  return do_step(env, action, obs, reward, done, terms, (cudaStream_t)stream, 1);
+}
+
+// device aliases of page-locked, mapped host buffers (false if any of them is not mappable)
+static bool map_host_buffers(const float* action_h, float* obs_h, float* reward_h, uint8_t* done_h, float* terms_h,
+                             void** da, void** dobs, void** dr, void** dd, void** dt) {
+  auto pinned = [](const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+  };
+  if (!(pinned(action_h) && pinned(obs_h) && pinned(reward_h) && pinned(done_h) && (!terms_h || pinned(terms_h)))) return false;
+  *dt = nullptr;
+  const bool ok = cudaHostGetDevicePointer(da, const_cast<float*>(action_h), 0) == cudaSuccess &&
+                  cudaHostGetDevicePointer(dobs, obs_h, 0) == cudaSuccess && cudaHostGetDevicePointer(dr, reward_h, 0) == cudaSuccess &&
+                  cudaHostGetDevicePointer(dd, done_h, 0) == cudaSuccess &&
+                  (!terms_h || cudaHostGetDevicePointer(dt, terms_h, 0) == cudaSuccess);
+  if (!ok) cudaGetLastError();
+  return ok;
 }
 
 int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* reward_h, uint8_t* done_h, float* terms_h,
                    void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (!action_h || !obs_h || !reward_h || !done_h) return fail(env, ILRL_ERR_ARG, "ilrl_step_host: null buffer");
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
   const size_t n = env->n;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!env->no_zero_copy) {
+    // Zero-copy: the step kernel reads the action tiles from, and writes obs / reward / done to, the caller's
+    // page-locked buffers through their device mappings.  One launch + one synchronise; the output writes of CTAs
+    // that finish early overlap the tail of the kernel instead of waiting for a separate D2H copy.
+    void *da, *dobs, *dr, *dd, *dt;
+    if (map_host_buffers(action_h, obs_h, reward_h, done_h, terms_h, &da, &dobs, &dr, &dd, &dt)) {
+      int r = do_step(env, (const float*)da, (float*)dobs, (float*)dr, (uint8_t*)dd, (float*)dt, st, 0);
+      if (r) return r;
+      CK(cudaStreamSynchronize(st));
+      return ILRL_OK;
+    }
+  }
   if (!env->d_action) {  // staging buffers: pinned host mirrors + device I/O, allocated on first use
     CK(cudaMallocHost(&env->h_action, sizeof(float) * 17 * n));
     CK(cudaMallocHost(&env->h_obs, sizeof(float) * 70 * n));
@@ -867,7 +947,6 @@ int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* re
     CK(cudaMalloc(&env->d_done, n));
     CK(cudaMemset(env->d_obs, 0, sizeof(float) * 70 * n));
   }
-  cudaStream_t st = (cudaStream_t)stream;
   // Page-locked caller buffers are DMA targets as they are; pageable ones go through the handle's pinned mirrors.
   auto pinned = [](const void* p) {
     cudaPointerAttributes at;
@@ -876,25 +955,9 @@ int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* re
   };
   const bool pa = pinned(action_h), po = pinned(obs_h), pr = pinned(reward_h), pd = pinned(done_h),
              pt = terms_h && pinned(terms_h);
-  if (pa && po && pr && pd && (!terms_h || pt) && !env->no_zero_copy) {
-    // Zero-copy: the step kernel reads the action tiles from, and writes obs / reward / done to, the caller's
-    // page-locked buffers through their device mappings.  One launch + one synchronise; the output writes of CTAs
-    // that finish early overlap the tail of the kernel instead of waiting for a separate D2H copy.
-    void *da = nullptr, *dobs = nullptr, *dr = nullptr, *dd = nullptr, *dt = nullptr;
-    if (cudaHostGetDevicePointer(&da, const_cast<float*>(action_h), 0) == cudaSuccess &&
-        cudaHostGetDevicePointer(&dobs, obs_h, 0) == cudaSuccess && cudaHostGetDevicePointer(&dr, reward_h, 0) == cudaSuccess &&
-        cudaHostGetDevicePointer(&dd, done_h, 0) == cudaSuccess &&
-        (!terms_h || cudaHostGetDevicePointer(&dt, terms_h, 0) == cudaSuccess)) {
-      int r = do_step(env, (const float*)da, (float*)dobs, (float*)dr, (uint8_t*)dd, (float*)dt, stream, 0);
-      if (r) return r;
-      CK(cudaStreamSynchronize(st));
-      return ILRL_OK;
-    }
-    cudaGetLastError();  // not mappable after all: fall through to explicit copies
-  }
   if (!pa) memcpy(env->h_action, action_h, sizeof(float) * 17 * n);
   CK(cudaMemcpyAsync(env->d_action, pa ? action_h : env->h_action, sizeof(float) * 17 * n, cudaMemcpyHostToDevice, st));
-  int r = do_step(env, env->d_action, env->d_obs, env->d_reward, env->d_done, terms_h ? env->d_terms : nullptr, stream, 0);
+  int r = do_step(env, env->d_action, env->d_obs, env->d_reward, env->d_done, terms_h ? env->d_terms : nullptr, st, 0);
   if (r) return r;
   CK(cudaMemcpyAsync(po ? obs_h : env->h_obs, env->d_obs, sizeof(float) * 70 * n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(pr ? reward_h : env->h_reward, env->d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
@@ -909,12 +972,66 @@ int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* re
   return ILRL_OK;
 }
 
+// envs of part p of nparts: contiguous blocks of ceil(N / nparts) rounded up to whole 16-env tiles
+static void part_range(const ilrl_env* env, int part, int nparts, int* first, int* count) {
+  int per = (env->n + nparts - 1) / nparts;
+  per = (per + QE - 1) / QE * QE;
+  *first = min(part * per, env->n);
+  *count = min(per, env->n - *first);
+}
+
+int ilrl_step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const float* action_h, float* obs_h, float* reward_h,
+                         uint8_t* done_h, float* terms_h) {
+  if (!env) return ILRL_ERR_ARG;
+  if (nparts < 1 || nparts > ILRL_MAX_PARTS || part < 0 || part >= nparts)
+    return fail(env, ILRL_ERR_ARG, "ilrl_step_host_async: part / nparts out of range (nparts <= 8)");
+  if (!action_h || !obs_h || !reward_h || !done_h) return fail(env, ILRL_ERR_ARG, "ilrl_step_host_async: null buffer");
+  if (env->part_busy[part]) return fail(env, ILRL_ERR_STATE, "ilrl_step_host_async: part is still in flight (ilrl_wait first)");
+  ON_DEVICE(env);
+  void *da, *dobs, *dr, *dd, *dt;
+  if (!map_host_buffers(action_h, obs_h, reward_h, done_h, terms_h, &da, &dobs, &dr, &dd, &dt))
+    return fail(env, ILRL_ERR_ARG, "ilrl_step_host_async: buffers must be page-locked and mapped (cudaHostAlloc / "
+                                   "cudaHostRegister / torch pin_memory)");
+  if (!env->part_stream[part]) {
+    CK(cudaStreamCreateWithFlags(&env->part_stream[part], cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&env->part_event[part], cudaEventDisableTiming));
+  }
+  int first, count;
+  part_range(env, part, nparts, &first, &count);
+  if (count > 0) {
+    int r = do_step(env, (const float*)da, (float*)dobs, (float*)dr, (uint8_t*)dd, (float*)dt, env->part_stream[part], 0,
+                    first, count, part);
+    if (r) return r;
+  }
+  CK(cudaEventRecord(env->part_event[part], env->part_stream[part]));
+  env->part_busy[part] = true;
+  return ILRL_OK;
+}
+
+int ilrl_wait(ilrl_env* env, int32_t part) {
+  if (!env) return ILRL_ERR_ARG;
+  if (part < 0 || part >= ILRL_MAX_PARTS) return fail(env, ILRL_ERR_ARG, "ilrl_wait: part out of range");
+  if (!env->part_busy[part]) return ILRL_OK;
+  ON_DEVICE(env);
+  CK(cudaEventSynchronize(env->part_event[part]));
+  env->part_busy[part] = false;
+  return ILRL_OK;
+}
+
+int ilrl_set_config(ilrl_env* env, int32_t max_timestep, int32_t step_per_level, int32_t skip_frame) {
+  if (!env) return ILRL_ERR_ARG;
+  if (max_timestep > 0) env->cfg.max_timestep = max_timestep;
+  if (step_per_level > 0) env->cfg.step_per_level = step_per_level;
+  if (skip_frame > 0) env->cfg.skip_frame = skip_frame;
+  return ILRL_OK;
+}
+
 int ilrl_high_step(ilrl_env* env, const float* action2, float* low_obs, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (env->cfg.mode != 1) return fail(env, ILRL_ERR_ARG, "ilrl_high_step: handle is not in hier mode");
   if (!action2 || !low_obs) return fail(env, ILRL_ERR_ARG, "ilrl_high_step: null buffer");
   if (int r = check_ready(env)) return r;
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
   HighArgs a;
   a.n = env->n; a.step_per_level = (float)env->cfg.step_per_level; a.phys = env->phys; a.envf = env->envf;
   a.action2 = action2; a.low_obs = low_obs;
@@ -928,17 +1045,18 @@ int ilrl_high_step(ilrl_env* env, const float* action2, float* low_obs, void* st
 int ilrl_high_readout(ilrl_env* env, float* high_obs, float* high_reward, uint8_t* high_flags, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (env->cfg.mode != 1) return fail(env, ILRL_ERR_ARG, "ilrl_high_readout: handle is not in hier mode");
-  CK(cudaSetDevice(env->cfg.device));
-  cudaStream_t st = (cudaStream_t)stream;
-  if (high_obs) CK(cudaMemcpyAsync(high_obs, env->high_obs, sizeof(float) * 44 * env->n, cudaMemcpyDeviceToDevice, st));
-  if (high_reward) CK(cudaMemcpyAsync(high_reward, env->high_reward, sizeof(float) * env->n, cudaMemcpyDeviceToDevice, st));
-  if (high_flags) CK(cudaMemcpyAsync(high_flags, env->high_flags, env->n, cudaMemcpyDeviceToDevice, st));
+  ON_DEVICE(env);
+  const int words = 44 * env->n;
+  high_readout_kernel<<<(words + 255) / 256, 256, 0, (cudaStream_t)stream>>>(env->n, env->high_obs, env->high_reward, env->high_flags,
+                                                                           high_obs, high_reward, high_flags);
+  env->launches++;
+  CK(cudaGetLastError());
   return ILRL_OK;
 }
 
 int ilrl_get_state(ilrl_env* env, float* phys, float* envf, void* stream) {
   if (!env) return ILRL_ERR_ARG;
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
   state_get_kernel<<<(env->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(view(env), phys, envf);
   env->launches++;
   CK(cudaGetLastError());
@@ -946,7 +1064,7 @@ int ilrl_get_state(ilrl_env* env, float* phys, float* envf, void* stream) {
 }
 int ilrl_set_state(ilrl_env* env, const float* phys, const float* envf, void* stream) {
   if (!env) return ILRL_ERR_ARG;
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
   state_set_kernel<<<(env->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(view(env), phys, envf);
   env->launches++;
   CK(cudaGetLastError());
@@ -960,7 +1078,7 @@ int ilrl_set_forced_target_deg(ilrl_env* env, const int32_t* deg) {
 int ilrl_physics_only(ilrl_env* env, const float* torque, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (!torque) return fail(env, ILRL_ERR_ARG, "ilrl_physics_only: null buffer");
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
   if (env->layout == 2)
     physics_only_kernel<SmemDense4><<<(env->n + QE - 1) / QE, QT, sizeof(SmemDense4), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);
   else if (env->layout == 1)
@@ -975,7 +1093,7 @@ int ilrl_endpoint_score(ilrl_env* env, float* score, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (!score) return fail(env, ILRL_ERR_ARG, "ilrl_endpoint_score: null buffer");
   if (int r = check_ready(env)) return r;
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
   EpArgs a; a.v = view(env); a.score = score;
   memcpy(a.clips, env->clips, sizeof a.clips);
   endpoint_kernel<<<nblk(env->n), BLOCK, 0, (cudaStream_t)stream>>>(a);
@@ -986,7 +1104,7 @@ int ilrl_endpoint_score(ilrl_env* env, float* score, void* stream) {
 int ilrl_stats(ilrl_env* env, float* stats16, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (!stats16) return fail(env, ILRL_ERR_ARG, "ilrl_stats: null buffer");
-  CK(cudaSetDevice(env->cfg.device));
+  ON_DEVICE(env);
   stats_fetch_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(env->stats, stats16);
   env->launches++;
   CK(cudaGetLastError());

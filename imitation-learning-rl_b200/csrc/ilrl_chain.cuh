@@ -262,6 +262,8 @@ __device__ __forceinline__ const Tables& tables(const SM& sm) {
   if constexpr (SM::TSM) return sm.T; else return kTables;
 }
 
+constexpr unsigned FULLMASK = 0xffffffffu;
+
 // replicated floating-base state of one env
 struct Base { float p[3], quat[4], v[3], w[3]; };
 
@@ -725,69 +727,87 @@ __device__ __forceinline__ void row_fetch(const SM& sm, const float* gscr, int e
   else row_load(reinterpret_cast<const float4*>(gscr + (size_t)(r - SM::RSM) * RW), rr);
 }
 
-// 5 projected-Gauss-Seidel sweeps for the env of this quad
+// 5 projected-Gauss-Seidel sweeps for the env of this quad.  Row order in storage = evaluation order of a sweep:
+// limits [0, nlim), contact normals [nlim, nlim + ncon), then the friction pair of contact c at nlim + ncon + 2c.
+// Every lane of the warp is here and every shuffle carries the constant full mask (a run-time quad mask costs a
+// MATCH / REDUX / VOTE / branch preamble in front of every shuffle: in-order issue put ~100 cycles of it on the
+// critical path of each row evaluation), so the loops run to the WARP's largest count and a lane past its own count
+// evaluates its row 0 (finite: zeroed at tile start or a real row) with a zero step.
 template <bool OVER, class SM>
-__device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int role, int qb, unsigned qm, int nlim,
-                                           int ncon, float* zb, float* zc) {
+__device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int role, int qb, int nlim, int ncon,
+                                           float* zb, float* zc) {
+  constexpr bool FULL = true;
+  constexpr unsigned m = FULLMASK;
   float* lamv = sm.lam(e);
+  const int nfirst = nlim + ncon;
+  const int nf_w = __reduce_max_sync(FULLMASK, nfirst);
+  const int nc_w = __reduce_max_sync(FULLMASK, ncon);
 #pragma unroll 1
   for (int itn = 0; itn < ILRL_SOLVER_ITERS; itn++) {
     // limits, then contact normals.  The next row (independent of z) is fetched while this one is applied:
     // two register buffers used alternately (the loop is unrolled by two so that no copies are needed).
-    const int nfirst = nlim + ncon;
-    auto row_of = [&](int k) { return k < nlim ? k : nlim + 3 * (k - nlim); };
     auto fetch = [&](int k, RowRegs& rr, float& lam) {
-      const int r = row_of(k);
+      const bool live = !FULL || k < nfirst;
+      const int r = live ? k : 0;
       row_fetch<OVER>(sm, gscr, e, r, rr);
       lam = lamv[r];
     };
     auto apply = [&](int k, const RowRegs& rr, float lam) {
+      const bool live = !FULL || k < nfirst;
       const int L = __float_as_int(rr.c.w);
       const bool mine = role == L;
-      const float nl = fmaxf(lam + rr.b.z - row_jdot(rr, zb, zc, mine, qb + (L & 3), qm) * rr.b.w, 0.f);
-      lamv[row_of(k)] = nl;
-      row_axpy(rr, nl - lam, mine, zb, zc);
+      const float nl = fmaxf(lam + rr.b.z - row_jdot(rr, zb, zc, mine, qb + (L & 3), m) * rr.b.w, 0.f);
+      if (live) lamv[k] = nl;
+      row_axpy(rr, live ? nl - lam : 0.f, mine, zb, zc);
     };
     RowRegs ra, rb;
     float lama = 0.f, lamb = 0.f;
-    fetch(0, ra, lama);  // nrows > 0 implies nfirst > 0
+    if (nf_w > 0) fetch(0, ra, lama);
 #pragma unroll 1
-    for (int k = 0; k < nfirst; k += 2) {
-      if (k + 1 < nfirst) fetch(k + 1, rb, lamb);
+    for (int k = 0; k < nf_w; k += 2) {
+      if (k + 1 < nf_w) fetch(k + 1, rb, lamb);
       apply(k, ra, lama);
-      if (k + 1 < nfirst) {
-        if (k + 2 < nfirst) fetch(k + 2, ra, lama);
+      if (k + 1 < nf_w) {
+        if (k + 2 < nf_w) fetch(k + 2, ra, lama);
         apply(k + 1, rb, lamb);
       }
     }
 #pragma unroll 1
-    for (int c = 0; c < ncon; c++) {  // friction pairs, cone re-projected on the current normal impulse
-      const int rn = nlim + 3 * c;
-      const float ln = lamv[rn];
-      if (!(ln > 0.f)) continue;
+    for (int c = 0; c < nc_w; c++) {  // friction pairs, cone re-projected on the current normal impulse
+      const bool in = !FULL || c < ncon;
+      const float ln = in ? lamv[nlim + c] : 0.f;
+      const bool live = in && ln > 0.f;
+      if (!__any_sync(FULLMASK, live)) continue;
+      const int r1i = live ? nfirst + 2 * c : 0, r2i = live ? r1i + 1 : 0;
       RowRegs r1, r2;
-      row_fetch<OVER>(sm, gscr, e, rn + 1, r1);
-      row_fetch<OVER>(sm, gscr, e, rn + 2, r2);
+      row_fetch<OVER>(sm, gscr, e, r1i, r1);
+      row_fetch<OVER>(sm, gscr, e, r2i, r2);
       const int L = __float_as_int(r1.c.w);
       const bool mine = role == L;
       const float lim_f = (float)ILRL_FRICTION * ln;
-      const float l1 = lamv[rn + 1], l2 = lamv[rn + 2];
-      float s1 = l1 + r1.b.z - row_jdot(r1, zb, zc, mine, qb + (L & 3), qm) * r1.b.w;
-      float s2 = l2 + r2.b.z - row_jdot(r2, zb, zc, mine, qb + (L & 3), qm) * r2.b.w;
+      const float l1 = lamv[r1i], l2 = lamv[r2i];
+      float s1 = l1 + r1.b.z - row_jdot(r1, zb, zc, mine, qb + (L & 3), m) * r1.b.w;
+      float s2 = l2 + r2.b.z - row_jdot(r2, zb, zc, mine, qb + (L & 3), m) * r2.b.w;
       const float n2 = s1 * s1 + s2 * s2;
       if (n2 > lim_f * lim_f) { const float sc = lim_f * rsqrtf(n2); s1 *= sc; s2 *= sc; }
-      lamv[rn + 1] = s1; lamv[rn + 2] = s2;
-      row_axpy(r1, s1 - l1, mine, zb, zc);
-      row_axpy(r2, s2 - l2, mine, zb, zc);
+      if (live) { lamv[r1i] = s1; lamv[r2i] = s2; }
+      row_axpy(r1, live ? s1 - l1 : 0.f, mine, zb, zc);
+      row_axpy(r2, live ? s2 - l2 : 0.f, mine, zb, zc);
     }
   }
 }
 
 // ---- one substep of dt for the env of this quad.  Joint state / torques live in the link records.
+// ALL 32 lanes of a warp execute it, so that every shuffle carries the compile-time full mask (see pgs_sweeps) and an
+// env computes bit-identical results whoever its neighbours are: the lanes of an env that does not step (beyond the
+// end of the batch, waiting for a high-level action, skipped by a NaN action) run on a benign dummy state
+// (`steps` = false: they produce no constraint rows and their results are never stored), and they still help to build
+// the rows of the warp's other envs.  gscr_tile: overflow-row scratch of env 0 of this CTA's tile.
 template <class SM>
-__device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int tid, int role, unsigned qm, unsigned wm,
-                                        float dt) {
+__device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e, int tid, int role, bool steps, float dt) {
   constexpr int RSM = SM::RSM;
+  constexpr unsigned qm = FULLMASK, wm = FULLMASK;
+  float* gscr = gscr_tile + (size_t)e * (GROWS * RW);
   const int qb = tid & ~3;
   const Tables& T = tables(sm);
   // ---- phase A
@@ -866,6 +886,7 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
   }
   lim |= __shfl_xor_sync(qm, lim, 1); lim |= __shfl_xor_sync(qm, lim, 2);
   act |= __shfl_xor_sync(qm, act, 1); act |= __shfl_xor_sync(qm, act, 2);
+  if (!steps) { lim = 0; act = 0; }
   __syncwarp(qm);
   int nact = __popc(act);
   while (nact > MAXC) {  // keep the deepest MAXC (ties: drop the highest index); replicated in the quad
@@ -889,11 +910,12 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
   // ---- build the rows.  The items (one violated limit = one row, one contact = three rows) of the warp's 8 envs form
   // ONE pool per kind that is dealt to all its lanes: an env with many rows is helped by the lanes of envs with few
   // (every input of an item is in shared memory or one shuffle away), so a warp needs ceil(items / lanes) rounds of a
-  // builder instead of max over its envs of ceil(items / 4).  wm = lanes of this warp that execute the substep.
+  // builder instead of max over its envs of ceil(items / 4).
   {
     const float idt = 1.0f / dt;
-    const int lane = tid & 31, q_own = lane >> 2;
-    const int nlanes = __popc(wm), rank = __popc(wm & ((1u << lane) - 1u));
+    const int lane = tid & 31;
+    constexpr int nlanes = 32;
+    const int rank = lane;
     __syncwarp(wm);   // the link records and base factors of every env of the warp are complete
 #pragma unroll 1
     for (int kind = 0; kind < 2; kind++) {
@@ -901,8 +923,7 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
       int cnt[8], total = 0;
 #pragma unroll
       for (int q = 0; q < 8; q++) {
-        const int c = __shfl_sync(wm, n_own, 4 * q);
-        cnt[q] = ((wm >> (4 * q)) & 1u) ? c : 0;   // a quad that does not step has no items (its lanes are not here)
+        cnt[q] = __shfl_sync(wm, n_own, 4 * q);   // (a quad that does not step has no items)
         total += cnt[q];
       }
 #pragma unroll 1
@@ -913,43 +934,44 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr, int e, int
 #pragma unroll
         for (int t = 0; t < 7; t++)
           if (q == t && k >= cnt[t]) { k -= cnt[t]; q = t + 1; }
-        if (!has) { q = q_own; k = 0; }
+        if (!has) { q = lane >> 2; k = 0; }
         const int src = 4 * q;
         const uint32_t mask_q = __shfl_sync(wm, kind == 0 ? lim : act, src);
         const int nlim_q = __shfl_sync(wm, nlim, src);
         float bz_q = 0.f, nub_q[6];
+        int ncon_q = 0;
         if (kind == 1) {
+          ncon_q = __shfl_sync(wm, ncon, src);
           bz_q = __shfl_sync(wm, b.p[2], src);
 #pragma unroll
           for (int i = 0; i < 6; i++) nub_q[i] = __shfl_sync(wm, nub[i], src);
         }
         if (has) {
           const int e_q = (e & ~7) + q, qb_q = (tid & ~31) + 4 * q;
-          float* gscr_q = gscr + (ptrdiff_t)(q - q_own) * (GROWS * RW);
+          float* gscr_q = gscr_tile + (size_t)e_q * (GROWS * RW);
           auto row_ptr = [&](int r) { return r < RSM ? &sm.rows[e_q][r * RW] : gscr_q + (size_t)(r - RSM) * RW; };
           const int g = nth_set_bit(mask_q, k);
           if (kind == 0) {
             sm.lam(e_q)[k] = 0.f;
             build_limit_row(sm, T, g, e_q, qb_q, idt, row_ptr(k));
           } else {
-            const int r0 = nlim_q + 3 * k;
-            sm.lam(e_q)[r0] = 0.f; sm.lam(e_q)[r0 + 1] = 0.f; sm.lam(e_q)[r0 + 2] = 0.f;
+            const int r0 = nlim_q + k, r1 = nlim_q + ncon_q + 2 * k;   // normal | friction pair (storage = sweep order)
+            sm.lam(e_q)[r0] = 0.f; sm.lam(e_q)[r1] = 0.f; sm.lam(e_q)[r1 + 1] = 0.f;
             const float* sp = &sm.sph[g][0][e_q];
             build_contact_rows(sm, T, g, e_q, qb_q, idt, mk(sp[0], sp[QE], sp[2 * QE]), bz_q + sp[2 * QE], nub_q,
-                               row_ptr(r0), row_ptr(r0 + 1), row_ptr(r0 + 2));
+                               row_ptr(r0), row_ptr(r1), row_ptr(r1 + 1));
           }
         }
       }
     }
     __syncwarp(wm);   // rows of an env may have been written by lanes of another quad
   }
-  if (nrows > 0) {
+  if (__any_sync(FULLMASK, nrows > 0)) {
     // ---- projected Gauss-Seidel on the whitened impulse sum
-    // One loop variant per layout wherever both would be common: the quads of a warp that took different variants
-    // run them one after the other.  The on-chip layout holds every row in shared memory: no overflow variant at all.
-    if (RSM >= MAXROWS) pgs_sweeps<false>(sm, gscr, e, role, qb, qm, nlim, ncon, zb, zc);
-    else pgs_sweeps<true>(sm, gscr, e, role, qb, qm, nlim, ncon, zb, zc);
-    bwd_subst(&sm.L0[0][e], zb);   // velocity change of the base: dv_base = L0^-T z_base
+    // One loop variant per layout: the on-chip layout holds every row in shared memory (no overflow variant at all),
+    // the dense layouts always take the overflow-aware loads.
+    pgs_sweeps<(RSM < MAXROWS)>(sm, gscr, e, role, qb, nlim, ncon, zb, zc);
+    if (nrows > 0) bwd_subst(&sm.L0[0][e], zb);   // velocity change of the base: dv_base = L0^-T z_base
   }
   // ---- velocity change of the chain (outward sweep of dv = W^T z) and integration (exponential map on the torso
   // quaternion, as btMultiBody::stepPositionsMultiDof)
@@ -1006,6 +1028,19 @@ __device__ __forceinline__ void load_base(const float* phys, int n, int i, Base&
   for (int k = 0; k < 3; k++) { b.p[k] = p[k * n]; b.v[k] = p[(7 + k) * n]; b.w[k] = p[(10 + k) * n]; }
 #pragma unroll
   for (int k = 0; k < 4; k++) b.quat[k] = p[(3 + k) * n];
+}
+// benign state for the lanes of an env that does not step: upright at rest, zero joint state and torques
+template <class SM>
+__device__ __forceinline__ void dummy_state(SM& sm, int e, int tid, Base& b) {
+  b.p[0] = 0.f; b.p[1] = 0.f; b.p[2] = 1.4f;
+  b.quat[0] = b.quat[1] = b.quat[2] = 0.f; b.quat[3] = 1.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { b.v[k] = 0.f; b.w[k] = 0.f; }
+#pragma unroll
+  for (int c = 0; c < NL; c++) {
+    float* rec = link_rec(sm, c, e, tid);
+    rec[W_Q] = 0.f; rec[W_QD] = 0.f; rec[W_TAU] = 0.f;
+  }
 }
 // joint state of this lane's chain from HBM into the link records (spine: every lane writes the same values)
 template <class SM>

@@ -284,12 +284,13 @@ __device__ __forceinline__ void reset_pose(Phys& s, EnvW& w, const ClipDesc& cl,
 // rfx, rfy: origin of the right_foot body relative to the torso origin; sumx, sumy: sums of the 31 part offsets.
 template <int MODE>
 __device__ __forceinline__ void reset_finish(Phys& s, EnvW& w, const ClipDesc& cl, const ResetCtx& rx, float rfx,
-                                             float rfy, float sumx, float sumy, float step_per_level, Calc& c) {
+                                             float rfy, float sumx, float sumy, float step_per_level, int skip_frame,
+                                             Calc& c) {
   const int start_frame = rx.start_frame;
   const float rot = rx.rot;
   const float* ep0 = cl.ep + start_frame * 27;
   if (MODE == 0) {
-    const float* ep1 = cl.ep + ((start_frame + 2) % cl.max_frame) * 27;
+    const float* ep1 = cl.ep + ((start_frame + skip_frame) % cl.max_frame) * 27;  // REF low_level_env.py:278
     float rf[3] = {__ldg(ep0 + 9), __ldg(ep0 + 10), __ldg(ep0 + 11)}, rfr[3];  // RightFoot
     rotz(rot, rf, rfr);
     w.e[ILRL_E_SEP_X] = s.p[0] + rfx - rfr[0];
@@ -310,7 +311,7 @@ __device__ __forceinline__ void reset_finish(Phys& s, EnvW& w, const ClipDesc& c
     w.e[ILRL_E_STEPS_REMAINING] = step_per_level;
     w.e[ILRL_E_HIGH_PENDING] = 1.f;
   }
-  inc_frame(w, cl, 2);
+  inc_frame(w, cl, skip_frame);
   calc_state(s, sumx, sumy, w.e[ILRL_E_WALK_X], w.e[ILRL_E_WALK_Y], c);
   w.e[ILRL_E_OBS_SIN] = c.obs[1]; w.e[ILRL_E_OBS_COS] = c.obs[2];
 }
@@ -318,12 +319,12 @@ __device__ __forceinline__ void reset_finish(Phys& s, EnvW& w, const ClipDesc& c
 // thread-per-env form (reset kernel).  Leaves FK of the reset pose in k and the calc_state result in c.
 template <int MODE>
 __device__ __forceinline__ void reset_env(Phys& s, EnvW& w, const ClipDesc& cl, int start_frame, float yaw_deg,
-                                          int target_deg, float step_per_level, Work& k, Calc& c,
+                                          int target_deg, float step_per_level, int skip_frame, Work& k, Calc& c,
                                           const float* target_xy = nullptr) {
   ResetCtx rx;
   reset_pose<MODE>(s, w, cl, start_frame, yaw_deg, target_deg, rx, target_xy);
   fk(s, k);
-  reset_finish<MODE>(s, w, cl, rx, k.o[5][0], k.o[5][1], k.sumx, k.sumy, step_per_level, c);  // body 5 = right_foot
+  reset_finish<MODE>(s, w, cl, rx, k.o[5][0], k.o[5][1], k.sumx, k.sumy, step_per_level, skip_frame, c);  // body 5 = right_foot
 }
 
 // calcEndPointScore(useExp=True)

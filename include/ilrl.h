@@ -90,6 +90,24 @@ int ilrl_step(ilrl_env* env, const float* action_dev, float* obs_dev, float* rew
 int ilrl_step_host(ilrl_env* env, const float* action_host, float* obs_host, float* reward_host, uint8_t* done_host,
                    float* terms_host, void* stream);
 
+/* Double-buffered host stepping: the batch is cut into `nparts` (<= 8) contiguous parts of whole 16-env tiles and each
+ * part steps on its own stream, so that a rollout worker computes the actions of one part while another part steps
+ * (the asynchronous vector-env pattern; what hides the launch, PCIe and synchronise latencies that ilrl_step_host
+ * exposes once per step).  The arguments are the FULL [N, ...] arrays, page-locked and mapped (else ILRL_ERR_ARG):
+ * the kernel reads rows [first, first + count) of the actions and writes the same rows of obs / reward / done
+ * (/ terms) in place.  The call returns as soon as the step is enqueued; ilrl_wait(part) returns when the part's
+ * outputs have landed in host memory.  One step per part may be in flight (ILRL_ERR_STATE otherwise).  Parts are
+ * independent envs: stepping the parts separately gives bit-identical results to one ilrl_step_host of the batch.
+ * Replaces the same reference call as ilrl_step_host (REF low_level_env.py:322-323 under a vectorised worker). */
+int ilrl_step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const float* action_host, float* obs_host,
+                         float* reward_host, uint8_t* done_host, float* terms_host);
+int ilrl_wait(ilrl_env* env, int32_t part);
+
+/* The reference's drivers assign these attributes on a live env (REF env_vis_hier.py:52 `env.max_timestep = 100000`;
+ * hier_env_2.py:58-63 uses step_per_level 20 and skipFrame 5): change them on the handle.  A non-positive argument
+ * keeps the current value.  Takes effect from the next step / reset. */
+int ilrl_set_config(ilrl_env* env, int32_t max_timestep, int32_t step_per_level, int32_t skip_frame);
+
 /* hier mode: high-level agent's action (cos, sin of the heading) for every env that is waiting for one; the others
  * ignore their row, and so does a waiting env whose row starts with NaN.  low_obs_dev [N,70]: the low-level obs
  * the reference returns from high_level_step. */

@@ -365,6 +365,51 @@ def test_step_host_paths_agree():
         env.close()
 
 
+def test_step_host_async_parts_agree_with_one_batch_step():
+    """ilrl_step_host_async / ilrl_wait: stepping the batch as 2 or 3 double-buffered parts (each on its own stream,
+    interleaved the way a rollout worker would) gives bit-identical results to ilrl_step of the whole batch."""
+    n = 1000   # parts of whole 16-env tiles: 2 x 512 (last one short), 3 x 336
+    rng = np.random.default_rng(5)
+    acts = rng.uniform(-1.2, 1.2, (5, n, 17)).astype(np.float32)
+    ref = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], seed=13, auto_reset=True)
+    ref.reset()
+    want = []
+    for a in acts:
+        o, r, d, t = ref.step(torch.from_numpy(a).cuda())
+        want.append((o.cpu().numpy().copy(), r.cpu().numpy().copy(), d.cpu().numpy().copy(), t.cpu().numpy().copy()))
+    ref.close()
+    for nparts in (2, 3):
+        env = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], seed=13, auto_reset=True)
+        env.reset()
+        pin = lambda shape, dt: torch.zeros(*shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+        a_h, o_h, r_h, d_h, t_h = pin((n, 17), torch.float32), pin((n, 70), torch.float32), pin((n,), torch.float32), \
+            pin((n,), torch.uint8), pin((n, 12), torch.float32)
+        sl = [env.part_slice(p, nparts) for p in range(nparts)]
+        assert sl[0].start == 0 and sl[-1].stop == n and all(sl[i].stop == sl[i + 1].start for i in range(nparts - 1))
+        # software pipeline: part p of step k is submitted while part p-1 of step k is still in flight
+        for p in range(nparts):
+            a_h[sl[p]] = acts[0][sl[p]]
+            env.step_host_async(p, nparts, a_h, o_h, r_h, d_h, t_h)
+        for k in range(len(acts)):
+            for p in range(nparts):
+                env.wait(p)
+                np.testing.assert_array_equal(o_h[sl[p]], want[k][0][sl[p]])
+                np.testing.assert_array_equal(r_h[sl[p]], want[k][1][sl[p]])
+                np.testing.assert_array_equal(d_h[sl[p]], want[k][2][sl[p]])
+                np.testing.assert_array_equal(t_h[sl[p]], want[k][3][sl[p]])
+                if k + 1 < len(acts):
+                    a_h[sl[p]] = acts[k + 1][sl[p]]
+                    env.step_host_async(p, nparts, a_h, o_h, r_h, d_h, t_h)
+        # a part that is in flight cannot be submitted again; pageable buffers are refused
+        env.step_host_async(0, nparts, a_h, o_h, r_h, d_h, t_h)
+        with pytest.raises(Exception):
+            env.step_host_async(0, nparts, a_h, o_h, r_h, d_h, t_h)
+        env.wait(0)
+        with pytest.raises(Exception):
+            env.step_host_async(0, nparts, np.zeros((n, 17), np.float32), o_h, r_h, d_h, t_h)
+        env.close()
+
+
 def test_c_abi_error_behaviour_on_device():
     """Call-order and argument errors come back as negative ilrl_status codes with a message, never as a crash."""
     import ctypes as C

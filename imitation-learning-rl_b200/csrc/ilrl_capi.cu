@@ -154,15 +154,26 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   const int base = a.first + tile * QE;
   const int i = base + e;
   const bool valid = i < a.end;
-  if (valid) {  // the quad stages its env's action row (the 8 rows of a warp are one contiguous 544-byte block)
+  // Head of a tile: every global load it needs (action row, waiting flag, base and chain state) is issued before any of
+  // them is consumed - one memory round trip instead of three dependent ones (actions -> flag -> state).
+  chain::Base b;
+  float av[(NJ + 3) / 4], qv[chain::NL], qdv[chain::NL], pend_flag = 0.f;
+#pragma unroll
+  for (int m = 0; m < (NJ + 3) / 4; m++) av[m] = 0.f;
+  if (valid) {  // (the 8 action rows of a warp are one contiguous 544-byte block)
     const float* arow = a.action + (size_t)i * NJ;
+#pragma unroll
+    for (int m = 0; m < (NJ + 3) / 4; m++) if (role + 4 * m < NJ) av[m] = arow[role + 4 * m];
+    if (MODE == 1) pend_flag = a.envf[(size_t)ILRL_E_HIGH_PENDING * a.n + i];
+    chain::load_base(a.phys, a.n, i, b);
+    chain::load_links(a.phys, a.n, i, sm, role, qv, qdv);
     float* dst = sm.act(e);
 #pragma unroll
-    for (int m = role; m < NJ; m += 4) dst[m] = arow[m];
+    for (int m = 0; m < (NJ + 3) / 4; m++) if (role + 4 * m < NJ) dst[role + 4 * m] = av[m];
   }
   // row 0 of every env must hold finite numbers: lanes past their own row count evaluate it with a zero step
   reinterpret_cast<float4*>(&sm.rows[e][0])[role] = make_float4(0.f, 0.f, 0.f, 0.f);
-  __syncthreads();
+  __syncwarp();
   bool write_obs = false;
   float st_ep = 0.f, st_ret = 0.f, st_len = 0.f, st_steps = 0.f, st_rew = 0.f, st_terms[11];
 #pragma unroll
@@ -170,8 +181,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
 
   // skipped envs: hier envs waiting for a high-level action, and rows whose first action component is NaN (the
   // batched adapters' "no action for this env in this call"; the reference asserts finite actions, REF humanoid.py:55)
-  const bool pending = valid && ((MODE == 1 && a.envf[(size_t)ILRL_E_HIGH_PENDING * a.n + i] != 0.f) ||
-                                 isnan(sm.act(e)[0]));
+  const bool pending = valid && ((MODE == 1 && pend_flag != 0.f) || isnan(sm.act(e)[0]));
   if (valid && pending) {
     if (role == 0) { a.reward[i] = 0.f; a.done[i] = 0; }
     if (a.terms)
@@ -183,13 +193,11 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   // Every lane runs the substeps (compile-time full shuffle masks, chain::substep): the lanes of an env that does
   // not step carry a benign dummy state that is never stored.
   const bool active = valid && !pending;
-  chain::Base b;
   float act[NJ];
   float stale_x = 0.f, stale_y = 0.f;
   float sumx = 0.f, sumy = 0.f, rfx = 0.f, rfy = 0.f;
   if (active) {
-    chain::load_base(a.phys, a.n, i, b);
-    chain::load_links(a.phys, a.n, i, sm, e, tid, role);
+    chain::store_links(sm, e, tid, qv, qdv);
 #pragma unroll
     for (int m = 0; m < NJ; m++) act[m] = sm.act(e)[m];
     set_torques(sm, e, tid, role, sm.act(e), nullptr);
@@ -322,16 +330,17 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
       for (int k = 0; k < ILRL_ENV_WORDS; k++) if ((k & 3) == role) ew[(size_t)k * a.n] = w.e[k];
     }
   }
-  // observations: only envs that stepped write their row (pending hier envs keep theirs); coalesced CTA store
+  // observations: only envs that stepped write their row (pending hier envs keep theirs).  Each warp stores the rows of
+  // its own 8 envs (one contiguous 2240-byte block of the caller's array) from the staging area, 8 bytes per lane.
   {
-    __shared__ unsigned int wrote[QT / 32];
-    unsigned int okmask = __ballot_sync(0xffffffffu, write_obs);
-    if ((tid & 31) == 0) wrote[tid >> 5] = okmask;
-    __syncthreads();
-    const int cnt = min(QE, a.end - base) * 70;
-    for (int t = tid; t < cnt; t += QT) {
-      int r = t / 70, cc = t - r * 70;
-      if ((wrote[r >> 3] >> ((r & 7) * 4)) & 1u) a.obs[(size_t)base * 70 + t] = sm.scr[r][cc];
+    const unsigned okmask = __ballot_sync(0xffffffffu, write_obs);   // (includes the staging writes' __syncwarp)
+    const int e0 = e & ~7, lane = tid & 31;
+    float* orow = a.obs + (size_t)(base + e0) * 70;
+#pragma unroll 1
+    for (int f = lane; f < 8 * 35; f += 32) {
+      const int r = f / 35, c2 = f - r * 35;
+      if ((okmask >> (4 * r)) & 1u)
+        *reinterpret_cast<float2*>(orow + r * 70 + 2 * c2) = *reinterpret_cast<const float2*>(&sm.scr[e0 + r][2 * c2]);
     }
   }
   // K5: episode / reward statistics -> one atomicAdd per warp per slot
@@ -476,8 +485,10 @@ __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const flo
   const bool valid = i < v.n;
   chain::Base b;
   if (valid) {
+    float qv[chain::NL], qdv[chain::NL];
     chain::load_base(v.phys, v.n, i, b);
-    chain::load_links(v.phys, v.n, i, sm, e, tid, role);
+    chain::load_links(v.phys, v.n, i, sm, role, qv, qdv);
+    chain::store_links(sm, e, tid, qv, qdv);
     set_torques(sm, e, tid, role, nullptr, torque + (size_t)i * NJ);
   } else {
     chain::dummy_state(sm, e, tid, b);

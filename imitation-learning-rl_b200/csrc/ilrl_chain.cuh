@@ -446,7 +446,7 @@ __device__ __forceinline__ SV chol6_solve_smem(const float* L, SV b) {
 // ---- phase A: forward kinematics, link velocities, velocity-product accelerations, body records, contact candidates.
 // Returns the candidate mask of the spheres this lane saw, the sums of part origins (spine part replicated in ssx/ssy,
 // limb part in sx/sy) and the origin of the lane's end body.
-struct FkOut { uint32_t act; float sx, sy, ssx, ssy, ex, ey; };
+struct FkOut { uint32_t act, lim; float sx, sy, ssx, ssy, ex, ey; };
 
 // FULL = false: pose only (part-origin sums and the end-body origin), nothing is written to shared memory.
 template <bool FULL, class SM>
@@ -455,7 +455,7 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
   float R0[9];
   quat2mat(b.quat[0], b.quat[1], b.quat[2], b.quat[3], R0);
   SV V0; V0.a = rd3(b.w); V0.l = rd3(b.v);
-  uint32_t act = 0;
+  uint32_t act = 0, lim = 0;
   // torso spheres
   // (a body whose origin is higher than its reach + the breaking distance cannot have a candidate: skip its spheres)
   if (FULL && b.p[2] - T.torso_reach < (float)ILRL_CONTACT_BREAK) {
@@ -500,7 +500,9 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
     S.l = cross(rw, S.a);
     {
       float sn, cs;
-      sincos_joint(rec[W_Q], sn, cs);
+      const float q = rec[W_Q];
+      if (FULL && L.j >= 0 && (q - L.lo <= 0.f || L.hi - q <= 0.f)) lim |= 1u << L.j;   // violated joint limit
+      sincos_joint(q, sn, cs);
       const float t = 1.f - cs;
       float Rj[9], Rn[9];
       Rj[0] = t * ax.x * ax.x + cs;        Rj[1] = t * ax.x * ax.y - sn * ax.z; Rj[2] = t * ax.x * ax.z + sn * ax.y;
@@ -552,7 +554,7 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
       }
     }
   }
-  o.act = act; o.sx = sx; o.sy = sy; o.ssx = ssx; o.ssy = ssy; o.ex = ex; o.ey = ey;
+  o.act = act; o.lim = lim; o.sx = sx; o.sy = sy; o.ssx = ssx; o.ssy = ssy; o.ex = ex; o.ey = ey;
 }
 
 // sums of the 31 part offsets (relative to the torso) and the right-foot origin, for calc_state / resetFromFrame
@@ -705,13 +707,18 @@ __device__ __forceinline__ void build_contact_rows(const SM& sm, const Tables& T
 struct RowRegs { float4 a, b, c, d; };
 template <class P4>
 __device__ __forceinline__ void row_load(P4 rp, RowRegs& r) { r.a = rp[0]; r.b = rp[1]; r.c = rp[2]; r.d = rp[3]; }
-__device__ __forceinline__ float row_jdot(const RowRegs& r, const float* zb, const float* zc, bool mine, int src, unsigned qm) {
-  // three short chains instead of one 9-deep one: this dot product sits on the Gauss-Seidel critical path
+// lam + rhs - (z_row . z) * dinv.  This sits on the Gauss-Seidel critical path: the limb part (owned by one lane of the
+// quad) is requested first, the replicated base / spine part is folded into the constant while the shuffle is in
+// flight (three short chains instead of one 9-deep one), one multiply-add remains after it.
+__device__ __forceinline__ float row_resid(const RowRegs& r, float lam, const float* zb, const float* zc, bool mine, int src,
+                                           unsigned qm) {
+  const float own = mine ? fmaf(r.d.y, zc[4], r.d.x * zc[3]) + fmaf(r.d.w, zc[6], r.d.z * zc[5]) : 0.f;
+  const float part = __shfl_sync(qm, own, src);
   const float r0 = fmaf(r.a.z, zb[2], fmaf(r.a.y, zb[1], r.a.x * zb[0]));
   const float r1 = fmaf(r.b.y, zb[5], fmaf(r.b.x, zb[4], r.a.w * zb[3]));
   const float r2 = fmaf(r.c.z, zc[2], fmaf(r.c.y, zc[1], r.c.x * zc[0]));
-  const float own = mine ? fmaf(r.d.y, zc[4], r.d.x * zc[3]) + fmaf(r.d.w, zc[6], r.d.z * zc[5]) : 0.f;
-  return (r0 + r1) + (r2 + __shfl_sync(qm, own, src));
+  const float t = fmaf(-r.b.w, (r0 + r1) + r2, lam + r.b.z);
+  return fmaf(-r.b.w, part, t);
 }
 __device__ __forceinline__ void row_axpy(const RowRegs& r, float a, bool mine, float* zb, float* zc) {
   zb[0] += a * r.a.x; zb[1] += a * r.a.y; zb[2] += a * r.a.z; zb[3] += a * r.a.w; zb[4] += a * r.b.x; zb[5] += a * r.b.y;
@@ -756,7 +763,7 @@ __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int
       const bool live = !FULL || k < nfirst;
       const int L = __float_as_int(rr.c.w);
       const bool mine = role == L;
-      const float nl = fmaxf(lam + rr.b.z - row_jdot(rr, zb, zc, mine, qb + (L & 3), m) * rr.b.w, 0.f);
+      const float nl = fmaxf(row_resid(rr, lam, zb, zc, mine, qb + (L & 3), m), 0.f);
       if (live) lamv[k] = nl;
       row_axpy(rr, live ? nl - lam : 0.f, mine, zb, zc);
     };
@@ -786,8 +793,8 @@ __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int
       const bool mine = role == L;
       const float lim_f = (float)ILRL_FRICTION * ln;
       const float l1 = lamv[r1i], l2 = lamv[r2i];
-      float s1 = l1 + r1.b.z - row_jdot(r1, zb, zc, mine, qb + (L & 3), m) * r1.b.w;
-      float s2 = l2 + r2.b.z - row_jdot(r2, zb, zc, mine, qb + (L & 3), m) * r2.b.w;
+      float s1 = row_resid(r1, l1, zb, zc, mine, qb + (L & 3), m);
+      float s2 = row_resid(r2, l2, zb, zc, mine, qb + (L & 3), m);
       const float n2 = s1 * s1 + s2 * s2;
       if (n2 > lim_f * lim_f) { const float sc = lim_f * rsqrtf(n2); s1 *= sc; s2 *= sc; }
       if (live) { lamv[r1i] = s1; lamv[r2i] = s2; }
@@ -813,7 +820,7 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
   // ---- phase A
   FkOut fo;
   fk_phase<true>(b, sm, e, tid, role, fo);
-  uint32_t act = fo.act, lim = 0;
+  uint32_t act = fo.act, lim = fo.lim;
   // ---- phase B: inward pass
   SV a0;
   {
@@ -871,7 +878,6 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
     for (int c = 0; c < NL; c++) {
       if (c == 3 && role >= 2) ap = a0;
       float* rec = link_rec(sm, c, e, tid);
-      const LinkC& L = c < 3 ? T.lc[4][c] : T.lc[role][c - 3];
       SV S, cJ, U;
       float di, uu;
       ld_all(rec, S, cJ, U, di, uu);
@@ -880,8 +886,6 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
       const float qa = di * (uu - sdot(ad, U));
       rec[W_NU] = clampf(st4.y + dt * qa, -M, M);
       ap = ad + qa * S;
-      const float q = st4.x;
-      if (L.j >= 0 && (q - L.lo <= 0.f || L.hi - q <= 0.f)) lim |= 1u << L.j;
     }
   }
   lim |= __shfl_xor_sync(qm, lim, 1); lim |= __shfl_xor_sync(qm, lim, 2);
@@ -1042,16 +1046,25 @@ __device__ __forceinline__ void dummy_state(SM& sm, int e, int tid, Base& b) {
     rec[W_Q] = 0.f; rec[W_QD] = 0.f; rec[W_TAU] = 0.f;
   }
 }
-// joint state of this lane's chain from HBM into the link records (spine: every lane writes the same values)
+// joint state of this lane's chain from HBM into registers / from registers into the link records (spine: every lane
+// writes the same values).  Two steps so that the loads of a tile's head are all in flight before the first is consumed.
 template <class SM>
-__device__ __forceinline__ void load_links(const float* phys, int n, int i, SM& sm, int e, int tid, int role) {
+__device__ __forceinline__ void load_links(const float* phys, int n, int i, const SM& sm, int role, float* qv, float* qdv) {
   const float* p = phys + i;
 #pragma unroll
   for (int c = 0; c < NL; c++) {
-    float* rec = link_rec(sm, c, e, tid);
     const int j = c < 3 ? c : tables(sm).lc[role][c - 3].j;
-    rec[W_Q] = j >= 0 ? p[(13 + j) * n] : 0.f;
-    rec[W_QD] = j >= 0 ? p[(30 + j) * n] : 0.f;
+    qv[c] = j >= 0 ? p[(13 + j) * n] : 0.f;
+    qdv[c] = j >= 0 ? p[(30 + j) * n] : 0.f;
+  }
+}
+template <class SM>
+__device__ __forceinline__ void store_links(SM& sm, int e, int tid, const float* qv, const float* qdv) {
+#pragma unroll
+  for (int c = 0; c < NL; c++) {
+    float* rec = link_rec(sm, c, e, tid);
+    rec[W_Q] = qv[c];
+    rec[W_QD] = qdv[c];
   }
 }
 // link records -> full Phys in every lane

@@ -58,6 +58,9 @@ struct StepArgs {
   float* gscr;         // [n][GROWS][RW] overflow scratch for constraint rows beyond the shared-memory budget
   unsigned int* tile_counter;  // [2]: next tile to hand out, CTAs that have left (both zero between launches)
   int ntiles;
+#ifdef ILRL_PROF
+  long long* prof;     // [warps of the launch][PF_WORDS] phase cycles (measurement build only)
+#endif
   ClipDesc clips[MAX_CLIPS];
 };
 
@@ -154,6 +157,12 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   const int base = a.first + tile * QE;
   const int i = base + e;
   const bool valid = i < a.end;
+  chain::Prof pf;
+#ifdef ILRL_PROF
+  if (a.prof && (tid & 31) == 0) pf.p = a.prof + (size_t)(tile * (QT / 32) + (tid >> 5)) * chain::PF_WORDS;
+  const long long t_tile = clock64();
+#endif
+  pf.start();
   // Head of a tile: every global load it needs (action row, waiting flag, base and chain state) is issued before any of
   // them is consumed - one memory round trip instead of three dependent ones (actions -> flag -> state).
   chain::Base b;
@@ -215,11 +224,14 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     float* gscr_tile = a.gscr + (size_t)min(base, a.n - 1) * chain::GROWS * chain::RW;
 #pragma unroll 1
     for (int sub = 0; sub < ILRL_SUBSTEPS; sub++) {
+      pf.mark(sub == 0 ? chain::PF_HEAD : chain::PF_INTEG);
       __syncthreads();
-      chain::substep(b, sm, gscr_tile, e, tid, role, active, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+      pf.mark(chain::PF_BARRIER);
+      chain::substep(b, sm, gscr_tile, e, tid, role, active, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf);
     }
   }
   __syncthreads();   // the once-per-step tail (4 k instructions) is entered together as well: +3 % at 65536 envs
+  pf.mark(chain::PF_BARRIER);
   if (active) {
     chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);
     Phys ps;
@@ -356,6 +368,10 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
       if ((tid & 31) == 0 && x != 0.f) atomicAdd(a.stats + t, x);
     }
   }
+  pf.mark(chain::PF_TAIL);
+#ifdef ILRL_PROF
+  if (pf.p) pf.p[chain::PF_TOTAL] += clock64() - t_tile;
+#endif
   __syncthreads();  // every warp is done with this tile's shared memory (and with s_tile) before the next one
   }  // tile loop
   if (!one_wave && tid == 0 && atomicAdd(a.tile_counter + 1, 1u) == gridDim.x - 1) {  // last CTA out: ready for the next launch
@@ -496,7 +512,7 @@ __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const flo
   __syncwarp();
   float* gscr_tile = gscr_all + (size_t)blockIdx.x * QE * chain::GROWS * chain::RW;
   for (int sub = 0; sub < nsub; sub++)
-    chain::substep(b, sm, gscr_tile, e, tid, role, valid, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS));
+    { chain::Prof pf; chain::substep(b, sm, gscr_tile, e, tid, role, valid, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf); }
   if (!valid) return;
   Phys ps;
   chain::gather(b, sm, e, qb, qm, ps);
@@ -612,6 +628,9 @@ struct ilrl_env {
   cudaEvent_t part_event[ILRL_MAX_PARTS] = {nullptr};
   bool part_busy[ILRL_MAX_PARTS] = {false};
   int32_t* clip_ids_dev = nullptr;        // staging for ilrl_set_clip_ids
+#ifdef ILRL_PROF
+  long long* prof = nullptr;
+#endif
   int grid_small = 0, grid_large = 0, grid_dense4 = 0;  // resident CTAs of the step kernel in each layout
   float* clip_mem[MAX_CLIPS] = {nullptr};
   ClipDesc clips[MAX_CLIPS];
@@ -759,6 +778,10 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMemset(env->high_reward, 0, sizeof(float) * n));
   CKC(cudaMemset(env->high_flags, 0, n));
   CKC(cudaMemset(env->stats, 0, sizeof(float) * ILRL_STATS_WORDS));
+#ifdef ILRL_PROF
+  CKC(cudaMalloc(&env->prof, sizeof(long long) * chain::PF_WORDS * ((n + 7) / 8 + 2)));
+  CKC(cudaMemset(env->prof, 0, sizeof(long long) * chain::PF_WORDS * ((n + 7) / 8 + 2)));
+#endif
   CKC(cudaEventCreate(&env->ev0));
   CKC(cudaEventCreate(&env->ev1));
   CKC(cudaDeviceSynchronize());
@@ -873,6 +896,9 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
   a.forced_deg = env->forced_deg; a.stats = env->stats; a.gscr = env->gscr;
   a.tile_counter = env->tile_counter + 2 * (part + 1);
+#ifdef ILRL_PROF
+  a.prof = env->prof;
+#endif
   memcpy(a.clips, env->clips, sizeof a.clips);
   if (env->timing) CK(cudaEventRecord(env->ev0, st));
   a.ntiles = (count + QE - 1) / QE;
@@ -1136,6 +1162,18 @@ int ilrl_gae_decisions(const float* reward, const uint8_t* flags, const float* v
 }
 /* harness only, not in ilrl.h: on = 0 forces ilrl_step_host onto explicit copies even for page-locked buffers */
 int ilrl_debug_zero_copy(ilrl_env* env, int32_t on) { if (!env) return ILRL_ERR_ARG; env->no_zero_copy = on == 0; return ILRL_OK; }
+#ifdef ILRL_PROF
+/* measurement build only: copy out and clear the per-warp phase cycles ([ceil(N/8)][16] int64) */
+int ilrl_debug_profile(ilrl_env* env, long long* out_host) {
+  if (!env || !out_host) return ILRL_ERR_ARG;
+  ON_DEVICE(env);
+  const size_t bytes = sizeof(long long) * chain::PF_WORDS * ((env->n + 7) / 8);
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out_host, env->prof, bytes, cudaMemcpyDeviceToHost));
+  CK(cudaMemset(env->prof, 0, bytes));
+  return ILRL_OK;
+}
+#endif
 /* harness only, not in ilrl.h: number of substeps ilrl_physics_only runs */
 int ilrl_debug_substeps(ilrl_env* env, int32_t n) { if (!env || n < 1) return ILRL_ERR_ARG; env->substeps = n; return ILRL_OK; }
 int64_t ilrl_launch_count(const ilrl_env* env) { return env ? env->launches : 0; }

@@ -264,6 +264,26 @@ __device__ __forceinline__ const Tables& tables(const SM& sm) {
 
 constexpr unsigned FULLMASK = 0xffffffffu;
 
+// Phase timer of the measurement build (-DILRL_PROF, tools/warp_profile.py): lane 0 of every warp accumulates clock64()
+// intervals per phase.  In the product build it is an empty object and every call vanishes.
+enum { PF_HEAD = 0, PF_FK, PF_INWARD, PF_OUTWARD, PF_ROWS, PF_PGS, PF_INTEG, PF_TAIL, PF_BARRIER, PF_TOTAL,
+       PF_MAXROWS, PF_WORDS = 16 };
+#ifdef ILRL_PROF
+struct Prof {
+  long long* p = nullptr;
+  long long t = 0;
+  __device__ __forceinline__ void start() { t = clock64(); }
+  __device__ __forceinline__ void mark(int k) { if (p) { const long long n = clock64(); p[k] += n - t; t = n; } }
+  __device__ __forceinline__ void maxv(int k, long long v) { if (p && v > p[k]) p[k] = v; }
+};
+#else
+struct Prof {
+  __device__ __forceinline__ void start() {}
+  __device__ __forceinline__ void mark(int) {}
+  __device__ __forceinline__ void maxv(int, long long) {}
+};
+#endif
+
 // replicated floating-base state of one env
 struct Base { float p[3], quat[4], v[3], w[3]; };
 
@@ -811,7 +831,8 @@ __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int
 // (`steps` = false: they produce no constraint rows and their results are never stored), and they still help to build
 // the rows of the warp's other envs.  gscr_tile: overflow-row scratch of env 0 of this CTA's tile.
 template <class SM>
-__device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e, int tid, int role, bool steps, float dt) {
+__device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e, int tid, int role, bool steps, float dt,
+                                        Prof& pf) {
   constexpr int RSM = SM::RSM;
   constexpr unsigned qm = FULLMASK, wm = FULLMASK;
   float* gscr = gscr_tile + (size_t)e * (GROWS * RW);
@@ -821,6 +842,7 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
   FkOut fo;
   fk_phase<true>(b, sm, e, tid, role, fo);
   uint32_t act = fo.act, lim = fo.lim;
+  pf.mark(PF_FK);
   // ---- phase B: inward pass
   SV a0;
   {
@@ -864,6 +886,7 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
     __syncwarp(qm);
     a0 = chol6_solve_smem(&sm.L0[0][e], neg(x.p));
   }
+  pf.mark(PF_INWARD);
   // ---- phase C: outward pass -> unconstrained new velocities; violated limits
   float nub[6];
   {
@@ -906,6 +929,8 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
     nact--;
   }
   const int nlim = __popc(lim), ncon = nact, nrows = nlim + 3 * ncon;
+  pf.mark(PF_OUTWARD);
+  pf.maxv(PF_MAXROWS, (long long)__reduce_max_sync(FULLMASK, nrows));
   float zb[6], zc[NL];   // whitened impulse sum: base (replicated), chain (spine replicated, limb private)
 #pragma unroll
   for (int i = 0; i < 6; i++) zb[i] = 0.f;
@@ -970,13 +995,17 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
     }
     __syncwarp(wm);   // rows of an env may have been written by lanes of another quad
   }
-  if (__any_sync(FULLMASK, nrows > 0)) {
-    // ---- projected Gauss-Seidel on the whitened impulse sum
-    // One loop variant per layout: the on-chip layout holds every row in shared memory (no overflow variant at all),
-    // the dense layouts always take the overflow-aware loads.
-    pgs_sweeps<(RSM < MAXROWS)>(sm, gscr, e, role, qb, nlim, ncon, zb, zc);
-    if (nrows > 0) bwd_subst(&sm.L0[0][e], zb);   // velocity change of the base: dv_base = L0^-T z_base
-  }
+  pf.mark(PF_ROWS);
+  // ---- projected Gauss-Seidel on the whitened impulse sum (warp-uniform loops).  One loop variant per layout: the
+  // on-chip layout holds every row in shared memory (no overflow variant at all), the dense layouts always take the
+  // overflow-aware loads.
+  // (A dense variant - Delassus matrix Z Z^T formed once per substep, sweeps on w = A lambda in registers, no shuffle -
+  // was built and measured: 45.3M against 52.8M env-steps/s at 4096 envs; the per-slot blocks are if-converted and
+  // every warp pays for all 20 slots, and it broke bit-identity between the layouts.  profiles/r2_warp_phases.txt.)
+  if (__any_sync(FULLMASK, nrows > 0)) pgs_sweeps<(RSM < MAXROWS)>(sm, gscr, e, role, qb, nlim, ncon, zb, zc);
+  if (nrows > 0) bwd_subst(&sm.L0[0][e], zb);   // velocity change of the base: dv_base = L0^-T z_base
+  __syncwarp();
+  pf.mark(PF_PGS);
   // ---- velocity change of the chain (outward sweep of dv = W^T z) and integration (exponential map on the torso
   // quaternion, as btMultiBody::stepPositionsMultiDof)
   {
@@ -1023,6 +1052,7 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
     }
   }
   __syncwarp(qm);
+  pf.mark(PF_INTEG);
 }
 
 // ---- state movement between HBM (SoA phys[47][n]), the link records and a replicated full Phys

@@ -102,27 +102,33 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+def reference_envs_per_core(cores):
+    """The CPU arm steps the SAME number of envs as one GPU of the contract workload (4096), split over the host threads."""
+    return max(1, ENVS_PER_GPU // max(cores, 1))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = host_cores()
-    envs_per_core = 64  # bounded sample of the 4096-env workload: `cores` x 64 envs
-    # one "step" of this arm advances every sampled env by `inner` env steps, sized so that the timed part lasts about
-    # 12 s whatever K is (a 20-step run of single env steps would time 20 ms of cold threads: measured 0.12 M env-steps/s
-    # against 0.21 M in steady state)
-    inner = max(1, min(200, int(12.0 * 2.0e5 / (cores * envs_per_core * max(args.steps, 1)))))
-    total, dt = cpu_rollout(cores, envs_per_core, min(args.warmup * inner, 200), args.steps * inner)
+    envs_per_core = reference_envs_per_core(cores)
+    n_envs = cores * envs_per_core
+    # one "step" of this arm advances every env of the 4096-env workload by `inner` env steps, sized so that the timed
+    # part lasts about 12 s whatever K is (a 20-step run of single env steps would time 0.4 s of cold threads)
+    inner = max(1, min(200, int(12.0 * 2.0e5 / (n_envs * max(args.steps, 1)))))
+    total, dt = cpu_rollout(cores, envs_per_core, min(args.warmup * inner, 20), args.steps * inner)
     value = total / dt
-    sample = "%d host threads x %d oracle envs (C, fp64, dense 23x23 dynamics) x %d steps of %d env steps of the same workload" % (
-        cores, envs_per_core, args.steps, inner)
+    sample = "%d host threads x %d oracle envs = %d envs (C, fp64, dense 23x23 dynamics) x %d steps of %d env steps of the same workload" % (
+        cores, envs_per_core, n_envs, args.steps, inner)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_step": cores * envs_per_core, "env_steps_per_env_per_step": inner,
-                   "note": "reference arm = oracle/ilrl_oracle.c (port of the reference path; the reference's own "
-                           "implementation needs PyBullet, which is not installable here)"},
+        "config": {"workload": WORKLOAD, "envs_per_gpu": n_envs, "env_steps_per_env_per_step": inner,
+                   "note": "reference arm = oracle/ilrl_oracle.c, a CPU PORT of the reference path written for this repo "
+                           "(the reference's own implementation needs PyBullet, which is not installable here): ratios "
+                           "against this line are ratios against that port, not against PyBullet"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -132,83 +138,85 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock, power and throttle reasons of one GPU, sampled IN PROCESS through NVML every 2 ms by a thread, from
+    before the warm-up to the end of the last timed region (nvidia-smi -lms cannot sample a 2 ms region).  `mark()`
+    brackets the regions that count as "under load"."""
 
-    def __init__(self, gpu_index):
-        self.path = "/tmp/ilrl_clocks_%d_%d.csv" % (os.getpid(), gpu_index)
-        self.p = None
+    def __init__(self, torch_device_index):
+        self.samples = []          # (t, sm_mhz, power_w, reasons_bitmask)
+        self.marks = []            # [t0, t1] load intervals
+        self.ok = False
+        self._stop = threading.Event()
         try:
-            self.f = open(self.path, "w")
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except Exception:
-            self.p = None
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            h = None
+            try:
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(torch_device_index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(torch_device_index)
+            self.nv, self.h = pynvml, h
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+            self.th = threading.Thread(target=self._run, daemon=True)
+            self.th.start()
+        except Exception as e:  # no NVML: the driver's own sampler is the only evidence
+            self.err = repr(e)
+
+    def _run(self):
+        nv, h = self.nv, self.h
+        while not self._stop.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                except Exception:
+                    pw = float("nan")
+                self.samples.append((time.perf_counter(), sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def mark(self, t0, t1):
+        self.marks.append((t0, t1))
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "samples_under_load": 0, "source": "nvml in-process, 2 ms period"}
+        if not self.ok:
+            out["source"] = "unavailable: " + getattr(self, "err", "?")
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in open(self.path):
-            c = [x.strip() for x in ln.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
+        self._stop.set()
+        self.th.join(timeout=1.0)
+        nv = self.nv
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        load = [s for s in self.samples if any(a <= s[0] <= b for a, b in self.marks)]
+        use = load or self.samples
+        reasons = set()
+        for s in use:
+            for nm, bit in bits.items():
+                if s[3] & bit:
                     reasons.add(nm)
-        try:
-            os.remove(self.path)
-        except OSError:
-            pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        if use:
+            pw = [s[2] for s in use if s[2] == s[2]]
+            out.update(sm_mhz=float(np.median([s[1] for s in use])), sm_max_mhz=self.sm_max, reasons=sorted(reasons),
+                       samples=len(self.samples), samples_under_load=len(load),
+                       power_w_max=float(max(pw)) if pw else None)
         return out
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def run_ours(args):
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    K, W = args.steps, max(args.warmup, 3)
-
-    # CPU baseline first (before CUDA is initialised in this process), rank 0 at N=1 only
-    cpu_base = None
-    if world == 1 and not args.no_cpu_baseline:
-        cores = host_cores()
-        steps = 2400  # ~12 s of CPU work: cores x 64 envs x 2400 steps at ~13k env-steps/s/core
-        total, dt = cpu_rollout(cores, 64, 10, steps)
-        cpu_base = {"value": total / dt, "unit": UNIT, "cores": cores, "kind": "port",
-                    "sample": "%d host threads x 64 oracle envs (oracle/ilrl_oracle.c, fp64) x %d env steps of the "
-                              "same workload (%d env-steps, %.1f s)" % (cores, steps, total, dt)}
-
-    import torch
-    import torch.distributed as dist
+def make_env(wl, rank, world, local_rank):
     import ilrl_b200
     from ilrl_b200.batched_env import BatchedHumanoidEnv
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    wl = WORKLOADS[args.workload]
     hier = wl["mode"] == "hier"
     if wl["total"]:  # strong scaling over a fixed total (cfg 4): contiguous env-id blocks, clip = global id mod 4
         first, n = ilrl_b200.stats.shard_envs(wl["total"], world, rank)
@@ -219,6 +227,19 @@ def run_ours(args):
     env = BatchedHumanoidEnv(n, wl["mode"], clips=wl["clips"], clip_of_env=cid, device=local_rank, seed=1234,
                              auto_reset=True, env_id_base=first)  # same seed, global env ids: sharding-invariant
     env.reset()
+    return env, n, hier
+
+
+def measure_device(wl, K, W, rank, world, local_rank, clocks=None, min_region_s=0.5, max_blocks=200, kernel_events=True):
+    """Device-timed throughput of one workload: W warm-up steps, then R blocks of EXACTLY K steps, each bracketed by a
+    barrier + synchronize on both sides and timed with CUDA events on the launching stream; per block the MAX over
+    ranks; reported: the MEDIAN block (R is chosen so that the blocks together last >= min_region_s: a single block of
+    20 steps is 2 ms).  Returns (result dict, env, pools) - the env is kept for the end-to-end legs."""
+    import torch
+    import torch.distributed as dist
+    import ilrl_b200
+    dev = torch.device("cuda", local_rank)
+    env, n, hier = make_env(wl, rank, world, local_rank)
     # action pool larger than L2 (126 MB), e.g. 512 batches x 4096 x 17 x 4 B = 142 MB, rotated through -> inputs are
     # never L2-resident from the previous use.  (The persistent env state IS on-chip between steps: that is the
     # workload — state never leaves the GPU.)
@@ -229,11 +250,12 @@ def run_ours(args):
     hpool = torch.rand(64, n, 2, device=dev, generator=g) * 2 - 1 if hier else None
     calls = [0]
 
-    def one_step(i):
+    def one_step():
         """one low-level env step of every env; in hier mode the waiting envs first get their heading action
         (the kernel ignores the others), so that every call advances every env by one low-level step"""
+        i = calls[0]
         if hier:
-            env.high_step(hpool[calls[0] % 64])
+            env.high_step(hpool[i % 64])
         calls[0] += 1
         env.step(pool[i % POOL])
 
@@ -242,111 +264,249 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(W):
-        one_step(i)
+    def block(k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k):
+            one_step()
+        e1.record()
+        barrier()
+        if clocks:
+            clocks.mark(t0, time.perf_counter())
+        return e0.elapsed_time(e1)
+
+    for _ in range(W):
+        one_step()
     env.stats()
-    barrier()
-    clocks = ClockSampler(local_rank) if rank == 0 else None
+    est = block(K)  # untimed extra block: sizes R
+    R = int(min(max_blocks, max(3, np.ceil(min_region_s * 1e3 / max(est, 1e-3)))))
+    if world > 1:  # every rank must run the same number of blocks
+        r_t = torch.tensor([R], device=dev)
+        dist.all_reduce(r_t, op=dist.ReduceOp.MAX)
+        R = int(r_t.item())
     l0 = env.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(K):
-        one_step(W + i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = env.launch_count() - l0
+    ms_blocks = torch.tensor([block(K) for _ in range(R)], device=dev, dtype=torch.float64)
+    launches_per_block = (env.launch_count() - l0) // R
     st = env.stats()  # {episodes, sum return, sum length, steps, sum reward, ...}: the only cross-rank exchange
-    t_ms = torch.tensor([ms], device=dev)
     ilrl_b200.stats.allreduce_stats(st)  # NCCL sum of 16 floats over the ranks (no-op at N=1)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
-    clk = clocks.stop() if clocks else None
     n_all = torch.tensor([float(n)], device=dev)
     if world > 1:
+        dist.all_reduce(ms_blocks, op=dist.ReduceOp.MAX)   # per block: the slowest rank
         dist.all_reduce(n_all, op=dist.ReduceOp.SUM)
-    value = float(n_all.item()) * K / (ms * 1e-3)
+    mb = np.sort(ms_blocks.cpu().numpy())
+    ms = float(mb[len(mb) // 2])
+    res = {"n": n, "n_all": float(n_all.item()), "hier": hier, "ms_block": ms, "ms_per_step": ms / K,
+           "value": float(n_all.item()) * K / (ms * 1e-3), "blocks": R, "block_ms_min": float(mb[0]), "block_ms_max": float(mb[-1]),
+           "launches_per_block": int(launches_per_block), "stats": st.cpu().numpy(), "pool_mb": POOL * n * 17 * 4 >> 20}
+    if kernel_events:
+        # time of the step kernel alone, measured ON THE DEVICE inside one more block of exactly K back-to-back steps:
+        # every step kernel stamps %globaltimer at its first CTA's start and its last CTA's end (ilrl_kernel_timing; no
+        # extra launch, no synchronisation), so the sum of the kernel times cannot exceed the block they ran in
+        env.kernel_timing(True)
+        kb = block(K)
+        kms, kcnt = env.kernel_timing(False)
+        res["kernel_ms"] = kms / max(kcnt, 1)
+        res["kernel_launches_timed"] = kcnt
+        res["kernel_block_ms_per_step"] = kb / K
+    return res, env, (pool, hpool, POOL)
 
-    # per-launch kernel time: events around every launch, on the launching stream, in a separate pass
-    KT = min(K, 200)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KT)]
-    torch.cuda.synchronize()
-    for i, (a, b) in enumerate(evs):
-        if hier:
-            env.high_step(hpool[i % 64])
-        a.record()
-        env.step(pool[(W + K + i) % POOL])
-        b.record()
-    torch.cuda.synchronize()
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
 
-    # end-to-end through the C ABI with HOST buffers (H2D actions, kernel, D2H obs/reward/done inside the timing)
-    # pinned host memory on both sides (the contract's e2e definition): DMA endpoints, no staging copies
+def measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks=None, min_region_s=0.5):
+    """The same metric end to end through the C ABI with HOST buffers: every step's actions come from pinned host memory
+    and its observations / rewards / dones land in pinned host memory inside the timed region.
+    (1) `async2`: ilrl_step_host_async / ilrl_wait with the batch cut in two double-buffered parts (the way a rollout
+        worker overlaps its own work with the env): the headline end-to-end number;
+    (2) `sync`: one blocking ilrl_step_host per step (launch + PCIe + synchronise exposed every step)."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    pool, hpool, POOL = pools
     NH = min(64, POOL)
-    host_act = pool[:NH].cpu().pin_memory().numpy()
-    obs_h = torch.zeros(n, 70).pin_memory().numpy(); rew_h = torch.zeros(n).pin_memory().numpy()
+    host_act = [pool[j].cpu().pin_memory().numpy() for j in range(NH)]
+    obs_h = torch.zeros(n, 70).pin_memory().numpy()
+    rew_h = torch.zeros(n).pin_memory().numpy()
     done_h = torch.zeros(n, dtype=torch.uint8).pin_memory().numpy()
-    KE = min(K, 300)
-    def host_step(i):
-        if hier:
-            env.high_step(hpool[i % 64])
-        env.step_host(host_act[i % NH], obs_h, rew_h, done_h)
 
-    for i in range(5):
-        host_step(i)
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(KE):
-        host_step(i)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t_e = torch.tensor([e2e_s], device=dev)
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    out = {}
+    steps = [0]
+    for kind in ("async2", "sync"):
+        if kind == "async2" and hier:
+            continue   # the hierarchical env needs its high-level call between the parts: only the blocking path is timed
+        def run(k):
+            if kind == "sync":
+                for _ in range(k):
+                    i = steps[0]
+                    if hier:
+                        env.high_step(hpool[i % 64])
+                    steps[0] += 1
+                    env.step_host(host_act[i % NH], obs_h, rew_h, done_h)
+            else:
+                # software pipeline over two parts: while part p steps on the GPU, the host consumes the outputs of the
+                # other part and submits its next step
+                i = steps[0]
+                env.step_host_async(0, 2, host_act[i % NH], obs_h, rew_h, done_h)
+                env.step_host_async(1, 2, host_act[i % NH], obs_h, rew_h, done_h)
+                for j in range(1, k):
+                    a = host_act[(i + j) % NH]
+                    env.wait(0)
+                    env.step_host_async(0, 2, a, obs_h, rew_h, done_h)
+                    env.wait(1)
+                    env.step_host_async(1, 2, a, obs_h, rew_h, done_h)
+                env.wait(0)
+                env.wait(1)
+                steps[0] += k
+        run(5)
+        barrier()
+        t0 = time.perf_counter()
+        run(K)
+        torch.cuda.synchronize()
+        est = time.perf_counter() - t0
+        R = int(min(200, max(3, np.ceil(min_region_s / max(est, 1e-6)))))
+        if world > 1:
+            r_t = torch.tensor([R], device=dev)
+            dist.all_reduce(r_t, op=dist.ReduceOp.MAX)
+            R = int(r_t.item())
+        ts = []
+        for _ in range(R):
+            barrier()
+            t0 = time.perf_counter()
+            run(K)
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            ts.append(t1 - t0)
+            if clocks:
+                clocks.mark(t0, t1)
+        t_e = torch.tensor(ts, device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        tb = np.sort(t_e.cpu().numpy())
+        out[kind] = {"s_block": float(tb[len(tb) // 2]), "blocks": R}
+    return out
+
+
+def run_ours(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    K, W = args.steps, max(args.warmup, 3)
+
+    # CPU baseline first (before CUDA is initialised in this process), rank 0 at N=1 only
+    cpu_base = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = host_cores()
+        epc = reference_envs_per_core(cores)
+        steps = max(10, int(12.0 * 2.0e5 / (cores * epc)))  # ~12 s of CPU work at ~13k env-steps/s/core
+        total, dt = cpu_rollout(cores, epc, 5, steps)
+        cpu_base = {"value": total / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                    "sample": "%d host threads x %d oracle envs = %d envs (oracle/ilrl_oracle.c, fp64: a CPU port of the "
+                              "reference path, not PyBullet) x %d env steps of the same workload (%d env-steps, %.1f s)" % (
+                                  cores, epc, cores * epc, steps, total, dt)}
+
+    import torch
+    import torch.distributed as dist
+    import ilrl_b200
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; this framework has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-    e2e_val = float(n_all.item()) * KE / float(t_e.item())
+        dist.init_process_group("nccl", device_id=dev)
+    clocks = ClockSampler(local_rank) if rank == 0 else None
+
+    wl = WORKLOADS[args.workload]
+    res, env, pools = measure_device(wl, K, W, rank, world, local_rank, clocks)
+    n, hier = res["n"], res["hier"]
+    e2e = measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks)
+    env.close()
+    del pools
+    torch.cuda.empty_cache()
+
+    # the other BASELINE configs, short runs in the same process (the contract line stays cfg 2): cfg 3 hierarchical
+    # 16384 envs per GPU, cfg 4 multi-clip 65536 envs sharded over the ranks, cfg 5 on-device rollout collection
+    extra = {}
+    if args.workload == "low4096" and not args.no_extra_configs:
+        for key, name in (("cfg3_hier16384", "hier16384"), ("cfg4_multiclip65536", "multiclip65536")):
+            r2, env2, p2 = measure_device(WORKLOADS[name], K, max(W, 10), rank, world, local_rank, clocks, min_region_s=0.3,
+                                          kernel_events=False)
+            env2.close()
+            del p2
+            torch.cuda.empty_cache()
+            extra[key] = {"workload": WORKLOADS[name]["name"], "value": r2["value"], "unit": UNIT, "ms_per_step": r2["ms_per_step"],
+                          "envs_per_gpu": r2["n"], "steps": K, "blocks": r2["blocks"],
+                          "scaling": "strong" if WORKLOADS[name]["total"] else "weak",
+                          "mean_episode_len": float(r2["stats"][2] / max(r2["stats"][0], 1))}
+        try:
+            extra["cfg5_rollout16384x8"] = rollout_measure(rank, world, local_rank, hier=False, K=max(3, min(K, 50)), W=3)
+        except Exception as e:  # the widened row must never take the contract line down with it
+            extra["cfg5_rollout16384x8"] = {"error": repr(e)}
+    clk = clocks.stop() if clocks else None
 
     if rank == 0:
         peak, which = measured_peak()
+        kern_ms = res["kernel_ms"]
         achieved = BYTES_PER_ENV_STEP * n / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        # DRAM traffic and executed warp-instructions are ncu counters: they cannot be measured inside this process.
+        # For the contract workload they are read from the committed ncu summary of THIS kernel generation
+        # (profiles/step_kernel_traffic.json names the capture); for every other workload they are null.
+        traffic, wipes, prof_src = None, None, None
         tp = os.path.join(ROOT, "profiles", "step_kernel_traffic.json")
-        if os.path.exists(tp):
+        if args.workload == "low4096" and os.path.exists(tp):
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic, wipes, prof_src = tj.get("dram_bytes_per_launch"), tj.get("warp_inst_per_env_step"), tj.get("source")
             except Exception:
-                traffic = None
-        stn = st.cpu().numpy()
+                pass
+        stn = res["stats"]
+        e2e_head = e2e.get("async2") or e2e["sync"]
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong" if wl["total"] else "weak",
+            "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if wl["total"] else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["name"], "envs_per_gpu": n, "clips": wl["clips"], "auto_reset": True,
                        "l2": "action batches rotate through a %d MB pool (> 126 MB L2); the env state is "
-                             "persistent on-device state by design" % (POOL * n * 17 * 4 >> 20),
+                             "persistent on-device state by design" % res["pool_mb"],
+                       "timing": "median of %d blocks of exactly %d steps, each block bracketed by barrier + synchronize and "
+                                 "timed with CUDA events (max over ranks per block)" % (res["blocks"], K),
+                       "blocks": res["blocks"], "block_ms_min": res["block_ms_min"], "block_ms_max": res["block_ms_max"],
                        "episodes": float(stn[0]), "mean_episode_len": float(stn[2] / max(stn[0], 1)),
                        "mean_step_reward": float(stn[4] / max(stn[3], 1))},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": which, "kernel_ms": kern_ms,
+                         "traffic": traffic, "traffic_source": prof_src, "peak_source": which, "kernel_ms": kern_ms,
+                         "kernel_block_ms_per_step": res["kernel_block_ms_per_step"],
+                         "kernel_timing": "%globaltimer stamps written by the step kernel itself (first CTA start, last CTA "
+                                          "end) in a block of the same K back-to-back steps",
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n,
                          "note": "latency/issue-bound path (SURVEY 8d): HBM fraction is reported as the tier asks; "
                                  "see profiles/ for SM issue utilisation",
-                         # informative second view: what actually bounds the kernel.  6018 warp-instructions per
-                         # env-step (smsp__inst_executed.sum / 4096, profiles/r1_v7_step_kernel_ncu.md) against
-                         # 4 issue slots per SM per cycle at the sampled SM clock
-                         "issue": {"achieved_gwarp_inst_s": 6018.0 * n / (kern_ms * 1e-3) * 1e-9,
-                                   "peak_gwarp_inst_s": 148 * 4 * float((clk or {}).get("sm_mhz") or 1965.0) * 1e-3,
-                                   "warp_inst_per_env_step": 6018}},
+                         # informative second view: what actually bounds the kernel (issue slots), from the same capture
+                         "issue": None if wipes is None else {
+                             "achieved_gwarp_inst_s": wipes * n / (kern_ms * 1e-3) * 1e-9,
+                             "peak_gwarp_inst_s": 148 * 4 * float((clk or {}).get("sm_mhz") or 1965.0) * 1e-3,
+                             "warp_inst_per_env_step": wipes}},
             "cpu_baseline": cpu_base,
-            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": n * 17 * 4,
-                    "d2h_bytes_per_step": n * (70 * 4 + 4 + 1), "steps": KE,
-                    "api": "ilrl_step_host (C ABI, pinned + mapped host buffers: actions read and obs/reward/done written in place by the step kernel)"},
-            "gpu_launches": int(launches),
+            "vs_cpu_port": None if not cpu_base else res["value"] / cpu_base["value"],
+            "e2e": {"value": res["n_all"] * K / e2e_head["s_block"], "unit": UNIT, "h2d_bytes_per_step": n * 17 * 4,
+                    "d2h_bytes_per_step": n * (70 * 4 + 4 + 1), "steps": K, "blocks": e2e_head["blocks"],
+                    "api": ("ilrl_step_host_async + ilrl_wait (C ABI): the batch in two double-buffered parts, each on its own "
+                            "stream; pinned + mapped host buffers, actions read and obs/reward/done written in place by the "
+                            "step kernel") if "async2" in e2e else
+                           "ilrl_step_host (C ABI, pinned + mapped host buffers, blocking)",
+                    "sync_value": res["n_all"] * K / e2e["sync"]["s_block"],
+                    "sync_api": "ilrl_step_host: one blocking call per step (launch + PCIe + synchronise exposed every step)"},
+            "gpu_launches": res["launches_per_block"],
             "clocks": clk,
         }
+        if extra:
+            line["configs"] = extra
         EMIT(json.dumps(line))
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -368,25 +528,18 @@ def _quiet_stdout():
 EMIT = print
 
 
-def run_rollout(args, hier=False):
-    """hier=True: the same for the hierarchical env (both policies on device, 5 launches per tick, horizon 10 =
-    rollout_fragment_length of REF train_config.py:257; counts low-level env steps).
-    Extra measurement mode (BASELINE cfg 5): on-device rollout collection, 16384 envs x 8 steps per GPU per
-    iteration (= 1 M env-steps per iteration on 8 GPUs): fused tcgen05 policy / value / sampling kernel -> fused env step,
-    2 launches per step captured in one CUDA graph, + GAE (ilrl_gae).  A "step" is one iteration; value = env-steps/s of the whole job."""
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
+def rollout_measure(rank, world, local_rank, hier, K, W):
+    """On-device rollout collection (BASELINE cfg 5): 16384 envs x 8 steps per GPU per iteration (= 1 M env-steps per
+    iteration on 8 GPUs): fused tcgen05 policy / value / sampling kernel -> fused env step, 2 launches per step captured
+    in one CUDA graph, + GAE (ilrl_gae).  hier=True: the same for the hierarchical env (both policies on device, 5 launches
+    per tick, horizon 10 = rollout_fragment_length of REF train_config.py:257; counts low-level env steps).
+    A "step" is one iteration.  The process group (world > 1) is the caller's."""
     import torch
     import torch.distributed as dist
     import ilrl_b200
     from ilrl_b200 import BatchedHumanoidEnv, GaussianMLPPolicy, HierRolloutCollector, RolloutCollector
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
     n, T = 16384, (10 if hier else 8)
-    K, W = min(args.steps, 200), max(3, min(args.warmup, 20))
     torch.manual_seed(0)
     if hier:
         env = BatchedHumanoidEnv(n, "hier", clips=["motion08_03", "motion09_03"], clip_of_env=np.ones(n, np.int32),
@@ -398,7 +551,6 @@ def run_rollout(args, hier=False):
     for _ in range(W):
         col.collect()
     env.stats()
-    l0 = env.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
@@ -415,24 +567,46 @@ def run_rollout(args, hier=False):
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms = float(t_ms.item())
-    if rank == 0:
-        summ = ilrl_b200.stats.summarize(st)
-        EMIT(json.dumps({
-            "metric": "rollout env-steps/sec (%spolicy + physics + reward + GAE on device)" % ("both policies: " if hier else ""), "value": world * n * T * K / (ms * 1e-3),
-            "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": ("on-device PPO rollout collection, hierarchical env: %d envs x %d low-level steps per GPU per "
-                                    "iteration, selected_motion=1, step_per_level=5, 44-256-256-2 and 70-256-256-17 tanh Gaussian "
-                                    "policies + value nets (fused tcgen05 kernel), gamma 0.99 lambda 0.9" % (n, T)) if hier else
-                                   ("on-device PPO rollout collection: %d envs x %d steps per GPU per iteration, %s, "
-                                    "70-256-256-17 tanh Gaussian policy + value net (fused tcgen05 kernel, bf16 operands / fp32 accumulation), "
-                                    "gamma 0.99 lambda 0.9" % (n, T, CLIP)), "envs_per_gpu": n, "horizon": T,
-                       "episode_len_mean": summ["episode_len_mean"],
-                       "sample_batch_columns": sorted(batch["low"].keys()) if hier else sorted(batch.keys())},
-            # per iteration, replayed from the graph: low: T env steps + (T + 1) policy steps, + 1 GAE launch;
-            # hier: 5 launches per tick + readout and two value calls after the last + 2 GAE launches
-            "gpu_launches": K * ((5 * T + 5) if hier else (2 * T + 2))}))
+    summ = ilrl_b200.stats.summarize(st)
+    out = {"metric": "rollout env-steps/sec (%spolicy + physics + reward + GAE on device)" % ("both policies: " if hier else ""),
+           "value": world * n * T * K / (ms * 1e-3), "unit": UNIT, "steps": K, "warmup": W, "ms_per_step": ms / K,
+           "workload": ("on-device PPO rollout collection, hierarchical env: %d envs x %d low-level steps per GPU per "
+                        "iteration, selected_motion=1, step_per_level=5, 44-256-256-2 and 70-256-256-17 tanh Gaussian "
+                        "policies + value nets (fused tcgen05 kernel), gamma 0.99 lambda 0.9" % (n, T)) if hier else
+                       ("on-device PPO rollout collection: %d envs x %d steps per GPU per iteration, %s, "
+                        "70-256-256-17 tanh Gaussian policy + value net (fused tcgen05 kernel, bf16 operands / fp32 accumulation), "
+                        "gamma 0.99 lambda 0.9" % (n, T, CLIP)),
+           "envs_per_gpu": n, "horizon": T, "episode_len_mean": summ["episode_len_mean"],
+           "sample_batch_columns": sorted(batch["low"].keys()) if hier else sorted(batch.keys()),
+           # per iteration, replayed from the graph: low: T env steps + (T + 1) policy steps, + 1 GAE launch;
+           # hier: 4 launches per tick + readout and two value calls after the last + 2 GAE launches
+           "gpu_launches": K * ((5 * T + 5) if hier else (2 * T + 2))}
     env.close()
+    del col
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_rollout(args, hier=False):
+    """Extra measurement mode (BASELINE cfg 5), see rollout_measure."""
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    r = rollout_measure(rank, world, local_rank, hier, min(args.steps, 200), max(3, min(args.warmup, 20)))
+    if rank == 0:
+        EMIT(json.dumps({
+            "metric": r["metric"], "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": r["steps"], "warmup": r["warmup"],
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": r["workload"], "envs_per_gpu": r["envs_per_gpu"], "horizon": r["horizon"],
+                       "episode_len_mean": r["episode_len_mean"], "sample_batch_columns": r["sample_batch_columns"]},
+            "gpu_launches": r["gpu_launches"]}))
     if world > 1:
         dist.destroy_process_group()
 
@@ -442,10 +616,11 @@ def main():
     EMIT = _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=500)
+    ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the short cfg 3 / 4 / 5 runs of the default line")
     ap.add_argument("--workload", default="low4096", choices=sorted(WORKLOADS) + ["rollout16384x8", "hier_rollout16384x10"],
                     help="low4096 = the contract line (BASELINE cfg 2); the others are extra measurement modes")
     args = ap.parse_args()

@@ -256,5 +256,12 @@ class BatchedHumanoidEnv:
         self._ck(self.L.ilrl_stats(self.h, _ptr(out), self._stream()))
         return out
 
+    def kernel_timing(self, on):
+        """Device-side timing of the step kernels (ilrl_kernel_timing): returns (milliseconds, launches) accumulated
+        since the previous call and switches the stamping on / off."""
+        ms, cnt = C.c_float(0), C.c_int64(0)
+        self._ck(self.L.ilrl_kernel_timing(self.h, int(bool(on)), C.byref(ms), C.byref(cnt)))
+        return float(ms.value), int(cnt.value)
+
     def launch_count(self):
         return int(self.L.ilrl_launch_count(self.h))

@@ -19,6 +19,7 @@
 
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/ilrl.h"
 #include "ilrl_chain.cuh"
@@ -58,6 +59,7 @@ struct StepArgs {
   float* gscr;         // [n][GROWS][RW] overflow scratch for constraint rows beyond the shared-memory budget
   unsigned int* tile_counter;  // [2]: next tile to hand out, CTAs that have left (both zero between launches)
   int ntiles;
+  unsigned long long* ktime;   // null, or {first CTA start, last CTA end} of this launch in %globaltimer ns (ilrl_kernel_timing)
 #ifdef ILRL_PROF
   long long* prof;     // [warps of the launch][PF_WORDS] phase cycles (measurement build only)
 #endif
@@ -99,6 +101,11 @@ __device__ __forceinline__ void store_state(const StepArgs& a, int i, const Phys
   for (int k = 0; k < ILRL_ENV_WORDS; k++) e[k * n] = w.e[k];
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 // shared-memory setup common to the quad kernels: model tables in (layouts that stage them)
 template <class SM>
 __device__ __forceinline__ void quad_smem_init(SM& sm) {
@@ -139,6 +146,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   SM& sm = *reinterpret_cast<SM*>(smraw);
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
+  if (a.ktime && tid == 0) atomicMin(a.ktime, globaltimer_ns());
   quad_smem_init(sm);
   // Persistent CTAs: the grid is at most what is resident at once (SMs x CTAs per SM) and tiles of QE envs are handed
   // out through an atomic counter, so a large batch has no partially filled last wave and no per-tile table copy, and
@@ -378,6 +386,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     a.tile_counter[0] = 0u;
     a.tile_counter[1] = 0u;
   }
+  if (a.ktime && tid == 0) atomicMax(a.ktime + 1, globaltimer_ns());
 }
 
 // ------------------------------------------------------------------------------------------------ K2: reset
@@ -612,6 +621,7 @@ __global__ void stats_fetch_kernel(float* acc, float* out) {
 using namespace ilrl;
 
 constexpr int ILRL_MAX_PARTS = 8;
+constexpr int KT_SLOTS = 8192;   // timed launches between two ilrl_kernel_timing calls
 struct ilrl_env {
   ilrl_config cfg;
   int n;
@@ -646,10 +656,10 @@ struct ilrl_env {
                                  // (chosen at create time from N)
   bool no_zero_copy = false;     // harness only (ilrl_debug_zero_copy): force the explicit-copy host path
   int64_t launches = 0;
-  bool timing = false;
+  bool timing = false;           // ilrl_kernel_timing: the step kernels stamp %globaltimer into ktime[slot]
+  unsigned long long* ktime = nullptr;   // [KT_SLOTS][2] device
+  int kt_used = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  float timed_ms = 0.f;
-  int64_t timed_launches = 0;
   std::string err;
 };
 
@@ -726,13 +736,16 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaFuncSetAttribute(physics_only_kernel<SmemDense4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDense4)));
   {
     // Layout.  The step kernel is persistent: resident CTAs (SMs x CTAs per SM) pull 16-env tiles,
-    // so a step takes x = tiles / resident CTAs "rounds", the last one partly filled.  Measured on B200 (us per round
-    // in steady state): on-chip 94 (2 CTAs per SM), dense 115 (3 per SM), dense4 141 (4 per SM); a partly filled round
-    // costs between the single-wave latency (~80) and the full-round time.  Estimate all three, take the smallest.
-    // Measured (M env-steps/s: on chip / dense / dense4; * = chosen):
-    //    4096: 37.9* / 32.7 / 29.5      6144: 32.1 / 43.5* / 39.6     8192: 41.5 / 37.4 / 50.0*   12288: 43.1 / 49.2* / 45.0
-    //   16384: 44.2 / 49.2 / 56.3*     24576: 45.5 / 53.7 / 58.7*    32768: 49.8 / 56.1 / 60.1*   65536: 50.7 / 60.6 / 65.7*
-    //  131072: 50.6 / 61.7 / 67.0*
+    // so a step takes x = tiles / resident CTAs "rounds", the last one partly filled.  Being latency-bound, a round costs
+    // about the same however full it is; what differs between the layouts is how many envs a round holds (4736 / 7104 /
+    // 9472 on 148 SMs) and how long it takes.  Measured on B200 (profiles/r2_layout_sweep.txt), time of a step ~
+    // floor(x) R + a + b frac(x) for x < 8 and x Rinf beyond (us): on-chip R 59.6 a 65 b 17.5 Rinf 63.5; dense R 78 a 72.5
+    // b 40.9 Rinf 84; dense4 R 88.1 a 81.9 b 37.5 Rinf 99.5.  Estimate all three, take the smallest.
+    // Measured (M env-steps/s: on chip / dense / dense4; * = chosen by the estimate):
+    //    2048: 27.1* / 24.0 / 23.3      4096: 52.6* / 45.8 / 44.1     5120: 40.6 / 53.0* / 51.0    6144: 46.8 / 60.6* / 58.6
+    //    8192: 59.6 / 52.3 / 73.5*     10240: 54.7 / 59.8* / 59.2    12288: 62.4 / 68.1* / 67.1   16384: 64.3 / 67.9 / 83.0*
+    //   20480: 65.8 / 75.0 / 77.5*     24576: 67.0 / 74.1 / 85.9*    32768: 72.1 / 77.1 / 87.3*   65536: 74.3 / 83.0 / 93.7*
+    //  131072: 75.3 / 85.2 / 95.1*
     // ILRL_LAYOUT=small|large|dense4 overrides (measurement aid).
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
@@ -754,13 +767,14 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
       env->layout = (o[0] == 'l' || o[0] == 'L') ? 1 : (o[0] == 'd' || o[0] == 'D') ? 2 : 0;
     } else {
       const float tiles = (float)((n + QE - 1) / QE);
-      const float t_round[3] = {94.f, 115.f, 141.f}, t_wave = 80.f;
+      const float R[3] = {59.6f, 78.f, 88.1f}, A[3] = {65.f, 72.5f, 81.9f}, B[3] = {17.5f, 40.9f, 37.5f},
+                  Rinf[3] = {63.5f, 84.f, 99.5f};
       const int grid[3] = {env->grid_small, env->grid_large, env->grid_dense4};
       float best = 0.f;
       for (int l = 0; l < 3; l++) {
-        const float x = tiles / (float)grid[l], full = floorf(x), frac = x - full;
+        const float x = tiles / (float)grid[l], full = ceilf(x) - 1.f, frac = x - full;   // last round: 0 < frac <= 1
         // (from 8 rounds on the CTAs have drifted apart and the tile queue keeps every SM busy: time ~ x)
-        const float est = x >= 8.f ? x * t_round[l] : full * t_round[l] + (frac > 0.f ? t_wave + (t_round[l] - t_wave) * frac : 0.f);
+        const float est = x >= 8.f ? x * Rinf[l] : full * R[l] + A[l] + B[l] * frac;
         if (l == 0 || est < best) { best = est; env->layout = l; }
       }
     }
@@ -798,6 +812,7 @@ void ilrl_destroy(ilrl_env* env) {
     if (env->part_event[p]) cudaEventDestroy(env->part_event[p]);
   }
   cudaFree(env->clip_ids_dev);
+  cudaFree(env->ktime);
   cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr);
   cudaFree(env->high_obs); cudaFree(env->high_reward); cudaFree(env->high_flags); cudaFree(env->stats); cudaFree(env->tile_counter);
   for (int c = 0; c < MAX_CLIPS; c++) cudaFree(env->clip_mem[c]);
@@ -900,7 +915,7 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   a.prof = env->prof;
 #endif
   memcpy(a.clips, env->clips, sizeof a.clips);
-  if (env->timing) CK(cudaEventRecord(env->ev0, st));
+  a.ktime = (env->timing && env->kt_used < KT_SLOTS) ? env->ktime + 2 * (size_t)env->kt_used++ : nullptr;
   a.ntiles = (count + QE - 1) / QE;
   const int qblk = min(a.ntiles, env->layout == 2 ? env->grid_dense4 : env->layout == 1 ? env->grid_large : env->grid_small);
   if (env->layout == 2) {
@@ -915,14 +930,6 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   }
   env->launches++;
   CK(cudaGetLastError());
-  if (env->timing) {
-    CK(cudaEventRecord(env->ev1, st));
-    CK(cudaEventSynchronize(env->ev1));
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, env->ev0, env->ev1));
-    env->timed_ms += ms;
-    env->timed_launches++;
-  }
   return ILRL_OK;
 }
 
@@ -1179,10 +1186,26 @@ int ilrl_debug_substeps(ilrl_env* env, int32_t n) { if (!env || n < 1) return IL
 int64_t ilrl_launch_count(const ilrl_env* env) { return env ? env->launches : 0; }
 int ilrl_kernel_timing(ilrl_env* env, int32_t on, float* ms_out, int64_t* launches_out) {
   if (!env) return ILRL_ERR_ARG;
-  if (ms_out) *ms_out = env->timed_ms;
-  if (launches_out) *launches_out = env->timed_launches;
-  env->timed_ms = 0.f; env->timed_launches = 0;
+  ON_DEVICE(env);
+  float ms = 0.f;
+  int64_t cnt = 0;
+  if (env->ktime && env->kt_used > 0) {   // durations of the launches stamped since the last call
+    CK(cudaDeviceSynchronize());
+    std::vector<unsigned long long> h(2 * (size_t)env->kt_used);
+    CK(cudaMemcpy(h.data(), env->ktime, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < env->kt_used; k++)
+      if (h[2 * k + 1] >= h[2 * k]) { ms += (float)((double)(h[2 * k + 1] - h[2 * k]) * 1e-6); cnt++; }
+  }
+  if (ms_out) *ms_out = ms;
+  if (launches_out) *launches_out = cnt;
   env->timing = on != 0;
+  env->kt_used = 0;
+  if (env->timing) {
+    if (!env->ktime) CK(cudaMalloc(&env->ktime, sizeof(unsigned long long) * 2 * KT_SLOTS));
+    std::vector<unsigned long long> init(2 * (size_t)KT_SLOTS);
+    for (int k = 0; k < KT_SLOTS; k++) { init[2 * k] = ~0ull; init[2 * k + 1] = 0ull; }
+    CK(cudaMemcpy(env->ktime, init.data(), sizeof(unsigned long long) * init.size(), cudaMemcpyHostToDevice));
+  }
   return ILRL_OK;
 }
 

@@ -177,8 +177,10 @@ int ilrl_policy_step(const void* blob_dev, const float* obs_dev, const float* no
 
 /* How many kernels of this library have been launched through the handle (bench.py "gpu_launches"). */
 int64_t ilrl_launch_count(const ilrl_env* env);
-/* Time of the step kernels only, measured with CUDA events on `stream` around each ilrl_step since the last call:
- * returns accumulated milliseconds and the number of timed launches, then clears both. Enable with on = 1. */
+/* Time of the step kernels only, measured ON THE DEVICE: while enabled (on = 1) every step kernel stamps %globaltimer
+ * when its first CTA starts and when its last CTA ends (two atomics per CTA; no extra launch, no synchronisation, so
+ * the launches still run back to back).  Returns the accumulated kernel milliseconds and the number of timed launches
+ * since the previous call (it synchronises the device to read them; at most 8192 launches are kept), then clears both. */
 int ilrl_kernel_timing(ilrl_env* env, int32_t on, float* ms_out, int64_t* launches_out);
 
 #ifdef __cplusplus

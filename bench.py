@@ -42,6 +42,7 @@ WORKLOADS = {
                            name="multi-clip imitation (02_04, 08_03, 09_03, 13_13; clip = env id mod 4), 65536 envs sharded "
                                 "over the GPUs, random actions, auto-reset"),
 }
+E2E_PARTS = 4   # parts of the pipelined end-to-end leg (measured 2 / 3 / 4 / 8: 42.9 / 44.5 / 44.8 / 45.0 M env-steps/s)
 BYTES_PER_ENV_STEP = 929  # 2 x 288 B state + 68 B action + 280 B obs + 4 B reward + 1 B done
 WORKLOAD = "low-level imitation env, %d batched envs per GPU, %s, random start frames, random actions, auto-reset" % (
     ENVS_PER_GPU, CLIP)
@@ -316,8 +317,9 @@ def measure_device(wl, K, W, rank, world, local_rank, clocks=None, min_region_s=
 def measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks=None, min_region_s=0.5):
     """The same metric end to end through the C ABI with HOST buffers: every step's actions come from pinned host memory
     and its observations / rewards / dones land in pinned host memory inside the timed region.
-    (1) `async2`: ilrl_step_host_async / ilrl_wait with the batch cut in two double-buffered parts (the way a rollout
-        worker overlaps its own work with the env): the headline end-to-end number;
+    (1) `async`: ilrl_step_host_async / ilrl_wait with the batch cut in E2E_PARTS parts, each on its own stream, stepped
+        as a software pipeline (the way a rollout worker overlaps its own work with the env; the host reads the part's
+        results between its wait and its next submit): the headline end-to-end number;
     (2) `sync`: one blocking ilrl_step_host per step (launch + PCIe + synchronise exposed every step)."""
     import torch
     import torch.distributed as dist
@@ -336,8 +338,11 @@ def measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks=None, mi
 
     out = {}
     steps = [0]
-    for kind in ("async2", "sync"):
-        if kind == "async2" and hier:
+    P = E2E_PARTS
+    sl = [env.part_slice(p, P) for p in range(P)]
+    sink = [0.0]
+    for kind in ("async", "sync"):
+        if kind == "async" and hier:
             continue   # the hierarchical env needs its high-level call between the parts: only the blocking path is timed
         def run(k):
             if kind == "sync":
@@ -351,16 +356,16 @@ def measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks=None, mi
                 # software pipeline over two parts: while part p steps on the GPU, the host consumes the outputs of the
                 # other part and submits its next step
                 i = steps[0]
-                env.step_host_async(0, 2, host_act[i % NH], obs_h, rew_h, done_h)
-                env.step_host_async(1, 2, host_act[i % NH], obs_h, rew_h, done_h)
+                for p in range(P):
+                    env.step_host_async(p, P, host_act[i % NH], obs_h, rew_h, done_h)
                 for j in range(1, k):
                     a = host_act[(i + j) % NH]
-                    env.wait(0)
-                    env.step_host_async(0, 2, a, obs_h, rew_h, done_h)
-                    env.wait(1)
-                    env.step_host_async(1, 2, a, obs_h, rew_h, done_h)
-                env.wait(0)
-                env.wait(1)
+                    for p in range(P):
+                        env.wait(p)
+                        sink[0] += rew_h[sl[p].start]            # the part's results are in host memory: read one
+                        env.step_host_async(p, P, a, obs_h, rew_h, done_h)
+                for p in range(P):
+                    env.wait(p)
                 steps[0] += k
         run(5)
         barrier()
@@ -465,7 +470,7 @@ def run_ours(args):
             except Exception:
                 pass
         stn = res["stats"]
-        e2e_head = e2e.get("async2") or e2e["sync"]
+        e2e_head = e2e.get("async") or e2e["sync"]
         line = {
             "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong" if wl["total"] else "weak",
@@ -495,9 +500,9 @@ def run_ours(args):
             "vs_cpu_port": None if not cpu_base else res["value"] / cpu_base["value"],
             "e2e": {"value": res["n_all"] * K / e2e_head["s_block"], "unit": UNIT, "h2d_bytes_per_step": n * 17 * 4,
                     "d2h_bytes_per_step": n * (70 * 4 + 4 + 1), "steps": K, "blocks": e2e_head["blocks"],
-                    "api": ("ilrl_step_host_async + ilrl_wait (C ABI): the batch in two double-buffered parts, each on its own "
+                    "api": ("ilrl_step_host_async + ilrl_wait (C ABI): the batch in %d pipelined parts, each on its own "
                             "stream; pinned + mapped host buffers, actions read and obs/reward/done written in place by the "
-                            "step kernel") if "async2" in e2e else
+                            "step kernel" % E2E_PARTS) if "async" in e2e else
                            "ilrl_step_host (C ABI, pinned + mapped host buffers, blocking)",
                     "sync_value": res["n_all"] * K / e2e["sync"]["s_block"],
                     "sync_api": "ilrl_step_host: one blocking call per step (launch + PCIe + synchronise exposed every step)"},

@@ -76,6 +76,7 @@ class BatchedHumanoidEnv:
             self.high_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._forced = None
         self._host_key = None
+        self._async_key = None
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):
@@ -155,14 +156,21 @@ class BatchedHumanoidEnv:
         if rc != 0:
             self._ck(rc)
 
-    def step_host_async(self, part, nparts, action_np, obs_np, reward_np, done_np, terms_np=None):
+    def step_host_async(self, part, nparts, action_np, obs_np, reward_np, done_np, terms_np=None, wait_first=False):
         """Enqueue one step of part `part` of `nparts` (contiguous blocks of envs, see `part_slice`) on the part's own
         stream and return at once.  The arrays are the FULL [N, ...] pinned buffers (torch `pin_memory()`); the part's
         rows of obs / reward / done are valid after `wait(part)`.  Lets a worker prepare the actions of one part while
-        the other steps (double-buffered rollout)."""
-        ptr = lambda a: None if a is None else a.__array_interface__["data"][0]  # noqa: E731
-        rc = self.L.ilrl_step_host_async(self.h, int(part), int(nparts), ptr(action_np), ptr(obs_np), ptr(reward_np),
-                                         ptr(done_np), ptr(terms_np))
+        the other steps (double-buffered rollout).  wait_first: first wait for the part's previous step (one call
+        instead of `wait` + `step_host_async`; the caller must not need the previous outputs any more... they stay
+        valid until the kernel of the new step overwrites them, i.e. read them BEFORE this call)."""
+        key = (id(obs_np), id(reward_np), id(done_np), id(terms_np))
+        if self._async_key != key:   # output buffers of the loop: pointers extracted once
+            ptr = lambda a: None if a is None else a.__array_interface__["data"][0]  # noqa: E731
+            self._async_out = (ptr(obs_np), ptr(reward_np), ptr(done_np), ptr(terms_np))
+            self._async_refs = (obs_np, reward_np, done_np, terms_np)
+            self._async_key = key
+        fn = self.L.ilrl_wait_step_host_async if wait_first else self.L.ilrl_step_host_async
+        rc = fn(self.h, part, nparts, action_np.__array_interface__["data"][0], *self._async_out)
         if rc != 0:
             self._ck(rc)
 

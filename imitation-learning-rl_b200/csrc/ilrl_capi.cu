@@ -19,6 +19,7 @@
 
 #include <new>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/ilrl.h"
@@ -634,10 +635,10 @@ struct ilrl_env {
   uint8_t* high_flags = nullptr;
   float* stats = nullptr;
   unsigned int* tile_counter = nullptr;   // [1 + ILRL_MAX_PARTS][2]: the whole batch, then one pair per part
-  cudaStream_t part_stream[ILRL_MAX_PARTS] = {nullptr};   // ilrl_step_host_async: one stream + completion event per part
-  cudaEvent_t part_event[ILRL_MAX_PARTS] = {nullptr};
+  cudaStream_t part_stream[ILRL_MAX_PARTS] = {nullptr};   // ilrl_step_host_async: one stream per part
   bool part_busy[ILRL_MAX_PARTS] = {false};
   int32_t* clip_ids_dev = nullptr;        // staging for ilrl_set_clip_ids
+  std::unordered_map<const void*, void*> alias;   // page-locked host buffer -> its device alias (host_alias)
 #ifdef ILRL_PROF
   long long* prof = nullptr;
 #endif
@@ -809,7 +810,6 @@ void ilrl_destroy(ilrl_env* env) {
   cudaDeviceSynchronize();
   for (int p = 0; p < ILRL_MAX_PARTS; p++) {
     if (env->part_stream[p]) cudaStreamDestroy(env->part_stream[p]);
-    if (env->part_event[p]) cudaEventDestroy(env->part_event[p]);
   }
   cudaFree(env->clip_ids_dev);
   cudaFree(env->ktime);
@@ -941,22 +941,28 @@ int ilrl_step_no_physics(ilrl_env* env, const float* action, float* obs, float* 
   return do_step(env, action, obs, reward, done, terms, (cudaStream_t)stream, 1);
 }
 
-// device aliases of page-locked, mapped host buffers (false if any of them is not mappable)
-static bool map_host_buffers(const float* action_h, float* obs_h, float* reward_h, uint8_t* done_h, float* terms_h,
+// device alias of a page-locked, mapped host buffer (null if it is pageable / not mappable).  The aliases are cached
+// per handle (a rollout loop presents the same few buffers again and again; the two runtime queries cost ~2 us per
+// buffer, i.e. more than the launch itself): a buffer must stay page-locked for as long as it is used with the handle.
+static void* host_alias(ilrl_env* env, const void* p) {
+  auto it = env->alias.find(p);
+  if (it != env->alias.end()) return it->second;
+  void* d = nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess || at.type != cudaMemoryTypeHost ||
+      cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;   // (not cached: the caller may pin the buffer later)
+  }
+  if (env->alias.size() > 4096) env->alias.clear();
+  env->alias[p] = d;
+  return d;
+}
+static bool map_host_buffers(ilrl_env* env, const float* action_h, float* obs_h, float* reward_h, uint8_t* done_h, float* terms_h,
                              void** da, void** dobs, void** dr, void** dd, void** dt) {
-  auto pinned = [](const void* p) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
-  };
-  if (!(pinned(action_h) && pinned(obs_h) && pinned(reward_h) && pinned(done_h) && (!terms_h || pinned(terms_h)))) return false;
   *dt = nullptr;
-  const bool ok = cudaHostGetDevicePointer(da, const_cast<float*>(action_h), 0) == cudaSuccess &&
-                  cudaHostGetDevicePointer(dobs, obs_h, 0) == cudaSuccess && cudaHostGetDevicePointer(dr, reward_h, 0) == cudaSuccess &&
-                  cudaHostGetDevicePointer(dd, done_h, 0) == cudaSuccess &&
-                  (!terms_h || cudaHostGetDevicePointer(dt, terms_h, 0) == cudaSuccess);
-  if (!ok) cudaGetLastError();
-  return ok;
+  return (*da = host_alias(env, action_h)) && (*dobs = host_alias(env, obs_h)) && (*dr = host_alias(env, reward_h)) &&
+         (*dd = host_alias(env, done_h)) && (!terms_h || (*dt = host_alias(env, terms_h)));
 }
 
 int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* reward_h, uint8_t* done_h, float* terms_h,
@@ -971,7 +977,7 @@ int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* re
     // page-locked buffers through their device mappings.  One launch + one synchronise; the output writes of CTAs
     // that finish early overlap the tail of the kernel instead of waiting for a separate D2H copy.
     void *da, *dobs, *dr, *dd, *dt;
-    if (map_host_buffers(action_h, obs_h, reward_h, done_h, terms_h, &da, &dobs, &dr, &dd, &dt)) {
+    if (map_host_buffers(env, action_h, obs_h, reward_h, done_h, terms_h, &da, &dobs, &dr, &dd, &dt)) {
       int r = do_step(env, (const float*)da, (float*)dobs, (float*)dr, (uint8_t*)dd, (float*)dt, st, 0);
       if (r) return r;
       CK(cudaStreamSynchronize(st));
@@ -1016,6 +1022,16 @@ int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* re
   return ILRL_OK;
 }
 
+// (A completion word in mapped host memory, set by the last CTA after a system-scope fence and polled by the host, was
+// measured against the driver's stream synchronisation: no faster - 94 against 91 us per step - and it costs every CTA
+// a fence and an atomic.  Not kept.)
+static int wait_part(ilrl_env* env, int part) {
+  ON_DEVICE(env);
+  CK(cudaStreamSynchronize(env->part_stream[part]));
+  env->part_busy[part] = false;
+  return ILRL_OK;
+}
+
 // envs of part p of nparts: contiguous blocks of ceil(N / nparts) rounded up to whole 16-env tiles
 static void part_range(const ilrl_env* env, int part, int nparts, int* first, int* count) {
   int per = (env->n + nparts - 1) / nparts;
@@ -1024,42 +1040,55 @@ static void part_range(const ilrl_env* env, int part, int nparts, int* first, in
   *count = min(per, env->n - *first);
 }
 
-int ilrl_step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const float* action_h, float* obs_h, float* reward_h,
-                         uint8_t* done_h, float* terms_h) {
+static int step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const float* action_h, float* obs_h, float* reward_h,
+                           uint8_t* done_h, float* terms_h, bool wait_first) {
   if (!env) return ILRL_ERR_ARG;
   if (nparts < 1 || nparts > ILRL_MAX_PARTS || part < 0 || part >= nparts)
     return fail(env, ILRL_ERR_ARG, "ilrl_step_host_async: part / nparts out of range (nparts <= 8)");
   if (!action_h || !obs_h || !reward_h || !done_h) return fail(env, ILRL_ERR_ARG, "ilrl_step_host_async: null buffer");
-  if (env->part_busy[part]) return fail(env, ILRL_ERR_STATE, "ilrl_step_host_async: part is still in flight (ilrl_wait first)");
   ON_DEVICE(env);
+  if (env->part_busy[part]) {
+    if (!wait_first) return fail(env, ILRL_ERR_STATE, "ilrl_step_host_async: part is still in flight (ilrl_wait first)");
+    if (int r = wait_part(env, part)) return r;
+  }
   void *da, *dobs, *dr, *dd, *dt;
-  if (!map_host_buffers(action_h, obs_h, reward_h, done_h, terms_h, &da, &dobs, &dr, &dd, &dt))
+  if (!map_host_buffers(env, action_h, obs_h, reward_h, done_h, terms_h, &da, &dobs, &dr, &dd, &dt))
     return fail(env, ILRL_ERR_ARG, "ilrl_step_host_async: buffers must be page-locked and mapped (cudaHostAlloc / "
                                    "cudaHostRegister / torch pin_memory)");
-  if (!env->part_stream[part]) {
-    CK(cudaStreamCreateWithFlags(&env->part_stream[part], cudaStreamNonBlocking));
-    CK(cudaEventCreateWithFlags(&env->part_event[part], cudaEventDisableTiming));
-  }
+  if (!env->part_stream[part]) CK(cudaStreamCreateWithFlags(&env->part_stream[part], cudaStreamNonBlocking));
   int first, count;
   part_range(env, part, nparts, &first, &count);
+  if (getenv("ILRL_ASYNC_NO_PCIE")) {   // measurement aid (tools/e2e_parts.py): same pipeline, kernel I/O in device memory
+    if (!env->d_action) {
+      const size_t n = env->n;
+      CK(cudaMalloc(&env->d_action, sizeof(float) * 17 * n)); CK(cudaMalloc(&env->d_obs, sizeof(float) * 70 * n));
+      CK(cudaMalloc(&env->d_reward, sizeof(float) * n)); CK(cudaMalloc(&env->d_terms, sizeof(float) * ILRL_TERM_WORDS * n));
+      CK(cudaMalloc(&env->d_done, n)); CK(cudaMemset(env->d_action, 0, sizeof(float) * 17 * n));
+    }
+    da = env->d_action; dobs = env->d_obs; dr = env->d_reward; dd = env->d_done; dt = terms_h ? env->d_terms : nullptr;
+  }
   if (count > 0) {
     int r = do_step(env, (const float*)da, (float*)dobs, (float*)dr, (uint8_t*)dd, (float*)dt, env->part_stream[part], 0,
                     first, count, part);
     if (r) return r;
   }
-  CK(cudaEventRecord(env->part_event[part], env->part_stream[part]));
   env->part_busy[part] = true;
   return ILRL_OK;
+}
+int ilrl_step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const float* action_h, float* obs_h, float* reward_h,
+                         uint8_t* done_h, float* terms_h) {
+  return step_host_async(env, part, nparts, action_h, obs_h, reward_h, done_h, terms_h, false);
+}
+int ilrl_wait_step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const float* action_h, float* obs_h,
+                              float* reward_h, uint8_t* done_h, float* terms_h) {
+  return step_host_async(env, part, nparts, action_h, obs_h, reward_h, done_h, terms_h, true);
 }
 
 int ilrl_wait(ilrl_env* env, int32_t part) {
   if (!env) return ILRL_ERR_ARG;
   if (part < 0 || part >= ILRL_MAX_PARTS) return fail(env, ILRL_ERR_ARG, "ilrl_wait: part out of range");
   if (!env->part_busy[part]) return ILRL_OK;
-  ON_DEVICE(env);
-  CK(cudaEventSynchronize(env->part_event[part]));
-  env->part_busy[part] = false;
-  return ILRL_OK;
+  return wait_part(env, part);
 }
 
 int ilrl_set_config(ilrl_env* env, int32_t max_timestep, int32_t step_per_level, int32_t skip_frame) {

@@ -102,6 +102,11 @@ int ilrl_step_host(ilrl_env* env, const float* action_host, float* obs_host, flo
 int ilrl_step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const float* action_host, float* obs_host,
                          float* reward_host, uint8_t* done_host, float* terms_host);
 int ilrl_wait(ilrl_env* env, int32_t part);
+/* ilrl_wait(part) followed by ilrl_step_host_async(part, ...) in one call (the steady state of a double-buffered loop:
+ * the caller has already consumed the part's previous outputs when it presents the next actions... if it has not, it
+ * calls ilrl_wait itself).  Saves one boundary crossing per part and step. */
+int ilrl_wait_step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const float* action_host, float* obs_host,
+                              float* reward_host, uint8_t* done_host, float* terms_host);
 
 /* The reference's drivers assign these attributes on a live env (REF env_vis_hier.py:52 `env.max_timestep = 100000`;
  * hier_env_2.py:58-63 uses step_per_level 20 and skipFrame 5): change them on the handle.  A non-positive argument

@@ -77,6 +77,7 @@ class BatchedHumanoidEnv:
         self._forced = None
         self._host_key = None
         self._async_key = None
+        self._pull_buf = None
 
     # ------------------------------------------------------------------ plumbing
     def _ck(self, rc):
@@ -185,6 +186,31 @@ class BatchedHumanoidEnv:
         per = -(-per // 16) * 16
         first = min(part * per, self.num_envs)
         return slice(first, min(first + per, self.num_envs))
+
+    # packed row of ilrl_step_pull / ilrl_pull (include/ilrl.h)
+    PULL_WORDS = 205
+    PULL_OBS, PULL_REWARD, PULL_DONE, PULL_TERMS, PULL_ENVF, PULL_PHYS = slice(0, 70), 70, 71, slice(72, 84), slice(84, 112), slice(112, 159)
+    PULL_HIGH_OBS, PULL_HIGH_REWARD, PULL_HIGH_FLAGS = slice(159, 203), 203, 204
+
+    def step_pull(self, action_np, forced_target_deg=None):
+        """One blocking step from host actions [N,17] returning the packed mirror rows [N,205] (numpy, owned by this
+        object): obs | reward | done | terms | envf | phys | high obs | high reward | high flags - one transfer."""
+        if self._pull_buf is None:
+            self._pull_buf = np.zeros((self.num_envs, self.PULL_WORDS), np.float32)
+        a = np.ascontiguousarray(action_np, dtype=np.float32).reshape(self.num_envs, ACT_LOW)
+        rc = self.L.ilrl_step_pull(self.h, a.ctypes.data, INT32_MIN if forced_target_deg is None else int(forced_target_deg),
+                                   self._pull_buf.ctypes.data, self._stream())
+        if rc != 0:
+            self._ck(rc)
+        return self._pull_buf
+
+    def pull(self, obs=None):
+        """The packed mirror rows without stepping (after a reset / high-level step).  obs: device tensor [N,70] to take
+        the observation columns from (default: the observation of the last step_pull)."""
+        if self._pull_buf is None:
+            self._pull_buf = np.zeros((self.num_envs, self.PULL_WORDS), np.float32)
+        self._ck(self.L.ilrl_pull(self.h, _ptr(obs), self._pull_buf.ctypes.data, self._stream()))
+        return self._pull_buf
 
     def set_config(self, max_timestep=0, step_per_level=0, skip_frame=0):
         """Change `max_timestep` / `step_per_level` / `skipFrame` of the live handle (0 = keep)."""

@@ -56,6 +56,7 @@ struct StepArgs {
   float* high_reward;  // [n]
   uint8_t* high_flags; // [n]
   const int32_t* forced_deg;  // [n] or null
+  int forced_scalar;          // INT_MIN, or the heading every env uses at its next target re-sampling (ilrl_step_pull)
   float* stats;        // [16] or null
   float* gscr;         // [n][GROWS][RW] overflow scratch for constraint rows beyond the shared-memory budget
   unsigned int* tile_counter;  // [2]: next tile to hand out, CTAs that have left (both zero between launches)
@@ -268,6 +269,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     uint32_t ctr = a.rng[i];
     int deg;
     if (a.forced_deg && a.forced_deg[i] != INT_MIN) deg = a.forced_deg[i];
+    else if (a.forced_scalar != INT_MIN) deg = a.forced_scalar;
     else {
       // the draw is consumed (counter advanced) only when the target actually switches
       uint32_t c2 = ctr;
@@ -601,6 +603,31 @@ __global__ void gae_decisions_kernel(const float* __restrict__ rew, const uint8_
     if (f & 2) { tau = t; a_tau = ok ? a : 0.f; }
   }
 }
+// everything a reference-shaped env object mirrors after a call, one packed row per env (ILRL_PULL_* layout of ilrl.h):
+// obs 70 | reward | done | terms 12 | envf 28 | phys 47 | high obs 44 | high reward | high flags
+struct PullArgs {
+  int n;
+  const float *obs, *reward, *terms, *phys, *envf, *high_obs, *high_reward;
+  const uint8_t *done, *high_flags;
+  float* out;
+};
+__global__ void pull_kernel(const PullArgs a) {
+  const int i = blockIdx.x;
+  float* o = a.out + (size_t)i * ILRL_PULL_WORDS;
+  for (int t = threadIdx.x; t < ILRL_PULL_WORDS; t += blockDim.x) {
+    float v;
+    if (t < 70) v = a.obs[(size_t)i * 70 + t];
+    else if (t == 70) v = a.reward[i];
+    else if (t == 71) v = (float)a.done[i];
+    else if (t < 84) v = a.terms[(size_t)i * ILRL_TERM_WORDS + (t - 72)];
+    else if (t < 112) v = a.envf[(size_t)(t - 84) * a.n + i];
+    else if (t < 159) v = a.phys[(size_t)(t - 112) * a.n + i];
+    else if (t < 203) v = a.high_obs[(size_t)i * 44 + (t - 159)];
+    else if (t == 203) v = a.high_reward[i];
+    else v = (float)a.high_flags[i];
+    o[t] = v;
+  }
+}
 // the high-level agent's outputs kept in the handle -> caller buffers (any of them may be null): one launch
 __global__ void high_readout_kernel(int n, const float* __restrict__ obs, const float* __restrict__ rew,
                                     const uint8_t* __restrict__ flags, float* obs_out, float* rew_out, uint8_t* flags_out) {
@@ -652,6 +679,7 @@ struct ilrl_env {
   uint8_t* h_done = nullptr;
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_terms = nullptr;
   uint8_t* d_done = nullptr;
+  float *h_pull = nullptr, *h_pull_dev = nullptr;   // mapped staging of ilrl_step_pull / ilrl_pull (+ its action tail)
   int substeps = ILRL_SUBSTEPS;  // harness only (ilrl_debug_substeps)
   int layout = 0;                // shared-memory layout of the step kernel: 0 LayoutSmall, 1 LayoutLarge, 2 LayoutDense4
                                  // (chosen at create time from N)
@@ -812,6 +840,7 @@ void ilrl_destroy(ilrl_env* env) {
     if (env->part_stream[p]) cudaStreamDestroy(env->part_stream[p]);
   }
   cudaFree(env->clip_ids_dev);
+  cudaFreeHost(env->h_pull);
   cudaFree(env->ktime);
   cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr);
   cudaFree(env->high_obs); cudaFree(env->high_reward); cudaFree(env->high_flags); cudaFree(env->stats); cudaFree(env->tile_counter);
@@ -896,7 +925,7 @@ int ilrl_reset(ilrl_env* env, const uint8_t* mask, const int32_t* start_frame, c
 
 // part < 0: the whole batch; otherwise envs [first, first + count) on the part's own tile counters
 static int do_step(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms,
-                   cudaStream_t st, int skip_physics, int first = 0, int count = -1, int part = -1) {
+                   cudaStream_t st, int skip_physics, int first = 0, int count = -1, int part = -1, int forced_scalar = INT_MIN) {
   if (!env) return ILRL_ERR_ARG;
   if (!action || !obs || !reward || !done) return fail(env, ILRL_ERR_ARG, "ilrl_step: null buffer");
   if (int r = check_ready(env)) return r;
@@ -909,7 +938,7 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
   a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.terms = terms;
   a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
-  a.forced_deg = env->forced_deg; a.stats = env->stats; a.gscr = env->gscr;
+  a.forced_deg = env->forced_deg; a.forced_scalar = forced_scalar; a.stats = env->stats; a.gscr = env->gscr;
   a.tile_counter = env->tile_counter + 2 * (part + 1);
 #ifdef ILRL_PROF
   a.prof = env->prof;
@@ -965,6 +994,7 @@ static bool map_host_buffers(ilrl_env* env, const float* action_h, float* obs_h,
          (*dd = host_alias(env, done_h)) && (!terms_h || (*dt = host_alias(env, terms_h)));
 }
 
+static int ensure_io_buffers(ilrl_env* env);
 int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* reward_h, uint8_t* done_h, float* terms_h,
                    void* stream) {
   if (!env) return ILRL_ERR_ARG;
@@ -984,18 +1014,13 @@ int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* re
       return ILRL_OK;
     }
   }
-  if (!env->d_action) {  // staging buffers: pinned host mirrors + device I/O, allocated on first use
+  if (!env->h_action) {  // staging buffers: pinned host mirrors + device I/O, allocated on first use
     CK(cudaMallocHost(&env->h_action, sizeof(float) * 17 * n));
     CK(cudaMallocHost(&env->h_obs, sizeof(float) * 70 * n));
     CK(cudaMallocHost(&env->h_reward, sizeof(float) * n));
     CK(cudaMallocHost(&env->h_terms, sizeof(float) * ILRL_TERM_WORDS * n));
     CK(cudaMallocHost(&env->h_done, n));
-    CK(cudaMalloc(&env->d_action, sizeof(float) * 17 * n));
-    CK(cudaMalloc(&env->d_obs, sizeof(float) * 70 * n));
-    CK(cudaMalloc(&env->d_reward, sizeof(float) * n));
-    CK(cudaMalloc(&env->d_terms, sizeof(float) * ILRL_TERM_WORDS * n));
-    CK(cudaMalloc(&env->d_done, n));
-    CK(cudaMemset(env->d_obs, 0, sizeof(float) * 70 * n));
+    if (int r = ensure_io_buffers(env)) return r;
   }
   // Page-locked caller buffers are DMA targets as they are; pageable ones go through the handle's pinned mirrors.
   auto pinned = [](const void* p) {
@@ -1058,15 +1083,6 @@ static int step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const fl
   if (!env->part_stream[part]) CK(cudaStreamCreateWithFlags(&env->part_stream[part], cudaStreamNonBlocking));
   int first, count;
   part_range(env, part, nparts, &first, &count);
-  if (getenv("ILRL_ASYNC_NO_PCIE")) {   // measurement aid (tools/e2e_parts.py): same pipeline, kernel I/O in device memory
-    if (!env->d_action) {
-      const size_t n = env->n;
-      CK(cudaMalloc(&env->d_action, sizeof(float) * 17 * n)); CK(cudaMalloc(&env->d_obs, sizeof(float) * 70 * n));
-      CK(cudaMalloc(&env->d_reward, sizeof(float) * n)); CK(cudaMalloc(&env->d_terms, sizeof(float) * ILRL_TERM_WORDS * n));
-      CK(cudaMalloc(&env->d_done, n)); CK(cudaMemset(env->d_action, 0, sizeof(float) * 17 * n));
-    }
-    da = env->d_action; dobs = env->d_obs; dr = env->d_reward; dd = env->d_done; dt = terms_h ? env->d_terms : nullptr;
-  }
   if (count > 0) {
     int r = do_step(env, (const float*)da, (float*)dobs, (float*)dr, (uint8_t*)dd, (float*)dt, env->part_stream[part], 0,
                     first, count, part);
@@ -1089,6 +1105,59 @@ int ilrl_wait(ilrl_env* env, int32_t part) {
   if (part < 0 || part >= ILRL_MAX_PARTS) return fail(env, ILRL_ERR_ARG, "ilrl_wait: part out of range");
   if (!env->part_busy[part]) return ILRL_OK;
   return wait_part(env, part);
+}
+
+static int ensure_io_buffers(ilrl_env* env) {
+  const size_t n = env->n;
+  if (!env->d_action) {
+    CK(cudaMalloc(&env->d_action, sizeof(float) * 17 * n));
+    CK(cudaMalloc(&env->d_obs, sizeof(float) * 70 * n));
+    CK(cudaMalloc(&env->d_reward, sizeof(float) * n));
+    CK(cudaMalloc(&env->d_terms, sizeof(float) * ILRL_TERM_WORDS * n));
+    CK(cudaMalloc(&env->d_done, n));
+    CK(cudaMemset(env->d_obs, 0, sizeof(float) * 70 * n));
+    CK(cudaMemset(env->d_reward, 0, sizeof(float) * n));
+    CK(cudaMemset(env->d_terms, 0, sizeof(float) * ILRL_TERM_WORDS * n));
+    CK(cudaMemset(env->d_done, 0, n));
+  }
+  if (!env->h_pull) {
+    CK(cudaHostAlloc(&env->h_pull, sizeof(float) * ILRL_PULL_WORDS * n + sizeof(float) * 17 * n, cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&env->h_pull_dev, env->h_pull, 0));
+  }
+  return ILRL_OK;
+}
+static int do_pull(ilrl_env* env, float* pull_host, const float* obs_dev, cudaStream_t st) {
+  PullArgs a;
+  a.n = env->n; a.obs = obs_dev ? obs_dev : env->d_obs; a.reward = env->d_reward; a.terms = env->d_terms; a.done = env->d_done;
+  a.phys = env->phys; a.envf = env->envf; a.high_obs = env->high_obs; a.high_reward = env->high_reward;
+  a.high_flags = env->high_flags; a.out = env->h_pull_dev;
+  pull_kernel<<<env->n, 64, 0, st>>>(a);
+  env->launches++;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(st));
+  memcpy(pull_host, env->h_pull, sizeof(float) * ILRL_PULL_WORDS * env->n);
+  return ILRL_OK;
+}
+int ilrl_step_pull(ilrl_env* env, const float* action_host, int32_t forced_target_deg, float* pull_host, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!action_host || !pull_host) return fail(env, ILRL_ERR_ARG, "ilrl_step_pull: null buffer");
+  ON_DEVICE(env);
+  if (int r = ensure_io_buffers(env)) return r;
+  cudaStream_t st = (cudaStream_t)stream;
+  // the actions travel through the tail of the mapped staging block: the step kernel reads them in place
+  float* ah = env->h_pull + (size_t)ILRL_PULL_WORDS * env->n;
+  memcpy(ah, action_host, sizeof(float) * 17 * env->n);
+  int r = do_step(env, env->h_pull_dev + (size_t)ILRL_PULL_WORDS * env->n, env->d_obs, env->d_reward, env->d_done, env->d_terms,
+                  st, 0, 0, -1, -1, forced_target_deg);
+  if (r) return r;
+  return do_pull(env, pull_host, nullptr, st);
+}
+int ilrl_pull(ilrl_env* env, const float* obs_dev, float* pull_host, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!pull_host) return fail(env, ILRL_ERR_ARG, "ilrl_pull: null buffer");
+  ON_DEVICE(env);
+  if (int r = ensure_io_buffers(env)) return r;
+  return do_pull(env, pull_host, obs_dev, (cudaStream_t)stream);
 }
 
 int ilrl_set_config(ilrl_env* env, int32_t max_timestep, int32_t step_per_level, int32_t skip_frame) {

@@ -87,7 +87,7 @@ class _SingleEnv(object):
                                        seed=0 if seed is None else int(seed), auto_reset=False)
         self.rng = np.random.default_rng(seed)
         self.cur_timestep = 0
-        self.max_timestep = 3000
+        self._max_timestep, self._skip_frame = 3000, 2
         self.frame = 0
         self.joint_map = dict(JOINT_MAP)
         self.joint_weight, self.joint_vel_weight = dict(JOINT_WEIGHT), dict(JOINT_VEL_WEIGHT)
@@ -96,12 +96,10 @@ class _SingleEnv(object):
         self.end_point_map, self.end_point_weight = dict(END_POINT_MAP), dict(END_POINT_WEIGHT)
         self.end_point_weight_sum = sum(self.end_point_weight.values())
         self.target = np.array([1.0, 0.0, 0.0])
-        self.targetLen = 5
         self.highLevelDegTarget = 0.0
         self.predefinedTarget = np.array([[]])
         self.predefinedTargetIndex = 0
         self.usePredefinedTarget = False
-        self.skipFrame = 2
         self.starting_ep_pos = np.zeros(3)
         self.starting_robot_pos = np.zeros(3)
         self.robot_pos = np.zeros(3)
@@ -124,6 +122,30 @@ class _SingleEnv(object):
 
     def close(self):
         self._env.close()
+
+    # Attributes the reference's drivers ASSIGN on a live env (REF env_vis_hier.py:52 `env.max_timestep = 100000`): they
+    # are kernel parameters here, so assignment is forwarded to the handle instead of staying a dead Python field.
+    max_timestep = property(lambda self: self._max_timestep)
+    skipFrame = property(lambda self: self._skip_frame)
+
+    @max_timestep.setter
+    def max_timestep(self, v):
+        self._max_timestep = int(v)
+        self._env.set_config(max_timestep=int(v))
+
+    @skipFrame.setter
+    def skipFrame(self, v):
+        self._skip_frame = int(v)
+        self._env.set_config(skip_frame=int(v))
+
+    @property
+    def targetLen(self):
+        return 5
+
+    @targetLen.setter
+    def targetLen(self, v):
+        if float(v) != 5.0:   # REF low_level_env.py:155 / hier_env.py:160: a compile-time constant of the kernels
+            raise NotImplementedError("targetLen is fixed at 5 m in the B200 path (ILRL_TARGET_LEN)")
 
     # the four reference tables as pandas DataFrames with the CSV's own column names (REF low_level_env.py:58-71 reads
     # them with pd.read_csv; drivers index them with .iloc[frame][column]).  Built on first use.
@@ -158,11 +180,13 @@ class _SingleEnv(object):
         self.rng = np.random.default_rng(seed)
         return [seed]
 
-    # ---- state mirror: pull the env words of the single env and expose them under the reference's names
-    def _pull(self, terms=None):
-        phys, envf = self._env.get_state()
-        e = envf[0].cpu().numpy().astype(np.float64)
-        self._phys = phys[0].cpu().numpy().astype(np.float64)
+    # ---- state mirror: ONE packed row per call (ilrl_step_pull / ilrl_pull) holds everything the reference keeps as
+    # Python attributes; it is exposed under the reference's names
+    def _mirror(self, row, with_terms=False):
+        E = BatchedHumanoidEnv
+        e = row[E.PULL_ENVF].astype(np.float64)
+        self._row = row
+        self._phys = row[E.PULL_PHYS].astype(np.float64)
         self._envf = e
         self.frame = int(e[B.E_FRAME])
         self.cur_timestep = int(e[B.E_T])
@@ -173,11 +197,14 @@ class _SingleEnv(object):
         self.highLevelDegTarget = float(e[B.E_HLDEG])
         self.lowTargetScore = float(e[B.E_LOW_TARGET_SCORE])
         self.highTargetScore = float(e[B.E_HIGH_TARGET_SCORE])
-        if terms is not None:
-            t = terms[0].cpu().numpy().astype(np.float64)
+        if with_terms:
+            t = row[E.PULL_TERMS].astype(np.float64)
             for k, i in _REWARD_ATTRS.items():
                 setattr(self, k, float(t[i]))
         return e
+
+    def _pull(self, obs=None):
+        return self._mirror(self._env.pull(obs)[0])
 
     def _push_env_words(self, **words):
         e = self._envf.astype(np.float32).copy()
@@ -234,6 +261,7 @@ class _SingleEnv(object):
         a = np.zeros((1, 17), np.float32) if action is None else np.asarray(action, np.float32).reshape(1, 17)
         _, _, _, terms = self._env.step(a, physics=False)
         t = terms[0].cpu().numpy().astype(np.float64)
+        self._env.set_forced_target_deg(None)
         self._env.set_state(phys, envf)
         return t
 
@@ -312,11 +340,11 @@ class LowLevelHumanoidEnv(_SingleEnv, _GymEnv):
                                       "the B200 path; every reference caller passes True")
         xy = self._first_target_xy()
         deg = None if xy is not None else np.array([int(self.rng.integers(-180, 180))], np.int32)
-        obs = self._env.reset(start_frame=np.array([startFrame], np.int32), target_deg=deg,
-                              reset_yaw_deg=np.array([resetYaw], np.float32), target_xy=xy)
-        obs = obs[0].cpu().numpy().astype(np.float64)
+        obs_dev = self._env.reset(start_frame=np.array([startFrame], np.int32), target_deg=deg,
+                                  reset_yaw_deg=np.array([resetYaw], np.float32), target_xy=xy)
         self.initReward()
-        self._pull()
+        self._pull(obs_dev)
+        obs = self._row[BatchedHumanoidEnv.PULL_OBS].astype(np.float64)
         if not initVel:
             p = self._phys.astype(np.float32)
             p[7:10] = 0.0
@@ -332,13 +360,13 @@ class LowLevelHumanoidEnv(_SingleEnv, _GymEnv):
         a = np.asarray(action, dtype=np.float32).reshape(17)
         assert np.isfinite(a).all()
         deg, after = self._peek_deg()
-        self._env.set_forced_target_deg(np.array([deg], np.int64))
         old_target = self.target.copy()
-        obs, rew, done, terms = self._env.step(a[None, :])
-        obs = obs[0].cpu().numpy().astype(np.float64)
-        reward = float(rew[0].item())
-        done = bool(done[0].item())
-        self._pull(terms)
+        E = BatchedHumanoidEnv
+        row = self._env.step_pull(a, deg)[0]      # one launch for the step, one for the packing, one transfer
+        obs = row[E.PULL_OBS].astype(np.float64)
+        reward = float(row[E.PULL_REWARD])
+        done = bool(row[E.PULL_DONE])
+        self._mirror(row, with_terms=True)
         self._after_target_logic(old_target, after)
         if debug:  # REF low_level_env.py:467-473: the debug rule ignores the distance test
             done = not (self.aliveReward > 0) or self.cur_timestep >= self.max_timestep
@@ -366,14 +394,21 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
         self.high_level_act_space = Box(low=-1, high=1, shape=[2])
         self.low_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[8 + 17 * 2 + 14 * 2])
         self.low_level_act_space = Box(low=-1, high=1, shape=[17])
-        self.step_per_level = 5
-        self.steps_remaining_at_level = self.step_per_level
+        self._step_per_level = 5
+        self.steps_remaining_at_level = self._step_per_level
         self.num_high_level_steps = 0
         self.max_frame = [load_clip(m)["max_frame"] for m in self.motion_list]
         self._selected_motion = 1
         self.selected_motion_frame = 0
         self.low_level_agent_id = "low_level_agent"
         self._make("hier", self.motion_list, self._selected_motion, device, seed)
+
+    step_per_level = property(lambda self: self._step_per_level)
+
+    @step_per_level.setter
+    def step_per_level(self, v):
+        self._step_per_level = int(v)
+        self._env.set_config(step_per_level=int(v))
 
     @property
     def selected_motion(self):
@@ -387,8 +422,8 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
         self._selected_motion = v
         self._env.set_clip_of_env(np.array([v], np.int32))
 
-    def _pull(self, terms=None):
-        e = _SingleEnv._pull(self, terms)
+    def _mirror(self, row, with_terms=False):
+        e = _SingleEnv._mirror(self, row, with_terms)
         self.selected_motion_frame = self.frame
         self.steps_remaining_at_level = int(e[B.E_STEPS_REMAINING])
         self.cumulative_driftScore = float(e[B.E_CUM_DRIFT])
@@ -409,7 +444,7 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
         deg = None if xy is not None else np.array([int(self.rng.integers(-180, 180))], np.int32)
         hobs = self._env.reset(start_frame=np.array([startFrame], np.int32), target_deg=deg,
                                reset_yaw_deg=np.array([resetYaw], np.float32), target_xy=xy)
-        hobs = hobs[0].cpu().numpy().astype(np.float64)
+        hobs = hobs[0].cpu().numpy().astype(np.float64)   # (the reset writes the first high-level obs to the caller's buffer)
         self.initReward()
         self._pull()
         if not initVel:
@@ -433,9 +468,9 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
     def high_level_step(self, action, debug=False):
         a = np.asarray(action, dtype=np.float32).reshape(2)
         self._set_pending(True)   # the reference applies a high-level action whenever one arrives
-        obs = self._env.high_step(a[None, :])
-        obs = obs[0].cpu().numpy().astype(np.float64)
-        self._pull()
+        obs_dev = self._env.high_step(a[None, :])
+        self._pull(obs_dev)
+        obs = self._row[BatchedHumanoidEnv.PULL_OBS].astype(np.float64)
         self.num_high_level_steps += 1
         return {self.low_level_agent_id: obs}, {self.low_level_agent_id: 0}, {"__all__": False}, {}
 
@@ -444,28 +479,28 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
         assert np.isfinite(a).all()
         self._set_pending(False)  # ... and a low-level action whenever one arrives
         deg, after = self._peek_deg()
-        self._env.set_forced_target_deg(np.array([deg], np.int64))
         old_target = self.target.copy()
-        obs, rew, done, terms = self._env.step(a[None, :])
-        hobs, hrew, hflags = self._env.high_readout()
-        low_obs = obs[0].cpu().numpy().astype(np.float64)
-        flags = int(hflags[0].item())
-        self._pull(terms)
+        E = BatchedHumanoidEnv
+        row = self._env.step_pull(a, deg)[0]
+        low_obs = row[E.PULL_OBS].astype(np.float64)
+        low_rew, high_rew = float(row[E.PULL_REWARD]), float(row[E.PULL_HIGH_REWARD])
+        flags = int(row[E.PULL_HIGH_FLAGS])
+        self._mirror(row, with_terms=True)
         self._after_target_logic(old_target, after)
         ended, high_present = bool(flags & 1), bool(flags & 2)
         o, r, d = {}, {}, {"__all__": False}
         if ended:
             d["__all__"] = True
-            r["high_level_agent"] = float(hrew[0].item())
-            o["high_level_agent"] = hobs[0].cpu().numpy().astype(np.float64)
+            r["high_level_agent"] = high_rew
+            o["high_level_agent"] = row[E.PULL_HIGH_OBS].astype(np.float64)
             o[self.low_level_agent_id] = low_obs
-            r[self.low_level_agent_id] = float(rew[0].item())
+            r[self.low_level_agent_id] = low_rew
         elif high_present:
-            r["high_level_agent"] = float(hrew[0].item())
-            o["high_level_agent"] = hobs[0].cpu().numpy().astype(np.float64)
+            r["high_level_agent"] = high_rew
+            o["high_level_agent"] = row[E.PULL_HIGH_OBS].astype(np.float64)
         else:
             o = {self.low_level_agent_id: low_obs}
-            r = {self.low_level_agent_id: float(rew[0].item())}
+            r = {self.low_level_agent_id: low_rew}
         if debug and ended and self.aliveReward > 0 and self.cur_timestep < self.max_timestep:
             # REF hier_env.py:573-581: the debug rule ignores the distance test
             d["__all__"] = False

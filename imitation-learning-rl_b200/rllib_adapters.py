@@ -46,12 +46,24 @@ class _EnvAttrView(object):
         if name in _REWARD_ATTRS:
             return float(self._o._terms_host[self._i, _REWARD_ATTRS[name]])
         if name == "robot_pos":
-            e = self._o.env.get_state()[1][self._i].cpu().numpy()
-            return np.array([e[B.E_ROBOT_X], e[B.E_ROBOT_Y], 0.0])
+            xy = self._o._robot_xy()[self._i]       # one device->host copy per step for ALL envs, on first use
+            return np.array([xy[0], xy[1], 0.0])
         raise AttributeError(name)
 
 
-class LowLevelVectorEnv(_VectorEnv):
+
+class _RobotPosCache(object):
+    """`robot_pos` of every env, fetched from the handle at most once per step (RewardLogCallback reads it for each
+    env after each step, REF custom_callback.py:43-46: one [N,28] device->host copy instead of N)."""
+
+    def _robot_xy(self):
+        if self._robot_cache is None:
+            envf = self.env.get_state()[1]
+            self._robot_cache = envf[:, [B.E_ROBOT_X, B.E_ROBOT_Y]].cpu().numpy().astype(np.float64)
+        return self._robot_cache
+
+
+class LowLevelVectorEnv(_RobotPosCache, _VectorEnv):
     """N `LowLevelHumanoidEnv`s as one RLlib VectorEnv.  Done envs are re-initialised by ONE masked reset launch
     right after the step; `reset_at(i)` (which RLlib calls for every done env) returns that env's new first obs."""
 
@@ -66,6 +78,7 @@ class LowLevelVectorEnv(_VectorEnv):
         self._rew_host, self._done_host = pin(self.num_envs), pin(self.num_envs, dtype=torch.uint8)
         self._terms_host = pin(self.num_envs, B.TERM_WORDS)
         self._next_obs = np.zeros((self.num_envs, 70), np.float32)
+        self._robot_cache = None
         self._views = [_EnvAttrView(self, i) for i in range(self.num_envs)]
 
     def vector_reset(self):
@@ -80,6 +93,7 @@ class LowLevelVectorEnv(_VectorEnv):
         self._act_host[:] = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, 17)
         assert np.isfinite(self._act_host).all()
         self.env.step_host(self._act_host, self._obs_host, self._rew_host, self._done_host, self._terms_host)
+        self._robot_cache = None
         done_h = self._done_host.astype(bool)
         obs64 = self._obs_host.astype(np.float64)
         if done_h.any():  # one masked reset for every env that finished; their first obs waits for reset_at()
@@ -95,7 +109,7 @@ class LowLevelVectorEnv(_VectorEnv):
         self.env.close()
 
 
-class HierBaseEnv(_BaseEnv):
+class HierBaseEnv(_RobotPosCache, _BaseEnv):
     """N `HierarchicalHumanoidEnv`s as one RLlib BaseEnv (async poll / send_actions protocol, agent ids
     "high_level_agent" / "low_level_agent").  Each env is either waiting for a heading from the high-level agent or
     for torques from the low-level one; both kinds advance in the same call: rows of agents that do not act are NaN
@@ -111,6 +125,7 @@ class HierBaseEnv(_BaseEnv):
         self.low_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[70])
         self.low_level_act_space = Box(low=-1, high=1, shape=[17])
         self._terms_host = np.zeros((self.num_envs, B.TERM_WORDS), np.float32)
+        self._robot_cache = None
         self._views = [_EnvAttrView(self, i) for i in range(self.num_envs)]
         self._pending = None  # what the next poll() returns
         hobs = self.env.reset().cpu().numpy().astype(np.float64)
@@ -137,6 +152,7 @@ class HierBaseEnv(_BaseEnv):
             else:
                 low[i] = a
         dev = self.env.device
+        self._robot_cache = None
         got_high = ~np.isnan(high[:, 0])
         got_low = ~np.isnan(low[:, 0])
         obs, rew, done = {}, {}, {}

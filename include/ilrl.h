@@ -108,6 +108,20 @@ int ilrl_wait(ilrl_env* env, int32_t part);
 int ilrl_wait_step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const float* action_host, float* obs_host,
                               float* reward_host, uint8_t* done_host, float* terms_host);
 
+/* The reference-shaped single-env classes (LowLevelHumanoidEnv / HierarchicalHumanoidEnv, N = 1 views) mirror, after every
+ * call, what the reference keeps as Python attributes: the observation, reward, done, the 12 reward terms, the env words
+ * (frame, target, robot_pos, ...), the physics state and the high-level agent's outputs.  ilrl_step_pull does one
+ * blocking step from HOST actions [N,17] and returns all of it as ONE packed host row per env (one launch for the step,
+ * one for the packing, one synchronise; nothing else crosses the bus):
+ *   [N][ILRL_PULL_WORDS] fp32 = obs 70 | reward | done | terms 12 | envf 28 | phys 47 | high obs 44 | high reward | flags
+ * forced_target_deg: INT32_MIN, or the heading (integer degrees) every env uses if it re-samples its target in this step
+ * (the N = 1 views draw it from the env object's own generator, as the reference does, REF low_level_env.py:240-245).
+ * ilrl_pull packs the same row without stepping (after a reset or a high-level step); obs_dev NULL = the observation
+ * of the last ilrl_step_pull, else a device [N,70] buffer to take the observation columns from. */
+#define ILRL_PULL_WORDS 205
+int ilrl_step_pull(ilrl_env* env, const float* action_host, int32_t forced_target_deg, float* pull_host, void* stream);
+int ilrl_pull(ilrl_env* env, const float* obs_dev, float* pull_host, void* stream);
+
 /* The reference's drivers assign these attributes on a live env (REF env_vis_hier.py:52 `env.max_timestep = 100000`;
  * hier_env_2.py:58-63 uses step_per_level 20 and skipFrame 5): change them on the handle.  A non-positive argument
  * keeps the current value.  Takes effect from the next step / reset. */

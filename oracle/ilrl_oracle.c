@@ -228,6 +228,37 @@ double ilrl_oracle_energy(const double* phys) {
   return e;
 }
 
+/* Model-sensitivity knobs (tools/model_sensitivity.py): the [BULLET] constants that no reference fixture pins can be
+ * varied one at a time in THIS restatement to see what they do to the rollout statistics.  Defaults = ilrl_constants.h
+ * (= what the CUDA product computes).  Not thread-safe: set before any thread steps. */
+typedef struct {
+  double limit_erp, contact_erp, friction, max_coord_vel, link_damp_scale;
+  int solver_iters, limit_rows_always;
+  double joint_damping[NJ], joint_armature[NJ], joint_stiffness[NJ];
+} orc_params;
+static orc_params g_par = {ILRL_LIMIT_ERP, ILRL_CONTACT_ERP, ILRL_FRICTION, ILRL_MAX_COORD_VEL, 1.0, ILRL_SOLVER_ITERS, 0, {0}, {0}, {0}};
+/* p[0..6] = limit_erp, contact_erp, friction, max_coord_vel, link_damp_scale, solver_iters, limit_rows_always;
+ * p[7..7+3*NJ) = joint damping, armature, stiffness (MJCF attributes; Bullet's importer is believed to ignore them).
+ * NULL restores the defaults. */
+void ilrl_oracle_set_params(const double* p) {
+  orc_params d = {ILRL_LIMIT_ERP, ILRL_CONTACT_ERP, ILRL_FRICTION, ILRL_MAX_COORD_VEL, 1.0, ILRL_SOLVER_ITERS, 0, {0}, {0}, {0}};
+  g_par = d;
+  if (!p) return;
+  g_par.limit_erp = p[0]; g_par.contact_erp = p[1]; g_par.friction = p[2]; g_par.max_coord_vel = p[3];
+  g_par.link_damp_scale = p[4]; g_par.solver_iters = (int)p[5]; g_par.limit_rows_always = (int)p[6];
+  for (int j = 0; j < NJ; j++) {
+    g_par.joint_damping[j] = p[7 + j]; g_par.joint_armature[j] = p[7 + NJ + j]; g_par.joint_stiffness[j] = p[7 + 2 * NJ + j];
+  }
+}
+/* Diagnostics (tools/model_sensitivity.py): extreme-event counters over all substeps since the last reset:
+ * [0] substeps, [1] max joint-limit overshoot (rad), [2] substeps with overshoot > 0.5 rad, [3] max |torso v_z change| in one
+ * substep (m/s), [4] substeps with |dv_z| > 2 m/s, [5] max torso height (m) */
+static double g_diag[8];
+void ilrl_oracle_diag(double* out, int reset) {
+  if (out) memcpy(out, g_diag, sizeof g_diag);
+  if (reset) memset(g_diag, 0, sizeof g_diag);
+}
+
 /* Diagnostics (tools/rowstats.py): when set, every substep counts its (violated limits, kept contacts) pair in a
  * [18][9] histogram.  Not thread-safe; single-threaded tools only. */
 static long* g_rowstats = 0;
@@ -270,7 +301,10 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
   double M[NV * NV], rhs[NV];
   mass_matrix(&k, p0, M);
   for (int i = 0; i < 6; i++) rhs[i] = 0;
-  for (int j = 0; j < NJ; j++) rhs[6 + j] = tau[j];
+  for (int j = 0; j < NJ; j++) {   /* (joint damping / stiffness / armature: zero unless the sensitivity knobs are set) */
+    rhs[6 + j] = tau[j] - g_par.joint_damping[j] * qd[j] - g_par.joint_stiffness[j] * q[j];
+    M[(6 + j) * NV + 6 + j] += g_par.joint_armature[j];
+  }
   for (int b = 0; b < NB; b++) {
     double Jw[NV][3], Jv[NV][3];
     int l = body_link[b];
@@ -298,8 +332,8 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
     if (!(flags & 2)) {
       double vn = sqrt(dot3(vb, vb)), wn = sqrt(dot3(wb, wb));
       for (int i = 0; i < 3; i++) {
-        f[i] -= body_mass[b] * vb[i] * (ILRL_DAMP_K1_LIN + ILRL_DAMP_K2_LIN * vn);
-        n[i] -= Iw_w[i] * (ILRL_DAMP_K1_ANG + ILRL_DAMP_K2_ANG * wn);
+        f[i] -= g_par.link_damp_scale * body_mass[b] * vb[i] * (ILRL_DAMP_K1_LIN + ILRL_DAMP_K2_LIN * vn);
+        n[i] -= g_par.link_damp_scale * Iw_w[i] * (ILRL_DAMP_K1_ANG + ILRL_DAMP_K2_ANG * wn);
       }
     }
     for (int c = 0; c < NV; c++) {
@@ -315,10 +349,11 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
   memcpy(L, M, sizeof M);
   chol(L, NV);
   chol_solve(L, NV, rhs, acc);
+  const double vz_before = phys[9];
   for (int c = 0; c < NV; c++) {
     nu[c] += dt * acc[c];
-    if (nu[c] > ILRL_MAX_COORD_VEL) nu[c] = ILRL_MAX_COORD_VEL;
-    if (nu[c] < -ILRL_MAX_COORD_VEL) nu[c] = -ILRL_MAX_COORD_VEL;
+    if (nu[c] > g_par.max_coord_vel) nu[c] = g_par.max_coord_vel;
+    if (nu[c] < -g_par.max_coord_vel) nu[c] = -g_par.max_coord_vel;
   }
 
   /* ---- constraint rows: violated joint limits, then contact normals, then 2 friction rows per contact */
@@ -327,14 +362,18 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
   int nlim = 0, ncon = 0;
   if (!(flags & 8))
     for (int j = 0; j < NJ; j++) {
-      double pen, dir;
-      if (q[j] - joint_lo[j] <= 0) { pen = q[j] - joint_lo[j]; dir = 1; }
-      else if (joint_hi[j] - q[j] <= 0) { pen = joint_hi[j] - q[j]; dir = -1; }
-      else continue;
-      int r = nlim++;
-      memset(J[r], 0, sizeof J[r]);
-      J[r][6 + j] = dir;
-      rrhs[r] = -pen * ILRL_LIMIT_ERP / dt; /* positional part; velocity part added below */
+      for (int side = 0; side < 2; side++) {
+        double pen = side == 0 ? q[j] - joint_lo[j] : joint_hi[j] - q[j], dir = side == 0 ? 1 : -1;
+        if (side == 1 && !g_par.limit_rows_always && q[j] - joint_lo[j] <= 0) continue; /* one row per joint, lower first */
+        if (pen > 0 && !g_par.limit_rows_always) continue;
+        int r = nlim++;
+        memset(J[r], 0, sizeof J[r]);
+        J[r][6 + j] = dir;
+        /* violated: ERP push-out; (knob) not violated: speculative row, closing speed limited to distance / dt */
+        rrhs[r] = pen > 0 ? -pen / dt : -pen * g_par.limit_erp / dt; /* positional part; velocity part added below */
+        if (-pen > g_diag[1]) g_diag[1] = -pen;
+        if (-pen > 0.5) g_diag[2] += 1;
+      }
     }
   int crow[ILRL_MAX_CONTACTS];
   if (!(flags & 4)) {
@@ -372,7 +411,7 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
         J[r + 2][c2] = dot3(Jv[c2], tdir[1]);
       }
       /* Bullet: penetration > 0 -> speculative row (velocityError -= pen/dt), else ERP push-out */
-      rrhs[r] = dist > 0 ? -dist / dt : -dist * ILRL_CONTACT_ERP / dt;
+      rrhs[r] = dist > 0 ? -dist / dt : -dist * g_par.contact_erp / dt;
       rrhs[r + 1] = rrhs[r + 2] = 0;
     }
   }
@@ -388,7 +427,7 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
   }
   double dv[NV];
   memset(dv, 0, sizeof dv);
-  for (int it = 0; it < ILRL_SOLVER_ITERS; it++) {
+  for (int it = 0; it < g_par.solver_iters; it++) {
     for (int r = 0; r < nlim; r++) { /* joint limits: impulse >= 0 */
       double jd = 0;
       for (int c = 0; c < NV; c++) jd += J[r][c] * dv[c];
@@ -411,7 +450,7 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
     for (int ci = 0; ci < ncon; ci++) { /* friction pair, implicit cone (resolveConeFrictionConstraintRows) */
       int rn = crow[ci], r1 = rn + 1, r2 = rn + 2;
       if (!(lam[rn] > 0)) continue;
-      double lim = ILRL_FRICTION * lam[rn], jd1 = 0, jd2 = 0;
+      double lim = g_par.friction * lam[rn], jd1 = 0, jd2 = 0;
       for (int c = 0; c < NV; c++) { jd1 += J[r1][c] * dv[c]; jd2 += J[r2][c] * dv[c]; }
       double s1 = lam[r1] + rrhs[r1] - jd1 * dinv[r1], s2 = lam[r2] + rrhs[r2] - jd2 * dinv[r2];
       double n2 = s1 * s1 + s2 * s2;
@@ -423,8 +462,15 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
   }
   for (int c = 0; c < NV; c++) {
     nu[c] += dv[c];
-    if (nu[c] > ILRL_MAX_COORD_VEL) nu[c] = ILRL_MAX_COORD_VEL;
-    if (nu[c] < -ILRL_MAX_COORD_VEL) nu[c] = -ILRL_MAX_COORD_VEL;
+    if (nu[c] > g_par.max_coord_vel) nu[c] = g_par.max_coord_vel;
+    if (nu[c] < -g_par.max_coord_vel) nu[c] = -g_par.max_coord_vel;
+  }
+  {
+    double dvz = fabs(nu[5] - vz_before);
+    g_diag[0] += 1;
+    if (dvz > g_diag[3]) g_diag[3] = dvz;
+    if (dvz > 2.0) g_diag[4] += 1;
+    if (p0[2] > g_diag[5]) g_diag[5] = p0[2];
   }
 
   /* ---- integrate positions (btMultiBody::stepPositionsMultiDof: exponential map on the base quaternion) */
@@ -866,6 +912,12 @@ static uint64_t sm64(uint64_t* s) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
   return z ^ (z >> 31);
 }
+static int g_action_mode = 0; /* 0: uniform in [-1,1] (bench workload); 1: N(0,1) clipped to [-1,1] (an untrained RLlib Gaussian policy) */
+void ilrl_oracle_rollout_action_mode(int m) { g_action_mode = m; }
+static double sm_gauss(uint64_t* st) {
+  double u1 = ((double)(sm64(st) >> 11) + 1.0) * (1.0 / 9007199254740993.0), u2 = (double)(sm64(st) >> 11) * (1.0 / 9007199254740992.0);
+  return sqrt(-2.0 * log(u1)) * cos(6.283185307179586 * u2);
+}
 long ilrl_oracle_rollout(orc_env** envs, int n, int steps, uint64_t seed, long* episodes, double* reward_sum) {
   uint64_t st = seed * 0x2545F4914F6CDD1Dull + 1;
   long done_steps = 0, eps = 0;
@@ -874,7 +926,10 @@ long ilrl_oracle_rollout(orc_env** envs, int n, int steps, uint64_t seed, long* 
     for (int i = 0; i < n; i++) {
       orc_env* v = envs[i];
       double a[NJ], obs[70], rew;
-      for (int k = 0; k < NJ; k++) a[k] = (double)(sm64(&st) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+      for (int k = 0; k < NJ; k++) {
+        if (g_action_mode == 0) a[k] = (double)(sm64(&st) >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+        else { double g = sm_gauss(&st); a[k] = g < -1 ? -1 : (g > 1 ? 1 : g); }
+      }
       int deg = (int)(sm64(&st) % 360) - 180;
       int done = ilrl_oracle_low_step(v, a, deg, 0, obs, &rew);
       rs += rew;

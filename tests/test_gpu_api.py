@@ -410,6 +410,43 @@ def test_step_host_async_parts_agree_with_one_batch_step():
         env.close()
 
 
+def test_assigned_attributes_reach_the_kernel():
+    """The reference's drivers assign `max_timestep`, `skipFrame` (and `step_per_level` in the hierarchical env) on a
+    live env (REF env_vis_hier.py:52): here they are kernel parameters, so the assignment must change what the kernel
+    does (round-1 advisor finding: they were dead Python fields)."""
+    env = LowLevelHumanoidEnv(reference_name="motion09_03", seed=4)
+    env.max_timestep = 3
+    env.resetFromFrame(startFrame=10)
+    dones = []
+    for _ in range(3):
+        _, _, d, _ = env.step(np.zeros(17))
+        dones.append(d)
+    assert dones[2] is True and env.cur_timestep == 3          # cut at the assigned horizon, not at 3000
+    env.max_timestep = 3000
+    env.resetFromFrame(startFrame=10)
+    f0 = env.frame
+    env.skipFrame = 5
+    env.step(np.zeros(17))
+    assert env.frame == (f0 + 5) % (env.max_frame - 1)         # incFrame(skipFrame), REF low_level_env.py:218-222, 513
+    env.skipFrame = 2
+    with pytest.raises(NotImplementedError):
+        env.targetLen = 7
+    env.targetLen = 5
+    env.close()
+    h = HierarchicalHumanoidEnv(seed=4)
+    h.step_per_level = 3
+    h.reset()
+    h.step({"high_level_agent": np.array([1.0, 0.0])})
+    seen = []
+    for _ in range(3):
+        o, r, d, _ = h.step({"low_level_agent": np.zeros(17)})
+        seen.append(set(o))
+        if d["__all__"]:
+            break
+    assert "high_level_agent" in seen[-1] and (len(seen) == 3 or d["__all__"])   # the level ends after 3 low steps
+    h.close()
+
+
 def test_c_abi_error_behaviour_on_device():
     """Call-order and argument errors come back as negative ilrl_status codes with a message, never as a crash."""
     import ctypes as C
@@ -543,11 +580,13 @@ def test_physical_invariants_after_long_rollout():
             z = bo[sb, 2] + np.einsum("ij,ij->i", br[sb][:, 2, :], sc) - sr
             worst_pen = min(worst_pen, z.min())
     print("worst penetration %.4f m, worst joint-limit overshoot %.3f rad" % (worst_pen, worst_viol))
-    assert worst_pen >= -0.10, worst_pen     # a falling limb reaches the plane at several m/s: a few cm per 4 ms substep
-    # Limit rows are soft, as Bullet's (they exist only while a joint is beyond its range, ERP 0.2, 5 sweeps shared
-    # with the other rows): under random bang-bang torques the hip_x joints (range 30 deg) overshoot by up to ~2.4 rad
-    # in BOTH this path and the fp64 oracle (tools/diag_limits.py replays the worst cases on the oracle: identical).
-    assert worst_viol <= 3.2, worst_viol
+    # Bounds = about 2x the worst case observed in this run (6.1 cm, 1.43 rad) - plausibility bounds of the RESTATED model:
+    # a falling limb reaches the plane at several m/s (a few cm per 4 ms substep), and the limit rows are soft (they
+    # exist only while a joint is beyond its range, ERP 0.2, 5 sweeps shared with the other rows), so under random
+    # torques the narrow hip_x range (30 deg) is overshot in BOTH this path and the fp64 oracle (tools/diag_limits.py
+    # replays the worst cases on the oracle: identical; profiles/r2_model_sensitivity.md: which constants move it).
+    assert worst_pen >= -0.12, worst_pen
+    assert worst_viol <= 2.9, worst_viol
     env.close()
 
 

@@ -140,7 +140,11 @@ def test_reset_matches_reference():
 
 
 def _phys_tol(contact):
-    k = 10.0 if contact else 1.0
+    # one env step from identical states, against the fp64 oracle.  Contact-free: |dq| <= 1e-4 rad, |dqd| <= 1e-2 rad/s,
+    # |dpos| <= 1e-4 m.  With limit / contact rows active the tier allowed 10x that; the whitened-row solver
+    # measures 1.5e-4 rad / 1.3e-2 rad/s / 6e-6 m at worst over 3 x 512 random states (tools/diag_tolerances.py), so the
+    # bar is 3x, for EVERY state (no outlier allowance).
+    k = 3.0 if contact else 1.0
     return dict(q=1e-4 * k, qd=1e-2 * k, pos=1e-4 * k, quat=1e-4 * k, vel=2e-3 * k)
 
 
@@ -177,15 +181,7 @@ def test_single_step_dynamics_matches_oracle(airborne):
     env.physics_only(tau.astype(np.float32))
     got = env.get_state()[0].cpu().numpy().astype(np.float64)
     assert np.isfinite(got).all()
-    if airborne:
-        _check_phys(got, want, False, "contact-free")
-    else:
-        # states with rows active: compare the bulk (PGS on fp32 vs fp64 may order ties differently on a few
-        # pathological samples); demand the 10x tolerance on >= 98 % of the envs and report the rest
-        t = _phys_tol(True)
-        bad = (np.abs(got[:, 13:30] - want[:, 13:30]).max(1) > t["q"]) | (np.abs(got[:, 30:47] - want[:, 30:47]).max(1) > t["qd"]) \
-            | (np.abs(got[:, 0:3] - want[:, 0:3]).max(1) > t["pos"])
-        assert bad.mean() <= 0.02, "contact/limit states outside tolerance: %d of %d" % (bad.sum(), n)
+    _check_phys(got, want, not airborne, "contact-free" if airborne else "limit / contact rows active")
     env.close()
 
 
@@ -203,10 +199,13 @@ def test_low_trajectory_cfg1():
     phys, envf = env.get_state()
     obs, rew, done, terms, phys, envf = [t.cpu().numpy() for t in (obs, rew, done, terms, phys, envf)]
     np.testing.assert_array_equal(envf[:, 0].astype(int), z["env_after"][:, 0].astype(int))
-    assert (done.astype(bool) == z["done"].astype(bool)).mean() >= 0.995   # alive threshold can flip on fp32 z
+    # done: identical, except where the oracle's torso height is within 1e-4 m of the alive threshold (fp32 z can flip it)
+    mism = np.nonzero(done.astype(bool) != z["done"].astype(bool))[0]
+    assert all(abs(z["phys_after"][i, 2] - 0.75) < 1e-4 for i in mism), mism
     _check_phys(phys.astype(np.float64), z["phys_after"], True, "cfg1 step")
-    # reward through physics: dominated by the dynamics tolerance (qd error 1e-1 -> jvel score), so 2e-3 absolute
-    assert np.abs(rew - z["reward"]).max() <= 5e-3, np.abs(rew - z["reward"]).max()
+    # reward through physics (measured 2.3e-6 at worst over the 1000 steps, tools/diag_tolerances.py)
+    keep = np.ones(n, bool); keep[mism] = False
+    assert np.abs(rew - z["reward"])[keep].max() <= 2e-5, np.abs(rew - z["reward"])[keep].max()
     assert np.abs(obs[:, 42:] - z["obs"][:, 42:]).max() <= 1e-5 * 150
     # resets of the same trajectory
     sel = z["reset_before"] == 1
@@ -250,10 +249,10 @@ def test_hier_trajectory_protocol():
     l = kind == 2
     flags = z["flags"][l]
     np.testing.assert_array_equal(envf[l][:, 0].astype(int), z["env_after"][l][:, 0].astype(int))
-    assert ((done[l] != 0) == ((flags & 1) != 0)).mean() >= 0.995
     agree = (done[l] != 0) == ((flags & 1) != 0)
+    assert all(abs(z["phys_after"][l][i, 2] - 0.75) < 1e-4 for i in np.nonzero(~agree)[0]), np.nonzero(~agree)[0]
     np.testing.assert_array_equal(((hf[l] & 2) != 0)[agree], ((flags & 2) != 0)[agree])
     _check_phys(phys[l].astype(np.float64), z["phys_after"][l], True, "hier step")
     has_low = ((flags & 4) != 0) & agree
-    assert np.abs(rew[l][has_low] - z["low_reward"][l][has_low]).max() <= 5e-3
+    assert np.abs(rew[l][has_low] - z["low_reward"][l][has_low]).max() <= 1e-4
     env.close()

@@ -231,7 +231,8 @@ def make_env(wl, rank, world, local_rank):
     return env, n, hier
 
 
-def measure_device(wl, K, W, rank, world, local_rank, clocks=None, min_region_s=0.5, max_blocks=200, kernel_events=True):
+def measure_device(wl, K, W, rank, world, local_rank, clocks=None, min_region_s=0.5, max_blocks=200, kernel_events=True,
+                   use_graph=True):
     """Device-timed throughput of one workload: W warm-up steps, then R blocks of EXACTLY K steps, each bracketed by a
     barrier + synchronize on both sides and timed with CUDA events on the launching stream; per block the MAX over
     ranks; reported: the MEDIAN block (R is chosen so that the blocks together last >= min_region_s: a single block of
@@ -265,13 +266,16 @@ def measure_device(wl, K, W, rank, world, local_rank, clocks=None, min_region_s=
             dist.barrier()
         torch.cuda.synchronize()
 
-    def block(k):
+    def block(k, graph=None):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0 = time.perf_counter()
         e0.record()
-        for _ in range(k):
-            one_step()
+        if graph is not None:
+            graph.replay()
+        else:
+            for _ in range(k):
+                one_step()
         e1.record()
         barrier()
         if clocks:
@@ -287,9 +291,27 @@ def measure_device(wl, K, W, rank, world, local_rank, clocks=None, min_region_s=
         r_t = torch.tensor([R], device=dev)
         dist.all_reduce(r_t, op=dist.ReduceOp.MAX)
         R = int(r_t.item())
+    # The K launches of a block are replayed from a CUDA graph (as rollout.py replays its fragments): the timed region
+    # then holds no Python and no per-launch driver call, so host jitter (8 ranks share the box's cores) stays out of it.
+    # G graphs over consecutive slices of the action pool are used in turn, so the actions still rotate through > L2.
     l0 = env.launch_count()
-    ms_blocks = torch.tensor([block(K) for _ in range(R)], device=dev, dtype=torch.float64)
-    launches_per_block = (env.launch_count() - l0) // R
+    block(K)
+    launches_per_block = env.launch_count() - l0
+    graphs = []
+    if use_graph:
+        G = int(max(1, min(R, POOL // max(K, 1))))
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        for _ in range(G):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=side):
+                for _ in range(K):
+                    one_step()
+            graphs.append(gr)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        block(K, graphs[0])   # first replay untimed
+    ms_blocks = torch.tensor([block(K, graphs[r % len(graphs)] if graphs else None) for r in range(R)], device=dev,
+                             dtype=torch.float64)
     st = env.stats()  # {episodes, sum return, sum length, steps, sum reward, ...}: the only cross-rank exchange
     ilrl_b200.stats.allreduce_stats(st)  # NCCL sum of 16 floats over the ranks (no-op at N=1)
     n_all = torch.tensor([float(n)], device=dev)
@@ -300,13 +322,14 @@ def measure_device(wl, K, W, rank, world, local_rank, clocks=None, min_region_s=
     ms = float(mb[len(mb) // 2])
     res = {"n": n, "n_all": float(n_all.item()), "hier": hier, "ms_block": ms, "ms_per_step": ms / K,
            "value": float(n_all.item()) * K / (ms * 1e-3), "blocks": R, "block_ms_min": float(mb[0]), "block_ms_max": float(mb[-1]),
-           "launches_per_block": int(launches_per_block), "stats": st.cpu().numpy(), "pool_mb": POOL * n * 17 * 4 >> 20}
+           "launches_per_block": int(launches_per_block), "stats": st.cpu().numpy(), "pool_mb": POOL * n * 17 * 4 >> 20,
+           "graphs": len(graphs)}
     if kernel_events:
         # time of the step kernel alone, measured ON THE DEVICE inside one more block of exactly K back-to-back steps:
         # every step kernel stamps %globaltimer at its first CTA's start and its last CTA's end (ilrl_kernel_timing; no
         # extra launch, no synchronisation), so the sum of the kernel times cannot exceed the block they ran in
         env.kernel_timing(True)
-        kb = block(K)
+        kb = block(K)   # (launched one by one: the slot a launch stamps is a launch argument)
         kms, kcnt = env.kernel_timing(False)
         res["kernel_ms"] = kms / max(kcnt, 1)
         res["kernel_launches_timed"] = kcnt
@@ -401,6 +424,13 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     K, W = args.steps, max(args.warmup, 3)
+    if world > 1:   # every rank on its own share of the host cores (the ranks of one box otherwise migrate over all of them)
+        try:
+            cores = sorted(os.sched_getaffinity(0))
+            per = max(1, len(cores) // world)
+            os.sched_setaffinity(0, set(cores[local_rank * per:(local_rank + 1) * per]) or set(cores))
+        except Exception:
+            pass
 
     # CPU baseline first (before CUDA is initialised in this process), rank 0 at N=1 only
     cpu_base = None
@@ -427,7 +457,7 @@ def run_ours(args):
     clocks = ClockSampler(local_rank) if rank == 0 else None
 
     wl = WORKLOADS[args.workload]
-    res, env, pools = measure_device(wl, K, W, rank, world, local_rank, clocks)
+    res, env, pools = measure_device(wl, K, W, rank, world, local_rank, clocks, use_graph=not args.no_graph)
     n, hier = res["n"], res["hier"]
     e2e = measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks)
     env.close()
@@ -440,7 +470,7 @@ def run_ours(args):
     if args.workload == "low4096" and not args.no_extra_configs:
         for key, name in (("cfg3_hier16384", "hier16384"), ("cfg4_multiclip65536", "multiclip65536")):
             r2, env2, p2 = measure_device(WORKLOADS[name], K, max(W, 10), rank, world, local_rank, clocks, min_region_s=0.3,
-                                          kernel_events=False)
+                                          kernel_events=False, use_graph=not args.no_graph)
             env2.close()
             del p2
             torch.cuda.empty_cache()
@@ -479,7 +509,9 @@ def run_ours(args):
                        "l2": "action batches rotate through a %d MB pool (> 126 MB L2); the env state is "
                              "persistent on-device state by design" % res["pool_mb"],
                        "timing": "median of %d blocks of exactly %d steps, each block bracketed by barrier + synchronize and "
-                                 "timed with CUDA events (max over ranks per block)" % (res["blocks"], K),
+                                 "timed with CUDA events (max over ranks per block); %s" % (
+                                     res["blocks"], K, ("the %d launches of a block replayed from one of %d CUDA graphs" % (
+                                         res["launches_per_block"], res["graphs"])) if res["graphs"] else "launched one by one"),
                        "blocks": res["blocks"], "block_ms_min": res["block_ms_min"], "block_ms_max": res["block_ms_max"],
                        "episodes": float(stn[0]), "mean_episode_len": float(stn[2] / max(stn[0], 1)),
                        "mean_step_reward": float(stn[4] / max(stn[3], 1))},
@@ -625,6 +657,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=50)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch the steps of a timed block one by one instead of replaying a CUDA graph")
     ap.add_argument("--no-extra-configs", action="store_true", help="skip the short cfg 3 / 4 / 5 runs of the default line")
     ap.add_argument("--workload", default="low4096", choices=sorted(WORKLOADS) + ["rollout16384x8", "hier_rollout16384x10"],
                     help="low4096 = the contract line (BASELINE cfg 2); the others are extra measurement modes")

@@ -57,7 +57,7 @@ struct StepArgs {
   uint8_t* high_flags; // [n]
   const int32_t* forced_deg;  // [n] or null
   int forced_scalar;          // INT_MIN, or the heading every env uses at its next target re-sampling (ilrl_step_pull)
-  float* stats;        // [16] or null
+  double* stats;       // [16] or null: fp64 accumulators (counts stay exact past 2^24 env steps between two reads)
   float* gscr;         // [n][GROWS][RW] overflow scratch for constraint rows beyond the shared-memory budget
   unsigned int* tile_counter;  // [2]: next tile to hand out, CTAs that have left (both zero between launches)
   int ntiles;
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
       float x = v[t];
 #pragma unroll
       for (int o = 16; o >= 4; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);  // (lanes 1..3 of a quad hold 0)
-      if ((tid & 31) == 0 && x != 0.f) atomicAdd(a.stats + t, x);
+      if ((tid & 31) == 0 && x != 0.f) atomicAdd(a.stats + t, (double)x);
     }
   }
   pf.mark(chain::PF_TAIL);
@@ -638,9 +638,9 @@ __global__ void high_readout_kernel(int n, const float* __restrict__ obs, const 
     if (flags_out) flags_out[t] = flags[t];
   }
 }
-__global__ void stats_fetch_kernel(float* acc, float* out) {
+__global__ void stats_fetch_kernel(double* acc, float* out) {
   int t = threadIdx.x;
-  if (t < ILRL_STATS_WORDS) { out[t] = acc[t]; acc[t] = 0.f; }
+  if (t < ILRL_STATS_WORDS) { out[t] = (float)acc[t]; acc[t] = 0.0; }
 }
 
 }  // namespace ilrl
@@ -660,7 +660,7 @@ struct ilrl_env {
   float* high_obs = nullptr;
   float* high_reward = nullptr;
   uint8_t* high_flags = nullptr;
-  float* stats = nullptr;
+  double* stats = nullptr;
   unsigned int* tile_counter = nullptr;   // [1 + ILRL_MAX_PARTS][2]: the whole batch, then one pair per part
   cudaStream_t part_stream[ILRL_MAX_PARTS] = {nullptr};   // ilrl_step_host_async: one stream per part
   bool part_busy[ILRL_MAX_PARTS] = {false};
@@ -811,7 +811,7 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMalloc(&env->high_obs, sizeof(float) * 44 * n));
   CKC(cudaMalloc(&env->high_reward, sizeof(float) * n));
   CKC(cudaMalloc(&env->high_flags, n));
-  CKC(cudaMalloc(&env->stats, sizeof(float) * ILRL_STATS_WORDS));
+  CKC(cudaMalloc(&env->stats, sizeof(double) * ILRL_STATS_WORDS));
   CKC(cudaMalloc(&env->tile_counter, 2 * (1 + ILRL_MAX_PARTS) * sizeof(unsigned int)));
   CKC(cudaMemset(env->tile_counter, 0, 2 * (1 + ILRL_MAX_PARTS) * sizeof(unsigned int)));
   CKC(cudaMemset(env->phys, 0, sizeof(float) * ILRL_PHYS_WORDS * n));
@@ -820,7 +820,7 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMemset(env->high_obs, 0, sizeof(float) * 44 * n));
   CKC(cudaMemset(env->high_reward, 0, sizeof(float) * n));
   CKC(cudaMemset(env->high_flags, 0, n));
-  CKC(cudaMemset(env->stats, 0, sizeof(float) * ILRL_STATS_WORDS));
+  CKC(cudaMemset(env->stats, 0, sizeof(double) * ILRL_STATS_WORDS));
 #ifdef ILRL_PROF
   CKC(cudaMalloc(&env->prof, sizeof(long long) * chain::PF_WORDS * ((n + 7) / 8 + 2)));
   CKC(cudaMemset(env->prof, 0, sizeof(long long) * chain::PF_WORDS * ((n + 7) / 8 + 2)));

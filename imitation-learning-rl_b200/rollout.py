@@ -71,7 +71,8 @@ class FusedPolicy:
             for m in net:
                 ps += [m.weight.detach().float().contiguous(), m.bias.detach().float().contiguous()]
         ps.append(self.policy.log_std.detach().float().contiguous())
-        rc = self.L.ilrl_policy_pack(*[_ptr(p) for p in ps], self.obs_dim, self.act_dim, _ptr(self.blob), self._st())
+        with torch.cuda.device(self.device):   # the handle-less C entry points launch on the CURRENT device
+            rc = self.L.ilrl_policy_pack(*[_ptr(p) for p in ps], self.obs_dim, self.act_dim, _ptr(self.blob), self._st())
         if rc != 0:
             raise _lib.IlrlError("ilrl_policy_pack failed (%d)" % rc)
         self._keep = ps   # alive until the pack kernel has certainly run
@@ -84,8 +85,9 @@ class FusedPolicy:
                          (logp, (n,)), (value, (n,))):
             assert t is None or (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape)
         p = lambda t: None if t is None else _ptr(t)  # noqa: E731
-        rc = self.L.ilrl_policy_step(_ptr(self.blob), _ptr(obs), p(noise), p(action), p(action_clipped), p(logp), p(value),
-                                     self.obs_dim, self.act_dim, n, self._st())
+        with torch.cuda.device(self.device):
+            rc = self.L.ilrl_policy_step(_ptr(self.blob), _ptr(obs), p(noise), p(action), p(action_clipped), p(logp), p(value),
+                                         self.obs_dim, self.act_dim, n, self._st())
         if rc != 0:
             raise _lib.IlrlError("ilrl_policy_step failed (%d)" % rc)
 
@@ -98,7 +100,8 @@ def gae(rewards, values, dones, gamma, lam, stream=None):
     assert rewards.is_cuda and rewards.is_contiguous() and values.is_contiguous() and dones.is_contiguous()
     adv, ret = torch.empty_like(rewards), torch.empty_like(rewards)
     st = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream if stream is None else stream)
-    rc = _lib.lib().ilrl_gae(_ptr(rewards), _ptr(values), _ptr(dones), gamma, lam, _ptr(adv), _ptr(ret), T, n, st)
+    with torch.cuda.device(rewards.device):
+        rc = _lib.lib().ilrl_gae(_ptr(rewards), _ptr(values), _ptr(dones), gamma, lam, _ptr(adv), _ptr(ret), T, n, st)
     if rc != 0:
         raise _lib.IlrlError("ilrl_gae failed (%d)" % rc)
     return adv, ret
@@ -106,7 +109,14 @@ def gae(rewards, values, dones, gamma, lam, stream=None):
 
 class RolloutCollector:
     """Collects [T, N] fragments from a BatchedHumanoidEnv (mode "low", auto_reset=True) with a policy living on the
-    same GPU.  `collect()` returns a dict of step-major device tensors named like RLlib's SampleBatch columns."""
+    same GPU.  `collect()` returns a dict of step-major device tensors named like RLlib's SampleBatch columns.
+
+    `action_logp` (fused=True) is the log-density of the sampled action under the KERNEL's policy: bf16 operands and
+    hidden activations, fp32 accumulation.  A learner that recomputes the old log-probability with the fp32 torch
+    module gets importance ratios that differ from 1 by up to exp(sum_j z_j d_j) (d = the two means' difference in
+    units of sigma; |logp difference| <= 0.3 on random-init weights, tests/test_gpu_rollout.py): use the stored
+    `action_logp` as the old log-probability (what RLlib's PPO does with the SampleBatch column), or collect with
+    fused=False when the learner must reproduce it exactly."""
 
     def __init__(self, env, policy=None, horizon=8, gamma=0.99, lam=0.9, seed=0, use_graph=True, autocast_dtype=None,
                  fused=True):
@@ -132,6 +142,7 @@ class RolloutCollector:
         self._noise = torch.zeros(T, n, ACT_LOW, **f)
         self._clipped = torch.zeros(n, ACT_LOW, **f)
         self._graph = None
+        self._warm = False
         self._use_graph = use_graph
         self.cur_obs.copy_(env.reset())
 
@@ -176,15 +187,17 @@ class RolloutCollector:
         self._noise.normal_(generator=self.gen)
         if not self._use_graph:
             self._loop()
-        elif self._graph is None:
+        elif not self._warm:
+            # The first fragment runs eagerly, on a side stream (cuBLAS workspaces, lazy module loads), and COUNTS: nothing
+            # is rolled back, so the envs' Philox draw counters and the statistics accumulators stay exactly what an
+            # ungraphed collector would have (use_graph=True and use_graph=False give the same trajectories).
             s = torch.cuda.Stream(device=self.env.device)
             s.wait_stream(torch.cuda.current_stream(self.env.device))
-            with torch.cuda.stream(s):   # warm-up on a side stream (cuBLAS workspaces, lazy module loads)
-                saved = [t.clone() for t in self.env.get_state()] + [self.cur_obs.clone()]
+            with torch.cuda.stream(s):
                 self._loop()
-                self.env.set_state(saved[0], saved[1])
-                self.cur_obs.copy_(saved[2])   # = row T of the observation buffer, which the captured loop reads first
             torch.cuda.current_stream(self.env.device).wait_stream(s)
+            self._warm = True
+        elif self._graph is None:
             self._graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self._graph):
                 self._loop()
@@ -209,8 +222,9 @@ def gae_decisions(rewards, flags, values, gamma, lam):
     adv, ret = torch.empty(T, n, device=rewards.device), torch.empty(T, n, device=rewards.device)
     valid = torch.empty(T, n, device=rewards.device, dtype=torch.uint8)
     st = C.c_void_p(torch.cuda.current_stream(rewards.device).cuda_stream)
-    rc = _lib.lib().ilrl_gae_decisions(_ptr(rewards), _ptr(flags), _ptr(values), gamma, lam, _ptr(adv), _ptr(ret),
-                                       _ptr(valid), T, n, st)
+    with torch.cuda.device(rewards.device):
+        rc = _lib.lib().ilrl_gae_decisions(_ptr(rewards), _ptr(flags), _ptr(values), gamma, lam, _ptr(adv), _ptr(ret),
+                                           _ptr(valid), T, n, st)
     if rc != 0:
         raise _lib.IlrlError("ilrl_gae_decisions failed (%d)" % rc)
     return adv, ret, valid

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOTAL, STEPS = 3000, 40
 
 
-def _rollout(first, count, device, seed_base):
+def _rollout(first, count, device, seed_base, TOTAL=TOTAL, STEPS=STEPS):
     import ilrl_b200
     from ilrl_b200 import BatchedHumanoidEnv, stats
     clips = ilrl_b200.CLIP_NAMES
@@ -35,7 +35,7 @@ def _rollout(first, count, device, seed_base):
     return st, phys
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, TOTAL=TOTAL, STEPS=STEPS):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     import ilrl_b200  # noqa: F401
@@ -45,14 +45,26 @@ def _worker(rank, world, port, q):
                             device_id=torch.device("cuda", rank))
     try:
         first, count = stats.shard_envs(TOTAL, world, rank)
-        st, phys = _rollout(first, count, rank, 5)
+        st, phys = _rollout(first, count, rank, 5, TOTAL, STEPS)
         total = stats.allreduce_stats(st.clone())
         q.put((rank, st.cpu().numpy(), total.cpu().numpy(), phys.numpy()))
     finally:
         dist.destroy_process_group()
 
 
+def test_eight_rank_cfg4_sharding_matches_single_process():
+    """BASELINE cfg 4 on a full box: 65536 multi-clip envs (clip = global env id mod 4) sharded 8192 per GPU over 8 NCCL
+    ranks; every shard bit-identical to the single-GPU batch, all-reduced statistics equal to its totals."""
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs eight CUDA devices")
+    _run_world(8, 65536, 12)
+
+
 def test_two_rank_sharding_matches_single_process():
+    _run_world(2, TOTAL, STEPS)
+
+
+def _run_world(world, TOTAL, STEPS):
     import torch.multiprocessing as mp
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -60,7 +72,7 @@ def test_two_rank_sharding_matches_single_process():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, TOTAL, STEPS)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in procs], key=lambda x: x[0])
@@ -68,13 +80,14 @@ def test_two_rank_sharding_matches_single_process():
         p.join(timeout=60)
         assert p.exitcode == 0
     sys.path.insert(0, ROOT)
-    whole_st, whole_phys = _rollout(0, TOTAL, 0, 5)
+    whole_st, whole_phys = _rollout(0, TOTAL, 0, 5, TOTAL, STEPS)
     whole_st = whole_st.cpu().numpy()
     # every rank holds the same all-reduced total, equal to the sum of the per-rank vectors
-    np.testing.assert_allclose(res[0][2], res[1][2], rtol=0, atol=0)
-    np.testing.assert_allclose(res[0][2], res[0][1] + res[1][1], rtol=1e-6)
+    for r in res[1:]:
+        np.testing.assert_allclose(res[0][2], r[2], rtol=0, atol=0)
+    np.testing.assert_allclose(res[0][2], sum(r[1] for r in res), rtol=1e-6)
     # counts are exact; sums agree to fp32 accumulation order; and every env's state is bit-identical to what the
     # single process computed for it (same seed, env_id_base = first global id of the shard)
     assert res[0][2][3] == TOTAL * STEPS and res[0][2][0] == whole_st[0]
     np.testing.assert_allclose(res[0][2], whole_st, rtol=2e-4, atol=1e-2)
-    np.testing.assert_array_equal(np.concatenate([res[0][3], res[1][3]]), whole_phys.numpy())
+    np.testing.assert_array_equal(np.concatenate([r[3] for r in res]), whole_phys.numpy())

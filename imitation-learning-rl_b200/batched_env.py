@@ -14,6 +14,7 @@ from . import _lib
 from .clips import CLIP_NAMES, load_clip
 
 OBS_LOW, OBS_HIGH, ACT_LOW, ACT_HIGH = 70, 44, 17, 2
+OBS_LOW2, OBS_HIGH2, ACT_HIGH2, JT_WORDS = 72, 60, 36, 34   # mode "hier2" (REF hier_env_2.py:48-60)
 PHYS_WORDS, ENV_WORDS, TERM_WORDS, STATS_WORDS = 47, 28, 12, 16
 INT32_MIN = -2 ** 31
 TERM_NAMES = ["deltaJoints", "deltaVelJoints", "delta_lowTargetScore", "electricityScore", "jointLimitScore",
@@ -32,21 +33,24 @@ def _ptr(t):
 
 class BatchedHumanoidEnv:
     """mode "low": LowLevelHumanoidEnv semantics (REF low_level_env.py); "hier": HierarchicalHumanoidEnv
-    (REF hier_env.py).  clips: list of clip names staged in HBM; clip_of_env: per-env index into that list.
+    (REF hier_env.py); "hier2": the hier_env_2.py variant (joint-target tracking low level: low obs 72, high obs 60,
+    high action 36, skipFrame 5, step_per_level 20 unless given).  clips: list of clip names staged in HBM; clip_of_env: per-env index into that list.
     env_id_base: global id of env 0 when a batch is sharded over several handles / GPUs (with the same seed the
     shards then reproduce exactly what one handle holding the whole batch would do)."""
 
     def __init__(self, num_envs, mode="low", clips=("motion09_03",), clip_of_env=None, device=0, seed=0,
-                 auto_reset=True, max_timestep=3000, step_per_level=5, env_id_base=0):
+                 auto_reset=True, max_timestep=3000, step_per_level=None, env_id_base=0, skip_frame=None):
         if not torch.cuda.is_available():
             raise _lib.IlrlError("BatchedHumanoidEnv needs a CUDA device (sm_100a); there is no CPU fallback")
         self.L = _lib.lib()
         self.num_envs = int(num_envs)
-        self.mode = {"low": 0, "hier": 1}[mode]
+        self.mode = {"low": 0, "hier": 1, "hier2": 2}[mode]
+        self.obs_w, self.hobs_w, self.hact_w = (OBS_LOW2, OBS_HIGH2, ACT_HIGH2) if self.mode == 2 else (OBS_LOW, OBS_HIGH, ACT_HIGH)
         self.device = torch.device("cuda", device)
         self.clip_names = list(clips)
         cfg = _lib.Config(device=device, num_envs=self.num_envs, mode=self.mode, auto_reset=int(bool(auto_reset)),
-                          seed=seed, skip_frame=2, max_timestep=max_timestep, step_per_level=step_per_level,
+                          seed=seed, skip_frame=int(skip_frame or 0), max_timestep=max_timestep,
+                          step_per_level=int(step_per_level or 0),
                           env_id_base=int(env_id_base))
         h = C.c_void_p()
         rc = self.L.ilrl_create(C.byref(cfg), C.byref(h))
@@ -66,15 +70,16 @@ class BatchedHumanoidEnv:
             assert ids.shape == (self.num_envs,)
         self._ck(self.L.ilrl_set_clip_ids(self.h, None if ids is None else ids.ctypes.data))
         n, dev = self.num_envs, self.device
-        self.obs = torch.zeros(n, OBS_LOW, device=dev)
+        self.obs = torch.zeros(n, self.obs_w, device=dev)
         self.reward = torch.zeros(n, device=dev)
         self.done = torch.zeros(n, dtype=torch.uint8, device=dev)
         self.terms = torch.zeros(n, TERM_WORDS, device=dev)
-        if self.mode == 1:
-            self.high_obs = torch.zeros(n, OBS_HIGH, device=dev)
+        if self.mode >= 1:
+            self.high_obs = torch.zeros(n, self.hobs_w, device=dev)
             self.high_reward = torch.zeros(n, device=dev)
             self.high_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
         self._forced = None
+        self._noise = None
         self._host_key = None
         self._async_key = None
         self._pull_buf = None
@@ -113,9 +118,9 @@ class BatchedHumanoidEnv:
         td = None if target_deg is None else torch.as_tensor(target_deg, device=self.device).to(torch.int32).contiguous()
         yw = None if reset_yaw_deg is None else self._f32(reset_yaw_deg, (n,))
         xy = None if target_xy is None else self._f32(target_xy, (n, 2))
-        out = self.high_obs if self.mode == 1 else self.obs
+        out = self.high_obs if self.mode >= 1 else self.obs
         self._ck(self.L.ilrl_reset(self.h, _ptr(m), _ptr(sf), _ptr(td), _ptr(yw), _ptr(xy), _ptr(out), self._stream()))
-        if self.mode == 1:
+        if self.mode >= 1:
             self._ck(self.L.ilrl_high_readout(self.h, None, None, _ptr(self.high_flags), self._stream()))
         return out
 
@@ -131,7 +136,7 @@ class BatchedHumanoidEnv:
         """`step` writing straight into caller-owned device tensors (rollout buffers): obs [N,70] f32, reward [N] f32,
         done [N] u8, optional terms [N,12]; all contiguous, on this env's device."""
         n = self.num_envs
-        for t, shape, dt in ((action, (n, ACT_LOW), torch.float32), (obs, (n, OBS_LOW), torch.float32),
+        for t, shape, dt in ((action, (n, ACT_LOW), torch.float32), (obs, (n, self.obs_w), torch.float32),
                              (reward, (n,), torch.float32), (done, (n,), torch.uint8)) + (
                                  () if terms is None else ((terms, (n, TERM_WORDS), torch.float32),)):
             assert t.is_cuda and t.device == self.device and t.dtype == dt and t.is_contiguous() and tuple(t.shape) == shape
@@ -144,7 +149,7 @@ class BatchedHumanoidEnv:
         key = (id(action_np), id(obs_np), id(reward_np), id(done_np), id(terms_np))
         if self._host_key != key:
             assert action_np.dtype == np.float32 and action_np.flags.c_contiguous and action_np.shape == (self.num_envs, ACT_LOW)
-            assert obs_np.dtype == np.float32 and obs_np.flags.c_contiguous and obs_np.shape == (self.num_envs, OBS_LOW)
+            assert obs_np.dtype == np.float32 and obs_np.flags.c_contiguous and obs_np.shape == (self.num_envs, self.obs_w)
             assert reward_np.dtype == np.float32 and done_np.dtype == np.uint8
             assert reward_np.shape == (self.num_envs,) and done_np.shape == (self.num_envs,)
             assert terms_np is None or (terms_np.dtype == np.float32 and terms_np.shape == (self.num_envs, TERM_WORDS))
@@ -188,13 +193,15 @@ class BatchedHumanoidEnv:
         return slice(first, min(first + per, self.num_envs))
 
     # packed row of ilrl_step_pull / ilrl_pull (include/ilrl.h)
-    PULL_WORDS = 205
-    PULL_OBS, PULL_REWARD, PULL_DONE, PULL_TERMS, PULL_ENVF, PULL_PHYS = slice(0, 70), 70, 71, slice(72, 84), slice(84, 112), slice(112, 159)
-    PULL_HIGH_OBS, PULL_HIGH_REWARD, PULL_HIGH_FLAGS = slice(159, 203), 203, 204
+    PULL_WORDS = 257
+    PULL_OBS, PULL_REWARD, PULL_DONE, PULL_TERMS, PULL_ENVF, PULL_PHYS = slice(0, 70), 72, 73, slice(74, 86), slice(86, 114), slice(114, 161)
+    PULL_HIGH_OBS, PULL_HIGH_REWARD, PULL_HIGH_FLAGS = slice(161, 205), 221, 222
+    PULL_OBS2, PULL_HIGH_OBS2, PULL_JT = slice(0, 72), slice(161, 221), slice(223, 257)   # mode "hier2" widths
 
     def step_pull(self, action_np, forced_target_deg=None):
-        """One blocking step from host actions [N,17] returning the packed mirror rows [N,205] (numpy, owned by this
-        object): obs | reward | done | terms | envf | phys | high obs | high reward | high flags - one transfer."""
+        """One blocking step from host actions [N,17] returning the packed mirror rows [N,257] (numpy, owned by this
+        object): obs | reward | done | terms | envf | phys | high obs | high reward | high flags | jointTarget - one
+        transfer (PULL_* slices)."""
         if self._pull_buf is None:
             self._pull_buf = np.zeros((self.num_envs, self.PULL_WORDS), np.float32)
         a = np.ascontiguousarray(action_np, dtype=np.float32).reshape(self.num_envs, ACT_LOW)
@@ -219,7 +226,7 @@ class BatchedHumanoidEnv:
     def high_step(self, action2):
         """hier mode: heading action [N,2] for the envs waiting for one; returns the low-level obs tensor [N,70]
         (rows of envs that were not waiting are untouched)."""
-        a = self._f32(action2, (self.num_envs, ACT_HIGH))
+        a = self._f32(action2, (self.num_envs, self.hact_w))
         self._ck(self.L.ilrl_high_step(self.h, _ptr(a), _ptr(self.obs), self._stream()))
         return self.obs
 
@@ -233,14 +240,14 @@ class BatchedHumanoidEnv:
     def high_step_into(self, action2, low_obs):
         """`high_step` writing the low-level obs rows of the envs that were waiting into a caller-owned [N,70] tensor."""
         n = self.num_envs
-        for t, shape in ((action2, (n, ACT_HIGH)), (low_obs, (n, OBS_LOW))):
+        for t, shape in ((action2, (n, self.hact_w)), (low_obs, (n, self.obs_w))):
             assert t.is_cuda and t.device == self.device and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == shape
         self._ck(self.L.ilrl_high_step(self.h, _ptr(action2), _ptr(low_obs), self._stream()))
 
     def high_readout_into(self, high_obs, high_reward, high_flags):
         """`high_readout` into caller-owned tensors: [N,44] f32, [N] f32, [N] u8."""
         n = self.num_envs
-        for t, shape, dt in ((high_obs, (n, OBS_HIGH), torch.float32), (high_reward, (n,), torch.float32),
+        for t, shape, dt in ((high_obs, (n, self.hobs_w), torch.float32), (high_reward, (n,), torch.float32),
                              (high_flags, (n,), torch.uint8)):
             assert t.is_cuda and t.device == self.device and t.dtype == dt and t.is_contiguous() and tuple(t.shape) == shape
         self._ck(self.L.ilrl_high_readout(self.h, _ptr(high_obs), _ptr(high_reward), _ptr(high_flags), self._stream()))
@@ -273,6 +280,20 @@ class BatchedHumanoidEnv:
         else:
             self._forced = torch.as_tensor(deg, device=self.device).to(torch.int32).contiguous()
             self._ck(self.L.ilrl_set_forced_target_deg(self.h, _ptr(self._forced)))
+
+    def set_forced_reset_noise(self, noise17):
+        """mode "hier2" harness: the joint noise [N,17] resets use instead of their own uniform(-0.1, 0.1) draws (only the
+        six arm joints keep it, REF hier_env_2.py:214-252); None = draw."""
+        self._noise = None if noise17 is None else self._f32(noise17, (self.num_envs, ACT_LOW))
+        self._ck(self.L.ilrl_set_forced_reset_noise(self.h, _ptr(self._noise)))
+
+    def get_joint_target(self):
+        out = torch.empty(self.num_envs, JT_WORDS, device=self.device)
+        self._ck(self.L.ilrl_get_joint_target(self.h, _ptr(out), self._stream()))
+        return out
+
+    def set_joint_target(self, jt):
+        self._ck(self.L.ilrl_set_joint_target(self.h, _ptr(self._f32(jt, (self.num_envs, JT_WORDS))), self._stream()))
 
     def physics_only(self, torque):
         t = self._f32(torque, (self.num_envs, ACT_LOW))

@@ -58,6 +58,8 @@ struct StepArgs {
   const int32_t* forced_deg;  // [n] or null
   int forced_scalar;          // INT_MIN, or the heading every env uses at its next target re-sampling (ilrl_step_pull)
   double* stats;       // [16] or null: fp64 accumulators (counts stay exact past 2^24 env steps between two reads)
+  float* jt;           // [34][n] jointTarget (MODE 2: hier_env_2.py:731)
+  const float* forced_noise;  // [n,17] or null: joint noise an auto-reset uses instead of its own draws (MODE 2 harness)
   float* gscr;         // [n][GROWS][RW] overflow scratch for constraint rows beyond the shared-memory budget
   unsigned int* tile_counter;  // [2]: next tile to hand out, CTAs that have left (both zero between launches)
   int ntiles;
@@ -139,7 +141,8 @@ __device__ __forceinline__ void set_torques(SM& sm, int e, int tid, int role, co
 
 // ------------------------------------------------------------------------------------------------ K1: fused step
 // MODE 0 = LowLevelHumanoidEnv.step (REF low_level_env.py:475-526), MODE 1 = HierarchicalHumanoidEnv low_level_step
-// (REF hier_env.py:355-366, 583-642).  Four lanes = one env (ilrl_chain.cuh): the physics substeps run distributed
+// (REF hier_env.py:355-366, 583-642), MODE 2 = the hier_env_2.py variant (REF hier_env_2.py:408-419, 751-769: obs rows
+// of 72 / 60 words, per-env jointTarget).  Four lanes = one env (ilrl_chain.cuh): the physics substeps run distributed
 // over the quad; the env bookkeeping after them is computed redundantly by the four lanes (identical instruction
 // stream, no divergence) and the outputs are dealt to the lanes for the stores.
 template <int MODE, class SM>
@@ -148,6 +151,8 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   SM& sm = *reinterpret_cast<SM*>(smraw);
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
+  constexpr int OBSW = MODE == 2 ? ILRL_OBS_LOW2 : ILRL_OBS_LOW, HOBSW = MODE == 2 ? ILRL_OBS_HIGH2 : ILRL_OBS_HIGH;
+  static_assert(SM::ES >= OBSW, "the obs row is staged in the env's scratch block");
   if (a.ktime && tid == 0) atomicMin(a.ktime, globaltimer_ns());
   quad_smem_init(sm);
   // Persistent CTAs: the grid is at most what is resident at once (SMs x CTAs per SM) and tiles of QE envs are handed
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     const float* arow = a.action + (size_t)i * NJ;
 #pragma unroll
     for (int m = 0; m < (NJ + 3) / 4; m++) if (role + 4 * m < NJ) av[m] = arow[role + 4 * m];
-    if (MODE == 1) pend_flag = a.envf[(size_t)ILRL_E_HIGH_PENDING * a.n + i];
+    if (MODE >= 1) pend_flag = a.envf[(size_t)ILRL_E_HIGH_PENDING * a.n + i];
     chain::load_base(a.phys, a.n, i, b);
     chain::load_links(a.phys, a.n, i, sm, role, qv, qdv);
     float* dst = sm.act(e);
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
 
   // skipped envs: hier envs waiting for a high-level action, and rows whose first action component is NaN (the
   // batched adapters' "no action for this env in this call"; the reference asserts finite actions, REF humanoid.py:55)
-  const bool pending = valid && ((MODE == 1 && pend_flag != 0.f) || isnan(sm.act(e)[0]));
+  const bool pending = valid && ((MODE >= 1 && pend_flag != 0.f) || isnan(sm.act(e)[0]));
   if (valid && pending) {
     if (role == 0) { a.reward[i] = 0.f; a.done[i] = 0; }
     if (a.terms)
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     for (int m = 0; m < NJ; m++) act[m] = sm.act(e)[m];
     set_torques(sm, e, tid, role, sm.act(e), nullptr);
     __syncwarp(qm);
-    if (MODE == 1) {
+    if (MODE >= 1) {
       // (Q13) robot_pos is refreshed from the PREVIOUS calc_state at the top of step()
       chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);
       stale_x = (32.f * b.p[0] + sumx) * (1.f / 33.f);
@@ -252,7 +257,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
 #pragma unroll
       for (int k = 0; k < ILRL_ENV_WORDS; k++) w.e[k] = ew[(size_t)k * a.n];
     }
-    if (MODE == 1) {
+    if (MODE >= 1) {
       w.e[ILRL_E_ROBOT_X] = stale_x; w.e[ILRL_E_ROBOT_Y] = stale_y;
       w.e[ILRL_E_STEPS_REMAINING] -= 1.f;
     }
@@ -264,8 +269,14 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     calc_state(ps, sumx, sumy, w.e[ILRL_E_WALK_X], w.e[ILRL_E_WALK_Y], c);
     w.e[ILRL_E_OBS_SIN] = c.obs[1]; w.e[ILRL_E_OBS_COS] = c.obs[2];
     if (MODE == 0) { w.e[ILRL_E_ROBOT_X] = c.bx; w.e[ILRL_E_ROBOT_Y] = c.by; }
-    float reward = update_reward<MODE>(ps, c, w, cl, act, terms);
-    inc_frame(w, cl, a.skip_frame);
+    float jt[MODE == 2 ? ILRL_JT_WORDS : 1];
+    if (MODE == 2) {
+#pragma unroll
+      for (int k = 0; k < ILRL_JT_WORDS; k++) jt[k] = a.jt[(size_t)k * a.n + i];
+    }
+    float reward;
+    if constexpr (MODE == 2) reward = update_reward2(c, w, jt, act, terms);   // (no frame advance in hier_env_2's low step)
+    else { reward = update_reward<MODE>(ps, c, w, cl, act, terms); inc_frame(w, cl, a.skip_frame); }
     uint32_t ctr = a.rng[i];
     int deg;
     if (a.forced_deg && a.forced_deg[i] != INT_MIN) deg = a.forced_deg[i];
@@ -278,7 +289,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
       if (dist <= (float)ILRL_TARGET_REACHED) ctr = c2;
     }
     check_target<MODE>(c, w, deg);
-    terms[ILRL_T_LOWTARGET] = w.e[ILRL_E_LOW_TARGET_SCORE];
+    if (MODE != 2) terms[ILRL_T_LOWTARGET] = w.e[ILRL_E_LOW_TARGET_SCORE];
     bool done = check_done<MODE>(w, terms[ILRL_T_ALIVE]);
     w.e[ILRL_E_T] += 1.f;
     if (w.e[ILRL_E_T] >= (float)a.max_timestep) done = true;
@@ -286,22 +297,28 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     w.e[ILRL_E_EP_LEN] += 1.f;
     float* so = &sm.scr[e][0];  // the env's scratch block is free after the substeps: stage the obs row there
     {
-      float obs[70];
-      write_low_obs(c.obs, w, cl, obs);
+      float obs[OBSW];
+      if constexpr (MODE == 2) write_low_obs2(c.obs, jt, obs); else write_low_obs(c.obs, w, cl, obs);
 #pragma unroll
-      for (int t = 0; t < 70; t++) if ((t & 3) == role) so[t] = obs[t];
+      for (int t = 0; t < OBSW; t++) if ((t & 3) == role) so[t] = obs[t];
     }
     write_obs = true;
     uint8_t hflags = 0;
-    if (MODE == 1) {
+    if (MODE >= 1) {
       if (done || w.e[ILRL_E_STEPS_REMAINING] <= 0.f) {
-        update_reward_high(w, terms, a.step_per_level);
-        if (role == 0) a.high_reward[i] = terms[ILRL_T_DHIGHTARGET] * 0.3f + terms[ILRL_T_DRIFT] * 0.7f;
-        float ho[44];
-        write_high_obs(c, w, ho);
+        float ho[HOBSW], hr;
+        if constexpr (MODE == 2) {
+          hr = update_reward_high2(ps, c, w, cl, terms, a.step_per_level);
+          write_high_obs2(c, w, cl, ho);
+        } else {
+          update_reward_high(w, terms, a.step_per_level);
+          hr = terms[ILRL_T_DHIGHTARGET] * 0.3f + terms[ILRL_T_DRIFT] * 0.7f;
+          write_high_obs(c, w, ho);
+          w.e[ILRL_E_CUM_ALIVE] = 0.f;
+        }
+        if (role == 0) a.high_reward[i] = hr;
 #pragma unroll
-        for (int t = 0; t < 44; t++) if ((t & 3) == role) a.high_obs[(size_t)i * 44 + t] = ho[t];
-        w.e[ILRL_E_CUM_ALIVE] = 0.f;
+        for (int t = 0; t < HOBSW; t++) if ((t & 3) == role) a.high_obs[(size_t)i * HOBSW + t] = ho[t];
         hflags = done ? 3 : 2;
         if (!done) { w.e[ILRL_E_HIGH_PENDING] = 1.f; hflags |= 4; }
       }
@@ -321,29 +338,37 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
       if (role == 0) { st_ep = 1.f; st_ret = w.e[ILRL_E_EP_RETURN]; st_len = w.e[ILRL_E_EP_LEN]; }
       if (a.auto_reset) {
         int sf = rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, 0, cl.max_frame - 5);
-        float yaw = MODE == 1 ? (float)rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180) : 0.f;
+        float yaw = MODE >= 1 ? (float)rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180) : 0.f;
         int tdeg = rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180);
+        float noise[MODE == 2 ? NJ : 1];
+        if (MODE == 2) {
+          draw_reset_noise(a.seed, (uint32_t)(i + a.id_base), ctr, noise);
+          if (a.forced_noise) {
+#pragma unroll
+            for (int j = 0; j < NJ; j++) noise[j] = a.forced_noise[(size_t)i * NJ + j];
+          }
+        }
         ResetCtx rx;
-        reset_pose<MODE>(ps, w, cl, sf, yaw, tdeg, rx);
+        reset_pose<MODE>(ps, w, cl, sf, yaw, tdeg, rx, nullptr, MODE == 2 ? noise : nullptr);
         chain::scatter(ps, sm, e, qb, role, qm, b);
         chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);
         reset_finish<MODE>(ps, w, cl, rx, rfx, rfy, sumx, sumy, a.step_per_level, a.skip_frame, c);
-        if (MODE == 0) {
+        if constexpr (MODE == 0) {
           float obs[70];
           write_low_obs(c.obs, w, cl, obs);
 #pragma unroll
           for (int t = 0; t < 70; t++) if ((t & 3) == role) so[t] = obs[t];
         } else {
-          float ho[44];
-          write_high_obs(c, w, ho);
+          float ho[HOBSW];
+          if constexpr (MODE == 2) write_high_obs2(c, w, cl, ho); else write_high_obs(c, w, ho);
 #pragma unroll
-          for (int t = 0; t < 44; t++) if ((t & 3) == role) a.high_obs[(size_t)i * 44 + t] = ho[t];
+          for (int t = 0; t < HOBSW; t++) if ((t & 3) == role) a.high_obs[(size_t)i * HOBSW + t] = ho[t];
           hflags |= 4;
         }
       }
     }
     if (role == 0) {
-      if (MODE == 1) a.high_flags[i] = hflags;
+      if (MODE >= 1) a.high_flags[i] = hflags;
       a.rng[i] = ctr;
     }
     chain::store_phys(a.phys, a.n, i, role, ps);
@@ -358,12 +383,12 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   {
     const unsigned okmask = __ballot_sync(0xffffffffu, write_obs);   // (includes the staging writes' __syncwarp)
     const int e0 = e & ~7, lane = tid & 31;
-    float* orow = a.obs + (size_t)(base + e0) * 70;
+    float* orow = a.obs + (size_t)(base + e0) * OBSW;
 #pragma unroll 1
-    for (int f = lane; f < 8 * 35; f += 32) {
-      const int r = f / 35, c2 = f - r * 35;
+    for (int f = lane; f < 8 * (OBSW / 2); f += 32) {
+      const int r = f / (OBSW / 2), c2 = f - r * (OBSW / 2);
       if ((okmask >> (4 * r)) & 1u)
-        *reinterpret_cast<float2*>(orow + r * 70 + 2 * c2) = *reinterpret_cast<const float2*>(&sm.scr[e0 + r][2 * c2]);
+        *reinterpret_cast<float2*>(orow + r * OBSW + 2 * c2) = *reinterpret_cast<const float2*>(&sm.scr[e0 + r][2 * c2]);
     }
   }
   // K5: episode / reward statistics -> one atomicAdd per warp per slot
@@ -401,6 +426,7 @@ struct ResetArgs {
   uint64_t seed;
   float* phys; float* envf; uint32_t* rng;
   const uint8_t* mask; const int32_t* start_frame; const int32_t* target_deg; const float* yaw_deg; const float* target_xy;
+  const float* noise;   // [n,17] or null (MODE 2: joint noise of robot_specific_reset; null = drawn)
   float* obs;
   uint8_t* high_flags;
   ClipDesc clips[MAX_CLIPS];
@@ -418,12 +444,18 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const ResetArgs a) {
   const ClipDesc cl = a.clips[(int)w.e[ILRL_E_CLIP]];
   uint32_t ctr = a.rng[i];
   int sf = a.start_frame ? a.start_frame[i] : rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, 0, cl.max_frame - 5);
-  float yaw = a.yaw_deg ? a.yaw_deg[i] : (MODE == 1 ? (float)rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180) : 0.f);
+  float yaw = a.yaw_deg ? a.yaw_deg[i] : (MODE >= 1 ? (float)rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180) : 0.f);
   int tdeg = (a.target_deg || a.target_xy) ? (a.target_deg ? a.target_deg[i] : 0) : rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180);
   float txy[2] = {0.f, 0.f};
   if (a.target_xy) { txy[0] = a.target_xy[2 * i]; txy[1] = a.target_xy[2 * i + 1]; }
   Work k; Calc c;
-  reset_env<MODE>(s, w, cl, sf, yaw, tdeg, a.step_per_level, a.skip_frame, k, c, a.target_xy ? txy : nullptr);
+  float noise[NJ];
+  if (MODE == 2) {
+    draw_reset_noise(a.seed, (uint32_t)(i + a.id_base), ctr, noise);
+    if (a.noise) for (int j = 0; j < NJ; j++) noise[j] = a.noise[(size_t)i * NJ + j];
+  }
+  reset_env<MODE>(s, w, cl, sf, yaw, tdeg, a.step_per_level, a.skip_frame, k, c, a.target_xy ? txy : nullptr,
+                  MODE == 2 ? noise : nullptr);
   a.rng[i] = ctr;
   store_state(v, i, s, w);
   if (a.obs) {
@@ -431,35 +463,59 @@ __global__ void __launch_bounds__(BLOCK) reset_kernel(const ResetArgs a) {
       float o[70];
       write_low_obs(c.obs, w, cl, o);
       for (int t = 0; t < 70; t++) a.obs[(size_t)i * 70 + t] = o[t];
-    } else {
+    } else if (MODE == 1) {
       float o[44];
       write_high_obs(c, w, o);
       for (int t = 0; t < 44; t++) a.obs[(size_t)i * 44 + t] = o[t];
+    } else {
+      float o[ILRL_OBS_HIGH2];
+      write_high_obs2(c, w, cl, o);
+      for (int t = 0; t < ILRL_OBS_HIGH2; t++) a.obs[(size_t)i * ILRL_OBS_HIGH2 + t] = o[t];
     }
   }
-  if (MODE == 1 && a.high_flags) a.high_flags[i] = 4;
+  if (MODE >= 1 && a.high_flags) a.high_flags[i] = 4;
 }
 
 // ------------------------------------------------------------------------------------------------ K4: high-level step
 struct HighArgs {
-  int n; float step_per_level;
-  float* phys; float* envf;
-  const float* action2; float* low_obs;
+  int n; float step_per_level; int skip_frame;
+  float* phys; float* envf; float* jt;
+  const float* action2; float* low_obs;   // MODE 1: [n,2] / [n,70]; MODE 2: [n,36] / [n,72]
   ClipDesc clips[MAX_CLIPS];
 };
+template <int MODE>
 __global__ void __launch_bounds__(BLOCK) high_step_kernel(const HighArgs a) {
+  constexpr int AW = MODE == 2 ? ILRL_ACT_HIGH2 : ILRL_ACT_HIGH;
   const int i = blockIdx.x * BLOCK + threadIdx.x;
   if (i >= a.n) return;
   StepArgs v; v.n = a.n; v.phys = a.phys; v.envf = a.envf;
   Phys s; EnvW w;
   load_state(v, i, s, w);
-  if (w.e[ILRL_E_HIGH_PENDING] == 0.f || isnan(a.action2[2 * i])) return;  // not waiting / no action in this call
+  if (w.e[ILRL_E_HIGH_PENDING] == 0.f || isnan(a.action2[AW * i])) return;  // not waiting / no action in this call
   const ClipDesc cl = a.clips[(int)w.e[ILRL_E_CLIP]];
   Work k; Calc c;
   fk(s, k);
   calc_state(s, k.sumx, k.sumy, w.e[ILRL_E_WALK_X], w.e[ILRL_E_WALK_Y], c);
   c.obs[1] = w.e[ILRL_E_OBS_SIN]; c.obs[2] = w.e[ILRL_E_OBS_COS];  // cur_obs predates the walk-target change below
   w.e[ILRL_E_ROBOT_X] = c.bx; w.e[ILRL_E_ROBOT_Y] = c.by;
+  if constexpr (MODE == 2) {
+    // REF hier_env_2.py:699-741: the action's tail becomes the joint targets, the frame advances, nothing else changes
+    float jt[ILRL_JT_WORDS];
+    for (int t = 0; t < ILRL_JT_WORDS; t++) {
+      jt[t] = a.action2[(size_t)AW * i + 2 + t];
+      a.jt[(size_t)t * a.n + i] = jt[t];
+    }
+    w.e[ILRL_E_STEPS_REMAINING] = a.step_per_level;
+    w.e[ILRL_E_HIGH_PENDING] = 0.f;
+    inc_frame<2>(w, cl, a.skip_frame);
+    float o[ILRL_OBS_LOW2];
+    write_low_obs2(c.obs, jt, o);
+    for (int t = 0; t < ILRL_OBS_LOW2; t++) a.low_obs[(size_t)i * ILRL_OBS_LOW2 + t] = o[t];
+    float* e = a.envf + i;
+#pragma unroll
+    for (int kk = 0; kk < ILRL_ENV_WORDS; kk++) e[kk * a.n] = w.e[kk];
+    return;
+  }
   const float R2D = 57.29577951308232f, D2R = 0.017453292519943295f;
   float ndeg = atan2f(a.action2[2 * i + 1], a.action2[2 * i]) * R2D + c.yaw * R2D;
   float h = ndeg * D2R, sh, ch;
@@ -495,6 +551,15 @@ __global__ void state_set_kernel(StateView v, const float* phys_aos, const float
   if (i >= v.n) return;
   if (phys_aos) for (int k = 0; k < ILRL_PHYS_WORDS; k++) v.phys[(size_t)k * v.n + i] = phys_aos[(size_t)i * ILRL_PHYS_WORDS + k];
   if (envf_aos) for (int k = 0; k < ILRL_ENV_WORDS; k++) v.envf[(size_t)k * v.n + i] = envf_aos[(size_t)i * ILRL_ENV_WORDS + k];
+}
+// jointTarget [34][n] <-> caller's [n,34] (exactly one of out / in is non-null)
+__global__ void jt_copy_kernel(int n, float* jt, float* out, const float* in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  for (int k = 0; k < ILRL_JT_WORDS; k++) {
+    if (out) out[(size_t)i * ILRL_JT_WORDS + k] = jt[(size_t)k * n + i];
+    else jt[(size_t)k * n + i] = in[(size_t)i * ILRL_JT_WORDS + k];
+  }
 }
 __global__ void clip_ids_kernel(StateView v, const int32_t* ids) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -604,9 +669,11 @@ __global__ void gae_decisions_kernel(const float* __restrict__ rew, const uint8_
   }
 }
 // everything a reference-shaped env object mirrors after a call, one packed row per env (ILRL_PULL_* layout of ilrl.h):
-// obs 70 | reward | done | terms 12 | envf 28 | phys 47 | high obs 44 | high reward | high flags
+// obs 72 | reward | done | terms 12 | envf 28 | phys 47 | high obs 60 | high reward | high flags | jointTarget 34
+// (modes 0 / 1 fill 70 / 44 of the obs columns, the rest is 0)
 struct PullArgs {
-  int n;
+  int n, obs_w, hobs_w;
+  const float* jt;
   const float *obs, *reward, *terms, *phys, *envf, *high_obs, *high_reward;
   const uint8_t *done, *high_flags;
   float* out;
@@ -616,23 +683,24 @@ __global__ void pull_kernel(const PullArgs a) {
   float* o = a.out + (size_t)i * ILRL_PULL_WORDS;
   for (int t = threadIdx.x; t < ILRL_PULL_WORDS; t += blockDim.x) {
     float v;
-    if (t < 70) v = a.obs[(size_t)i * 70 + t];
-    else if (t == 70) v = a.reward[i];
-    else if (t == 71) v = (float)a.done[i];
-    else if (t < 84) v = a.terms[(size_t)i * ILRL_TERM_WORDS + (t - 72)];
-    else if (t < 112) v = a.envf[(size_t)(t - 84) * a.n + i];
-    else if (t < 159) v = a.phys[(size_t)(t - 112) * a.n + i];
-    else if (t < 203) v = a.high_obs[(size_t)i * 44 + (t - 159)];
-    else if (t == 203) v = a.high_reward[i];
-    else v = (float)a.high_flags[i];
+    if (t < 72) v = t < a.obs_w ? a.obs[(size_t)i * a.obs_w + t] : 0.f;
+    else if (t == 72) v = a.reward[i];
+    else if (t == 73) v = (float)a.done[i];
+    else if (t < 86) v = a.terms[(size_t)i * ILRL_TERM_WORDS + (t - 74)];
+    else if (t < 114) v = a.envf[(size_t)(t - 86) * a.n + i];
+    else if (t < 161) v = a.phys[(size_t)(t - 114) * a.n + i];
+    else if (t < 221) v = (t - 161) < a.hobs_w ? a.high_obs[(size_t)i * a.hobs_w + (t - 161)] : 0.f;
+    else if (t == 221) v = a.high_reward[i];
+    else if (t == 222) v = (float)a.high_flags[i];
+    else v = a.jt ? a.jt[(size_t)(t - 223) * a.n + i] : 0.f;
     o[t] = v;
   }
 }
 // the high-level agent's outputs kept in the handle -> caller buffers (any of them may be null): one launch
-__global__ void high_readout_kernel(int n, const float* __restrict__ obs, const float* __restrict__ rew,
+__global__ void high_readout_kernel(int n, int hobs_w, const float* __restrict__ obs, const float* __restrict__ rew,
                                     const uint8_t* __restrict__ flags, float* obs_out, float* rew_out, uint8_t* flags_out) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (obs_out && t < 44 * n) obs_out[t] = obs[t];
+  if (obs_out && t < hobs_w * n) obs_out[t] = obs[t];
   if (t < n) {
     if (rew_out) rew_out[t] = rew[t];
     if (flags_out) flags_out[t] = flags[t];
@@ -657,6 +725,9 @@ struct ilrl_env {
   float* envf = nullptr;
   uint32_t* rng = nullptr;
   float* gscr = nullptr;
+  float* jt = nullptr;                    // [34][n] jointTarget (mode 2 only)
+  const float* forced_noise = nullptr;    // ilrl_set_forced_reset_noise
+  int obs_w = ILRL_OBS_LOW, hobs_w = ILRL_OBS_HIGH, hact_w = ILRL_ACT_HIGH;   // row widths of the mode
   float* high_obs = nullptr;
   float* high_reward = nullptr;
   uint8_t* high_flags = nullptr;
@@ -726,7 +797,7 @@ const char* ilrl_last_error(const ilrl_env* env) { return env ? env->err.c_str()
 int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   ilrl_env* env = nullptr;
   if (!cfg || !out) return fail(nullptr, ILRL_ERR_ARG, "ilrl_create: null argument");
-  if (cfg->num_envs <= 0 || (cfg->mode != 0 && cfg->mode != 1)) return fail(nullptr, ILRL_ERR_ARG, "ilrl_create: bad num_envs/mode");
+  if (cfg->num_envs <= 0 || cfg->mode < 0 || cfg->mode > 2) return fail(nullptr, ILRL_ERR_ARG, "ilrl_create: bad num_envs/mode");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0)
     return fail(nullptr, ILRL_ERR_CUDA, "ilrl_create: no CUDA device (this library has no CPU path)");
@@ -736,9 +807,11 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   env = new (std::nothrow) ilrl_env();
   if (!env) return fail(nullptr, ILRL_ERR_ARG, "ilrl_create: out of host memory");
   env->cfg = *cfg;
-  if (env->cfg.skip_frame <= 0) env->cfg.skip_frame = 2;
+  const bool m2 = cfg->mode == 2;   // hier_env_2.py:58-63, 160: step_per_level 20, skipFrame 5
+  if (env->cfg.skip_frame <= 0) env->cfg.skip_frame = m2 ? 5 : 2;
   if (env->cfg.max_timestep <= 0) env->cfg.max_timestep = 3000;
-  if (env->cfg.step_per_level <= 0) env->cfg.step_per_level = 5;
+  if (env->cfg.step_per_level <= 0) env->cfg.step_per_level = m2 ? 20 : 5;
+  if (m2) { env->obs_w = ILRL_OBS_LOW2; env->hobs_w = ILRL_OBS_HIGH2; env->hact_w = ILRL_ACT_HIGH2; }
   const int n = env->n = cfg->num_envs;
   memset(env->clips, 0, sizeof env->clips);
 #define CKC(call)                                                                              \
@@ -756,6 +829,9 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMalloc(&env->gscr, sizeof(float) * (size_t)chain::GROWS * chain::RW * n));
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
   CKC(cudaFuncSetAttribute(step_kernel<1, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
+  CKC(cudaFuncSetAttribute(step_kernel<2, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
+  CKC(cudaFuncSetAttribute(step_kernel<2, SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
+  CKC(cudaFuncSetAttribute(step_kernel<2, SmemDense4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDense4)));
   CKC(cudaFuncSetAttribute(physics_only_kernel<SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(step_kernel<1, SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
@@ -783,10 +859,14 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
       CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], step_kernel<0, SmemSmall>, QT, sizeof(SmemSmall)));
       CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], step_kernel<0, SmemLarge>, QT, sizeof(SmemLarge)));
       CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], step_kernel<0, SmemDense4>, QT, sizeof(SmemDense4)));
-    } else {
+    } else if (cfg->mode == 1) {
       CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], step_kernel<1, SmemSmall>, QT, sizeof(SmemSmall)));
       CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], step_kernel<1, SmemLarge>, QT, sizeof(SmemLarge)));
       CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], step_kernel<1, SmemDense4>, QT, sizeof(SmemDense4)));
+    } else {
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], step_kernel<2, SmemSmall>, QT, sizeof(SmemSmall)));
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], step_kernel<2, SmemLarge>, QT, sizeof(SmemLarge)));
+      CKC(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], step_kernel<2, SmemDense4>, QT, sizeof(SmemDense4)));
     }
     if (occ[0] < 1 || occ[1] < 1 || occ[2] < 1) { g_create_err = "step kernel does not fit on this device"; ilrl_destroy(env); return ILRL_ERR_CUDA; }
     env->grid_small = occ[0] * prop.multiProcessorCount;
@@ -808,7 +888,11 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
       }
     }
   }
-  CKC(cudaMalloc(&env->high_obs, sizeof(float) * 44 * n));
+  CKC(cudaMalloc(&env->high_obs, sizeof(float) * env->hobs_w * n));
+  if (m2) {
+    CKC(cudaMalloc(&env->jt, sizeof(float) * ILRL_JT_WORDS * n));
+    CKC(cudaMemset(env->jt, 0, sizeof(float) * ILRL_JT_WORDS * n));   // self.jointTarget = [0] * 16 (hier_env_2.py:172)
+  }
   CKC(cudaMalloc(&env->high_reward, sizeof(float) * n));
   CKC(cudaMalloc(&env->high_flags, n));
   CKC(cudaMalloc(&env->stats, sizeof(double) * ILRL_STATS_WORDS));
@@ -817,7 +901,7 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMemset(env->phys, 0, sizeof(float) * ILRL_PHYS_WORDS * n));
   CKC(cudaMemset(env->envf, 0, sizeof(float) * ILRL_ENV_WORDS * n));
   CKC(cudaMemset(env->rng, 0, sizeof(uint32_t) * n));
-  CKC(cudaMemset(env->high_obs, 0, sizeof(float) * 44 * n));
+  CKC(cudaMemset(env->high_obs, 0, sizeof(float) * env->hobs_w * n));
   CKC(cudaMemset(env->high_reward, 0, sizeof(float) * n));
   CKC(cudaMemset(env->high_flags, 0, n));
   CKC(cudaMemset(env->stats, 0, sizeof(double) * ILRL_STATS_WORDS));
@@ -842,7 +926,7 @@ void ilrl_destroy(ilrl_env* env) {
   cudaFree(env->clip_ids_dev);
   cudaFreeHost(env->h_pull);
   cudaFree(env->ktime);
-  cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr);
+  cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr); cudaFree(env->jt);
   cudaFree(env->high_obs); cudaFree(env->high_reward); cudaFree(env->high_flags); cudaFree(env->stats); cudaFree(env->tile_counter);
   for (int c = 0; c < MAX_CLIPS; c++) cudaFree(env->clip_mem[c]);
   cudaFreeHost(env->h_action); cudaFreeHost(env->h_obs); cudaFreeHost(env->h_reward); cudaFreeHost(env->h_terms);
@@ -913,11 +997,13 @@ int ilrl_reset(ilrl_env* env, const uint8_t* mask, const int32_t* start_frame, c
   a.n = env->n; a.skip_frame = env->cfg.skip_frame; a.id_base = env->cfg.env_id_base; a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
   a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
   a.mask = mask; a.start_frame = start_frame; a.target_deg = target_deg; a.yaw_deg = yaw_deg; a.target_xy = target_xy; a.obs = obs;
+  a.noise = env->forced_noise;
   a.high_flags = env->high_flags;
   memcpy(a.clips, env->clips, sizeof a.clips);
   cudaStream_t st = (cudaStream_t)stream;
   if (env->cfg.mode == 0) reset_kernel<0><<<nblk(env->n), BLOCK, 0, st>>>(a);
-  else reset_kernel<1><<<nblk(env->n), BLOCK, 0, st>>>(a);
+  else if (env->cfg.mode == 1) reset_kernel<1><<<nblk(env->n), BLOCK, 0, st>>>(a);
+  else reset_kernel<2><<<nblk(env->n), BLOCK, 0, st>>>(a);
   env->launches++;
   CK(cudaGetLastError());
   return ILRL_OK;
@@ -939,6 +1025,7 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.terms = terms;
   a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
   a.forced_deg = env->forced_deg; a.forced_scalar = forced_scalar; a.stats = env->stats; a.gscr = env->gscr;
+  a.jt = env->jt; a.forced_noise = env->forced_noise;
   a.tile_counter = env->tile_counter + 2 * (part + 1);
 #ifdef ILRL_PROF
   a.prof = env->prof;
@@ -947,15 +1034,19 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   a.ktime = (env->timing && env->kt_used < KT_SLOTS) ? env->ktime + 2 * (size_t)env->kt_used++ : nullptr;
   a.ntiles = (count + QE - 1) / QE;
   const int qblk = min(a.ntiles, env->layout == 2 ? env->grid_dense4 : env->layout == 1 ? env->grid_large : env->grid_small);
+  const int md = env->cfg.mode;
   if (env->layout == 2) {
-    if (env->cfg.mode == 0) step_kernel<0, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
-    else step_kernel<1, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
+    if (md == 0) step_kernel<0, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
+    else if (md == 1) step_kernel<1, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
+    else step_kernel<2, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
   } else if (env->layout == 1) {
-    if (env->cfg.mode == 0) step_kernel<0, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
-    else step_kernel<1, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
+    if (md == 0) step_kernel<0, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
+    else if (md == 1) step_kernel<1, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
+    else step_kernel<2, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
   } else {
-    if (env->cfg.mode == 0) step_kernel<0, SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a);
-    else step_kernel<1, SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a);
+    if (md == 0) step_kernel<0, SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a);
+    else if (md == 1) step_kernel<1, SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a);
+    else step_kernel<2, SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a);
   }
   env->launches++;
   CK(cudaGetLastError());
@@ -1016,7 +1107,7 @@ int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* re
   }
   if (!env->h_action) {  // staging buffers: pinned host mirrors + device I/O, allocated on first use
     CK(cudaMallocHost(&env->h_action, sizeof(float) * 17 * n));
-    CK(cudaMallocHost(&env->h_obs, sizeof(float) * 70 * n));
+    CK(cudaMallocHost(&env->h_obs, sizeof(float) * env->obs_w * n));
     CK(cudaMallocHost(&env->h_reward, sizeof(float) * n));
     CK(cudaMallocHost(&env->h_terms, sizeof(float) * ILRL_TERM_WORDS * n));
     CK(cudaMallocHost(&env->h_done, n));
@@ -1034,13 +1125,13 @@ int ilrl_step_host(ilrl_env* env, const float* action_h, float* obs_h, float* re
   CK(cudaMemcpyAsync(env->d_action, pa ? action_h : env->h_action, sizeof(float) * 17 * n, cudaMemcpyHostToDevice, st));
   int r = do_step(env, env->d_action, env->d_obs, env->d_reward, env->d_done, terms_h ? env->d_terms : nullptr, st, 0);
   if (r) return r;
-  CK(cudaMemcpyAsync(po ? obs_h : env->h_obs, env->d_obs, sizeof(float) * 70 * n, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(po ? obs_h : env->h_obs, env->d_obs, sizeof(float) * env->obs_w * n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(pr ? reward_h : env->h_reward, env->d_reward, sizeof(float) * n, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(pd ? done_h : env->h_done, env->d_done, n, cudaMemcpyDeviceToHost, st));
   if (terms_h)
     CK(cudaMemcpyAsync(pt ? terms_h : env->h_terms, env->d_terms, sizeof(float) * ILRL_TERM_WORDS * n, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  if (!po) memcpy(obs_h, env->h_obs, sizeof(float) * 70 * n);
+  if (!po) memcpy(obs_h, env->h_obs, sizeof(float) * env->obs_w * n);
   if (!pr) memcpy(reward_h, env->h_reward, sizeof(float) * n);
   if (!pd) memcpy(done_h, env->h_done, n);
   if (terms_h && !pt) memcpy(terms_h, env->h_terms, sizeof(float) * ILRL_TERM_WORDS * n);
@@ -1111,11 +1202,11 @@ static int ensure_io_buffers(ilrl_env* env) {
   const size_t n = env->n;
   if (!env->d_action) {
     CK(cudaMalloc(&env->d_action, sizeof(float) * 17 * n));
-    CK(cudaMalloc(&env->d_obs, sizeof(float) * 70 * n));
+    CK(cudaMalloc(&env->d_obs, sizeof(float) * env->obs_w * n));
     CK(cudaMalloc(&env->d_reward, sizeof(float) * n));
     CK(cudaMalloc(&env->d_terms, sizeof(float) * ILRL_TERM_WORDS * n));
     CK(cudaMalloc(&env->d_done, n));
-    CK(cudaMemset(env->d_obs, 0, sizeof(float) * 70 * n));
+    CK(cudaMemset(env->d_obs, 0, sizeof(float) * env->obs_w * n));
     CK(cudaMemset(env->d_reward, 0, sizeof(float) * n));
     CK(cudaMemset(env->d_terms, 0, sizeof(float) * ILRL_TERM_WORDS * n));
     CK(cudaMemset(env->d_done, 0, n));
@@ -1131,6 +1222,7 @@ static int do_pull(ilrl_env* env, float* pull_host, const float* obs_dev, cudaSt
   a.n = env->n; a.obs = obs_dev ? obs_dev : env->d_obs; a.reward = env->d_reward; a.terms = env->d_terms; a.done = env->d_done;
   a.phys = env->phys; a.envf = env->envf; a.high_obs = env->high_obs; a.high_reward = env->high_reward;
   a.high_flags = env->high_flags; a.out = env->h_pull_dev;
+  a.obs_w = env->obs_w; a.hobs_w = env->hobs_w; a.jt = env->jt;
   pull_kernel<<<env->n, 64, 0, st>>>(a);
   env->launches++;
   CK(cudaGetLastError());
@@ -1170,15 +1262,17 @@ int ilrl_set_config(ilrl_env* env, int32_t max_timestep, int32_t step_per_level,
 
 int ilrl_high_step(ilrl_env* env, const float* action2, float* low_obs, void* stream) {
   if (!env) return ILRL_ERR_ARG;
-  if (env->cfg.mode != 1) return fail(env, ILRL_ERR_ARG, "ilrl_high_step: handle is not in hier mode");
+  if (env->cfg.mode < 1) return fail(env, ILRL_ERR_ARG, "ilrl_high_step: handle is not in hier mode");
   if (!action2 || !low_obs) return fail(env, ILRL_ERR_ARG, "ilrl_high_step: null buffer");
   if (int r = check_ready(env)) return r;
   ON_DEVICE(env);
   HighArgs a;
-  a.n = env->n; a.step_per_level = (float)env->cfg.step_per_level; a.phys = env->phys; a.envf = env->envf;
+  a.n = env->n; a.step_per_level = (float)env->cfg.step_per_level; a.skip_frame = env->cfg.skip_frame;
+  a.phys = env->phys; a.envf = env->envf; a.jt = env->jt;
   a.action2 = action2; a.low_obs = low_obs;
   memcpy(a.clips, env->clips, sizeof a.clips);
-  high_step_kernel<<<nblk(env->n), BLOCK, 0, (cudaStream_t)stream>>>(a);
+  if (env->cfg.mode == 1) high_step_kernel<1><<<nblk(env->n), BLOCK, 0, (cudaStream_t)stream>>>(a);
+  else high_step_kernel<2><<<nblk(env->n), BLOCK, 0, (cudaStream_t)stream>>>(a);
   env->launches++;
   CK(cudaGetLastError());
   return ILRL_OK;
@@ -1186,10 +1280,10 @@ int ilrl_high_step(ilrl_env* env, const float* action2, float* low_obs, void* st
 
 int ilrl_high_readout(ilrl_env* env, float* high_obs, float* high_reward, uint8_t* high_flags, void* stream) {
   if (!env) return ILRL_ERR_ARG;
-  if (env->cfg.mode != 1) return fail(env, ILRL_ERR_ARG, "ilrl_high_readout: handle is not in hier mode");
+  if (env->cfg.mode < 1) return fail(env, ILRL_ERR_ARG, "ilrl_high_readout: handle is not in hier mode");
   ON_DEVICE(env);
-  const int words = 44 * env->n;
-  high_readout_kernel<<<(words + 255) / 256, 256, 0, (cudaStream_t)stream>>>(env->n, env->high_obs, env->high_reward, env->high_flags,
+  const int words = env->hobs_w * env->n;
+  high_readout_kernel<<<(words + 255) / 256, 256, 0, (cudaStream_t)stream>>>(env->n, env->hobs_w, env->high_obs, env->high_reward, env->high_flags,
                                                                            high_obs, high_reward, high_flags);
   env->launches++;
   CK(cudaGetLastError());
@@ -1215,6 +1309,30 @@ int ilrl_set_state(ilrl_env* env, const float* phys, const float* envf, void* st
 int ilrl_set_forced_target_deg(ilrl_env* env, const int32_t* deg) {
   if (!env) return ILRL_ERR_ARG;
   env->forced_deg = deg;
+  return ILRL_OK;
+}
+int ilrl_set_forced_reset_noise(ilrl_env* env, const float* noise17) {
+  if (!env) return ILRL_ERR_ARG;
+  if (env->cfg.mode != 2) return fail(env, ILRL_ERR_ARG, "ilrl_set_forced_reset_noise: only the hier_env_2 mode keeps reset noise");
+  env->forced_noise = noise17;
+  return ILRL_OK;
+}
+int ilrl_get_joint_target(ilrl_env* env, float* jt, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (env->cfg.mode != 2 || !jt) return fail(env, ILRL_ERR_ARG, "ilrl_get_joint_target: mode 2 handle and a buffer needed");
+  ON_DEVICE(env);
+  jt_copy_kernel<<<(env->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->n, env->jt, jt, nullptr);
+  env->launches++;
+  CK(cudaGetLastError());
+  return ILRL_OK;
+}
+int ilrl_set_joint_target(ilrl_env* env, const float* jt, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (env->cfg.mode != 2 || !jt) return fail(env, ILRL_ERR_ARG, "ilrl_set_joint_target: mode 2 handle and a buffer needed");
+  ON_DEVICE(env);
+  jt_copy_kernel<<<(env->n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(env->n, env->jt, nullptr, jt);
+  env->launches++;
+  CK(cudaGetLastError());
   return ILRL_OK;
 }
 int ilrl_physics_only(ilrl_env* env, const float* torque, void* stream) {

@@ -33,6 +33,7 @@
 /* ---- reference env constants */
 #define ILRL_INITIAL_Z       0.8             /* REF humanoid.py:49 */
 #define ILRL_RESET_Z         1.17            /* REF low_level_env.py:264, hier_env.py:266 */
+#define ILRL_RESET_Z_HIER2   1.15            /* REF hier_env_2.py:295 */
 #define ILRL_TARGET_LEN      5.0             /* REF low_level_env.py:155 */
 #define ILRL_ALIVE_Z         0.75            /* REF low_level_env.py:387 */
 #define ILRL_TARGET_REACHED  0.5             /* REF low_level_env.py:415 */
@@ -49,6 +50,17 @@
 #define ILRL_RW_LIMIT 0.15
 #define ILRL_RW_ALIVE 0.034
 #define ILRL_RW_POSTURE 0.1
+/* hier_env_2 (MODE 2): low-level reward REF hier_env_2.py:625-641 = sum(r * w) / 2 over [delta_deltaJoints (never
+ * written: 0), delta_deltaVelJoints (0), electricity, joint limit, alive, posture]; high-level reward :683-697 =
+ * sum / 3 over [delta_highTargetScore, driftScore, deltaJoints, deltaVelJoints, bodyPostureScore, mean deltaJoints_low,
+ * mean deltaVelJoints_low] */
+#define ILRL_RW2_ELEC 0.1
+#define ILRL_RW2_LIMIT 0.2
+#define ILRL_RW2_ALIVE 0.1
+#define ILRL_RW2_POSTURE 0.4
+#define ILRL_RW2_HIGH {0.3, 0.2, 1.0, 0.3, 0.2, 0.6, 0.4}
+#define ILRL_JOINT_W_SUM2    16.0            /* REF hier_env_2.py:104-114: the 8 leg joints, weights 3,1,3,1,3,1,3,1 */
+#define ILRL_JOINT_WV_SUM2   8.0             /* REF hier_env_2.py:116-126 */
 
 /* ---- flat state layouts shared by the C-ABI get/set_state calls, the oracle and the tests */
 #define ILRL_PHYS_WORDS 47   /* base pos3, quat4 (x,y,z,w), lin vel3, ang vel3 (world), q[17], qd[17] */
@@ -61,6 +73,10 @@ enum {
   ILRL_E_EP_RETURN, ILRL_E_EP_LEN,                      /* running episode return / length (statistics only) */
   ILRL_ENV_WORDS /* = 28 */
 };
+/* MODE 2 (hier_env_2.py) keeps two accumulators the other modes do not have in words it does not use otherwise:
+ * lowTargetScore is the constant -targetLen there (initReward, never updated) and there is no cumulative_aliveReward. */
+#define ILRL_E2_CUM_DV_LOW ILRL_E_LOW_TARGET_SCORE   /* cumulative_deltaVelJoints_low REF hier_env_2.py:622 */
+#define ILRL_E2_CUM_DJ_LOW ILRL_E_CUM_ALIVE          /* cumulative_deltaJoints_low    REF hier_env_2.py:621 */
 /* per-step "terms" row (the attributes RewardLogCallback reads, REF custom_callback.py:43-80) */
 enum {
   ILRL_T_JOINT = 0, ILRL_T_JVEL, ILRL_T_DLOWTARGET, ILRL_T_ELEC, ILRL_T_LIMIT, ILRL_T_ALIVE, ILRL_T_POSTURE,
@@ -68,9 +84,17 @@ enum {
   ILRL_T_DRIFT, ILRL_T_DHIGHTARGET /* delta_highTargetScore (baseReward is always 0: host side) */,
   ILRL_TERM_WORDS /* = 12 */
 };
+/* MODE 2: delta_lowTargetScore and deltaEndPoints are constant 0 in hier_env_2.py; their slots carry the two low-level
+ * tracking scores of calcJointPosVelLowScore (REF hier_env_2.py:461-474) */
+#define ILRL_T2_DJ_LOW ILRL_T_DLOWTARGET
+#define ILRL_T2_DV_LOW ILRL_T_ENDPOINT
 #define ILRL_OBS_LOW  70
 #define ILRL_OBS_HIGH 44
 #define ILRL_ACT_LOW  17
 #define ILRL_ACT_HIGH 2
+#define ILRL_OBS_LOW2  72   /* hier_env_2: cur_obs[1:3], [6:8], [8:42] + jointTarget[34]  REF hier_env_2.py:369-372 */
+#define ILRL_OBS_HIGH2 60   /* 44 + (rel, vel) of the 8 leg joints at the current frame   REF hier_env_2.py:374-406 */
+#define ILRL_ACT_HIGH2 36   /* 2 unused + jointTarget[34]                                 REF hier_env_2.py:54-56, 731 */
+#define ILRL_JT_WORDS  34
 #define ILRL_STATS_WORDS 16
 #endif

@@ -403,6 +403,8 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
         self.low_level_agent_id = "low_level_agent"
         self._make("hier", self.motion_list, self._selected_motion, device, seed)
 
+    _PO, _PH, _HACT = BatchedHumanoidEnv.PULL_OBS, BatchedHumanoidEnv.PULL_HIGH_OBS, 2   # packed-row columns / widths of the mode
+
     step_per_level = property(lambda self: self._step_per_level)
 
     @step_per_level.setter
@@ -466,11 +468,11 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
             self._push_env_words(E_HIGH_PENDING=1.0 if flag else 0.0)
 
     def high_level_step(self, action, debug=False):
-        a = np.asarray(action, dtype=np.float32).reshape(2)
+        a = np.asarray(action, dtype=np.float32).reshape(self._HACT)
         self._set_pending(True)   # the reference applies a high-level action whenever one arrives
         obs_dev = self._env.high_step(a[None, :])
         self._pull(obs_dev)
-        obs = self._row[BatchedHumanoidEnv.PULL_OBS].astype(np.float64)
+        obs = self._row[self._PO].astype(np.float64)
         self.num_high_level_steps += 1
         return {self.low_level_agent_id: obs}, {self.low_level_agent_id: 0}, {"__all__": False}, {}
 
@@ -482,7 +484,7 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
         old_target = self.target.copy()
         E = BatchedHumanoidEnv
         row = self._env.step_pull(a, deg)[0]
-        low_obs = row[E.PULL_OBS].astype(np.float64)
+        low_obs = row[self._PO].astype(np.float64)
         low_rew, high_rew = float(row[E.PULL_REWARD]), float(row[E.PULL_HIGH_REWARD])
         flags = int(row[E.PULL_HIGH_FLAGS])
         self._mirror(row, with_terms=True)
@@ -492,12 +494,12 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
         if ended:
             d["__all__"] = True
             r["high_level_agent"] = high_rew
-            o["high_level_agent"] = row[E.PULL_HIGH_OBS].astype(np.float64)
+            o["high_level_agent"] = row[self._PH].astype(np.float64)
             o[self.low_level_agent_id] = low_obs
             r[self.low_level_agent_id] = low_rew
         elif high_present:
             r["high_level_agent"] = high_rew
-            o["high_level_agent"] = row[E.PULL_HIGH_OBS].astype(np.float64)
+            o["high_level_agent"] = row[self._PH].astype(np.float64)
         else:
             o = {self.low_level_agent_id: low_obs}
             r = {self.low_level_agent_id: low_rew}
@@ -505,3 +507,67 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
             # REF hier_env.py:573-581: the debug rule ignores the distance test
             d["__all__"] = False
         return o, r, d, {}
+
+
+class HierarchicalHumanoidEnv2(HierarchicalHumanoidEnv):
+    """REF hier_env_2.py:39 (its class is also called HierarchicalHumanoidEnv): the variant whose high-level agent
+    hands the low level 17 (joint position, joint velocity) targets instead of a heading.  36-d high action, 60-d high
+    obs, 72-d low obs, step_per_level 20, skipFrame 5; the frame advances in reset and high_level_step only.
+    Declared substitutions: clips from "Joints CSV With Hand" (the reference reads an unshipped
+    Relative_Joints_CSV directory with the same file names) and the humanoid_symmetric_2.xml robot with the stock
+    class's 44-entry state (the reference builds pybullet_envs' stock Humanoid on the unshipped humanoid_symmetric.xml)."""
+
+    _PO, _PH, _HACT = BatchedHumanoidEnv.PULL_OBS2, BatchedHumanoidEnv.PULL_HIGH_OBS2, 36
+
+    def __init__(self, device=0, seed=None):
+        self.motion_list = ["motion08_03", "motion09_03"]
+        self.high_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[2 + 42 + 8 * 2])
+        self.high_level_act_space = Box(low=-1, high=1, shape=[2 + 17 * 2])
+        self.low_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[4 + 17 * 2 + 17 * 2])
+        self.low_level_act_space = Box(low=-1, high=1, shape=[17])
+        self._step_per_level = 20
+        self.steps_remaining_at_level = self._step_per_level
+        self.num_high_level_steps = 0
+        self.max_frame = [load_clip(m)["max_frame"] for m in self.motion_list]
+        self._selected_motion = 1
+        self.selected_motion_frame = 0
+        self.low_level_agent_id = "low_level_agent"
+        self.jointTarget = [0] * 16                                          # REF hier_env_2.py:172
+        self._make("hier2", self.motion_list, self._selected_motion, device, seed)
+        self._skip_frame = 5
+        legs = [k for k in JOINT_MAP if "knee" in k or "hip" in k]          # REF hier_env_2.py:90-126
+        self.joint_map = {k: JOINT_MAP[k] for k in legs}
+        self.joint_weight = {k: JOINT_WEIGHT[k] for k in legs}
+        self.joint_vel_weight = {k: 1 for k in legs}
+        self.joint_weight_sum = sum(self.joint_weight.values())
+        self.joint_vel_weight_sum = sum(self.joint_vel_weight.values())
+        self.cur_obs = np.zeros(44, np.float32)
+
+    def initReward(self):                                                    # REF hier_env_2.py:176-203
+        HierarchicalHumanoidEnv.initReward(self)
+        self.deltaJoints_low = self.deltaVelJoints_low = 0
+        self.lowTargetScore = self.highTargetScore = -5
+        self.cumulative_deltaJoints_low = self.cumulative_deltaVelJoints_low = 0
+
+    def _mirror(self, row, with_terms=False):
+        e = HierarchicalHumanoidEnv._mirror(self, row, with_terms)
+        # MODE 2 keeps its two accumulators in the words the other modes use for lowTargetScore / cumulative_aliveReward
+        self.cumulative_deltaVelJoints_low = float(e[B.E_LOW_TARGET_SCORE])
+        self.cumulative_deltaJoints_low = float(e[B.E_CUM_ALIVE])
+        self.lowTargetScore = -5
+        self.cumulative_aliveReward = 0
+        self.jointTarget = row[BatchedHumanoidEnv.PULL_JT].astype(np.float64)
+        if with_terms:   # slots 2 / 8 of the terms row carry the low-level tracking scores in this mode
+            t = row[BatchedHumanoidEnv.PULL_TERMS].astype(np.float64)
+            self.deltaJoints_low, self.deltaVelJoints_low = float(t[2]), float(t[8])
+            self.delta_lowTargetScore = self.deltaEndPoints = 0
+        return e
+
+    def reset(self, startFrame=None, startFromRef=True):                    # REF hier_env_2.py:254-262
+        sf = int(self.rng.integers(0, self.max_frame[self._selected_motion] - 5)) if startFrame is None else startFrame
+        yaw = int(self.rng.integers(-180, 180))
+        return self.resetFromFrame(startFrame=sf, resetYaw=yaw, startFromRef=True)
+
+    def resetFromFrame(self, startFrame=0, resetYaw=0, startFromRef=True):   # REF hier_env_2.py:277-352
+        return HierarchicalHumanoidEnv.resetFromFrame(self, startFrame=startFrame, resetYaw=resetYaw,
+                                                      startFromRef=startFromRef, initVel=True)

@@ -113,16 +113,18 @@ class HierBaseEnv(_RobotPosCache, _BaseEnv):
     """N `HierarchicalHumanoidEnv`s as one RLlib BaseEnv (async poll / send_actions protocol, agent ids
     "high_level_agent" / "low_level_agent").  Each env is either waiting for a heading from the high-level agent or
     for torques from the low-level one; both kinds advance in the same call: rows of agents that do not act are NaN
-    and the kernels skip them (include/ilrl.h)."""
+    and the kernels skip them (include/ilrl.h).  variant "hier2" = N envs of REF hier_env_2.py (36-d high action carrying
+    the joint targets, 60-d / 72-d observations)."""
 
-    def __init__(self, num_envs, device=0, seed=0, motion_list=("motion08_03", "motion09_03"), selected_motion=1):
+    def __init__(self, num_envs, device=0, seed=0, motion_list=("motion08_03", "motion09_03"), selected_motion=1,
+                 variant="hier"):
         self.num_envs = int(num_envs)
-        self.env = BatchedHumanoidEnv(num_envs, "hier", clips=list(motion_list),
+        self.env = BatchedHumanoidEnv(num_envs, variant, clips=list(motion_list),
                                       clip_of_env=np.full(num_envs, selected_motion, np.int32), device=device,
                                       seed=seed, auto_reset=False)
-        self.high_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[44])
-        self.high_level_act_space = Box(low=-1, high=1, shape=[2])
-        self.low_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[70])
+        self.high_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[self.env.hobs_w])
+        self.high_level_act_space = Box(low=-1, high=1, shape=[self.env.hact_w])
+        self.low_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[self.env.obs_w])
         self.low_level_act_space = Box(low=-1, high=1, shape=[17])
         self._terms_host = np.zeros((self.num_envs, B.TERM_WORDS), np.float32)
         self._robot_cache = None
@@ -141,7 +143,7 @@ class HierBaseEnv(_RobotPosCache, _BaseEnv):
     def send_actions(self, action_dict):
         n = self.num_envs
         low = np.full((n, 17), np.nan, np.float32)
-        high = np.full((n, 2), np.nan, np.float32)
+        high = np.full((n, self.env.hact_w), np.nan, np.float32)
         for i, acts in action_dict.items():
             assert len(acts) == 1, acts
             (agent, a), = acts.items()

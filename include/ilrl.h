@@ -4,6 +4,7 @@
  * observation that the reference reaches through
  *     LowLevelHumanoidEnv.{reset,resetFromFrame,step}          REF low_level_env.py:224-305, 322-323, 475-526
  *     HierarchicalHumanoidEnv.{reset,resetFromFrame,step}      REF hier_env.py:235-319, 355-366, 538-642
+ *     hier_env_2.HierarchicalHumanoidEnv.{reset,...,step}      REF hier_env_2.py:254-352, 408-419, 699-769  (mode 2)
  *     CustomHumanoidRobot.apply_action / calc_state            REF humanoid.py:54-60 (+ pybullet_envs WalkerBase)
  *     scene.global_step() -> pybullet.stepSimulation           REF low_level_env.py:479, hier_env.py:589
  * The reference has no FFI of its own (it is pure Python over pybullet's C extension); the entry points below are
@@ -20,6 +21,11 @@
  * Layouts: observations [N,70] (low) / [N,44] (high) row-major fp32, actions [N,17] / [N,2] fp32, reward [N] fp32,
  * done [N] uint8, terms [N,12] fp32 (ILRL_T_* order, ilrl_constants.h), phys [N,47] and envf [N,28] fp32
  * (ILRL_PHYS_WORDS / ILRL_E_* order).
+ * Mode 2 (hier_env_2.py: the high level hands the low level 17 joint (position, velocity) targets) has wider rows:
+ * low obs [N,72], high obs [N,60], high action [N,36] (2 unused + jointTarget[34]); everywhere below "[N,70]",
+ * "[N,44]" and "[N,2]" read as those widths for a mode-2 handle.  Its defaults are skip_frame 5, step_per_level 20.
+ * The reference's hier_env_2 reads a data directory and a robot MJCF it does not ship; the declared substitutions
+ * ("Joints CSV With Hand", humanoid_symmetric_2.xml) are stated in DESIGN.md section 4.
  */
 #ifndef ILRL_H
 #define ILRL_H
@@ -40,13 +46,13 @@ typedef enum {
 typedef struct {
   int32_t device;         /* CUDA ordinal */
   int32_t num_envs;       /* N */
-  int32_t mode;           /* 0 = LowLevelHumanoidEnv, 1 = HierarchicalHumanoidEnv */
+  int32_t mode;           /* 0 = LowLevelHumanoidEnv, 1 = HierarchicalHumanoidEnv (hier_env.py), 2 = hier_env_2.py variant */
   int32_t auto_reset;     /* 1: an env that finishes is reset inside the same step kernel (obs = first obs of the
                              new episode, done = 1); 0: the caller resets, as the reference env does (Q19) */
   uint64_t seed;          /* Philox key for start frames, headings and re-sampled targets */
-  int32_t skip_frame;     /* 2  REF low_level_env.py:162 */
+  int32_t skip_frame;     /* 2  REF low_level_env.py:162 (mode 2: 5, REF hier_env_2.py:160); <= 0 = the mode's default */
   int32_t max_timestep;   /* 3000 REF low_level_env.py:73 */
-  int32_t step_per_level; /* 5  REF hier_env.py:58 */
+  int32_t step_per_level; /* 5  REF hier_env.py:58 (mode 2: 20, REF hier_env_2.py:58); <= 0 = the mode's default */
   int32_t env_id_base;    /* global id of env 0 of this handle (0 on a single GPU).  The random draws of env i are a
                              function of (seed, env_id_base + i, draw index) only, so sharding a batch over GPUs with
                              the same seed does not change any env's trajectory */
@@ -113,12 +119,14 @@ int ilrl_wait_step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const
  * (frame, target, robot_pos, ...), the physics state and the high-level agent's outputs.  ilrl_step_pull does one
  * blocking step from HOST actions [N,17] and returns all of it as ONE packed host row per env (one launch for the step,
  * one for the packing, one synchronise; nothing else crosses the bus):
- *   [N][ILRL_PULL_WORDS] fp32 = obs 70 | reward | done | terms 12 | envf 28 | phys 47 | high obs 44 | high reward | flags
+ *   [N][ILRL_PULL_WORDS] fp32 = obs 72 | reward | done | terms 12 | envf 28 | phys 47 | high obs 60 | high reward | flags
+ *                               | jointTarget 34      (obs / high obs columns beyond the mode's width and, outside mode 2,
+ *                               the jointTarget columns are 0)
  * forced_target_deg: INT32_MIN, or the heading (integer degrees) every env uses if it re-samples its target in this step
  * (the N = 1 views draw it from the env object's own generator, as the reference does, REF low_level_env.py:240-245).
  * ilrl_pull packs the same row without stepping (after a reset or a high-level step); obs_dev NULL = the observation
  * of the last ilrl_step_pull, else a device [N,70] buffer to take the observation columns from. */
-#define ILRL_PULL_WORDS 205
+#define ILRL_PULL_WORDS 257
 int ilrl_step_pull(ilrl_env* env, const float* action_host, int32_t forced_target_deg, float* pull_host, void* stream);
 int ilrl_pull(ilrl_env* env, const float* obs_dev, float* pull_host, void* stream);
 
@@ -129,7 +137,8 @@ int ilrl_set_config(ilrl_env* env, int32_t max_timestep, int32_t step_per_level,
 
 /* hier mode: high-level agent's action (cos, sin of the heading) for every env that is waiting for one; the others
  * ignore their row, and so does a waiting env whose row starts with NaN.  low_obs_dev [N,70]: the low-level obs
- * the reference returns from high_level_step. */
+ * the reference returns from high_level_step.  Mode 2: action [N,36] whose columns 2..35 become the env's jointTarget
+ * (REF hier_env_2.py:731), low_obs_dev [N,72]; the frame advances by skip_frame here, not in the low-level step. */
 int ilrl_high_step(ilrl_env* env, const float* action2_dev, float* low_obs_dev, void* stream);
 /* hier mode: high-level obs [N,44], reward [N] and flags [N] (bit0 = episode ended this step, bit1 = high-level
  * agent present in the reference's returned dicts, bit2 = env is now waiting for a high-level action). */
@@ -142,6 +151,14 @@ int ilrl_set_state(ilrl_env* env, const float* phys_dev, const float* envf_dev, 
 /* Parity harness: the random heading the next target re-sampling uses, per env (INT32_MIN entry = draw normally);
  * NULL clears the override.  The pointer must stay valid until cleared. */
 int ilrl_set_forced_target_deg(ilrl_env* env, const int32_t* deg_dev);
+/* Mode 2 parity harness.  hier_env_2's reset leaves WalkerBase.robot_specific_reset's joint noise (uniform(-0.1, 0.1))
+ * in the six arm joints (its setJointsOrientation writes the abdomen and the legs only, REF hier_env_2.py:214-252).
+ * noise17_dev [N,17] (ordered_joints order; only the arm entries matter): used by ilrl_reset and auto-resets instead
+ * of the env's own draws; NULL = draw.  The pointer must stay valid until cleared. */
+int ilrl_set_forced_reset_noise(ilrl_env* env, const float* noise17_dev);
+/* Mode 2: read / overwrite the per-env jointTarget [N,34]. */
+int ilrl_get_joint_target(ilrl_env* env, float* jt_dev, void* stream);
+int ilrl_set_joint_target(ilrl_env* env, const float* jt_dev, void* stream);
 /* Parity harness (K3): everything ilrl_step does EXCEPT the physics, on the state currently held. */
 int ilrl_step_no_physics(ilrl_env* env, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                          float* terms_dev, void* stream);

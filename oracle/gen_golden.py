@@ -11,6 +11,9 @@
   hier_traj.npz             HierarchicalHumanoidEnv protocol trace with physics, 1000 low-level steps.
   hier_injected.npz         hier low/high steps on injected states, 2 x 400.
   reset_vectors.npz         resetFromFrame / reset outputs for fixed (start_frame, yaw, target) triples, low + hier.
+  hier2_injected.npz        REF hier_env_2.py (row a18) reset / high_level_step / low_level_step on injected states, under
+                            the two declared substitutions of ref_shim.make_hier2_env (data directory, robot stand-in).
+  hier2_traj.npz            hier_env_2 protocol trace with physics (reset -> high -> 20 low -> high ...), 600 low steps.
   notebook_vectors.json     the recorded cell outputs of "Eksplor Ray RLLib.ipynb" that pin layout facts.
 """
 import json
@@ -273,6 +276,120 @@ def gen_reset_vectors(seed=30):
     print("reset_vectors", out["obs"].shape)
 
 
+def _pad(v, n):
+    out = np.zeros(n)
+    if v is not None:
+        v = np.asarray(v, dtype=np.float64).ravel()
+        out[:len(v)] = v
+    return out
+
+
+def gen_hier2_injected(n=400, n_reset=48, seed=40):
+    rng = np.random.default_rng(seed)
+    env = S.make_hier2_env(seed=seed, physics="none")
+    env.reset()
+    mf = O.load_clip("motion09_03")["max_frame"]
+    K = ["kind", "phys", "env_before", "jt_before", "action", "rand_deg", "draws", "phys_after", "env_after", "jt_after",
+         "low_obs", "low_reward", "high_obs", "high_reward", "flags", "terms", "obs_sincos"]
+    rec = {k: [] for k in K}
+    for kind in (0, 1, 2):
+        for _ in range(n_reset if kind == 0 else n):
+            phys = random_phys(rng)
+            e = random_env_words(rng, phys, mf, hier=True)
+            e[21] = 1 if rng.uniform() < 0.3 else rng.integers(1, 21)
+            e[15] = rng.uniform(0, 10); e[24] = rng.uniform(0, 10)
+            e = f32(e)
+            jt = f32(rng.uniform(-1.5, 1.5, 34))
+            env.flat_env.phys[:] = phys
+            S.set_env_words2(env, e)
+            env.jointTarget = jt.copy()
+            env.aliveReward = 0
+            env.cur_obs = env.flat_env.robot.calc_state()   # also refreshes robot.body_xyz
+            sc = np.array(env.cur_obs[1:3], dtype=np.float64)
+            aa, deg, draws = np.zeros(36), -999, [0, 0, 0]
+            lo = lr = ho = hr = None
+            flags = 0
+            if kind == 0:
+                draws = [int(rng.integers(0, mf - 5)), int(rng.integers(-180, 180)), int(rng.integers(-180, 180))]
+                env.rng.forced = list(draws)
+                ho = env.reset()["high_level_agent"]
+            elif kind == 1:
+                aa = f32(rng.uniform(-1, 1, 36))
+                obs, rew, done, _ = env.step({"high_level_agent": aa})
+                assert list(obs) == ["low_level_agent"] and rew["low_level_agent"] == 0 and not done["__all__"]
+                lo = obs["low_level_agent"]
+            else:
+                aa[:17] = f32(rng.uniform(-1.3, 1.3, 17))
+                deg = int(rng.integers(-180, 180))
+                env.rng.forced = [deg]
+                obs, rew, done, _ = env.step({"low_level_agent": aa[:17].copy()})
+                deg = deg if len(env.rng.forced) == 0 else -999
+                env.rng.forced = []
+                has_high, has_low = "high_level_agent" in obs, "low_level_agent" in obs
+                flags = int(done["__all__"]) | (int(has_high) << 1) | (int(has_low) << 2)
+                lo, lr = obs.get("low_level_agent"), rew.get("low_level_agent")
+                ho, hr = obs.get("high_level_agent"), rew.get("high_level_agent")
+            rec["kind"].append(kind); rec["phys"].append(phys); rec["env_before"].append(e); rec["jt_before"].append(jt)
+            rec["action"].append(aa); rec["rand_deg"].append(deg); rec["draws"].append(draws)
+            rec["phys_after"].append(env.flat_env.phys.copy()); rec["env_after"].append(S.env_words2(env))
+            rec["jt_after"].append(np.asarray(env.jointTarget, dtype=np.float64))
+            rec["low_obs"].append(_pad(lo, 72)); rec["low_reward"].append(0.0 if lr is None else lr)
+            rec["high_obs"].append(_pad(ho, 60)); rec["high_reward"].append(0.0 if hr is None else hr)
+            rec["flags"].append(flags); rec["terms"].append(S.terms_of2(env)); rec["obs_sincos"].append(sc)
+    out = {k: np.array(v) for k, v in rec.items()}
+    np.savez_compressed(os.path.join(OUT, "hier2_injected.npz"), **out)
+    lowk = out["kind"] == 2
+    print("hier2_injected", out["phys"].shape, "low-step flags hist", np.bincount(out["flags"][lowk]), "switches",
+          int((out["rand_deg"] != -999).sum()))
+
+
+def gen_hier2_traj(low_steps=600, seed=41):
+    env = S.make_hier2_env(seed=seed, physics="oracle")
+    arng = np.random.default_rng(seed + 1)
+    K = ["kind", "phys_before", "env_before", "jt_before", "action", "rand_deg", "draws", "phys_after", "env_after",
+         "low_obs", "low_reward", "high_obs", "high_reward", "flags", "terms"]
+    rec = {k: [] for k in K}
+    n_low = 0
+    need_reset, need_high = True, False
+    while n_low < low_steps:
+        pb, eb, jb = env.flat_env.phys.copy(), S.env_words2(env), _pad(env.jointTarget, 34)
+        aa, deg, draws, flags = np.zeros(36), -999, [0, 0, 0], 0
+        lo = lr = ho = hr = None
+        if need_reset:
+            n0 = len(env.rng.log)
+            ho = env.reset()["high_level_agent"]
+            draws = env.rng.log[n0:n0 + 3]
+            kind, need_reset, need_high = 0, False, True
+        elif need_high:
+            aa = arng.uniform(-1, 1, 36)
+            obs, rew, done, _ = env.step({"high_level_agent": aa})
+            lo = obs["low_level_agent"]
+            kind, need_high = 1, False
+        else:
+            aa[:17] = arng.uniform(-1, 1, 17)
+            n0 = len(env.rng.log)
+            obs, rew, done, _ = env.step({"low_level_agent": aa[:17].copy()})
+            deg = env.rng.log[n0] if len(env.rng.log) > n0 else -999
+            has_high, has_low = "high_level_agent" in obs, "low_level_agent" in obs
+            flags = int(done["__all__"]) | (int(has_high) << 1) | (int(has_low) << 2)
+            lo, lr = obs.get("low_level_agent"), rew.get("low_level_agent")
+            ho, hr = obs.get("high_level_agent"), rew.get("high_level_agent")
+            kind = 2
+            n_low += 1
+            need_reset = done["__all__"]
+            need_high = has_high and not done["__all__"]
+        rec["kind"].append(kind); rec["phys_before"].append(pb); rec["env_before"].append(eb); rec["jt_before"].append(jb)
+        rec["action"].append(aa); rec["rand_deg"].append(deg); rec["draws"].append(list(draws))
+        rec["phys_after"].append(env.flat_env.phys.copy()); rec["env_after"].append(S.env_words2(env))
+        rec["low_obs"].append(_pad(lo, 72)); rec["low_reward"].append(0.0 if lr is None else lr)
+        rec["high_obs"].append(_pad(ho, 60)); rec["high_reward"].append(0.0 if hr is None else hr)
+        rec["flags"].append(flags); rec["terms"].append(S.terms_of2(env))
+    out = {k: np.array(v) for k, v in rec.items()}
+    np.savez_compressed(os.path.join(OUT, "hier2_traj.npz"), **out)
+    print("hier2_traj records", len(out["kind"]), "resets", int((out["kind"] == 0).sum()), "high", int((out["kind"] == 1).sum()),
+          "high outcomes", int(((out["flags"] & 2) != 0).sum()))
+
+
 def gen_notebook_vectors():
     nb = json.load(open(os.path.join(S.REF, "Eksplor Ray RLLib.ipynb")))
     found = {}
@@ -297,10 +414,12 @@ def gen_notebook_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["nb", "reset", "low_inj", "hier_inj", "low_traj", "hier_traj"]
+    which = sys.argv[1:] or ["nb", "reset", "low_inj", "hier_inj", "low_traj", "hier_traj", "hier2_inj", "hier2_traj"]
     if "nb" in which: gen_notebook_vectors()
     if "reset" in which: gen_reset_vectors()
     if "low_inj" in which: gen_low_injected()
     if "hier_inj" in which: gen_hier_injected()
     if "low_traj" in which: gen_low_traj()
     if "hier_traj" in which: gen_hier_traj()
+    if "hier2_inj" in which: gen_hier2_injected()
+    if "hier2_traj" in which: gen_hier2_traj()

@@ -182,12 +182,13 @@ class _Box:
 class FakeFlatEnv:
     """Stand-in for pybullet_envs.gym_locomotion_envs.HumanoidBulletEnv(robot=...)."""
     physics = "oracle"  # "oracle" -> C oracle physics; "none" -> global_step is a no-op (injected-state mode)
+    default_robot = None  # class used for HumanoidBulletEnv() without robot= (hier_env_2.py:45); None -> CustomHumanoidRobot
 
     def __init__(self, robot=None, render=False):
         from oracle import oracle as O
         self._O = O
         self.phys = O.default_phys()
-        self.robot = robot if robot is not None else sys.modules["humanoid"].CustomHumanoidRobot()
+        self.robot = robot if robot is not None else (FakeFlatEnv.default_robot or sys.modules["humanoid"].CustomHumanoidRobot)()
         self.action_space = _Box(-np.ones(17, np.float32), np.ones(17, np.float32))
         self.observation_space = _Box(-np.inf * np.ones(44, np.float32), np.inf * np.ones(44, np.float32))
         self.jdict = {n: FakeJoint(self, i, n) for i, n in enumerate(MODEL["joint_name"])}
@@ -251,6 +252,7 @@ class FakeFlatEnv:
 class WalkerBase:
     """Stand-in for pybullet_envs.robot_locomotors.WalkerBase; calc_state restated from the upstream source."""
     foot_list = []
+    reset_rng = None  # persistent generator for the joint noise of robot_specific_reset (None: a fresh seeded one per reset)
 
     def __init__(self, fn, robot_name, action_dim, obs_dim, power):
         self.model_xml, self.robot_name, self.power = fn, robot_name, power
@@ -259,7 +261,7 @@ class WalkerBase:
         self.body_xyz = [0, 0, 0]
 
     def robot_specific_reset(self, bullet_client):
-        rng = np.random.default_rng(12345)
+        rng = WalkerBase.reset_rng or np.random.default_rng(12345)
         for j in self.ordered_joints:
             j.reset_current_position(rng.uniform(low=-0.1, high=0.1), 0)
         self.feet = [self.parts[f] for f in self.foot_list]
@@ -335,8 +337,13 @@ def install():
     ray.rllib.env = mod("ray.rllib.env", MultiAgentEnv=MultiAgentEnv)
 
     home = tempfile.mkdtemp(prefix="ilrl_home_")
-    os.makedirs(os.path.join(home, "GitHub"))
-    os.symlink(REF, os.path.join(home, "GitHub", "TA"))
+    ta = os.path.join(home, "GitHub", "TA")
+    os.makedirs(ta)
+    for name in os.listdir(REF):
+        os.symlink(os.path.join(REF, name), os.path.join(ta, name))
+    # DECLARED DATA SUBSTITUTION: hier_env_2.py:64 reads ~/GitHub/TA/Relative_Joints_CSV, which the
+    # reference repo does not ship; the four file names it opens per motion are exactly those of "Joints CSV With Hand".
+    os.symlink(os.path.join(REF, "Joints CSV With Hand"), os.path.join(ta, "Relative_Joints_CSV"))
     os.environ["HOME"] = home
     if REF not in sys.path:
         sys.path.insert(0, REF)
@@ -438,4 +445,84 @@ def terms_of(env):
     return np.array([env.deltaJoints, env.deltaVelJoints, env.delta_lowTargetScore, env.electricityScore,
                      env.jointLimitScore, env.aliveReward, env.bodyPostureScore, env.lowTargetScore,
                      env.deltaEndPoints, env.highTargetScore, env.driftScore, env.delta_highTargetScore],
+                    dtype=np.float64)
+
+
+# ----------------------------------------------------------------------------- hier_env_2.py
+def make_hier2_env(seed=0, physics="oracle"):
+    """The unmodified REF hier_env_2.HierarchicalHumanoidEnv under two DECLARED SUBSTITUTIONS:
+    data  - ~/GitHub/TA/Relative_Joints_CSV (not shipped) -> "Joints CSV With Hand" (same four file names per motion);
+    robot - `HumanoidBulletEnv()` (REF hier_env_2.py:45) builds pybullet_envs' stock `Humanoid` on humanoid_symmetric.xml
+            (not shipped either).  The stand-in is the reference's CustomHumanoidRobot (humanoid_symmetric_2.xml, same
+            motor order / gears / power / initial_z as the stock class) with the stock class's foot_list, so calc_state
+            returns the stock 44 entries; the two feet_contact entries stay 0 because hier_env_2 never calls
+            flat_env.step(), the only place upstream refreshes them."""
+    install()
+    import humanoid
+    import hier_env_2
+
+    class StockHumanoidStandIn(humanoid.CustomHumanoidRobot):
+        foot_list = ["right_foot", "left_foot"]
+
+    FakeFlatEnv.physics = physics
+    FakeFlatEnv.default_robot = StockHumanoidStandIn
+    WalkerBase.reset_rng = np.random.default_rng(seed + 777)   # the arm joints keep this noise (hier_env_2.py:214-252)
+    try:
+        env = hier_env_2.HierarchicalHumanoidEnv()
+    finally:
+        FakeFlatEnv.default_robot = None
+    env.rng = LoggingRng(seed)
+    return env
+
+
+def env_words2(env):
+    """hier_env_2 bookkeeping in the ILRL_E_* layout; MODE 2 re-uses two words (ilrl_constants.h ILRL_E2_*)."""
+    e = np.zeros(26)
+    e[0] = env.selected_motion_frame
+    e[2] = env.cur_timestep
+    e[3:5] = env.target[:2]
+    e[5:7] = env.starting_robot_pos[:2]
+    e[7:10] = env.starting_ep_pos[:3]
+    e[10:12] = env.robot_pos[:2]
+    e[12] = env.highLevelDegTarget
+    e[13] = env.flat_env.robot.walk_target_x
+    e[14] = env.flat_env.robot.walk_target_y
+    e[15] = env.cumulative_deltaVelJoints_low
+    e[16] = env.deltaJoints
+    e[17] = env.deltaVelJoints
+    e[18] = env.bodyPostureScore
+    if getattr(env, "cur_obs", None) is not None:
+        e[19:21] = env.cur_obs[1:3]
+    e[21] = env.steps_remaining_at_level
+    e[22] = env.cumulative_driftScore
+    e[23] = env.highTargetScore
+    e[24] = env.cumulative_deltaJoints_low
+    return e
+
+
+def set_env_words2(env, e):
+    env.selected_motion_frame = int(e[0])
+    env.cur_timestep = int(e[2])
+    env.target = np.array([e[3], e[4], 0.0])
+    env.starting_robot_pos = np.array([e[5], e[6], 0.0])
+    env.starting_ep_pos = np.array([e[7], e[8], e[9]])
+    env.robot_pos = np.array([e[10], e[11], 0.0])
+    env.highLevelDegTarget = float(e[12])
+    env.setWalkTarget(float(e[13]), float(e[14]))
+    env.cumulative_deltaVelJoints_low = float(e[15])
+    env.deltaJoints = float(e[16])
+    env.deltaVelJoints = float(e[17])
+    env.bodyPostureScore = float(e[18])
+    env.steps_remaining_at_level = int(e[21])
+    env.cumulative_driftScore = float(e[22])
+    env.highTargetScore = float(e[23])
+    env.cumulative_deltaJoints_low = float(e[24])
+
+
+def terms_of2(env):
+    """ILRL_T_* row in MODE 2: slots 2 and 8 (delta_lowTargetScore / deltaEndPoints, constant 0 in hier_env_2) carry
+    deltaJoints_low / deltaVelJoints_low."""
+    return np.array([env.deltaJoints, env.deltaVelJoints, env.deltaJoints_low, env.electricityScore,
+                     env.jointLimitScore, env.aliveReward, env.bodyPostureScore, env.lowTargetScore,
+                     env.deltaVelJoints_low, env.highTargetScore, env.driftScore, env.delta_highTargetScore],
                     dtype=np.float64)

@@ -759,3 +759,84 @@ def test_concurrent_handles_and_streams():
         torch.cuda.synchronize()
         assert torch.equal(got[0], w[0]) and torch.equal(got[1], w[1])
         env.close()
+
+
+def test_hier2_env_view_replays_the_reference_protocol():
+    """HierarchicalHumanoidEnv2 (REF hier_env_2.py:39), the N = 1 drop-in view: dict keys, shapes, the 20-step level
+    protocol and the mirrored attributes; values against the numpy oracle of the variant (oracle/hier2_np.py)."""
+    from ilrl_b200 import HierarchicalHumanoidEnv2
+    from oracle import hier2_np as H
+    env = HierarchicalHumanoidEnv2(seed=5)
+    assert tuple(env.high_level_obs_space.shape) == (60,) and tuple(env.high_level_act_space.shape) == (36,)
+    assert tuple(env.low_level_obs_space.shape) == (72,) and env.step_per_level == 20 and env.skipFrame == 5
+    assert list(env.joint_map) == ["right_knee", "right_hip_x", "right_hip_y", "right_hip_z", "left_knee", "left_hip_x",
+                                   "left_hip_y", "left_hip_z"] and env.joint_weight_sum == 16
+    clip = O.load_clip("motion09_03")
+    rng = np.random.default_rng(6)
+    o = env.reset()
+    assert list(o) == ["high_level_agent"] and o["high_level_agent"].shape == (60,)
+    assert env.lowTargetScore == -5 and env.highTargetScore == -5 and env.steps_remaining_at_level == 20
+    f0 = env.selected_motion_frame
+    ha = rng.uniform(-1, 1, 36)
+    o, r, d, _ = env.step({"high_level_agent": ha})
+    assert list(o) == ["low_level_agent"] and r == {"low_level_agent": 0} and d == {"__all__": False}
+    assert o["low_level_agent"].shape == (72,)
+    np.testing.assert_allclose(o["low_level_agent"][38:], ha[2:].astype(np.float32), rtol=0, atol=0)
+    np.testing.assert_allclose(env.jointTarget, ha[2:].astype(np.float32), rtol=0, atol=0)
+    assert env.selected_motion_frame == (f0 + 5) % (env.max_frame[1] - 1)      # the frame advances here ...
+    n_low = 0
+    for k in range(20):
+        f1 = env.selected_motion_frame
+        a = rng.uniform(-0.2, 0.2, 17)
+        # oracle step (physics skipped there: only the quantities that do not depend on the post-step state are compared)
+        o, r, d, _ = env.step({env.low_level_agent_id: a})
+        n_low += 1
+        assert env.selected_motion_frame == f1                                   # ... and not in the low-level step
+        assert env.steps_remaining_at_level == 20 - n_low
+        if d["__all__"]:
+            assert sorted(o) == ["high_level_agent", "low_level_agent"]
+            break
+        if k < 19:
+            assert list(o) == ["low_level_agent"] and o["low_level_agent"].shape == (72,)
+            # low reward = (0.1 elec + 0.2 limit + 0.1 alive + 0.4 posture) / 2 from the mirrored terms
+            want = (0.1 * env.electricityScore + 0.2 * env.jointLimitScore + 0.1 * env.aliveReward + 0.4 * env.bodyPostureScore) / 2
+            assert abs(r["low_level_agent"] - want) < 1e-6
+            assert 0 < env.deltaJoints_low <= 1 and 0 < env.deltaVelJoints_low <= 1
+        else:
+            assert list(o) == ["high_level_agent"] and o["high_level_agent"].shape == (60,)
+            assert env.cumulative_driftScore == 0 and env.cumulative_deltaJoints_low == 0
+            assert 0.0 <= env.driftScore <= 1.0 + 1e-6
+            f = env.selected_motion_frame
+            tail = np.array([[clip["rel"][f][c], clip["vel"][f][c]] for c in H.MAP_COL]).ravel()
+            np.testing.assert_allclose(o["high_level_agent"][44:], tail, rtol=1e-6, atol=1e-6)
+    env.max_timestep = 3
+    env.reset()
+    env.step({"high_level_agent": ha})
+    for k in range(3):
+        o, r, d, _ = env.step({"low_level_agent": np.zeros(17)})
+    assert d["__all__"] and sorted(o) == ["high_level_agent", "low_level_agent"]
+    env.close()
+
+
+def test_hier2_base_env_adapter():
+    n = 16
+    be = HierBaseEnv(n, seed=3, variant="hier2")
+    assert tuple(be.high_level_act_space.shape) == (36,) and tuple(be.low_level_obs_space.shape) == (72,)
+    rng = np.random.default_rng(2)
+    obs, rew, done, info, off = be.poll()
+    assert all(list(o) == ["high_level_agent"] and o["high_level_agent"].shape == (60,) for o in obs.values())
+    for it in range(45):
+        acts = {}
+        for i, o in obs.items():
+            if "high_level_agent" in o and "low_level_agent" not in o:
+                acts[i] = {"high_level_agent": rng.uniform(-1, 1, 36)}
+            else:
+                acts[i] = {"low_level_agent": rng.uniform(-1, 1, 17)}
+        be.send_actions(acts)
+        new_obs, rew, done, info, off = be.poll()
+        assert sorted(new_obs) == sorted(acts)
+        for i, d in done.items():
+            if d["__all__"]:
+                new_obs[i] = be.try_reset(i)
+        obs = new_obs
+    be.stop()

@@ -256,3 +256,176 @@ def test_hier_trajectory_protocol():
     has_low = ((flags & 4) != 0) & agree
     assert np.abs(rew[l][has_low] - z["low_reward"][l][has_low]).max() <= 1e-4
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------- hier_env_2.py (row a18)
+ENV_SCALE2 = ENV_SCALE.copy()
+ENV_SCALE2[[15, 24]] = 10.0      # MODE 2: cumulative_deltaVelJoints_low / cumulative_deltaJoints_low live in these words
+
+
+def _hier2_env(n, auto_reset=False):
+    return BatchedHumanoidEnv(n, "hier2", clips=["motion08_03", "motion09_03"], clip_of_env=np.ones(n, np.int32),
+                              auto_reset=auto_reset)
+
+
+def _noise_from_phys(phys_after):
+    """the joint noise a hier_env_2 reset left in the arms = the post-reset arm angles themselves"""
+    return phys_after[:, 13:30].astype(np.float32)
+
+
+def test_hier2_kernels_match_reference_on_injected_states():
+    """REF hier_env_2.py reset / high_level_step / low_level_step (unmodified, under the declared data + robot
+    substitutions) on injected states, physics skipped: 1e-5 relative, frame / done / protocol flags bit-exact."""
+    z = _load("hier2_injected.npz")
+    n = len(z["kind"])
+    env = _hier2_env(n)
+    assert env.obs.shape == (n, 72) and env.high_obs.shape == (n, 60)
+    kind = z["kind"]
+    e = _pad_env(z["env_before"])
+    e[:, 1] = 1
+    e[:, 19:21] = z["obs_sincos"]
+    e[:, 25] = (kind == 1)
+    phys0 = z["phys"].astype(np.float32)
+    # --- reset records
+    r = kind == 0
+    env.set_state(phys0, e)
+    env.set_joint_target(z["jt_before"].astype(np.float32))
+    env.set_forced_reset_noise(_noise_from_phys(z["phys_after"]))
+    hobs = env.reset(mask=r.astype(np.uint8), start_frame=z["draws"][:, 0], reset_yaw_deg=z["draws"][:, 1].astype(np.float32),
+                     target_deg=z["draws"][:, 2]).cpu().numpy().copy()
+    phys, envf = [t.cpu().numpy() for t in env.get_state()]
+    _close(hobs[r], z["high_obs"][r], what="hier2 reset high obs")
+    _close(phys[r], z["phys_after"][r], scale=1.0, what="hier2 reset phys")
+    np.testing.assert_array_equal(envf[r][:, 0].astype(int), z["env_after"][r][:, 0].astype(int))
+    _close(envf[r][:, 2:25], z["env_after"][r][:, 2:25], scale=ENV_SCALE2[2:25] * 100, what="hier2 reset env words")
+    assert (envf[r][:, 25] == 1).all()                                   # waiting for the high-level agent
+    _close(envf[~r][:, :25], e[~r][:, :25], rt=0, scale=0, what="unmasked envs untouched by reset")
+    # --- high-level steps
+    h = kind == 1
+    env.set_state(phys0, e)
+    env.set_joint_target(z["jt_before"].astype(np.float32))
+    lo_obs = env.high_step(z["action"].astype(np.float32)).cpu().numpy().copy()
+    _, envf = [t.cpu().numpy() for t in env.get_state()]
+    jt = env.get_joint_target().cpu().numpy()
+    _close(lo_obs[h], z["low_obs"][h], what="low obs returned by hier2 high_level_step")
+    np.testing.assert_array_equal(envf[h][:, 0].astype(int), z["env_after"][h][:, 0].astype(int))
+    _close(envf[h][:, 2:25], z["env_after"][h][:, 2:25], scale=ENV_SCALE2[2:25], what="env words after hier2 high step")
+    _close(jt[h], z["jt_after"][h], what="jointTarget after high step")
+    _close(jt[~h], z["jt_before"][~h], rt=0, scale=1e-7, what="jointTarget of non-waiting envs")
+    _close(envf[~h][:, :25], e[~h][:, :25], rt=0, scale=0, what="non-waiting envs untouched")
+    # --- low-level steps (everything but the physics)
+    l = kind == 2
+    e2 = e.copy(); e2[:, 25] = ~l
+    env.set_state(phys0, e2)
+    env.set_joint_target(z["jt_before"].astype(np.float32))
+    env.set_forced_target_deg(np.where(z["rand_deg"] == -999, INT32_MIN, z["rand_deg"]).astype(np.int64))
+    obs, rew, done, terms = env.step(z["action"][:, :17].astype(np.float32), physics=False)
+    ho, hr, hf = env.high_readout()
+    _, envf = env.get_state()
+    obs, rew, done, terms, ho, hr, hf, envf = [t.cpu().numpy() for t in (obs, rew, done, terms, ho, hr, hf, envf)]
+    flags = z["flags"][l]
+    np.testing.assert_array_equal(envf[l][:, 0].astype(int), z["env_after"][l][:, 0].astype(int))
+    np.testing.assert_array_equal(done[l].astype(bool), (flags & 1).astype(bool))
+    np.testing.assert_array_equal((hf[l] & 2) != 0, (flags & 2) != 0)
+    np.testing.assert_array_equal((hf[l] & 4) != 0, ((flags & 2) != 0) & ((flags & 1) == 0))   # waits unless the episode ended
+    has_low, has_high = (flags & 4) != 0, (flags & 2) != 0
+    _close(obs[l][has_low], z["low_obs"][l][has_low], what="hier2 low obs")
+    _close(rew[l][has_low], z["low_reward"][l][has_low], what="hier2 low reward")
+    _close(ho[l][has_high], z["high_obs"][l][has_high], what="hier2 high obs")
+    _close(hr[l][has_high], z["high_reward"][l][has_high], scale=10.0, what="hier2 high reward")
+    tsc = np.array([1, 1, 1, 1, 1, 1, 1, 10, 1, 10, 1, 100.0])
+    _close(terms[l][:, :10], z["terms"][l][:, :10], scale=tsc[:10], what="hier2 terms")
+    # driftScore / delta_highTargetScore are attributes the reference only rewrites in updateRewardHigh
+    _close(terms[l][has_high][:, 10:], z["terms"][l][has_high][:, 10:], scale=tsc[10:], what="hier2 high terms")
+    _close(envf[l][:, 2:25], z["env_after"][l][:, 2:25], scale=ENV_SCALE2[2:25], what="hier2 env words")
+    env.close()
+
+
+def test_hier2_trajectory_protocol():
+    """hier_env_2 protocol trace with physics (reset -> high -> 20 low -> high ...), every record restarted from its
+    recorded pre-state: the full fused MODE 2 step kernel."""
+    z = _load("hier2_traj.npz")
+    n = len(z["kind"])
+    env = _hier2_env(n)
+    kind = z["kind"]
+    e = _pad_env(z["env_before"])
+    e[:, 1] = 1
+    e[:, 25] = (kind == 1)
+    r, h, l = kind == 0, kind == 1, kind == 2      # (env_before carries cur_obs[1:3] of the moment: words 19, 20)
+    phys0 = z["phys_before"].astype(np.float32)
+    env.set_joint_target(z["jt_before"].astype(np.float32))
+    env.set_state(phys0, e)
+    env.set_forced_reset_noise(_noise_from_phys(z["phys_after"]))
+    hobs = env.reset(mask=r.astype(np.uint8), start_frame=z["draws"][:, 0], reset_yaw_deg=z["draws"][:, 1].astype(np.float32),
+                     target_deg=z["draws"][:, 2]).cpu().numpy().copy()
+    _close(hobs[r], z["high_obs"][r], what="hier2 traj reset high obs")
+    phys, envf = [t.cpu().numpy() for t in env.get_state()]
+    _close(phys[r], z["phys_after"][r], scale=1.0, what="hier2 traj reset phys")
+    env.set_state(phys0, e)
+    env.set_joint_target(z["jt_before"].astype(np.float32))
+    lo_obs = env.high_step(z["action"].astype(np.float32)).cpu().numpy().copy()
+    _close(lo_obs[h], z["low_obs"][h], what="hier2 traj high->low obs")
+    e2 = e.copy(); e2[:, 25] = ~l
+    env.set_state(phys0, e2)
+    env.set_joint_target(z["jt_before"].astype(np.float32))
+    env.set_forced_target_deg(np.where(z["rand_deg"] == -999, INT32_MIN, z["rand_deg"]).astype(np.int64))
+    obs, rew, done, terms = env.step(z["action"][:, :17].astype(np.float32))
+    ho, hr, hf = env.high_readout()
+    phys, envf = env.get_state()
+    obs, rew, done, ho, hr, hf, phys, envf = [t.cpu().numpy() for t in (obs, rew, done, ho, hr, hf, phys, envf)]
+    flags = z["flags"][l]
+    np.testing.assert_array_equal(envf[l][:, 0].astype(int), z["env_after"][l][:, 0].astype(int))
+    agree = (done[l] != 0) == ((flags & 1) != 0)
+    assert all(abs(z["phys_after"][l][i, 2] - 0.75) < 1e-4 for i in np.nonzero(~agree)[0]), np.nonzero(~agree)[0]
+    np.testing.assert_array_equal(((hf[l] & 2) != 0)[agree], ((flags & 2) != 0)[agree])
+    _check_phys(phys[l].astype(np.float64), z["phys_after"][l], True, "hier2 step")
+    has_low = ((flags & 4) != 0) & agree
+    assert np.abs(rew[l][has_low] - z["low_reward"][l][has_low]).max() <= 1e-4
+    has_high = ((flags & 2) != 0) & agree
+    assert has_high.sum() > 20
+    assert np.abs(hr[l][has_high] - z["high_reward"][l][has_high]).max() <= 2e-3   # /0.0165 amplifies the fp32 position
+    assert np.abs(ho[l][has_high][:, 44:] - z["high_obs"][l][has_high][:, 44:]).max() <= 1e-5 * 150
+    env.close()
+
+
+def test_hier2_auto_reset_and_rollout_invariants():
+    """MODE 2 with auto-reset and its own draws: protocol invariants over a few hundred ticks."""
+    n = 512
+    env = BatchedHumanoidEnv(n, "hier2", clips=["motion08_03", "motion09_03"], clip_of_env=np.ones(n, np.int32),
+                             auto_reset=True, seed=11)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    hobs = env.reset()
+    assert hobs.shape == (n, 60) and bool(torch.isfinite(hobs).all())
+    phys, envf = env.get_state()
+    arms = phys[:, 13 + 11:13 + 17]
+    assert float(arms.abs().max()) <= 0.1 and float(arms.std()) > 0.03      # uniform(-0.1, 0.1) joint noise kept by the arms
+    assert float(phys[:, 13:16].abs().max()) == 0.0 and bool((phys[:, 2] == 1.15).all())
+    waits, outcomes, episodes = 0, 0, 0
+    steps_since = torch.zeros(n, device="cuda")
+    for t in range(120):
+        _, _, hf = env.high_readout()
+        waiting = (hf & 4) != 0
+        waits += int(waiting.sum())
+        a2 = torch.rand(n, 36, device="cuda", generator=g) * 2 - 1
+        a2[~waiting] = float("nan")
+        env.high_step(a2)
+        steps_since[waiting] = 0
+        a = torch.rand(n, 17, device="cuda", generator=g) * 2 - 1
+        obs, rew, done, terms = env.step(a)
+        assert bool(torch.isfinite(obs).all()) and bool(torch.isfinite(rew).all())
+        steps_since += 1
+        _, hr, hf = env.high_readout()
+        out = (hf & 2) != 0
+        ended = (hf & 1) != 0
+        assert bool((ended == (done != 0)).all())
+        # an outcome arrives at the end of the episode or exactly step_per_level = 20 low steps after the decision
+        assert bool(((steps_since[out & ~ended]) == 20).all())
+        assert bool((steps_since[~out] < 20).all())
+        assert bool(torch.isfinite(hr[out]).all())
+        outcomes += int(out.sum()); episodes += int(ended.sum())
+        jt = env.get_joint_target()
+        assert bool((obs[:, 38:] == jt).all())                      # the low obs tail is the env's jointTarget
+    assert episodes > n // 2 and outcomes >= episodes and waits > outcomes
+    st = env.stats().cpu().numpy()
+    assert st[0] == episodes
+    env.close()

@@ -206,3 +206,38 @@ def test_golden_fixtures_regenerate_bit_identically_from_the_reference(tmp_path)
                     assert np.array_equal(a[k], b[k]), (f, k)
         else:
             assert open(os.path.join(gold, f)).read() == open(os.path.join(str(tmp_path), f)).read(), f
+
+
+def test_hier2_numpy_oracle_matches_reference_vectors():
+    """Row a18: oracle/hier2_np.py (the CPU restatement of hier_env_2's env logic) against the vectors recorded from the
+    UNMODIFIED REF hier_env_2.py: high_level_step and low_level_step on 400 injected states each."""
+    from oracle import hier2_np as H
+    z = dict(np.load(os.path.join(G, "hier2_injected.npz")))
+    clip = O.load_clip("motion09_03")
+    kinds = z["kind"]
+    n_high = n_low = 0
+    for i in np.nonzero(kinds == 1)[0]:
+        e = z["env_before"][i].copy(); e[19:21] = z["obs_sincos"][i]
+        lo, jt = H.high_step(z["phys"][i], e, z["action"][i], clip)
+        np.testing.assert_allclose(lo, z["low_obs"][i], rtol=1e-6, atol=1e-6)
+        np.testing.assert_allclose(jt, z["jt_after"][i], rtol=0, atol=0)
+        assert int(e[0]) == int(z["env_after"][i][0])
+        np.testing.assert_allclose(e[2:25], z["env_after"][i][2:25], rtol=1e-6, atol=1e-6)
+        n_high += 1
+    for i in np.nonzero(kinds == 2)[0]:
+        e = z["env_before"][i].copy()
+        r = H.low_step_no_physics(z["phys"][i], e, z["jt_before"][i], z["action"][i][:17], int(z["rand_deg"][i]), clip)
+        assert r["flags"] == int(z["flags"][i]), i
+        assert int(e[0]) == int(z["env_after"][i][0])
+        np.testing.assert_allclose(e[2:25], z["env_after"][i][2:25], rtol=1e-6, atol=1e-5)
+        if r["flags"] & 4:
+            np.testing.assert_allclose(r["low_obs"], z["low_obs"][i], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(r["low_reward"], z["low_reward"][i], rtol=1e-6, atol=1e-6)
+        if r["flags"] & 2:
+            np.testing.assert_allclose(r["high_obs"], z["high_obs"][i], rtol=1e-6, atol=1e-6)
+            np.testing.assert_allclose(r["high_reward"], z["high_reward"][i], rtol=1e-5, atol=1e-5)
+        n_low += 1
+    assert n_high == 400 and n_low == 400
+    # fixture sanity: all three protocol outcomes occur, and the reset records carry the stock robot's 60-word high obs
+    assert set(np.unique(z["flags"][kinds == 2])) == {2, 4, 7}
+    assert np.abs(z["high_obs"][kinds == 0][:, 44:]).max() > 0

@@ -281,6 +281,18 @@ class BatchedHumanoidEnv:
             self._forced = torch.as_tensor(deg, device=self.device).to(torch.int32).contiguous()
             self._ck(self.L.ilrl_set_forced_target_deg(self.h, _ptr(self._forced)))
 
+    def set_heightfield(self, data, rows=256, cols=256, body_z=0.25):
+        """Heightfield terrain for every env of the handle ("low" mode; REF humanoid.py:68-144 CustomScene /
+        replaceHeightfieldData).  data[i + j * rows] as the reference's heightfieldData; None = flat ground.  The world
+        height of a sample is data - (min + max) / 2 + body_z, as Bullet places a heightfield shape."""
+        if data is None:
+            self._ck(self.L.ilrl_set_heightfield(self.h, None, 0, 0, 0.0))
+            return
+        d = np.ascontiguousarray(data, dtype=np.float32).reshape(-1)
+        assert d.size == rows * cols
+        zoff = float(body_z) - 0.5 * (float(d.min()) + float(d.max()))
+        self._ck(self.L.ilrl_set_heightfield(self.h, d.ctypes.data, int(rows), int(cols), zoff))
+
     def set_forced_reset_noise(self, noise17):
         """mode "hier2" harness: the joint noise [N,17] resets use instead of their own uniform(-0.1, 0.1) draws (only the
         six arm joints keep it, REF hier_env_2.py:214-252); None = draw."""

@@ -13,6 +13,7 @@
 // high-level step, harness) map one thread to one env.
 #include <cuda_runtime.h>
 #include <limits.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -67,6 +68,7 @@ struct StepArgs {
 #ifdef ILRL_PROF
   long long* prof;     // [warps of the launch][PF_WORDS] phase cycles (measurement build only)
 #endif
+  chain::Terrain terr; // heightfield terrain (terr.h null: flat ground; only read by the TERR instantiations)
   ClipDesc clips[MAX_CLIPS];
 };
 
@@ -145,7 +147,7 @@ __device__ __forceinline__ void set_torques(SM& sm, int e, int tid, int role, co
 // of 72 / 60 words, per-env jointTarget).  Four lanes = one env (ilrl_chain.cuh): the physics substeps run distributed
 // over the quad; the env bookkeeping after them is computed redundantly by the four lanes (identical instruction
 // stream, no divergence) and the outputs are dealt to the lanes for the stores.
-template <int MODE, class SM>
+template <int MODE, class SM, bool TERR = false>
 __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   SM& sm = *reinterpret_cast<SM*>(smraw);
@@ -242,7 +244,8 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
       pf.mark(sub == 0 ? chain::PF_HEAD : chain::PF_INTEG);
       __syncthreads();
       pf.mark(chain::PF_BARRIER);
-      chain::substep(b, sm, gscr_tile, e, tid, role, active, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf);
+      chain::substep<TERR>(b, sm, gscr_tile, e, tid, role, active, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf,
+                           TERR ? &a.terr : nullptr);
     }
   }
   __syncthreads();   // the once-per-step tail (4 k instructions) is entered together as well: +3 % at 65536 envs
@@ -566,8 +569,9 @@ __global__ void clip_ids_kernel(StateView v, const int32_t* ids) {
   if (i >= v.n) return;
   v.envf[(size_t)ILRL_E_CLIP * v.n + i] = ids ? (float)ids[i] : 0.f;
 }
-template <class SM>
-__global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const float* torque, float* gscr_all, int nsub) {
+template <class SM, bool TERR = false>
+__global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const float* torque, float* gscr_all, int nsub,
+                                                          const chain::Terrain terr = chain::Terrain()) {
   extern __shared__ __align__(16) unsigned char smraw[];
   SM& sm = *reinterpret_cast<SM*>(smraw);
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
@@ -589,7 +593,7 @@ __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const flo
   __syncwarp();
   float* gscr_tile = gscr_all + (size_t)blockIdx.x * QE * chain::GROWS * chain::RW;
   for (int sub = 0; sub < nsub; sub++)
-    { chain::Prof pf; chain::substep(b, sm, gscr_tile, e, tid, role, valid, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf); }
+    { chain::Prof pf; chain::substep<TERR>(b, sm, gscr_tile, e, tid, role, valid, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf, TERR ? &terr : nullptr); }
   if (!valid) return;
   Phys ps;
   chain::gather(b, sm, e, qb, qm, ps);
@@ -726,6 +730,8 @@ struct ilrl_env {
   uint32_t* rng = nullptr;
   float* gscr = nullptr;
   float* jt = nullptr;                    // [34][n] jointTarget (mode 2 only)
+  chain::Terrain terr = {nullptr, 0, 0, 0.f, 0.f, 1.f};   // ilrl_set_heightfield (mode 0); h = device copy owned by the handle
+  float* terr_mem = nullptr;
   const float* forced_noise = nullptr;    // ilrl_set_forced_reset_noise
   int obs_w = ILRL_OBS_LOW, hobs_w = ILRL_OBS_HIGH, hact_w = ILRL_ACT_HIGH;   // row widths of the mode
   float* high_obs = nullptr;
@@ -829,6 +835,8 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMalloc(&env->gscr, sizeof(float) * (size_t)chain::GROWS * chain::RW * n));
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
   CKC(cudaFuncSetAttribute(step_kernel<1, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
+  CKC(cudaFuncSetAttribute(step_kernel<0, SmemLarge, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
+  CKC(cudaFuncSetAttribute(physics_only_kernel<SmemLarge, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(step_kernel<2, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
   CKC(cudaFuncSetAttribute(step_kernel<2, SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(step_kernel<2, SmemDense4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDense4)));
@@ -924,6 +932,7 @@ void ilrl_destroy(ilrl_env* env) {
     if (env->part_stream[p]) cudaStreamDestroy(env->part_stream[p]);
   }
   cudaFree(env->clip_ids_dev);
+  cudaFree(env->terr_mem);
   cudaFreeHost(env->h_pull);
   cudaFree(env->ktime);
   cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr); cudaFree(env->jt);
@@ -1025,7 +1034,7 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.terms = terms;
   a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
   a.forced_deg = env->forced_deg; a.forced_scalar = forced_scalar; a.stats = env->stats; a.gscr = env->gscr;
-  a.jt = env->jt; a.forced_noise = env->forced_noise;
+  a.jt = env->jt; a.forced_noise = env->forced_noise; a.terr = env->terr;
   a.tile_counter = env->tile_counter + 2 * (part + 1);
 #ifdef ILRL_PROF
   a.prof = env->prof;
@@ -1033,9 +1042,13 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   memcpy(a.clips, env->clips, sizeof a.clips);
   a.ktime = (env->timing && env->kt_used < KT_SLOTS) ? env->ktime + 2 * (size_t)env->kt_used++ : nullptr;
   a.ntiles = (count + QE - 1) / QE;
-  const int qblk = min(a.ntiles, env->layout == 2 ? env->grid_dense4 : env->layout == 1 ? env->grid_large : env->grid_small);
+  // (heightfield terrain: one instantiation, the mid-size layout, whatever the batch size)
+  const int layout = env->terr.h ? 1 : env->layout;
+  const int qblk = min(a.ntiles, layout == 2 ? env->grid_dense4 : layout == 1 ? env->grid_large : env->grid_small);
   const int md = env->cfg.mode;
-  if (env->layout == 2) {
+  if (env->terr.h) {
+    step_kernel<0, SmemLarge, true><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
+  } else if (env->layout == 2) {
     if (md == 0) step_kernel<0, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
     else if (md == 1) step_kernel<1, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
     else step_kernel<2, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
@@ -1311,6 +1324,39 @@ int ilrl_set_forced_target_deg(ilrl_env* env, const int32_t* deg) {
   env->forced_deg = deg;
   return ILRL_OK;
 }
+int ilrl_set_heightfield(ilrl_env* env, const float* heights, int32_t rows, int32_t cols, float zoff) {
+  if (!env) return ILRL_ERR_ARG;
+  ON_DEVICE(env);
+  CK(cudaDeviceSynchronize());   // no step may be reading the old terrain
+  if (!heights) {                // back to the flat ground plane
+    cudaFree(env->terr_mem);
+    env->terr_mem = nullptr;
+    env->terr = chain::Terrain{nullptr, 0, 0, 0.f, 0.f, 1.f};
+    return ILRL_OK;
+  }
+  if (env->cfg.mode != 0) return fail(env, ILRL_ERR_ARG, "ilrl_set_heightfield: only the low-level env has a terrain (REF low_level_env.py:43-47)");
+  if (rows < 2 || cols < 2 || rows > 4096 || cols > 4096) return fail(env, ILRL_ERR_ARG, "ilrl_set_heightfield: bad grid size");
+  float hmax = -1e30f, g2max = 0.f;
+  for (int j = 0; j < cols; j++)
+    for (int i = 0; i < rows; i++) {
+      const float h = heights[i + (size_t)j * rows];
+      if (!(h == h) || fabsf(h) > 1e6f) return fail(env, ILRL_ERR_ARG, "ilrl_set_heightfield: non-finite height");
+      hmax = fmaxf(hmax, h);
+      if (i + 1 < rows && j + 1 < cols) {   // both triangles of the cell
+        const float h10 = heights[i + 1 + (size_t)j * rows], h01 = heights[i + (size_t)(j + 1) * rows],
+                    h11 = heights[i + 1 + (size_t)(j + 1) * rows];
+        g2max = fmaxf(g2max, (h10 - h) * (h10 - h) + (h01 - h) * (h01 - h));
+        g2max = fmaxf(g2max, (h11 - h01) * (h11 - h01) + (h11 - h10) * (h11 - h10));
+      }
+    }
+  if (g2max >= 1.f) return fail(env, ILRL_ERR_ARG, "ilrl_set_heightfield: a triangle is steeper than 45 degrees (the friction "
+                                                   "frame of this path assumes |n.z| > 0.707)");
+  if (env->terr_mem && (env->terr.rows != rows || env->terr.cols != cols)) { cudaFree(env->terr_mem); env->terr_mem = nullptr; }
+  if (!env->terr_mem) CK(cudaMalloc(&env->terr_mem, sizeof(float) * (size_t)rows * cols));
+  CK(cudaMemcpy(env->terr_mem, heights, sizeof(float) * (size_t)rows * cols, cudaMemcpyHostToDevice));
+  env->terr = chain::Terrain{env->terr_mem, rows, cols, zoff, hmax + zoff, 1.f / sqrtf(1.f + g2max)};
+  return ILRL_OK;
+}
 int ilrl_set_forced_reset_noise(ilrl_env* env, const float* noise17) {
   if (!env) return ILRL_ERR_ARG;
   if (env->cfg.mode != 2) return fail(env, ILRL_ERR_ARG, "ilrl_set_forced_reset_noise: only the hier_env_2 mode keeps reset noise");
@@ -1339,7 +1385,9 @@ int ilrl_physics_only(ilrl_env* env, const float* torque, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (!torque) return fail(env, ILRL_ERR_ARG, "ilrl_physics_only: null buffer");
   ON_DEVICE(env);
-  if (env->layout == 2)
+  if (env->terr.h)
+    physics_only_kernel<SmemLarge, true><<<(env->n + QE - 1) / QE, QT, sizeof(SmemLarge), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps, env->terr);
+  else if (env->layout == 2)
     physics_only_kernel<SmemDense4><<<(env->n + QE - 1) / QE, QT, sizeof(SmemDense4), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);
   else if (env->layout == 1)
     physics_only_kernel<SmemLarge><<<(env->n + QE - 1) / QE, QT, sizeof(SmemLarge), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);

@@ -287,6 +287,33 @@ struct Prof {
 // replicated floating-base state of one env
 struct Base { float p[3], quat[4], v[3], w[3]; };
 
+// Heightfield terrain of the handle (REF humanoid.py:68-144 CustomScene).  [BULLET, restated]
+// btHeightfieldTerrainShape: sample (i, j) at x = i - (rows - 1) / 2, y = j - (cols - 1) / 2, world z = h[i + j * rows]
+// + zoff; cells cut along the diagonal (i+1, j) - (i, j+1).  Contact model (declared): a candidate sphere meets the
+// plane of the triangle under its centre.  hmax / nzmin (largest world height, smallest normal z of any triangle) make
+// the per-body early-outs conservative.  The kernels that take a Terrain are separate instantiations (TERR = true):
+// the flat-ground kernels carry none of this.
+struct Terrain { const float* h; int rows, cols; float zoff, hmax, nzmin; };
+__device__ __forceinline__ float terrain_sample(const Terrain& t, float x, float y, V3& n) {
+  const float fx = x + 0.5f * (float)(t.rows - 1), fy = y + 0.5f * (float)(t.cols - 1);
+  const int i = min(max((int)floorf(fx), 0), t.rows - 2), j = min(max((int)floorf(fy), 0), t.cols - 2);
+  const float u = fminf(fmaxf(fx - (float)i, 0.f), 1.f), v = fminf(fmaxf(fy - (float)j, 0.f), 1.f);
+  const float* p = t.h + i + j * t.rows;
+  const float h00 = __ldg(p), h10 = __ldg(p + 1), h01 = __ldg(p + t.rows), h11 = __ldg(p + t.rows + 1);
+  float gx, gy, h;
+  if (u + v <= 1.f) { gx = h10 - h00; gy = h01 - h00; h = h00 + u * gx + v * gy; }
+  else { gx = h11 - h01; gy = h11 - h10; h = h11 - (1.f - u) * gx - (1.f - v) * gy; }
+  const float il = rsqrtf(1.f + gx * gx + gy * gy);
+  n = mk(-gx * il, -gy * il, il);
+  return h + t.zoff;
+}
+// btPlaneSpace1 for a normal with |n.z| > 0.707 (heightfield slopes below 45 degrees; checked when the terrain is set)
+__device__ __forceinline__ void plane_space_up(V3 n, V3& p, V3& q) {
+  const float a = n.y * n.y + n.z * n.z, k = rsqrtf(a);
+  p = mk(0.f, -n.z * k, n.y * k);
+  q = mk(a * k, -n.x * p.z, n.x * p.y);
+}
+
 __device__ __forceinline__ float qsum(float v, unsigned qm) {
   v += __shfl_xor_sync(qm, v, 1);
   v += __shfl_xor_sync(qm, v, 2);
@@ -469,8 +496,9 @@ __device__ __forceinline__ SV chol6_solve_smem(const float* L, SV b) {
 struct FkOut { uint32_t act, lim; float sx, sy, ssx, ssy, ex, ey; };
 
 // FULL = false: pose only (part-origin sums and the end-body origin), nothing is written to shared memory.
-template <bool FULL, class SM>
-__device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, int role, FkOut& o) {
+template <bool FULL, bool TERR = false, class SM>
+__device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, int role, FkOut& o,
+                                         const Terrain* terr = nullptr) {
   const Tables& T = tables(sm);
   float R0[9];
   quat2mat(b.quat[0], b.quat[1], b.quat[2], b.quat[3], R0);
@@ -478,15 +506,23 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
   uint32_t act = 0, lim = 0;
   // torso spheres
   // (a body whose origin is higher than its reach + the breaking distance cannot have a candidate: skip its spheres)
-  if (FULL && b.p[2] - T.torso_reach < (float)ILRL_CONTACT_BREAK) {
+  // TERR: candidate words = centre x, y (relative to the torso) and distance - base z (so that, as on flat ground,
+  // distance = base z + word 2 wherever it is needed again)
+  if (FULL && (TERR ? (b.p[2] - terr->hmax) * terr->nzmin - T.torso_reach : b.p[2] - T.torso_reach) < (float)ILRL_CONTACT_BREAK) {
 #pragma unroll 1
     for (int g = NS - 5; g < NS; g++) {
       V3 c = mv(R0, mk(kSphereC[3 * g], kSphereC[3 * g + 1], kSphereC[3 * g + 2]));
-      const float rad = kSphereR[g], d = b.p[2] + (c.z - rad);   // same association as where it is recomputed
+      const float rad = kSphereR[g];
+      float d, w2;
+      if constexpr (TERR) {
+        V3 n;
+        const float hgt = terrain_sample(*terr, b.p[0] + c.x, b.p[1] + c.y, n);
+        d = (b.p[2] + c.z - hgt) * n.z - rad; w2 = d - b.p[2];
+      } else { w2 = c.z - rad; d = b.p[2] + w2; }   // same association as where it is recomputed
       if (d < (float)ILRL_CONTACT_BREAK) {
         act |= 1u << g;
         float* sp = &sm.sph[g][0][e];
-        sp[0] = c.x; sp[QE] = c.y; sp[2 * QE] = c.z - rad;
+        sp[0] = c.x; sp[QE] = c.y; sp[2 * QE] = w2;
       }
     }
   }
@@ -553,16 +589,22 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
         if (FULL) rigid_rec(Rc, ob, B.m, B.ix, B.iy, B.iz, Vp, rcd);
         if (c < 3) { ssx += ob.x; ssy += ob.y; } else { sx += ob.x; sy += ob.y; }
         ex = ob.x; ey = ob.y;
-        if (FULL && b.p[2] + ob.z - B.reach < (float)ILRL_CONTACT_BREAK) {
+        if (FULL && (TERR ? (b.p[2] + ob.z - terr->hmax) * terr->nzmin - B.reach : b.p[2] + ob.z - B.reach) < (float)ILRL_CONTACT_BREAK) {
 #pragma unroll 1
           for (int t = 0; t < B.nsph; t++) {
             const int g = B.sidx[t];
             V3 cs_ = ob + mv(Rc, rd3(B.sph[t]));
-            const float rad = B.sph[t][3], d = b.p[2] + (cs_.z - rad);
+            const float rad = B.sph[t][3];
+            float d, w2;
+            if constexpr (TERR) {
+              V3 n;
+              const float hgt = terrain_sample(*terr, b.p[0] + cs_.x, b.p[1] + cs_.y, n);
+              d = (b.p[2] + cs_.z - hgt) * n.z - rad; w2 = d - b.p[2];
+            } else { w2 = cs_.z - rad; d = b.p[2] + w2; }
             if (d < (float)ILRL_CONTACT_BREAK) {
               act |= 1u << g;
               float* sp = &sm.sph[g][0][e];
-              sp[0] = cs_.x; sp[QE] = cs_.y; sp[2 * QE] = cs_.z - rad;
+              sp[0] = cs_.x; sp[QE] = cs_.y; sp[2 * QE] = w2;
             }
           }
         }
@@ -670,16 +712,18 @@ __device__ __forceinline__ void build_limit_row(const SM& sm, const Tables& T, i
 }
 
 // the three rows (normal, two friction directions) of the ground contact of sphere g of env e: one walk, link records
-// loaded once, 3-way instruction-level parallelism.  xx: contact point relative to the torso origin, dist: its height.
+// loaded once, 3-way instruction-level parallelism.  xx: contact point relative to the torso origin, dist: its distance
+// along the normal nrm; t1, t2 = btPlaneSpace1(nrm) (flat ground: (0,0,1), (0,-1,0), (1,0,0), folded at compile time).
 template <class SM>
 __device__ __forceinline__ void build_contact_rows(const SM& sm, const Tables& T, int g, int e, int qb, float idt, V3 xx,
-                                                   float dist, const float* nub, float* row0, float* row1, float* row2) {
+                                                   float dist, const float* nub, float* row0, float* row1, float* row2,
+                                                   V3 nrm, V3 t1, V3 t2) {
   const int L = T.sphL[g];
   int c = T.sphC[g];
   float* rows[3] = {row0, row1, row2};
   // normal (0,0,1), tangents btPlaneSpace1 -> (0,-1,0), (1,0,0); spatial force of a unit impulse at the contact point
   SV F[3], pf[3];
-  F[0].l = mk(0.f, 0.f, 1.f); F[1].l = mk(0.f, -1.f, 0.f); F[2].l = mk(1.f, 0.f, 0.f);
+  F[0].l = nrm; F[1].l = t1; F[2].l = t2;
   float dd[3];
 #pragma unroll
   for (int i = 0; i < 3; i++) {
@@ -830,9 +874,9 @@ __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int
 // end of the batch, waiting for a high-level action, skipped by a NaN action) run on a benign dummy state
 // (`steps` = false: they produce no constraint rows and their results are never stored), and they still help to build
 // the rows of the warp's other envs.  gscr_tile: overflow-row scratch of env 0 of this CTA's tile.
-template <class SM>
+template <bool TERR = false, class SM>
 __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e, int tid, int role, bool steps, float dt,
-                                        Prof& pf) {
+                                        Prof& pf, const Terrain* terr = nullptr) {
   constexpr int RSM = SM::RSM;
   constexpr unsigned qm = FULLMASK, wm = FULLMASK;
   float* gscr = gscr_tile + (size_t)e * (GROWS * RW);
@@ -840,7 +884,7 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
   const Tables& T = tables(sm);
   // ---- phase A
   FkOut fo;
-  fk_phase<true>(b, sm, e, tid, role, fo);
+  fk_phase<true, TERR>(b, sm, e, tid, role, fo, terr);
   uint32_t act = fo.act, lim = fo.lim;
   pf.mark(PF_FK);
   // ---- phase B: inward pass
@@ -967,11 +1011,12 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
         const int src = 4 * q;
         const uint32_t mask_q = __shfl_sync(wm, kind == 0 ? lim : act, src);
         const int nlim_q = __shfl_sync(wm, nlim, src);
-        float bz_q = 0.f, nub_q[6];
+        float bz_q = 0.f, bx_q = 0.f, by_q = 0.f, nub_q[6];
         int ncon_q = 0;
         if (kind == 1) {
           ncon_q = __shfl_sync(wm, ncon, src);
           bz_q = __shfl_sync(wm, b.p[2], src);
+          if (TERR) { bx_q = __shfl_sync(wm, b.p[0], src); by_q = __shfl_sync(wm, b.p[1], src); }
 #pragma unroll
           for (int i = 0; i < 6; i++) nub_q[i] = __shfl_sync(wm, nub[i], src);
         }
@@ -987,8 +1032,21 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
             const int r0 = nlim_q + k, r1 = nlim_q + ncon_q + 2 * k;   // normal | friction pair (storage = sweep order)
             sm.lam(e_q)[r0] = 0.f; sm.lam(e_q)[r1] = 0.f; sm.lam(e_q)[r1 + 1] = 0.f;
             const float* sp = &sm.sph[g][0][e_q];
-            build_contact_rows(sm, T, g, e_q, qb_q, idt, mk(sp[0], sp[QE], sp[2 * QE]), bz_q + sp[2 * QE], nub_q,
-                               row_ptr(r0), row_ptr(r1), row_ptr(r1 + 1));
+            if constexpr (TERR) {
+              // the plane under the sphere's centre again (L2-resident heightfield); centre height from the stored
+              // distance: dist = (bz + cz - h) nz - r
+              V3 n, t1, t2;
+              const float cx = sp[0], cy = sp[QE], dist = bz_q + sp[2 * QE], rad = kSphereR[g];
+              const float hgt = terrain_sample(*terr, bx_q + cx, by_q + cy, n);
+              plane_space_up(n, t1, t2);
+              const float cz = (dist + rad) / n.z + hgt - bz_q;
+              build_contact_rows(sm, T, g, e_q, qb_q, idt, mk(cx - rad * n.x, cy - rad * n.y, cz - rad * n.z), dist, nub_q,
+                                 row_ptr(r0), row_ptr(r1), row_ptr(r1 + 1), n, t1, t2);
+            } else {
+              build_contact_rows(sm, T, g, e_q, qb_q, idt, mk(sp[0], sp[QE], sp[2 * QE]), bz_q + sp[2 * QE], nub_q,
+                                 row_ptr(r0), row_ptr(r1), row_ptr(r1 + 1), mk(0.f, 0.f, 1.f), mk(0.f, -1.f, 0.f),
+                                 mk(1.f, 0.f, 0.f));
+            }
           }
         }
       }

@@ -313,21 +313,57 @@ class _SingleEnv(object):
         return None
 
 
+class _CustomSceneShim(object):
+    """The part of REF humanoid.py:68-144 `CustomScene` a driver touches through `env.flat_env.stadium_scene`: the
+    heightfield data, its per-episode random regeneration and `replaceHeightfieldData` (REF env_vis_low.py:155-171).
+    The collision shape itself is the handle's heightfield (ilrl_set_heightfield)."""
+    numHeightfieldRows = 256
+    numHeightfieldColumns = 256
+
+    def __init__(self, owner):
+        self._owner = owner
+        self.heightfieldData = [0] * self.numHeightfieldRows * self.numHeightfieldColumns
+
+    def _upload(self):
+        self._owner._env.set_heightfield(self.heightfieldData, self.numHeightfieldRows, self.numHeightfieldColumns)
+
+    def replaceHeightfieldData(self, newData):       # REF humanoid.py:76-86
+        self.heightfieldData = list(newData)
+        self._upload()
+
+    def episode_restart(self, bullet_client=None):   # REF humanoid.py:88-124: 2 x 2 sample plateaus of U(0, 0.5), flat centre
+        import random
+        R, d = self.numHeightfieldRows, self.heightfieldData
+        for j in range(self.numHeightfieldColumns // 2):
+            for i in range(R // 2):
+                h = random.uniform(0, 0.05) * 10
+                d[2 * i + 2 * j * R] = d[2 * i + 1 + 2 * j * R] = d[2 * i + (2 * j + 1) * R] = d[2 * i + 1 + (2 * j + 1) * R] = h
+        for j in (63, 64):
+            for i in (63, 64):
+                d[2 * i + 2 * j * R] = d[2 * i + 1 + 2 * j * R] = d[2 * i + (2 * j + 1) * R] = d[2 * i + 1 + (2 * j + 1) * R] = 0
+        self._upload()
+
+
+class _FlatEnvShim(object):
+    def __init__(self, owner):
+        self.stadium_scene = _CustomSceneShim(owner)
+
+
 class LowLevelHumanoidEnv(_SingleEnv, _GymEnv):
-    """REF low_level_env.py:36.  `useCustomEnv=True` (random heightfield terrain, REF humanoid.py:68-144) is outside
-    this path and raises; `customRobot` is accepted and ignored (the kernels model `CustomHumanoidRobot` on
-    `humanoid_symmetric_2.xml`, the robot every reference config passes)."""
+    """REF low_level_env.py:36.  `useCustomEnv=True` steps on the reference's random heightfield terrain
+    (REF humanoid.py:68-144: regenerated at every reset, replaceable through
+    `env.flat_env.stadium_scene.replaceHeightfieldData`); `customRobot` is accepted and ignored (the kernels model
+    `CustomHumanoidRobot` on `humanoid_symmetric_2.xml`, the robot every reference config passes)."""
 
     def __init__(self, reference_name="motion08_03", useCustomEnv=False, customRobot=None, device=0, seed=None):
-        if useCustomEnv:
-            raise NotImplementedError("useCustomEnv=True (CustomScene heightfield terrain) is out of scope of the "
-                                      "B200 path (DESIGN.md section 7); the reference's training configs use False")
-        self.useCustomEnv = False
+        self.useCustomEnv = bool(useCustomEnv)
         self.reference_name = reference_name
         self.observation_space = Box(low=-np.inf, high=np.inf, shape=[8 + 17 * 2 + 14 * 2])
         self.action_space = Box(low=-1, high=1, shape=[17])
         self.max_frame = load_clip(reference_name)["max_frame"]
         self._make("low", [reference_name], 0, device, seed)
+        if self.useCustomEnv:
+            self.flat_env = _FlatEnvShim(self)
 
     def reset(self, resetYaw=0):
         # REF low_level_env.py:224-232: the start frame comes from the env's own generator
@@ -338,6 +374,8 @@ class LowLevelHumanoidEnv(_SingleEnv, _GymEnv):
         if not startFromRef:
             raise NotImplementedError("startFromRef=False (keep PyBullet's U(-0.1, 0.1) joint noise) is not part of "
                                       "the B200 path; every reference caller passes True")
+        if self.useCustomEnv:   # flat_env.reset() -> CustomScene.episode_restart: a new terrain every episode
+            self.flat_env.stadium_scene.episode_restart()
         xy = self._first_target_xy()
         deg = None if xy is not None else np.array([int(self.rng.integers(-180, 180))], np.int32)
         obs_dev = self._env.reset(start_frame=np.array([startFrame], np.int32), target_deg=deg,

@@ -151,6 +151,16 @@ int ilrl_set_state(ilrl_env* env, const float* phys_dev, const float* envf_dev, 
 /* Parity harness: the random heading the next target re-sampling uses, per env (INT32_MIN entry = draw normally);
  * NULL clears the override.  The pointer must stay valid until cleared. */
 int ilrl_set_forced_target_deg(ilrl_env* env, const int32_t* deg_dev);
+/* Heightfield terrain of the `useCustomEnv=True` low-level env (REF humanoid.py:68-144 CustomScene: 256 x 256 samples,
+ * 1 m cells, the terrain body at z = 0.25; REF env_vis_low.py:155-171 replaces the data with a ramp).  Replaces
+ * CustomScene.episode_restart's createCollisionShape(GEOM_HEIGHTFIELD, ...) / replaceHeightfieldData for every env of
+ * the handle (one terrain per handle).  heights_host[i + j * rows] as the reference's heightfieldData; world height of a
+ * sample = value + zoff (Bullet centres the shape on (min + max) / 2: zoff = 0.25 - (min + max) / 2 mirrors the
+ * reference).  The step then runs the terrain instantiation of the kernel: ground contacts against the plane of the
+ * triangle under each candidate sphere.  NULL = flat ground again.  Mode 0 only; slopes must stay below 45 degrees.
+ * Synchronises the device. */
+int ilrl_set_heightfield(ilrl_env* env, const float* heights_host, int32_t rows, int32_t cols, float zoff);
+
 /* Mode 2 parity harness.  hier_env_2's reset leaves WalkerBase.robot_specific_reset's joint noise (uniform(-0.1, 0.1))
  * in the six arm joints (its setJointsOrientation writes the abdomen and the legs only, REF hier_env_2.py:214-252).
  * noise17_dev [N,17] (ordered_joints order; only the arm entries matter): used by ilrl_reset and auto-resets instead

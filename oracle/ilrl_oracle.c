@@ -250,6 +250,50 @@ void ilrl_oracle_set_params(const double* p) {
     g_par.joint_damping[j] = p[7 + j]; g_par.joint_armature[j] = p[7 + NJ + j]; g_par.joint_stiffness[j] = p[7 + 2 * NJ + j];
   }
 }
+/* Heightfield terrain (REF humanoid.py:68-144 CustomScene: 256 x 256 samples, meshScale 1, body at z = 0.25).
+ * [BULLET, restated] btHeightfieldTerrainShape: sample (i, j) sits at x = i - (rows - 1) / 2, y = j - (cols - 1) / 2,
+ * z = data[i + j * rows] - (min + max) / 2 (+ the body position); a cell is cut along the diagonal (i+1, j) - (i, j+1).
+ * Contact model of this restatement (declared): every candidate sphere meets the PLANE of the triangle
+ * under its centre (face contacts only; edge / vertex contacts of a real triangle mesh are not modelled).
+ * zoff = body z - (min + max) / 2.  NULL = the flat ground plane z = 0.  Not thread-safe: set before stepping. */
+static const double* g_hf = 0;
+static int g_hf_rows = 0, g_hf_cols = 0;
+static double g_hf_zoff = 0;
+void ilrl_oracle_set_heightfield(const double* h, int rows, int cols, double zoff) {
+  g_hf = h; g_hf_rows = rows; g_hf_cols = cols; g_hf_zoff = zoff;
+}
+/* ground height under (x, y) and the unit normal of its triangle */
+static double terrain_sample(double x, double y, double* n) {
+  if (!g_hf) { n[0] = n[1] = 0; n[2] = 1; return 0; }
+  double fx = x + 0.5 * (g_hf_rows - 1), fy = y + 0.5 * (g_hf_cols - 1);
+  int i = (int)floor(fx), j = (int)floor(fy);
+  i = i < 0 ? 0 : (i > g_hf_rows - 2 ? g_hf_rows - 2 : i);
+  j = j < 0 ? 0 : (j > g_hf_cols - 2 ? g_hf_cols - 2 : j);
+  double u = fx - i, v = fy - j;
+  u = u < 0 ? 0 : (u > 1 ? 1 : u);
+  v = v < 0 ? 0 : (v > 1 ? 1 : v);
+  const double h00 = g_hf[i + j * g_hf_rows], h10 = g_hf[i + 1 + j * g_hf_rows];
+  const double h01 = g_hf[i + (j + 1) * g_hf_rows], h11 = g_hf[i + 1 + (j + 1) * g_hf_rows];
+  double gx, gy, h;
+  if (u + v <= 1) { gx = h10 - h00; gy = h01 - h00; h = h00 + u * gx + v * gy; }
+  else { gx = h11 - h01; gy = h11 - h10; h = h11 - (1 - u) * gx - (1 - v) * gy; }
+  const double il = 1.0 / sqrt(1 + gx * gx + gy * gy);
+  n[0] = -gx * il; n[1] = -gy * il; n[2] = il;
+  return h + g_hf_zoff;
+}
+/* btPlaneSpace1 */
+static void plane_space(const double* n, double* p, double* q) {
+  if (fabs(n[2]) > 0.7071067811865475244) {
+    double a = n[1] * n[1] + n[2] * n[2], k = 1.0 / sqrt(a);
+    p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+    q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+  } else {
+    double a = n[0] * n[0] + n[1] * n[1], k = 1.0 / sqrt(a);
+    p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+    q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+  }
+}
+
 /* Diagnostics (tools/model_sensitivity.py): extreme-event counters over all substeps since the last reset:
  * [0] substeps, [1] max joint-limit overshoot (rad), [2] substeps with overshoot > 0.5 rad, [3] max |torso v_z change| in one
  * substep (m/s), [4] substeps with |dv_z| > 2 m/s, [5] max torso height (m) */
@@ -357,7 +401,7 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
   }
 
   /* ---- constraint rows: violated joint limits, then contact normals, then 2 friction rows per contact */
-  static const double tdir[2][3] = {{0, -1, 0}, {1, 0, 0}}; /* btPlaneSpace1((0,0,1)) */
+  /* flat ground: normal (0,0,1), tangents btPlaneSpace1((0,0,1)) = (0,-1,0), (1,0,0) */
   double J[MAXROWS][NV], Rsp[MAXROWS][NV], rrhs[MAXROWS], dinv[MAXROWS], lam[MAXROWS];
   int nlim = 0, ncon = 0;
   if (!(flags & 8))
@@ -379,13 +423,14 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
   if (!(flags & 4)) {
     /* candidate set: every sphere closer than the breaking threshold; if more than ILRL_MAX_CONTACTS, drop the
      * shallowest (largest distance, ties -> highest index) until the cap holds; rows then follow table order */
-    double sdist[NS], sc[NS][3];
+    double sdist[NS], sc[NS][3], sn[NS][3];
     int act[NS], nact = 0;
     for (int s = 0; s < NS; s++) {
       int b = sphere_body[s];
       matvec3(k.R[b], sphere_c + 3 * s, sc[s]);
       for (int i = 0; i < 3; i++) sc[s][i] += k.o[b][i];
-      sdist[s] = sc[s][2] - sphere_r[s];
+      const double hgt = terrain_sample(sc[s][0], sc[s][1], sn[s]);
+      sdist[s] = (sc[s][2] - hgt) * sn[s][2] - sphere_r[s];   /* distance of the sphere to the plane under its centre */
       act[s] = sdist[s] < ILRL_CONTACT_BREAK;
       nact += act[s];
     }
@@ -400,15 +445,16 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
       if (!act[s]) continue;
       int b = sphere_body[s];
       double dist = sdist[s];
-      double x[3] = {sc[s][0], sc[s][1], sc[s][2] - sphere_r[s]};
-      double Jw[NV][3], Jv[NV][3];
+      double x[3] = {sc[s][0] - sphere_r[s] * sn[s][0], sc[s][1] - sphere_r[s] * sn[s][1], sc[s][2] - sphere_r[s] * sn[s][2]};
+      double Jw[NV][3], Jv[NV][3], t1[3], t2[3];
+      plane_space(sn[s], t1, t2);
       point_jac(&k, p0, body_link[b], x, Jw, Jv);
       int r = nlim + 3 * ncon;
       crow[ncon++] = r;
       for (int c2 = 0; c2 < NV; c2++) {
-        J[r][c2] = Jv[c2][2];
-        J[r + 1][c2] = dot3(Jv[c2], tdir[0]);
-        J[r + 2][c2] = dot3(Jv[c2], tdir[1]);
+        J[r][c2] = dot3(Jv[c2], sn[s]);
+        J[r + 1][c2] = dot3(Jv[c2], t1);
+        J[r + 2][c2] = dot3(Jv[c2], t2);
       }
       /* Bullet: penetration > 0 -> speculative row (velocityError -= pen/dt), else ERP push-out */
       rrhs[r] = dist > 0 ? -dist / dt : -dist * g_par.contact_erp / dt;

@@ -65,6 +65,7 @@ def lib():
         L.ilrl_oracle_endpoint_score.argtypes = [C.c_void_p]
         L.ilrl_oracle_endpoint_score.restype = C.c_double
         L.ilrl_oracle_env_refresh.argtypes = [C.c_void_p]
+        L.ilrl_oracle_set_heightfield.argtypes = [_dp, C.c_int, C.c_int, C.c_double]
         _lib = L
     return _lib
 
@@ -104,6 +105,29 @@ def fk(phys):
     bo, ao, br = np.zeros((15, 3)), np.zeros((17, 3)), np.zeros((15, 9))
     lib().ilrl_oracle_fk(_d(phys), _d(bo), _d(ao), _d(br))
     return bo, ao, br.reshape(15, 3, 3)
+
+
+_hf_keep = None
+
+
+def heightfield_zoff(data, body_z=0.25):
+    """world z of a sample = data + zoff: Bullet centres the shape on (min + max) / 2 and REF humanoid.py:130 puts the
+    terrain body at z = 0.25"""
+    d = np.asarray(data, dtype=np.float64)
+    return body_z - 0.5 * (float(d.min()) + float(d.max()))
+
+
+def set_heightfield(data, rows=256, cols=256, body_z=0.25):
+    """Heightfield terrain for every physics call of this process (None = flat ground).  data[i + j * rows], as the
+    reference's CustomScene.heightfieldData (REF humanoid.py:74)."""
+    global _hf_keep
+    if data is None:
+        _hf_keep = None
+        lib().ilrl_oracle_set_heightfield(None, 0, 0, 0.0)
+        return
+    _hf_keep = np.ascontiguousarray(data, dtype=np.float64).reshape(-1)
+    assert _hf_keep.size == rows * cols
+    lib().ilrl_oracle_set_heightfield(_d(_hf_keep), rows, cols, heightfield_zoff(_hf_keep, body_z))
 
 
 def energy(phys):

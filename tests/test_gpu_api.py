@@ -54,7 +54,7 @@ def test_low_level_env_matches_oracle_over_an_episode():
     with pytest.raises(AssertionError):
         env.step(np.full(17, np.nan))
     with pytest.raises(NotImplementedError):
-        LowLevelHumanoidEnv(useCustomEnv=True)
+        env.resetFromFrame(startFrame=0, startFromRef=False)
     env.close()
 
 
@@ -840,3 +840,29 @@ def test_hier2_base_env_adapter():
                 new_obs[i] = be.try_reset(i)
         obs = new_obs
     be.stop()
+
+
+def test_use_custom_env_terrain_view():
+    """LowLevelHumanoidEnv(useCustomEnv=True) (REF low_level_env.py:43-47, humanoid.py:68-144): a new random terrain at
+    every reset, replaceable through env.flat_env.stadium_scene.replaceHeightfieldData as REF env_vis_low.py:155-171 does."""
+    env = LowLevelHumanoidEnv(reference_name="motion09_03", useCustomEnv=True, seed=1)
+    sc = env.flat_env.stadium_scene
+    env.reset()
+    d0 = np.array(sc.heightfieldData).reshape(256, 256)
+    assert 0.4 < d0.max() <= 0.5 and d0.min() == 0 and (d0[126:130, 126:130] == 0).all()
+    assert (d0[0::2, 0::2] == d0[1::2, 1::2]).all()
+    env.reset()
+    assert (np.array(sc.heightfieldData).reshape(256, 256) != d0).any()
+    terrain = [0] * 256 * 256
+    for j in range(63 - 5, 64 + 5 + 1):
+        for i in range(63, 68):
+            terrain[2 * i + 2 * j * 256] = terrain[2 * i + 1 + 2 * j * 256] = (i - 63) / 10
+            terrain[2 * i + (2 * j + 1) * 256] = terrain[2 * i + 1 + (2 * j + 1) * 256] = (i - 63) / 10
+    env.resetFromFrame(startFrame=0, startFromRef=True, initVel=True)
+    sc.replaceHeightfieldData(terrain)
+    for k in range(30):
+        obs, rew, done, _ = env.step(np.zeros(17))
+        assert np.isfinite(obs).all() and np.isfinite(rew)
+        if done:
+            break
+    env.close()

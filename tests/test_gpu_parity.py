@@ -429,3 +429,92 @@ def test_hier2_auto_reset_and_rollout_invariants():
     st = env.stats().cpu().numpy()
     assert st[0] == episodes
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------- heightfield terrain (f4)
+def _reference_terrain(seed):
+    """CustomScene.episode_restart (REF humanoid.py:88-124): 2 x 2 sample plateaus of U(0, 0.5), flat centre blocks."""
+    rng = np.random.default_rng(seed)
+    h = np.repeat(np.repeat(rng.uniform(0, 0.5, (128, 128)), 2, axis=0), 2, axis=1)    # h[j, i]
+    h[126:130, 126:130] = 0.0
+    return h.reshape(-1)                                                              # data[i + j * 256]
+
+
+def _ramp_terrain():
+    """REF env_vis_low.py:155-163 ('tanjakan')"""
+    d = np.zeros(256 * 256)
+    for j in range(63 - 5, 64 + 5 + 1):
+        for i in range(63, 68):
+            for di in (0, 1):
+                for dj in (0, 1):
+                    d[2 * i + di + (2 * j + dj) * 256] = (i - 63) / 10
+    return d
+
+
+@pytest.mark.parametrize("terrain", ["random", "ramp", "flat"])
+def test_terrain_single_step_dynamics_matches_oracle(terrain):
+    """Ground contact against the heightfield: one env step of the terrain instantiation of the kernel vs the fp64
+    oracle with the same heightfield, from identical states scattered over the terrain near the ground."""
+    data = {"random": _reference_terrain(3), "ramp": _ramp_terrain(), "flat": np.zeros(256 * 256)}[terrain]
+    rng = np.random.default_rng(8)
+    n = 512
+    p0 = _random_states(rng, n, False)
+    span = 1.0 if terrain == "ramp" else 40.0
+    p0[:, 0] = rng.uniform(-1.5, 7.5, n) if terrain == "ramp" else rng.uniform(-span, span, n)
+    p0[:, 1] = rng.uniform(-4, 4, n) if terrain == "ramp" else rng.uniform(-span, span, n)
+    p0[:, 2] += 0.25           # plateaus reach 0.5 m
+    p0 = p0.astype(np.float32).astype(np.float64)
+    tau = (rng.uniform(-40, 40, (n, 17)) * (rng.uniform(size=(n, 1)) < 0.7)).astype(np.float32).astype(np.float64)
+    O.set_heightfield(data.astype(np.float32).astype(np.float64))
+    try:
+        want = np.stack([O.physics_step(p0[i], tau[i]) for i in range(n)])
+        O.set_heightfield(None)
+        flat = np.stack([O.physics_step(p0[i], tau[i]) for i in range(n)])
+    finally:
+        O.set_heightfield(None)
+    if terrain != "flat":   # the terrain matters for a good share of these states
+        assert (np.abs(want - flat).max(axis=1) > 1e-3).mean() > 0.3
+    env = BatchedHumanoidEnv(n, "low", auto_reset=False)
+    env.set_heightfield(data)
+    env.set_state(p0.astype(np.float32), None)
+    env.physics_only(tau.astype(np.float32))
+    got = env.get_state()[0].cpu().numpy().astype(np.float64)
+    assert np.isfinite(got).all()
+    _check_phys(got, want, True, "terrain %s" % terrain)
+    # back to flat ground: identical to a handle that never had a terrain
+    env.set_heightfield(None)
+    env.set_state(p0.astype(np.float32), None)
+    env.physics_only(tau.astype(np.float32))
+    a = env.get_state()[0].cpu().numpy()
+    env2 = BatchedHumanoidEnv(n, "low", auto_reset=False)
+    env2.set_state(p0.astype(np.float32), None)
+    env2.physics_only(tau.astype(np.float32))
+    np.testing.assert_array_equal(a, env2.get_state()[0].cpu().numpy())
+    env.close(); env2.close()
+
+
+def test_terrain_full_step_and_error_paths():
+    """The fused step on a terrain (reward / obs / bookkeeping unchanged, physics on the heightfield) and the C ABI's
+    argument checks."""
+    n = 256
+    data = _reference_terrain(5)
+    env = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], auto_reset=True, seed=3)
+    env.set_heightfield(data)
+    env.reset()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    zmin = 10.0
+    for t in range(200):
+        obs, rew, done, terms = env.step(torch.rand(n, 17, device="cuda", generator=g) * 2 - 1)
+        assert bool(torch.isfinite(obs).all()) and bool(torch.isfinite(rew).all())
+    phys, _ = env.get_state()
+    assert float(phys[:, 2].min()) > -0.2 and float(phys[:, 2].max()) < 25.0
+    st = env.stats().cpu().numpy()
+    assert st[0] > n and 5 < st[2] / st[0] < 200          # episodes end and restart on the terrain as on flat ground
+    steep = np.zeros(256 * 256); steep[300] = 2.0
+    with pytest.raises(ilrl_b200._lib.IlrlError):
+        env.set_heightfield(steep)                          # a 63-degree triangle
+    env.close()
+    hier = BatchedHumanoidEnv(8, "hier", clips=["motion08_03", "motion09_03"], auto_reset=False)
+    with pytest.raises(ilrl_b200._lib.IlrlError):
+        hier.set_heightfield(data)
+    hier.close()

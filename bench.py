@@ -343,7 +343,9 @@ def measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks=None, mi
     (1) `async`: ilrl_step_host_async / ilrl_wait with the batch cut in E2E_PARTS parts, each on its own stream, stepped
         as a software pipeline (the way a rollout worker overlaps its own work with the env; the host reads the part's
         results between its wait and its next submit): the headline end-to-end number;
-    (2) `sync`: one blocking ilrl_step_host per step (launch + PCIe + synchronise exposed every step)."""
+    (2) `sync`: one blocking ilrl_step_host per step (launch + PCIe + synchronise exposed every step);
+    (3) `serve`: one blocking ilrl_serve_step per step against the resident serving kernel (no launch, no stream
+        synchronise; begin / end of the session inside every timed block).  Batches that fit one wave only."""
     import torch
     import torch.distributed as dist
     dev = torch.device("cuda", local_rank)
@@ -364,11 +366,20 @@ def measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks=None, mi
     P = E2E_PARTS
     sl = [env.part_slice(p, P) for p in range(P)]
     sink = [0.0]
-    for kind in ("async", "sync"):
+    for kind in ("async", "sync", "serve"):
         if kind == "async" and hier:
             continue   # the hierarchical env needs its high-level call between the parts: only the blocking path is timed
+        if kind == "serve" and (hier or n > 4096):
+            continue
         def run(k):
-            if kind == "sync":
+            if kind == "serve":
+                env.serve_begin(obs_h, rew_h, done_h)
+                for _ in range(k):
+                    i = steps[0]
+                    steps[0] += 1
+                    env.serve_step(host_act[i % NH])
+                env.serve_end()
+            elif kind == "sync":
                 for _ in range(k):
                     i = steps[0]
                     if hier:
@@ -537,7 +548,10 @@ def run_ours(args):
                             "step kernel" % E2E_PARTS) if "async" in e2e else
                            "ilrl_step_host (C ABI, pinned + mapped host buffers, blocking)",
                     "sync_value": res["n_all"] * K / e2e["sync"]["s_block"],
-                    "sync_api": "ilrl_step_host: one blocking call per step (launch + PCIe + synchronise exposed every step)"},
+                    "sync_api": "ilrl_step_host: one blocking call per step (launch + PCIe + synchronise exposed every step)",
+                    "serve_value": None if "serve" not in e2e else res["n_all"] * K / e2e["serve"]["s_block"],
+                    "serve_api": "ilrl_serve_step: one blocking call per step against the resident serving kernel (doorbell in "
+                                 "mapped host memory: no launch, no stream synchronise; session begin / end inside each block)"},
             "gpu_launches": res["launches_per_block"],
             "clocks": clk,
         }

@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 #include <string>
@@ -147,30 +148,14 @@ __device__ __forceinline__ void set_torques(SM& sm, int e, int tid, int role, co
 // of 72 / 60 words, per-env jointTarget).  Four lanes = one env (ilrl_chain.cuh): the physics substeps run distributed
 // over the quad; the env bookkeeping after them is computed redundantly by the four lanes (identical instruction
 // stream, no divergence) and the outputs are dealt to the lanes for the stores.
-template <int MODE, class SM, bool TERR = false>
-__global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  SM& sm = *reinterpret_cast<SM*>(smraw);
+// One tile (QE envs) of one env step: everything between a CTA picking its tile and moving on.  Shared by the
+// launch-per-step kernel and the persistent serving kernel (K1s).  action: the [n,17] action array of this step.
+template <int MODE, class SM, bool TERR>
+__device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int tile, const float* __restrict__ action) {
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
   constexpr int OBSW = MODE == 2 ? ILRL_OBS_LOW2 : ILRL_OBS_LOW, HOBSW = MODE == 2 ? ILRL_OBS_HIGH2 : ILRL_OBS_HIGH;
   static_assert(SM::ES >= OBSW, "the obs row is staged in the env's scratch block");
-  if (a.ktime && tid == 0) atomicMin(a.ktime, globaltimer_ns());
-  quad_smem_init(sm);
-  // Persistent CTAs: the grid is at most what is resident at once (SMs x CTAs per SM) and tiles of QE envs are handed
-  // out through an atomic counter, so a large batch has no partially filled last wave and no per-tile table copy, and
-  // CTAs that drew cheap tiles simply take more of them.  The last CTA to leave resets the counters (graph-safe).
-  // (The first tile of a CTA is its own index: a batch that fits one wave never touches the counter.)
-  __shared__ int s_tile;
-  const bool one_wave = a.ntiles <= (int)gridDim.x;
-  for (int it = 0;; it++) {
-  if (it > 0) {
-    if (one_wave) break;
-    if (tid == 0) s_tile = (int)gridDim.x + (int)atomicAdd(a.tile_counter, 1u);
-  } else if (tid == 0) s_tile = (int)blockIdx.x;
-  __syncthreads();
-  const int tile = s_tile;
-  if (tile >= a.ntiles) break;
   const int base = a.first + tile * QE;
   const int i = base + e;
   const bool valid = i < a.end;
@@ -187,7 +172,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
 #pragma unroll
   for (int m = 0; m < (NJ + 3) / 4; m++) av[m] = 0.f;
   if (valid) {  // (the 8 action rows of a warp are one contiguous 544-byte block)
-    const float* arow = a.action + (size_t)i * NJ;
+    const float* arow = action + (size_t)i * NJ;
 #pragma unroll
     for (int m = 0; m < (NJ + 3) / 4; m++) if (role + 4 * m < NJ) av[m] = arow[role + 4 * m];
     if (MODE >= 1) pend_flag = a.envf[(size_t)ILRL_E_HIGH_PENDING * a.n + i];
@@ -412,12 +397,105 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   if (pf.p) pf.p[chain::PF_TOTAL] += clock64() - t_tile;
 #endif
   __syncthreads();  // every warp is done with this tile's shared memory (and with s_tile) before the next one
+}
+
+
+template <int MODE, class SM, bool TERR = false>
+__global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  SM& sm = *reinterpret_cast<SM*>(smraw);
+  const int tid = threadIdx.x;
+  if (a.ktime && tid == 0) atomicMin(a.ktime, globaltimer_ns());
+  quad_smem_init(sm);
+  // Persistent CTAs: the grid is at most what is resident at once (SMs x CTAs per SM) and tiles of QE envs are handed
+  // out through an atomic counter, so a large batch has no partially filled last wave and no per-tile table copy, and
+  // CTAs that drew cheap tiles simply take more of them.  The last CTA to leave resets the counters (graph-safe).
+  // (The first tile of a CTA is its own index: a batch that fits one wave never touches the counter.)
+  __shared__ int s_tile;
+  const bool one_wave = a.ntiles <= (int)gridDim.x;
+  for (int it = 0;; it++) {
+  if (it > 0) {
+    if (one_wave) break;
+    if (tid == 0) s_tile = (int)gridDim.x + (int)atomicAdd(a.tile_counter, 1u);
+  } else if (tid == 0) s_tile = (int)blockIdx.x;
+  __syncthreads();
+  const int tile = s_tile;
+  if (tile >= a.ntiles) break;
+  step_tile<MODE, SM, TERR>(a, sm, tile, a.action);
   }  // tile loop
   if (!one_wave && tid == 0 && atomicAdd(a.tile_counter + 1, 1u) == gridDim.x - 1) {  // last CTA out: ready for the next launch
     a.tile_counter[0] = 0u;
     a.tile_counter[1] = 0u;
   }
   if (a.ktime && tid == 0) atomicMax(a.ktime + 1, globaltimer_ns());
+}
+
+// ------------------------------------------------------------------------------------------------ K1s: persistent serving
+// The end-to-end path pays, per env step, a kernel launch and a stream synchronisation (~13 us of a 90 us step) although
+// the kernel itself is latency-bound at ~75 us.  Between ilrl_serve_begin and ilrl_serve_end ONE launch of this kernel
+// stays resident (the batch must fit one wave: every CTA owns one tile for the whole session) and the host drives it
+// through a doorbell in mapped, page-locked host memory:
+//   host:  actions already in their mapped buffer -> ctl.action = its device alias, ctl.seq = t (store order; x86 TSO)
+//   CTA 0: polls ctl.seq over PCIe, republishes {action, seq} in device memory; the other CTAs poll that copy in L2
+//   CTAs:  one step_tile each (reading the actions from / writing obs, reward, done to the mapped host buffers in place)
+//   last CTA to finish (device counter): system-scope fence, then ack = t into mapped host memory; the host spins on it.
+// A watchdog ends the kernel when no doorbell arrives for `timeout_ns` (a host that died must not leave the GPU busy).
+struct ServeCtl {            // mapped host memory, written by the host
+  volatile long long action; // device alias of this step's [n,17] actions
+  volatile int seq;          // step number, > 0; -1 = quit
+  int pad;
+};
+struct ServeDev {            // device memory
+  volatile long long action;
+  volatile int seq;
+  unsigned int arrive;
+};
+template <int MODE, class SM>
+__global__ void __launch_bounds__(QT) serve_kernel(const StepArgs a, const ServeCtl* ctl, ServeDev* dv, volatile int* ack,
+                                                   unsigned long long timeout_ns) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  SM& sm = *reinterpret_cast<SM*>(smraw);
+  const int tid = threadIdx.x;
+  __shared__ int s_seq;
+  __shared__ long long s_action;
+  quad_smem_init(sm);
+  int last = 0;
+  for (;;) {
+    if (tid == 0) {
+      int q;
+      long long act = 0;
+      if (blockIdx.x == 0) {
+        const unsigned long long t0 = globaltimer_ns();
+        while ((q = ctl->seq) == last) {
+          if (globaltimer_ns() - t0 > timeout_ns) { q = -2; break; }
+          __nanosleep(200);
+        }
+        if (q > 0) act = ctl->action;   // (written before seq by the host)
+        dv->action = act;
+        __threadfence();
+        dv->seq = q;
+      } else {
+        while ((q = dv->seq) == last) __nanosleep(100);
+        __threadfence();
+        act = dv->action;
+      }
+      s_seq = q; s_action = act;
+    }
+    __syncthreads();
+    const int seq = s_seq;
+    if (seq < 0) break;
+    last = seq;
+    if ((int)blockIdx.x < a.ntiles)
+      step_tile<MODE, SM, false>(a, sm, (int)blockIdx.x, reinterpret_cast<const float*>(s_action));
+    if (tid == 0) {
+      __threadfence_system();   // this CTA's rows have left for host memory before it is counted
+      if (atomicAdd(&dv->arrive, 1u) == gridDim.x - 1) {
+        dv->arrive = 0u;
+        __threadfence_system();
+        *ack = seq;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ K2: reset
@@ -761,6 +839,14 @@ struct ilrl_env {
   int layout = 0;                // shared-memory layout of the step kernel: 0 LayoutSmall, 1 LayoutLarge, 2 LayoutDense4
                                  // (chosen at create time from N)
   bool no_zero_copy = false;     // harness only (ilrl_debug_zero_copy): force the explicit-copy host path
+  // ilrl_serve_*: the resident serving kernel and its doorbell
+  bool serving = false;
+  cudaStream_t serve_stream = nullptr;
+  ServeCtl* serve_ctl = nullptr;          // mapped host memory (+ the ack word behind it)
+  volatile int* serve_ack = nullptr;
+  ServeDev* serve_dev = nullptr;
+  int serve_seq = 0;
+  int serve_posted = 0;
   int64_t launches = 0;
   bool timing = false;           // ilrl_kernel_timing: the step kernels stamp %globaltimer into ktime[slot]
   unsigned long long* ktime = nullptr;   // [KT_SLOTS][2] device
@@ -794,9 +880,15 @@ struct DeviceGuard {
   }
   ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
-#define ON_DEVICE(env) DeviceGuard _dg((env)->cfg.device); CK(_dg.status)
+#define ON_DEVICE_RAW(env) DeviceGuard _dg((env)->cfg.device); CK(_dg.status)
+// (between ilrl_serve_begin and ilrl_serve_end the handle belongs to its resident kernel: only ilrl_serve_* may be called)
+#define ON_DEVICE(env)                                                                                              \
+  if ((env)->serving) return fail(env, ILRL_ERR_STATE, "the handle is serving (ilrl_serve_begin): call ilrl_serve_end first"); \
+  ON_DEVICE_RAW(env)
 
 extern "C" {
+
+int ilrl_serve_end(ilrl_env* env);
 
 const char* ilrl_last_error(const ilrl_env* env) { return env ? env->err.c_str() : g_create_err.c_str(); }
 
@@ -926,6 +1018,7 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
 
 void ilrl_destroy(ilrl_env* env) {
   if (!env) return;
+  if (env->serving) ilrl_serve_end(env);
   DeviceGuard dg(env->cfg.device);
   cudaDeviceSynchronize();
   for (int p = 0; p < ILRL_MAX_PARTS; p++) {
@@ -933,6 +1026,9 @@ void ilrl_destroy(ilrl_env* env) {
   }
   cudaFree(env->clip_ids_dev);
   cudaFree(env->terr_mem);
+  if (env->serve_stream) cudaStreamDestroy(env->serve_stream);
+  cudaFreeHost(env->serve_ctl);
+  cudaFree(env->serve_dev);
   cudaFreeHost(env->h_pull);
   cudaFree(env->ktime);
   cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr); cudaFree(env->jt);
@@ -1263,6 +1359,116 @@ int ilrl_pull(ilrl_env* env, const float* obs_dev, float* pull_host, void* strea
   ON_DEVICE(env);
   if (int r = ensure_io_buffers(env)) return r;
   return do_pull(env, pull_host, obs_dev, (cudaStream_t)stream);
+}
+
+// ---- persistent serving (K1s)
+static const unsigned long long SERVE_WATCHDOG_NS = 2000000000ull;   // the kernel leaves after 2 s without a doorbell
+static double now_s() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+int ilrl_serve_begin(ilrl_env* env, float* obs_h, float* reward_h, uint8_t* done_h, float* terms_h) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!obs_h || !reward_h || !done_h) return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: null buffer");
+  if (int r = check_ready(env)) return r;
+  ON_DEVICE(env);
+  if (env->cfg.mode != 0) return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: low-level mode only (the hierarchical modes need their high-level call between steps)");
+  if (env->terr.h) return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: not available with a heightfield terrain");
+  const int ntiles = (env->n + QE - 1) / QE;
+  if (ntiles > env->grid_small)
+    return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: the batch must fit one wave of resident CTAs (N <= 16 x SMs x 2): use ilrl_step_host_async");
+  for (int p = 0; p < ILRL_MAX_PARTS; p++) if (env->part_busy[p]) return fail(env, ILRL_ERR_STATE, "ilrl_serve_begin: a part is still in flight");
+  void *dobs, *dr, *dd, *dt = nullptr;
+  if (!(dobs = host_alias(env, obs_h)) || !(dr = host_alias(env, reward_h)) || !(dd = host_alias(env, done_h)) ||
+      (terms_h && !(dt = host_alias(env, terms_h))))
+    return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: buffers must be page-locked and mapped");
+  if (!env->serve_stream) CK(cudaStreamCreateWithFlags(&env->serve_stream, cudaStreamNonBlocking));
+  if (!env->serve_ctl) {
+    CK(cudaHostAlloc((void**)&env->serve_ctl, 256, cudaHostAllocMapped));
+    CK(cudaMalloc((void**)&env->serve_dev, sizeof(ServeDev)));
+  }
+  memset((void*)env->serve_ctl, 0, 256);
+  env->serve_ack = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(env->serve_ctl) + 128);   // its own cache line
+  CK(cudaMemset(env->serve_dev, 0, sizeof(ServeDev)));
+  CK(cudaDeviceSynchronize());
+  void* ctl_dev = nullptr;
+  CK(cudaHostGetDevicePointer(&ctl_dev, (void*)env->serve_ctl, 0));
+  StepArgs a;
+  a.n = env->n; a.first = 0; a.end = env->n; a.skip_frame = env->cfg.skip_frame;
+  a.id_base = env->cfg.env_id_base; a.skip_physics = 0; a.auto_reset = env->cfg.auto_reset; a.max_timestep = env->cfg.max_timestep;
+  a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
+  a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
+  a.action = nullptr; a.obs = (float*)dobs; a.reward = (float*)dr; a.done = (uint8_t*)dd; a.terms = (float*)dt;
+  a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
+  a.forced_deg = env->forced_deg; a.forced_scalar = INT_MIN; a.stats = env->stats; a.gscr = env->gscr;
+  a.jt = env->jt; a.forced_noise = env->forced_noise; a.terr = env->terr;
+  a.tile_counter = env->tile_counter; a.ntiles = ntiles; a.ktime = nullptr;
+#ifdef ILRL_PROF
+  a.prof = nullptr;
+#endif
+  memcpy(a.clips, env->clips, sizeof a.clips);
+  CK(cudaFuncSetAttribute(serve_kernel<0, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
+  serve_kernel<0, SmemSmall><<<ntiles, QT, sizeof(SmemSmall), env->serve_stream>>>(
+      a, (const ServeCtl*)ctl_dev, env->serve_dev, (volatile int*)((char*)ctl_dev + 128), SERVE_WATCHDOG_NS);
+  env->launches++;
+  CK(cudaGetLastError());
+  env->serving = true;
+  env->serve_seq = 0;
+  env->serve_posted = 0;
+  return ILRL_OK;
+}
+int ilrl_serve_post(ilrl_env* env, const float* action_h) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!env->serving) return fail(env, ILRL_ERR_STATE, "ilrl_serve_post: not serving (ilrl_serve_begin first)");
+  if (env->serve_posted) return fail(env, ILRL_ERR_STATE, "ilrl_serve_post: the previous step has not been waited for");
+  void* da = action_h ? host_alias(env, action_h) : nullptr;
+  if (!da) return fail(env, ILRL_ERR_ARG, "ilrl_serve_post: actions must be in page-locked, mapped host memory");
+  env->serve_ctl->action = (long long)(uintptr_t)da;
+  __atomic_thread_fence(__ATOMIC_RELEASE);
+  env->serve_ctl->seq = ++env->serve_seq;
+  env->serve_posted = 1;
+  return ILRL_OK;
+}
+int ilrl_serve_wait(ilrl_env* env) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!env->serving) return fail(env, ILRL_ERR_STATE, "ilrl_serve_wait: not serving");
+  if (!env->serve_posted) return ILRL_OK;
+  const int want = env->serve_seq;
+  double t0 = 0.0;
+  for (unsigned spins = 0; *env->serve_ack != want; spins++) {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+    if ((spins & 0xffffu) == 0xffffu) {   // rarely: has the kernel died (watchdog, device error)?
+      if (t0 == 0.0) t0 = now_s();
+      if (cudaStreamQuery(env->serve_stream) != cudaErrorNotReady || now_s() - t0 > 10.0) {
+        env->serving = false;
+        env->serve_posted = 0;
+        cudaGetLastError();
+        return fail(env, ILRL_ERR_STATE, "ilrl_serve_wait: the serving kernel is gone (watchdog after 2 s without a step, or a device error)");
+      }
+    }
+  }
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  env->serve_posted = 0;
+  return ILRL_OK;
+}
+int ilrl_serve_step(ilrl_env* env, const float* action_h) {
+  if (int r = ilrl_serve_post(env, action_h)) return r;
+  return ilrl_serve_wait(env);
+}
+int ilrl_serve_end(ilrl_env* env) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!env->serving) return ILRL_OK;
+  ON_DEVICE_RAW(env);
+  if (env->serve_posted) ilrl_serve_wait(env);
+  env->serve_ctl->seq = -1;
+  cudaError_t r = cudaStreamSynchronize(env->serve_stream);
+  env->serving = false;
+  env->serve_posted = 0;
+  if (r != cudaSuccess) return fail(env, ILRL_ERR_CUDA, std::string("ilrl_serve_end: ") + cudaGetErrorString(r));
+  return ILRL_OK;
 }
 
 int ilrl_set_config(ilrl_env* env, int32_t max_timestep, int32_t step_per_level, int32_t skip_frame) {

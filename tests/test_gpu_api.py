@@ -866,3 +866,66 @@ def test_use_custom_env_terrain_view():
         if done:
             break
     env.close()
+
+
+def test_persistent_serving_matches_step_host():
+    """ilrl_serve_*: one resident kernel driven through a doorbell in mapped host memory gives bit-identical steps to
+    ilrl_step_host; the handle is locked while serving; the watchdog frees the GPU when the host stops stepping."""
+    import time
+    n, K = 1000, 40          # (not a multiple of 16: the last tile is partly filled)
+    pin = lambda shape, dt: torch.zeros(*shape, dtype=dt).pin_memory().numpy()  # noqa: E731
+    rng = np.random.default_rng(3)
+    acts = [pin((n, 17), torch.float32) for _ in range(4)]
+    outs = {}
+    for kind in ("host", "serve"):
+        env = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], auto_reset=True, seed=9)
+        env.reset()
+        o_h, r_h, d_h, t_h = pin((n, 70), torch.float32), pin((n,), torch.float32), pin((n,), torch.uint8), pin((n, 12), torch.float32)
+        rng = np.random.default_rng(3)
+        rec = []
+        if kind == "serve":
+            env.serve_begin(o_h, r_h, d_h, t_h)
+            with pytest.raises(ilrl_b200._lib.IlrlError):
+                env.reset()                                   # the handle belongs to its resident kernel
+        for k in range(K):
+            a = acts[k % 4]
+            a[:] = rng.uniform(-1, 1, (n, 17)).astype(np.float32)
+            if kind == "serve":
+                if k % 2:
+                    env.serve_post(a)
+                    env.serve_wait()
+                else:
+                    env.serve_step(a)
+            else:
+                env.step_host(a, o_h, r_h, d_h, t_h)
+            rec.append((o_h.copy(), r_h.copy(), d_h.copy(), t_h.copy()))
+        if kind == "serve":
+            env.serve_end()
+            env.serve_end()                                   # idempotent
+        phys, envf = [t.cpu().numpy() for t in env.get_state()]
+        outs[kind] = (rec, phys, envf, env.stats().cpu().numpy())
+        env.close()
+    for (a, b) in zip(outs["host"][0], outs["serve"][0]):
+        for x, y in zip(a, b):
+            np.testing.assert_array_equal(x, y)
+    np.testing.assert_array_equal(outs["host"][1], outs["serve"][1])
+    np.testing.assert_array_equal(outs["host"][2], outs["serve"][2])
+    np.testing.assert_array_equal(outs["host"][3], outs["serve"][3])
+    assert sum(int(r[2].sum()) for r in outs["serve"][0]) > 0      # episodes ended and restarted while serving
+    # argument checks
+    big = BatchedHumanoidEnv(8192, "low", clips=["motion09_03"])
+    with pytest.raises(ilrl_b200._lib.IlrlError):
+        big.serve_begin(pin((8192, 70), torch.float32), pin((8192,), torch.float32), pin((8192,), torch.uint8))
+    big.close()
+    # watchdog: a host that stops stepping does not keep the GPU
+    env = BatchedHumanoidEnv(64, "low", clips=["motion09_03"])
+    env.reset()
+    o_h, r_h, d_h = pin((64, 70), torch.float32), pin((64,), torch.float32), pin((64,), torch.uint8)
+    a = pin((64, 17), torch.float32)
+    env.serve_begin(o_h, r_h, d_h)
+    env.serve_step(a)
+    time.sleep(2.6)
+    with pytest.raises(ilrl_b200._lib.IlrlError):
+        env.serve_step(a)
+    env.reset()                                                # the handle is usable again
+    env.close()

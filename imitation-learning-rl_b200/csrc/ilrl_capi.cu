@@ -151,7 +151,7 @@ __device__ __forceinline__ void set_torques(SM& sm, int e, int tid, int role, co
 // One tile (QE envs) of one env step: everything between a CTA picking its tile and moving on.  Shared by the
 // launch-per-step kernel and the persistent serving kernel (K1s).  action: the [n,17] action array of this step.
 template <int MODE, class SM, bool TERR>
-__device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int tile, const float* __restrict__ action) {
+__device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int tile, const float* action) {
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
   constexpr int OBSW = MODE == 2 ? ILRL_OBS_LOW2 : ILRL_OBS_LOW, HOBSW = MODE == 2 ? ILRL_OBS_HIGH2 : ILRL_OBS_HIGH;

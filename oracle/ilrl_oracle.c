@@ -630,6 +630,7 @@ typedef struct {
   double e[ILRL_ENV_WORDS];
   double terms[ILRL_TERM_WORDS];
   orc_calc cs; /* last calc_state */
+  int skip;    /* skipFrame (REF low_level_env.py:162; 0 = the reference's 2) */
 } orc_env;
 
 orc_env* ilrl_oracle_env_create(int mode, const double* pos, const double* rel, const double* vel, const double* ep,
@@ -644,6 +645,9 @@ orc_env* ilrl_oracle_env_create(int mode, const double* pos, const double* rel, 
   return v;
 }
 void ilrl_oracle_env_destroy(orc_env* v) { free(v); }
+/* the reference's drivers assign env.skipFrame; earlier versions of the env (the ones its shipped checkpoints were
+ * trained on, REF Log/catatan_low_level.txt:596-640) ran with skipFrame 1 */
+void ilrl_oracle_env_set_skip(orc_env* v, int skip) { v->skip = skip; }
 void ilrl_oracle_env_get(const orc_env* v, double* phys, double* e, double* terms) {
   memcpy(phys, v->phys, sizeof v->phys);
   memcpy(e, v->e, sizeof v->e);
@@ -756,7 +760,7 @@ void ilrl_oracle_env_reset(orc_env* v, int start_frame, double reset_yaw_deg, in
     e[ILRL_E_STEPS_REMAINING] = 5;
     e[ILRL_E_HIGH_PENDING] = 1;
   }
-  inc_frame(v, 2);
+  inc_frame(v, v->skip > 0 ? v->skip : 2);
   do_calc_state(v);
   if (obs_out) {
     if (hier) ilrl_oracle_high_obs(v, obs_out);
@@ -855,7 +859,7 @@ int ilrl_oracle_low_step(orc_env* v, const double* action, int rand_deg, int ski
   v->e[ILRL_E_ROBOT_X] = v->cs.body_xyz[0];
   v->e[ILRL_E_ROBOT_Y] = v->cs.body_xyz[1];
   *reward = update_reward(v, action);
-  inc_frame(v, 2);
+  inc_frame(v, v->skip > 0 ? v->skip : 2);
   check_target(v, rand_deg);
   v->terms[ILRL_T_LOWTARGET] = v->e[ILRL_E_LOW_TARGET_SCORE]; /* attribute as read after the step */
   ilrl_oracle_low_obs(v, obs70);
@@ -898,7 +902,7 @@ int ilrl_oracle_hier_low_step(orc_env* v, const double* action, int rand_deg, in
   if (!skip_physics) ilrl_oracle_physics_step(v->phys, tau, 0);
   do_calc_state(v);
   *low_reward = update_reward(v, action);
-  inc_frame(v, 2);
+  inc_frame(v, v->skip > 0 ? v->skip : 2);
   check_target(v, rand_deg);
   int done = check_done(v);
   e[ILRL_E_T] += 1;

@@ -38,6 +38,13 @@ WORKLOADS = {
     "hier16384": dict(mode="hier", envs=16384, total=None, clips=["motion08_03", "motion09_03"],
                       name="hierarchical env (HumanoidBulletEnvHier-v0), 16384 envs per GPU, selected_motion=1, step_per_level=5, "
                            "random high (heading) and low (torque) actions, auto-reset; low-level steps counted"),
+    "hier2_16384": dict(mode="hier2", envs=16384, total=None, clips=["motion08_03", "motion09_03"],
+                        name="hier_env_2.py variant (SURVEY row a18), 16384 envs per GPU, selected_motion=1, step_per_level=20, "
+                             "skipFrame=5, random 36-d high (joint-target) and 17-d low (torque) actions, auto-reset; low-level "
+                             "steps counted"),
+    "terrain4096": dict(mode="low", envs=4096, total=None, clips=[CLIP], terrain=True,
+                        name="low-level imitation env on the CustomScene heightfield terrain (SURVEY row f4: 256 x 256 samples, "
+                             "2 x 2 plateaus of U(0, 0.5) m), 4096 envs per GPU, motion09_03, random actions, auto-reset"),
     "multiclip65536": dict(mode="low", envs=None, total=65536, clips=["motion02_04", "motion08_03", "motion09_03", "motion13_13"],
                            name="multi-clip imitation (02_04, 08_03, 09_03, 13_13; clip = env id mod 4), 65536 envs sharded "
                                 "over the GPUs, random actions, auto-reset"),
@@ -218,7 +225,7 @@ class ClockSampler:
 def make_env(wl, rank, world, local_rank):
     import ilrl_b200
     from ilrl_b200.batched_env import BatchedHumanoidEnv
-    hier = wl["mode"] == "hier"
+    hier = wl["mode"] in ("hier", "hier2")
     if wl["total"]:  # strong scaling over a fixed total (cfg 4): contiguous env-id blocks, clip = global id mod 4
         first, n = ilrl_b200.stats.shard_envs(wl["total"], world, rank)
     else:
@@ -227,6 +234,11 @@ def make_env(wl, rank, world, local_rank):
         np.ones(n, np.int32) if hier else None)
     env = BatchedHumanoidEnv(n, wl["mode"], clips=wl["clips"], clip_of_env=cid, device=local_rank, seed=1234,
                              auto_reset=True, env_id_base=first)  # same seed, global env ids: sharding-invariant
+    if wl.get("terrain"):   # CustomScene.episode_restart (REF humanoid.py:88-124), one terrain per handle
+        tr = np.random.default_rng(99)
+        h = np.repeat(np.repeat(tr.uniform(0, 0.5, (128, 128)), 2, axis=0), 2, axis=1)
+        h[126:130, 126:130] = 0.0
+        env.set_heightfield(h.reshape(-1))
     env.reset()
     return env, n, hier
 
@@ -249,7 +261,7 @@ def measure_device(wl, K, W, rank, world, local_rank, clocks=None, min_region_s=
     g.manual_seed(1234 + rank)
     POOL = max(8, min(512, (160 << 20) // (n * 17 * 4)))  # keep the pool just above L2 size at every N
     pool = torch.rand(POOL, n, 17, device=dev, generator=g) * 2 - 1
-    hpool = torch.rand(64, n, 2, device=dev, generator=g) * 2 - 1 if hier else None
+    hpool = torch.rand(64, n, env.hact_w, device=dev, generator=g) * 2 - 1 if hier else None
     calls = [0]
 
     def one_step():
@@ -352,7 +364,7 @@ def measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks=None, mi
     pool, hpool, POOL = pools
     NH = min(64, POOL)
     host_act = [pool[j].cpu().pin_memory().numpy() for j in range(NH)]
-    obs_h = torch.zeros(n, 70).pin_memory().numpy()
+    obs_h = torch.zeros(n, env.obs_w).pin_memory().numpy()
     rew_h = torch.zeros(n).pin_memory().numpy()
     done_h = torch.zeros(n, dtype=torch.uint8).pin_memory().numpy()
 
@@ -369,8 +381,8 @@ def measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks=None, mi
     for kind in ("async", "sync", "serve"):
         if kind == "async" and hier:
             continue   # the hierarchical env needs its high-level call between the parts: only the blocking path is timed
-        if kind == "serve" and (hier or n > 4096):
-            continue
+        if kind == "serve" and (hier or n > 4096 or not os.environ.get("ILRL_BENCH_SERVE")):
+            continue   # opt-in (ILRL_BENCH_SERVE=1): tools/serve_bench.py is where the serving path is measured
         def run(k):
             if kind == "serve":
                 env.serve_begin(obs_h, rew_h, done_h)
@@ -479,7 +491,8 @@ def run_ours(args):
     # 16384 envs per GPU, cfg 4 multi-clip 65536 envs sharded over the ranks, cfg 5 on-device rollout collection
     extra = {}
     if args.workload == "low4096" and not args.no_extra_configs:
-        for key, name in (("cfg3_hier16384", "hier16384"), ("cfg4_multiclip65536", "multiclip65536")):
+        for key, name in (("cfg3_hier16384", "hier16384"), ("cfg4_multiclip65536", "multiclip65536"),
+                          ("a18_hier2_16384", "hier2_16384"), ("f4_terrain4096", "terrain4096")):
             r2, env2, p2 = measure_device(WORKLOADS[name], K, max(W, 10), rank, world, local_rank, clocks, min_region_s=0.3,
                                           kernel_events=False, use_graph=not args.no_graph)
             env2.close()

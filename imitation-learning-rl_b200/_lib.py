@@ -47,9 +47,9 @@ def lib():
     L.ilrl_step_host.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp]
     L.ilrl_step_host_async.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp]
     L.ilrl_wait.argtypes = [_vp, C.c_int32]
-    L.ilrl_serve_begin.argtypes = [_vp, _vp, _vp, _vp, _vp]
-    L.ilrl_serve_post.argtypes = [_vp, _vp]
-    L.ilrl_serve_wait.argtypes = [_vp]
+    L.ilrl_serve_begin.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp]
+    L.ilrl_serve_post.argtypes = [_vp, C.c_int32, _vp]
+    L.ilrl_serve_wait.argtypes = [_vp, C.c_int32]
     L.ilrl_serve_step.argtypes = [_vp, _vp]
     L.ilrl_serve_end.argtypes = [_vp]
     L.ilrl_step_pull.argtypes = [_vp, _vp, C.c_int32, _vp, _vp]

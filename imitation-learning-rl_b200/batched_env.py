@@ -186,27 +186,28 @@ class BatchedHumanoidEnv:
             self._ck(rc)
 
     # ---- persistent serving (ilrl_serve_*): one resident kernel, no launch / synchronise per step
-    def serve_begin(self, obs_np, reward_np, done_np, terms_np=None):
-        """Start the resident step kernel writing into these pinned [N,...] numpy buffers.  Until `serve_end` only
-        `serve_step` / `serve_post` / `serve_wait` may be called, and nothing may synchronise the whole device."""
+    def serve_begin(self, obs_np, reward_np, done_np, terms_np=None, nparts=1):
+        """Start the resident step kernels (one per part, `part_slice`) writing into these pinned [N,...] numpy buffers.
+        Until `serve_end` only `serve_step` / `serve_post` / `serve_wait` may be called, and nothing may synchronise the
+        whole device."""
         ptr = lambda a: None if a is None else a.__array_interface__["data"][0]  # noqa: E731
         assert obs_np.dtype == np.float32 and obs_np.shape == (self.num_envs, self.obs_w) and obs_np.flags.c_contiguous
         assert reward_np.dtype == np.float32 and reward_np.shape == (self.num_envs,) and done_np.dtype == np.uint8
         self._serve_refs = (obs_np, reward_np, done_np, terms_np)
-        self._ck(self.L.ilrl_serve_begin(self.h, ptr(obs_np), ptr(reward_np), ptr(done_np), ptr(terms_np)))
+        self._ck(self.L.ilrl_serve_begin(self.h, int(nparts), ptr(obs_np), ptr(reward_np), ptr(done_np), ptr(terms_np)))
 
     def serve_step(self, action_np):
         rc = self.L.ilrl_serve_step(self.h, action_np.__array_interface__["data"][0])
         if rc != 0:
             self._ck(rc)
 
-    def serve_post(self, action_np):
-        rc = self.L.ilrl_serve_post(self.h, action_np.__array_interface__["data"][0])
+    def serve_post(self, action_np, part=0):
+        rc = self.L.ilrl_serve_post(self.h, part, action_np.__array_interface__["data"][0])
         if rc != 0:
             self._ck(rc)
 
-    def serve_wait(self):
-        rc = self.L.ilrl_serve_wait(self.h)
+    def serve_wait(self, part=0):
+        rc = self.L.ilrl_serve_wait(self.h, part)
         if rc != 0:
             self._ck(rc)
 

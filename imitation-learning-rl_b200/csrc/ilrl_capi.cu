@@ -841,12 +841,12 @@ struct ilrl_env {
   bool no_zero_copy = false;     // harness only (ilrl_debug_zero_copy): force the explicit-copy host path
   // ilrl_serve_*: the resident serving kernel and its doorbell
   bool serving = false;
-  cudaStream_t serve_stream = nullptr;
-  ServeCtl* serve_ctl = nullptr;          // mapped host memory (+ the ack word behind it)
-  volatile int* serve_ack = nullptr;
-  ServeDev* serve_dev = nullptr;
-  int serve_seq = 0;
-  int serve_posted = 0;
+  int serve_nparts = 0;
+  ServeCtl* serve_ctl = nullptr;          // mapped host memory: one 256-byte slot per part (doorbell at +0, ack at +128)
+  ServeDev* serve_dev = nullptr;          // [ILRL_MAX_PARTS]
+  int serve_seq[8] = {0};
+  int serve_posted[8] = {0};
+  bool serve_live[8] = {false};           // the part has a resident kernel (non-empty part)
   int64_t launches = 0;
   bool timing = false;           // ilrl_kernel_timing: the step kernels stamp %globaltimer into ktime[slot]
   unsigned long long* ktime = nullptr;   // [KT_SLOTS][2] device
@@ -1026,7 +1026,6 @@ void ilrl_destroy(ilrl_env* env) {
   }
   cudaFree(env->clip_ids_dev);
   cudaFree(env->terr_mem);
-  if (env->serve_stream) cudaStreamDestroy(env->serve_stream);
   cudaFreeHost(env->serve_ctl);
   cudaFree(env->serve_dev);
   cudaFreeHost(env->h_pull);
@@ -1362,111 +1361,148 @@ int ilrl_pull(ilrl_env* env, const float* obs_dev, float* pull_host, void* strea
 }
 
 // ---- persistent serving (K1s)
-static const unsigned long long SERVE_WATCHDOG_NS = 2000000000ull;   // the kernel leaves after 2 s without a doorbell
+static const unsigned long long SERVE_WATCHDOG_NS = 2000000000ull;   // a serving kernel leaves after 2 s without a doorbell
 static double now_s() {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
-int ilrl_serve_begin(ilrl_env* env, float* obs_h, float* reward_h, uint8_t* done_h, float* terms_h) {
+static inline ServeCtl* serve_ctl_of(ilrl_env* env, int part) {
+  return reinterpret_cast<ServeCtl*>(reinterpret_cast<char*>(env->serve_ctl) + 256 * part);
+}
+static inline volatile int* serve_ack_of(ilrl_env* env, int part) {
+  return reinterpret_cast<volatile int*>(reinterpret_cast<char*>(env->serve_ctl) + 256 * part + 128);   // its own cache line
+}
+int ilrl_serve_begin(ilrl_env* env, int32_t nparts, float* obs_h, float* reward_h, uint8_t* done_h, float* terms_h) {
   if (!env) return ILRL_ERR_ARG;
   if (!obs_h || !reward_h || !done_h) return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: null buffer");
+  if (nparts < 1 || nparts > ILRL_MAX_PARTS) return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: nparts out of range (1..8)");
   if (int r = check_ready(env)) return r;
   ON_DEVICE(env);
   if (env->cfg.mode != 0) return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: low-level mode only (the hierarchical modes need their high-level call between steps)");
   if (env->terr.h) return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: not available with a heightfield terrain");
-  const int ntiles = (env->n + QE - 1) / QE;
-  if (ntiles > env->grid_small)
+  int total_tiles = 0;
+  for (int p = 0; p < nparts; p++) {
+    int first, count;
+    part_range(env, p, nparts, &first, &count);
+    total_tiles += (count + QE - 1) / QE;
+  }
+  if (total_tiles > env->grid_small)   // every serving kernel must be resident at once: a waiting one would never start
     return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: the batch must fit one wave of resident CTAs (N <= 16 x SMs x 2): use ilrl_step_host_async");
   for (int p = 0; p < ILRL_MAX_PARTS; p++) if (env->part_busy[p]) return fail(env, ILRL_ERR_STATE, "ilrl_serve_begin: a part is still in flight");
   void *dobs, *dr, *dd, *dt = nullptr;
   if (!(dobs = host_alias(env, obs_h)) || !(dr = host_alias(env, reward_h)) || !(dd = host_alias(env, done_h)) ||
       (terms_h && !(dt = host_alias(env, terms_h))))
     return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: buffers must be page-locked and mapped");
-  if (!env->serve_stream) CK(cudaStreamCreateWithFlags(&env->serve_stream, cudaStreamNonBlocking));
   if (!env->serve_ctl) {
-    CK(cudaHostAlloc((void**)&env->serve_ctl, 256, cudaHostAllocMapped));
-    CK(cudaMalloc((void**)&env->serve_dev, sizeof(ServeDev)));
+    CK(cudaHostAlloc((void**)&env->serve_ctl, 256 * ILRL_MAX_PARTS, cudaHostAllocMapped));
+    CK(cudaMalloc((void**)&env->serve_dev, sizeof(ServeDev) * ILRL_MAX_PARTS));
   }
-  memset((void*)env->serve_ctl, 0, 256);
-  env->serve_ack = reinterpret_cast<volatile int*>(reinterpret_cast<char*>(env->serve_ctl) + 128);   // its own cache line
-  CK(cudaMemset(env->serve_dev, 0, sizeof(ServeDev)));
+  memset((void*)env->serve_ctl, 0, 256 * ILRL_MAX_PARTS);
+  CK(cudaMemset(env->serve_dev, 0, sizeof(ServeDev) * ILRL_MAX_PARTS));
   CK(cudaDeviceSynchronize());
   void* ctl_dev = nullptr;
   CK(cudaHostGetDevicePointer(&ctl_dev, (void*)env->serve_ctl, 0));
-  StepArgs a;
-  a.n = env->n; a.first = 0; a.end = env->n; a.skip_frame = env->cfg.skip_frame;
-  a.id_base = env->cfg.env_id_base; a.skip_physics = 0; a.auto_reset = env->cfg.auto_reset; a.max_timestep = env->cfg.max_timestep;
-  a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
-  a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
-  a.action = nullptr; a.obs = (float*)dobs; a.reward = (float*)dr; a.done = (uint8_t*)dd; a.terms = (float*)dt;
-  a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
-  a.forced_deg = env->forced_deg; a.forced_scalar = INT_MIN; a.stats = env->stats; a.gscr = env->gscr;
-  a.jt = env->jt; a.forced_noise = env->forced_noise; a.terr = env->terr;
-  a.tile_counter = env->tile_counter; a.ntiles = ntiles; a.ktime = nullptr;
-#ifdef ILRL_PROF
-  a.prof = nullptr;
-#endif
-  memcpy(a.clips, env->clips, sizeof a.clips);
   CK(cudaFuncSetAttribute(serve_kernel<0, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
-  serve_kernel<0, SmemSmall><<<ntiles, QT, sizeof(SmemSmall), env->serve_stream>>>(
-      a, (const ServeCtl*)ctl_dev, env->serve_dev, (volatile int*)((char*)ctl_dev + 128), SERVE_WATCHDOG_NS);
-  env->launches++;
-  CK(cudaGetLastError());
+  for (int p = 0; p < nparts; p++) {
+    int first, count;
+    part_range(env, p, nparts, &first, &count);
+    env->serve_seq[p] = 0;
+    env->serve_posted[p] = 0;
+    env->serve_live[p] = false;
+    if (count <= 0) continue;
+    if (!env->part_stream[p]) CK(cudaStreamCreateWithFlags(&env->part_stream[p], cudaStreamNonBlocking));
+    StepArgs a;
+    a.n = env->n; a.first = first; a.end = first + count; a.skip_frame = env->cfg.skip_frame;
+    a.id_base = env->cfg.env_id_base; a.skip_physics = 0; a.auto_reset = env->cfg.auto_reset; a.max_timestep = env->cfg.max_timestep;
+    a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
+    a.phys = env->phys; a.envf = env->envf; a.rng = env->rng;
+    a.action = nullptr; a.obs = (float*)dobs; a.reward = (float*)dr; a.done = (uint8_t*)dd; a.terms = (float*)dt;
+    a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
+    a.forced_deg = env->forced_deg; a.forced_scalar = INT_MIN; a.stats = env->stats; a.gscr = env->gscr;
+    a.jt = env->jt; a.forced_noise = env->forced_noise; a.terr = env->terr;
+    a.tile_counter = env->tile_counter; a.ntiles = (count + QE - 1) / QE; a.ktime = nullptr;
+#ifdef ILRL_PROF
+    a.prof = nullptr;
+#endif
+    memcpy(a.clips, env->clips, sizeof a.clips);
+    serve_kernel<0, SmemSmall><<<a.ntiles, QT, sizeof(SmemSmall), env->part_stream[p]>>>(
+        a, (const ServeCtl*)((char*)ctl_dev + 256 * p), env->serve_dev + p, (volatile int*)((char*)ctl_dev + 256 * p + 128),
+        SERVE_WATCHDOG_NS);
+    env->launches++;
+    CK(cudaGetLastError());
+    env->serve_live[p] = true;
+  }
   env->serving = true;
-  env->serve_seq = 0;
-  env->serve_posted = 0;
+  env->serve_nparts = nparts;
   return ILRL_OK;
 }
-int ilrl_serve_post(ilrl_env* env, const float* action_h) {
+static int serve_gone(ilrl_env* env, const char* who) {
+  env->serving = false;
+  for (int p = 0; p < ILRL_MAX_PARTS; p++) env->serve_posted[p] = 0;
+  for (int p = 0; p < env->serve_nparts; p++)     // the other parts' kernels leave as well
+    if (env->serve_live[p]) serve_ctl_of(env, p)->seq = -1;
+  cudaGetLastError();
+  return fail(env, ILRL_ERR_STATE, std::string(who) + ": a serving kernel is gone (watchdog after 2 s without a step, or a device error)");
+}
+int ilrl_serve_post(ilrl_env* env, int32_t part, const float* action_h) {
   if (!env) return ILRL_ERR_ARG;
   if (!env->serving) return fail(env, ILRL_ERR_STATE, "ilrl_serve_post: not serving (ilrl_serve_begin first)");
-  if (env->serve_posted) return fail(env, ILRL_ERR_STATE, "ilrl_serve_post: the previous step has not been waited for");
+  if (part < 0 || part >= env->serve_nparts) return fail(env, ILRL_ERR_ARG, "ilrl_serve_post: part out of range");
+  if (env->serve_posted[part]) return fail(env, ILRL_ERR_STATE, "ilrl_serve_post: the part's previous step has not been waited for");
+  if (!env->serve_live[part]) return ILRL_OK;   // (an empty part)
   void* da = action_h ? host_alias(env, action_h) : nullptr;
   if (!da) return fail(env, ILRL_ERR_ARG, "ilrl_serve_post: actions must be in page-locked, mapped host memory");
-  env->serve_ctl->action = (long long)(uintptr_t)da;
+  ServeCtl* c = serve_ctl_of(env, part);
+  c->action = (long long)(uintptr_t)da;
   __atomic_thread_fence(__ATOMIC_RELEASE);
-  env->serve_ctl->seq = ++env->serve_seq;
-  env->serve_posted = 1;
+  c->seq = ++env->serve_seq[part];
+  env->serve_posted[part] = 1;
   return ILRL_OK;
 }
-int ilrl_serve_wait(ilrl_env* env) {
+int ilrl_serve_wait(ilrl_env* env, int32_t part) {
   if (!env) return ILRL_ERR_ARG;
   if (!env->serving) return fail(env, ILRL_ERR_STATE, "ilrl_serve_wait: not serving");
-  if (!env->serve_posted) return ILRL_OK;
-  const int want = env->serve_seq;
+  if (part < 0 || part >= env->serve_nparts) return fail(env, ILRL_ERR_ARG, "ilrl_serve_wait: part out of range");
+  if (!env->serve_posted[part]) return ILRL_OK;
+  const int want = env->serve_seq[part];
+  volatile int* ack = serve_ack_of(env, part);
   double t0 = 0.0;
-  for (unsigned spins = 0; *env->serve_ack != want; spins++) {
+  for (unsigned spins = 0; *ack != want; spins++) {
 #if defined(__x86_64__) || defined(__i386__)
     __builtin_ia32_pause();
 #endif
     if ((spins & 0xffffu) == 0xffffu) {   // rarely: has the kernel died (watchdog, device error)?
       if (t0 == 0.0) t0 = now_s();
-      if (cudaStreamQuery(env->serve_stream) != cudaErrorNotReady || now_s() - t0 > 10.0) {
-        env->serving = false;
-        env->serve_posted = 0;
-        cudaGetLastError();
-        return fail(env, ILRL_ERR_STATE, "ilrl_serve_wait: the serving kernel is gone (watchdog after 2 s without a step, or a device error)");
-      }
+      if (cudaStreamQuery(env->part_stream[part]) != cudaErrorNotReady || now_s() - t0 > 10.0)
+        return serve_gone(env, "ilrl_serve_wait");
     }
   }
   __atomic_thread_fence(__ATOMIC_ACQUIRE);
-  env->serve_posted = 0;
+  env->serve_posted[part] = 0;
   return ILRL_OK;
 }
 int ilrl_serve_step(ilrl_env* env, const float* action_h) {
-  if (int r = ilrl_serve_post(env, action_h)) return r;
-  return ilrl_serve_wait(env);
+  if (!env) return ILRL_ERR_ARG;
+  for (int p = 0; p < env->serve_nparts; p++) if (int r = ilrl_serve_post(env, p, action_h)) return r;
+  for (int p = 0; p < env->serve_nparts; p++) if (int r = ilrl_serve_wait(env, p)) return r;
+  return env->serving ? ILRL_OK : fail(env, ILRL_ERR_STATE, "ilrl_serve_step: not serving (ilrl_serve_begin first)");
 }
 int ilrl_serve_end(ilrl_env* env) {
   if (!env) return ILRL_ERR_ARG;
   if (!env->serving) return ILRL_OK;
   ON_DEVICE_RAW(env);
-  if (env->serve_posted) ilrl_serve_wait(env);
-  env->serve_ctl->seq = -1;
-  cudaError_t r = cudaStreamSynchronize(env->serve_stream);
+  for (int p = 0; p < env->serve_nparts; p++) if (env->serve_posted[p] && env->serving) ilrl_serve_wait(env, p);
+  cudaError_t r = cudaSuccess;
+  for (int p = 0; p < env->serve_nparts; p++) {
+    if (!env->serve_live[p]) continue;
+    serve_ctl_of(env, p)->seq = -1;
+    cudaError_t rp = cudaStreamSynchronize(env->part_stream[p]);
+    if (rp != cudaSuccess) r = rp;
+    env->serve_live[p] = false;
+    env->serve_posted[p] = 0;
+  }
   env->serving = false;
-  env->serve_posted = 0;
   if (r != cudaSuccess) return fail(env, ILRL_ERR_CUDA, std::string("ilrl_serve_end: ") + cudaGetErrorString(r));
   return ILRL_OK;
 }

@@ -114,20 +114,23 @@ int ilrl_wait(ilrl_env* env, int32_t part);
 int ilrl_wait_step_host_async(ilrl_env* env, int32_t part, int32_t nparts, const float* action_host, float* obs_host,
                               float* reward_host, uint8_t* done_host, float* terms_host);
 
-/* Persistent serving: the lowest-latency form of the host path.  Between ilrl_serve_begin and ilrl_serve_end ONE step
- * kernel stays resident on the GPU and is driven through a doorbell in mapped host memory, so an env step costs neither
- * a kernel launch nor a stream synchronisation: ilrl_serve_post publishes the step's actions (any page-locked, mapped
- * [N,17] buffer, already filled), ilrl_serve_wait spins until obs / reward / done (/ terms) of that step have landed in
- * the buffers given to ilrl_serve_begin; ilrl_serve_step = post + wait.  Results are identical to ilrl_step_host.
- * Low-level mode, flat ground, and a batch that fits one wave of resident CTAs (N <= 16 x 2 x SMs = 4736 on a B200;
- * larger batches use ilrl_step_host_async).  While serving, every other call on the handle fails with ILRL_ERR_STATE,
- * and device-wide synchronisation (cudaDeviceSynchronize, torch.cuda.synchronize, ilrl_create of another handle) must
- * be avoided: it would wait for the resident kernel, which leaves by itself after 2 s without a step (watchdog; the
- * next ilrl_serve_* call then reports ILRL_ERR_STATE).  Replaces the same reference call as ilrl_step_host
- * (REF low_level_env.py:322-323). */
-int ilrl_serve_begin(ilrl_env* env, float* obs_host, float* reward_host, uint8_t* done_host, float* terms_host);
-int ilrl_serve_post(ilrl_env* env, const float* action_host);
-int ilrl_serve_wait(ilrl_env* env);
+/* Persistent serving: the lowest-latency form of the host path.  Between ilrl_serve_begin and ilrl_serve_end the step
+ * kernel stays RESIDENT on the GPU — one launch per part (`nparts` <= 8 contiguous parts of whole 16-env tiles, as in
+ * ilrl_step_host_async) — and every part is driven through its own doorbell in mapped host memory, so an env step costs
+ * neither a kernel launch nor a stream synchronisation: ilrl_serve_post(part) publishes the step's actions (the FULL
+ * [N,17] array, any page-locked, mapped buffer, already filled: the part reads its own rows), ilrl_serve_wait(part)
+ * spins until obs / reward / done (/ terms) of the part's rows have landed in the buffers given to ilrl_serve_begin.
+ * With several parts a worker overlaps its own work on one part with the steps of the others, and the parts'
+ * observation bursts no longer hit PCIe at the same moment.  ilrl_serve_step = post all parts, wait for all.
+ * Results are identical to ilrl_step_host.  Low-level mode, flat ground, and a batch that fits one wave of resident CTAs
+ * (N <= 16 x 2 x SMs = 4736 on a B200; larger batches use ilrl_step_host_async).  While serving, every other call on
+ * the handle fails with ILRL_ERR_STATE, and device-wide synchronisation (cudaDeviceSynchronize, torch.cuda.synchronize,
+ * ilrl_create of another handle) must be avoided: it would wait for the resident kernels, which leave by themselves
+ * after 2 s without a step (watchdog; the next ilrl_serve_* call then reports ILRL_ERR_STATE).  Replaces the same
+ * reference call as ilrl_step_host (REF low_level_env.py:322-323). */
+int ilrl_serve_begin(ilrl_env* env, int32_t nparts, float* obs_host, float* reward_host, uint8_t* done_host, float* terms_host);
+int ilrl_serve_post(ilrl_env* env, int32_t part, const float* action_host);
+int ilrl_serve_wait(ilrl_env* env, int32_t part);
 int ilrl_serve_step(ilrl_env* env, const float* action_host);
 int ilrl_serve_end(ilrl_env* env);
 

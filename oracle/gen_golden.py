@@ -14,6 +14,8 @@
   hier2_injected.npz        REF hier_env_2.py (row a18) reset / high_level_step / low_level_step on injected states, under
                             the two declared substitutions of ref_shim.make_hier2_env (data directory, robot stand-in).
   hier2_traj.npz            hier_env_2 protocol trace with physics (reset -> high -> 20 low -> high ...), 600 low steps.
+  ref_policies.npz          weights of the low-level policies the reference trained in PyBullet (Log/Best Model) and its own
+                            evaluation logs of them (Log/data_*.json): oracle/extract_ref_policies.py, DESIGN.md section 4.
   notebook_vectors.json     the recorded cell outputs of "Eksplor Ray RLLib.ipynb" that pin layout facts.
 """
 import json
@@ -414,7 +416,7 @@ def gen_notebook_vectors():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["nb", "reset", "low_inj", "hier_inj", "low_traj", "hier_traj", "hier2_inj", "hier2_traj"]
+    which = sys.argv[1:] or ["nb", "reset", "low_inj", "hier_inj", "low_traj", "hier_traj", "hier2_inj", "hier2_traj", "ref_policies"]
     if "nb" in which: gen_notebook_vectors()
     if "reset" in which: gen_reset_vectors()
     if "low_inj" in which: gen_low_injected()
@@ -423,3 +425,7 @@ if __name__ == "__main__":
     if "hier_traj" in which: gen_hier_traj()
     if "hier2_inj" in which: gen_hier2_injected()
     if "hier2_traj" in which: gen_hier2_traj()
+    if "ref_policies" in which:   # weights + PyBullet evaluation logs of the reference's shipped checkpoints (data files)
+        from oracle import extract_ref_policies
+        extract_ref_policies.OUT = OUT
+        extract_ref_policies.main()

@@ -877,7 +877,7 @@ def test_persistent_serving_matches_step_host():
     rng = np.random.default_rng(3)
     acts = [pin((n, 17), torch.float32) for _ in range(4)]
     outs = {}
-    for kind in ("host", "serve"):
+    for kind in ("host", "serve", "serve3"):
         env = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], auto_reset=True, seed=9)
         env.reset()
         o_h, r_h, d_h, t_h = pin((n, 70), torch.float32), pin((n,), torch.float32), pin((n,), torch.uint8), pin((n, 12), torch.float32)
@@ -887,6 +887,8 @@ def test_persistent_serving_matches_step_host():
             env.serve_begin(o_h, r_h, d_h, t_h)
             with pytest.raises(ilrl_b200._lib.IlrlError):
                 env.reset()                                   # the handle belongs to its resident kernel
+        if kind == "serve3":
+            env.serve_begin(o_h, r_h, d_h, t_h, nparts=3)     # three resident kernels, one doorbell each
         for k in range(K):
             a = acts[k % 4]
             a[:] = rng.uniform(-1, 1, (n, 17)).astype(np.float32)
@@ -896,21 +898,30 @@ def test_persistent_serving_matches_step_host():
                     env.serve_wait()
                 else:
                     env.serve_step(a)
+            elif kind == "serve3":
+                if k % 2:
+                    for p in (2, 0, 1):
+                        env.serve_post(a, p)
+                    for p in (1, 2, 0):
+                        env.serve_wait(p)
+                else:
+                    env.serve_step(a)
             else:
                 env.step_host(a, o_h, r_h, d_h, t_h)
             rec.append((o_h.copy(), r_h.copy(), d_h.copy(), t_h.copy()))
-        if kind == "serve":
+        if kind != "host":
             env.serve_end()
             env.serve_end()                                   # idempotent
         phys, envf = [t.cpu().numpy() for t in env.get_state()]
         outs[kind] = (rec, phys, envf, env.stats().cpu().numpy())
         env.close()
-    for (a, b) in zip(outs["host"][0], outs["serve"][0]):
-        for x, y in zip(a, b):
-            np.testing.assert_array_equal(x, y)
-    np.testing.assert_array_equal(outs["host"][1], outs["serve"][1])
-    np.testing.assert_array_equal(outs["host"][2], outs["serve"][2])
-    np.testing.assert_array_equal(outs["host"][3], outs["serve"][3])
+    for kind in ("serve", "serve3"):
+        for (a, b) in zip(outs["host"][0], outs[kind][0]):
+            for x, y in zip(a, b):
+                np.testing.assert_array_equal(x, y)
+        np.testing.assert_array_equal(outs["host"][1], outs[kind][1])
+        np.testing.assert_array_equal(outs["host"][2], outs[kind][2])
+        np.testing.assert_allclose(outs["host"][3], outs[kind][3], rtol=1e-6)   # (statistics: atomics, order-dependent sums)
     assert sum(int(r[2].sum()) for r in outs["serve"][0]) > 0      # episodes ended and restarted while serving
     # argument checks
     big = BatchedHumanoidEnv(8192, "low", clips=["motion09_03"])

@@ -50,4 +50,24 @@ for k in range(K):
 t = time.perf_counter() - t0
 env.serve_end()
 print("serve_step       %.2f us/step  %.2f M env-steps/s" % (t / K * 1e6, n * K / t / 1e6))
+for P in (2, 4, 8):
+    sl = [env.part_slice(p, P) for p in range(P)]
+    env.serve_begin(o_h, r_h, d_h, nparts=P)
+    for p in range(P):
+        env.serve_post(acts[0], p)
+    for k in range(100):
+        for p in range(P):
+            env.serve_wait(p); env.serve_post(acts[k % 16], p)
+    t0 = time.perf_counter()
+    for k in range(K):
+        a = acts[k % 16]
+        for p in range(P):
+            env.serve_wait(p)
+            s += r_h[sl[p].start]
+            env.serve_post(a, p)
+    for p in range(P):
+        env.serve_wait(p)
+    t = time.perf_counter() - t0
+    env.serve_end()
+    print("serve x%d parts   %.2f us/step  %.2f M env-steps/s" % (P, t / K * 1e6, n * K / t / 1e6))
 env.close()

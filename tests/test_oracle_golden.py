@@ -182,6 +182,19 @@ def test_notebook_vectors():
     _, xyz, _, _, _ = O.calc_state(p, 0.0, 0.0)
     bo, ao, _ = O.fk(p)
     np.testing.assert_allclose(xyz[:2], (bo[:, :2].sum(0) + ao[:, :2].sum(0)) / 33.0, atol=1e-12)
+    # ... and the part positions behind that mean against the SECOND, independent forward kinematics (numpy / scipy,
+    # oracle/ref_shim.py: the one the unmodified reference Python runs on when the fixtures are recorded), on random poses
+    from oracle import ref_shim as S
+    from oracle.gen_golden import random_phys
+    rng = np.random.default_rng(12)
+    for _ in range(25):
+        ph = random_phys(rng, upright=False)
+        pos, _, anc = S.py_fk(ph)
+        _, xyz, _, _, _ = O.calc_state(ph, 0.0, 0.0)
+        bo, ao, _ = O.fk(ph)
+        np.testing.assert_allclose(bo, pos, atol=1e-9)
+        np.testing.assert_allclose(ao, anc, atol=1e-9)
+        np.testing.assert_allclose(xyz[:2], (pos[:, :2].sum(0) + anc[:, :2].sum(0)) / 33.0, atol=1e-9)
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="the reference checkout exists only in the build container")

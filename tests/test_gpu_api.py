@@ -184,23 +184,33 @@ def test_hier_base_env_adapter():
     be.stop()
 
 
-@pytest.mark.parametrize("n,mode", [(4096, "low"), (16384, "hier"), (65536, "low"), (37, "low"), (1, "low")])
+@pytest.mark.parametrize("n,mode", [(4096, "low"), (16384, "hier"), (65536, "low"), (37, "low"), (1, "low"),
+                                    (16384, "hier2"), (4096, "terrain")])
 def test_full_size_properties(n, mode):
     """BASELINE.json's batch sizes (and ragged / single-env edge cases): properties that need no oracle.
     Determinism across handles, batch-invariance (an env's trajectory does not depend on its neighbours), frame
     advance rule bit-exact, finite outputs, statistics = sums of the per-step outputs."""
+    terrain = mode == "terrain"
+    if terrain:   # the CustomScene heightfield (row f4) under the low-level env
+        mode = "low"
+        tr = np.random.default_rng(5)
+        hf = np.repeat(np.repeat(tr.uniform(0, 0.5, (128, 128)), 2, axis=0), 2, axis=1)
+        hf[126:130, 126:130] = 0.0
+    hier = mode in ("hier", "hier2")
     clips = ilrl_b200.CLIP_NAMES if mode == "low" else ["motion08_03", "motion09_03"]
     first, count = stats.shard_envs(n, 1, 0)
     cid = stats.clip_of_env(first, count, len(clips))
     g = torch.Generator(device="cuda")
     g.manual_seed(7)
     acts = [torch.rand(n, 17, device="cuda", generator=g) * 2 - 1 for _ in range(6)]
-    hact = torch.rand(n, 2, device="cuda", generator=g) * 2 - 1
+    hact = torch.rand(n, 36 if mode == "hier2" else 2, device="cuda", generator=g) * 2 - 1
 
     def run(seed):
         env = BatchedHumanoidEnv(n, mode, clips=clips, clip_of_env=cid, seed=seed, auto_reset=True)
+        if terrain:
+            env.set_heightfield(hf.reshape(-1))
         env.reset()
-        if mode == "hier":
+        if hier:
             env.high_step(hact)
         out, rsum, dsum = [], 0.0, 0
         f0 = env.get_state()[1][:, B.E_FRAME].clone()
@@ -222,22 +232,30 @@ def test_full_size_properties(n, mode):
     assert torch.equal(a_phys, b_phys) and torch.equal(a_envf, b_envf)
     assert st[0] == dsum and st[3] == n * 5
     assert abs(st[4] - rsum) <= 1e-3 * max(1.0, abs(rsum))
-    # frame rule on the envs that never finished: 5 advances of 2 modulo (max_frame - 1)
+    # frame rule on the envs that never finished: 5 advances of 2 modulo (max_frame - 1); hier_env_2's low-level step
+    # does not advance the frame at all (REF hier_env_2.py:751-769)
     never = torch.stack([d for _, _, d in a_out]).sum(0) == 0
     mf = torch.tensor([ilrl_b200.load_clip(c)["max_frame"] for c in clips], device="cuda")[torch.as_tensor(cid, device="cuda").long()]
-    want = (f0.long() + 10) % (mf - 1)
+    want = f0.long() if mode == "hier2" else (f0.long() + 10) % (mf - 1)
     assert torch.equal(a_envf[:, B.E_FRAME].long()[never], want[never])
     # batch-invariance: replay a few envs alone from their recorded start state
     if n >= 37:
         pick = [0, 5, n // 2, n - 1]
         env = BatchedHumanoidEnv(n, mode, clips=clips, clip_of_env=cid, seed=21, auto_reset=True)
+        if terrain:
+            env.set_heightfield(hf.reshape(-1))
         env.reset()
-        if mode == "hier":
+        if hier:
             env.high_step(hact)
         p0, e0 = env.get_state()
+        jt0 = env.get_joint_target() if mode == "hier2" else None
         env.close()
         small = BatchedHumanoidEnv(len(pick), mode, clips=clips, clip_of_env=cid[pick], seed=99, auto_reset=False)
+        if terrain:
+            small.set_heightfield(hf.reshape(-1))
         small.set_state(p0[pick], e0[pick])
+        if jt0 is not None:
+            small.set_joint_target(jt0[pick])
         obs, rew, done, _ = small.step(acts[0][pick])
         assert torch.equal(obs, a_out[0][0][pick]) or bool((done != 0).any())
         nd = done == 0

@@ -51,6 +51,11 @@ static const double joint_hi[NJ] = ILRL_JOINT_HI;
 static const int sphere_body[NS] = ILRL_SPHERE_BODY;
 static const double sphere_c[NS * 3] = ILRL_SPHERE_C;
 static const double sphere_r[NS] = ILRL_SPHERE_R;
+#define NG ILRL_NG
+static const int geom_body[NG] = ILRL_GEOM_BODY;
+static const double geom_p0[NG * 3] = ILRL_GEOM_P0;
+static const double geom_p1[NG * 3] = ILRL_GEOM_P1;
+static const double geom_r[NG] = ILRL_GEOM_R;
 static const int motor_joint[NJ] = ILRL_MOTOR_JOINT;
 static const double motor_gear[NJ] = ILRL_MOTOR_GEAR;
 static const int map_joint[ILRL_NMAP] = ILRL_MAP_JOINT;
@@ -294,6 +299,49 @@ static void plane_space(const double* n, double* p, double* q) {
   }
 }
 
+/* Self-collision (REF humanoid.py:13 `self_collision = True`; the CUDA product does NOT model it: declared divergence,
+ * DESIGN.md 4 / 7).  The oracle can switch it on to QUANTIFY what the omission does to the rollout statistics
+ * (tools/model_sensitivity.py).  [BULLET, restated] pybullet_envs loads the MJCF with URDF_USE_SELF_COLLISION |
+ * URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS: every pair of geoms collides unless one body is an ancestor of the
+ * other; combined friction = product of the two geoms' friction (2.0 x 2.0).  Geoms are capsules (spheres = zero
+ * length): closest points of the two axis segments, contact while distance < the breaking threshold, at most
+ * MAX_SELF deepest pairs, rows (normal + 2 friction) after the ground contacts. */
+#define MAX_SELF 8
+static int g_selfcol = 0;
+static long g_selfcol_contacts = 0, g_selfcol_substeps = 0, g_selfcol_hist[NG * NG];
+void ilrl_oracle_set_self_collision(int on) {
+  g_selfcol = on; g_selfcol_contacts = g_selfcol_substeps = 0;
+  memset(g_selfcol_hist, 0, sizeof g_selfcol_hist);
+}
+void ilrl_oracle_self_collision_hist(long* out /* [NG * NG] contacts per geom pair */) { memcpy(out, g_selfcol_hist, sizeof g_selfcol_hist); }
+void ilrl_oracle_self_collision_stats(long* contacts, long* substeps) { *contacts = g_selfcol_contacts; *substeps = g_selfcol_substeps; }
+static int body_is_ancestor(int a, int b) { /* a is b or an ancestor of b */
+  for (; b >= 0; b = body_parent[b]) if (b == a) return 1;
+  return 0;
+}
+/* closest points of segments p1-q1 and p2-q2 (Ericson, Real-Time Collision Detection 5.1.9) */
+static void seg_seg(const double* p1, const double* q1, const double* p2, const double* q2, double* c1, double* c2) {
+  double d1[3], d2[3], r[3];
+  for (int i = 0; i < 3; i++) { d1[i] = q1[i] - p1[i]; d2[i] = q2[i] - p2[i]; r[i] = p1[i] - p2[i]; }
+  const double a = dot3(d1, d1), e = dot3(d2, d2), f = dot3(d2, r), EPS = 1e-12;
+  double s, t;
+  if (a <= EPS && e <= EPS) { s = t = 0; }
+  else if (a <= EPS) { s = 0; t = f / e; t = t < 0 ? 0 : (t > 1 ? 1 : t); }
+  else {
+    const double c = dot3(d1, r);
+    if (e <= EPS) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+    else {
+      const double b = dot3(d1, d2), den = a * e - b * b;
+      s = den > EPS ? (b * f - c * e) / den : 0;
+      s = s < 0 ? 0 : (s > 1 ? 1 : s);
+      t = (b * s + f) / e;
+      if (t < 0) { t = 0; s = -c / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+      else if (t > 1) { t = 1; s = (b - c) / a; s = s < 0 ? 0 : (s > 1 ? 1 : s); }
+    }
+  }
+  for (int i = 0; i < 3; i++) { c1[i] = p1[i] + s * d1[i]; c2[i] = p2[i] + t * d2[i]; }
+}
+
 /* Diagnostics (tools/model_sensitivity.py): extreme-event counters over all substeps since the last reset:
  * [0] substeps, [1] max joint-limit overshoot (rad), [2] substeps with overshoot > 0.5 rad, [3] max |torso v_z change| in one
  * substep (m/s), [4] substeps with |dv_z| > 2 m/s, [5] max torso height (m) */
@@ -419,7 +467,8 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
         if (-pen > 0.5) g_diag[2] += 1;
       }
     }
-  int crow[ILRL_MAX_CONTACTS];
+  int crow[ILRL_MAX_CONTACTS + MAX_SELF];
+  double cmu[ILRL_MAX_CONTACTS + MAX_SELF];
   if (!(flags & 4)) {
     /* candidate set: every sphere closer than the breaking threshold; if more than ILRL_MAX_CONTACTS, drop the
      * shallowest (largest distance, ties -> highest index) until the cap holds; rows then follow table order */
@@ -450,6 +499,7 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
       plane_space(sn[s], t1, t2);
       point_jac(&k, p0, body_link[b], x, Jw, Jv);
       int r = nlim + 3 * ncon;
+      cmu[ncon] = g_par.friction;
       crow[ncon++] = r;
       for (int c2 = 0; c2 < NV; c2++) {
         J[r][c2] = dot3(Jv[c2], sn[s]);
@@ -457,6 +507,63 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
         J[r + 2][c2] = dot3(Jv[c2], t2);
       }
       /* Bullet: penetration > 0 -> speculative row (velocityError -= pen/dt), else ERP push-out */
+      rrhs[r] = dist > 0 ? -dist / dt : -dist * g_par.contact_erp / dt;
+      rrhs[r + 1] = rrhs[r + 2] = 0;
+    }
+  }
+  if (g_selfcol && !(flags & 4)) {
+    /* geom axis end points in the world, then every admissible pair */
+    double w0[NG][3], w1[NG][3];
+    for (int g = 0; g < NG; g++) {
+      const int b = geom_body[g];
+      matvec3(k.R[b], geom_p0 + 3 * g, w0[g]);
+      matvec3(k.R[b], geom_p1 + 3 * g, w1[g]);
+      for (int i = 0; i < 3; i++) { w0[g][i] += k.o[b][i]; w1[g][i] += k.o[b][i]; }
+    }
+    int pa[MAX_SELF], pb[MAX_SELF], ns = 0;
+    double pd[MAX_SELF], pc1[MAX_SELF][3], pc2[MAX_SELF][3];
+    for (int ga = 0; ga < NG; ga++)
+      for (int gb = ga + 1; gb < NG; gb++) {
+        const int ba = geom_body[ga], bb = geom_body[gb];
+        if (body_is_ancestor(ba, bb) || body_is_ancestor(bb, ba)) continue;
+        double c1[3], c2[3];
+        seg_seg(w0[ga], w1[ga], w0[gb], w1[gb], c1, c2);
+        const double dx[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+        const double dist = sqrt(dot3(dx, dx)) - geom_r[ga] - geom_r[gb];
+        if (!(dist < ILRL_CONTACT_BREAK)) continue;
+        int slot = ns;
+        if (ns == MAX_SELF) { /* keep the deepest: replace the shallowest if this one is deeper */
+          slot = 0;
+          for (int q = 1; q < MAX_SELF; q++) if (pd[q] > pd[slot]) slot = q;
+          if (pd[slot] <= dist) continue;
+        } else ns++;
+        pa[slot] = ga; pb[slot] = gb; pd[slot] = dist;
+        memcpy(pc1[slot], c1, sizeof c1); memcpy(pc2[slot], c2, sizeof c2);
+      }
+    g_selfcol_substeps++;
+    g_selfcol_contacts += ns;
+    for (int q = 0; q < ns; q++) g_selfcol_hist[pa[q] * NG + pb[q]]++;
+    for (int q = 0; q < ns; q++) {
+      double n[3] = {pc1[q][0] - pc2[q][0], pc1[q][1] - pc2[q][1], pc1[q][2] - pc2[q][2]};
+      double len = sqrt(dot3(n, n));
+      if (len < 1e-9) { n[0] = 0; n[1] = 0; n[2] = 1; len = 1; }
+      for (int i = 0; i < 3; i++) n[i] /= len; /* from geom b towards geom a */
+      double xa[3], xb[3], t1[3], t2[3];
+      for (int i = 0; i < 3; i++) { xa[i] = pc1[q][i] - geom_r[pa[q]] * n[i]; xb[i] = pc2[q][i] + geom_r[pb[q]] * n[i]; }
+      plane_space(n, t1, t2);
+      double Jwa[NV][3], Jva[NV][3], Jwb[NV][3], Jvb[NV][3];
+      point_jac(&k, p0, body_link[geom_body[pa[q]]], xa, Jwa, Jva);
+      point_jac(&k, p0, body_link[geom_body[pb[q]]], xb, Jwb, Jvb);
+      int r = nlim + 3 * ncon;
+      cmu[ncon] = 4.0; /* 2.0 x 2.0 */
+      crow[ncon++] = r;
+      for (int c2 = 0; c2 < NV; c2++) {
+        double dv[3] = {Jva[c2][0] - Jvb[c2][0], Jva[c2][1] - Jvb[c2][1], Jva[c2][2] - Jvb[c2][2]};
+        J[r][c2] = dot3(dv, n);
+        J[r + 1][c2] = dot3(dv, t1);
+        J[r + 2][c2] = dot3(dv, t2);
+      }
+      const double dist = pd[q];
       rrhs[r] = dist > 0 ? -dist / dt : -dist * g_par.contact_erp / dt;
       rrhs[r + 1] = rrhs[r + 2] = 0;
     }
@@ -496,7 +603,7 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
     for (int ci = 0; ci < ncon; ci++) { /* friction pair, implicit cone (resolveConeFrictionConstraintRows) */
       int rn = crow[ci], r1 = rn + 1, r2 = rn + 2;
       if (!(lam[rn] > 0)) continue;
-      double lim = g_par.friction * lam[rn], jd1 = 0, jd2 = 0;
+      double lim = cmu[ci] * lam[rn], jd1 = 0, jd2 = 0;
       for (int c = 0; c < NV; c++) { jd1 += J[r1][c] * dv[c]; jd2 += J[r2][c] * dv[c]; }
       double s1 = lam[r1] + rrhs[r1] - jd1 * dinv[r1], s2 = lam[r2] + rrhs[r2] - jd2 * dinv[r2];
       double n2 = s1 * s1 + s2 * s2;

@@ -197,6 +197,9 @@ def main():
         comp_inertia=arr([c["inertia"] for c in comps]),
         sphere_body=[s["body"] for s in spheres], sphere_link=[s["link"] for s in spheres],
         sphere_c=arr([s["c"] for s in spheres]), sphere_r=[s["r"] for s in spheres],
+        # every collision geom as a capsule (a sphere is a zero-length one), body frame: self-collision pairs
+        ng=len(geoms), geom_name=[g["name"] for g in geoms], geom_body=[g["body"] for g in geoms],
+        geom_p0=arr([g["p0"] for g in geoms]), geom_p1=arr([g["p1"] for g in geoms]), geom_r=[g["r"] for g in geoms],
         motor_names=MOTOR_NAMES, motor_joint=motor_joint, motor_gear=gear_motor,
         map_joint=map_joint, map_col=map_col, map_w=map_w, map_wv=map_wv, csv_cols=CSV_COLS,
     )
@@ -215,11 +218,11 @@ def main():
          " * low_level_env.py:86-101). link == joint index that carries the body, -1 = floating base (torso). */",
          "#ifndef ILRL_MODEL_DATA_H", "#define ILRL_MODEL_DATA_H",
          "#define ILRL_NB 15", "#define ILRL_NJ 17", "#define ILRL_NC 11", "#define ILRL_NS 29", "#define ILRL_NMAP 14",
-         "#define ILRL_TOTAL_MASS %.17g" % total_mass]
+         "#define ILRL_NG %d" % len(geoms), "#define ILRL_TOTAL_MASS %.17g" % total_mass]
     for key in ["body_parent", "body_link", "body_pos", "body_quat", "body_mass", "body_inertia", "joint_body",
                 "joint_parent", "joint_anchor", "joint_axis", "joint_lo", "joint_hi", "comp_body", "comp_link",
                 "comp_mass", "comp_com", "comp_inertia", "sphere_body", "sphere_link", "sphere_c", "sphere_r",
-                "motor_joint", "motor_gear", "map_joint", "map_col", "map_w", "map_wv"]:
+                "geom_body", "geom_p0", "geom_p1", "geom_r", "motor_joint", "motor_gear", "map_joint", "map_col", "map_w", "map_wv"]:
         L.append("#define ILRL_%s %s" % (key.upper(), cl(model[key])))
     L.append("#endif")
     os.makedirs(os.path.dirname(OUT_H), exist_ok=True)

@@ -42,7 +42,12 @@ VARIANTS = [
     ("solver iterations 5 -> 50", dict(solver_iters=50)),
     ("max coordinate velocity 100 -> 1000 rad/s", dict(max_coord_vel=1000.0)),
     ("friction 1.6 -> 0.8 (plane only)", dict(friction=0.8)),
+    # the reference loads the robot with self_collision = True (REF humanoid.py:13); the CUDA product does not model it
+    ("Bullet self-collision on (all geom pairs but ancestors)", dict(selfcol=1)),
 ]
+
+
+BOTH_ACTION_MODES = [VARIANTS[k][0] for k in (0, 3, 4, 6, 7, -1)]
 
 
 def run(params, n, steps, action_mode):
@@ -54,6 +59,7 @@ def run(params, n, steps, action_mode):
     L.ilrl_oracle_rollout_action_mode.argtypes = [C.c_int]
     p = dict(BASE)
     p.update(params)
+    L.ilrl_oracle_set_self_collision(int(p.pop("selfcol", 0)))
     flat = np.array([p["limit_erp"], p["contact_erp"], p["friction"], p["max_coord_vel"], p["link_damp_scale"], p["solver_iters"],
                      p["limit_rows_always"]] + [p["damping"] * d for d in DAMPING] + [p["armature"] * a for a in ARMATURE] +
                     [p["stiffness"] * k for k in STIFFNESS], dtype=np.float64)
@@ -71,6 +77,11 @@ def run(params, n, steps, action_mode):
     L.ilrl_oracle_diag(d.ctypes.data_as(C.POINTER(C.c_double)), 1)
     L.ilrl_oracle_set_params(None)
     L.ilrl_oracle_rollout_action_mode(0)
+    sc, ss = C.c_long(0), C.c_long(0)
+    L.ilrl_oracle_self_collision_stats(C.byref(sc), C.byref(ss))
+    L.ilrl_oracle_set_self_collision(0)
+    if ss.value:
+        print("  (self-contacts per substep %.3f)" % (sc.value / ss.value), file=sys.stderr)
     return dict(len=done / max(eps.value, 1), ret=rs.value / max(eps.value, 1), over_max=d[1], over_rate=d[2] / d[0],
                 dvz_max=d[3], dvz_rate=d[4] / d[0], zmax=d[5])
 
@@ -81,7 +92,7 @@ def main(n=192, steps=250):
     print("|---|---|---|---|---|---|---|---|---|")
     for name, prm in VARIANTS:
         for am, an in ((0, "U(-1,1)"), (1, "clip N(0,1)")):
-            if am == 1 and name not in (VARIANTS[0][0], VARIANTS[3][0], VARIANTS[4][0], VARIANTS[6][0], VARIANTS[7][0]):
+            if am == 1 and name not in BOTH_ACTION_MODES:
                 continue
             r = run(prm, n, steps, am)
             print("| %s | %s | %.1f | %.2f | %.2f | %.1e | %.1f | %.1e | %.2f |" % (
@@ -89,4 +100,6 @@ def main(n=192, steps=250):
 
 
 if __name__ == "__main__":
+    if os.environ.get("ILRL_SENS_ONLY"):   # e.g. ILRL_SENS_ONLY=0,13: a subset of the variants
+        VARIANTS = [VARIANTS[int(k)] for k in os.environ["ILRL_SENS_ONLY"].split(",")]
     main(*[int(x) for x in sys.argv[1:]])

@@ -45,6 +45,9 @@ WORKLOADS = {
     "terrain4096": dict(mode="low", envs=4096, total=None, clips=[CLIP], terrain=True,
                         name="low-level imitation env on the CustomScene heightfield terrain (SURVEY row f4: 256 x 256 samples, "
                              "2 x 2 plateaus of U(0, 0.5) m), 4096 envs per GPU, motion09_03, random actions, auto-reset"),
+    "selfcol4096": dict(mode="low", envs=4096, total=None, clips=[CLIP], self_collision=True,
+                        name="low-level imitation env with Bullet-style self-collision on (SURVEY row f4: 66 capsule pairs, "
+                             "two-body contact rows), 4096 envs per GPU, motion09_03, random actions, auto-reset"),
     "multiclip65536": dict(mode="low", envs=None, total=65536, clips=["motion02_04", "motion08_03", "motion09_03", "motion13_13"],
                            name="multi-clip imitation (02_04, 08_03, 09_03, 13_13; clip = env id mod 4), 65536 envs sharded "
                                 "over the GPUs, random actions, auto-reset"),
@@ -233,7 +236,8 @@ def make_env(wl, rank, world, local_rank):
     cid = ilrl_b200.stats.clip_of_env(first, n, len(wl["clips"])) if len(wl["clips"]) > 2 else (
         np.ones(n, np.int32) if hier else None)
     env = BatchedHumanoidEnv(n, wl["mode"], clips=wl["clips"], clip_of_env=cid, device=local_rank, seed=1234,
-                             auto_reset=True, env_id_base=first)  # same seed, global env ids: sharding-invariant
+                             auto_reset=True, env_id_base=first,  # same seed, global env ids: sharding-invariant
+                             self_collision=bool(wl.get("self_collision")))
     if wl.get("terrain"):   # CustomScene.episode_restart (REF humanoid.py:88-124), one terrain per handle
         tr = np.random.default_rng(99)
         h = np.repeat(np.repeat(tr.uniform(0, 0.5, (128, 128)), 2, axis=0), 2, axis=1)
@@ -492,7 +496,8 @@ def run_ours(args):
     extra = {}
     if args.workload == "low4096" and not args.no_extra_configs:
         for key, name in (("cfg3_hier16384", "hier16384"), ("cfg4_multiclip65536", "multiclip65536"),
-                          ("a18_hier2_16384", "hier2_16384"), ("f4_terrain4096", "terrain4096")):
+                          ("a18_hier2_16384", "hier2_16384"), ("f4_terrain4096", "terrain4096"),
+                          ("f4_selfcol4096", "selfcol4096")):
             r2, env2, p2 = measure_device(WORKLOADS[name], K, max(W, 10), rank, world, local_rank, clocks, min_region_s=0.3,
                                           kernel_events=False, use_graph=not args.no_graph)
             env2.close()

@@ -35,11 +35,13 @@ class BatchedHumanoidEnv:
     """mode "low": LowLevelHumanoidEnv semantics (REF low_level_env.py); "hier": HierarchicalHumanoidEnv
     (REF hier_env.py); "hier2": the hier_env_2.py variant (joint-target tracking low level: low obs 72, high obs 60,
     high action 36, skipFrame 5, step_per_level 20 unless given).  clips: list of clip names staged in HBM; clip_of_env: per-env index into that list.
+    self_collision: Bullet-style self-collision of the robot (REF humanoid.py:13; off by default, `set_self_collision`).
     env_id_base: global id of env 0 when a batch is sharded over several handles / GPUs (with the same seed the
     shards then reproduce exactly what one handle holding the whole batch would do)."""
 
     def __init__(self, num_envs, mode="low", clips=("motion09_03",), clip_of_env=None, device=0, seed=0,
-                 auto_reset=True, max_timestep=3000, step_per_level=None, env_id_base=0, skip_frame=None):
+                 auto_reset=True, max_timestep=3000, step_per_level=None, env_id_base=0, skip_frame=None,
+                 self_collision=False):
         if not torch.cuda.is_available():
             raise _lib.IlrlError("BatchedHumanoidEnv needs a CUDA device (sm_100a); there is no CPU fallback")
         self.L = _lib.lib()
@@ -78,6 +80,8 @@ class BatchedHumanoidEnv:
             self.high_obs = torch.zeros(n, self.hobs_w, device=dev)
             self.high_reward = torch.zeros(n, device=dev)
             self.high_flags = torch.zeros(n, dtype=torch.uint8, device=dev)
+        if self_collision:
+            self._ck(self.L.ilrl_set_self_collision(self.h, 1))
         self._forced = None
         self._noise = None
         self._host_key = None
@@ -321,6 +325,11 @@ class BatchedHumanoidEnv:
         assert d.size == rows * cols
         zoff = float(body_z) - 0.5 * (float(d.min()) + float(d.max()))
         self._ck(self.L.ilrl_set_heightfield(self.h, d.ctypes.data, int(rows), int(cols), zoff))
+
+    def set_self_collision(self, on=True):
+        """Bullet-style self-collision of the robot ("low" mode; REF humanoid.py:13 `self_collision = True`): 66 capsule
+        pairs, two-body contact rows.  Off by default."""
+        self._ck(self.L.ilrl_set_self_collision(self.h, int(bool(on))))
 
     def set_forced_reset_noise(self, noise17):
         """mode "hier2" harness: the joint noise [N,17] resets use instead of their own uniform(-0.1, 0.1) draws (only the

@@ -35,6 +35,7 @@ using chain::QT;
 using SmemSmall = chain::SmemT<chain::LayoutSmall>;
 using SmemLarge = chain::SmemT<chain::LayoutLarge>;
 using SmemDense4 = chain::SmemT<chain::LayoutDense4>;
+using SmemSelf = chain::SmemT<chain::LayoutSelf>;
 
 struct StepArgs {
   int n;               // envs of the handle (stride of the structure-of-arrays state)
@@ -70,6 +71,7 @@ struct StepArgs {
   long long* prof;     // [warps of the launch][PF_WORDS] phase cycles (measurement build only)
 #endif
   chain::Terrain terr; // heightfield terrain (terr.h null: flat ground; only read by the TERR instantiations)
+  chain::SelfC selfc;  // self-collision scratch (only read by the SELFC instantiations)
   ClipDesc clips[MAX_CLIPS];
 };
 
@@ -127,6 +129,9 @@ __device__ __forceinline__ void quad_smem_init(SM& sm) {
 #pragma unroll
     for (int k = 0; k < PER; k++) { const int t = threadIdx.x + k * QT; if (t < chain::TABLE_WORDS) dst[t] = v[k]; }
   }
+  if constexpr (SM::SELF) {   // wide row 0 of every env must hold finite numbers (lanes past their count re-evaluate it)
+    for (int k = 0; k < chain::WRW / 4; k++) sm.S.wr[threadIdx.x >> 2][(threadIdx.x & 3) * (chain::WRW / 4) + k] = 0.f;
+  }
 }
 // torques of this lane's chain into the link records: apply_action (REF humanoid.py:54-60): clip, gear x power,
 // motor slot -> joint.  act: the env's action row in shared memory (null: joint-order torques in `torque`)
@@ -150,7 +155,7 @@ __device__ __forceinline__ void set_torques(SM& sm, int e, int tid, int role, co
 // stream, no divergence) and the outputs are dealt to the lanes for the stores.
 // One tile (QE envs) of one env step: everything between a CTA picking its tile and moving on.  Shared by the
 // launch-per-step kernel and the persistent serving kernel (K1s).  action: the [n,17] action array of this step.
-template <int MODE, class SM, bool TERR>
+template <int MODE, class SM, bool TERR, bool SELFC = false>
 __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int tile, const float* action) {
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
@@ -224,13 +229,15 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
   }
   if (!a.skip_physics) {
     float* gscr_tile = a.gscr + (size_t)min(base, a.n - 1) * chain::GROWS * chain::RW;
+    chain::SelfC sct = a.selfc;
+
 #pragma unroll 1
     for (int sub = 0; sub < ILRL_SUBSTEPS; sub++) {
       pf.mark(sub == 0 ? chain::PF_HEAD : chain::PF_INTEG);
       __syncthreads();
       pf.mark(chain::PF_BARRIER);
-      chain::substep<TERR>(b, sm, gscr_tile, e, tid, role, active, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf,
-                           TERR ? &a.terr : nullptr);
+      chain::substep<TERR, SELFC>(b, sm, gscr_tile, e, tid, role, active, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf,
+                                  TERR ? &a.terr : nullptr, SELFC ? &sct : nullptr);
     }
   }
   __syncthreads();   // the once-per-step tail (4 k instructions) is entered together as well: +3 % at 65536 envs
@@ -400,7 +407,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
 }
 
 
-template <int MODE, class SM, bool TERR = false>
+template <int MODE, class SM, bool TERR = false, bool SELFC = false>
 __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   SM& sm = *reinterpret_cast<SM*>(smraw);
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   __syncthreads();
   const int tile = s_tile;
   if (tile >= a.ntiles) break;
-  step_tile<MODE, SM, TERR>(a, sm, tile, a.action);
+  step_tile<MODE, SM, TERR, SELFC>(a, sm, tile, a.action);
   }  // tile loop
   if (!one_wave && tid == 0 && atomicAdd(a.tile_counter + 1, 1u) == gridDim.x - 1) {  // last CTA out: ready for the next launch
     a.tile_counter[0] = 0u;
@@ -647,9 +654,10 @@ __global__ void clip_ids_kernel(StateView v, const int32_t* ids) {
   if (i >= v.n) return;
   v.envf[(size_t)ILRL_E_CLIP * v.n + i] = ids ? (float)ids[i] : 0.f;
 }
-template <class SM, bool TERR = false>
+template <class SM, bool TERR = false, bool SELFC = false>
 __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const float* torque, float* gscr_all, int nsub,
-                                                          const chain::Terrain terr = chain::Terrain()) {
+                                                          const chain::Terrain terr = chain::Terrain(),
+                                                          const chain::SelfC selfc = chain::SelfC()) {
   extern __shared__ __align__(16) unsigned char smraw[];
   SM& sm = *reinterpret_cast<SM*>(smraw);
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
@@ -671,7 +679,13 @@ __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const flo
   __syncwarp();
   float* gscr_tile = gscr_all + (size_t)blockIdx.x * QE * chain::GROWS * chain::RW;
   for (int sub = 0; sub < nsub; sub++)
-    { chain::Prof pf; chain::substep<TERR>(b, sm, gscr_tile, e, tid, role, valid, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf, TERR ? &terr : nullptr); }
+  {
+    chain::Prof pf;
+    chain::SelfC sct = selfc;
+
+    chain::substep<TERR, SELFC>(b, sm, gscr_tile, e, tid, role, valid, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf,
+                                TERR ? &terr : nullptr, SELFC ? &sct : nullptr);
+  }
   if (!valid) return;
   Phys ps;
   chain::gather(b, sm, e, qb, qm, ps);
@@ -810,6 +824,8 @@ struct ilrl_env {
   float* jt = nullptr;                    // [34][n] jointTarget (mode 2 only)
   chain::Terrain terr = {nullptr, 0, 0, 0.f, 0.f, 1.f};   // ilrl_set_heightfield (mode 0); h = device copy owned by the handle
   float* terr_mem = nullptr;
+  chain::SelfC selfc = {0};
+  bool self_on = false;
   const float* forced_noise = nullptr;    // ilrl_set_forced_reset_noise
   int obs_w = ILRL_OBS_LOW, hobs_w = ILRL_OBS_HIGH, hact_w = ILRL_ACT_HIGH;   // row widths of the mode
   float* high_obs = nullptr;
@@ -929,6 +945,12 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaFuncSetAttribute(step_kernel<1, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemLarge, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(physics_only_kernel<SmemLarge, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
+  CKC(cudaFuncSetAttribute(step_kernel<0, SmemSelf, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSelf)));
+  CKC(cudaFuncSetAttribute(step_kernel<0, SmemSelf, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSelf)));
+  CKC(cudaFuncSetAttribute(step_kernel<1, SmemSelf, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSelf)));
+  CKC(cudaFuncSetAttribute(step_kernel<2, SmemSelf, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSelf)));
+  CKC(cudaFuncSetAttribute(physics_only_kernel<SmemSelf, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSelf)));
+  CKC(cudaFuncSetAttribute(physics_only_kernel<SmemSelf, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSelf)));
   CKC(cudaFuncSetAttribute(step_kernel<2, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
   CKC(cudaFuncSetAttribute(step_kernel<2, SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(step_kernel<2, SmemDense4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDense4)));
@@ -1129,7 +1151,7 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   a.action = action; a.obs = obs; a.reward = reward; a.done = done; a.terms = terms;
   a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
   a.forced_deg = env->forced_deg; a.forced_scalar = forced_scalar; a.stats = env->stats; a.gscr = env->gscr;
-  a.jt = env->jt; a.forced_noise = env->forced_noise; a.terr = env->terr;
+  a.jt = env->jt; a.forced_noise = env->forced_noise; a.terr = env->terr; a.selfc = env->selfc;
   a.tile_counter = env->tile_counter + 2 * (part + 1);
 #ifdef ILRL_PROF
   a.prof = env->prof;
@@ -1137,12 +1159,17 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   memcpy(a.clips, env->clips, sizeof a.clips);
   a.ktime = (env->timing && env->kt_used < KT_SLOTS) ? env->ktime + 2 * (size_t)env->kt_used++ : nullptr;
   a.ntiles = (count + QE - 1) / QE;
-  // (heightfield terrain: one instantiation, the mid-size layout, whatever the batch size)
-  const int layout = env->terr.h ? 1 : env->layout;
+  // (heightfield terrain / self-collision: their own instantiations, in the mid-size layout whatever the batch size)
+  const bool special = env->terr.h || env->self_on;
+  const int layout = special ? 1 : env->layout;
   const int qblk = min(a.ntiles, layout == 2 ? env->grid_dense4 : layout == 1 ? env->grid_large : env->grid_small);
   const int md = env->cfg.mode;
-  if (env->terr.h) {
-    step_kernel<0, SmemLarge, true><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
+  if (special) {
+    if (env->terr.h && env->self_on) step_kernel<0, SmemSelf, true, true><<<qblk, QT, sizeof(SmemSelf), st>>>(a);
+    else if (env->self_on && md == 0) step_kernel<0, SmemSelf, false, true><<<qblk, QT, sizeof(SmemSelf), st>>>(a);
+    else if (env->self_on && md == 1) step_kernel<1, SmemSelf, false, true><<<qblk, QT, sizeof(SmemSelf), st>>>(a);
+    else if (env->self_on) step_kernel<2, SmemSelf, false, true><<<qblk, QT, sizeof(SmemSelf), st>>>(a);
+    else step_kernel<0, SmemLarge, true><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
   } else if (env->layout == 2) {
     if (md == 0) step_kernel<0, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
     else if (md == 1) step_kernel<1, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
@@ -1380,7 +1407,7 @@ int ilrl_serve_begin(ilrl_env* env, int32_t nparts, float* obs_h, float* reward_
   if (int r = check_ready(env)) return r;
   ON_DEVICE(env);
   if (env->cfg.mode != 0) return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: low-level mode only (the hierarchical modes need their high-level call between steps)");
-  if (env->terr.h) return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: not available with a heightfield terrain");
+  if (env->terr.h || env->self_on) return fail(env, ILRL_ERR_ARG, "ilrl_serve_begin: not available with a heightfield terrain / self-collision");
   int total_tiles = 0;
   for (int p = 0; p < nparts; p++) {
     int first, count;
@@ -1420,7 +1447,7 @@ int ilrl_serve_begin(ilrl_env* env, int32_t nparts, float* obs_h, float* reward_
     a.action = nullptr; a.obs = (float*)dobs; a.reward = (float*)dr; a.done = (uint8_t*)dd; a.terms = (float*)dt;
     a.high_obs = env->high_obs; a.high_reward = env->high_reward; a.high_flags = env->high_flags;
     a.forced_deg = env->forced_deg; a.forced_scalar = INT_MIN; a.stats = env->stats; a.gscr = env->gscr;
-    a.jt = env->jt; a.forced_noise = env->forced_noise; a.terr = env->terr;
+    a.jt = env->jt; a.forced_noise = env->forced_noise; a.terr = env->terr; a.selfc = env->selfc;
     a.tile_counter = env->tile_counter; a.ntiles = (count + QE - 1) / QE; a.ktime = nullptr;
 #ifdef ILRL_PROF
     a.prof = nullptr;
@@ -1599,6 +1626,14 @@ int ilrl_set_heightfield(ilrl_env* env, const float* heights, int32_t rows, int3
   env->terr = chain::Terrain{env->terr_mem, rows, cols, zoff, hmax + zoff, 1.f / sqrtf(1.f + g2max)};
   return ILRL_OK;
 }
+int ilrl_set_self_collision(ilrl_env* env, int32_t on) {
+  if (!env) return ILRL_ERR_ARG;
+  ON_DEVICE(env);
+  CK(cudaDeviceSynchronize());
+  if (!on) { env->self_on = false; return ILRL_OK; }
+  env->self_on = true;
+  return ILRL_OK;
+}
 int ilrl_set_forced_reset_noise(ilrl_env* env, const float* noise17) {
   if (!env) return ILRL_ERR_ARG;
   if (env->cfg.mode != 2) return fail(env, ILRL_ERR_ARG, "ilrl_set_forced_reset_noise: only the hier_env_2 mode keeps reset noise");
@@ -1627,7 +1662,11 @@ int ilrl_physics_only(ilrl_env* env, const float* torque, void* stream) {
   if (!env) return ILRL_ERR_ARG;
   if (!torque) return fail(env, ILRL_ERR_ARG, "ilrl_physics_only: null buffer");
   ON_DEVICE(env);
-  if (env->terr.h)
+  if (env->terr.h && env->self_on)
+    physics_only_kernel<SmemSelf, true, true><<<(env->n + QE - 1) / QE, QT, sizeof(SmemSelf), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps, env->terr, env->selfc);
+  else if (env->self_on)
+    physics_only_kernel<SmemSelf, false, true><<<(env->n + QE - 1) / QE, QT, sizeof(SmemSelf), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps, env->terr, env->selfc);
+  else if (env->terr.h)
     physics_only_kernel<SmemLarge, true><<<(env->n + QE - 1) / QE, QT, sizeof(SmemLarge), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps, env->terr);
   else if (env->layout == 2)
     physics_only_kernel<SmemDense4><<<(env->n + QE - 1) / QE, QT, sizeof(SmemDense4), (cudaStream_t)stream>>>(view(env), torque, env->gscr, env->substeps);

@@ -193,8 +193,12 @@ static_assert(sizeof(Tables) % 4 == 0, "table copy is word-wise");
 //                 substep): 4 CTAs per SM.
 // In all, the body records (written by the FK phase, consumed by the inward pass) share their storage with what
 // only the row phase uses (multipliers) and with the action tile (consumed before the first substep).
-template <int RSM_, int BRW_, bool TSM_, int LANE_>
+constexpr int NSELF = ILRL_NSELF, MAXSELF = 8, WRW = 24;   // self-collision: pairs, kept contacts per env, words per wide row
+constexpr int SELF_GP = NS * 3 + 1;                          // sphere centres of an env (+1: env stride 88 = 24 mod 32 words)
+constexpr int SELF_WR = 3 * MAXSELF * WRW;                   // wide-row words per env
+template <int RSM_, int BRW_, bool TSM_, int LANE_, bool SELF_ = false>
 struct Layout {
+  static constexpr bool SELF = SELF_;            // self-collision instantiations: sphere centres + candidate masks on chip
   static constexpr int RSM = RSM_;               // constraint rows per env kept in shared memory
   static constexpr int ROWSTRIDE = RSM_ * RW + 4;  // env stride in words: = 4 (mod 32)
   static constexpr int BRW = BRW_;               // words per body record (20: room for padding; 16: dense)
@@ -213,6 +217,7 @@ static_assert(ILRL_LARGE_RSM >= MIN_RSM, "the overflow scratch holds MAXROWS - M
 using LayoutSmall = Layout<ILRL_SMALL_RSM, 20, true, 40>;
 using LayoutLarge = Layout<ILRL_LARGE_RSM, ILRL_LARGE_BRW, ILRL_LARGE_TSM, 40>;
 using LayoutDense4 = Layout<ILRL_MIN_RSM, 16, false, 32>;
+using LayoutSelf = Layout<ILRL_LARGE_RSM, ILRL_LARGE_BRW, ILRL_LARGE_TSM, 40, true>;   // LayoutLarge + the self-collision arrays
 
 // Per-env scratch block, seen in two ways that are never live at the same time within an env:
 //   body view (FK phase -> inward pass): body records of the four lanes (2 each, lane stride LANE words) + the spine's 2
@@ -230,10 +235,17 @@ template <int BRW, int LANE> constexpr int scr_words() {
 }
 
 struct NoTables {};
+struct NoSelf {};
+struct alignas(16) SelfSm {
+  float gp[QE][SELF_GP];      // sphere centres relative to the torso (world axes), published by the FK pass
+  uint32_t mask[QE][4];       // candidate pairs (66 bits), set by the pair tests of the warp's pool
+  float wr[QE][SELF_WR + 4];  // the wide rows (env stride = 4 mod 32 words): 36 KB per CTA, 2 CTAs per SM
+};
 template <class LY>
 struct __align__(16) SmemT {
   static constexpr int RSM = LY::RSM, ROWSTRIDE = LY::ROWSTRIDE, BRW = LY::BRW, ES = scr_words<LY::BRW, LY::LANE>();
   static constexpr bool TSM = LY::TSM;
+  static constexpr bool SELF = LY::SELF;
   static constexpr int SCR_LANE = LY::LANE;
   static_assert(2 * BRW <= SCR_LANE, "two body records per lane");
   // --- float4-accessed arrays first (every size below is a multiple of 16 bytes)
@@ -245,6 +257,7 @@ struct __align__(16) SmemT {
   float L0[21][QE];            // Cholesky factor of the base articulated inertia
   float sph[NS][3][QE];        // contact candidates: x, y, z - r relative to the torso origin (distance = base z + that)
   typename std::conditional<TSM, Tables, NoTables>::type T;
+  typename std::conditional<LY::SELF, SelfSm, NoSelf>::type S;
   static_assert((sizeof(float) * QE * ROWSTRIDE) % 16 == 0 && (sizeof(float) * LKW) % 16 == 0 && BRW % 4 == 0 && ES % 4 == 0,
                 "float4 alignment of the shared-memory records");
   static_assert(ES >= 71, "the obs row is staged in the env's scratch block");
@@ -322,7 +335,78 @@ __device__ __forceinline__ float qsum(float v, unsigned qm) {
 __device__ __forceinline__ SV neg(SV a) { SV r; r.a = mk(-a.a.x, -a.a.y, -a.a.z); r.l = mk(-a.l.x, -a.l.y, -a.l.z); return r; }
 __device__ __forceinline__ SV svzero() { SV r; r.a = r.l = mk(0, 0, 0); return r; }
 __device__ __forceinline__ V3 rd3(const float* p) { return mk(p[0], p[1], p[2]); }
+__device__ __forceinline__ V3 rd3g(const float* p) { return mk(__ldcg(p), __ldcg(p + 1), __ldcg(p + 2)); }  // L2 (written by other lanes)
 __device__ __forceinline__ float rcp_or_zero(float d) { return d > 1e-9f ? __frcp_rn(d) : 0.f; }
+
+// ---- self-collision (REF humanoid.py:13 `self_collision = True`).  Only the SELFC instantiations of the
+// kernels carry any of it.  [BULLET, restated] URDF_USE_SELF_COLLISION | URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS: every
+// pair of geoms collides unless one body is an ancestor of the other: 66 pairs of the 14 single-geom bodies below the
+// torso (capsules; spheres are zero-length capsules), friction 2.0 x 2.0, rows after the ground contacts, at most
+// MAXSELF contacts per env (the deepest).  Same model as the oracle (ilrl_oracle_set_self_collision).
+// A contact between bodies A and B is a row on base + spine + (up to) TWO limbs: 17 whitened numbers, stored as a
+// 24-word "wide" row in shared memory (SelfSm::wr):
+//   zb[0..3] | zb[4] zb[5] rhs dinv | zs[0..2] limbs (LA | LB << 8; 15 = none) | zlA[0..3] | zlB[0..3] | - - - lambda
+__device__ constexpr int kSelfA0[NSELF] = ILRL_SELF_A0;
+__device__ constexpr int kSelfA1[NSELF] = ILRL_SELF_A1;
+__device__ constexpr int kSelfB0[NSELF] = ILRL_SELF_B0;
+__device__ constexpr int kSelfB1[NSELF] = ILRL_SELF_B1;
+__device__ constexpr float kSelfReach[NSELF] = ILRL_SELF_REACH;   // broad phase: no contact while the axis midpoints are farther apart
+constexpr float SELF_FRICTION = 4.0f;   // geom friction 2.0 (REF humanoid_symmetric_2.xml:5) x 2.0
+// (sphere centres, candidate masks and the wide rows live in shared memory: SelfSm)
+struct SelfC { int unused; };
+
+// closest points of two segments (Ericson 5.1.9), as the oracle's seg_seg
+__device__ __forceinline__ void seg_seg_f(V3 p1, V3 q1, V3 p2, V3 q2, V3& c1, V3& c2) {
+  const V3 d1 = q1 - p1, d2 = q2 - p2, r = p1 - p2;
+  const float a = dot(d1, d1), e = dot(d2, d2), f = dot(d2, r), EPS = 1e-12f;
+  float s, t;
+  if (a <= EPS && e <= EPS) { s = t = 0.f; }
+  else if (a <= EPS) { s = 0.f; t = fminf(fmaxf(f / e, 0.f), 1.f); }
+  else {
+    const float c = dot(d1, r);
+    if (e <= EPS) { t = 0.f; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
+    else {
+      const float b = dot(d1, d2), den = a * e - b * b;
+      s = den > EPS ? fminf(fmaxf((b * f - c * e) / den, 0.f), 1.f) : 0.f;
+      t = (b * s + f) / e;
+      if (t < 0.f) { t = 0.f; s = fminf(fmaxf(-c / a, 0.f), 1.f); }
+      else if (t > 1.f) { t = 1.f; s = fminf(fmaxf((b - c) / a, 0.f), 1.f); }
+    }
+  }
+  c1 = p1 + s * d1; c2 = p2 + t * d2;
+}
+// pair p of an env whose sphere centres are at gp: closest points on the two axes, distance between the surfaces
+__device__ __forceinline__ float self_pair(const float* gp, int p, V3& c1, V3& c2) {
+  const int a0 = kSelfA0[p], a1 = kSelfA1[p], b0 = kSelfB0[p], b1 = kSelfB1[p];
+  seg_seg_f(rd3(gp + 3 * a0), rd3(gp + 3 * a1), rd3(gp + 3 * b0), rd3(gp + 3 * b1), c1, c2);
+  const V3 d = c1 - c2;
+  return sqrtf(dot(d, d)) - kSphereR[a0] - kSphereR[b0];
+}
+// the same with the broad phase in front: a pair whose axis midpoints are farther apart than its reach cannot touch
+__device__ __forceinline__ bool self_pair_active(const float* gp, int p) {
+  const int a0 = kSelfA0[p], a1 = kSelfA1[p], b0 = kSelfB0[p], b1 = kSelfB1[p];
+  const V3 pa0 = rd3(gp + 3 * a0), pa1 = rd3(gp + 3 * a1), pb0 = rd3(gp + 3 * b0), pb1 = rd3(gp + 3 * b1);
+  const V3 dm = 0.5f * ((pa0 + pa1) - (pb0 + pb1));
+  const float reach = kSelfReach[p];
+  if (dot(dm, dm) > reach * reach) return false;
+  V3 c1, c2;
+  seg_seg_f(pa0, pa1, pb0, pb1, c1, c2);
+  const V3 d = c1 - c2;
+  return sqrtf(dot(d, d)) - kSphereR[a0] - kSphereR[b0] < (float)ILRL_CONTACT_BREAK;
+}
+
+// btPlaneSpace1 (any unit normal)
+__device__ __forceinline__ void plane_space(V3 n, V3& p, V3& q) {
+  if (fabsf(n.z) > 0.7071067811865475244f) {
+    const float a = n.y * n.y + n.z * n.z, k = rsqrtf(a);
+    p = mk(0.f, -n.z * k, n.y * k);
+    q = mk(a * k, -n.x * p.z, n.x * p.y);
+  } else {
+    const float a = n.x * n.x + n.y * n.y, k = rsqrtf(a);
+    p = mk(-n.y * k, n.x * k, 0.f);
+    q = mk(-n.z * p.y, n.z * p.x, a * k);
+  }
+}
 
 // sin/cos of a joint angle.  Joint angles stay within a few radians of their limits (|q| << 100), so the Payne-Hanek
 // large-argument path of sincosf() would be dead weight in the instruction stream: two-constant Cody-Waite reduction
@@ -496,9 +580,9 @@ __device__ __forceinline__ SV chol6_solve_smem(const float* L, SV b) {
 struct FkOut { uint32_t act, lim; float sx, sy, ssx, ssy, ex, ey; };
 
 // FULL = false: pose only (part-origin sums and the end-body origin), nothing is written to shared memory.
-template <bool FULL, bool TERR = false, class SM>
+template <bool FULL, bool TERR = false, bool SELFC = false, class SM>
 __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, int role, FkOut& o,
-                                         const Terrain* terr = nullptr) {
+                                         const Terrain* terr = nullptr, float* gpe = nullptr) {
   const Tables& T = tables(sm);
   float R0[9];
   quat2mat(b.quat[0], b.quat[1], b.quat[2], b.quat[3], R0);
@@ -589,12 +673,15 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
         if (FULL) rigid_rec(Rc, ob, B.m, B.ix, B.iy, B.iz, Vp, rcd);
         if (c < 3) { ssx += ob.x; ssy += ob.y; } else { sx += ob.x; sy += ob.y; }
         ex = ob.x; ey = ob.y;
-        if (FULL && (TERR ? (b.p[2] + ob.z - terr->hmax) * terr->nzmin - B.reach : b.p[2] + ob.z - B.reach) < (float)ILRL_CONTACT_BREAK) {
+        // (SELFC: the sphere centres of every body are published for the pair tests, so the per-body early-out of the
+        // ground test - an optimisation that never changes which spheres pass - is not taken)
+        if (FULL && (SELFC || (TERR ? (b.p[2] + ob.z - terr->hmax) * terr->nzmin - B.reach : b.p[2] + ob.z - B.reach) < (float)ILRL_CONTACT_BREAK)) {
 #pragma unroll 1
           for (int t = 0; t < B.nsph; t++) {
             const int g = B.sidx[t];
             V3 cs_ = ob + mv(Rc, rd3(B.sph[t]));
             const float rad = B.sph[t][3];
+            if (SELFC && gpe) { gpe[3 * g] = cs_.x; gpe[3 * g + 1] = cs_.y; gpe[3 * g + 2] = cs_.z; }
             float d, w2;
             if constexpr (TERR) {
               V3 n;
@@ -767,6 +854,181 @@ __device__ __forceinline__ void build_contact_rows(const SM& sm, const Tables& T
   }
 }
 
+// the three WIDE rows (normal, two friction directions) of self-contact pair p of env e: +F on body A at xa, -F on body
+// B at xb.  Each side walks its own limb inward; the legs' remainders (and the forces on lwaist / pelvis) enter the
+// spine walk, the arms' remainders go straight to the base.  gp: the env's sphere centres; wrow: 3 x WRW words.
+template <class SM>
+__device__ __forceinline__ void build_self_rows(const SM& sm, const Tables& T, int p, int e, int qb, float idt,
+                                                const float* gp, const float* nub, float* wrow) {
+  V3 c1, c2;
+  const float dist = self_pair(gp, p, c1, c2);
+  V3 n = c1 - c2;
+  float len = sqrtf(dot(n, n));
+  if (len < 1e-9f) { n = mk(0.f, 0.f, 1.f); len = 1.f; }
+  n = (1.f / len) * n;   // from body B towards body A
+  const int ga = kSelfA0[p], gb = kSelfB0[p];
+  const V3 xa = c1 - kSphereR[ga] * n, xb = c2 + kSphereR[gb] * n;
+  V3 dir[3];
+  dir[0] = n;
+  plane_space(n, dir[1], dir[2]);
+  const int LA = T.sphL[ga], CA = T.sphC[ga], LB = T.sphL[gb], CB = T.sphC[gb];
+  SV FA[3], FB[3], pfS[3], pfB0[3];   // pfS: force travelling down the spine, pfB0: force arriving at the base directly
+  float dd[3], zs[3][3], zl[2][3][4];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    FA[i].l = dir[i]; FA[i].a = cross(xa, dir[i]);
+    FB[i].l = dir[i]; FB[i].a = cross(xb, dir[i]);
+    pfS[i] = svzero(); pfB0[i] = svzero(); dd[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) zs[i][k] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; k++) { zl[0][i][k] = 0.f; zl[1][i][k] = 0.f; }
+  }
+  SV Vs[2];   // unconstrained new velocity of the two bodies
+  Vs[0].a = mk(nub[0], nub[1], nub[2]); Vs[0].l = mk(nub[3], nub[4], nub[5]);
+  Vs[1] = Vs[0];
+  int enter[2];   // spine index at which the side's force enters the spine walk (-1: never, an arm)
+#pragma unroll
+  for (int side = 0; side < 2; side++) {
+    const int L = side ? LB : LA, C = side ? CB : CA;
+    SV pf[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) pf[i] = side ? FB[i] : neg(FA[i]);
+    if (L >= 0) {
+#pragma unroll 1
+      for (int c = C; c >= 3; c--) {
+        SV S, U;
+        float di, sq;
+        const float* rec = link_rec_of(sm, L, c, e, qb);
+        ld_SUq(rec, S, U, di, sq);
+        Vs[side] = Vs[side] + rec[W_NU] * S;
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const float u = -sdot(S, pf[i]), z = u * sq;
+          zl[side][i][c - 3] = z;
+          dd[i] = fmaf(z, z, dd[i]);
+          pf[i] = pf[i] + (u * di) * U;
+        }
+      }
+      enter[side] = L < 2 ? 2 : -1;
+    } else {
+      enter[side] = C;   // lwaist (1) or pelvis (2)
+    }
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      if (enter[side] == 2) pfS[i] = pfS[i] + pf[i];
+      else if (enter[side] < 0) pfB0[i] = pfB0[i] + pf[i];
+    }
+  }
+  // spine walk 2 -> 0; a force on lwaist joins at link 1
+#pragma unroll 1
+  for (int c = 2; c >= 0; c--) {
+    if (c == 1) {
+#pragma unroll
+      for (int side = 0; side < 2; side++)
+        if (enter[side] == 1) {
+#pragma unroll
+          for (int i = 0; i < 3; i++) pfS[i] = pfS[i] + (side ? FB[i] : neg(FA[i]));
+        }
+    }
+    SV S, U;
+    float di, sq;
+    const float* rec = link_rec_of(sm, -1, c, e, qb);
+    ld_SUq(rec, S, U, di, sq);
+    const float nu = rec[W_NU];
+#pragma unroll
+    for (int side = 0; side < 2; side++)
+      if (enter[side] >= c) Vs[side] = Vs[side] + nu * S;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float u = -sdot(S, pfS[i]), z = u * sq;
+      zs[i][c] = z;
+      dd[i] = fmaf(z, z, dd[i]);
+      pfS[i] = pfS[i] + (u * di) * U;
+    }
+  }
+  const float* L0 = &sm.L0[0][e];
+  const int lab = (LA < 0 ? 15 : LA) | ((LB < 0 ? 15 : LB) << 8);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float y[6];
+    fwd_subst(L0, neg(pfS[i] + pfB0[i]), y);
+    float d = dd[i];
+#pragma unroll
+    for (int k = 0; k < 6; k++) d = fmaf(y[k], y[k], d);
+    const float dinv = __frcp_rn(d);
+    const float pos = i == 0 ? (dist > 0.f ? -dist * idt : -dist * (float)ILRL_CONTACT_ERP * idt) : 0.f;
+    const float rv = sdot(Vs[0], FA[i]) - sdot(Vs[1], FB[i]);
+    float4* r4 = reinterpret_cast<float4*>(wrow + i * WRW);
+    r4[0] = make_float4(y[0], y[1], y[2], y[3]);
+    r4[1] = make_float4(y[4], y[5], (pos - rv) * dinv, dinv);
+    r4[2] = make_float4(zs[i][0], zs[i][1], zs[i][2], __int_as_float(lab));
+    r4[3] = make_float4(zl[0][i][0], zl[0][i][1], zl[0][i][2], zl[0][i][3]);
+    r4[4] = make_float4(zl[1][i][0], zl[1][i][1], zl[1][i][2], zl[1][i][3]);
+    r4[5] = make_float4(0.f, 0.f, 0.f, 0.f);   // (word 23: the row's multiplier)
+  }
+}
+// wide-row Gauss-Seidel pieces (the quad sums the limb parts: a wide row has two owner lanes)
+struct WRow { float4 a, b, c, d, f, g; };
+__device__ __forceinline__ void wrow_load(const float* w, WRow& r) {
+  const float4* p = reinterpret_cast<const float4*>(w);
+  r.a = p[0]; r.b = p[1]; r.c = p[2]; r.d = p[3]; r.f = p[4]; r.g = p[5];
+}
+__device__ __forceinline__ float wrow_resid(const WRow& r, const float* zb, const float* zc, int role) {
+  const int lab = __float_as_int(r.c.w), LA = lab & 15, LB = (lab >> 8) & 15;
+  float own = 0.f;
+  if (role == LA) own = fmaf(r.d.y, zc[4], r.d.x * zc[3]) + fmaf(r.d.w, zc[6], r.d.z * zc[5]);
+  if (role == LB) own += fmaf(r.f.y, zc[4], r.f.x * zc[3]) + fmaf(r.f.w, zc[6], r.f.z * zc[5]);
+  own += __shfl_xor_sync(FULLMASK, own, 1);
+  own += __shfl_xor_sync(FULLMASK, own, 2);
+  const float r0 = fmaf(r.a.z, zb[2], fmaf(r.a.y, zb[1], r.a.x * zb[0]));
+  const float r1 = fmaf(r.b.y, zb[5], fmaf(r.b.x, zb[4], r.a.w * zb[3]));
+  const float r2 = fmaf(r.c.z, zc[2], fmaf(r.c.y, zc[1], r.c.x * zc[0]));
+  return fmaf(-r.b.w, ((r0 + r1) + r2) + own, r.g.w + r.b.z);   // lambda + rhs - dinv (z_row . z)
+}
+__device__ __forceinline__ void wrow_axpy(const WRow& r, float a, int role, float* zb, float* zc) {
+  const int lab = __float_as_int(r.c.w), LA = lab & 15, LB = (lab >> 8) & 15;
+  zb[0] += a * r.a.x; zb[1] += a * r.a.y; zb[2] += a * r.a.z; zb[3] += a * r.a.w; zb[4] += a * r.b.x; zb[5] += a * r.b.y;
+  zc[0] += a * r.c.x; zc[1] += a * r.c.y; zc[2] += a * r.c.z;
+  const float aa = role == LA ? a : 0.f, ab = role == LB ? a : 0.f;
+  zc[3] += aa * r.d.x + ab * r.f.x; zc[4] += aa * r.d.y + ab * r.f.y; zc[5] += aa * r.d.z + ab * r.f.z; zc[6] += aa * r.d.w + ab * r.f.w;
+}
+// one sweep's self-contact normals / friction pairs (warp-uniform loops; a quad past its own count re-evaluates its
+// row 0 - finite: zero at allocation or a real row - with a zero step)
+__device__ __forceinline__ void wide_normals(float* wr, int nself, int ns_w, int role, float* zb, float* zc) {
+#pragma unroll 1
+  for (int k = 0; k < ns_w; k++) {
+    const bool live = k < nself;
+    float* w = wr + (live ? 3 * k : 0) * WRW;
+    WRow r;
+    wrow_load(w, r);
+    const float nl = fmaxf(wrow_resid(r, zb, zc, role), 0.f);
+    if (live && role == 0) w[23] = nl;
+    wrow_axpy(r, live ? nl - r.g.w : 0.f, role, zb, zc);
+  }
+}
+__device__ __forceinline__ void wide_friction(float* wr, int nself, int ns_w, int role, float* zb, float* zc) {
+#pragma unroll 1
+  for (int k = 0; k < ns_w; k++) {
+    const bool in = k < nself;
+    const float ln = in ? wr[3 * k * WRW + 23] : 0.f;
+    const bool live = in && ln > 0.f;
+    if (!__any_sync(FULLMASK, live)) continue;
+    float* w1 = wr + (live ? 3 * k + 1 : 0) * WRW;
+    float* w2 = wr + (live ? 3 * k + 2 : 0) * WRW;
+    WRow r1, r2;
+    wrow_load(w1, r1);
+    wrow_load(w2, r2);
+    const float lim_f = SELF_FRICTION * ln;
+    float s1 = wrow_resid(r1, zb, zc, role), s2 = wrow_resid(r2, zb, zc, role);
+    const float n2 = s1 * s1 + s2 * s2;
+    if (n2 > lim_f * lim_f) { const float sc = lim_f * rsqrtf(n2); s1 *= sc; s2 *= sc; }
+    if (live && role == 0) { w1[23] = s1; w2[23] = s2; }
+    wrow_axpy(r1, live ? s1 - r1.g.w : 0.f, role, zb, zc);
+    wrow_axpy(r2, live ? s2 - r2.g.w : 0.f, role, zb, zc);
+  }
+}
+
 // ---- projected Gauss-Seidel on the whitened impulse sum z.  zb: base, zc: chain (spine replicated, limb private)
 struct RowRegs { float4 a, b, c, d; };
 template <class P4>
@@ -804,10 +1066,11 @@ __device__ __forceinline__ void row_fetch(const SM& sm, const float* gscr, int e
 // MATCH / REDUX / VOTE / branch preamble in front of every shuffle: in-order issue put ~100 cycles of it on the
 // critical path of each row evaluation), so the loops run to the WARP's largest count and a lane past its own count
 // evaluates its row 0 (finite: zeroed at tile start or a real row) with a zero step.
-template <bool OVER, class SM>
+template <bool OVER, bool SELFC = false, class SM>
 __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int role, int qb, int nlim, int ncon,
-                                           float* zb, float* zc) {
+                                           float* zb, float* zc, float* wr = nullptr, int nself = 0) {
   constexpr bool FULL = true;
+  const int ns_w = SELFC ? __reduce_max_sync(FULLMASK, nself) : 0;
   constexpr unsigned m = FULLMASK;
   float* lamv = sm.lam(e);
   const int nfirst = nlim + ncon;
@@ -843,6 +1106,7 @@ __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int
         apply(k + 1, rb, lamb);
       }
     }
+    if constexpr (SELFC) wide_normals(wr, nself, ns_w, role, zb, zc);   // self-contact normals follow the ground normals
 #pragma unroll 1
     for (int c = 0; c < nc_w; c++) {  // friction pairs, cone re-projected on the current normal impulse
       const bool in = !FULL || c < ncon;
@@ -865,6 +1129,7 @@ __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int
       row_axpy(r1, live ? s1 - l1 : 0.f, mine, zb, zc);
       row_axpy(r2, live ? s2 - l2 : 0.f, mine, zb, zc);
     }
+    if constexpr (SELFC) wide_friction(wr, nself, ns_w, role, zb, zc);
   }
 }
 
@@ -874,9 +1139,10 @@ __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int
 // end of the batch, waiting for a high-level action, skipped by a NaN action) run on a benign dummy state
 // (`steps` = false: they produce no constraint rows and their results are never stored), and they still help to build
 // the rows of the warp's other envs.  gscr_tile: overflow-row scratch of env 0 of this CTA's tile.
-template <bool TERR = false, class SM>
+// SELFC: sc_tile = the self-collision scratch of env 0 of this CTA's tile (gp / sd / wr already offset to it).
+template <bool TERR = false, bool SELFC = false, class SM>
 __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e, int tid, int role, bool steps, float dt,
-                                        Prof& pf, const Terrain* terr = nullptr) {
+                                        Prof& pf, const Terrain* terr = nullptr, const SelfC* sc_tile = nullptr) {
   constexpr int RSM = SM::RSM;
   constexpr unsigned qm = FULLMASK, wm = FULLMASK;
   float* gscr = gscr_tile + (size_t)e * (GROWS * RW);
@@ -884,7 +1150,9 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
   const Tables& T = tables(sm);
   // ---- phase A
   FkOut fo;
-  fk_phase<true, TERR>(b, sm, e, tid, role, fo, terr);
+  float* gpe = nullptr;
+  if constexpr (SELFC) { if (steps) gpe = &sm.S.gp[e][0]; }
+  fk_phase<true, TERR, SELFC>(b, sm, e, tid, role, fo, terr, gpe);
   uint32_t act = fo.act, lim = fo.lim;
   pf.mark(PF_FK);
   // ---- phase B: inward pass
@@ -972,7 +1240,42 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
     act &= ~(1u << worst);
     nact--;
   }
-  const int nlim = __popc(lim), ncon = nact, nrows = nlim + 3 * ncon;
+  // ---- self-collision candidates: the 8 x 66 pair tests of the warp are one pool dealt to its 32 lanes
+  uint32_t sm0 = 0u, sm1 = 0u, sm2 = 0u;
+  int nself = 0;
+  float* wr_e = nullptr;
+  if constexpr (SELFC) {
+    const int lane = tid & 31, e0 = e & ~7;
+    const unsigned stepmask = __ballot_sync(FULLMASK, steps);
+    if (role < 3) sm.S.mask[e][role] = 0u;
+    __syncwarp();   // every lane's sphere centres (FK pass) and the cleared masks are visible to the warp
+#pragma unroll 1
+    for (int it = lane; it < 8 * NSELF; it += 32) {
+      const int q = it / NSELF, p = it - q * NSELF;
+      if (((stepmask >> (4 * q)) & 1u) && self_pair_active(&sm.S.gp[e0 + q][0], p))
+        atomicOr(&sm.S.mask[e0 + q][p >> 5], 1u << (p & 31));
+    }
+    __syncwarp();
+    if (steps) { sm0 = sm.S.mask[e][0]; sm1 = sm.S.mask[e][1]; sm2 = sm.S.mask[e][2]; }
+    nself = __popc(sm0) + __popc(sm1) + __popc(sm2);
+    while (nself > MAXSELF) {   // keep the deepest (ties: drop the later pair); replicated in the quad
+      int worst = -1;
+      float wd = -1e30f;
+#pragma unroll 1
+      for (int p = 0; p < NSELF; p++) {
+        const uint32_t w = p < 32 ? sm0 : p < 64 ? sm1 : sm2;
+        if ((w >> (p & 31)) & 1u) {
+          V3 c1, c2;
+          const float d = self_pair(&sm.S.gp[e][0], p, c1, c2);
+          if (d >= wd) { wd = d; worst = p; }
+        }
+      }
+      if (worst < 32) sm0 &= ~(1u << worst); else if (worst < 64) sm1 &= ~(1u << (worst - 32)); else sm2 &= ~(1u << (worst - 64));
+      nself--;
+    }
+    wr_e = &sm.S.wr[e][0];
+  }
+  const int nlim = __popc(lim), ncon = nact, nrows = nlim + 3 * ncon + 3 * nself;
   pf.mark(PF_OUTWARD);
   pf.maxv(PF_MAXROWS, (long long)__reduce_max_sync(FULLMASK, nrows));
   float zb[6], zc[NL];   // whitened impulse sum: base (replicated), chain (spine replicated, limb private)
@@ -991,8 +1294,8 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
     const int rank = lane;
     __syncwarp(wm);   // the link records and base factors of every env of the warp are complete
 #pragma unroll 1
-    for (int kind = 0; kind < 2; kind++) {
-      const int n_own = kind == 0 ? nlim : ncon;
+    for (int kind = 0; kind < (SELFC ? 3 : 2); kind++) {
+      const int n_own = kind == 0 ? nlim : kind == 1 ? ncon : nself;
       int cnt[8], total = 0;
 #pragma unroll
       for (int q = 0; q < 8; q++) {
@@ -1009,21 +1312,34 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
           if (q == t && k >= cnt[t]) { k -= cnt[t]; q = t + 1; }
         if (!has) { q = lane >> 2; k = 0; }
         const int src = 4 * q;
-        const uint32_t mask_q = __shfl_sync(wm, kind == 0 ? lim : act, src);
+        const uint32_t mask_q = __shfl_sync(wm, kind == 0 ? lim : kind == 1 ? act : sm0, src);
         const int nlim_q = __shfl_sync(wm, nlim, src);
         float bz_q = 0.f, bx_q = 0.f, by_q = 0.f, nub_q[6];
         int ncon_q = 0;
-        if (kind == 1) {
+        uint32_t m1_q = 0u, m2_q = 0u;
+        if (kind >= 1) {
           ncon_q = __shfl_sync(wm, ncon, src);
           bz_q = __shfl_sync(wm, b.p[2], src);
           if (TERR) { bx_q = __shfl_sync(wm, b.p[0], src); by_q = __shfl_sync(wm, b.p[1], src); }
 #pragma unroll
           for (int i = 0; i < 6; i++) nub_q[i] = __shfl_sync(wm, nub[i], src);
+          if (SELFC && kind == 2) { m1_q = __shfl_sync(wm, sm1, src); m2_q = __shfl_sync(wm, sm2, src); }
         }
         if (has) {
           const int e_q = (e & ~7) + q, qb_q = (tid & ~31) + 4 * q;
           float* gscr_q = gscr_tile + (size_t)e_q * (GROWS * RW);
           auto row_ptr = [&](int r) { return r < RSM ? &sm.rows[e_q][r * RW] : gscr_q + (size_t)(r - RSM) * RW; };
+          if constexpr (SELFC) if (kind == 2) {
+            // k-th set bit of the env's 66-bit pair mask
+            int kk = k, pidx;
+            const int c0 = __popc(mask_q), c1 = __popc(m1_q);
+            if (kk < c0) pidx = nth_set_bit(mask_q, kk);
+            else if (kk - c0 < c1) pidx = 32 + nth_set_bit(m1_q, kk - c0);
+            else pidx = 64 + nth_set_bit(m2_q, kk - c0 - c1);
+            build_self_rows(sm, T, pidx, e_q, qb_q, idt, &sm.S.gp[e_q][0], nub_q,
+                            &sm.S.wr[e_q][3 * k * WRW]);
+            continue;
+          }
           const int g = nth_set_bit(mask_q, k);
           if (kind == 0) {
             sm.lam(e_q)[k] = 0.f;
@@ -1060,7 +1376,7 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
   // (A dense variant - Delassus matrix Z Z^T formed once per substep, sweeps on w = A lambda in registers, no shuffle -
   // was built and measured: 45.3M against 52.8M env-steps/s at 4096 envs; the per-slot blocks are if-converted and
   // every warp pays for all 20 slots, and it broke bit-identity between the layouts.  profiles/r2_warp_phases.txt.)
-  if (__any_sync(FULLMASK, nrows > 0)) pgs_sweeps<(RSM < MAXROWS)>(sm, gscr, e, role, qb, nlim, ncon, zb, zc);
+  if (__any_sync(FULLMASK, nrows > 0)) pgs_sweeps<(RSM < MAXROWS), SELFC>(sm, gscr, e, role, qb, nlim, ncon, zb, zc, wr_e, nself);
   if (nrows > 0) bwd_subst(&sm.L0[0][e], zb);   // velocity change of the base: dv_base = L0^-T z_base
   __syncwarp();
   pf.mark(PF_PGS);

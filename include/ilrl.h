@@ -181,6 +181,13 @@ int ilrl_set_forced_target_deg(ilrl_env* env, const int32_t* deg_dev);
  * Synchronises the device. */
 int ilrl_set_heightfield(ilrl_env* env, const float* heights_host, int32_t rows, int32_t cols, float zoff);
 
+/* Self-collision of the robot (REF humanoid.py:13 `self_collision = True`; Bullet: URDF_USE_SELF_COLLISION |
+ * URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS): on = 1 makes the step run the self-collision instantiation of the kernel
+ * - every pair of the 14 limb / waist geoms whose bodies are not ancestor-related (66 capsule - capsule pairs), at most
+ * 8 contacts per env, two-body rows (normal + friction, coefficient 2.0 x 2.0) after the ground contacts.  Off by
+ * default (the path north_star scopes has ground contact only); every mode.  Synchronises the device. */
+int ilrl_set_self_collision(ilrl_env* env, int32_t on);
+
 /* Mode 2 parity harness.  hier_env_2's reset leaves WalkerBase.robot_specific_reset's joint noise (uniform(-0.1, 0.1))
  * in the six arm joints (its setJointsOrientation writes the abdomen and the legs only, REF hier_env_2.py:214-252).
  * noise17_dev [N,17] (ordered_joints order; only the arm entries matter): used by ilrl_reset and auto-resets instead

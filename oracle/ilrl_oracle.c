@@ -309,9 +309,16 @@ static void plane_space(const double* n, double* p, double* q) {
 #define MAX_SELF 8
 static int g_selfcol = 0;
 static long g_selfcol_contacts = 0, g_selfcol_substeps = 0, g_selfcol_hist[NG * NG];
+static double g_selfcol_min_sep = 1e30; /* smallest distance between the AXES of an active pair since the last reset of the
+                                           statistics: near 0 the contact normal is ill-conditioned (crossing capsules) */
 void ilrl_oracle_set_self_collision(int on) {
-  g_selfcol = on; g_selfcol_contacts = g_selfcol_substeps = 0;
+  g_selfcol = on; g_selfcol_contacts = g_selfcol_substeps = 0; g_selfcol_min_sep = 1e30;
   memset(g_selfcol_hist, 0, sizeof g_selfcol_hist);
+}
+double ilrl_oracle_self_collision_min_sep(int reset) {
+  const double v = g_selfcol_min_sep;
+  if (reset) g_selfcol_min_sep = 1e30;
+  return v;
 }
 void ilrl_oracle_self_collision_hist(long* out /* [NG * NG] contacts per geom pair */) { memcpy(out, g_selfcol_hist, sizeof g_selfcol_hist); }
 void ilrl_oracle_self_collision_stats(long* contacts, long* substeps) { *contacts = g_selfcol_contacts; *substeps = g_selfcol_substeps; }
@@ -520,8 +527,11 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
       matvec3(k.R[b], geom_p1 + 3 * g, w1[g]);
       for (int i = 0; i < 3; i++) { w0[g][i] += k.o[b][i]; w1[g][i] += k.o[b][i]; }
     }
-    int pa[MAX_SELF], pb[MAX_SELF], ns = 0;
-    double pd[MAX_SELF], pc1[MAX_SELF][3], pc2[MAX_SELF][3];
+    /* candidates in pair order; if more than MAX_SELF, drop the shallowest (largest distance, ties -> the later pair)
+     * until the cap holds; rows follow pair order (the rule of the ground contacts) */
+    enum { NPAIR = NG * (NG - 1) / 2 };
+    int ca[NPAIR], cb[NPAIR], nc = 0;
+    double cd[NPAIR], cc1[NPAIR][3], cc2[NPAIR][3];
     for (int ga = 0; ga < NG; ga++)
       for (int gb = ga + 1; gb < NG; gb++) {
         const int ba = geom_body[ga], bb = geom_body[gb];
@@ -531,18 +541,33 @@ static void orc_substep(double* phys, const double* tau, double dt, int flags) {
         const double dx[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
         const double dist = sqrt(dot3(dx, dx)) - geom_r[ga] - geom_r[gb];
         if (!(dist < ILRL_CONTACT_BREAK)) continue;
-        int slot = ns;
-        if (ns == MAX_SELF) { /* keep the deepest: replace the shallowest if this one is deeper */
-          slot = 0;
-          for (int q = 1; q < MAX_SELF; q++) if (pd[q] > pd[slot]) slot = q;
-          if (pd[slot] <= dist) continue;
-        } else ns++;
-        pa[slot] = ga; pb[slot] = gb; pd[slot] = dist;
-        memcpy(pc1[slot], c1, sizeof c1); memcpy(pc2[slot], c2, sizeof c2);
+        ca[nc] = ga; cb[nc] = gb; cd[nc] = dist;
+        memcpy(cc1[nc], c1, sizeof c1); memcpy(cc2[nc], c2, sizeof c2);
+        nc++;
       }
+    while (nc > MAX_SELF) {
+      int worst = 0;
+      for (int q = 1; q < nc; q++) if (cd[q] >= cd[worst]) worst = q;
+      for (int q = worst; q + 1 < nc; q++) {
+        ca[q] = ca[q + 1]; cb[q] = cb[q + 1]; cd[q] = cd[q + 1];
+        memcpy(cc1[q], cc1[q + 1], sizeof cc1[q]); memcpy(cc2[q], cc2[q + 1], sizeof cc2[q]);
+      }
+      nc--;
+    }
+    const int ns = nc;
+    int pa[MAX_SELF], pb[MAX_SELF];
+    double pd[MAX_SELF], pc1[MAX_SELF][3], pc2[MAX_SELF][3];
+    for (int q = 0; q < ns; q++) {
+      pa[q] = ca[q]; pb[q] = cb[q]; pd[q] = cd[q];
+      memcpy(pc1[q], cc1[q], sizeof pc1[q]); memcpy(pc2[q], cc2[q], sizeof pc2[q]);
+    }
     g_selfcol_substeps++;
     g_selfcol_contacts += ns;
-    for (int q = 0; q < ns; q++) g_selfcol_hist[pa[q] * NG + pb[q]]++;
+    for (int q = 0; q < ns; q++) {
+      g_selfcol_hist[pa[q] * NG + pb[q]]++;
+      const double sep = pd[q] + geom_r[pa[q]] + geom_r[pb[q]];
+      if (sep < g_selfcol_min_sep) g_selfcol_min_sep = sep;
+    }
     for (int q = 0; q < ns; q++) {
       double n[3] = {pc1[q][0] - pc2[q][0], pc1[q][1] - pc2[q][1], pc1[q][2] - pc2[q][2]};
       double len = sqrt(dot3(n, n));

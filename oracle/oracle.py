@@ -66,6 +66,10 @@ def lib():
         L.ilrl_oracle_endpoint_score.restype = C.c_double
         L.ilrl_oracle_env_refresh.argtypes = [C.c_void_p]
         L.ilrl_oracle_set_heightfield.argtypes = [_dp, C.c_int, C.c_int, C.c_double]
+        L.ilrl_oracle_set_self_collision.argtypes = [C.c_int]
+        L.ilrl_oracle_self_collision_stats.argtypes = [C.POINTER(C.c_long), C.POINTER(C.c_long)]
+        L.ilrl_oracle_self_collision_min_sep.argtypes = [C.c_int]
+        L.ilrl_oracle_self_collision_min_sep.restype = C.c_double
         _lib = L
     return _lib
 
@@ -128,6 +132,23 @@ def set_heightfield(data, rows=256, cols=256, body_z=0.25):
     _hf_keep = np.ascontiguousarray(data, dtype=np.float64).reshape(-1)
     assert _hf_keep.size == rows * cols
     lib().ilrl_oracle_set_heightfield(_d(_hf_keep), rows, cols, heightfield_zoff(_hf_keep, body_z))
+
+
+def set_self_collision(on):
+    """Bullet-style self-collision for every physics call of this process (off by default, as in the CUDA product)."""
+    lib().ilrl_oracle_set_self_collision(int(bool(on)))
+
+
+def self_collision_stats():
+    """(self-contacts, substeps) counted since set_self_collision"""
+    c, s = C.c_long(0), C.c_long(0)
+    lib().ilrl_oracle_self_collision_stats(C.byref(c), C.byref(s))
+    return c.value, s.value
+
+
+def self_collision_min_sep(reset=True):
+    """smallest distance between the axes of a colliding capsule pair seen since the last reset (1e30: none)"""
+    return lib().ilrl_oracle_self_collision_min_sep(int(reset))
 
 
 def energy(phys):

@@ -169,6 +169,32 @@ def main():
                 spheres.append(dict(body=bi, link=bodies[bi]["link"], c=p, r=g["r"]))
     assert len(spheres) == 29
 
+    # self-collision pairs (Bullet: URDF_USE_SELF_COLLISION | ..._EXCLUDE_ALL_PARENTS): every pair of geoms whose bodies
+    # are not ancestor-related, in geom order; each geom by the contact-sphere indices of its axis end points (p0, p1)
+    def is_anc(a, b):
+        while b >= 0:
+            if b == a:
+                return True
+            b = bodies[b]["parent"]
+        return False
+
+    def sph_of(g, p):
+        k = [i for i, sp in enumerate(spheres) if sp["body"] == g["body"] and np.allclose(sp["c"], p) and sp["r"] == g["r"]]
+        assert len(k) == 1, (g["name"], k)
+        return k[0]
+
+    self_pairs, self_reach = [], []
+    for ia, ga in enumerate(geoms):
+        for gb in geoms[ia + 1:]:
+            if is_anc(ga["body"], gb["body"]) or is_anc(gb["body"], ga["body"]):
+                continue
+            self_pairs.append((sph_of(ga, ga["p0"]), sph_of(ga, ga["p1"]), sph_of(gb, gb["p0"]), sph_of(gb, gb["p1"])))
+            # no contact is possible while the axis midpoints are farther apart than this (half lengths + radii + the
+            # contact breaking distance 0.02, 1 mm of slack): the broad phase of the pair tests
+            self_reach.append(0.5 * np.linalg.norm(ga["p1"] - ga["p0"]) + 0.5 * np.linalg.norm(gb["p1"] - gb["p0"]) +
+                              ga["r"] + gb["r"] + 0.02 + 0.001)
+    assert len(self_pairs) == 66
+
     jidx = {j["name"]: k for k, j in enumerate(joints)}
     motor_joint = [jidx[n] for n in MOTOR_NAMES]
     gear_motor = [p * POWER for p in MOTOR_POWER]
@@ -200,6 +226,8 @@ def main():
         # every collision geom as a capsule (a sphere is a zero-length one), body frame: self-collision pairs
         ng=len(geoms), geom_name=[g["name"] for g in geoms], geom_body=[g["body"] for g in geoms],
         geom_p0=arr([g["p0"] for g in geoms]), geom_p1=arr([g["p1"] for g in geoms]), geom_r=[g["r"] for g in geoms],
+        nself=len(self_pairs), self_a0=[p[0] for p in self_pairs], self_a1=[p[1] for p in self_pairs],
+        self_b0=[p[2] for p in self_pairs], self_b1=[p[3] for p in self_pairs], self_reach=self_reach,
         motor_names=MOTOR_NAMES, motor_joint=motor_joint, motor_gear=gear_motor,
         map_joint=map_joint, map_col=map_col, map_w=map_w, map_wv=map_wv, csv_cols=CSV_COLS,
     )
@@ -218,11 +246,11 @@ def main():
          " * low_level_env.py:86-101). link == joint index that carries the body, -1 = floating base (torso). */",
          "#ifndef ILRL_MODEL_DATA_H", "#define ILRL_MODEL_DATA_H",
          "#define ILRL_NB 15", "#define ILRL_NJ 17", "#define ILRL_NC 11", "#define ILRL_NS 29", "#define ILRL_NMAP 14",
-         "#define ILRL_NG %d" % len(geoms), "#define ILRL_TOTAL_MASS %.17g" % total_mass]
+         "#define ILRL_NG %d" % len(geoms), "#define ILRL_NSELF %d" % len(self_pairs), "#define ILRL_TOTAL_MASS %.17g" % total_mass]
     for key in ["body_parent", "body_link", "body_pos", "body_quat", "body_mass", "body_inertia", "joint_body",
                 "joint_parent", "joint_anchor", "joint_axis", "joint_lo", "joint_hi", "comp_body", "comp_link",
                 "comp_mass", "comp_com", "comp_inertia", "sphere_body", "sphere_link", "sphere_c", "sphere_r",
-                "geom_body", "geom_p0", "geom_p1", "geom_r", "motor_joint", "motor_gear", "map_joint", "map_col", "map_w", "map_wv"]:
+                "geom_body", "geom_p0", "geom_p1", "geom_r", "self_a0", "self_a1", "self_b0", "self_b1", "self_reach", "motor_joint", "motor_gear", "map_joint", "map_col", "map_w", "map_wv"]:
         L.append("#define ILRL_%s %s" % (key.upper(), cl(model[key])))
     L.append("#endif")
     os.makedirs(os.path.dirname(OUT_H), exist_ok=True)

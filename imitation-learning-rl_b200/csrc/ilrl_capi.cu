@@ -131,6 +131,12 @@ __device__ __forceinline__ void quad_smem_init(SM& sm) {
   }
   if constexpr (SM::SELF) {   // wide row 0 of every env must hold finite numbers (lanes past their count re-evaluate it)
     for (int k = 0; k < chain::WRW / 4; k++) sm.S.wr[threadIdx.x >> 2][(threadIdx.x & 3) * (chain::WRW / 4) + k] = 0.f;
+    for (int p = threadIdx.x; p < chain::NSELF; p += QT) {   // the pair table, packed
+      const float r = chain::kSelfReach[p];
+      sm.S.pairs[p] = make_uint2((unsigned)chain::kSelfA0[p] | ((unsigned)chain::kSelfA1[p] << 8) |
+                                     ((unsigned)chain::kSelfB0[p] << 16) | ((unsigned)chain::kSelfB1[p] << 24),
+                                 __float_as_uint(r * r));
+    }
   }
 }
 // torques of this lane's chain into the link records: apply_action (REF humanoid.py:54-60): clip, gear x power,
@@ -676,6 +682,9 @@ __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const flo
   } else {
     chain::dummy_state(sm, e, tid, b);
   }
+  // row 0 of every env must hold finite numbers (as in step_tile): lanes past their own row count evaluate it with a zero
+  // step, and with self-collision an env may have rows of the wide kind only
+  reinterpret_cast<float4*>(&sm.rows[e][0])[role] = make_float4(0.f, 0.f, 0.f, 0.f);
   __syncwarp();
   float* gscr_tile = gscr_all + (size_t)blockIdx.x * QE * chain::GROWS * chain::RW;
   for (int sub = 0; sub < nsub; sub++)

@@ -239,6 +239,7 @@ struct NoSelf {};
 struct alignas(16) SelfSm {
   float gp[QE][SELF_GP];      // sphere centres relative to the torso (world axes), published by the FK pass
   uint32_t mask[QE][4];       // candidate pairs (66 bits), set by the pair tests of the warp's pool
+  uint2 pairs[NSELF + 2];     // per pair: sphere indices a0 | a1 << 8 | b0 << 16 | b1 << 24, squared broad-phase reach
   float wr[QE][SELF_WR + 4];  // the wide rows (env stride = 4 mod 32 words): 36 KB per CTA, 2 CTAs per SM
 };
 template <class LY>
@@ -675,13 +676,15 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
         ex = ob.x; ey = ob.y;
         // (SELFC: the sphere centres of every body are published for the pair tests, so the per-body early-out of the
         // ground test - an optimisation that never changes which spheres pass - is not taken)
-        if (FULL && (SELFC || (TERR ? (b.p[2] + ob.z - terr->hmax) * terr->nzmin - B.reach : b.p[2] + ob.z - B.reach) < (float)ILRL_CONTACT_BREAK)) {
+        const bool near_ground = (TERR ? (b.p[2] + ob.z - terr->hmax) * terr->nzmin - B.reach : b.p[2] + ob.z - B.reach) < (float)ILRL_CONTACT_BREAK;
+        if (FULL && (SELFC || near_ground)) {
 #pragma unroll 1
           for (int t = 0; t < B.nsph; t++) {
             const int g = B.sidx[t];
             V3 cs_ = ob + mv(Rc, rd3(B.sph[t]));
             const float rad = B.sph[t][3];
             if (SELFC && gpe) { gpe[3 * g] = cs_.x; gpe[3 * g + 1] = cs_.y; gpe[3 * g + 2] = cs_.z; }
+            if (SELFC && !near_ground) continue;
             float d, w2;
             if constexpr (TERR) {
               V3 n;
@@ -1249,11 +1252,31 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
     const unsigned stepmask = __ballot_sync(FULLMASK, steps);
     if (role < 3) sm.S.mask[e][role] = 0u;
     __syncwarp();   // every lane's sphere centres (FK pass) and the cleared masks are visible to the warp
+    // broad phase (axis midpoints farther apart than the pair's reach: no contact possible) on three items per lane and
+    // iteration - independent shared-memory loads in flight together -, the segment test only for what is left
 #pragma unroll 1
-    for (int it = lane; it < 8 * NSELF; it += 32) {
-      const int q = it / NSELF, p = it - q * NSELF;
-      if (((stepmask >> (4 * q)) & 1u) && self_pair_active(&sm.S.gp[e0 + q][0], p))
-        atomicOr(&sm.S.mask[e0 + q][p >> 5], 1u << (p & 31));
+    for (int it0 = lane; it0 < 8 * NSELF; it0 += 96) {
+      bool near[3];
+      int qq[3], pp[3];
+#pragma unroll
+      for (int u = 0; u < 3; u++) {
+        const int it = it0 + 32 * u;
+        const int q = min(it, 8 * NSELF - 1) / NSELF, p = min(it, 8 * NSELF - 1) - q * NSELF;
+        qq[u] = q; pp[u] = p;
+        const uint2 pr = sm.S.pairs[p];
+        const float* gp = &sm.S.gp[e0 + q][0];
+        const V3 pa0 = rd3(gp + 3 * (pr.x & 255u)), pa1 = rd3(gp + 3 * ((pr.x >> 8) & 255u));
+        const V3 pb0 = rd3(gp + 3 * ((pr.x >> 16) & 255u)), pb1 = rd3(gp + 3 * (pr.x >> 24));
+        const V3 dm = (pa0 + pa1) - (pb0 + pb1);   // twice the midpoint difference
+        near[u] = it < 8 * NSELF && ((stepmask >> (4 * q)) & 1u) && dot(dm, dm) <= 4.f * __uint_as_float(pr.y);
+      }
+#pragma unroll
+      for (int u = 0; u < 3; u++)
+        if (near[u]) {
+          V3 c1, c2;
+          if (self_pair(&sm.S.gp[e0 + qq[u]][0], pp[u], c1, c2) < (float)ILRL_CONTACT_BREAK)
+            atomicOr(&sm.S.mask[e0 + qq[u]][pp[u] >> 5], 1u << (pp[u] & 31));
+        }
     }
     __syncwarp();
     if (steps) { sm0 = sm.S.mask[e][0]; sm1 = sm.S.mask[e][1]; sm2 = sm.S.mask[e][2]; }

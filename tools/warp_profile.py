@@ -29,7 +29,8 @@ if __name__ == "__main__":
     import ilrl_b200  # noqa: F401
     from ilrl_b200.batched_env import BatchedHumanoidEnv
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
-    env = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], auto_reset=True, seed=1234)
+    env = BatchedHumanoidEnv(n, "low", clips=["motion09_03"], auto_reset=True, seed=1234,
+                             self_collision=bool(os.environ.get("ILRL_SELFCOL")))   # ILRL_SELFCOL=1: the SELFC kernel
     env.reset()
     g = torch.Generator(device="cuda")
     g.manual_seed(0)

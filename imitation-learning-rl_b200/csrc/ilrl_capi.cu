@@ -133,9 +133,10 @@ __device__ __forceinline__ void quad_smem_init(SM& sm) {
     for (int k = 0; k < chain::WRW / 4; k++) sm.S.wr[threadIdx.x >> 2][(threadIdx.x & 3) * (chain::WRW / 4) + k] = 0.f;
     for (int p = threadIdx.x; p < chain::NSELF; p += QT) {   // the pair table, packed
       const float r = chain::kSelfReach[p];
-      sm.S.pairs[p] = make_uint2((unsigned)chain::kSelfA0[p] | ((unsigned)chain::kSelfA1[p] << 8) |
+      sm.S.pairs[p] = make_uint4((unsigned)chain::kSelfA0[p] | ((unsigned)chain::kSelfA1[p] << 8) |
                                      ((unsigned)chain::kSelfB0[p] << 16) | ((unsigned)chain::kSelfB1[p] << 24),
-                                 __float_as_uint(r * r));
+                                 __float_as_uint(4.f * r * r),
+                                 __float_as_uint(kSphereR[chain::kSelfA0[p]] + kSphereR[chain::kSelfB0[p]] + (float)ILRL_CONTACT_BREAK), 0u);
     }
   }
 }

@@ -239,7 +239,8 @@ struct NoSelf {};
 struct alignas(16) SelfSm {
   float gp[QE][SELF_GP];      // sphere centres relative to the torso (world axes), published by the FK pass
   uint32_t mask[QE][4];       // candidate pairs (66 bits), set by the pair tests of the warp's pool
-  uint2 pairs[NSELF + 2];     // per pair: sphere indices a0 | a1 << 8 | b0 << 16 | b1 << 24, squared broad-phase reach
+  uint4 pairs[NSELF + 2];     // per pair: sphere indices a0 | a1 << 8 | b0 << 16 | b1 << 24, 4 x squared broad-phase reach,
+                              // sum of the two radii + the breaking distance, -
   float wr[QE][SELF_WR + 4];  // the wide rows (env stride = 4 mod 32 words): 36 KB per CTA, 2 CTAs per SM
 };
 template <class LY>
@@ -1252,30 +1253,34 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
     const unsigned stepmask = __ballot_sync(FULLMASK, steps);
     if (role < 3) sm.S.mask[e][role] = 0u;
     __syncwarp();   // every lane's sphere centres (FK pass) and the cleared masks are visible to the warp
-    // broad phase (axis midpoints farther apart than the pair's reach: no contact possible) on three items per lane and
-    // iteration - independent shared-memory loads in flight together -, the segment test only for what is left
+    // two items per lane and iteration: every load (pair record, 4 axis end points) in flight together, broad phase (axis
+    // midpoints farther apart than the pair's reach: no contact possible), the segment test on the same registers
 #pragma unroll 1
-    for (int it0 = lane; it0 < 8 * NSELF; it0 += 96) {
-      bool near[3];
-      int qq[3], pp[3];
+    for (int it0 = lane; it0 < 8 * NSELF; it0 += 64) {
+      V3 A0[2], A1[2], B0[2], B1[2];
+      float lim[2];
+      bool near[2];
+      int qq[2], pp[2];
 #pragma unroll
-      for (int u = 0; u < 3; u++) {
-        const int it = it0 + 32 * u;
-        const int q = min(it, 8 * NSELF - 1) / NSELF, p = min(it, 8 * NSELF - 1) - q * NSELF;
+      for (int u = 0; u < 2; u++) {
+        const int it = it0 + 32 * u, itc = min(it, 8 * NSELF - 1);
+        const int q = itc / NSELF, p = itc - q * NSELF;
         qq[u] = q; pp[u] = p;
-        const uint2 pr = sm.S.pairs[p];
+        const uint4 pr = sm.S.pairs[p];
         const float* gp = &sm.S.gp[e0 + q][0];
-        const V3 pa0 = rd3(gp + 3 * (pr.x & 255u)), pa1 = rd3(gp + 3 * ((pr.x >> 8) & 255u));
-        const V3 pb0 = rd3(gp + 3 * ((pr.x >> 16) & 255u)), pb1 = rd3(gp + 3 * (pr.x >> 24));
-        const V3 dm = (pa0 + pa1) - (pb0 + pb1);   // twice the midpoint difference
-        near[u] = it < 8 * NSELF && ((stepmask >> (4 * q)) & 1u) && dot(dm, dm) <= 4.f * __uint_as_float(pr.y);
+        A0[u] = rd3(gp + 3 * (pr.x & 255u)); A1[u] = rd3(gp + 3 * ((pr.x >> 8) & 255u));
+        B0[u] = rd3(gp + 3 * ((pr.x >> 16) & 255u)); B1[u] = rd3(gp + 3 * (pr.x >> 24));
+        const V3 dm = (A0[u] + A1[u]) - (B0[u] + B1[u]);   // twice the midpoint difference
+        lim[u] = __uint_as_float(pr.z);
+        near[u] = it < 8 * NSELF && ((stepmask >> (4 * q)) & 1u) && dot(dm, dm) <= __uint_as_float(pr.y);
       }
 #pragma unroll
-      for (int u = 0; u < 3; u++)
+      for (int u = 0; u < 2; u++)
         if (near[u]) {
           V3 c1, c2;
-          if (self_pair(&sm.S.gp[e0 + qq[u]][0], pp[u], c1, c2) < (float)ILRL_CONTACT_BREAK)
-            atomicOr(&sm.S.mask[e0 + qq[u]][pp[u] >> 5], 1u << (pp[u] & 31));
+          seg_seg_f(A0[u], A1[u], B0[u], B1[u], c1, c2);
+          const V3 d = c1 - c2;
+          if (sqrtf(dot(d, d)) < lim[u]) atomicOr(&sm.S.mask[e0 + qq[u]][pp[u] >> 5], 1u << (pp[u] & 31));
         }
     }
     __syncwarp();

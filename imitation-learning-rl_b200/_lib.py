@@ -9,7 +9,7 @@ SYMBOLS = ["ilrl_create", "ilrl_destroy", "ilrl_last_error", "ilrl_load_clip", "
            "ilrl_step", "ilrl_step_host", "ilrl_step_host_async", "ilrl_wait", "ilrl_wait_step_host_async", "ilrl_serve_begin", "ilrl_serve_post", "ilrl_serve_wait", "ilrl_serve_step", "ilrl_serve_end", "ilrl_step_pull", "ilrl_pull", "ilrl_set_config", "ilrl_high_step", "ilrl_high_readout", "ilrl_get_state", "ilrl_set_state",
            "ilrl_set_heightfield", "ilrl_set_self_collision", "ilrl_set_forced_reset_noise", "ilrl_get_joint_target", "ilrl_set_joint_target",
            "ilrl_set_forced_target_deg", "ilrl_step_no_physics", "ilrl_physics_only", "ilrl_endpoint_score",
-           "ilrl_stats", "ilrl_gae", "ilrl_gae_decisions", "ilrl_policy_blob_bytes", "ilrl_policy_pack", "ilrl_policy_step",
+           "ilrl_stats", "ilrl_gae", "ilrl_episode_columns", "ilrl_gae_decisions", "ilrl_policy_blob_bytes", "ilrl_policy_pack", "ilrl_policy_step",
            "ilrl_launch_count", "ilrl_kernel_timing"]
 
 
@@ -71,6 +71,7 @@ def lib():
     L.ilrl_endpoint_score.argtypes = [_vp, _vp, _vp]
     L.ilrl_stats.argtypes = [_vp, _vp, _vp]
     L.ilrl_gae.argtypes = [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, C.c_int32, C.c_int32, _vp]
+    L.ilrl_episode_columns.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int64, _vp]
     L.ilrl_gae_decisions.argtypes = [_vp, _vp, _vp, C.c_float, C.c_float, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]
     L.ilrl_policy_blob_bytes.restype = C.c_int64
     L.ilrl_policy_blob_bytes.argtypes = []

@@ -731,6 +731,24 @@ __global__ void gae_kernel(const float* __restrict__ rew, const float* __restric
     vnext = v;
   }
 }
+// RLlib's per-step bookkeeping columns of a [T, N] fragment from its done flags: `t` (step index inside the episode) and
+// `eps_id` (unique per episode: global env id << 32 | episode counter).  One thread per env walks its column; the
+// carries (t of the env's next step, its episode counter) continue from fragment to fragment.
+__global__ void episode_columns_kernel(const uint8_t* __restrict__ done, int32_t* t_carry, int32_t* eps_carry,
+                                       int32_t* __restrict__ t_out, long long* __restrict__ eps_out, int T, int n,
+                                       long long id_base) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int t = t_carry[i], ep = eps_carry[i];
+  const long long hi = (id_base + i) << 32;
+  for (int k = 0; k < T; k++) {
+    const size_t j = (size_t)k * n + i;
+    t_out[j] = t;
+    eps_out[j] = hi | (long long)(unsigned)ep;
+    if (done[j]) { t = 0; ep++; } else t++;
+  }
+  t_carry[i] = t; eps_carry[i] = ep;
+}
 // GAE for the HIGH-level agent of the hierarchical env, whose decisions are irregular in time: per env, a decision is
 // taken at every tick whose flag has bit2 (waiting) and its outcome — reward, end of episode, the next decision's value
 // — is what ilrl_high_readout reports at the next tick with bit1 (REF hier_env.py:524-536, 613-631).  Rows 0..T of
@@ -1713,6 +1731,13 @@ int ilrl_gae(const float* reward, const float* value, const uint8_t* done, float
              float* value_target, int32_t T, int32_t n, void* stream) {
   if (!reward || !value || !done || !advantage || !value_target || T <= 0 || n <= 0) return ILRL_ERR_ARG;
   gae_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(reward, value, done, gamma, lam, advantage, value_target, T, n);
+  return cudaGetLastError() == cudaSuccess ? ILRL_OK : ILRL_ERR_CUDA;
+}
+int ilrl_episode_columns(const uint8_t* done, int32_t* t_carry, int32_t* eps_carry, int32_t* t_out, int64_t* eps_id_out,
+                          int32_t T, int32_t n, int64_t env_id_base, void* stream) {
+  if (!done || !t_carry || !eps_carry || !t_out || !eps_id_out || T <= 0 || n <= 0) return ILRL_ERR_ARG;
+  episode_columns_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(done, t_carry, eps_carry, t_out,
+                                                                          (long long*)eps_id_out, T, n, (long long)env_id_base);
   return cudaGetLastError() == cudaSuccess ? ILRL_OK : ILRL_ERR_CUDA;
 }
 int ilrl_gae_decisions(const float* reward, const uint8_t* flags, const float* value, float gamma, float lam,

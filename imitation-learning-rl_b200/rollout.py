@@ -141,6 +141,12 @@ class RolloutCollector:
         }
         self._noise = torch.zeros(T, n, ACT_LOW, **f)
         self._clipped = torch.zeros(n, ACT_LOW, **f)
+        # RLlib's `t` / `eps_id` columns (ilrl_episode_columns): carries continue from fragment to fragment
+        self._t_carry = torch.zeros(n, device=dev, dtype=torch.int32)
+        self._eps_carry = torch.zeros(n, device=dev, dtype=torch.int32)
+        self._t_col = torch.zeros(T, n, device=dev, dtype=torch.int32)
+        self._eps_col = torch.zeros(T, n, device=dev, dtype=torch.int64)
+        self._id_base = 0   # global id of env 0 of this shard (set it when a batch is sharded over ranks)
         self._graph = None
         self._warm = False
         self._use_graph = use_graph
@@ -209,6 +215,13 @@ class RolloutCollector:
         out = {k: b[k] for k in ("obs", "new_obs", "actions", "rewards", "dones", "action_logp")}
         out["vf_preds"] = b["vf_preds"][:self.T]
         out["advantages"], out["value_targets"] = adv, vt
+        st = C.c_void_p(torch.cuda.current_stream(self.env.device).cuda_stream)
+        with torch.cuda.device(self.env.device):
+            rc = _lib.lib().ilrl_episode_columns(_ptr(b["dones"]), _ptr(self._t_carry), _ptr(self._eps_carry), _ptr(self._t_col),
+                                                 _ptr(self._eps_col), self.T, self.env.num_envs, int(self._id_base), st)
+        if rc != 0:
+            raise _lib.IlrlError("ilrl_episode_columns failed (%d)" % rc)
+        out["t"], out["eps_id"] = self._t_col, self._eps_col
         return out
 
 

@@ -217,6 +217,13 @@ int ilrl_stats(ilrl_env* env, float* stats16_dev, void* stream);
 int ilrl_gae(const float* reward_dev, const float* value_dev, const uint8_t* done_dev, float gamma, float lambda_,
              float* advantage_dev, float* value_target_dev, int32_t T, int32_t n, void* stream);
 
+/* The two bookkeeping columns RLlib keeps next to every step of a sample batch, for a [T, N] fragment laid out step-major:
+ * t_dev [T,N] int32 = step index inside the episode, eps_id_dev [T,N] int64 = (env_id_base + env) << 32 | episode counter.
+ * t_carry_dev / eps_carry_dev [N] int32 (in / out): t of the env's next step and its episode counter, continued from
+ * fragment to fragment (zero them once).  No handle; asynchronous on `stream`. */
+int ilrl_episode_columns(const uint8_t* done_dev, int32_t* t_carry_dev, int32_t* eps_carry_dev, int32_t* t_dev,
+                         int64_t* eps_id_dev, int32_t T, int32_t n, int64_t env_id_base, void* stream);
+
 /* GAE for the high-level agent of the hierarchical env over a fragment of T ticks (rows 0..T of the ilrl_high_readout
  * outputs, taken before every tick and once after the last; value_dev [T+1,N] = value estimates of those high-level
  * observations).  A decision is taken where flags has bit2; its reward / termination / successor value are the ones

@@ -45,10 +45,17 @@ def test_collector_sample_batch_invariants(use_graph, fused):
     col = RolloutCollector(env, GaussianMLPPolicy(), horizon=T, gamma=0.99, lam=0.9, seed=1, use_graph=use_graph, fused=fused)
     env.stats()
     total_done = 0
+    t_chk, ep_chk = np.zeros(n, np.int64), np.zeros(n, np.int64)     # NumPy restatement of RLlib's t / eps_id columns
     for it in range(3):
         b = col.collect()
         torch.cuda.synchronize()
         assert b["obs"].shape == (T, n, 70) and b["actions"].shape == (T, n, 17) and b["dones"].dtype == torch.uint8
+        d, tc, ec = b["dones"].cpu().numpy(), b["t"].cpu().numpy(), b["eps_id"].cpu().numpy()
+        for k in range(T):
+            np.testing.assert_array_equal(tc[k], t_chk)
+            np.testing.assert_array_equal(ec[k], (np.arange(n, dtype=np.int64) << 32) | ep_chk)
+            t_chk = np.where(d[k] != 0, 0, t_chk + 1)
+            ep_chk = ep_chk + (d[k] != 0)
         for k, t in b.items():
             assert bool(torch.isfinite(t.float()).all()), k
         # the state a step returns is the state the next step acts on (auto-reset included)

@@ -82,9 +82,12 @@ class _SingleEnv(object):
 
     metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 60}
 
-    def _make(self, mode, clips, selected, device, seed):
+    def _make(self, mode, clips, selected, device, seed, self_collision=False):
+        # self_collision: the reference's robot class has `self_collision = True` (REF humanoid.py:13); the B200 path models
+        # it as an option of the handle (ilrl_set_self_collision), off unless asked for
         self._env = BatchedHumanoidEnv(1, mode, clips=clips, clip_of_env=np.array([selected], np.int32), device=device,
-                                       seed=0 if seed is None else int(seed), auto_reset=False)
+                                       seed=0 if seed is None else int(seed), auto_reset=False,
+                                       self_collision=self_collision)
         self.rng = np.random.default_rng(seed)
         self.cur_timestep = 0
         self._max_timestep, self._skip_frame = 3000, 2
@@ -355,13 +358,14 @@ class LowLevelHumanoidEnv(_SingleEnv, _GymEnv):
     `env.flat_env.stadium_scene.replaceHeightfieldData`); `customRobot` is accepted and ignored (the kernels model
     `CustomHumanoidRobot` on `humanoid_symmetric_2.xml`, the robot every reference config passes)."""
 
-    def __init__(self, reference_name="motion08_03", useCustomEnv=False, customRobot=None, device=0, seed=None):
+    def __init__(self, reference_name="motion08_03", useCustomEnv=False, customRobot=None, device=0, seed=None,
+                 self_collision=False):
         self.useCustomEnv = bool(useCustomEnv)
         self.reference_name = reference_name
         self.observation_space = Box(low=-np.inf, high=np.inf, shape=[8 + 17 * 2 + 14 * 2])
         self.action_space = Box(low=-1, high=1, shape=[17])
         self.max_frame = load_clip(reference_name)["max_frame"]
-        self._make("low", [reference_name], 0, device, seed)
+        self._make("low", [reference_name], 0, device, seed, self_collision)
         if self.useCustomEnv:
             self.flat_env = _FlatEnvShim(self)
 
@@ -426,7 +430,7 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
     """REF hier_env.py:39.  `selected_motion` indexes `motion_list` and may be reassigned between episodes, as the
     reference's evaluation scripts do (REF env_check_hier.py:93)."""
 
-    def __init__(self, customRobot=None, device=0, seed=None):
+    def __init__(self, customRobot=None, device=0, seed=None, self_collision=False):
         self.motion_list = ["motion08_03", "motion09_03"]
         self.high_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[8 + 17 * 2 + 2])
         self.high_level_act_space = Box(low=-1, high=1, shape=[2])
@@ -439,7 +443,7 @@ class HierarchicalHumanoidEnv(_SingleEnv, _MultiAgentEnv):
         self._selected_motion = 1
         self.selected_motion_frame = 0
         self.low_level_agent_id = "low_level_agent"
-        self._make("hier", self.motion_list, self._selected_motion, device, seed)
+        self._make("hier", self.motion_list, self._selected_motion, device, seed, self_collision)
 
     _PO, _PH, _HACT = BatchedHumanoidEnv.PULL_OBS, BatchedHumanoidEnv.PULL_HIGH_OBS, 2   # packed-row columns / widths of the mode
 
@@ -557,7 +561,7 @@ class HierarchicalHumanoidEnv2(HierarchicalHumanoidEnv):
 
     _PO, _PH, _HACT = BatchedHumanoidEnv.PULL_OBS2, BatchedHumanoidEnv.PULL_HIGH_OBS2, 36
 
-    def __init__(self, device=0, seed=None):
+    def __init__(self, device=0, seed=None, self_collision=False):
         self.motion_list = ["motion08_03", "motion09_03"]
         self.high_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[2 + 42 + 8 * 2])
         self.high_level_act_space = Box(low=-1, high=1, shape=[2 + 17 * 2])
@@ -571,7 +575,7 @@ class HierarchicalHumanoidEnv2(HierarchicalHumanoidEnv):
         self.selected_motion_frame = 0
         self.low_level_agent_id = "low_level_agent"
         self.jointTarget = [0] * 16                                          # REF hier_env_2.py:172
-        self._make("hier2", self.motion_list, self._selected_motion, device, seed)
+        self._make("hier2", self.motion_list, self._selected_motion, device, seed, self_collision)
         self._skip_frame = 5
         legs = [k for k in JOINT_MAP if "knee" in k or "hip" in k]          # REF hier_env_2.py:90-126
         self.joint_map = {k: JOINT_MAP[k] for k in legs}

@@ -67,8 +67,9 @@ class LowLevelVectorEnv(_RobotPosCache, _VectorEnv):
     """N `LowLevelHumanoidEnv`s as one RLlib VectorEnv.  Done envs are re-initialised by ONE masked reset launch
     right after the step; `reset_at(i)` (which RLlib calls for every done env) returns that env's new first obs."""
 
-    def __init__(self, num_envs, reference_name="motion09_03", device=0, seed=0):
-        self.env = BatchedHumanoidEnv(num_envs, "low", clips=[reference_name], device=device, seed=seed, auto_reset=False)
+    def __init__(self, num_envs, reference_name="motion09_03", device=0, seed=0, self_collision=False):
+        self.env = BatchedHumanoidEnv(num_envs, "low", clips=[reference_name], device=device, seed=seed, auto_reset=False,
+                                      self_collision=self_collision)
         self.num_envs = int(num_envs)
         self.observation_space = Box(low=-np.inf, high=np.inf, shape=[70])
         self.action_space = Box(low=-1, high=1, shape=[17])
@@ -117,11 +118,11 @@ class HierBaseEnv(_RobotPosCache, _BaseEnv):
     the joint targets, 60-d / 72-d observations)."""
 
     def __init__(self, num_envs, device=0, seed=0, motion_list=("motion08_03", "motion09_03"), selected_motion=1,
-                 variant="hier"):
+                 variant="hier", self_collision=False):
         self.num_envs = int(num_envs)
         self.env = BatchedHumanoidEnv(num_envs, variant, clips=list(motion_list),
                                       clip_of_env=np.full(num_envs, selected_motion, np.int32), device=device,
-                                      seed=seed, auto_reset=False)
+                                      seed=seed, auto_reset=False, self_collision=self_collision)
         self.high_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[self.env.hobs_w])
         self.high_level_act_space = Box(low=-1, high=1, shape=[self.env.hact_w])
         self.low_level_obs_space = Box(low=-np.inf, high=np.inf, shape=[self.env.obs_w])

@@ -958,3 +958,26 @@ def test_persistent_serving_matches_step_host():
         env.serve_step(a)
     env.reset()                                                # the handle is usable again
     env.close()
+
+
+def test_self_collision_option_of_the_views():
+    """`self_collision=True` on the reference-shaped classes and adapters: same API, the SELFC kernel underneath."""
+    env = LowLevelHumanoidEnv(reference_name="motion09_03", seed=2, self_collision=True)
+    obs = env.reset()
+    for k in range(15):
+        obs, rew, done, _ = env.step(np.random.default_rng(k).uniform(-1, 1, 17))
+        assert obs.shape == (70,) and np.isfinite(obs).all() and np.isfinite(rew)
+        if done:
+            break
+    env.close()
+    h = HierarchicalHumanoidEnv(seed=2, self_collision=True)
+    o = h.reset()
+    o, r, d, _ = h.step({"high_level_agent": [1.0, 0.0]})
+    o, r, d, _ = h.step({"low_level_agent": np.zeros(17)})
+    assert np.isfinite(list(o.values())[0]).all()
+    h.close()
+    v = LowLevelVectorEnv(8, seed=1, self_collision=True)
+    v.vector_reset()
+    o, r, d, _ = v.vector_step([np.zeros(17)] * 8)
+    assert len(o) == 8 and all(np.isfinite(x).all() for x in o)
+    v.close()

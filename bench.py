@@ -547,8 +547,9 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": prof_src, "peak_source": which, "kernel_ms": kern_ms,
                          "kernel_block_ms_per_step": res["kernel_block_ms_per_step"],
-                         "kernel_timing": "%globaltimer stamps written by the step kernel itself (first CTA start, last CTA "
-                                          "end) in a block of the same K back-to-back steps",
+                         "kernel_timing": "%globaltimer stamps written by the step kernel itself (first CTA past its grid-"
+                                          "dependency wait, last CTA end) in a block of the same K back-to-back EAGER launches "
+                                          "(kernel_block_ms_per_step); `ms_per_step` is the graph-replayed block",
                          "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n,
                          "note": "latency/issue-bound path (SURVEY 8d): HBM fraction is reported as the tier asks; "
                                  "see profiles/ for SM issue utilisation",

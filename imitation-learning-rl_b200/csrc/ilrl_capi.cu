@@ -419,8 +419,15 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
   extern __shared__ __align__(16) unsigned char smraw[];
   SM& sm = *reinterpret_cast<SM*>(smraw);
   const int tid = threadIdx.x;
-  if (a.ktime && tid == 0) atomicMin(a.ktime, globaltimer_ns());
+  // Programmatic dependent launch: consecutive step kernels of a stream form a chain, and everything up to here depends
+  // on nothing the previous step wrote.  The trigger lets the NEXT launch's CTAs become resident as this one's finish (a
+  // step ends with its slowest warp: most SMs idle for the last ~20 % of it) and run their prologue - model tables into
+  // shared memory - early; the wait below holds them until this grid has completed and flushed.  (No-ops when the launch
+  // does not carry the attribute.)
+  asm volatile("griddepcontrol.launch_dependents;");
   quad_smem_init(sm);
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (a.ktime && tid == 0) atomicMin(a.ktime, globaltimer_ns());
   // Persistent CTAs: the grid is at most what is resident at once (SMs x CTAs per SM) and tiles of QE envs are handed
   // out through an atomic counter, so a large batch has no partially filled last wave and no per-tile table copy, and
   // CTAs that drew cheap tiles simply take more of them.  The last CTA to leave resets the counters (graph-safe).
@@ -930,6 +937,19 @@ struct DeviceGuard {
   if ((env)->serving) return fail(env, ILRL_ERR_STATE, "the handle is serving (ilrl_serve_begin): call ilrl_serve_end first"); \
   ON_DEVICE_RAW(env)
 
+// step-kernel launch, optionally with the programmatic-stream-serialization attribute (see the kernel's prologue)
+static bool g_pdl = [] { const char* e = getenv("ILRL_PDL"); return !(e && e[0] == '0'); }();
+template <class K>
+static void launch_step(K kernel, int grid, size_t smem, cudaStream_t st, const StepArgs& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(QT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, a);
+}
+
 extern "C" {
 
 int ilrl_serve_end(ilrl_env* env);
@@ -1193,23 +1213,23 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   const int qblk = min(a.ntiles, layout == 2 ? env->grid_dense4 : layout == 1 ? env->grid_large : env->grid_small);
   const int md = env->cfg.mode;
   if (special) {
-    if (env->terr.h && env->self_on) step_kernel<0, SmemSelf, true, true><<<qblk, QT, sizeof(SmemSelf), st>>>(a);
-    else if (env->self_on && md == 0) step_kernel<0, SmemSelf, false, true><<<qblk, QT, sizeof(SmemSelf), st>>>(a);
-    else if (env->self_on && md == 1) step_kernel<1, SmemSelf, false, true><<<qblk, QT, sizeof(SmemSelf), st>>>(a);
-    else if (env->self_on) step_kernel<2, SmemSelf, false, true><<<qblk, QT, sizeof(SmemSelf), st>>>(a);
-    else step_kernel<0, SmemLarge, true><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
+    if (env->terr.h && env->self_on) launch_step(step_kernel<0, SmemSelf, true, true>, qblk, sizeof(SmemSelf), st, a);
+    else if (env->self_on && md == 0) launch_step(step_kernel<0, SmemSelf, false, true>, qblk, sizeof(SmemSelf), st, a);
+    else if (env->self_on && md == 1) launch_step(step_kernel<1, SmemSelf, false, true>, qblk, sizeof(SmemSelf), st, a);
+    else if (env->self_on) launch_step(step_kernel<2, SmemSelf, false, true>, qblk, sizeof(SmemSelf), st, a);
+    else launch_step(step_kernel<0, SmemLarge, true>, qblk, sizeof(SmemLarge), st, a);
   } else if (env->layout == 2) {
-    if (md == 0) step_kernel<0, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
-    else if (md == 1) step_kernel<1, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
-    else step_kernel<2, SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a);
+    if (md == 0) launch_step(step_kernel<0, SmemDense4>, qblk, sizeof(SmemDense4), st, a);
+    else if (md == 1) launch_step(step_kernel<1, SmemDense4>, qblk, sizeof(SmemDense4), st, a);
+    else launch_step(step_kernel<2, SmemDense4>, qblk, sizeof(SmemDense4), st, a);
   } else if (env->layout == 1) {
-    if (md == 0) step_kernel<0, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
-    else if (md == 1) step_kernel<1, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
-    else step_kernel<2, SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a);
+    if (md == 0) launch_step(step_kernel<0, SmemLarge>, qblk, sizeof(SmemLarge), st, a);
+    else if (md == 1) launch_step(step_kernel<1, SmemLarge>, qblk, sizeof(SmemLarge), st, a);
+    else launch_step(step_kernel<2, SmemLarge>, qblk, sizeof(SmemLarge), st, a);
   } else {
-    if (md == 0) step_kernel<0, SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a);
-    else if (md == 1) step_kernel<1, SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a);
-    else step_kernel<2, SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a);
+    if (md == 0) launch_step(step_kernel<0, SmemSmall>, qblk, sizeof(SmemSmall), st, a);
+    else if (md == 1) launch_step(step_kernel<1, SmemSmall>, qblk, sizeof(SmemSmall), st, a);
+    else launch_step(step_kernel<2, SmemSmall>, qblk, sizeof(SmemSmall), st, a);
   }
   env->launches++;
   CK(cudaGetLastError());

@@ -353,6 +353,42 @@ def measure_device(wl, K, W, rank, world, local_rank, clocks=None, min_region_s=
     return res, env, (pool, hpool, POOL)
 
 
+def measure_sequence(env, n, pools, K, world, local_rank, blocks=60):
+    """The same K steps per block through ilrl_step_sequence: ONE launch per block, a CTA takes its tile through all K
+    steps (possible only because the K action batches exist before the block starts, as they do in this benchmark and
+    in open-loop playback; a policy in the loop cannot use it).  Same timing rules as measure_device."""
+    import torch
+    import torch.distributed as dist
+    dev = torch.device("cuda", local_rank)
+    pool, _, POOL = pools
+    obs = torch.empty(K, n, 70, device=dev)
+    rew = torch.empty(K, n, device=dev)
+    done = torch.empty(K, n, dtype=torch.uint8, device=dev)
+    slices = max(1, POOL // K)
+
+    def block(r):
+        a = pool[(r % slices) * K:(r % slices) * K + K]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        env.step_sequence(a, obs, rew, done)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for r in range(3):
+        block(r)
+    ms = torch.tensor([block(r) for r in range(blocks)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    mb = np.sort(ms.cpu().numpy())
+    return {"ms_block": float(mb[len(mb) // 2]), "blocks": blocks}
+
+
 def measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks=None, min_region_s=0.5):
     """The same metric end to end through the C ABI with HOST buffers: every step's actions come from pinned host memory
     and its observations / rewards / dones land in pinned host memory inside the timed region.
@@ -486,6 +522,9 @@ def run_ours(args):
     wl = WORKLOADS[args.workload]
     res, env, pools = measure_device(wl, K, W, rank, world, local_rank, clocks, use_graph=not args.no_graph)
     n, hier = res["n"], res["hier"]
+    seq = None
+    if not hier and not wl.get("terrain") and not wl.get("self_collision") and K <= pools[2]:
+        seq = measure_sequence(env, n, pools, K, world, local_rank)
     e2e = measure_e2e(env, n, hier, pools, K, rank, world, local_rank, clocks)
     env.close()
     del pools
@@ -572,6 +611,12 @@ def run_ours(args):
                     "serve_api": "ilrl_serve_step: one blocking call per step against the resident serving kernel (doorbell in "
                                  "mapped host memory: no launch, no stream synchronise; session begin / end inside each block)"},
             "gpu_launches": res["launches_per_block"],
+            # NOT the headline: the same K steps as one ilrl_step_sequence launch (no grid-wide barrier between steps)
+            "sequence": None if seq is None else {
+                "value": res["n_all"] * K / (seq["ms_block"] * 1e-3), "unit": UNIT, "ms_per_step": seq["ms_block"] / K,
+                "launches_per_block": 1, "blocks": seq["blocks"],
+                "api": "ilrl_step_sequence: K steps of open-loop actions in one launch; bit-identical to K ilrl_step calls "
+                       "(tests/test_gpu_api.py); `value` above stays the launch-per-step path every RL caller uses"},
             "clocks": clk,
         }
         if extra:

@@ -146,6 +146,17 @@ class BatchedHumanoidEnv:
             assert t.is_cuda and t.device == self.device and t.dtype == dt and t.is_contiguous() and tuple(t.shape) == shape
         self._ck(self.L.ilrl_step(self.h, _ptr(action), _ptr(obs), _ptr(reward), _ptr(done), _ptr(terms), self._stream()))
 
+    def step_sequence(self, actions, obs, reward, done, terms=None):
+        """K low-level steps in one launch (mode "low"): actions [K,N,17] -> obs [K,N,70], reward [K,N], done [K,N] u8,
+        optional terms [K,N,12], all caller-owned contiguous device tensors.  Same results as K `step_into` calls."""
+        k, n = int(actions.shape[0]), self.num_envs
+        for t, shape, dt in ((actions, (k, n, ACT_LOW), torch.float32), (obs, (k, n, self.obs_w), torch.float32),
+                             (reward, (k, n), torch.float32), (done, (k, n), torch.uint8)) + (
+                                 () if terms is None else ((terms, (k, n, TERM_WORDS), torch.float32),)):
+            assert t.is_cuda and t.device == self.device and t.dtype == dt and t.is_contiguous() and tuple(t.shape) == shape
+        self._ck(self.L.ilrl_step_sequence(self.h, k, _ptr(actions), _ptr(obs), _ptr(reward), _ptr(done), _ptr(terms),
+                                           self._stream()))
+
     def step_host(self, action_np, obs_np, reward_np, done_np, terms_np=None):
         """Same step through host (numpy) buffers: H2D of the actions, kernel, D2H of obs/reward/done, synchronous."""
         # the argument tuple of the previous call is reused while the same buffers come back (the usual loop): dtype /

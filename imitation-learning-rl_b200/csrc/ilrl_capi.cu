@@ -163,8 +163,12 @@ __device__ __forceinline__ void set_torques(SM& sm, int e, int tid, int role, co
 // One tile (QE envs) of one env step: everything between a CTA picking its tile and moving on.  Shared by the
 // launch-per-step kernel and the persistent serving kernel (K1s).  action: the [n,17] action array of this step.
 template <int MODE, class SM, bool TERR, bool SELFC = false>
-__device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int tile, const float* action) {
+__device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int tile, const float* action, const int ko = 0) {
   const int tid = threadIdx.x, e = tid >> 2, role = tid & 3, qb = tid & ~3;
+  // (ko: index of this step in a sequence launch, K1q - its outputs go to slab ko of [K, n, ...] arrays)
+  float* const o_reward = a.reward + (size_t)ko * a.n;
+  uint8_t* const o_done = a.done + (size_t)ko * a.n;
+  float* const o_terms = a.terms ? a.terms + (size_t)ko * a.n * ILRL_TERM_WORDS : nullptr;
   const unsigned qm = 0xFu << ((tid & 31) & ~3);
   constexpr int OBSW = MODE == 2 ? ILRL_OBS_LOW2 : ILRL_OBS_LOW, HOBSW = MODE == 2 ? ILRL_OBS_HIGH2 : ILRL_OBS_HIGH;
   static_assert(SM::ES >= OBSW, "the obs row is staged in the env's scratch block");
@@ -206,9 +210,9 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
   // batched adapters' "no action for this env in this call"; the reference asserts finite actions, REF humanoid.py:55)
   const bool pending = valid && ((MODE >= 1 && pend_flag != 0.f) || isnan(sm.act(e)[0]));
   if (valid && pending) {
-    if (role == 0) { a.reward[i] = 0.f; a.done[i] = 0; }
-    if (a.terms)
-      for (int t = role; t < ILRL_TERM_WORDS; t += 4) a.terms[(size_t)i * ILRL_TERM_WORDS + t] = 0.f;
+    if (role == 0) { o_reward[i] = 0.f; o_done[i] = 0; }
+    if (o_terms)
+      for (int t = role; t < ILRL_TERM_WORDS; t += 4) o_terms[(size_t)i * ILRL_TERM_WORDS + t] = 0.f;
   }
   // envs that step.  The physics substeps run between CTA barriers: the warps of a CTA (and, because tiles start
   // together, mostly the CTAs of an SM) then execute the same 70 KB of substep code at about the same time and share
@@ -326,10 +330,10 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
       }
       terms[ILRL_T_HIGHTARGET] = w.e[ILRL_E_HIGH_TARGET_SCORE];
     }
-    if (role == 0) { a.reward[i] = reward; a.done[i] = done ? 1 : 0; }
-    if (a.terms) {
+    if (role == 0) { o_reward[i] = reward; o_done[i] = done ? 1 : 0; }
+    if (o_terms) {
 #pragma unroll
-      for (int t = 0; t < ILRL_TERM_WORDS; t++) if ((t & 3) == role) a.terms[(size_t)i * ILRL_TERM_WORDS + t] = terms[t];
+      for (int t = 0; t < ILRL_TERM_WORDS; t++) if ((t & 3) == role) o_terms[(size_t)i * ILRL_TERM_WORDS + t] = terms[t];
     }
     if (role == 0) {
       st_steps = 1.f; st_rew = reward;
@@ -385,7 +389,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
   {
     const unsigned okmask = __ballot_sync(0xffffffffu, write_obs);   // (includes the staging writes' __syncwarp)
     const int e0 = e & ~7, lane = tid & 31;
-    float* orow = a.obs + (size_t)(base + e0) * OBSW;
+    float* orow = a.obs + ((size_t)ko * a.n + (size_t)(base + e0)) * OBSW;
 #pragma unroll 1
     for (int f = lane; f < 8 * (OBSW / 2); f += 32) {
       const int r = f / (OBSW / 2), c2 = f - r * (OBSW / 2);
@@ -449,6 +453,25 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     a.tile_counter[1] = 0u;
   }
   if (a.ktime && tid == 0) atomicMax(a.ktime + 1, globaltimer_ns());
+}
+
+// ------------------------------------------------------------------------------------------------ K1q: action sequences
+// K consecutive env steps of the low-level env in ONE launch, for callers that hold the actions of all K steps before
+// the first one runs (open-loop playback of recorded or scripted action sequences, random-action rollouts).  Envs never
+// interact, so a CTA takes its tile through all K steps without waiting for any other CTA: the grid-wide barrier that a
+// launch per step implies - every step ends with its slowest warp, ~25 % above the mean at 4096 envs -
+// is paid once per K steps instead of once per step.  action [K,n,17]; obs [K,n,70], reward / done [K,n], terms [K,n,12].
+template <class SM>
+__global__ void __launch_bounds__(QT) step_seq_kernel(const StepArgs a, const int ksteps) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  SM& sm = *reinterpret_cast<SM*>(smraw);
+  quad_smem_init(sm);
+  if (a.ktime && threadIdx.x == 0) atomicMin(a.ktime, globaltimer_ns());
+  __syncthreads();
+  for (int tile = (int)blockIdx.x; tile < a.ntiles; tile += (int)gridDim.x)
+    for (int k = 0; k < ksteps; k++)   // (step_tile ends with a CTA barrier: step k's stores are visible to step k+1's loads)
+      step_tile<0, SM, false>(a, sm, tile, a.action + (size_t)k * a.n * NJ, k);
+  if (a.ktime && threadIdx.x == 0) atomicMax(a.ktime + 1, globaltimer_ns());
 }
 
 // ------------------------------------------------------------------------------------------------ K1s: persistent serving
@@ -991,6 +1014,9 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaMalloc(&env->gscr, sizeof(float) * (size_t)chain::GROWS * chain::RW * n));
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
   CKC(cudaFuncSetAttribute(step_kernel<1, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
+  CKC(cudaFuncSetAttribute(step_seq_kernel<SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
+  CKC(cudaFuncSetAttribute(step_seq_kernel<SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
+  CKC(cudaFuncSetAttribute(step_seq_kernel<SmemDense4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDense4)));
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemLarge, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(physics_only_kernel<SmemLarge, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemSelf, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSelf)));
@@ -1183,15 +1209,8 @@ int ilrl_reset(ilrl_env* env, const uint8_t* mask, const int32_t* start_frame, c
   return ILRL_OK;
 }
 
-// part < 0: the whole batch; otherwise envs [first, first + count) on the part's own tile counters
-static int do_step(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms,
-                   cudaStream_t st, int skip_physics, int first = 0, int count = -1, int part = -1, int forced_scalar = INT_MIN) {
-  if (!env) return ILRL_ERR_ARG;
-  if (!action || !obs || !reward || !done) return fail(env, ILRL_ERR_ARG, "ilrl_step: null buffer");
-  if (int r = check_ready(env)) return r;
-  ON_DEVICE(env);
-  if (count < 0) count = env->n;
-  StepArgs a;
+static void fill_step_args(ilrl_env* env, StepArgs& a, const float* action, float* obs, float* reward, uint8_t* done,
+                           float* terms, int skip_physics, int first, int count, int part, int forced_scalar) {
   a.n = env->n; a.first = first; a.end = first + count; a.skip_frame = env->cfg.skip_frame;
   a.id_base = env->cfg.env_id_base; a.skip_physics = skip_physics; a.auto_reset = env->cfg.auto_reset; a.max_timestep = env->cfg.max_timestep;
   a.step_per_level = (float)env->cfg.step_per_level; a.seed = env->cfg.seed;
@@ -1207,6 +1226,18 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   memcpy(a.clips, env->clips, sizeof a.clips);
   a.ktime = (env->timing && env->kt_used < KT_SLOTS) ? env->ktime + 2 * (size_t)env->kt_used++ : nullptr;
   a.ntiles = (count + QE - 1) / QE;
+}
+
+// part < 0: the whole batch; otherwise envs [first, first + count) on the part's own tile counters
+static int do_step(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms,
+                   cudaStream_t st, int skip_physics, int first = 0, int count = -1, int part = -1, int forced_scalar = INT_MIN) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!action || !obs || !reward || !done) return fail(env, ILRL_ERR_ARG, "ilrl_step: null buffer");
+  if (int r = check_ready(env)) return r;
+  ON_DEVICE(env);
+  if (count < 0) count = env->n;
+  StepArgs a;
+  fill_step_args(env, a, action, obs, reward, done, terms, skip_physics, first, count, part, forced_scalar);
   // (heightfield terrain / self-collision: their own instantiations, in the mid-size layout whatever the batch size)
   const bool special = env->terr.h || env->self_on;
   const int layout = special ? 1 : env->layout;
@@ -1238,6 +1269,26 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
 
 int ilrl_step(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms, void* stream) {
   return do_step(env, action, obs, reward, done, terms, (cudaStream_t)stream, 0);
+}
+
+int ilrl_step_sequence(ilrl_env* env, int32_t ksteps, const float* action, float* obs, float* reward, uint8_t* done,
+                       float* terms, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  if (!action || !obs || !reward || !done || ksteps < 1) return fail(env, ILRL_ERR_ARG, "ilrl_step_sequence: null buffer or ksteps < 1");
+  if (env->cfg.mode != 0) return fail(env, ILRL_ERR_ARG, "ilrl_step_sequence: low-level env only (a hier env needs its high-level action between steps)");
+  if (env->terr.h || env->self_on) return fail(env, ILRL_ERR_STATE, "ilrl_step_sequence: not available with a heightfield or self-collision");
+  if (int r = check_ready(env)) return r;
+  ON_DEVICE(env);
+  cudaStream_t st = (cudaStream_t)stream;
+  StepArgs a;
+  fill_step_args(env, a, action, obs, reward, done, terms, 0, 0, env->n, -1, INT_MIN);
+  const int qblk = min(a.ntiles, env->layout == 2 ? env->grid_dense4 : env->layout == 1 ? env->grid_large : env->grid_small);
+  if (env->layout == 2) step_seq_kernel<SmemDense4><<<qblk, QT, sizeof(SmemDense4), st>>>(a, ksteps);
+  else if (env->layout == 1) step_seq_kernel<SmemLarge><<<qblk, QT, sizeof(SmemLarge), st>>>(a, ksteps);
+  else step_seq_kernel<SmemSmall><<<qblk, QT, sizeof(SmemSmall), st>>>(a, ksteps);
+  env->launches++;
+  CK(cudaGetLastError());
+  return ILRL_OK;
 }
 int ilrl_step_no_physics(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms,
                          void* stream) {

@@ -88,6 +88,13 @@ int ilrl_reset(ilrl_env* env, const uint8_t* mask_dev, const int32_t* start_fram
 int ilrl_step(ilrl_env* env, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
               float* terms_dev, void* stream);
 
+/* K consecutive steps of the LOW-LEVEL env (mode 0, flat ground, no self-collision) in one launch, for callers that hold
+ * the actions of all K steps up front (open-loop playback of recorded / scripted action sequences, random-action
+ * rollouts): action_dev [K,N,17]; obs_dev [K,N,70], reward_dev / done_dev [K,N], terms_dev [K,N,12] or NULL.  Bit-identical
+ * to K calls of ilrl_step (auto-reset included); envs do not wait for each other between steps. */
+int ilrl_step_sequence(ilrl_env* env, int32_t ksteps, const float* action_dev, float* obs_dev, float* reward_dev,
+                       uint8_t* done_dev, float* terms_dev, void* stream);
+
 /* Same step through HOST buffers: copies the actions up, runs the step, copies obs/reward/done back and waits.
  * When every buffer is page-locked and mapped (cudaHostAlloc / cudaHostRegister / torch pin_memory) the kernel reads
  * and writes them in place (zero-copy: one launch, one synchronise); otherwise page-locked buffers are DMA endpoints

@@ -608,6 +608,53 @@ def test_physical_invariants_after_long_rollout():
     env.close()
 
 
+def test_step_sequence_equals_k_single_steps(monkeypatch):
+    """ilrl_step_sequence (K steps of the low-level env in one launch, a CTA taking its tile through all K without
+    waiting for the rest of the grid) is bit-identical to K ilrl_step calls - outputs of every step, final state, rng
+    counters and statistics - in every shared-memory layout, with episodes ending and auto-resetting inside the
+    sequence, and with more tiles than resident CTAs (grid-stride over tiles)."""
+    for layout, n in (("small", 1000), ("large", 1000), ("dense4", 9700)):
+        monkeypatch.setenv("ILRL_LAYOUT", layout)
+        k = 40 if n == 1000 else 6
+        g = torch.Generator(device="cuda")
+        g.manual_seed(11)
+        acts = (torch.rand(k, n, 17, device="cuda", generator=g) * 2 - 1) * 2.0
+        kw = dict(clips=["motion08_03", "motion09_03"], clip_of_env=np.arange(n, dtype=np.int32) % 2, seed=9, auto_reset=True)
+        ref = BatchedHumanoidEnv(n, "low", **kw)
+        ref.reset()
+        want = [tuple(x.clone() for x in ref.step(acts[t])) for t in range(k)]
+        want_state = [x.clone() for x in ref.get_state()]
+        want_stats = ref.stats()
+        ref.close()
+        env = BatchedHumanoidEnv(n, "low", **kw)
+        env.reset()
+        obs = torch.full((k, n, 70), float("nan"), device="cuda")
+        rew = torch.full((k, n), float("nan"), device="cuda")
+        done = torch.full((k, n), 7, dtype=torch.uint8, device="cuda")
+        terms = torch.full((k, n, 12), float("nan"), device="cuda")
+        env.step_sequence(acts, obs, rew, done, terms)
+        torch.cuda.synchronize()
+        for t in range(k):
+            for got, w in zip((obs[t], rew[t], done[t], terms[t]), want[t]):
+                assert torch.equal(got, w), (layout, t)
+        if n == 1000:
+            assert int(done.sum()) > 0, "no episode ended inside the sequence: the auto-reset path went untested"
+        for x, y in zip(env.get_state(), want_state):
+            assert torch.equal(x, y), layout
+        torch.testing.assert_close(env.stats(), want_stats, rtol=1e-6, atol=1e-6)   # (atomic accumulation order differs)
+        # K = 1 is a plain step; hier handles and bad arguments are refused
+        env.step_sequence(acts[:1].contiguous(), obs[:1], rew[:1], done[:1])
+        with pytest.raises(Exception):
+            env.step_sequence(acts[:0].contiguous(), obs[:0], rew[:0], done[:0])
+        env.close()
+    h = BatchedHumanoidEnv(64, "hier", clips=["motion09_03"], seed=1)
+    h.reset()
+    with pytest.raises(Exception):
+        h.step_sequence(torch.zeros(2, 64, 17, device="cuda"), torch.zeros(2, 64, 70, device="cuda"),
+                        torch.zeros(2, 64, device="cuda"), torch.zeros(2, 64, dtype=torch.uint8, device="cuda"))
+    h.close()
+
+
 def test_both_shared_memory_layouts_are_bit_identical(monkeypatch):
     """The step kernel has two shared-memory layouts picked from the batch size (all on chip / 3 CTAs per SM with rows
     spilling to the global scratch beyond 8).  They must agree bit for bit, including envs with many rows."""

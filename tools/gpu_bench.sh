@@ -6,6 +6,7 @@ import json
 d=json.loads(open('gpurun_out/b20.json').read().strip().splitlines()[-1])
 print(json.dumps({k:d[k] for k in ('value','ms_per_step','gpu_launches','vs_cpu_port')}))
 print('e2e', json.dumps({k:v for k,v in d['e2e'].items() if k!='api' and k!='sync_api'}))
+print('sequence', json.dumps({k:v for k,v in (d.get('sequence') or {}).items() if k!='api'}))
 print('clocks', json.dumps(d['clocks']))
 print('roofline', json.dumps({k:v for k,v in d['roofline'].items() if k not in('note',)}))
 print('config', json.dumps({k:v for k,v in d['config'].items() if k in('blocks','block_ms_min','block_ms_max','timing')}))

@@ -8,7 +8,7 @@ SO = os.environ.get("ILRL_SO") or os.path.join(HERE, "libilrl_b200.so")  # ILRL_
 SYMBOLS = ["ilrl_create", "ilrl_destroy", "ilrl_last_error", "ilrl_load_clip", "ilrl_set_clip_ids", "ilrl_reset",
            "ilrl_step", "ilrl_step_sequence", "ilrl_step_host", "ilrl_step_host_async", "ilrl_wait", "ilrl_wait_step_host_async", "ilrl_serve_begin", "ilrl_serve_post", "ilrl_serve_wait", "ilrl_serve_step", "ilrl_serve_end", "ilrl_step_pull", "ilrl_pull", "ilrl_set_config", "ilrl_high_step", "ilrl_high_readout", "ilrl_get_state", "ilrl_set_state",
            "ilrl_set_heightfield", "ilrl_set_self_collision", "ilrl_set_forced_reset_noise", "ilrl_get_joint_target", "ilrl_set_joint_target",
-           "ilrl_set_forced_target_deg", "ilrl_step_no_physics", "ilrl_physics_only", "ilrl_endpoint_score",
+           "ilrl_set_forced_target_deg", "ilrl_get_grouping", "ilrl_step_no_physics", "ilrl_physics_only", "ilrl_endpoint_score",
            "ilrl_stats", "ilrl_gae", "ilrl_episode_columns", "ilrl_gae_decisions", "ilrl_policy_blob_bytes", "ilrl_policy_pack", "ilrl_policy_step",
            "ilrl_launch_count", "ilrl_kernel_timing"]
 
@@ -57,6 +57,7 @@ def lib():
     L.ilrl_wait_step_host_async.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp, _vp]
     L.ilrl_set_config.argtypes = [_vp, C.c_int32, C.c_int32, C.c_int32]
     L.ilrl_step_no_physics.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.ilrl_get_grouping.argtypes = [_vp, _vp, _vp, _vp]
     L.ilrl_step_sequence.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp, _vp, _vp]
     L.ilrl_high_step.argtypes = [_vp, _vp, _vp, _vp]
     L.ilrl_high_readout.argtypes = [_vp, _vp, _vp, _vp, _vp]

@@ -1,8 +1,10 @@
 // ilrl_capi.cu — kernels + the C ABI declared in include/ilrl.h (libilrl_b200.so, sm_100a only, no CPU path).
 //
 // Data layout in HBM (per handle, N envs):
-//   phys  [47][N] fp32  structure-of-arrays: word-major, env-minor -> every load/store of a warp is one coalesced
-//   envf  [28][N] fp32  128-byte line per word.  Persistent state = 75 words + 1 rng counter = 304 B / env.
+//   phys  [N][48] fp32  one 16-byte-aligned row per env (47 words used): the four lanes that step an env move its row, and
+//   envf  [N][28] fp32  a row stays one contiguous block when envs are reached through the cost-grouping permutation (K8).
+//                       Persistent state = 75 words + 1 rng counter = 304 B / env.  (Rounds 1-2 held it word-major,
+//                       [47][N]: fine for neighbours in a warp, 8 sectors per access once the envs of a warp are scattered.)
 //   rng   [N]     u32   Philox draw counter
 //   clips: the 4 tables of every loaded motion clip, row-major fp32, read through the read-only path (L2-resident,
 //          ~200 KB for all four clips).
@@ -47,8 +49,8 @@ struct StepArgs {
   int max_timestep;
   float step_per_level;
   uint64_t seed;
-  float* phys;         // [47][n]
-  float* envf;         // [28][n]
+  float* phys;         // [n][ILRL_PHYS_STRIDE]
+  float* envf;         // [n][ILRL_ENV_STRIDE]
   uint32_t* rng;       // [n]
   const float* action; // [n,17]
   float* obs;          // [n,70]
@@ -61,11 +63,13 @@ struct StepArgs {
   const int32_t* forced_deg;  // [n] or null
   int forced_scalar;          // INT_MIN, or the heading every env uses at its next target re-sampling (ilrl_step_pull)
   double* stats;       // [16] or null: fp64 accumulators (counts stay exact past 2^24 env steps between two reads)
-  float* jt;           // [34][n] jointTarget (MODE 2: hier_env_2.py:731)
+  float* jt;           // [n][ILRL_JT_STRIDE] jointTarget (MODE 2: hier_env_2.py:731)
   const float* forced_noise;  // [n,17] or null: joint noise an auto-reset uses instead of its own draws (MODE 2 harness)
   float* gscr;         // [n][GROWS][RW] overflow scratch for constraint rows beyond the shared-memory budget
   unsigned int* tile_counter;  // [2]: next tile to hand out, CTAs that have left (both zero between launches)
   int ntiles;
+  const int* perm = nullptr;     // null, or [n]: the env that batch position p steps (envs grouped by cost, heaviest first: K8)
+  uint8_t* cost = nullptr;       // null, or [n]: the key of that grouping, 0 = most expensive
   unsigned long long* ktime;   // null, or {first CTA start, last CTA end} of this launch in %globaltimer ns (ilrl_kernel_timing)
 #ifdef ILRL_PROF
   long long* prof;     // [warps of the launch][PF_WORDS] phase cycles (measurement build only)
@@ -76,38 +80,36 @@ struct StepArgs {
 };
 
 __device__ __forceinline__ void load_state(const StepArgs& a, int i, Phys& s, EnvW& w) {
-  const float* p = a.phys + i;
-  const int n = a.n;
+  const float* p = a.phys + (size_t)i * ILRL_PHYS_STRIDE;
 #pragma unroll
-  for (int k = 0; k < 3; k++) s.p[k] = p[(0 + k) * n];
+  for (int k = 0; k < 3; k++) s.p[k] = p[0 + k];
 #pragma unroll
-  for (int k = 0; k < 4; k++) s.quat[k] = p[(3 + k) * n];
+  for (int k = 0; k < 4; k++) s.quat[k] = p[3 + k];
 #pragma unroll
-  for (int k = 0; k < 3; k++) s.v[k] = p[(7 + k) * n];
+  for (int k = 0; k < 3; k++) s.v[k] = p[7 + k];
 #pragma unroll
-  for (int k = 0; k < 3; k++) s.w[k] = p[(10 + k) * n];
+  for (int k = 0; k < 3; k++) s.w[k] = p[10 + k];
 #pragma unroll
-  for (int k = 0; k < NJ; k++) { s.q[k] = p[(13 + k) * n]; s.qd[k] = p[(30 + k) * n]; }
-  const float* e = a.envf + i;
+  for (int k = 0; k < NJ; k++) { s.q[k] = p[13 + k]; s.qd[k] = p[30 + k]; }
+  const float* e = a.envf + (size_t)i * ILRL_ENV_STRIDE;
 #pragma unroll
-  for (int k = 0; k < ILRL_ENV_WORDS; k++) w.e[k] = e[k * n];
+  for (int k = 0; k < ILRL_ENV_WORDS; k++) w.e[k] = e[k];
 }
 __device__ __forceinline__ void store_state(const StepArgs& a, int i, const Phys& s, const EnvW& w) {
-  float* p = a.phys + i;
-  const int n = a.n;
+  float* p = a.phys + (size_t)i * ILRL_PHYS_STRIDE;
 #pragma unroll
-  for (int k = 0; k < 3; k++) p[(0 + k) * n] = s.p[k];
+  for (int k = 0; k < 3; k++) p[0 + k] = s.p[k];
 #pragma unroll
-  for (int k = 0; k < 4; k++) p[(3 + k) * n] = s.quat[k];
+  for (int k = 0; k < 4; k++) p[3 + k] = s.quat[k];
 #pragma unroll
-  for (int k = 0; k < 3; k++) p[(7 + k) * n] = s.v[k];
+  for (int k = 0; k < 3; k++) p[7 + k] = s.v[k];
 #pragma unroll
-  for (int k = 0; k < 3; k++) p[(10 + k) * n] = s.w[k];
+  for (int k = 0; k < 3; k++) p[10 + k] = s.w[k];
 #pragma unroll
-  for (int k = 0; k < NJ; k++) { p[(13 + k) * n] = s.q[k]; p[(30 + k) * n] = s.qd[k]; }
-  float* e = a.envf + i;
+  for (int k = 0; k < NJ; k++) { p[13 + k] = s.q[k]; p[30 + k] = s.qd[k]; }
+  float* e = a.envf + (size_t)i * ILRL_ENV_STRIDE;
 #pragma unroll
-  for (int k = 0; k < ILRL_ENV_WORDS; k++) e[k * n] = w.e[k];
+  for (int k = 0; k < ILRL_ENV_WORDS; k++) e[k] = w.e[k];
 }
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -173,8 +175,8 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
   constexpr int OBSW = MODE == 2 ? ILRL_OBS_LOW2 : ILRL_OBS_LOW, HOBSW = MODE == 2 ? ILRL_OBS_HIGH2 : ILRL_OBS_HIGH;
   static_assert(SM::ES >= OBSW, "the obs row is staged in the env's scratch block");
   const int base = a.first + tile * QE;
-  const int i = base + e;
-  const bool valid = i < a.end;
+  const bool valid = base + e < a.end;
+  const int i = (valid && a.perm) ? a.perm[base + e] : base + e;
   chain::Prof pf;
 #ifdef ILRL_PROF
   if (a.prof && (tid & 31) == 0) pf.p = a.prof + (size_t)(tile * (QT / 32) + (tid >> 5)) * chain::PF_WORDS;
@@ -191,7 +193,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
     const float* arow = action + (size_t)i * NJ;
 #pragma unroll
     for (int m = 0; m < (NJ + 3) / 4; m++) if (role + 4 * m < NJ) av[m] = arow[role + 4 * m];
-    if (MODE >= 1) pend_flag = a.envf[(size_t)ILRL_E_HIGH_PENDING * a.n + i];
+    if (MODE >= 1) pend_flag = a.envf[(size_t)i * ILRL_ENV_STRIDE + ILRL_E_HIGH_PENDING];
     chain::load_base(a.phys, a.n, i, b);
     chain::load_links(a.phys, a.n, i, sm, role, qv, qdv);
     float* dst = sm.act(e);
@@ -210,7 +212,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
   // batched adapters' "no action for this env in this call"; the reference asserts finite actions, REF humanoid.py:55)
   const bool pending = valid && ((MODE >= 1 && pend_flag != 0.f) || isnan(sm.act(e)[0]));
   if (valid && pending) {
-    if (role == 0) { o_reward[i] = 0.f; o_done[i] = 0; }
+    if (role == 0) { o_reward[i] = 0.f; o_done[i] = 0; if (a.cost) a.cost[i] = 63; }
     if (o_terms)
       for (int t = role; t < ILRL_TERM_WORDS; t += 4) o_terms[(size_t)i * ILRL_TERM_WORDS + t] = 0.f;
   }
@@ -238,6 +240,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
   } else {
     chain::dummy_state(sm, e, tid, b);
   }
+  int rows_last = 0;
   if (!a.skip_physics) {
     float* gscr_tile = a.gscr + (size_t)min(base, a.n - 1) * chain::GROWS * chain::RW;
     chain::SelfC sct = a.selfc;
@@ -247,8 +250,10 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
       pf.mark(sub == 0 ? chain::PF_HEAD : chain::PF_INTEG);
       __syncthreads();
       pf.mark(chain::PF_BARRIER);
-      chain::substep<TERR, SELFC>(b, sm, gscr_tile, e, tid, role, active, (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf,
-                                  TERR ? &a.terr : nullptr, SELFC ? &sct : nullptr);
+      const int nrows = chain::substep<TERR, SELFC>(b, sm, gscr_tile, e, tid, role, active,
+                                                    (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf, TERR ? &a.terr : nullptr,
+                                                    SELFC ? &sct : nullptr);
+      if (sub == ILRL_SUBSTEPS - 1) rows_last = nrows;
     }
   }
   __syncthreads();   // the once-per-step tail (4 k instructions) is entered together as well: +3 % at 65536 envs
@@ -259,9 +264,9 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
     chain::gather(b, sm, e, qb, qm, ps);
     EnvW w;
     {
-      const float* ew = a.envf + i;
+      const float* ew = a.envf + (size_t)i * ILRL_ENV_STRIDE;
 #pragma unroll
-      for (int k = 0; k < ILRL_ENV_WORDS; k++) w.e[k] = ew[(size_t)k * a.n];
+      for (int k = 0; k < ILRL_ENV_WORDS; k++) w.e[k] = ew[k];
     }
     if (MODE >= 1) {
       w.e[ILRL_E_ROBOT_X] = stale_x; w.e[ILRL_E_ROBOT_Y] = stale_y;
@@ -278,7 +283,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
     float jt[MODE == 2 ? ILRL_JT_WORDS : 1];
     if (MODE == 2) {
 #pragma unroll
-      for (int k = 0; k < ILRL_JT_WORDS; k++) jt[k] = a.jt[(size_t)k * a.n + i];
+      for (int k = 0; k < ILRL_JT_WORDS; k++) jt[k] = a.jt[(size_t)i * ILRL_JT_STRIDE + k];
     }
     float reward;
     if constexpr (MODE == 2) reward = update_reward2(c, w, jt, act, terms);   // (no frame advance in hier_env_2's low step)
@@ -376,12 +381,19 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
     if (role == 0) {
       if (MODE >= 1) a.high_flags[i] = hflags;
       a.rng[i] = ctr;
+      // K8 key, 0 = most expensive: torso height (a fallen env tests and touches the ground with many spheres and is
+      // about to end and auto-reset - the longest path of the tail) less 5 cm per constraint row of the last substep;
+      // 1.6 cm buckets (tools/sort_experiment.py compares the candidates)
+      if (a.cost) {
+        const float ze = fminf(ps.p[2], 1.3f) - 0.05f * (float)((done && a.auto_reset) ? 0 : rows_last);
+        a.cost[i] = (uint8_t)min(max((int)((ze - 0.3f) * 64.f), 0), 63);
+      }
     }
     chain::store_phys(a.phys, a.n, i, role, ps);
     {
-      float* ew = a.envf + i;
+      float* ew = a.envf + (size_t)i * ILRL_ENV_STRIDE;
 #pragma unroll
-      for (int k = 0; k < ILRL_ENV_WORDS; k++) if ((k & 3) == role) ew[(size_t)k * a.n] = w.e[k];
+      for (int k = 0; k < ILRL_ENV_WORDS; k++) if ((k & 3) == role) ew[k] = w.e[k];
     }
   }
   // observations: only envs that stepped write their row (pending hier envs keep theirs).  Each warp stores the rows of
@@ -389,12 +401,13 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
   {
     const unsigned okmask = __ballot_sync(0xffffffffu, write_obs);   // (includes the staging writes' __syncwarp)
     const int e0 = e & ~7, lane = tid & 31;
-    float* orow = a.obs + ((size_t)ko * a.n + (size_t)(base + e0)) * OBSW;
+    float* const oall = a.obs + (size_t)ko * a.n * OBSW;
 #pragma unroll 1
-    for (int f = lane; f < 8 * (OBSW / 2); f += 32) {
-      const int r = f / (OBSW / 2), c2 = f - r * (OBSW / 2);
-      if ((okmask >> (4 * r)) & 1u)
-        *reinterpret_cast<float2*>(orow + r * OBSW + 2 * c2) = *reinterpret_cast<const float2*>(&sm.scr[e0 + r][2 * c2]);
+    for (int f0 = 0; f0 < 8 * (OBSW / 2); f0 += 32) {
+      const int f = f0 + lane, r = min(f / (OBSW / 2), 7), c2 = f - r * (OBSW / 2);
+      const int ir = __shfl_sync(0xffffffffu, i, 4 * r);   // (without grouping the 8 rows are one contiguous block)
+      if (f < 8 * (OBSW / 2) && ((okmask >> (4 * r)) & 1u))
+        *reinterpret_cast<float2*>(oall + (size_t)ir * OBSW + 2 * c2) = *reinterpret_cast<const float2*>(&sm.scr[e0 + r][2 * c2]);
     }
   }
   // K5: episode / reward statistics -> one atomicAdd per warp per slot
@@ -453,6 +466,67 @@ __global__ void __launch_bounds__(QT) step_kernel(const StepArgs a) {
     a.tile_counter[1] = 0u;
   }
   if (a.ktime && tid == 0) atomicMax(a.ktime + 1, globaltimer_ns());
+}
+
+// ------------------------------------------------------------------------------------------------ K8: cost grouping
+// A warp steps 8 envs in lock step and pays for the one with the most constraint rows (warp-uniform Gauss-Seidel loops
+// over the warp's maximum, row items pooled per warp).  In batches of more than one wave, where throughput follows the
+// MEAN warp time, envs of similar cost are therefore put into the same warps: every few steps this kernel sorts the env
+// ids by a cost key the step kernel leaves per env (torso height and constraint rows of the last substep, see step_tile)
+// into `perm`, most expensive first - the tile queue then also hands out the long tiles first.  Results do
+// not depend on the grouping (an env's arithmetic never involves its warp neighbours): bit-identical, tests/test_gpu_api.py.
+// One CTA, counting sort on 64 keys: warp-private histograms in shared memory (an atomic only ever conflicts with lanes of
+// its own warp; __match_any_sync costs a round per distinct key and was 10x slower), scan in (key, warp) order, scatter.
+// (The order of equal keys inside one 32-env group is whatever the hardware serialises; results do not depend on it.)
+// cost: 32 chunks of `chunk` bytes (a multiple of 512; entries past n hold 255 = "no env").  Warp w owns chunk w and reads it
+// 16 keys per lane and load, four loads in flight.
+template <bool SCATTER>
+__device__ __forceinline__ void cost_sort_pass(const uint8_t* cost, int* perm, const int chunk, unsigned (*hist)[64],
+                                               const unsigned* start) {
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint4* src = reinterpret_cast<const uint4*>(cost + (size_t)w * chunk);
+  const int nld = chunk / 512;
+  for (int l0 = 0; l0 < nld; l0 += 4) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) v[u] = l0 + u < nld ? src[(l0 + u) * 32 + lane] : make_uint4(~0u, ~0u, ~0u, ~0u);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const unsigned wd[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int b = 0; b < 16; b++) {
+        const int raw = (int)((wd[b >> 2] >> (8 * (b & 3))) & 255u);
+        if (raw != 255) {   // (0 = most expensive: first)
+          const unsigned at = atomicAdd(&hist[w][min(raw, 63)], 1u);   // warp-private counters: conflicts only inside this warp
+          if (SCATTER) perm[start[min(raw, 63)] + at] = w * chunk + ((l0 + u) * 32 + lane) * 16 + b;
+        }
+      }
+    }
+  }
+}
+__global__ void __launch_bounds__(1024) cost_sort_kernel(const uint8_t* __restrict__ cost, int* __restrict__ perm, const int chunk) {
+  __shared__ unsigned hist[32][64];
+  __shared__ unsigned start[64];
+  for (int k = threadIdx.x; k < 32 * 64; k += 1024) (&hist[0][0])[k] = 0u;
+  __syncthreads();
+  cost_sort_pass<false>(cost, perm, chunk, hist, start);
+  __syncthreads();
+  if (threadIdx.x < 64) {   // exclusive scan in (key, warp) order
+    unsigned s = 0;
+    for (int ww = 0; ww < 32; ww++) { const unsigned c = hist[ww][threadIdx.x]; hist[ww][threadIdx.x] = s; s += c; }
+    start[threadIdx.x] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned s = 0;
+    for (int k = 0; k < 64; k++) { const unsigned c = start[k]; start[k] = s; s += c; }
+  }
+  __syncthreads();
+  cost_sort_pass<true>(cost, perm, chunk, hist, start);
+}
+__global__ void iota_kernel(int* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = i;
 }
 
 // ------------------------------------------------------------------------------------------------ K1q: action sequences
@@ -628,7 +702,7 @@ __global__ void __launch_bounds__(BLOCK) high_step_kernel(const HighArgs a) {
     float jt[ILRL_JT_WORDS];
     for (int t = 0; t < ILRL_JT_WORDS; t++) {
       jt[t] = a.action2[(size_t)AW * i + 2 + t];
-      a.jt[(size_t)t * a.n + i] = jt[t];
+      a.jt[(size_t)i * ILRL_JT_STRIDE + t] = jt[t];
     }
     w.e[ILRL_E_STEPS_REMAINING] = a.step_per_level;
     w.e[ILRL_E_HIGH_PENDING] = 0.f;
@@ -636,9 +710,9 @@ __global__ void __launch_bounds__(BLOCK) high_step_kernel(const HighArgs a) {
     float o[ILRL_OBS_LOW2];
     write_low_obs2(c.obs, jt, o);
     for (int t = 0; t < ILRL_OBS_LOW2; t++) a.low_obs[(size_t)i * ILRL_OBS_LOW2 + t] = o[t];
-    float* e = a.envf + i;
+    float* e = a.envf + (size_t)i * ILRL_ENV_STRIDE;
 #pragma unroll
-    for (int kk = 0; kk < ILRL_ENV_WORDS; kk++) e[kk * a.n] = w.e[kk];
+    for (int kk = 0; kk < ILRL_ENV_WORDS; kk++) e[kk] = w.e[kk];
     return;
   }
   const float R2D = 57.29577951308232f, D2R = 0.017453292519943295f;
@@ -659,37 +733,37 @@ __global__ void __launch_bounds__(BLOCK) high_step_kernel(const HighArgs a) {
   float o[70];
   write_low_obs(c.obs, w, cl, o);
   for (int t = 0; t < 70; t++) a.low_obs[(size_t)i * 70 + t] = o[t];
-  float* e = a.envf + i;
+  float* e = a.envf + (size_t)i * ILRL_ENV_STRIDE;
 #pragma unroll
-  for (int kk = 0; kk < ILRL_ENV_WORDS; kk++) e[kk * a.n] = w.e[kk];
+  for (int kk = 0; kk < ILRL_ENV_WORDS; kk++) e[kk] = w.e[kk];
 }
 
 // ------------------------------------------------------------------------------------------------ harness kernels
 __global__ void state_get_kernel(StateView v, float* phys_aos, float* envf_aos) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= v.n) return;
-  if (phys_aos) for (int k = 0; k < ILRL_PHYS_WORDS; k++) phys_aos[(size_t)i * ILRL_PHYS_WORDS + k] = v.phys[(size_t)k * v.n + i];
-  if (envf_aos) for (int k = 0; k < ILRL_ENV_WORDS; k++) envf_aos[(size_t)i * ILRL_ENV_WORDS + k] = v.envf[(size_t)k * v.n + i];
+  if (phys_aos) for (int k = 0; k < ILRL_PHYS_WORDS; k++) phys_aos[(size_t)i * ILRL_PHYS_WORDS + k] = v.phys[(size_t)i * ILRL_PHYS_STRIDE + k];
+  if (envf_aos) for (int k = 0; k < ILRL_ENV_WORDS; k++) envf_aos[(size_t)i * ILRL_ENV_WORDS + k] = v.envf[(size_t)i * ILRL_ENV_STRIDE + k];
 }
 __global__ void state_set_kernel(StateView v, const float* phys_aos, const float* envf_aos) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= v.n) return;
-  if (phys_aos) for (int k = 0; k < ILRL_PHYS_WORDS; k++) v.phys[(size_t)k * v.n + i] = phys_aos[(size_t)i * ILRL_PHYS_WORDS + k];
-  if (envf_aos) for (int k = 0; k < ILRL_ENV_WORDS; k++) v.envf[(size_t)k * v.n + i] = envf_aos[(size_t)i * ILRL_ENV_WORDS + k];
+  if (phys_aos) for (int k = 0; k < ILRL_PHYS_WORDS; k++) v.phys[(size_t)i * ILRL_PHYS_STRIDE + k] = phys_aos[(size_t)i * ILRL_PHYS_WORDS + k];
+  if (envf_aos) for (int k = 0; k < ILRL_ENV_WORDS; k++) v.envf[(size_t)i * ILRL_ENV_STRIDE + k] = envf_aos[(size_t)i * ILRL_ENV_WORDS + k];
 }
-// jointTarget [34][n] <-> caller's [n,34] (exactly one of out / in is non-null)
+// resident jointTarget rows (stride ILRL_JT_STRIDE) <-> caller's [n,34] (exactly one of out / in is non-null)
 __global__ void jt_copy_kernel(int n, float* jt, float* out, const float* in) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   for (int k = 0; k < ILRL_JT_WORDS; k++) {
-    if (out) out[(size_t)i * ILRL_JT_WORDS + k] = jt[(size_t)k * n + i];
-    else jt[(size_t)k * n + i] = in[(size_t)i * ILRL_JT_WORDS + k];
+    if (out) out[(size_t)i * ILRL_JT_WORDS + k] = jt[(size_t)i * ILRL_JT_STRIDE + k];
+    else jt[(size_t)i * ILRL_JT_STRIDE + k] = in[(size_t)i * ILRL_JT_WORDS + k];
   }
 }
 __global__ void clip_ids_kernel(StateView v, const int32_t* ids) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= v.n) return;
-  v.envf[(size_t)ILRL_E_CLIP * v.n + i] = ids ? (float)ids[i] : 0.f;
+  v.envf[(size_t)i * ILRL_ENV_STRIDE + ILRL_E_CLIP] = ids ? (float)ids[i] : 0.f;
 }
 template <class SM, bool TERR = false, bool SELFC = false>
 __global__ void __launch_bounds__(QT) physics_only_kernel(StateView v, const float* torque, float* gscr_all, int nsub,
@@ -841,12 +915,12 @@ __global__ void pull_kernel(const PullArgs a) {
     else if (t == 72) v = a.reward[i];
     else if (t == 73) v = (float)a.done[i];
     else if (t < 86) v = a.terms[(size_t)i * ILRL_TERM_WORDS + (t - 74)];
-    else if (t < 114) v = a.envf[(size_t)(t - 86) * a.n + i];
-    else if (t < 161) v = a.phys[(size_t)(t - 114) * a.n + i];
+    else if (t < 114) v = a.envf[(size_t)i * ILRL_ENV_STRIDE + (t - 86)];
+    else if (t < 161) v = a.phys[(size_t)i * ILRL_PHYS_STRIDE + (t - 114)];
     else if (t < 221) v = (t - 161) < a.hobs_w ? a.high_obs[(size_t)i * a.hobs_w + (t - 161)] : 0.f;
     else if (t == 221) v = a.high_reward[i];
     else if (t == 222) v = (float)a.high_flags[i];
-    else v = a.jt ? a.jt[(size_t)(t - 223) * a.n + i] : 0.f;
+    else v = a.jt ? a.jt[(size_t)i * ILRL_JT_STRIDE + (t - 223)] : 0.f;
     o[t] = v;
   }
 }
@@ -879,7 +953,7 @@ struct ilrl_env {
   float* envf = nullptr;
   uint32_t* rng = nullptr;
   float* gscr = nullptr;
-  float* jt = nullptr;                    // [34][n] jointTarget (mode 2 only)
+  float* jt = nullptr;                    // [n][ILRL_JT_STRIDE] jointTarget (mode 2 only)
   chain::Terrain terr = {nullptr, 0, 0, 0.f, 0.f, 1.f};   // ilrl_set_heightfield (mode 0); h = device copy owned by the handle
   float* terr_mem = nullptr;
   chain::SelfC selfc = {0};
@@ -910,6 +984,11 @@ struct ilrl_env {
   uint8_t* d_done = nullptr;
   float *h_pull = nullptr, *h_pull_dev = nullptr;   // mapped staging of ilrl_step_pull / ilrl_pull (+ its action tail)
   int substeps = ILRL_SUBSTEPS;  // harness only (ilrl_debug_substeps)
+  int* perm = nullptr;           // [n] env ids grouped by cost (K8); identity until the first sort
+  uint8_t* cost = nullptr;       // [n] constraint rows of each env's last substep
+  int group_every = 2;           // sort every this many whole-batch steps (ILRL_GROUP_EVERY; 0 = never group; measured 1/2/4/8)
+  long long group_ctr = 0;
+  int cost_chunk = 0;
   int layout = 0;                // shared-memory layout of the step kernel: 0 LayoutSmall, 1 LayoutLarge, 2 LayoutDense4
                                  // (chosen at create time from N)
   bool no_zero_copy = false;     // harness only (ilrl_debug_zero_copy): force the explicit-copy host path
@@ -1008,10 +1087,17 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
       return ILRL_ERR_CUDA;                                                                    \
     }                                                                                          \
   } while (0)
-  CKC(cudaMalloc(&env->phys, sizeof(float) * ILRL_PHYS_WORDS * n));
-  CKC(cudaMalloc(&env->envf, sizeof(float) * ILRL_ENV_WORDS * n));
+  CKC(cudaMalloc(&env->phys, sizeof(float) * ILRL_PHYS_STRIDE * n));
+  CKC(cudaMalloc(&env->envf, sizeof(float) * ILRL_ENV_STRIDE * n));
   CKC(cudaMalloc(&env->rng, sizeof(uint32_t) * n));
   CKC(cudaMalloc(&env->gscr, sizeof(float) * (size_t)chain::GROWS * chain::RW * n));
+  CKC(cudaMalloc(&env->perm, sizeof(int) * n));
+  env->cost_chunk = (((n + 31) / 32) + 511) / 512 * 512;   // bytes per sorting warp; entries past n stay 255
+  CKC(cudaMalloc(&env->cost, 32 * (size_t)env->cost_chunk));
+  CKC(cudaMemset(env->cost, 255, 32 * (size_t)env->cost_chunk));
+  CKC(cudaMemset(env->cost, 0, n));
+  iota_kernel<<<nblk(n), BLOCK>>>(env->perm, n);
+  if (const char* o = getenv("ILRL_GROUP_EVERY")) env->group_every = atoi(o);
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
   CKC(cudaFuncSetAttribute(step_kernel<1, SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
   CKC(cudaFuncSetAttribute(step_seq_kernel<SmemSmall>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
@@ -1086,16 +1172,16 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   }
   CKC(cudaMalloc(&env->high_obs, sizeof(float) * env->hobs_w * n));
   if (m2) {
-    CKC(cudaMalloc(&env->jt, sizeof(float) * ILRL_JT_WORDS * n));
-    CKC(cudaMemset(env->jt, 0, sizeof(float) * ILRL_JT_WORDS * n));   // self.jointTarget = [0] * 16 (hier_env_2.py:172)
+    CKC(cudaMalloc(&env->jt, sizeof(float) * ILRL_JT_STRIDE * n));
+    CKC(cudaMemset(env->jt, 0, sizeof(float) * ILRL_JT_STRIDE * n));   // self.jointTarget = [0] * 16 (hier_env_2.py:172)
   }
   CKC(cudaMalloc(&env->high_reward, sizeof(float) * n));
   CKC(cudaMalloc(&env->high_flags, n));
   CKC(cudaMalloc(&env->stats, sizeof(double) * ILRL_STATS_WORDS));
   CKC(cudaMalloc(&env->tile_counter, 2 * (1 + ILRL_MAX_PARTS) * sizeof(unsigned int)));
   CKC(cudaMemset(env->tile_counter, 0, 2 * (1 + ILRL_MAX_PARTS) * sizeof(unsigned int)));
-  CKC(cudaMemset(env->phys, 0, sizeof(float) * ILRL_PHYS_WORDS * n));
-  CKC(cudaMemset(env->envf, 0, sizeof(float) * ILRL_ENV_WORDS * n));
+  CKC(cudaMemset(env->phys, 0, sizeof(float) * ILRL_PHYS_STRIDE * n));
+  CKC(cudaMemset(env->envf, 0, sizeof(float) * ILRL_ENV_STRIDE * n));
   CKC(cudaMemset(env->rng, 0, sizeof(uint32_t) * n));
   CKC(cudaMemset(env->high_obs, 0, sizeof(float) * env->hobs_w * n));
   CKC(cudaMemset(env->high_reward, 0, sizeof(float) * n));
@@ -1126,7 +1212,7 @@ void ilrl_destroy(ilrl_env* env) {
   cudaFree(env->serve_dev);
   cudaFreeHost(env->h_pull);
   cudaFree(env->ktime);
-  cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr); cudaFree(env->jt);
+  cudaFree(env->phys); cudaFree(env->envf); cudaFree(env->rng); cudaFree(env->gscr); cudaFree(env->jt); cudaFree(env->perm); cudaFree(env->cost);
   cudaFree(env->high_obs); cudaFree(env->high_reward); cudaFree(env->high_flags); cudaFree(env->stats); cudaFree(env->tile_counter);
   for (int c = 0; c < MAX_CLIPS; c++) cudaFree(env->clip_mem[c]);
   cudaFreeHost(env->h_action); cudaFreeHost(env->h_obs); cudaFreeHost(env->h_reward); cudaFreeHost(env->h_terms);
@@ -1243,6 +1329,14 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   const int layout = special ? 1 : env->layout;
   const int qblk = min(a.ntiles, layout == 2 ? env->grid_dense4 : layout == 1 ? env->grid_large : env->grid_small);
   const int md = env->cfg.mode;
+  // K8: whole-batch steps of more than one wave run on envs grouped by cost
+  if (part < 0 && first == 0 && count == env->n && env->group_every > 0 && a.ntiles > qblk) {
+    a.perm = env->perm; a.cost = env->cost;
+    if (env->group_ctr++ % env->group_every == 0) {
+      cost_sort_kernel<<<1, 1024, 0, st>>>(env->cost, env->perm, env->cost_chunk);
+      env->launches++;
+    }
+  }
   if (special) {
     if (env->terr.h && env->self_on) launch_step(step_kernel<0, SmemSelf, true, true>, qblk, sizeof(SmemSelf), st, a);
     else if (env->self_on && md == 0) launch_step(step_kernel<0, SmemSelf, false, true>, qblk, sizeof(SmemSelf), st, a);
@@ -1269,6 +1363,14 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
 
 int ilrl_step(ilrl_env* env, const float* action, float* obs, float* reward, uint8_t* done, float* terms, void* stream) {
   return do_step(env, action, obs, reward, done, terms, (cudaStream_t)stream, 0);
+}
+
+int ilrl_get_grouping(ilrl_env* env, uint8_t* cost_dev, int32_t* perm_dev, void* stream) {
+  if (!env) return ILRL_ERR_ARG;
+  ON_DEVICE(env);
+  if (cost_dev) CK(cudaMemcpyAsync(cost_dev, env->cost, env->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  if (perm_dev) CK(cudaMemcpyAsync(perm_dev, env->perm, sizeof(int) * env->n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return ILRL_OK;
 }
 
 int ilrl_step_sequence(ilrl_env* env, int32_t ksteps, const float* action, float* obs, float* reward, uint8_t* done,

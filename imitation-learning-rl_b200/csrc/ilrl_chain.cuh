@@ -1145,8 +1145,8 @@ __device__ __forceinline__ void pgs_sweeps(SM& sm, const float* gscr, int e, int
 // the rows of the warp's other envs.  gscr_tile: overflow-row scratch of env 0 of this CTA's tile.
 // SELFC: sc_tile = the self-collision scratch of env 0 of this CTA's tile (gp / sd / wr already offset to it).
 template <bool TERR = false, bool SELFC = false, class SM>
-__device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e, int tid, int role, bool steps, float dt,
-                                        Prof& pf, const Terrain* terr = nullptr, const SelfC* sc_tile = nullptr) {
+__device__ __forceinline__ int substep(Base& b, SM& sm, float* gscr_tile, int e, int tid, int role, bool steps, float dt,
+                                       Prof& pf, const Terrain* terr = nullptr, const SelfC* sc_tile = nullptr) {
   constexpr int RSM = SM::RSM;
   constexpr unsigned qm = FULLMASK, wm = FULLMASK;
   float* gscr = gscr_tile + (size_t)e * (GROWS * RW);
@@ -1455,15 +1455,16 @@ __device__ __forceinline__ void substep(Base& b, SM& sm, float* gscr_tile, int e
   }
   __syncwarp(qm);
   pf.mark(PF_INTEG);
+  return nrows;   // (the env's constraint rows of this substep: the cost key of the env-to-warp grouping)
 }
 
-// ---- state movement between HBM (SoA phys[47][n]), the link records and a replicated full Phys
+// ---- state movement between HBM (one row of ILRL_PHYS_STRIDE words per env), the link records and a replicated full Phys
 __device__ __forceinline__ void load_base(const float* phys, int n, int i, Base& b) {
-  const float* p = phys + i;
+  const float* p = phys + (size_t)i * ILRL_PHYS_STRIDE;
 #pragma unroll
-  for (int k = 0; k < 3; k++) { b.p[k] = p[k * n]; b.v[k] = p[(7 + k) * n]; b.w[k] = p[(10 + k) * n]; }
+  for (int k = 0; k < 3; k++) { b.p[k] = p[k]; b.v[k] = p[7 + k]; b.w[k] = p[10 + k]; }
 #pragma unroll
-  for (int k = 0; k < 4; k++) b.quat[k] = p[(3 + k) * n];
+  for (int k = 0; k < 4; k++) b.quat[k] = p[3 + k];
 }
 // benign state for the lanes of an env that does not step: upright at rest, zero joint state and torques
 template <class SM>
@@ -1482,12 +1483,12 @@ __device__ __forceinline__ void dummy_state(SM& sm, int e, int tid, Base& b) {
 // writes the same values).  Two steps so that the loads of a tile's head are all in flight before the first is consumed.
 template <class SM>
 __device__ __forceinline__ void load_links(const float* phys, int n, int i, const SM& sm, int role, float* qv, float* qdv) {
-  const float* p = phys + i;
+  const float* p = phys + (size_t)i * ILRL_PHYS_STRIDE;
 #pragma unroll
   for (int c = 0; c < NL; c++) {
     const int j = c < 3 ? c : tables(sm).lc[role][c - 3].j;
-    qv[c] = j >= 0 ? p[(13 + j) * n] : 0.f;
-    qdv[c] = j >= 0 ? p[(30 + j) * n] : 0.f;
+    qv[c] = j >= 0 ? p[13 + j] : 0.f;
+    qdv[c] = j >= 0 ? p[30 + j] : 0.f;
   }
 }
 template <class SM>
@@ -1538,19 +1539,19 @@ __device__ __forceinline__ void scatter(const Phys& ps, SM& sm, int e, int qb, i
 }
 // store a replicated Phys: the 47 words are dealt to the 4 lanes
 __device__ __forceinline__ void store_phys(float* phys, int n, int i, int role, const Phys& ps) {
-  float* p = phys + i;
+  float* p = phys + (size_t)i * ILRL_PHYS_STRIDE;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
-    if (((0 + k) & 3) == role) p[(0 + k) * n] = ps.p[k];
-    if (((7 + k) & 3) == role) p[(7 + k) * n] = ps.v[k];
-    if (((10 + k) & 3) == role) p[(10 + k) * n] = ps.w[k];
+    if (((0 + k) & 3) == role) p[0 + k] = ps.p[k];
+    if (((7 + k) & 3) == role) p[7 + k] = ps.v[k];
+    if (((10 + k) & 3) == role) p[10 + k] = ps.w[k];
   }
 #pragma unroll
-  for (int k = 0; k < 4; k++) if (((3 + k) & 3) == role) p[(3 + k) * n] = ps.quat[k];
+  for (int k = 0; k < 4; k++) if (((3 + k) & 3) == role) p[3 + k] = ps.quat[k];
 #pragma unroll
   for (int k = 0; k < NJ; k++) {
-    if (((13 + k) & 3) == role) p[(13 + k) * n] = ps.q[k];
-    if (((30 + k) & 3) == role) p[(30 + k) * n] = ps.qd[k];
+    if (((13 + k) & 3) == role) p[13 + k] = ps.q[k];
+    if (((30 + k) & 3) == role) p[30 + k] = ps.qd[k];
   }
 }
 

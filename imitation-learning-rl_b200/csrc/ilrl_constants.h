@@ -64,6 +64,11 @@
 
 /* ---- flat state layouts shared by the C-ABI get/set_state calls, the oracle and the tests */
 #define ILRL_PHYS_WORDS 47   /* base pos3, quat4 (x,y,z,w), lin vel3, ang vel3 (world), q[17], qd[17] */
+/* Resident state in HBM: one row per env (env-major), rows 16-byte aligned so that the four lanes of an env move it with
+ * 128-bit accesses and a row can be reached through the cost-grouping permutation without losing coalescing. */
+#define ILRL_PHYS_STRIDE 48
+#define ILRL_ENV_STRIDE 28
+#define ILRL_JT_STRIDE 36
 enum {
   ILRL_E_FRAME = 0, ILRL_E_CLIP, ILRL_E_T, ILRL_E_TARGET_X, ILRL_E_TARGET_Y, ILRL_E_START_X, ILRL_E_START_Y,
   ILRL_E_SEP_X, ILRL_E_SEP_Y, ILRL_E_SEP_Z, ILRL_E_ROBOT_X, ILRL_E_ROBOT_Y, ILRL_E_HLDEG, ILRL_E_WALK_X,

@@ -203,6 +203,10 @@ int ilrl_set_forced_reset_noise(ilrl_env* env, const float* noise17_dev);
 /* Mode 2: read / overwrite the per-env jointTarget [N,34]. */
 int ilrl_get_joint_target(ilrl_env* env, float* jt_dev, void* stream);
 int ilrl_set_joint_target(ilrl_env* env, const float* jt_dev, void* stream);
+/* Measurement aid: the cost key [N] u8 (0 = most expensive) each env left at its last grouped step and the current
+ * env order [N] i32 of whole-batch steps (K8; identity until a batch of more than one wave has stepped).
+ * Either pointer may be NULL.  Grouping never changes results; ILRL_GROUP_EVERY=0 in the environment switches it off. */
+int ilrl_get_grouping(ilrl_env* env, uint8_t* cost_dev, int32_t* perm_dev, void* stream);
 /* Parity harness (K3): everything ilrl_step does EXCEPT the physics, on the state currently held. */
 int ilrl_step_no_physics(ilrl_env* env, const float* action_dev, float* obs_dev, float* reward_dev, uint8_t* done_dev,
                          float* terms_dev, void* stream);

@@ -655,6 +655,52 @@ def test_step_sequence_equals_k_single_steps(monkeypatch):
     h.close()
 
 
+@pytest.mark.parametrize("mode", ["low", "hier", "hier2"])
+def test_cost_grouping_does_not_change_results(monkeypatch, mode):
+    """Batches of more than one wave step their envs grouped by cost (K8: env ids sorted by the constraint rows of their
+    last substep, re-sorted every few steps).  The grouping must be invisible: outputs of every step, final state and
+    high-level outputs bit-identical with it off, sorting every step, and sorting every third step - in each layout."""
+    n = 9700 if mode == "low" else 5000   # (607 / 313 tiles: more than the resident CTAs of the layouts forced below)
+    steps = 14
+    g = torch.Generator(device="cuda")
+    g.manual_seed(21)
+    acts = [(torch.rand(n, 17, device="cuda", generator=g) * 2 - 1) * (2.5 if t % 4 == 0 else 1.0) for t in range(steps)]
+    hw = 36 if mode == "hier2" else 2
+    hacts = [torch.rand(n, hw, device="cuda", generator=g) * 2 - 1 for t in range(steps)]
+    outs, launches = {}, {}
+    for layout in (("small", "dense4") if mode == "low" else ("small",)):
+        monkeypatch.setenv("ILRL_LAYOUT", layout)
+        for every in ("0", "1", "3"):
+            monkeypatch.setenv("ILRL_GROUP_EVERY", every)
+            env = BatchedHumanoidEnv(n, mode, clips=["motion08_03", "motion09_03"], clip_of_env=np.arange(n, dtype=np.int32) % 2,
+                                     seed=5, auto_reset=True)
+            env.reset()
+            l0 = env.launch_count()
+            rec = []
+            for t in range(steps):
+                if mode != "low":
+                    env.high_step(hacts[t])
+                rec.append(tuple(x.clone() for x in env.step(acts[t])))
+                if mode != "low":
+                    rec.append(tuple(x.clone() for x in env.high_readout()))
+            rec.append(tuple(x.clone() for x in env.get_state()))
+            launches[every] = env.launch_count() - l0
+            perm = torch.empty(n, dtype=torch.int32, device="cuda")
+            cost = torch.empty(n, dtype=torch.uint8, device="cuda")
+            env.L.ilrl_get_grouping(env.h, cost.data_ptr(), perm.data_ptr(), None)
+            assert torch.equal(torch.sort(perm.long()).values, torch.arange(n, device="cuda")), "not a permutation"
+            if every != "0":   # sorted by the key the envs held when it was last sorted: with every=1 that is `cost` of the step before
+                assert int(cost.max()) <= 63 and not torch.equal(perm.long(), torch.arange(n, device="cuda"))
+            outs[(layout, every)] = rec
+            env.close()
+        assert launches["1"] - launches["0"] == steps and launches["3"] - launches["0"] == (steps + 2) // 3, launches
+        for every in ("1", "3"):
+            for x, y in zip(outs[(layout, "0")], outs[(layout, every)]):
+                for u, v in zip(x, y):
+                    assert torch.equal(u, v), (mode, layout, every)
+        assert int(sum(r[2].sum() for r in outs[(layout, "0")][:-1] if len(r) == 4)) > 0   # episodes ended and auto-reset
+
+
 def test_both_shared_memory_layouts_are_bit_identical(monkeypatch):
     """The step kernel has two shared-memory layouts picked from the batch size (all on chip / 3 CTAs per SM with rows
     spilling to the global scratch beyond 8).  They must agree bit for bit, including envs with many rows."""

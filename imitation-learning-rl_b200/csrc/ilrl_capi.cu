@@ -1039,16 +1039,19 @@ struct DeviceGuard {
   if ((env)->serving) return fail(env, ILRL_ERR_STATE, "the handle is serving (ilrl_serve_begin): call ilrl_serve_end first"); \
   ON_DEVICE_RAW(env)
 
-// step-kernel launch, optionally with the programmatic-stream-serialization attribute (see the kernel's prologue)
+// step-kernel launch, optionally with the programmatic-stream-serialization attribute (see the kernel's prologue).
+// Only where it pays: with the 3-CTA-per-SM layout (and the terrain instantiation, which uses it) the early-resident CTAs
+// of the next step crowd onto the SMs that finished first - three CTAs on some SMs, none on others - and the step gets
+// SLOWER (6000 / 7000 envs -4 / -3 %, terrain 4096 envs -9 %); self-collision: no difference (tools/pdl_ab.py).
 static bool g_pdl = [] { const char* e = getenv("ILRL_PDL"); return !(e && e[0] == '0'); }();
 template <class K>
-static void launch_step(K kernel, int grid, size_t smem, cudaStream_t st, const StepArgs& a) {
+static void launch_step(K kernel, int grid, size_t smem, cudaStream_t st, const StepArgs& a, bool pdl = false) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(QT); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = (g_pdl && pdl) ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kernel, a);
 }
 
@@ -1344,17 +1347,17 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
     else if (env->self_on) launch_step(step_kernel<2, SmemSelf, false, true>, qblk, sizeof(SmemSelf), st, a);
     else launch_step(step_kernel<0, SmemLarge, true>, qblk, sizeof(SmemLarge), st, a);
   } else if (env->layout == 2) {
-    if (md == 0) launch_step(step_kernel<0, SmemDense4>, qblk, sizeof(SmemDense4), st, a);
-    else if (md == 1) launch_step(step_kernel<1, SmemDense4>, qblk, sizeof(SmemDense4), st, a);
-    else launch_step(step_kernel<2, SmemDense4>, qblk, sizeof(SmemDense4), st, a);
+    if (md == 0) launch_step(step_kernel<0, SmemDense4>, qblk, sizeof(SmemDense4), st, a, true);
+    else if (md == 1) launch_step(step_kernel<1, SmemDense4>, qblk, sizeof(SmemDense4), st, a, true);
+    else launch_step(step_kernel<2, SmemDense4>, qblk, sizeof(SmemDense4), st, a, true);
   } else if (env->layout == 1) {
     if (md == 0) launch_step(step_kernel<0, SmemLarge>, qblk, sizeof(SmemLarge), st, a);
     else if (md == 1) launch_step(step_kernel<1, SmemLarge>, qblk, sizeof(SmemLarge), st, a);
     else launch_step(step_kernel<2, SmemLarge>, qblk, sizeof(SmemLarge), st, a);
   } else {
-    if (md == 0) launch_step(step_kernel<0, SmemSmall>, qblk, sizeof(SmemSmall), st, a);
-    else if (md == 1) launch_step(step_kernel<1, SmemSmall>, qblk, sizeof(SmemSmall), st, a);
-    else launch_step(step_kernel<2, SmemSmall>, qblk, sizeof(SmemSmall), st, a);
+    if (md == 0) launch_step(step_kernel<0, SmemSmall>, qblk, sizeof(SmemSmall), st, a, true);
+    else if (md == 1) launch_step(step_kernel<1, SmemSmall>, qblk, sizeof(SmemSmall), st, a, true);
+    else launch_step(step_kernel<2, SmemSmall>, qblk, sizeof(SmemSmall), st, a, true);
   }
   env->launches++;
   CK(cudaGetLastError());

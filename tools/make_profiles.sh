@@ -18,5 +18,6 @@ rows = list(csv.reader(open('gpurun_out/$1_raw.csv')))
 h, u, d = rows[0], rows[1], rows[2:]
 sc = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6}
 tot = [float(r[h.index('dram__bytes_read.sum')]) * sc[u[h.index('dram__bytes_read.sum')]] + float(r[h.index('dram__bytes_write.sum')]) * sc[u[h.index('dram__bytes_write.sum')]] for r in d]
-json.dump({"dram_bytes_per_launch": int(sum(tot) / len(tot)), "source": "${P}_step_kernel_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum, mean of %d steady-state launches, N=4096)" % len(tot)}, open('profiles/step_kernel_traffic.json', 'w'))
+wi = [float(r[h.index('smsp__inst_executed.sum')]) for r in d]
+json.dump({"dram_bytes_per_launch": int(sum(tot) / len(tot)), "warp_inst_per_env_step": round(sum(wi) / len(wi) / 4096, 1), "source": "${P}_step_kernel_ncu.md (dram__bytes_read.sum + dram__bytes_write.sum, smsp__inst_executed.sum; mean of %d steady-state launches, N=4096)" % len(tot)}, open('profiles/step_kernel_traffic.json', 'w'))
 PY

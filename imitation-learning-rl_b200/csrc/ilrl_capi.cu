@@ -248,7 +248,9 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
 #pragma unroll 1
     for (int sub = 0; sub < ILRL_SUBSTEPS; sub++) {
       pf.mark(sub == 0 ? chain::PF_HEAD : chain::PF_INTEG);
+#ifndef ILRL_NO_SUBSTEP_BAR
       __syncthreads();
+#endif
       pf.mark(chain::PF_BARRIER);
       const int nrows = chain::substep<TERR, SELFC>(b, sm, gscr_tile, e, tid, role, active,
                                                     (float)(ILRL_FRAME_DT / ILRL_SUBSTEPS), pf, TERR ? &a.terr : nullptr,
@@ -256,7 +258,9 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
       if (sub == ILRL_SUBSTEPS - 1) rows_last = nrows;
     }
   }
+#ifndef ILRL_NO_TAIL_BAR
   __syncthreads();   // the once-per-step tail (4 k instructions) is entered together as well: +3 % at 65536 envs
+#endif
   pf.mark(chain::PF_BARRIER);
   if (active) {
     chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);

@@ -547,7 +547,7 @@ def run_ours(args):
                           "scaling": "strong" if WORKLOADS[name]["total"] else "weak",
                           "mean_episode_len": float(r2["stats"][2] / max(r2["stats"][0], 1))}
         try:
-            extra["cfg5_rollout16384x8"] = rollout_measure(rank, world, local_rank, hier=False, K=max(3, min(K, 50)), W=3)
+            extra["cfg5_rollout16384x8"] = rollout_measure(rank, world, local_rank, hier=False, K=max(3, min(K, 50)), W=5, blocks=5)
         except Exception as e:  # the widened row must never take the contract line down with it
             extra["cfg5_rollout16384x8"] = {"error": repr(e)}
     clk = clocks.stop() if clocks else None
@@ -643,7 +643,7 @@ def _quiet_stdout():
 EMIT = print
 
 
-def rollout_measure(rank, world, local_rank, hier, K, W):
+def rollout_measure(rank, world, local_rank, hier, K, W, blocks=1):
     """On-device rollout collection (BASELINE cfg 5): 16384 envs x 8 steps per GPU per iteration (= 1 M env-steps per
     iteration on 8 GPUs): fused tcgen05 policy / value / sampling kernel -> fused env step, 2 launches per step captured
     in one CUDA graph, + GAE (ilrl_gae).  hier=True: the same for the hierarchical env (both policies on device, 5 launches
@@ -666,25 +666,29 @@ def rollout_measure(rank, world, local_rank, hier, K, W):
     for _ in range(W):
         col.collect()
     env.stats()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(K):
-        batch = col.collect()
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    block_ms = []
+    for _ in range(blocks):   # median of `blocks` timed blocks of exactly K iterations (max over ranks per block)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(K):
+            batch = col.collect()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        block_ms.append(float(t_ms.item()))
     st = ilrl_b200.stats.allreduce_stats(env.stats())
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    ms = float(t_ms.item())
+    ms = sorted(block_ms)[len(block_ms) // 2]
     summ = ilrl_b200.stats.summarize(st)
     out = {"metric": "rollout env-steps/sec (%spolicy + physics + reward + GAE on device)" % ("both policies: " if hier else ""),
            "value": world * n * T * K / (ms * 1e-3), "unit": UNIT, "steps": K, "warmup": W, "ms_per_step": ms / K,
+           "blocks": blocks, "block_ms": [round(b, 3) for b in block_ms],
            "workload": ("on-device PPO rollout collection, hierarchical env: %d envs x %d low-level steps per GPU per "
                         "iteration, selected_motion=1, step_per_level=5, 44-256-256-2 and 70-256-256-17 tanh Gaussian "
                         "policies + value nets (fused tcgen05 kernel), gamma 0.99 lambda 0.9" % (n, T)) if hier else

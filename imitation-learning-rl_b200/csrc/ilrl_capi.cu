@@ -131,6 +131,17 @@ __device__ __forceinline__ void quad_smem_init(SM& sm) {
 #pragma unroll
     for (int k = 0; k < PER; k++) { const int t = threadIdx.x + k * QT; if (t < chain::TABLE_WORDS) dst[t] = v[k]; }
   }
+  if constexpr (SM::HSM) {   // the per-link part only (layouts that read the rest of the tables through L1)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&chain::kTables.lc[0][0]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.H.lc[0][0]);
+    constexpr int PER = (chain::HOT_LC_WORDS + QT - 1) / QT;
+    uint32_t v[PER];
+#pragma unroll
+    for (int k = 0; k < PER; k++) { const int t = threadIdx.x + k * QT; v[k] = t < chain::HOT_LC_WORDS ? __ldg(src + t) : 0u; }
+#pragma unroll
+    for (int k = 0; k < PER; k++) { const int t = threadIdx.x + k * QT; if (t < chain::HOT_LC_WORDS) dst[t] = v[k]; }
+    if (threadIdx.x < 9) sm.H.Q[threadIdx.x] = chain::kTables.Q[threadIdx.x];
+  }
   if constexpr (SM::SELF) {   // wide row 0 of every env must hold finite numbers (lanes past their count re-evaluate it)
     for (int k = 0; k < chain::WRW / 4; k++) sm.S.wr[threadIdx.x >> 2][(threadIdx.x & 3) * (chain::WRW / 4) + k] = 0.f;
     for (int p = threadIdx.x; p < chain::NSELF; p += QT) {   // the pair table, packed
@@ -149,7 +160,7 @@ __device__ __forceinline__ void set_torques(SM& sm, int e, int tid, int role, co
 #pragma unroll
   for (int c = 0; c < chain::NL; c++) {
     float* rec = chain::link_rec(sm, c, e, tid);
-    const chain::LinkC& L = c < 3 ? chain::tables(sm).lc[4][c] : chain::tables(sm).lc[role][c - 3];
+    const chain::LinkC& L = c < 3 ? chain::link_c(sm, 4, c) : chain::link_c(sm, role, c - 3);
     float t = 0.f;
     if (L.j >= 0) t = act ? L.gear * fminf(fmaxf(act[L.motor], -1.f), 1.f) : torque[L.j];
     rec[chain::W_TAU] = t;
@@ -266,6 +277,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
     chain::pose_sums(b, sm, e, tid, role, qm, sumx, sumy, rfx, rfy);
     Phys ps;
     chain::gather(b, sm, e, qb, qm, ps);
+    pf.mark(chain::PF_T_POSE);
     EnvW w;
     {
       const float* ew = a.envf + (size_t)i * ILRL_ENV_STRIDE;
@@ -310,6 +322,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
     if (w.e[ILRL_E_T] >= (float)a.max_timestep) done = true;
     w.e[ILRL_E_EP_RETURN] += reward;
     w.e[ILRL_E_EP_LEN] += 1.f;
+    pf.mark(chain::PF_T_REWARD);
     float* so = &sm.scr[e][0];  // the env's scratch block is free after the substeps: stage the obs row there
     {
       float obs[OBSW];
@@ -344,13 +357,12 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
 #pragma unroll
       for (int t = 0; t < ILRL_TERM_WORDS; t++) if ((t & 3) == role) o_terms[(size_t)i * ILRL_TERM_WORDS + t] = terms[t];
     }
-    if (role == 0) {
-      st_steps = 1.f; st_rew = reward;
+    // (statistics: the four lanes of a quad hold the same values; lane `role` reduces slots = role mod 4 below)
+    st_steps = 1.f; st_rew = reward;
 #pragma unroll
-      for (int t = 0; t < 11; t++) st_terms[t] = terms[t];
-    }
+    for (int t = 0; t < 11; t++) st_terms[t] = terms[t];
     if (done) {
-      if (role == 0) { st_ep = 1.f; st_ret = w.e[ILRL_E_EP_RETURN]; st_len = w.e[ILRL_E_EP_LEN]; }
+      st_ep = 1.f; st_ret = w.e[ILRL_E_EP_RETURN]; st_len = w.e[ILRL_E_EP_LEN];
       if (a.auto_reset) {
         int sf = rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, 0, cl.max_frame - 5);
         float yaw = MODE >= 1 ? (float)rand_int(a.seed, (uint32_t)(i + a.id_base), ctr, -180, 180) : 0.f;
@@ -382,6 +394,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
         }
       }
     }
+    pf.mark(chain::PF_T_OBS);
     if (role == 0) {
       if (MODE >= 1) a.high_flags[i] = hflags;
       a.rng[i] = ctr;
@@ -399,6 +412,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
 #pragma unroll
       for (int k = 0; k < ILRL_ENV_WORDS; k++) if ((k & 3) == role) ew[k] = w.e[k];
     }
+    pf.mark(chain::PF_T_STORE);
   }
   // observations: only envs that stepped write their row (pending hier envs keep theirs).  Each warp stores the rows of
   // its own 8 envs (one contiguous 2240-byte block of the caller's array) from the staging area, 8 bytes per lane.
@@ -406,7 +420,7 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
     const unsigned okmask = __ballot_sync(0xffffffffu, write_obs);   // (includes the staging writes' __syncwarp)
     const int e0 = e & ~7, lane = tid & 31;
     float* const oall = a.obs + (size_t)ko * a.n * OBSW;
-#pragma unroll 1
+#pragma unroll 3   // (three rounds of loads in flight: +0.2 % at 4096 envs, +0.9 % at 16384 / 65536; 5 or 9: the same)
     for (int f0 = 0; f0 < 8 * (OBSW / 2); f0 += 32) {
       const int f = f0 + lane, r = min(f / (OBSW / 2), 7), c2 = f - r * (OBSW / 2);
       const int ir = __shfl_sync(0xffffffffu, i, 4 * r);   // (without grouping the 8 rows are one contiguous block)
@@ -419,12 +433,14 @@ __device__ __forceinline__ void step_tile(const StepArgs& a, SM& sm, const int t
     float v[16] = {st_ep, st_ret, st_len, st_steps, st_rew};
 #pragma unroll
     for (int t = 0; t < 11; t++) v[5 + t] = st_terms[t];
+    // slot 4 m + role is summed over the warp's 8 envs by the lanes of that role (12 shuffles instead of 48; the same
+    // butterfly over the same envs, so the sums are the ones lane 0 used to form alone)
 #pragma unroll
-    for (int t = 0; t < 16; t++) {
-      float x = v[t];
+    for (int m = 0; m < 4; m++) {
+      float x = role == 0 ? v[4 * m] : role == 1 ? v[4 * m + 1] : role == 2 ? v[4 * m + 2] : v[4 * m + 3];
 #pragma unroll
-      for (int o = 16; o >= 4; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);  // (lanes 1..3 of a quad hold 0)
-      if ((tid & 31) == 0 && x != 0.f) atomicAdd(a.stats + t, (double)x);
+      for (int o = 16; o >= 4; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+      if ((tid & 31) < 4 && x != 0.f) atomicAdd(a.stats + 4 * m + role, (double)x);
     }
   }
   pf.mark(chain::PF_TAIL);

@@ -203,6 +203,12 @@ struct Layout {
   static constexpr int ROWSTRIDE = RSM_ * RW + 4;  // env stride in words: = 4 (mod 32)
   static constexpr int BRW = BRW_;               // words per body record (20: room for padding; 16: dense)
   static constexpr bool TSM = TSM_;              // model tables staged in shared memory
+#ifndef ILRL_HOT_TABLES
+#define ILRL_HOT_TABLES 1
+#endif
+  // layouts that leave the tables in global memory still stage the per-link part (what the FK pass reads for every link
+  // of every substep, 1.5 KB) when it fits without costing a resident CTA (not next to the self-collision arrays)
+  static constexpr bool HSM = !TSM_ && !SELF_ && ILRL_HOT_TABLES;
   static constexpr int LANE = LANE_;             // lane stride of the body view in the per-env scratch block (words)
 };
 #ifndef ILRL_LARGE_RSM  // (overridable for layout experiments)
@@ -235,7 +241,10 @@ template <int BRW, int LANE> constexpr int scr_words() {
 }
 
 struct NoTables {};
+struct NoHot {};
 struct NoSelf {};
+struct alignas(16) HotTables { LinkC lc[5][4]; float Q[9]; float pad[3]; };   // Tables::lc + Tables::Q
+constexpr int HOT_LC_WORDS = sizeof(LinkC) * 20 / 4;
 struct alignas(16) SelfSm {
   float gp[QE][SELF_GP];      // sphere centres relative to the torso (world axes), published by the FK pass
   uint32_t mask[QE][4];       // candidate pairs (66 bits), set by the pair tests of the warp's pool
@@ -246,7 +255,7 @@ struct alignas(16) SelfSm {
 template <class LY>
 struct __align__(16) SmemT {
   static constexpr int RSM = LY::RSM, ROWSTRIDE = LY::ROWSTRIDE, BRW = LY::BRW, ES = scr_words<LY::BRW, LY::LANE>();
-  static constexpr bool TSM = LY::TSM;
+  static constexpr bool TSM = LY::TSM, HSM = LY::HSM;
   static constexpr bool SELF = LY::SELF;
   static constexpr int SCR_LANE = LY::LANE;
   static_assert(2 * BRW <= SCR_LANE, "two body records per lane");
@@ -259,6 +268,7 @@ struct __align__(16) SmemT {
   float L0[21][QE];            // Cholesky factor of the base articulated inertia
   float sph[NS][3][QE];        // contact candidates: x, y, z - r relative to the torso origin (distance = base z + that)
   typename std::conditional<TSM, Tables, NoTables>::type T;
+  typename std::conditional<HSM, HotTables, NoHot>::type H;
   typename std::conditional<LY::SELF, SelfSm, NoSelf>::type S;
   static_assert((sizeof(float) * QE * ROWSTRIDE) % 16 == 0 && (sizeof(float) * LKW) % 16 == 0 && BRW % 4 == 0 && ES % 4 == 0,
                 "float4 alignment of the shared-memory records");
@@ -277,12 +287,23 @@ __device__ __forceinline__ const Tables& tables(const SM& sm) {
   if constexpr (SM::TSM) return sm.T; else return kTables;
 }
 
+// the per-link constants (record k of chain ch) and the fixed lwaist / pelvis rotation: shared memory in every layout
+// but the self-collision one
+template <class SM>
+__device__ __forceinline__ const LinkC& link_c(const SM& sm, int ch, int k) {
+  if constexpr (SM::HSM) return sm.H.lc[ch][k]; else return tables(sm).lc[ch][k];
+}
+template <class SM>
+__device__ __forceinline__ const float* fixed_rot(const SM& sm) {
+  if constexpr (SM::HSM) return sm.H.Q; else return tables(sm).Q;
+}
+
 constexpr unsigned FULLMASK = 0xffffffffu;
 
 // Phase timer of the measurement build (-DILRL_PROF, tools/warp_profile.py): lane 0 of every warp accumulates clock64()
 // intervals per phase.  In the product build it is an empty object and every call vanishes.
 enum { PF_HEAD = 0, PF_FK, PF_INWARD, PF_OUTWARD, PF_ROWS, PF_PGS, PF_INTEG, PF_TAIL, PF_BARRIER, PF_TOTAL,
-       PF_MAXROWS, PF_WORDS = 16 };
+       PF_MAXROWS, PF_T_POSE, PF_T_REWARD, PF_T_OBS, PF_T_STORE, PF_WORDS = 16 };  // (PF_T_*: parts of the tail; PF_TAIL = its rest)
 #ifdef ILRL_PROF
 struct Prof {
   long long* p = nullptr;
@@ -618,7 +639,7 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
   V3 oc = mk(0.f, 0.f, 0.f);
   SV Vp = V0;
   float sx = 0.f, sy = 0.f, ssx = 0.f, ssy = 0.f, ex = 0.f, ey = 0.f;
-#pragma unroll 1
+#pragma unroll 1   // (the pose-only pass as well: unrolled, its three inlined copies cost more instruction fetch than they save, -3 %)
   for (int c = 0; c < NL; c++) {
     if (c == 3 && role >= 2) {  // the arms hang off the torso
 #pragma unroll
@@ -626,12 +647,12 @@ __device__ __forceinline__ void fk_phase(const Base& b, SM& sm, int e, int tid, 
       oc = mk(0.f, 0.f, 0.f);
       Vp = V0;
     }
-    const LinkC& L = c < 3 ? T.lc[4][c] : T.lc[role][c - 3];
+    const LinkC& L = c < 3 ? link_c(sm, 4, c) : link_c(sm, role, c - 3);
     float* rec = link_rec(sm, c, e, tid);
     oc = oc + mv(Rc, rd3(L.pre));
     if (L.rot) {
       float Rn[9];
-      mm(Rc, T.Q, Rn);
+      mm(Rc, fixed_rot(sm), Rn);
 #pragma unroll
       for (int i = 0; i < 9; i++) Rc[i] = Rn[i];
     }
@@ -1486,7 +1507,7 @@ __device__ __forceinline__ void load_links(const float* phys, int n, int i, cons
   const float* p = phys + (size_t)i * ILRL_PHYS_STRIDE;
 #pragma unroll
   for (int c = 0; c < NL; c++) {
-    const int j = c < 3 ? c : tables(sm).lc[role][c - 3].j;
+    const int j = c < 3 ? c : link_c(sm, role, c - 3).j;
     qv[c] = j >= 0 ? p[13 + j] : 0.f;
     qdv[c] = j >= 0 ? p[30 + j] : 0.f;
   }

@@ -41,7 +41,8 @@ if __name__ == "__main__":
     buf = np.zeros((nw, 16), np.int64)
     env.L.ilrl_debug_profile.argtypes = [C.c_void_p, C.c_void_p]
     env.L.ilrl_debug_profile(env.h, buf.ctypes.data)   # clear
-    names = ["head", "fk", "inward", "outward", "rows", "pgs", "integ", "tail", "barrier", "total", "maxrows"]
+    names = ["head", "fk", "inward", "outward", "rows", "pgs", "integ", "tail", "barrier", "total", "maxrows",
+             "t_pose", "t_reward", "t_obs", "t_store"]   # parts of the tail ("tail" = its rest: obs rows out + statistics)
     K = 50
     acc_mean = np.zeros(16)
     acc_slow = np.zeros(16)

@@ -794,7 +794,9 @@ __device__ __forceinline__ void build_limit_row(const SM& sm, const Tables& T, i
   const float* rec0 = link_rec_of(sm, L, c, e, qb);
   const float q_ = rec0[W_Q], nu = rec0[W_NU];
   float pen, dir;
-  if (q_ - kJointLo[j] <= 0.f) { pen = q_ - kJointLo[j]; dir = 1.f; } else { pen = kJointHi[j] - q_; dir = -1.f; }
+  const LinkC& K = c < 3 ? link_c(sm, 4, c) : link_c(sm, L, c - 3);   // (the joint's limits from the staged per-link table)
+  const float lo = K.lo, hi = K.hi;
+  if (q_ - lo <= 0.f) { pen = q_ - lo; dir = 1.f; } else { pen = hi - q_; dir = -1.f; }
   float4* r4 = reinterpret_cast<float4*>(row);
   r4[2] = make_float4(0.f, 0.f, 0.f, __int_as_float(c >= 3 ? L : -1));
   r4[3] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -263,30 +263,37 @@ __device__ __forceinline__ void body_inertia_bias(const Work& k, int b, SV V, In
                      kBodyInertia[3 * b + 2], V, I, pb);
 }
 
-// Cholesky of the 6x6 SPD base inertia [[A,B],[B^T,C]] -> packed lower L (row-major: L[i*(i+1)/2 + j])
-__device__ __forceinline__ void chol6(const Inertia& I, float* L) {
-  float M[6][6];
-  M[0][0] = I.A[0]; M[0][1] = I.A[1]; M[0][2] = I.A[2]; M[1][1] = I.A[3]; M[1][2] = I.A[4]; M[2][2] = I.A[5];
-  M[3][3] = I.C[0]; M[3][4] = I.C[1]; M[3][5] = I.C[2]; M[4][4] = I.C[3]; M[4][5] = I.C[4]; M[5][5] = I.C[5];
+// Cholesky of the 6x6 SPD base inertia [[A,B],[B^T,C]] -> packed lower L (row-major: L[i*(i+1)/2 + j]), in place on the
+// packed lower triangle, one column per template instance: every index is a compile-time constant, so the 21 numbers
+// stay in registers (with run-time loop bounds the loops were left partly rolled and the arrays - 57 words - lived in
+// local memory: 28 local stores and 13 dependent local loads per substep and lane).  Same operations in the same
+// order as the textbook left-looking loop: identical results.
+template <int J>
+__device__ __forceinline__ void chol6_column(float (&a)[21]) {
+  constexpr int rj = J * (J + 1) / 2;
+  float sdiag = a[rj + J];
 #pragma unroll
-  for (int i = 0; i < 3; i++)
+  for (int c = 0; c < J; c++) sdiag -= a[rj + c] * a[rj + c];
+  const float inv = rsqrtf(fmaxf(sdiag, 1e-20f));
+  a[rj + J] = inv;  // store the INVERSE of the diagonal
 #pragma unroll
-    for (int j = 0; j < 3; j++) M[i][3 + j] = I.B[i * 3 + j];
+  for (int i = J + 1; i < 6; i++) {
+    const int ri = i * (i + 1) / 2;
+    float t = a[ri + J];
 #pragma unroll
-  for (int j = 0; j < 6; j++) {
-    float sdiag = M[j][j];
-#pragma unroll
-    for (int c = 0; c < j; c++) sdiag -= L[j * (j + 1) / 2 + c] * L[j * (j + 1) / 2 + c];
-    float inv = rsqrtf(fmaxf(sdiag, 1e-20f));
-    L[j * (j + 1) / 2 + j] = inv;  // store the INVERSE of the diagonal
-#pragma unroll
-    for (int i = j + 1; i < 6; i++) {
-      float t = M[j][i];  // symmetric: M[i][j] == M[j][i]
-#pragma unroll
-      for (int c = 0; c < j; c++) t -= L[i * (i + 1) / 2 + c] * L[j * (j + 1) / 2 + c];
-      L[i * (i + 1) / 2 + j] = t * inv;
-    }
+    for (int c = 0; c < J; c++) t -= a[ri + c] * a[rj + c];
+    a[ri + J] = t * inv;
   }
+}
+__device__ __forceinline__ void chol6(const Inertia& I, float (&L)[21]) {
+  // lower triangle of the symmetric matrix: rows 0-2 = A, rows 3-5 = [B^T | C]
+  L[0] = I.A[0];
+  L[1] = I.A[1]; L[2] = I.A[3];
+  L[3] = I.A[2]; L[4] = I.A[4]; L[5] = I.A[5];
+  L[6] = I.B[0]; L[7] = I.B[3]; L[8] = I.B[6]; L[9] = I.C[0];
+  L[10] = I.B[1]; L[11] = I.B[4]; L[12] = I.B[7]; L[13] = I.C[1]; L[14] = I.C[3];
+  L[15] = I.B[2]; L[16] = I.B[5]; L[17] = I.B[8]; L[18] = I.C[2]; L[19] = I.C[4]; L[20] = I.C[5];
+  chol6_column<0>(L); chol6_column<1>(L); chol6_column<2>(L); chol6_column<3>(L); chol6_column<4>(L); chol6_column<5>(L);
 }
 // x = M^-1 b with the factor above (diagonal entries hold 1/L_jj)
 __device__ __forceinline__ SV chol6_solve(const float* L, SV b) {

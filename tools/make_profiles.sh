@@ -9,8 +9,9 @@ ncu -i $REP --page source --csv --print-source sass --launch-skip 0 --launch-cou
 rm -rf /tmp/cub && mkdir -p /tmp/cub && (cd /tmp/cub && cuobjdump -xelf all /root/repo/imitation-learning-rl_b200/libilrl_b200.so >/dev/null && for f in *.cubin; do nvdisasm -gi -c $f 2>/dev/null >> all_gi.sass; done)
 python tools/ncu_summary.py gpurun_out/$1_raw.csv "$2 — ncu --set full of \`step_kernel<0>\`, 3 steady-state launches (skip 400), N = 4096 envs, B200" "ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 400 -c 3 python bench.py --steps 500 --warmup 5 --no-cpu-baseline" > ${P}_step_kernel_ncu.md
 python tools/ncu_lines.py gpurun_out/$1_cs.csv 50 > ${P}_step_kernel_lines.txt
-L=$(grep -n "^__device__ __forceinline__ void substep" imitation-learning-rl_b200/csrc/ilrl_chain.cuh | cut -d: -f1)
-python tools/ncu_callsites.py gpurun_out/$1_sass.csv /tmp/cub/all_gi.sass "step_kernelILi0,LayoutILi42E" ilrl_chain.cuh $L 1100 30 > ${P}_step_kernel_callsites.txt
+L=$(grep -n "^__device__ __forceinline__ int substep(" imitation-learning-rl_b200/csrc/ilrl_chain.cuh | cut -d: -f1)
+H=$(awk -v l=$L 'NR>=l && /^}/ {print NR; exit}' imitation-learning-rl_b200/csrc/ilrl_chain.cuh)   # closing brace of substep()
+python tools/ncu_callsites.py gpurun_out/$1_sass.csv /tmp/cub/all_gi.sass "step_kernelILi0,LayoutILi42E" ilrl_chain.cuh $L $H 30 > ${P}_step_kernel_callsites.txt
 cp gpurun_out/$3.json ${P}_bench.json; cp gpurun_out/$3_ref.json ${P}_bench_reference_arm.json; cp gpurun_out/$4.csv ${P}_launches.csv
 python - <<PY
 import csv, json

@@ -1148,14 +1148,14 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
     // Layout.  The step kernel is persistent: resident CTAs (SMs x CTAs per SM) pull 16-env tiles,
     // so a step takes x = tiles / resident CTAs "rounds", the last one partly filled.  Being latency-bound, a round costs
     // about the same however full it is; what differs between the layouts is how many envs a round holds (4736 / 7104 /
-    // 9472 on 148 SMs) and how long it takes.  Measured on B200 (profiles/r2_layout_sweep.txt), time of a step ~
-    // floor(x) R + a + b frac(x) for x < 8 and x Rinf beyond (us): on-chip R 59.6 a 65 b 17.5 Rinf 63.5; dense R 78 a 72.5
-    // b 40.9 Rinf 84; dense4 R 88.1 a 81.9 b 37.5 Rinf 99.5.  Estimate all three, take the smallest.
+    // 9472 on 148 SMs) and how long it takes.  Measured on B200 (profiles/r2_v6_layout_sweep.txt), time of a step ~
+    // floor(x) R + a + b frac(x) for x < 8 and x Rinf beyond (us, least squares): on-chip R 53.6 a 54.8 b 23.3 Rinf 57.5;
+    // dense R 69.8 a 57.8 b 44.2 Rinf 73.2; dense4 R 76.8 a 67.2 b 48.1 Rinf 83.4.  Estimate all three, take the smallest.
     // Measured (M env-steps/s: on chip / dense / dense4; * = chosen by the estimate):
-    //    2048: 27.1* / 24.0 / 23.3      4096: 52.6* / 45.8 / 44.1     5120: 40.6 / 53.0* / 51.0    6144: 46.8 / 60.6* / 58.6
-    //    8192: 59.6 / 52.3 / 73.5*     10240: 54.7 / 59.8* / 59.2    12288: 62.4 / 68.1* / 67.1   16384: 64.3 / 67.9 / 83.0*
-    //   20480: 65.8 / 75.0 / 77.5*     24576: 67.0 / 74.1 / 85.9*    32768: 72.1 / 77.1 / 87.3*   65536: 74.3 / 83.0 / 93.7*
-    //  131072: 75.3 / 85.2 / 95.1*
+    //    2048: 28.8* / 25.5 / 22.2      4096: 56.3* / 49.6 / 42.9     5120: 48.4 / 56.4* / 51.6    6144: 55.0 / 64.6* / 61.4
+    //    8192: 67.7 / 66.0 / 79.2*     10240: 63.1 / 74.4* / 74.5    12288: 71.4 / 79.1 / 82.2*   16384: 72.8 / 82.2 / 96.8*
+    //   20480: 73.7 / 87.2 / 92.2*     24576: 74.9 / 85.8 / 101.9*   32768: 81.6 / 88.3 / 103.7*  65536: 82.8 / 96.0 / 112.5*
+    //  131072: 83.3 / 98.2 / 113.6*
     // ILRL_LAYOUT=small|large|dense4 overrides (measurement aid).
     cudaDeviceProp prop;
     CKC(cudaGetDeviceProperties(&prop, cfg->device));
@@ -1181,8 +1181,8 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
       env->layout = (o[0] == 'l' || o[0] == 'L') ? 1 : (o[0] == 'd' || o[0] == 'D') ? 2 : 0;
     } else {
       const float tiles = (float)((n + QE - 1) / QE);
-      const float R[3] = {59.6f, 78.f, 88.1f}, A[3] = {65.f, 72.5f, 81.9f}, B[3] = {17.5f, 40.9f, 37.5f},
-                  Rinf[3] = {63.5f, 84.f, 99.5f};
+      const float R[3] = {53.6f, 69.8f, 76.8f}, A[3] = {54.8f, 57.8f, 67.2f}, B[3] = {23.3f, 44.2f, 48.1f},
+                  Rinf[3] = {57.5f, 73.2f, 83.4f};
       const int grid[3] = {env->grid_small, env->grid_large, env->grid_dense4};
       float best = 0.f;
       for (int l = 0; l < 3; l++) {

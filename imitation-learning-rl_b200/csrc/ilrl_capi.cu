@@ -1127,6 +1127,7 @@ int ilrl_create(const ilrl_config* cfg, ilrl_env** out) {
   CKC(cudaFuncSetAttribute(step_seq_kernel<SmemLarge>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(step_seq_kernel<SmemDense4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemDense4)));
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemLarge, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
+  CKC(cudaFuncSetAttribute(step_kernel<0, SmemSmall, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSmall)));
   CKC(cudaFuncSetAttribute(physics_only_kernel<SmemLarge, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemLarge)));
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemSelf, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSelf)));
   CKC(cudaFuncSetAttribute(step_kernel<0, SmemSelf, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SmemSelf)));
@@ -1347,9 +1348,10 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
   if (count < 0) count = env->n;
   StepArgs a;
   fill_step_args(env, a, action, obs, reward, done, terms, skip_physics, first, count, part, forced_scalar);
-  // (heightfield terrain / self-collision: their own instantiations, in the mid-size layout whatever the batch size)
+  // (heightfield terrain / self-collision: their own instantiations - self-collision in the mid-size layout whatever
+  // the batch size, the terrain alone on chip when the batch is small enough for that layout and mid-size otherwise)
   const bool special = env->terr.h || env->self_on;
-  const int layout = special ? 1 : env->layout;
+  const int layout = !special ? env->layout : (!env->self_on && env->layout == 0) ? 0 : 1;
   const int qblk = min(a.ntiles, layout == 2 ? env->grid_dense4 : layout == 1 ? env->grid_large : env->grid_small);
   const int md = env->cfg.mode;
   // K8: whole-batch steps of more than one wave run on envs grouped by cost
@@ -1365,6 +1367,7 @@ static int do_step(ilrl_env* env, const float* action, float* obs, float* reward
     else if (env->self_on && md == 0) launch_step(step_kernel<0, SmemSelf, false, true>, qblk, sizeof(SmemSelf), st, a);
     else if (env->self_on && md == 1) launch_step(step_kernel<1, SmemSelf, false, true>, qblk, sizeof(SmemSelf), st, a);
     else if (env->self_on) launch_step(step_kernel<2, SmemSelf, false, true>, qblk, sizeof(SmemSelf), st, a);
+    else if (layout == 0) launch_step(step_kernel<0, SmemSmall, true>, qblk, sizeof(SmemSmall), st, a, true);
     else launch_step(step_kernel<0, SmemLarge, true>, qblk, sizeof(SmemLarge), st, a);
   } else if (env->layout == 2) {
     if (md == 0) launch_step(step_kernel<0, SmemDense4>, qblk, sizeof(SmemDense4), st, a, true);

@@ -493,6 +493,30 @@ def test_terrain_single_step_dynamics_matches_oracle(terrain):
     env.close(); env2.close()
 
 
+def test_terrain_layouts_agree(monkeypatch):
+    """The terrain instantiation exists in the on-chip layout (batches of one wave) and in the mid-size one: the same
+    batch stepped through either gives bit-identical results, auto-resets included."""
+    n = 512
+    data = _reference_terrain(7)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    acts = [(torch.rand(n, 17, device="cuda", generator=g) * 2 - 1) * (2.0 if t % 4 == 0 else 1.0) for t in range(40)]
+    outs = {}
+    for layout in ("small", "large"):
+        monkeypatch.setenv("ILRL_LAYOUT", layout)
+        env = BatchedHumanoidEnv(n, "low", clips=["motion08_03", "motion09_03"], clip_of_env=np.arange(n, dtype=np.int32) % 2,
+                                 auto_reset=True, seed=8)
+        env.set_heightfield(data)
+        env.reset()
+        rec = [tuple(x.clone() for x in env.step(a)) for a in acts]
+        rec.append(tuple(x.clone() for x in env.get_state()))
+        outs[layout] = rec
+        env.close()
+    assert int(sum(r[2].sum() for r in outs["small"][:-1])) > 0, "no episode ended: the auto-reset path went untested"
+    for x, y in zip(outs["small"], outs["large"]):
+        for u, v in zip(x, y):
+            assert torch.equal(u, v)
+
+
 def test_terrain_full_step_and_error_paths():
     """The fused step on a terrain (reward / obs / bookkeeping unchanged, physics on the heightfield) and the C ABI's
     argument checks."""

@@ -900,16 +900,19 @@ __device__ __forceinline__ void build_self_rows(const SM& sm, const Tables& T, i
   plane_space(n, dir[1], dir[2]);
   const int LA = T.sphL[ga], CA = T.sphC[ga], LB = T.sphL[gb], CB = T.sphC[gb];
   SV FA[3], FB[3], pfS[3], pfB0[3];   // pfS: force travelling down the spine, pfB0: force arriving at the base directly
-  float dd[3], zs[3][3], zl[2][3][4];
+  // (the whitened spine / limb entries go straight into the stored row, words 8..10 and 12..19: the walks below index
+  // them with run-time link numbers, and as register arrays they lived in local memory)
+  const int lab = (LA < 0 ? 15 : LA) | ((LB < 0 ? 15 : LB) << 8);
+  float dd[3];
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     FA[i].l = dir[i]; FA[i].a = cross(xa, dir[i]);
     FB[i].l = dir[i]; FB[i].a = cross(xb, dir[i]);
     pfS[i] = svzero(); pfB0[i] = svzero(); dd[i] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 3; k++) zs[i][k] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; k++) { zl[0][i][k] = 0.f; zl[1][i][k] = 0.f; }
+    float4* r4 = reinterpret_cast<float4*>(wrow + i * WRW);
+    r4[2] = make_float4(0.f, 0.f, 0.f, __int_as_float(lab));
+    r4[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+    r4[4] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   SV Vs[2];   // unconstrained new velocity of the two bodies
   Vs[0].a = mk(nub[0], nub[1], nub[2]); Vs[0].l = mk(nub[3], nub[4], nub[5]);
@@ -932,7 +935,7 @@ __device__ __forceinline__ void build_self_rows(const SM& sm, const Tables& T, i
 #pragma unroll
         for (int i = 0; i < 3; i++) {
           const float u = -sdot(S, pf[i]), z = u * sq;
-          zl[side][i][c - 3] = z;
+          wrow[i * WRW + 12 + 4 * side + (c - 3)] = z;
           dd[i] = fmaf(z, z, dd[i]);
           pf[i] = pf[i] + (u * di) * U;
         }
@@ -969,13 +972,12 @@ __device__ __forceinline__ void build_self_rows(const SM& sm, const Tables& T, i
 #pragma unroll
     for (int i = 0; i < 3; i++) {
       const float u = -sdot(S, pfS[i]), z = u * sq;
-      zs[i][c] = z;
+      wrow[i * WRW + 8 + c] = z;
       dd[i] = fmaf(z, z, dd[i]);
       pfS[i] = pfS[i] + (u * di) * U;
     }
   }
   const float* L0 = &sm.L0[0][e];
-  const int lab = (LA < 0 ? 15 : LA) | ((LB < 0 ? 15 : LB) << 8);
 #pragma unroll
   for (int i = 0; i < 3; i++) {
     float y[6];
@@ -989,9 +991,6 @@ __device__ __forceinline__ void build_self_rows(const SM& sm, const Tables& T, i
     float4* r4 = reinterpret_cast<float4*>(wrow + i * WRW);
     r4[0] = make_float4(y[0], y[1], y[2], y[3]);
     r4[1] = make_float4(y[4], y[5], (pos - rv) * dinv, dinv);
-    r4[2] = make_float4(zs[i][0], zs[i][1], zs[i][2], __int_as_float(lab));
-    r4[3] = make_float4(zl[0][i][0], zl[0][i][1], zl[0][i][2], zl[0][i][3]);
-    r4[4] = make_float4(zl[1][i][0], zl[1][i][1], zl[1][i][2], zl[1][i][3]);
     r4[5] = make_float4(0.f, 0.f, 0.f, 0.f);   // (word 23: the row's multiplier)
   }
 }

@@ -12,8 +12,10 @@ DEPS = [SRC, SRC_POLICY] + [os.path.join(HERE, "csrc", f) for f in ("ilrl_env.cu
 # -ftz / -prec-div=false / -prec-sqrt=false: flush denormals, 2-ulp division and square root without their slow-path
 # subroutines (+4..5 % throughput).  NOT --use_fast_math: sincosf / expf / atan2f keep full accuracy (the reward and
 # observation parity bar is 1e-5 relative; the whole GPU suite passes with these flags).
+# --register-usage-level=10 (ptxas spends more effort on keeping register use down): same results, +1.0..1.2 % at 65536
+# envs, no change at 4096 (profiles/r2_v7_ptxas_flags_ab.txt; level 0: -2 %; --allow-expensive-optimizations: same code).
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-ftz=true",
-              "-prec-div=false", "-prec-sqrt=false", "-Xcompiler", "-fPIC", "-shared"]
+              "-prec-div=false", "-prec-sqrt=false", "-Xptxas", "--register-usage-level=10", "-Xcompiler", "-fPIC", "-shared"]
 
 
 def stale():
